@@ -1,0 +1,174 @@
+/* spe_b200.h -- C ABI of libspe_b200.so: the sm_100a hot path of MingXiangL/SPE.
+ *
+ * The reference (pure Python/PyTorch) has no FFI layer; its boundary for this path is
+ * the Python module API of models/{cait,transformer,attention,matcher,conditional_detr,
+ * position_encoding}.py and util/box_ops.py.  The Python shells in spe_b200/models mirror that API
+ * and call ONLY the entry points below (ctypes).  Each entry point cites the
+ * reference call site(s) it replaces.
+ *
+ * Conventions
+ *   - every pointer is a BORROWED device pointer (caller allocates inputs, outputs, workspaces);
+ *   - `stream` is a cudaStream_t passed as void*; no entry point synchronises the host;
+ *   - return value 0 = ok, <0 = error; spe_last_error() returns a thread-local message;
+ *   - bf16 tensors are raw uint16 storage; "f32" = float; shapes are row-major unless stated;
+ *   - no CPU fallback exists: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef SPE_B200_H
+#define SPE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* spe_last_error(void);
+int spe_version(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t spe_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * tcgen05 GEMM:  C[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )
+ * bf16 operands staged by TMA (128B swizzle) into shared memory, fp32 accumulation in TMEM.
+ * Replaces every nn.Linear / torch.bmm / `@` on the path: cait.py:376,379,389,390 (qkv, QK^T, PV,
+ * proj), timm Mlp fc1/fc2, cait.py:115-133 (class attention), transformer.py:280-287,368-423
+ * (in/out projections, FFN), attention.py:345,372 (bmm), conditional_detr.py:103-110 (heads),
+ * and their backward (dgrad: B operand MN-major = the same weight; wgrad: both MN-major).
+ * ------------------------------------------------------------------------------------------- */
+enum { SPE_MAJOR_K = 0, SPE_MAJOR_MN = 1 };
+enum { SPE_DT_BF16 = 0, SPE_DT_F32 = 1 };
+enum { SPE_ACT_NONE = 0, SPE_ACT_RELU = 1, SPE_ACT_GELU = 2,
+       SPE_ACT_RELU_GRAD = 3,   /* out = v * (aux_in > 0)           */
+       SPE_ACT_GELU_GRAD = 4 }; /* out = v * gelu'(aux_in)          */
+
+typedef struct {
+    int M, N, K;
+    int batch1, batch2;               /* batch index b = b1 * batch2 + b2 (e.g. image x head)      */
+    const void* A; int a_major;       /* K-major: (m,k) at m*lda+k;  MN-major: (m,k) at k*lda+m    */
+    int64_t lda, a_sb1, a_sb2;        /* strides in elements; batch stride 0 (batch>1) = broadcast */
+    const void* B; int b_major;       /* K-major: (n,k) at n*ldb+k;  MN-major: (n,k) at k*ldb+n    */
+    int64_t ldb, b_sb1, b_sb2;
+    void* C; int c_dtype;             /* SPE_DT_BF16 / SPE_DT_F32                                  */
+    int64_t ldc, c_sb1, c_sb2;
+    float alpha;
+    const float* bias;                /* [N] or NULL : v = alpha*acc + bias[n]                     */
+    int act;                          /* SPE_ACT_*   : v = act(v)                                  */
+    const void* aux_in;               /* bf16 [M,N] (ld = ld_aux), for *_GRAD activations          */
+    void* aux_out;                    /* bf16 [M,N] (ld = ld_aux) or NULL: v after bias, BEFORE act */
+    int64_t ld_aux;
+    const float* gamma;               /* [N] or NULL : v = gamma[n]*v   (LayerScale, cait.py:414)  */
+    const float* residual;            /* f32 [M,N] (ld = ldr) or NULL : v += residual[m][n]        */
+    int64_t ldr, r_sb1, r_sb2;
+    int split, split_stride;          /* if split>0: dest column = (n/split)*split_stride + n%split */
+} spe_gemm_args;
+
+int spe_gemm(const spe_gemm_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise / elementwise kernels of the backbone + transformer
+ * ------------------------------------------------------------------------------------------- */
+/* LayerNorm over the last dim (cait.py:414-415 eps 1e-6; transformer.py:284,288,384,425,427 eps 1e-5).
+ * x f32 [rows,D] -> y_bf16 and/or y_f32 (either may be NULL); saves mean/rstd [rows]. */
+int spe_layernorm_fwd(const float* x, const float* w, const float* b, float eps, int64_t rows, int D,
+                      void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
+/* dx = (dres ? dres : 0) + LN'(dy) ; dy given as bf16 and/or f32 (summed); dw/db accumulated (+=) in f32 */
+int spe_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres, const float* x,
+                      const float* w, const float* mean, const float* rstd, int64_t rows, int D,
+                      float* dx, float* dw, float* db, void* stream);
+
+/* Talking-heads mix + softmax + mix (cait.py:381-386):
+ *   L[g] = sum_h Wl[g,h] S[h] + bl[g];  P = softmax_j(L);  A[g] = sum_h Ww[g,h] P[h] + bw[g]
+ * S f32 [B,H,Nq,ldS] (Nk valid columns) -> A bf16 same layout (ldA).  */
+int spe_talking_softmax_fwd(const float* S, void* A, const float* Wl, const float* bl, const float* Ww,
+                            const float* bw, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream);
+/* backward: dA bf16 -> dS bf16 (may alias dA); parameter grads accumulated (+=) */
+int spe_talking_softmax_bwd(const float* S, const void* dA, void* dS, const float* Wl, const float* bl,
+                            const float* Ww, const float* bw, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA,
+                            float* dWl, float* dbl, float* dWw, float* dbw, float* workspace, int64_t workspace_floats,
+                            void* stream);
+int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk);
+
+/* Plain softmax over keys with optional key-padding mask (attention.py:363-371, nn.MultiheadAttention).
+ * S f32 [B,H,Nq,ldS] -> P bf16 [B,H,Nq,ldP]; mask u8 [B,Nk] (1 = padded -> -inf) or NULL.
+ * If pmean != NULL also writes the head-mean of P, f32 [B,Nq,Nk] (cait.py:658-667 cams). */
+int spe_softmax_fwd(const float* S, void* P, const uint8_t* mask, int B, int H, int Nq, int Nk, int64_t ldS,
+                    int64_t ldP, float* pmean, void* stream);
+/* dS = P * (dP - sum_j P dP), bf16 in / bf16 out (dS may alias dP) */
+int spe_softmax_bwd(const void* P, const void* dP, void* dS, int B, int H, int Nq, int Nk, int64_t ldP, void* stream);
+
+/* LayerScale branch backward (cait.py:414-415: x + gamma * y):
+ * dy_bf16 = gamma * dout ; dgamma += sum_rows dout*y ; dbias += sum_rows dy  */
+int spe_layerscale_bwd(const float* dout, const void* y_bf16, const float* gamma, int64_t rows, int D,
+                       void* dy_bf16, float* dgamma, float* dbias, void* stream);
+/* column sums of a bf16 [rows, N] (ld) matrix, accumulated into out f32 [N] (bias gradients) */
+int spe_colsum_bf16(const void* x, int64_t rows, int N, int64_t ld, float* out, void* stream);
+/* y_bf16 = (a*x + b*y) with f32 inputs (y may be NULL); also optional f32 output */
+int spe_axpby_cast(const float* x, const float* y, float a, float b, int64_t n, void* out_bf16, float* out_f32,
+                   void* stream);
+int spe_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+/* ReLU backward for an activation fused into a GEMM epilogue: out = dout * (h > 0), all bf16 (transformer.py:21-33 MLP) */
+int spe_relu_bwd_bf16(const void* dout, const void* h, void* out, int64_t n, void* stream);
+/* out[i] += x_bf16[i] (f32 accumulate) */
+int spe_add_bf16_into_f32(const void* x, float* out, int64_t n, void* stream);
+
+/* Patch embedding im2col (cait.py:527, Conv2d k=s=16): img f32 [B,3,H,W] -> bf16 [B*h*w, 3*p*p] */
+int spe_im2col_patch(const float* img, int B, int H, int W, int p, void* out_bf16, void* stream);
+/* col2im is not needed (images carry no gradient). */
+
+/* Bicubic resize (align_corners=False, A=-0.75) of pos_embed (cait.py:588-613):
+ * src f32 [sh*sw, D] token-major -> dst f32 [dh*dw, D]; bwd scatters dst-grad into src-grad (+=). */
+int spe_bicubic_tokens_fwd(const float* src, int sh, int sw, int D, float* dst, int dh, int dw, void* stream);
+int spe_bicubic_tokens_bwd(const float* ddst, int dh, int dw, int D, float* dsrc, int sh, int sw, void* stream);
+
+/* PositionEmbeddingSine(normalize=True) (position_encoding.py:37-57): mask u8 [B,h,w] -> pos f32 [B,h*w,D] */
+int spe_sine_pos_2d(const uint8_t* mask, int B, int h, int w, int D, float* pos, void* pos_bf16, void* stream);
+/* gen_sineembed_for_position (transformer.py:35-49, /128 exponent): ref f32 [n,2] -> emb f32 [n,D];
+ * bwd: dref[n,2] = sum_c demb * d emb/d ref */
+int spe_query_sine_fwd(const float* ref, int64_t n, int D, float* emb, void* stream);
+int spe_query_sine_bwd(const float* ref, const float* demb, int64_t n, int D, float* dref, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Matcher (models/matcher.py:41-87) -- cost matrix + batched rectangular LSAP on the GPU
+ * ------------------------------------------------------------------------------------------- */
+/* Block-diagonal cost only: for image b, cost[b][q][g], g < G_b = gt_off[b+1]-gt_off[b].
+ * logits f32 [B,Q,C], boxes f32 [B,Q,4] cxcywh, gt_labels i32 [sumG], gt_boxes f32 [sumG,4],
+ * gt_off i32 [B+1]; cost f32 [B,Q,ldc] (ldc >= max G_b).  fp32, reference op order, no FMA contraction. */
+int spe_match_cost(const float* logits, const float* boxes, const int32_t* gt_labels, const float* gt_boxes,
+                   const int32_t* gt_off, int B, int Q, int C, float w_class, float w_bbox, float w_giou,
+                   float* cost, int64_t ldc, void* stream);
+/* scipy.optimize.linear_sum_assignment (matcher.py:86) for B independent problems: cost f32 [B,nr,ldc],
+ * problem b uses the first nc[b] columns (nc = NULL -> all ldc).  Output query_to_col i32 [B,nr]
+ * (-1 = unassigned row; when nr <= nc[b] every row is assigned).  Identical indices to scipy incl. ties:
+ * rows sorted ascending with their columns == scipy's (row_ind, col_ind).
+ * workspace: spe_lsap_workspace_bytes(B, nr, max_nc) bytes. */
+int64_t spe_lsap_workspace_bytes(int B, int nr, int max_nc);
+int spe_lsap_batched(const float* cost, int B, int nr, int64_t ldc, const int32_t* nc, int max_nc,
+                     int32_t* row_to_col, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Set criterion (models/conditional_detr.py:237-319, 468-494, 504-561)
+ * ------------------------------------------------------------------------------------------- */
+/* Focal classification loss + gradient + class_error + cardinality, from the dense assignment.
+ *   logits f32 [B,Q,C]; row_to_gt i32 [B,Q] (-1 none); gt_labels i32[sumG]; gt_off i32[B+1];
+ *   gt_scores f32[sumG] or NULL (SetCriterionRefine weights :523-529)
+ *   inv_num_boxes: device f32 scalar (1/num_boxes, conditional_detr.py:436-440)
+ * outputs: out[0]=loss_ce, out[1]=class_error, out[2]=cardinality_error (f32[3]);
+ *          dlogits f32 [B,Q,C] = d loss_ce / d logits (may be NULL). */
+int spe_focal_loss(const float* logits, const int32_t* row_to_gt, const int32_t* gt_labels, const int32_t* gt_off,
+                   const float* gt_scores, const float* inv_num_boxes, int B, int Q, int C, float alpha, float gamma,
+                   float* out, float* dlogits, void* stream);
+/* L1 + GIoU on matched pairs (diag only; conditional_detr.py:300-319 / :540-561).
+ * out[0]=loss_bbox, out[1]=loss_giou; dboxes f32 [B,Q,4] receives w_l1*dL1 + w_giou*dGIoU?  No: two planes
+ * dboxes_l1 and dboxes_giou (each [B,Q,4], zero on unmatched rows; may be NULL). */
+int spe_box_loss(const float* boxes, const int32_t* row_to_gt, const float* gt_boxes, const int32_t* gt_off,
+                 const float* gt_scores, const float* inv_num_boxes, int B, int Q,
+                 float* out, float* dboxes_l1, float* dboxes_giou, void* stream);
+/* Multi-label BCE-with-logits mean (conditional_detr.py:225-235): x f32 [n], y f32 [n] -> out[0]; dx = d/dx */
+int spe_bce_logits(const float* x, const float* y, int64_t n, float* out, float* dx, void* stream);
+
+/* Pairwise IoU / GIoU (util/box_ops.py:33-74): a f32 [N,4], b f32 [M,4] xyxy -> iou/giou/union f32 [N,M] */
+int spe_box_iou_pairwise(const float* a, int N, const float* b, int M, float* iou, float* uni, float* giou, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPE_B200_H */

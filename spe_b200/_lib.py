@@ -1,0 +1,100 @@
+"""ctypes binding of libspe_b200.so (the C ABI declared in include/spe_b200.h).
+
+There is no fallback: if the shared library is missing the import of any compute op raises.  Build it
+with ``python -m spe_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libspe_b200.so")
+_lib = None
+
+c_p = C.c_void_p
+c_i = C.c_int
+c_l = C.c_int64
+c_f = C.c_float
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", c_i), ("N", c_i), ("K", c_i), ("batch1", c_i), ("batch2", c_i),
+        ("A", c_p), ("a_major", c_i), ("lda", c_l), ("a_sb1", c_l), ("a_sb2", c_l),
+        ("B", c_p), ("b_major", c_i), ("ldb", c_l), ("b_sb1", c_l), ("b_sb2", c_l),
+        ("C", c_p), ("c_dtype", c_i), ("ldc", c_l), ("c_sb1", c_l), ("c_sb2", c_l),
+        ("alpha", c_f), ("bias", c_p), ("act", c_i), ("aux_in", c_p), ("aux_out", c_p), ("ld_aux", c_l),
+        ("gamma", c_p), ("residual", c_p), ("ldr", c_l), ("r_sb1", c_l), ("r_sb2", c_l),
+        ("split", c_i), ("split_stride", c_i),
+    ]
+
+
+_SIGS = {
+    "spe_version": (c_i, []),
+    "spe_launch_count": (c_l, []),
+    "spe_gemm": (c_i, [C.POINTER(GemmArgs), c_p]),
+    "spe_layernorm_fwd": (c_i, [c_p, c_p, c_p, c_f, c_l, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "spe_layernorm_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
+    "spe_talking_softmax_fwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p]),
+    "spe_talking_softmax_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p, c_p, c_p,
+                                      c_p, c_l, c_p]),
+    "spe_talking_softmax_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i]),
+    "spe_softmax_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p]),
+    "spe_softmax_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_p]),
+    "spe_layerscale_bwd": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
+    "spe_colsum_bf16": (c_i, [c_p, c_l, c_i, c_l, c_p, c_p]),
+    "spe_axpby_cast": (c_i, [c_p, c_p, c_f, c_f, c_l, c_p, c_p, c_p]),
+    "spe_cast_bf16_to_f32": (c_i, [c_p, c_p, c_l, c_p]),
+    "spe_add_bf16_into_f32": (c_i, [c_p, c_p, c_l, c_p]),
+    "spe_relu_bwd_bf16": (c_i, [c_p, c_p, c_p, c_l, c_p]),
+    "spe_im2col_patch": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "spe_bicubic_tokens_fwd": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
+    "spe_bicubic_tokens_bwd": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
+    "spe_sine_pos_2d": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "spe_query_sine_fwd": (c_i, [c_p, c_l, c_i, c_p, c_p]),
+    "spe_query_sine_bwd": (c_i, [c_p, c_p, c_l, c_i, c_p, c_p]),
+    "spe_match_cost": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_l, c_p]),
+    "spe_lsap_workspace_bytes": (c_l, [c_i, c_i, c_i]),
+    "spe_lsap_batched": (c_i, [c_p, c_i, c_i, c_l, c_p, c_i, c_p, c_p, c_p]),
+    "spe_focal_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
+    "spe_box_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "spe_bce_logits": (c_i, [c_p, c_p, c_l, c_p, c_p, c_p]),
+    "spe_box_iou_pairwise": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
+}
+EXPORTS = sorted(list(_SIGS) + ["spe_last_error"])
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises if the native library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError("spe_b200: native library %s is missing -- run `python -m spe_b200.build`; "
+                               "there is no CPU/PyTorch fallback" % SO_PATH)
+        L = C.CDLL(SO_PATH)
+        L.spe_last_error.restype = C.c_char_p
+        L.spe_last_error.argtypes = []
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libspe_b200: " + lib().spe_last_error().decode())
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def launch_count():
+    return int(lib().spe_launch_count())

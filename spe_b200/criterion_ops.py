@@ -1,0 +1,169 @@
+"""Device-side matcher + set-criterion plumbing over the C ABI (spe_match_cost, spe_lsap_batched,
+spe_focal_loss, spe_box_loss, spe_bce_logits).  Ragged targets are packed once per step into
+(labels, boxes, offsets) arrays on the device; the assignment stays on the device as a
+dense query->gt map, so the criterion needs no host synchronisation.  Index lists in the reference's
+format (CPU int64 pairs, matcher.py:87) are produced only on request (HungarianMatcher.forward)."""
+import torch
+
+from ._lib import check, lib, ptr, stream
+
+
+class PackedTargets:
+    """labels i32 [sumG], boxes f32 [sumG,4], offsets i32 [B+1], optional scores f32 [sumG] (all on device)."""
+
+    def __init__(self, targets, device):
+        sizes = [int(t["labels"].shape[0]) for t in targets]
+        self.sizes = sizes
+        self.B = len(targets)
+        self.total = sum(sizes)
+        self.max_g = max(sizes) if sizes else 0
+        off = [0]
+        for s in sizes:
+            off.append(off[-1] + s)
+        pin = torch.cuda.is_available()
+        self.offsets_host = torch.tensor(off, dtype=torch.int32)
+        self.counts_host = torch.tensor(sizes, dtype=torch.int32)
+        if self.total > 0:
+            labels = torch.cat([t["labels"].reshape(-1) for t in targets]).to(torch.int32)
+            boxes = torch.cat([t["boxes"].reshape(-1, 4) for t in targets]).to(torch.float32)
+        else:
+            labels = torch.zeros(1, dtype=torch.int32)
+            boxes = torch.zeros(1, 4, dtype=torch.float32)
+        self.labels = labels.to(device, non_blocking=True).contiguous()
+        self.boxes = boxes.to(device, non_blocking=True).contiguous()
+        self.offsets = self.offsets_host.to(device, non_blocking=True)
+        self.counts = self.counts_host.to(device, non_blocking=True)
+        self.scores = None
+        if targets and all("scores" in t for t in targets) and self.total > 0:
+            self.scores = torch.cat([t["scores"].reshape(-1) for t in targets]).to(torch.float32).to(device, non_blocking=True).contiguous()
+        self.device = device
+        self._inv_num_boxes = None
+
+    def inv_num_boxes(self):
+        """1 / clamp(all_reduce(num_boxes)/world, 1) as a device scalar (conditional_detr.py:436-440), no .item()."""
+        if self._inv_num_boxes is None:
+            nb = torch.tensor([float(self.total)], dtype=torch.float32).to(self.device, non_blocking=True)
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                torch.distributed.all_reduce(nb)
+                nb = nb / torch.distributed.get_world_size()
+            self._inv_num_boxes = 1.0 / torch.clamp(nb, min=1.0)
+        return self._inv_num_boxes
+
+
+def pack_targets(targets, device):
+    return PackedTargets(targets, device)
+
+
+def match_cost(logits, boxes, T, weights):
+    """cost f32 [B,Q,ld] (block-diagonal: image b uses its own G_b columns), matcher.py:62-82."""
+    if not logits.is_cuda:
+        raise RuntimeError("spe_b200 matcher needs CUDA tensors (no CPU fallback exists)")
+    B, Q, C = logits.shape
+    ld = max(T.max_g, 1)
+    cost = torch.empty((B, Q, ld), dtype=torch.float32, device=logits.device)
+    w_class, w_bbox, w_giou = weights
+    check(lib().spe_match_cost(ptr(logits.detach().float().contiguous()), ptr(boxes.detach().float().contiguous()), ptr(T.labels), ptr(T.boxes),
+                               ptr(T.offsets), B, Q, C, float(w_class), float(w_bbox), float(w_giou), ptr(cost), ld, stream()))
+    return cost
+
+
+def lsap_raw(cost, ncols):
+    """cost f32 [B,nr,ld]; ncols i32 [B] device or None -> row_to_col i32 [B,nr]."""
+    B, nr, ld = cost.shape
+    out = torch.empty((B, nr), dtype=torch.int32, device=cost.device)
+    check(lib().spe_lsap_batched(ptr(cost), B, nr, ld, ptr(ncols), ld, ptr(out), 0, stream()))
+    return out
+
+
+def lsap(cost, T):
+    if T.max_g == 0:
+        return torch.full(cost.shape[:2], -1, dtype=torch.int32, device=cost.device)
+    return lsap_raw(cost, T.counts)
+
+
+def match(logits, boxes, T, weights):
+    """dense query->gt assignment i32 [B,Q] (-1 = unmatched), on device."""
+    return lsap(match_cost(logits, boxes, T, weights), T)
+
+
+def indices_from_dense(r2g_cpu):
+    """reference format: list of (idx_pred int64, idx_gt int64), predictions ascending (= scipy's order, App. C)."""
+    out = []
+    for row in r2g_cpu:
+        i = torch.nonzero(row >= 0).flatten()
+        out.append((i.to(torch.int64), row[i].to(torch.int64)))
+    return out
+
+
+class FocalLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, r2g, T, alpha, gamma, use_scores):
+        B, Q, C = logits.shape
+        lg = logits.contiguous()
+        out = torch.empty(3, dtype=torch.float32, device=logits.device)
+        dl = torch.empty_like(lg)
+        sc = T.scores if use_scores else None
+        check(lib().spe_focal_loss(ptr(lg), ptr(r2g), ptr(T.labels), ptr(T.offsets), ptr(sc), ptr(T.inv_num_boxes()), B, Q, C, float(alpha),
+                                   float(gamma), ptr(out), ptr(dl), stream()))
+        ctx.save_for_backward(dl)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g[0], None, None, None, None, None
+
+
+class BoxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, boxes, r2g, T, use_scores):
+        B, Q, _ = boxes.shape
+        bx = boxes.contiguous()
+        out = torch.empty(2, dtype=torch.float32, device=boxes.device)
+        d1, d2 = torch.empty_like(bx), torch.empty_like(bx)
+        sc = T.scores if use_scores else None
+        check(lib().spe_box_loss(ptr(bx), ptr(r2g), ptr(T.boxes), ptr(T.offsets), ptr(sc), ptr(T.inv_num_boxes()), B, Q, ptr(out), ptr(d1), ptr(d2),
+                                 stream()))
+        ctx.save_for_backward(d1, d2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        d1, d2 = ctx.saved_tensors
+        return d1 * g[0] + d2 * g[1], None, None, None
+
+
+class BceLogitsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        xc = x.contiguous()
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(xc)
+        check(lib().spe_bce_logits(ptr(xc), ptr(y.contiguous()), xc.numel(), ptr(out), ptr(dx), stream()))
+        ctx.save_for_backward(dx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g[0], None
+
+
+def set_losses(logits, boxes, T, match_weights, alpha, gamma, refine=False, losses=("labels", "boxes", "cardinality"), log=True, r2g=None):
+    """One decoder level: match + labels/boxes/cardinality losses; returns dict of 0-dim tensors (+ '_r2g')."""
+    if r2g is None:
+        r2g = match(logits, boxes, T, match_weights)
+    res = {"_r2g": r2g}
+    if "labels" in losses or "cardinality" in losses:
+        f = FocalLossFn.apply(logits.float(), r2g, T, alpha, gamma, refine)
+        if "labels" in losses:
+            res["loss_ce"] = f[0]
+            if log:
+                res["class_error"] = f[1].detach()
+        if "cardinality" in losses:
+            res["cardinality_error"] = f[2].detach()
+    if "boxes" in losses:
+        b = BoxLossFn.apply(boxes.float(), r2g, T, refine)
+        res["loss_bbox"] = b[0]
+        res["loss_giou"] = b[1]
+    return res

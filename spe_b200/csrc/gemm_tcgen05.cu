@@ -1,0 +1,412 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C = epilogue(alpha * A * B^T)
+//
+//   * operands bf16, staged global->shared by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a
+//     STAGES-deep mbarrier ring; both K-major and MN-major operand layouts are consumed directly
+//     (UMMA descriptor major bits), so dgrad (B = weight as MN-major) and wgrad (both MN-major)
+//     need no transposed copies;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) with the
+//     fp32 accumulator in TMEM; tcgen05.commit releases smem stages and signals the epilogue;
+//   * 4 warps read the accumulator with tcgen05.ld (32x32b), apply bias / activation / LayerScale /
+//     residual / head-interleave and store bf16 or fp32;
+//   * <=98 KB smem and BN TMEM columns per CTA -> 2 CTAs per SM, so one CTA's epilogue overlaps the
+//     other's main loop.
+//
+// Reference call sites replaced: see include/spe_b200.h (spe_gemm).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr uint32_t CHUNK_BYTES = 64 * BK * 2;   // one 64(mn) x 64(k) MN-major TMA box
+
+struct EpiParams {
+    void* C; int c_dtype; long long ldc, c_sb1, c_sb2;
+    float alpha; const float* bias; int act;
+    const uint16_t* aux_in; uint16_t* aux_out; long long ld_aux;
+    const float* gamma; const float* residual; long long ldr, r_sb1, r_sb2;
+    int split, split_stride;
+    int M, N, K, batch2;
+    int vec_ok;
+    int a_m1, a_m2, b_m1, b_m2;   // 0 = operand broadcast over that batch dim (stride 0), else 1
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B, version 1 (sm_100).  lbo/sbo in bytes.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;       // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TMEM_LD_32x32b_X32(taddr, r)                                                                         \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
+        : "r"(taddr))
+
+__device__ __forceinline__ float apply_act(float v, int act, float aux) {
+    switch (act) {
+        case SPE_ACT_RELU: return fmaxf(v, 0.f);
+        case SPE_ACT_GELU: return gelu_erf(v);
+        case SPE_ACT_RELU_GRAD: return aux > 0.f ? v : 0.f;
+        case SPE_ACT_GELU_GRAD: return v * gelu_erf_grad(aux);
+        default: return v;
+    }
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, const EpiParams ep) {
+    constexpr uint32_t A_BYTES = BM * BK * 2;
+    constexpr uint32_t B_BYTES = BN * BK * 2;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int b1 = blockIdx.z / ep.batch2, b2 = blockIdx.z % ep.batch2;
+    const int num_kb = (ep.K + BK - 1) / BK;
+
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const uint32_t fb = full0 + 8 * s;
+                mbar_expect_tx(fb, A_BYTES + B_BYTES);
+                const uint32_t a_dst = smem_u32(sA + s * A_BYTES), b_dst = smem_u32(sB + s * B_BYTES);
+                if constexpr (!A_MN) {
+                    tma_load_4d(a_dst, &tmA, fb, kb * BK, m0, b2 * ep.a_m2, b1 * ep.a_m1);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + c * 64, kb * BK, b2 * ep.a_m2, b1 * ep.a_m1);
+                }
+                if constexpr (!B_MN) {
+                    tma_load_4d(b_dst, &tmB, fb, kb * BK, n0, b2 * ep.b_m2, b1 * ep.b_m1);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + c * 64, kb * BK, b2 * ep.b_m2, b1 * ep.b_m1);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // K-major: 16 k-elements = 32 B inside the 128B swizzle row; SBO = 8 rows * 128 B.
+                    // MN-major: 16 k-rows = 2 groups of 8 rows (SBO = 1024 B); LBO = next 64-wide MN chunk.
+                    const uint64_t ad = A_MN ? umma_desc(a_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(a_base + k * 32, 0, 1024);
+                    const uint64_t bd = B_MN ? umma_desc(b_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(b_base + k * 32, 0, 1024);
+                    umma_f16(tmem_base, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty0 + 8 * s);   // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tfull);                // accumulator complete
+        }
+        __syncwarp();
+    }
+
+    // ---------------- epilogue: all 4 warps, warp w owns TMEM lanes [32w, 32w+32) ----------------
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const int m = m0 + warp * 32 + lane;
+    const bool row_ok = m < ep.M;
+    const long long boff_c = (long long)b1 * ep.c_sb1 + (long long)b2 * ep.c_sb2;
+    const long long boff_r = (long long)b1 * ep.r_sb1 + (long long)b2 * ep.r_sb2;
+    float* Cf = reinterpret_cast<float*>(ep.C) + boff_c + (long long)m * ep.ldc;
+    uint16_t* Cb = reinterpret_cast<uint16_t*>(ep.C) + boff_c + (long long)m * ep.ldc;
+    const float* Rr = ep.residual ? ep.residual + boff_r + (long long)m * ep.ldr : nullptr;
+    const uint16_t* auxi = ep.aux_in ? ep.aux_in + (long long)m * ep.ld_aux : nullptr;
+    uint16_t* auxo = ep.aux_out ? ep.aux_out + (long long)m * ep.ld_aux : nullptr;
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= ep.N) break;                    // uniform across the CTA
+        uint32_t r[32];
+        TMEM_LD_32x32b_X32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!row_ok) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int n = n0 + c0 + g * 8;
+            if (n >= ep.N) break;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * ep.alpha;
+            const bool full = (n + 8 <= ep.N) && ep.vec_ok;
+            const int dn = ep.split > 0 ? (n / ep.split) * ep.split_stride + (n % ep.split) : n;
+            if (full) {
+                if (ep.bias) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+                    const float4 b1v = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                    v[4] += b1v.x; v[5] += b1v.y; v[6] += b1v.z; v[7] += b1v.w;
+                }
+                if (auxo) {
+                    uint4 o;
+                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(auxo + n) = o;
+                }
+                if (ep.act != SPE_ACT_NONE) {
+                    float ax[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    if (auxi) {
+                        const uint4 a = __ldg(reinterpret_cast<const uint4*>(auxi + n));
+                        float2 t;
+                        t = unpack_bf16x2(a.x); ax[0] = t.x; ax[1] = t.y;
+                        t = unpack_bf16x2(a.y); ax[2] = t.x; ax[3] = t.y;
+                        t = unpack_bf16x2(a.z); ax[4] = t.x; ax[5] = t.y;
+                        t = unpack_bf16x2(a.w); ax[6] = t.x; ax[7] = t.y;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act, ax[j]);
+                }
+                if (ep.gamma) {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
+                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
+                    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+                    v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+                }
+                if (Rr) {
+                    const float4 r0 = *reinterpret_cast<const float4*>(Rr + n);
+                    const float4 r1 = *reinterpret_cast<const float4*>(Rr + n + 4);
+                    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+                    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                }
+                if (ep.c_dtype == SPE_DT_F32) {
+                    *reinterpret_cast<float4*>(Cf + dn) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(Cf + dn + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+                    uint4 o;
+                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(Cb + dn) = o;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int nj = n + j;
+                    if (nj >= ep.N) break;
+                    float x = v[j];
+                    if (ep.bias) x += __ldg(ep.bias + nj);
+                    if (auxo) auxo[nj] = f_to_bf16(x);
+                    if (ep.act != SPE_ACT_NONE) x = apply_act(x, ep.act, auxi ? bf16_to_f(auxi[nj]) : 0.f);
+                    if (ep.gamma) x *= __ldg(ep.gamma + nj);
+                    if (Rr) x += Rr[nj];
+                    const int dj = ep.split > 0 ? (nj / ep.split) * ep.split_stride + (nj % ep.split) : nj;
+                    if (ep.c_dtype == SPE_DT_F32) Cf[dj] = x; else Cb[dj] = f_to_bf16(x);
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+int make_tmap(CUtensorMap* tm, const void* ptr, int major, int rows, int K, int64_t ld, int64_t sb1, int64_t sb2, int batch1,
+              int batch2, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    SPE_CHECK(enc, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    SPE_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm operand pointer must be 16-byte aligned");
+    SPE_CHECK(ld % 8 == 0, "gemm operand leading dimension (%lld) must be a multiple of 8 elements", (long long)ld);
+    SPE_CHECK((batch1 == 1 || sb1 % 8 == 0) && (batch2 == 1 || sb2 % 8 == 0), "gemm batch strides must be multiples of 8 elements");
+    cuuint64_t gdim[4];
+    cuuint64_t gstr[3];
+    cuuint32_t box[4];
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint64_t inner = (major == SPE_MAJOR_K) ? (cuuint64_t)K : (cuuint64_t)rows;
+    const cuuint64_t outer = (major == SPE_MAJOR_K) ? (cuuint64_t)rows : (cuuint64_t)K;
+    // a batch dim with stride 0 is a broadcast: describe it with extent 1 (the kernel passes coordinate 0)
+    const bool bc2 = batch2 > 1 && sb2 == 0, bc1 = batch1 > 1 && sb1 == 0;
+    gdim[0] = inner; gdim[1] = outer; gdim[2] = bc2 ? 1 : (cuuint64_t)batch2; gdim[3] = bc1 ? 1 : (cuuint64_t)batch1;
+    gstr[0] = (cuuint64_t)ld * 2;
+    gstr[1] = (batch2 > 1 && !bc2 ? (cuuint64_t)sb2 : (cuuint64_t)ld * outer) * 2;
+    gstr[2] = (batch1 > 1 && !bc1 ? (cuuint64_t)sb1 : (cuuint64_t)ld * outer) * 2;
+    box[0] = 64;
+    box[1] = (major == SPE_MAJOR_K) ? (cuuint32_t)box_rows : 64;
+    box[2] = 1; box[3] = 1;
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SPE_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu ld %lld", (int)r, (unsigned long long)inner,
+              (unsigned long long)outer, (long long)ld);
+    return 0;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& tA, const CUtensorMap& tB, const EpiParams& ep, int batch, cudaStream_t st) {
+    constexpr size_t SMEM = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool attr_done = false;
+    auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
+    if (!attr_done) {
+        SPE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_done = true;
+    }
+    dim3 grid((ep.N + BN - 1) / BN, (ep.M + BM - 1) / BM, batch);
+    kfn<<<grid, 128, SMEM, st>>>(tA, tB, ep);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+template <int BN, int STAGES>
+int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB, const EpiParams& ep, int batch, cudaStream_t st) {
+    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_K) return launch<BN, STAGES, false, false>(tA, tB, ep, batch, st);
+    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_MN) return launch<BN, STAGES, false, true>(tA, tB, ep, batch, st);
+    if (am == SPE_MAJOR_MN && bm == SPE_MAJOR_K) return launch<BN, STAGES, true, false>(tA, tB, ep, batch, st);
+    return launch<BN, STAGES, true, true>(tA, tB, ep, batch, st);
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_args* a, void* stream) {
+    SPE_CHECK(a && a->A && a->B && a->C, "spe_gemm: null argument");
+    SPE_CHECK(a->M > 0 && a->N > 0 && a->K > 0 && a->batch1 > 0 && a->batch2 > 0, "spe_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+    SPE_CHECK((long long)a->batch1 * a->batch2 <= 65535, "spe_gemm: batch too large");
+    SPE_CHECK(a->act == SPE_ACT_NONE || a->act == SPE_ACT_RELU || a->act == SPE_ACT_GELU || a->aux_in, "spe_gemm: *_GRAD activation needs aux_in");
+    const int BN = a->N <= 64 ? 64 : 128;
+    const int batch = a->batch1 * a->batch2;
+    CUtensorMap tA, tB;
+    if (make_tmap(&tA, a->A, a->a_major, a->M, a->K, a->lda, a->a_sb1, a->a_sb2, a->batch1, a->batch2, BM)) return -1;
+    if (make_tmap(&tB, a->B, a->b_major, a->N, a->K, a->ldb, a->b_sb1, a->b_sb2, a->batch1, a->batch2, BN)) return -1;
+
+    EpiParams ep;
+    ep.C = a->C; ep.c_dtype = a->c_dtype; ep.ldc = a->ldc; ep.c_sb1 = a->c_sb1; ep.c_sb2 = a->c_sb2;
+    ep.alpha = a->alpha; ep.bias = a->bias; ep.act = a->act;
+    ep.aux_in = reinterpret_cast<const uint16_t*>(a->aux_in); ep.aux_out = reinterpret_cast<uint16_t*>(a->aux_out); ep.ld_aux = a->ld_aux;
+    ep.gamma = a->gamma; ep.residual = a->residual; ep.ldr = a->ldr; ep.r_sb1 = a->r_sb1; ep.r_sb2 = a->r_sb2;
+    ep.split = a->split; ep.split_stride = a->split_stride;
+    ep.M = a->M; ep.N = a->N; ep.K = a->K; ep.batch2 = a->batch2;
+    ep.a_m1 = (a->batch1 > 1 && a->a_sb1 == 0) ? 0 : 1; ep.a_m2 = (a->batch2 > 1 && a->a_sb2 == 0) ? 0 : 1;
+    ep.b_m1 = (a->batch1 > 1 && a->b_sb1 == 0) ? 0 : 1; ep.b_m2 = (a->batch2 > 1 && a->b_sb2 == 0) ? 0 : 1;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const int celt = a->c_dtype == SPE_DT_F32 ? 4 : 8;      // elements per 16 B
+    bool vec = al16(a->C) && a->ldc % celt == 0 && a->c_sb1 % celt == 0 && a->c_sb2 % celt == 0;
+    if (a->bias) vec = vec && al16(a->bias);
+    if (a->gamma) vec = vec && al16(a->gamma);
+    if (a->residual) vec = vec && al16(a->residual) && a->ldr % 4 == 0 && a->r_sb1 % 4 == 0 && a->r_sb2 % 4 == 0;
+    if (a->aux_in) vec = vec && al16(a->aux_in) && a->ld_aux % 8 == 0;
+    if (a->aux_out) vec = vec && al16(a->aux_out) && a->ld_aux % 8 == 0;
+    if (a->split > 0) vec = vec && a->split % 8 == 0 && a->split_stride % 8 == 0;
+    ep.vec_ok = vec ? 1 : 0;
+
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, ep, batch, st);
+    return dispatch_major<128, 3>(a->a_major, a->b_major, tA, tB, ep, batch, st);
+}

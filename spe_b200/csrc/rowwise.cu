@@ -1,0 +1,887 @@
+// Row-wise / elementwise kernels of the backbone and transformer (HBM-bound: coalesced, vectorised,
+// grid sized in multiples of the SM count).  Reference call sites: include/spe_b200.h.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LN_MAXCH = 8;   // D <= 1024 (float4 per lane per 128-column chunk)
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                            float eps, long long rows, int D, uint16_t* __restrict__ y16, float* __restrict__ y32,
+                                                            float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+    const int lane = threadIdx.x & 31;
+    const long long row0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 5);
+    const int nch = (D + 127) / 128;
+    for (long long row = row0; row < rows; row += stride) {
+        const float* xr = x + row * D;
+        float4 v[LN_MAXCH];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN_MAXCH; ++k) {
+            const int c = k * 128 + lane * 4;
+            if (k < nch && c < D) {
+                v[k] = *reinterpret_cast<const float4*>(xr + c);
+                s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+            } else v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN_MAXCH; ++k) {
+            const int c = k * 128 + lane * 4;
+            if (k < nch && c < D) {
+                const float a0 = v[k].x - mean, a1 = v[k].y - mean, a2 = v[k].z - mean, a3 = v[k].w - mean;
+                q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+        if (lane == 0) { if (mean_o) mean_o[row] = mean; if (rstd_o) rstd_o[row] = rstd; }
+#pragma unroll
+        for (int k = 0; k < LN_MAXCH; ++k) {
+            const int c = k * 128 + lane * 4;
+            if (k < nch && c < D) {
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+                float4 o;
+                o.x = (v[k].x - mean) * rstd * ww.x + bb.x;
+                o.y = (v[k].y - mean) * rstd * ww.y + bb.y;
+                o.z = (v[k].z - mean) * rstd * ww.z + bb.z;
+                o.w = (v[k].w - mean) * rstd * ww.w + bb.w;
+                if (y32) *reinterpret_cast<float4*>(y32 + row * D + c) = o;
+                if (y16) *reinterpret_cast<uint2*>(y16 + row * D + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward: warp per row, per-lane column accumulators for dw/db, one atomic per column per CTA
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __restrict__ dy16, const float* __restrict__ dy32,
+                                                            const float* __restrict__ dres, const float* __restrict__ x,
+                                                            const float* __restrict__ w, const float* __restrict__ mean_i,
+                                                            const float* __restrict__ rstd_i, long long rows, int D, float* __restrict__ dx,
+                                                            float* __restrict__ dw, float* __restrict__ db) {
+    extern __shared__ float sm[];     // [2][D] per-CTA column sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nch = (D + 127) / 128;
+    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) sm[c] = 0.f;
+    __syncthreads();
+    float4 aw[LN_MAXCH], ab[LN_MAXCH];
+#pragma unroll
+    for (int k = 0; k < LN_MAXCH; ++k) { aw[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = aw[k]; }
+    for (long long row = (long long)blockIdx.x * nw + warp; row < rows; row += (long long)gridDim.x * nw) {
+        const float mean = mean_i[row], rstd = rstd_i[row];
+        float4 g[LN_MAXCH], xh[LN_MAXCH];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LN_MAXCH; ++k) {
+            const int c = k * 128 + lane * 4;
+            if (k < nch && c < D) {
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (dy32) d = *reinterpret_cast<const float4*>(dy32 + row * D + c);
+                if (dy16) {
+                    const uint2 p = *reinterpret_cast<const uint2*>(dy16 + row * D + c);
+                    const float2 a = unpack_bf16x2(p.x), bq = unpack_bf16x2(p.y);
+                    d.x += a.x; d.y += a.y; d.z += bq.x; d.w += bq.y;
+                }
+                const float4 xv = *reinterpret_cast<const float4*>(x + row * D + c);
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c));
+                xh[k] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+                g[k] = make_float4(d.x * ww.x, d.y * ww.y, d.z * ww.z, d.w * ww.w);
+                s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
+                s2 += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
+                aw[k].x += d.x * xh[k].x; aw[k].y += d.y * xh[k].y; aw[k].z += d.z * xh[k].z; aw[k].w += d.w * xh[k].w;
+                ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
+            }
+        }
+        const float c1 = warp_sum(s1) / (float)D, c2 = warp_sum(s2) / (float)D;
+#pragma unroll
+        for (int k = 0; k < LN_MAXCH; ++k) {
+            const int c = k * 128 + lane * 4;
+            if (k < nch && c < D) {
+                float4 o;
+                o.x = rstd * (g[k].x - c1 - xh[k].x * c2);
+                o.y = rstd * (g[k].y - c1 - xh[k].y * c2);
+                o.z = rstd * (g[k].z - c1 - xh[k].z * c2);
+                o.w = rstd * (g[k].w - c1 - xh[k].w * c2);
+                if (dres) {
+                    const float4 r = *reinterpret_cast<const float4*>(dres + row * D + c);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                *reinterpret_cast<float4*>(dx + row * D + c) = o;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LN_MAXCH; ++k) {
+        const int c = k * 128 + lane * 4;
+        if (k < nch && c < D) {
+            atomicAdd(&sm[c + 0], aw[k].x); atomicAdd(&sm[c + 1], aw[k].y); atomicAdd(&sm[c + 2], aw[k].z); atomicAdd(&sm[c + 3], aw[k].w);
+            atomicAdd(&sm[D + c + 0], ab[k].x); atomicAdd(&sm[D + c + 1], ab[k].y); atomicAdd(&sm[D + c + 2], ab[k].z); atomicAdd(&sm[D + c + 3], ab[k].w);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        if (dw) atomicAdd(dw + c, sm[c]);
+        if (db) atomicAdd(db + c, sm[D + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax over keys (optionally masked), fp32 in -> bf16 out; one CTA per (b,h,q) row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, uint16_t* __restrict__ P, const uint8_t* __restrict__ mask,
+                                                          int H, int Nq, int Nk, long long ldS, long long ldP, float* __restrict__ pmean) {
+    extern __shared__ float row[];
+    __shared__ float red[32];
+    const long long r = blockIdx.x;                  // (b*H + h)*Nq + q
+    const int q = (int)(r % Nq);
+    const int b = (int)(r / ((long long)H * Nq));
+    const float* s = S + r * ldS;
+    const uint8_t* mk = mask ? mask + (long long)b * Nk : nullptr;
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < Nk; j += blockDim.x) {
+        float v = s[j];
+        if (mk && mk[j]) v = -INFINITY;
+        row[j] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = block_max(mx, red);
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < Nk; j += blockDim.x) {
+        const float e = __expf(row[j] - mx);
+        row[j] = e;
+        sum += e;
+    }
+    sum = block_sum(sum, red);
+    const float inv = 1.f / sum;
+    uint16_t* p = P + r * ldP;
+    for (int j = threadIdx.x; j < Nk; j += blockDim.x) {
+        const float v = row[j] * inv;
+        p[j] = f_to_bf16(v);
+        if (pmean) atomicAdd(pmean + ((long long)b * Nq + q) * Nk + j, v / (float)H);
+    }
+    for (int j = Nk + threadIdx.x; j < ldP; j += blockDim.x) p[j] = 0;      // keep the padding columns clean
+}
+
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const uint16_t* __restrict__ P, const uint16_t* __restrict__ dP, uint16_t* __restrict__ dS,
+                                                          int Nk, long long ldP) {
+    extern __shared__ float row[];    // [2][Nk]
+    __shared__ float red[32];
+    const long long r = blockIdx.x;
+    const uint16_t* p = P + r * ldP;
+    const uint16_t* dp = dP + r * ldP;
+    float* pr = row;
+    float* dr = row + Nk;
+    float dot = 0.f;
+    for (int j = threadIdx.x; j < Nk; j += blockDim.x) {
+        const float a = bf16_to_f(p[j]), d = bf16_to_f(dp[j]);
+        pr[j] = a; dr[j] = d;
+        dot += a * d;
+    }
+    dot = block_sum(dot, red);
+    uint16_t* o = dS + r * ldP;
+    for (int j = threadIdx.x; j < Nk; j += blockDim.x) o[j] = f_to_bf16(pr[j] * (dr[j] - dot));
+    for (int j = Nk + threadIdx.x; j < ldP; j += blockDim.x) o[j] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// talking-heads mix -> softmax -> mix   (cait.py:381-386)
+//   one CTA per (b, q); the H x Nk slab of logits lives in shared memory; 2 adjacent keys per thread
+// ------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256) talking_fwd_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
+                                                          const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
+                                                          int Nq, int Nk, long long ldS, long long ldA) {
+    extern __shared__ float sm[];
+    float* L = sm;                                   // [H][Nkp]
+    const int Nkp = (Nk + 1) & ~1;
+    __shared__ float sWl[H * H], sWw[H * H], sbl[H], sbw[H];
+    __shared__ float redm[H][8], stat[H];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < H * H; i += 256) { sWl[i] = Wl[i]; sWw[i] = Ww[i]; }
+    if (tid < H) { sbl[tid] = bl[tid]; sbw[tid] = bw[tid]; }
+    __syncthreads();
+    const int b = blockIdx.x / Nq, q = blockIdx.x % Nq;
+    const float* Sb = S + ((long long)b * H * Nq + q) * ldS;          // head h at + h*Nq*ldS
+    uint16_t* Ab = A + ((long long)b * H * Nq + q) * ldA;
+    const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
+
+    float mx[H];
+#pragma unroll
+    for (int g = 0; g < H; ++g) mx[g] = -INFINITY;
+    for (int j = 2 * tid; j < Nk; j += 512) {
+        const bool two = (j + 1 < Nk);
+        float s0[H], s1[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            if (two) { const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j); s0[h] = t.x; s1[h] = t.y; }
+            else { s0[h] = Sb[h * hS + j]; s1[h] = -INFINITY; }
+        }
+#pragma unroll
+        for (int g = 0; g < H; ++g) {
+            float a0 = sbl[g], a1 = sbl[g];
+#pragma unroll
+            for (int h = 0; h < H; ++h) { const float wv = sWl[g * H + h]; a0 += wv * s0[h]; if (two) a1 += wv * s1[h]; }
+            if (!two) a1 = -INFINITY;
+            L[g * Nkp + j] = a0; L[g * Nkp + j + 1] = a1;
+            mx[g] = fmaxf(mx[g], fmaxf(a0, a1));
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < H; ++g) { const float m = warp_max(mx[g]); if (lane == 0) redm[g][warp] = m; }
+    __syncthreads();
+    if (tid < H) { float m = redm[tid][0]; for (int w2 = 1; w2 < 8; ++w2) m = fmaxf(m, redm[tid][w2]); stat[tid] = m; }
+    __syncthreads();
+    float sum[H];
+#pragma unroll
+    for (int g = 0; g < H; ++g) { mx[g] = stat[g]; sum[g] = 0.f; }
+    for (int j = 2 * tid; j < Nk; j += 512) {
+#pragma unroll
+        for (int g = 0; g < H; ++g) {
+            const float e0 = __expf(L[g * Nkp + j] - mx[g]), e1 = __expf(L[g * Nkp + j + 1] - mx[g]);   // exp(-inf)=0 for the pad
+            L[g * Nkp + j] = e0; L[g * Nkp + j + 1] = e1;
+            sum[g] += e0 + e1;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < H; ++g) { const float s = warp_sum(sum[g]); if (lane == 0) redm[g][warp] = s; }
+    __syncthreads();
+    if (tid < H) { float s = 0.f; for (int w2 = 0; w2 < 8; ++w2) s += redm[tid][w2]; stat[tid] = 1.f / s; }
+    __syncthreads();
+    float inv[H];
+#pragma unroll
+    for (int g = 0; g < H; ++g) inv[g] = stat[g];
+    for (int j = 2 * tid; j < Nk; j += 512) {
+        float p0[H], p1[H];
+#pragma unroll
+        for (int g = 0; g < H; ++g) { p0[g] = L[g * Nkp + j] * inv[g]; p1[g] = L[g * Nkp + j + 1] * inv[g]; }
+#pragma unroll
+        for (int o = 0; o < H; ++o) {
+            float a0 = sbw[o], a1 = sbw[o];
+#pragma unroll
+            for (int g = 0; g < H; ++g) { const float wv = sWw[o * H + g]; a0 += wv * p0[g]; a1 += wv * p1[g]; }
+            if (j + 1 < Nk) *reinterpret_cast<uint32_t*>(Ab + o * hA + j) = pack_bf16x2(a0, a1);
+            else Ab[o * hA + j] = f_to_bf16(a0);
+        }
+    }
+    // zero the padding columns [Nk, ldA) so K-tail TMA reads see zeros
+    for (int o = 0; o < H; ++o)
+        for (int j = Nk + tid; j < ldA; j += 256) Ab[o * hA + j] = 0;
+}
+
+// backward: dA (bf16) -> dS (bf16), parameter-gradient partials per CTA in `part` [gridDim.x][2*H*H + 2*H]
+template <int H>
+__global__ void __launch_bounds__(256, 1) talking_bwd_kernel(const float* __restrict__ S, const uint16_t* __restrict__ dA, uint16_t* __restrict__ dS,
+                                                             const float* __restrict__ Wl, const float* __restrict__ bl, const float* __restrict__ Ww,
+                                                             int rows_total, int Nq, int Nk, long long ldS, long long ldA, float* __restrict__ part) {
+    extern __shared__ float sm[];
+    const int Nkp = (Nk + 1) & ~1;
+    float* Ss = sm;                                   // [H][Nkp] raw logits
+    float* Ps = Ss + (size_t)H * Nkp;                 // [H][Nkp] L -> e -> P
+    float* Ds = Ps + (size_t)H * Nkp;                 // [H][Nkp] dP
+    __shared__ float sWl[H * H], sWw[H * H], sbl[H];
+    __shared__ float redm[H][8], stat[H];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < H * H; i += 256) { sWl[i] = Wl[i]; sWw[i] = Ww[i]; }
+    if (tid < H) sbl[tid] = bl[tid];
+    __syncthreads();
+    const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
+
+    float aWw[H][H], aWl[H][H], abw[H], abl[H];       // per-thread partial parameter gradients (persist over rows)
+#pragma unroll
+    for (int a = 0; a < H; ++a) { abw[a] = 0.f; abl[a] = 0.f;
+#pragma unroll
+        for (int c = 0; c < H; ++c) { aWw[a][c] = 0.f; aWl[a][c] = 0.f; } }
+
+    for (int rowi = blockIdx.x; rowi < rows_total; rowi += gridDim.x) {
+        const int b = rowi / Nq, q = rowi % Nq;
+        const float* Sb = S + ((long long)b * H * Nq + q) * ldS;
+        const uint16_t* dAb = dA + ((long long)b * H * Nq + q) * ldA;
+        uint16_t* dSb = dS + ((long long)b * H * Nq + q) * ldA;
+        float mx[H];
+#pragma unroll
+        for (int g = 0; g < H; ++g) mx[g] = -INFINITY;
+        // pass 1: S -> smem, L -> smem, running max
+        for (int j = 2 * tid; j < Nk; j += 512) {
+            const bool two = (j + 1 < Nk);
+            float s0[H], s1[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                if (two) { const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j); s0[h] = t.x; s1[h] = t.y; }
+                else { s0[h] = Sb[h * hS + j]; s1[h] = 0.f; }
+                Ss[h * Nkp + j] = s0[h]; Ss[h * Nkp + j + 1] = s1[h];
+            }
+#pragma unroll
+            for (int g = 0; g < H; ++g) {
+                float a0 = sbl[g], a1 = sbl[g];
+#pragma unroll
+                for (int h = 0; h < H; ++h) { const float wv = sWl[g * H + h]; a0 += wv * s0[h]; a1 += wv * s1[h]; }
+                if (!two) a1 = -INFINITY;
+                Ps[g * Nkp + j] = a0; Ps[g * Nkp + j + 1] = a1;
+                mx[g] = fmaxf(mx[g], fmaxf(a0, a1));
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < H; ++g) { const float m = warp_max(mx[g]); if (lane == 0) redm[g][warp] = m; }
+        __syncthreads();
+        if (tid < H) { float m = redm[tid][0]; for (int w2 = 1; w2 < 8; ++w2) m = fmaxf(m, redm[tid][w2]); stat[tid] = m; }
+        __syncthreads();
+        float sum[H];
+#pragma unroll
+        for (int g = 0; g < H; ++g) { mx[g] = stat[g]; sum[g] = 0.f; }
+        for (int j = 2 * tid; j < Nk; j += 512) {
+#pragma unroll
+            for (int g = 0; g < H; ++g) {
+                const float e0 = __expf(Ps[g * Nkp + j] - mx[g]), e1 = __expf(Ps[g * Nkp + j + 1] - mx[g]);
+                Ps[g * Nkp + j] = e0; Ps[g * Nkp + j + 1] = e1;
+                sum[g] += e0 + e1;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < H; ++g) { const float s = warp_sum(sum[g]); if (lane == 0) redm[g][warp] = s; }
+        __syncthreads();
+        if (tid < H) { float s = 0.f; for (int w2 = 0; w2 < 8; ++w2) s += redm[tid][w2]; stat[tid] = 1.f / s; }
+        __syncthreads();
+        // pass 3: P, dP = Ww^T dA, rho = sum_j P dP, dWw += dA (x) P, dbw += dA
+        float rho[H];
+#pragma unroll
+        for (int g = 0; g < H; ++g) { sum[g] = stat[g]; rho[g] = 0.f; }
+        for (int j = 2 * tid; j < Nk; j += 512) {
+            const bool two = (j + 1 < Nk);
+            float d0[H], d1[H], p0[H], p1[H];
+#pragma unroll
+            for (int o = 0; o < H; ++o) {
+                if (two) { const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + o * hA + j)); d0[o] = t.x; d1[o] = t.y; }
+                else { d0[o] = bf16_to_f(dAb[o * hA + j]); d1[o] = 0.f; }
+                abw[o] += d0[o] + d1[o];
+            }
+#pragma unroll
+            for (int g = 0; g < H; ++g) {
+                p0[g] = Ps[g * Nkp + j] * sum[g]; p1[g] = Ps[g * Nkp + j + 1] * sum[g];
+                Ps[g * Nkp + j] = p0[g]; Ps[g * Nkp + j + 1] = p1[g];
+                float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+                for (int o = 0; o < H; ++o) {
+                    const float wv = sWw[o * H + g];
+                    x0 += wv * d0[o]; x1 += wv * d1[o];
+                    aWw[o][g] += d0[o] * p0[g] + d1[o] * p1[g];
+                }
+                Ds[g * Nkp + j] = x0; Ds[g * Nkp + j + 1] = x1;
+                rho[g] += p0[g] * x0 + p1[g] * x1;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < H; ++g) { const float s = warp_sum(rho[g]); if (lane == 0) redm[g][warp] = s; }
+        __syncthreads();
+        if (tid < H) { float s = 0.f; for (int w2 = 0; w2 < 8; ++w2) s += redm[tid][w2]; stat[tid] = s; }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < H; ++g) rho[g] = stat[g];
+        // pass 4: dL = P (dP - rho); dS = Wl^T dL; dWl += dL (x) S; dbl += dL
+        for (int j = 2 * tid; j < Nk; j += 512) {
+            float l0[H], l1[H];
+#pragma unroll
+            for (int g = 0; g < H; ++g) {
+                l0[g] = Ps[g * Nkp + j] * (Ds[g * Nkp + j] - rho[g]);
+                l1[g] = Ps[g * Nkp + j + 1] * (Ds[g * Nkp + j + 1] - rho[g]);
+                abl[g] += l0[g] + l1[g];
+            }
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float s0 = Ss[h * Nkp + j], s1 = Ss[h * Nkp + j + 1];
+                float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+                for (int g = 0; g < H; ++g) {
+                    const float wv = sWl[g * H + h];
+                    x0 += wv * l0[g]; x1 += wv * l1[g];
+                    aWl[g][h] += l0[g] * s0 + l1[g] * s1;
+                }
+                if (j + 1 < Nk) *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = pack_bf16x2(x0, x1);
+                else dSb[h * hA + j] = f_to_bf16(x0);
+            }
+        }
+        for (int h = 0; h < H; ++h)
+            for (int j = Nk + tid; j < ldA; j += 256) dSb[h * hA + j] = 0;
+        __syncthreads();
+    }
+    // CTA reduction of the partials -> part[blockIdx.x][...]: layout dWl[H*H], dbl[H], dWw[H*H], dbw[H]
+    float* redbuf = sm;          // reuse: [8 warps][2*H*H+2*H]
+    constexpr int NP = 2 * H * H + 2 * H;
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < H; ++a) {
+#pragma unroll
+        for (int c = 0; c < H; ++c) {
+            const float v1 = warp_sum(aWl[a][c]), v2 = warp_sum(aWw[a][c]);
+            if (lane == 0) { redbuf[warp * NP + a * H + c] = v1; redbuf[warp * NP + H * H + H + a * H + c] = v2; }
+        }
+        const float v3 = warp_sum(abl[a]), v4 = warp_sum(abw[a]);
+        if (lane == 0) { redbuf[warp * NP + H * H + a] = v3; redbuf[warp * NP + 2 * H * H + H + a] = v4; }
+    }
+    __syncthreads();
+    for (int i = tid; i < NP; i += 256) {
+        float s = 0.f;
+        for (int w2 = 0; w2 < 8; ++w2) s += redbuf[w2 * NP + i];
+        part[(long long)blockIdx.x * NP + i] = s;
+    }
+}
+
+__global__ void talking_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int H, float* __restrict__ dWl, float* __restrict__ dbl,
+                                            float* __restrict__ dWw, float* __restrict__ dbw) {
+    const int NP = 2 * H * H + 2 * H;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NP) return;
+    float s = 0.f;
+    for (int k = 0; k < nblocks; ++k) s += part[(long long)k * NP + i];
+    if (i < H * H) dWl[i] += s;
+    else if (i < H * H + H) dbl[i - H * H] += s;
+    else if (i < 2 * H * H + H) dWw[i - H * H - H] += s;
+    else dbw[i - 2 * H * H - H] += s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerScale branch backward + column sums
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float* __restrict__ dout, const uint16_t* __restrict__ y, const float* __restrict__ gamma,
+                                                             long long rows, int D, uint16_t* __restrict__ dy, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbias) {
+    // block (32 x 8): x -> 4-column groups, y -> rows
+    __shared__ float4 rg[8][32], rb[8][32];
+    const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const bool ok = c < D;
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+    float4 gm = ag;
+    if (ok) gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows && ok; r += (long long)gridDim.y * 8) {
+        const float4 d = *reinterpret_cast<const float4*>(dout + r * D + c);
+        const uint2 yp = *reinterpret_cast<const uint2*>(y + r * D + c);
+        const float2 y0 = unpack_bf16x2(yp.x), y1 = unpack_bf16x2(yp.y);
+        const float4 o = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        *reinterpret_cast<uint2*>(dy + r * D + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        ag.x += d.x * y0.x; ag.y += d.y * y0.y; ag.z += d.z * y1.x; ag.w += d.w * y1.y;
+        ab.x += o.x; ab.y += o.y; ab.z += o.z; ab.w += o.w;
+    }
+    rg[threadIdx.y][threadIdx.x] = ag; rb[threadIdx.y][threadIdx.x] = ab;
+    __syncthreads();
+    if (threadIdx.y == 0 && ok) {
+        for (int k = 1; k < 8; ++k) {
+            const float4 a = rg[k][threadIdx.x], b2 = rb[k][threadIdx.x];
+            ag.x += a.x; ag.y += a.y; ag.z += a.z; ag.w += a.w;
+            ab.x += b2.x; ab.y += b2.y; ab.z += b2.z; ab.w += b2.w;
+        }
+        if (dgamma) { atomicAdd(dgamma + c, ag.x); atomicAdd(dgamma + c + 1, ag.y); atomicAdd(dgamma + c + 2, ag.z); atomicAdd(dgamma + c + 3, ag.w); }
+        if (dbias) { atomicAdd(dbias + c, ab.x); atomicAdd(dbias + c + 1, ab.y); atomicAdd(dbias + c + 2, ab.z); atomicAdd(dbias + c + 3, ab.w); }
+    }
+}
+
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const uint16_t* __restrict__ x, long long rows, int N, long long ld, float* __restrict__ out) {
+    __shared__ float2 red[8][32];
+    const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+    float2 acc = make_float2(0.f, 0.f);
+    if (c + 1 < N) {
+        for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+            const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
+            acc.x += v.x; acc.y += v.y;
+        }
+    } else if (c < N) {
+        for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) acc.x += bf16_to_f(x[r * ld + c]);
+    }
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        for (int k = 1; k < 8; ++k) { acc.x += red[k][threadIdx.x].x; acc.y += red[k][threadIdx.x].y; }
+        atomicAdd(out + c, acc.x);
+        if (c + 1 < N) atomicAdd(out + c + 1, acc.y);
+    }
+}
+
+__global__ void axpby_cast_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b, long long n, uint16_t* __restrict__ o16,
+                                  float* __restrict__ o32) {
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < n) {
+            float4 v = *reinterpret_cast<const float4*>(x + i);
+            v.x *= a; v.y *= a; v.z *= a; v.w *= a;
+            if (y) { const float4 u = *reinterpret_cast<const float4*>(y + i); v.x += b * u.x; v.y += b * u.y; v.z += b * u.z; v.w += b * u.w; }
+            if (o32) *reinterpret_cast<float4*>(o32 + i) = v;
+            if (o16) *reinterpret_cast<uint2*>(o16 + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        } else {
+            for (long long k = i; k < n; ++k) {
+                float v = a * x[k] + (y ? b * y[k] : 0.f);
+                if (o32) o32[k] = v;
+                if (o16) o16[k] = f_to_bf16(v);
+            }
+        }
+    }
+}
+
+__global__ void cast_bf16_f32_kernel(const uint16_t* __restrict__ x, float* __restrict__ y, long long n, int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = bf16_to_f(x[i]);
+        y[i] = accumulate ? y[i] + v : v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// patch im2col: img f32 [B,3,H,W] -> bf16 [B*h*w, 3*p*p], 4 pixels per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_patch_kernel(const float* __restrict__ img, int B, int Himg, int Wimg, int p, uint16_t* __restrict__ out) {
+    const int h = Himg / p, w = Wimg / p, Kc = 3 * p * p;
+    const long long total = (long long)B * h * w * Kc / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * 4;
+        const int k = (int)(e % Kc);
+        const long long tok = e / Kc;
+        const int px = (int)(tok % w), py = (int)((tok / w) % h), b = (int)(tok / ((long long)w * h));
+        const int c = k / (p * p), ky = (k / p) % p, kx = k % p;
+        const float* src = img + (((long long)b * 3 + c) * Himg + (py * p + ky)) * Wimg + px * p + kx;
+        const float4 v = *reinterpret_cast<const float4*>(src);
+        *reinterpret_cast<uint2*>(out + e) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bicubic (A = -0.75, align_corners = False), token-major
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_coeffs(float t, float* c) {
+    const float A = -0.75f;
+    float x = t + 1.f;  c[0] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+    x = t;              c[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    x = 1.f - t;        c[2] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    x = 2.f - t;        c[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+}
+
+template <bool BWD>
+__global__ void bicubic_tokens_kernel(const float* __restrict__ a, float* __restrict__ o, int sh, int sw, int dh, int dw, int D) {
+    // FWD: a = src [sh*sw,D], o = dst [dh*dw,D].   BWD: a = ddst, o = dsrc (atomic scatter)
+    const long long total = (long long)dh * dw * D;
+    const float scy = (float)sh / (float)dh, scx = (float)sw / (float)dw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % D);
+        const int ox = (int)((i / D) % dw), oy = (int)(i / ((long long)D * dw));
+        const float ry = scy * (oy + 0.5f) - 0.5f, rx = scx * (ox + 0.5f) - 0.5f;
+        const int iy = (int)floorf(ry), ix = (int)floorf(rx);
+        float cy[4], cx[4];
+        cubic_coeffs(ry - iy, cy);
+        cubic_coeffs(rx - ix, cx);
+        float acc = 0.f;
+        const float gin = BWD ? a[i] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int yy = min(max(iy - 1 + u, 0), sh - 1);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int xx = min(max(ix - 1 + v, 0), sw - 1);
+                if (BWD) atomicAdd(o + ((long long)yy * sw + xx) * D + c, gin * cy[u] * cx[v]);
+                else acc += a[((long long)yy * sw + xx) * D + c] * cy[u] * cx[v];
+            }
+        }
+        if (!BWD) o[i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sine position encodings
+// ------------------------------------------------------------------------------------------------
+__global__ void sine_pos_2d_kernel(const uint8_t* __restrict__ mask, int B, int h, int w, int D, float* __restrict__ pos, uint16_t* __restrict__ pos16) {
+    const int npf = D / 2;
+    const long long total = (long long)B * h * w * npf;
+    const float two_pi = 6.283185307179586f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i % npf);
+        const int x = (int)((i / npf) % w), y = (int)((i / ((long long)npf * w)) % h), b = (int)(i / ((long long)npf * w * h));
+        const uint8_t* m = mask + (long long)b * h * w;
+        float ye = 0.f, yt = 0.f, xe = 0.f, xt = 0.f;
+        for (int yy = 0; yy < h; ++yy) { const float nm = m[yy * w + x] ? 0.f : 1.f; yt += nm; if (yy <= y) ye += nm; }
+        for (int xx = 0; xx < w; ++xx) { const float nm = m[y * w + xx] ? 0.f : 1.f; xt += nm; if (xx <= x) xe += nm; }
+        ye = ye / (yt + 1e-6f) * two_pi;
+        xe = xe / (xt + 1e-6f) * two_pi;
+        const float dim_t = powf(10000.f, (float)(2 * (f / 2)) / (float)npf);
+        const float ay = ye / dim_t, ax = xe / dim_t;
+        const float vy = (f & 1) ? cosf(ay) : sinf(ay);
+        const float vx = (f & 1) ? cosf(ax) : sinf(ax);
+        const long long tok = ((long long)b * h + y) * w + x;
+        if (pos) { pos[tok * D + f] = vy; pos[tok * D + npf + f] = vx; }
+        if (pos16) { pos16[tok * D + f] = f_to_bf16(vy); pos16[tok * D + npf + f] = f_to_bf16(vx); }
+    }
+}
+
+template <bool BWD>
+__global__ void query_sine_kernel(const float* __restrict__ ref, const float* __restrict__ demb, long long n, int D, float* __restrict__ out) {
+    // FWD: out = emb [n,D].  BWD: out = dref [n,2], one warp per row
+    const int half = D / 2;
+    const float two_pi = 6.283185307179586f;
+    if (!BWD) {
+        const long long total = n * half;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int f = (int)(i % half);
+            const long long r = i / half;
+            const float dim_t = powf(10000.f, (float)(2 * (f / 2)) / 128.f);
+            const float ax = ref[r * 2 + 0] * two_pi / dim_t, ay = ref[r * 2 + 1] * two_pi / dim_t;
+            out[r * D + f] = (f & 1) ? cosf(ay) : sinf(ay);
+            out[r * D + half + f] = (f & 1) ? cosf(ax) : sinf(ax);
+        }
+    } else {
+        const int lane = threadIdx.x & 31;
+        const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (r >= n) return;
+        const float rx = ref[r * 2 + 0], ry = ref[r * 2 + 1];
+        float gx = 0.f, gy = 0.f;
+        for (int f = lane; f < half; f += 32) {
+            const float k = two_pi / powf(10000.f, (float)(2 * (f / 2)) / 128.f);
+            const float ay = ry * k, ax = rx * k;
+            gy += demb[r * D + f] * ((f & 1) ? -sinf(ay) : cosf(ay)) * k;
+            gx += demb[r * D + half + f] * ((f & 1) ? -sinf(ax) : cosf(ax)) * k;
+        }
+        gx = warp_sum(gx); gy = warp_sum(gy);
+        if (lane == 0) { out[r * 2 + 0] = gx; out[r * 2 + 1] = gy; }
+    }
+}
+
+// dpre = dout * (h > 0)   (bf16 x bf16 -> bf16), for a ReLU fused into the producing GEMM's epilogue
+__global__ void relu_bwd_kernel(const uint16_t* __restrict__ dout, const uint16_t* __restrict__ h, uint16_t* __restrict__ out, long long n) {
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (long long)gridDim.x * blockDim.x * 2) {
+        if (i + 1 < n) {
+            const uint32_t d = *reinterpret_cast<const uint32_t*>(dout + i), hv = *reinterpret_cast<const uint32_t*>(h + i);
+            const float2 hf = unpack_bf16x2(hv);
+            uint32_t o = d;
+            if (!(hf.x > 0.f)) o &= 0xffff0000u;
+            if (!(hf.y > 0.f)) o &= 0x0000ffffu;
+            *reinterpret_cast<uint32_t*>(out + i) = o;
+        } else {
+            out[i] = bf16_to_f(h[i]) > 0.f ? dout[i] : (uint16_t)0;
+        }
+    }
+}
+
+inline int grid_for(long long work_items, int threads) {
+    long long g = (work_items + threads - 1) / threads;
+    const long long cap = (long long)spe_num_sms() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" __attribute__((visibility("default"))) int spe_layernorm_fwd(const float* x, const float* w, const float* b, float eps, int64_t rows, int D, void* y_bf16, float* y_f32,
+                                 float* mean, float* rstd, void* stream) {
+    SPE_CHECK(x && w && b && rows > 0, "spe_layernorm_fwd: bad argument");
+    SPE_CHECK(D % 4 == 0 && D <= 128 * LN_MAXCH, "spe_layernorm_fwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXCH);
+    const int g = (int)((rows + 7) / 8 < (long long)spe_num_sms() * 8 ? (rows + 7) / 8 : (long long)spe_num_sms() * 8);
+    layernorm_fwd_kernel<<<g, 256, 0, ST(stream)>>>(x, w, b, eps, rows, D, reinterpret_cast<uint16_t*>(y_bf16), y_f32, mean, rstd);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres, const float* x, const float* w, const float* mean,
+                                 const float* rstd, int64_t rows, int D, float* dx, float* dw, float* db, void* stream) {
+    SPE_CHECK((dy_bf16 || dy_f32) && x && w && mean && rstd && dx && rows > 0, "spe_layernorm_bwd: bad argument");
+    SPE_CHECK(D % 4 == 0 && D <= 128 * LN_MAXCH, "spe_layernorm_bwd: unsupported D=%d", D);
+    long long g = (rows + 7) / 8;
+    if (g > (long long)spe_num_sms() * 2) g = (long long)spe_num_sms() * 2;
+    layernorm_bwd_kernel<<<(int)g, 256, 2 * D * sizeof(float), ST(stream)>>>(reinterpret_cast<const uint16_t*>(dy_bf16), dy_f32, dres, x, w, mean, rstd,
+                                                                               rows, D, dx, dw, db);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_softmax_fwd(const float* S, void* P, const uint8_t* mask, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldP, float* pmean,
+                               void* stream) {
+    SPE_CHECK(S && P && B > 0 && H > 0 && Nq > 0 && Nk > 0 && ldS >= Nk && ldP >= Nk, "spe_softmax_fwd: bad argument");
+    SPE_CHECK((size_t)Nk * 4 <= 200 * 1024, "spe_softmax_fwd: Nk too large");
+    static bool done = false;
+    if (!done) { SPE_CUDA(cudaFuncSetAttribute(softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
+    if (pmean) SPE_CUDA(cudaMemsetAsync(pmean, 0, (size_t)B * Nq * Nk * 4, ST(stream)));
+    softmax_fwd_kernel<<<(unsigned)((long long)B * H * Nq), 256, (size_t)Nk * 4, ST(stream)>>>(S, reinterpret_cast<uint16_t*>(P), mask, H, Nq, Nk, ldS,
+                                                                                                ldP, pmean);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_softmax_bwd(const void* P, const void* dP, void* dS, int B, int H, int Nq, int Nk, int64_t ldP, void* stream) {
+    SPE_CHECK(P && dP && dS && B > 0 && H > 0 && Nq > 0 && Nk > 0 && ldP >= Nk, "spe_softmax_bwd: bad argument");
+    SPE_CHECK((size_t)Nk * 8 <= 200 * 1024, "spe_softmax_bwd: Nk too large");
+    static bool done = false;
+    if (!done) { SPE_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
+    softmax_bwd_kernel<<<(unsigned)((long long)B * H * Nq), 256, (size_t)Nk * 8, ST(stream)>>>(reinterpret_cast<const uint16_t*>(P),
+                                                                                                reinterpret_cast<const uint16_t*>(dP),
+                                                                                                reinterpret_cast<uint16_t*>(dS), Nk, ldP);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+template <int H>
+static int talking_fwd_launch(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, int B, int Nq, int Nk,
+                              int64_t ldS, int64_t ldA, cudaStream_t st) {
+    const size_t smem = (size_t)H * ((Nk + 1) & ~1) * 4;
+    SPE_CHECK(smem <= 200 * 1024, "spe_talking_softmax_fwd: H*Nk=%d*%d does not fit shared memory", H, Nk);
+    static bool done = false;
+    if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
+    talking_fwd_kernel<H><<<B * Nq, 256, smem, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, Nq, Nk, ldS, ldA);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, int B, int H,
+                                       int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream) {
+    SPE_CHECK(S && A && Wl && bl && Ww && bw && B > 0 && Nq > 0 && Nk > 0, "spe_talking_softmax_fwd: bad argument");
+    SPE_CHECK(ldS % 2 == 0 && ldA % 2 == 0 && ldS >= Nk && ldA >= Nk, "spe_talking_softmax_fwd: leading dims must be even and >= Nk");
+    switch (H) {
+        case 2: return talking_fwd_launch<2>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
+        case 4: return talking_fwd_launch<4>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
+        case 8: return talking_fwd_launch<8>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
+        default: SPE_FAIL("spe_talking_softmax_fwd: unsupported head count %d (2/4/8)", H);
+    }
+}
+
+static int talking_bwd_grid(int B, int Nq) {
+    long long rows = (long long)B * Nq;
+    long long g = spe_num_sms();
+    return (int)(rows < g ? rows : g);
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk) {
+    (void)Nk;
+    return (int64_t)talking_bwd_grid(B, Nq) * (2 * H * H + 2 * H);
+}
+
+template <int H>
+static int talking_bwd_launch(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, int B, int Nq, int Nk,
+                              int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* ws, cudaStream_t st) {
+    const size_t smem = (size_t)3 * H * ((Nk + 1) & ~1) * 4;
+    SPE_CHECK(smem <= 220 * 1024, "spe_talking_softmax_bwd: H*Nk=%d*%d does not fit shared memory", H, Nk);
+    SPE_CHECK(smem >= (size_t)8 * (2 * H * H + 2 * H) * 4 || true, "unreachable");
+    const size_t smem_use = smem < (size_t)8 * (2 * H * H + 2 * H) * 4 ? (size_t)8 * (2 * H * H + 2 * H) * 4 : smem;
+    static bool done = false;
+    if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); done = true; }
+    const int grid = talking_bwd_grid(B, Nq);
+    talking_bwd_kernel<H><<<grid, 256, smem_use, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, B * Nq,
+                                                       Nq, Nk, ldS, ldA, ws);
+    SPE_LAUNCHED();
+    const int NP = 2 * H * H + 2 * H;
+    talking_bwd_finalize_kernel<<<(NP + 127) / 128, 128, 0, st>>>(ws, grid, H, dWl, dbl, dWw, dbw);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* bw,
+                                       int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw,
+                                       float* workspace, int64_t workspace_floats, void* stream) {
+    (void)bw;
+    SPE_CHECK(S && dA && dS && Wl && bl && Ww && dWl && dbl && dWw && dbw && workspace, "spe_talking_softmax_bwd: null argument");
+    SPE_CHECK(ldS % 2 == 0 && ldA % 2 == 0 && ldS >= Nk && ldA >= Nk, "spe_talking_softmax_bwd: leading dims must be even and >= Nk");
+    SPE_CHECK(workspace_floats >= spe_talking_softmax_bwd_workspace(B, H, Nq, Nk), "spe_talking_softmax_bwd: workspace too small");
+    switch (H) {
+        case 2: return talking_bwd_launch<2>(S, dA, dS, Wl, bl, Ww, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
+        case 4: return talking_bwd_launch<4>(S, dA, dS, Wl, bl, Ww, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
+        case 8: return talking_bwd_launch<8>(S, dA, dS, Wl, bl, Ww, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
+        default: SPE_FAIL("spe_talking_softmax_bwd: unsupported head count %d (2/4/8)", H);
+    }
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_layerscale_bwd(const float* dout, const void* y_bf16, const float* gamma, int64_t rows, int D, void* dy_bf16, float* dgamma,
+                                  float* dbias, void* stream) {
+    SPE_CHECK(dout && y_bf16 && gamma && dy_bf16 && rows > 0 && D % 4 == 0, "spe_layerscale_bwd: bad argument");
+    const int gx = (D + 127) / 128;
+    long long gy = (rows + 7) / 8;
+    const long long cap = ((long long)spe_num_sms() * 4 + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    layerscale_bwd_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, ST(stream)>>>(dout, reinterpret_cast<const uint16_t*>(y_bf16), gamma, rows, D,
+                                                                                    reinterpret_cast<uint16_t*>(dy_bf16), dgamma, dbias);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_colsum_bf16(const void* x, int64_t rows, int N, int64_t ld, float* out, void* stream) {
+    SPE_CHECK(x && out && rows > 0 && N > 0 && ld % 2 == 0, "spe_colsum_bf16: bad argument (ld must be even)");
+    const int gx = (N + 63) / 64;
+    long long gy = (rows + 7) / 8;
+    const long long cap = ((long long)spe_num_sms() * 4 + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    colsum_bf16_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(x), rows, N, ld, out);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_axpby_cast(const float* x, const float* y, float a, float b, int64_t n, void* out_bf16, float* out_f32, void* stream) {
+    SPE_CHECK(x && n > 0 && (out_bf16 || out_f32), "spe_axpby_cast: bad argument");
+    axpby_cast_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, ST(stream)>>>(x, y, a, b, n, reinterpret_cast<uint16_t*>(out_bf16), out_f32);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
+    SPE_CHECK(x && y && n > 0, "spe_cast_bf16_to_f32: bad argument");
+    cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(x), y, n, 0);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_add_bf16_into_f32(const void* x, float* out, int64_t n, void* stream) {
+    SPE_CHECK(x && out && n > 0, "spe_add_bf16_into_f32: bad argument");
+    cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(x), out, n, 1);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_im2col_patch(const float* img, int B, int H, int W, int p, void* out_bf16, void* stream) {
+    SPE_CHECK(img && out_bf16 && B > 0 && p % 4 == 0 && H >= p && W >= p && W % 4 == 0, "spe_im2col_patch: bad argument");
+    const long long total = (long long)B * (H / p) * (W / p) * 3 * p * p / 4;
+    im2col_patch_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(img, B, H, W, p, reinterpret_cast<uint16_t*>(out_bf16));
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_bicubic_tokens_fwd(const float* src, int sh, int sw, int D, float* dst, int dh, int dw, void* stream) {
+    SPE_CHECK(src && dst && sh > 0 && sw > 0 && dh > 0 && dw > 0 && D > 0, "spe_bicubic_tokens_fwd: bad argument");
+    bicubic_tokens_kernel<false><<<grid_for((long long)dh * dw * D, 256), 256, 0, ST(stream)>>>(src, dst, sh, sw, dh, dw, D);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_bicubic_tokens_bwd(const float* ddst, int dh, int dw, int D, float* dsrc, int sh, int sw, void* stream) {
+    SPE_CHECK(ddst && dsrc && sh > 0 && sw > 0 && dh > 0 && dw > 0 && D > 0, "spe_bicubic_tokens_bwd: bad argument");
+    bicubic_tokens_kernel<true><<<grid_for((long long)dh * dw * D, 256), 256, 0, ST(stream)>>>(ddst, dsrc, sh, sw, dh, dw, D);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_sine_pos_2d(const uint8_t* mask, int B, int h, int w, int D, float* pos, void* pos_bf16, void* stream) {
+    SPE_CHECK(mask && (pos || pos_bf16) && B > 0 && h > 0 && w > 0 && D % 4 == 0, "spe_sine_pos_2d: bad argument");
+    sine_pos_2d_kernel<<<grid_for((long long)B * h * w * (D / 2), 256), 256, 0, ST(stream)>>>(mask, B, h, w, D, pos, reinterpret_cast<uint16_t*>(pos_bf16));
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_query_sine_fwd(const float* ref, int64_t n, int D, float* emb, void* stream) {
+    SPE_CHECK(ref && emb && n > 0 && D % 4 == 0, "spe_query_sine_fwd: bad argument");
+    query_sine_kernel<false><<<grid_for(n * (D / 2), 256), 256, 0, ST(stream)>>>(ref, nullptr, n, D, emb);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_query_sine_bwd(const float* ref, const float* demb, int64_t n, int D, float* dref, void* stream) {
+    SPE_CHECK(ref && demb && dref && n > 0 && D % 4 == 0, "spe_query_sine_bwd: bad argument");
+    query_sine_kernel<true><<<(unsigned)((n + 7) / 8), 256, 0, ST(stream)>>>(ref, demb, n, D, dref);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_relu_bwd_bf16(const void* dout, const void* h, void* out, int64_t n, void* stream) {
+    SPE_CHECK(dout && h && out && n > 0, "spe_relu_bwd_bf16: bad argument");
+    relu_bwd_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(dout), reinterpret_cast<const uint16_t*>(h),
+                                                                         reinterpret_cast<uint16_t*>(out), n);
+    SPE_LAUNCHED();
+    return 0;
+}

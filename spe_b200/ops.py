@@ -1,0 +1,621 @@
+"""Host-side operator layer: torch.autograd Functions whose forward AND backward are calls into the
+C ABI of libspe_b200.so (sm_100a kernels).  PyTorch is used for device memory, streams and the
+autograd tape only -- there is no eager/PyTorch compute fallback: every op raises if the native
+library is missing or the tensors are not CUDA tensors.
+
+Layout conventions (batch-first, token-major):
+  residual streams / LayerNorm inputs : fp32 [B, N, D]
+  GEMM operands (activations)         : bf16 [B, N, D]   (row stride may exceed D for packed views)
+  attention logits S                  : fp32 [B, H, Lq, ld]   ld = Lk rounded up to 8
+  attention probabilities             : bf16 [B, H, Lq, ld]
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check, lib, ptr, stream
+
+MAJOR_K, MAJOR_MN = 0, 1
+DT_BF16, DT_F32 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_RELU_GRAD, ACT_GELU_GRAD = 0, 1, 2, 3, 4
+_ACT = {None: ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU}
+_ACT_GRAD = {"relu": ACT_RELU_GRAD, "gelu": ACT_GELU_GRAD}
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("spe_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def rup(x, m):
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 shadows of fp32 parameters (H4: reference-named fp32 nn.Parameters stay the source of truth)
+# ------------------------------------------------------------------------------------------------
+_shadow = {}
+
+
+def shadow(p):
+    """bf16 copy of an fp32 parameter (or of a slice view of one), refreshed when the parameter changes."""
+    key = (p.data_ptr(), tuple(p.shape))
+    ent = _shadow.get(key)
+    ver = p._version
+    if ent is not None and ent[0] == ver and ent[1].device == p.device:
+        return ent[1]
+    src = p.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    out = ent[1] if ent is not None and ent[1].device == p.device else torch.empty(p.shape, dtype=torch.bfloat16, device=p.device)
+    axpby_cast(src, None, 1.0, 0.0, out_bf16=out)
+    _shadow[key] = (ver, out)
+    return out
+
+
+def clear_shadows():
+    _shadow.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+# raw kernel wrappers (no autograd)
+# ------------------------------------------------------------------------------------------------
+def gemm(a, b, c, M, N, K, *, a_major=MAJOR_K, lda=None, b_major=MAJOR_K, ldb=None, ldc=None, batch=(1, 1),
+         a_sb=(0, 0), b_sb=(0, 0), c_sb=(0, 0), alpha=1.0, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, ld_aux=0,
+         gamma=None, residual=None, ldr=0, r_sb=(0, 0), split=0, split_stride=0):
+    _need_cuda(a, b, c)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    g = GemmArgs()
+    g.M, g.N, g.K, g.batch1, g.batch2 = M, N, K, batch[0], batch[1]
+    g.A, g.a_major, g.lda, g.a_sb1, g.a_sb2 = a.data_ptr(), a_major, lda, a_sb[0], a_sb[1]
+    g.B, g.b_major, g.ldb, g.b_sb1, g.b_sb2 = b.data_ptr(), b_major, ldb, b_sb[0], b_sb[1]
+    g.C, g.c_dtype = c.data_ptr(), (DT_F32 if c.dtype == torch.float32 else DT_BF16)
+    g.ldc, g.c_sb1, g.c_sb2 = ldc, c_sb[0], c_sb[1]
+    g.alpha, g.bias, g.act = alpha, ptr(bias), act
+    g.aux_in, g.aux_out, g.ld_aux = ptr(aux_in), ptr(aux_out), ld_aux
+    g.gamma, g.residual, g.ldr, g.r_sb1, g.r_sb2 = ptr(gamma), ptr(residual), ldr, r_sb[0], r_sb[1]
+    g.split, g.split_stride = split, split_stride
+    check(lib().spe_gemm(C.byref(g), stream()))
+    return c
+
+
+def axpby_cast(x, y, a, b, out_bf16=None, out_f32=None):
+    _need_cuda(x)
+    check(lib().spe_axpby_cast(ptr(x), ptr(y), a, b, x.numel(), ptr(out_bf16), ptr(out_f32), stream()))
+
+
+def to_bf16(x):
+    """fp32 -> bf16 cast kernel (contiguous)."""
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    axpby_cast(x, None, 1.0, 0.0, out_bf16=out)
+    return out
+
+
+def colsum_bf16(x2d, out):
+    rows, n = x2d.shape
+    check(lib().spe_colsum_bf16(ptr(x2d), rows, n, x2d.stride(0), ptr(out), stream()))
+
+
+def _rows(t):
+    return t.numel() // t.shape[-1]
+
+
+# y[M,N] = x[M,K] @ w[N,K]^T (+ epilogue)
+def _linear_fwd(x, w16, bias, out, **kw):
+    M, K = _rows(x), x.shape[-1]
+    N = w16.shape[0]
+    return gemm(x, w16, out, M, N, K, lda=x.stride(-2) if x.dim() > 1 else K, ldb=w16.stride(0), ldc=kw.pop("ldc", N), bias=bias, **kw)
+
+
+# dx[M,K] = dy[M,N] @ w[N,K]
+def _linear_dgrad(dy, w16, out, **kw):
+    M, N = _rows(dy), dy.shape[-1]
+    K = w16.shape[1]
+    return gemm(dy, w16, out, M, K, N, lda=dy.stride(-2), b_major=MAJOR_MN, ldb=w16.stride(0), ldc=kw.pop("ldc", K), **kw)
+
+
+# dw[N,K] = dy[M,N]^T @ x[M,K]   (fp32 out)
+def _linear_wgrad(dy, x, out):
+    M, N = _rows(dy), dy.shape[-1]
+    K = x.shape[-1]
+    return gemm(dy, x, out, N, K, M, a_major=MAJOR_MN, lda=dy.stride(-2), b_major=MAJOR_MN, ldb=x.stride(-2), ldc=K)
+
+
+def _pad_cols(t2d):
+    """TMA needs a 16-byte row pitch: return a view of t2d [M,N] whose row stride is N rounded up to 8."""
+    M, N = t2d.shape
+    if N % 8 == 0 and t2d.stride(0) % 8 == 0:
+        return t2d
+    buf = torch.zeros((M, rup(N, 8)), dtype=t2d.dtype, device=t2d.device)
+    buf[:, :N].copy_(t2d)
+    return buf[:, :N]
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions
+# ------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on bf16 activations:  out = [residual +] [gamma *] act(x W^T + b).
+    `residual` (fp32) has the shape of the output, or the output shape without its leading batch dim
+    (broadcast over the batch, e.g. the batch-invariant query_pos projections of transformer.py:368-372).
+    Output is fp32 when out_f32 (always when gamma is given), else bf16.
+    Replaces cait.py:376,390 / transformer.py projections / conditional_detr.py heads / MLP layers."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, gamma, out_f32, act):
+        _need_cuda(x, weight)
+        assert x.dtype == torch.bfloat16 and x.stride(-1) == 1
+        x = x if x.is_contiguous() else x.contiguous()
+        w16 = shadow(weight)
+        N, Kd = weight.shape
+        f32 = bool(out_f32) or gamma is not None
+        out = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32 if f32 else torch.bfloat16, device=x.device)
+        y = None
+        bcast = residual is not None and residual.dim() == x.dim() - 1
+        if residual is not None:
+            residual = residual.contiguous()
+            assert residual.dtype == torch.float32
+        if gamma is not None:
+            assert not bcast and act is None
+            y = torch.empty(x.shape[:-1] + (N,), dtype=torch.bfloat16, device=x.device)   # pre-LayerScale branch (for dgamma)
+        if bcast:
+            Bt = x.shape[0]
+            Mb = _rows(x) // Bt
+            gemm(x, w16, out, Mb, N, Kd, lda=Kd, ldb=Kd, ldc=N, batch=(Bt, 1), a_sb=(Mb * Kd, 0), b_sb=(0, 0), c_sb=(Mb * N, 0), bias=bias,
+                 act=_ACT[act], residual=residual, ldr=N, r_sb=(0, 0))
+        else:
+            _linear_fwd(x, w16, bias, out, gamma=gamma, residual=residual, ldr=N, aux_out=y, ld_aux=N, act=_ACT[act])
+        ctx.save_for_backward(x, weight, gamma, y, out if act is not None else None)
+        ctx.has_bias = bias is not None
+        ctx.res = None if residual is None else ("b" if bcast else "f")
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, gamma, y, h = ctx.saved_tensors
+        w16 = shadow(weight)
+        N, K = weight.shape
+        dout = dout.contiguous()
+        dgamma = dbias = None
+        dres = None
+        if ctx.res is not None:
+            d32 = dout if dout.dtype == torch.float32 else _to_f32(dout)
+            dres = d32 if ctx.res == "f" else d32.sum(0)
+        if gamma is not None:
+            dy = torch.empty(dout.shape, dtype=torch.bfloat16, device=dout.device)
+            dgamma = torch.zeros_like(gamma)
+            dbias = torch.zeros(N, dtype=torch.float32, device=dout.device) if ctx.has_bias else None
+            check(lib().spe_layerscale_bwd(ptr(dout), ptr(y), ptr(gamma), _rows(dout), N, ptr(dy), ptr(dgamma), ptr(dbias), stream()))
+        else:
+            dy = dout if dout.dtype == torch.bfloat16 else to_bf16(dout)
+            if ctx.act is not None:
+                assert ctx.act == "relu"
+                h16 = h if h.dtype == torch.bfloat16 else to_bf16(h)
+                dpre = torch.empty_like(dy)
+                check(lib().spe_relu_bwd_bf16(ptr(dy), ptr(h16), ptr(dpre), dy.numel(), stream()))
+                dy = dpre
+            if ctx.has_bias:
+                dbias = torch.zeros(N, dtype=torch.float32, device=dout.device)
+                colsum_bf16(_pad_cols(dy.view(-1, N)), dbias)
+        dy = _pad_cols(dy.view(-1, N))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            _linear_dgrad(dy, w16, dx)
+        dw = torch.empty((N, K), dtype=torch.float32, device=x.device)
+        _linear_wgrad(dy, x, dw)
+        return dx, dw, dbias, dres, dgamma, None, None
+
+
+def linear(x, weight, bias=None, residual=None, gamma=None, out_f32=False, act=None):
+    return LinearFn.apply(x, weight, bias, residual, gamma, out_f32, act)
+
+
+def _to_f32(x16):
+    out = torch.empty(x16.shape, dtype=torch.float32, device=x16.device)
+    check(lib().spe_cast_bf16_to_f32(ptr(x16.contiguous()), ptr(out), x16.numel(), stream()))
+    return out
+
+
+class FfnFn(torch.autograd.Function):
+    """out_f32 = residual + [gamma *] (act(x W1^T + b1) W2^T + b2).   timm Mlp (GELU, cait.py:415) and the DETR
+    FFN (ReLU, transformer.py:285-286, 424).  The activation derivative is fused into the dgrad epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual, gamma, act):
+        _need_cuda(x, w1, w2)
+        w1_16, w2_16 = shadow(w1), shadow(w2)
+        Fh, D = w1.shape
+        lead = x.shape[:-1]
+        a = torch.empty(lead + (Fh,), dtype=torch.bfloat16, device=x.device) if act == "gelu" else None
+        h = torch.empty(lead + (Fh,), dtype=torch.bfloat16, device=x.device)
+        # one GEMM: C = act(x W1^T + b1); aux_out = the pre-activation (needed by gelu')
+        _linear_fwd(x, w1_16, b1, h, act=_ACT[act], aux_out=a, ld_aux=Fh)
+        out = torch.empty(lead + (w2.shape[0],), dtype=torch.float32, device=x.device)
+        y = torch.empty(lead + (w2.shape[0],), dtype=torch.bfloat16, device=x.device) if gamma is not None else None
+        _linear_fwd(h, w2_16, b2, out, gamma=gamma, residual=residual, ldr=w2.shape[0], aux_out=y, ld_aux=w2.shape[0])
+        ctx.save_for_backward(x, w1, w2, gamma, a, h, y)
+        ctx.act = act
+        ctx.has_res = residual is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w1, w2, gamma, a, h, y = ctx.saved_tensors
+        w1_16, w2_16 = shadow(w1), shadow(w2)
+        Fh, D = w1.shape
+        Do = w2.shape[0]
+        dout = dout.contiguous()
+        dev = dout.device
+        dgamma = None
+        db2 = torch.zeros(Do, dtype=torch.float32, device=dev)
+        if gamma is not None:
+            dy = torch.empty(dout.shape, dtype=torch.bfloat16, device=dev)
+            dgamma = torch.zeros_like(gamma)
+            check(lib().spe_layerscale_bwd(ptr(dout), ptr(y), ptr(gamma), _rows(dout), Do, ptr(dy), ptr(dgamma), ptr(db2), stream()))
+        else:
+            dy = to_bf16(dout)
+            colsum_bf16(dy.view(-1, Do), db2)
+        dw2 = torch.empty((Do, Fh), dtype=torch.float32, device=dev)
+        _linear_wgrad(dy, h, dw2)
+        da = torch.empty(h.shape, dtype=torch.bfloat16, device=dev)
+        aux = a if ctx.act == "gelu" else h
+        _linear_dgrad(dy, w2_16, da, act=_ACT_GRAD[ctx.act], aux_in=aux, ld_aux=Fh)
+        db1 = torch.zeros(Fh, dtype=torch.float32, device=dev)
+        colsum_bf16(da.view(-1, Fh), db1)
+        dw1 = torch.empty((Fh, D), dtype=torch.float32, device=dev)
+        _linear_wgrad(da, x, dw1)
+        dx = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
+        _linear_dgrad(da, w1_16, dx)
+        return dx, dw1, db1, dw2, db2, (dout if ctx.has_res else None), dgamma, None
+
+
+def ffn(x, w1, b1, w2, b2, residual=None, gamma=None, act="relu"):
+    return FfnFn.apply(x, w1, b1, w2, b2, residual, gamma, act)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """LayerNorm(x_f32) -> (y_f32 or None, y_bf16).  Backward sums the gradients of both outputs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, want_f32):
+        _need_cuda(x, weight, bias)
+        x = x.contiguous()
+        D = x.shape[-1]
+        rows = _rows(x)
+        y16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        y32 = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_f32 else None
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        check(lib().spe_layernorm_fwd(ptr(x), ptr(weight), ptr(bias), eps, rows, D, ptr(y16), ptr(y32), ptr(mean), ptr(rstd), stream()))
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.want_f32 = want_f32
+        if want_f32:
+            return y32, y16
+        return y16
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, weight, mean, rstd = ctx.saved_tensors
+        if ctx.want_f32:
+            d32, d16 = grads
+        else:
+            d32, d16 = None, grads[0]
+        D = x.shape[-1]
+        if d32 is None and d16 is None:
+            return None, None, None, None, None
+        d32 = d32.contiguous() if d32 is not None else None
+        d16 = d16.contiguous() if d16 is not None else None
+        dx = torch.empty_like(x)
+        dw = torch.zeros(D, dtype=torch.float32, device=x.device)
+        db = torch.zeros(D, dtype=torch.float32, device=x.device)
+        check(lib().spe_layernorm_bwd(ptr(d16), ptr(d32), 0, ptr(x), ptr(weight), ptr(mean), ptr(rstd), _rows(x), D, ptr(dx), ptr(dw), ptr(db),
+                                      stream()))
+        return dx, dw, db, None, None
+
+
+def layernorm(x, weight, bias, eps, want_f32=False):
+    """returns y_bf16, or (y_f32, y_bf16) when want_f32."""
+    return LayerNormFn.apply(x, weight, bias, eps, want_f32)
+
+
+class AddCastFn(torch.autograd.Function):
+    """(a_f32 + b_f32) -> bf16   (with_pos_embed, transformer.py:272-273)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        assert a.shape == b.shape
+        out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+        axpby_cast(a, b, 1.0, 1.0, out_bf16=out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d32 = torch.empty(d.shape, dtype=torch.float32, device=d.device)
+        check(lib().spe_cast_bf16_to_f32(ptr(d.contiguous()), ptr(d32), d.numel(), stream()))
+        return d32, d32
+
+
+class CastBf16Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a):
+        return to_bf16(a)
+
+    @staticmethod
+    def backward(ctx, d):
+        d32 = torch.empty(d.shape, dtype=torch.float32, device=d.device)
+        check(lib().spe_cast_bf16_to_f32(ptr(d.contiguous()), ptr(d32), d.numel(), stream()))
+        return d32
+
+
+class CastF32Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a):
+        out = torch.empty(a.shape, dtype=torch.float32, device=a.device)
+        check(lib().spe_cast_bf16_to_f32(ptr(a.contiguous()), ptr(out), a.numel(), stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return to_bf16(d)
+
+
+def add_cast(a, b):
+    return AddCastFn.apply(a, b)
+
+
+def cast_bf16(a):
+    return CastBf16Fn.apply(a)
+
+
+def cast_f32(a):
+    return CastF32Fn.apply(a)
+
+
+# ---- attention ---------------------------------------------------------------------------------
+def _qk_logits(q, k, H, alpha, S, ldS, q2=None, k2=None):
+    """S[b,h] = alpha * (q_h k_h^T [+ q2_h k2_h^T])   q [B,Lq,H*d] (row stride free), S f32 [B,H,Lq,ldS]."""
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    d = E // H
+    gemm(q, k, S, Lq, Lk, d, lda=q.stride(1), ldb=k.stride(1), ldc=ldS, batch=(B, H), a_sb=(q.stride(0), d), b_sb=(k.stride(0), d),
+         c_sb=(H * Lq * ldS, Lq * ldS), alpha=alpha)
+    if q2 is not None:
+        d2 = q2.shape[2] // H
+        gemm(q2, k2, S, Lq, Lk, d2, lda=q2.stride(1), ldb=k2.stride(1), ldc=ldS, batch=(B, H), a_sb=(q2.stride(0), d2), b_sb=(k2.stride(0), d2),
+             c_sb=(H * Lq * ldS, Lq * ldS), alpha=alpha, residual=S, ldr=ldS, r_sb=(H * Lq * ldS, Lq * ldS))
+
+
+def _pv(P, v, H, out, Lq, Lk, ldP):
+    """out[b,:,h*dv:(h+1)*dv] = P[b,h] @ v_h   (v consumed MN-major straight from [B,Lk,H*dv])."""
+    B = v.shape[0]
+    dv = v.shape[2] // H
+    gemm(P, v, out, Lq, dv, Lk, lda=ldP, a_sb=(H * Lq * ldP, Lq * ldP), b_major=MAJOR_MN, ldb=v.stride(1), b_sb=(v.stride(0), dv),
+         ldc=out.stride(1), c_sb=(out.stride(0), dv), batch=(B, H))
+
+
+def _attn_bwd_common(dO, P, v, H, Lq, Lk, ldP):
+    """dP[b,h] = dO_h v_h^T (bf16 [B,H,Lq,ldP]);  dV = P^T dO  (bf16 [B,Lk,H*dv])."""
+    B = v.shape[0]
+    dv = v.shape[2] // H
+    dP = torch.empty((B, H, Lq, ldP), dtype=torch.bfloat16, device=v.device)
+    gemm(dO, v, dP, Lq, Lk, dv, lda=dO.stride(1), a_sb=(dO.stride(0), dv), ldb=v.stride(1), b_sb=(v.stride(0), dv), ldc=ldP,
+         c_sb=(H * Lq * ldP, Lq * ldP), batch=(B, H))
+    dV = torch.empty((B, Lk, H * dv), dtype=torch.bfloat16, device=v.device)
+    gemm(P, dO, dV, Lk, dv, Lq, a_major=MAJOR_MN, lda=ldP, a_sb=(H * Lq * ldP, Lq * ldP), b_major=MAJOR_MN, ldb=dO.stride(1),
+         b_sb=(dO.stride(0), dv), ldc=H * dv, c_sb=(Lk * H * dv, dv), batch=(B, H))
+    return dP, dV
+
+
+def _dq_dk(dS, q, k, H, alpha, Lq, Lk, ldP, dq_out=None, dk_out=None):
+    """dQ = alpha dS K ; dK = alpha dS^T Q  (both bf16, laid out like q / k)."""
+    B = q.shape[0]
+    d = q.shape[2] // H
+    dq = dq_out if dq_out is not None else torch.empty((B, Lq, H * d), dtype=torch.bfloat16, device=q.device)
+    dk = dk_out if dk_out is not None else torch.empty((B, Lk, H * d), dtype=torch.bfloat16, device=q.device)
+    gemm(dS, k, dq, Lq, d, Lk, lda=ldP, a_sb=(H * Lq * ldP, Lq * ldP), b_major=MAJOR_MN, ldb=k.stride(1), b_sb=(k.stride(0), d),
+         ldc=dq.stride(1), c_sb=(dq.stride(0), d), batch=(B, H), alpha=alpha)
+    gemm(dS, q, dk, Lk, d, Lq, a_major=MAJOR_MN, lda=ldP, a_sb=(H * Lq * ldP, Lq * ldP), b_major=MAJOR_MN, ldb=q.stride(1),
+         b_sb=(q.stride(0), d), ldc=dk.stride(1), c_sb=(dk.stride(0), d), batch=(B, H), alpha=alpha)
+    return dq, dk
+
+
+class AttentionFn(torch.autograd.Function):
+    """softmax(scale * (q k^T [+ q2 k2^T]) + key_padding_mask) v, heads packed along the feature dim.
+    nn.MultiheadAttention core (transformer.py:280) and models/attention.py:345-378 (d_qk != d_v, the
+    conditional cross-attention's [content | position] concat expressed as two accumulated QK^T GEMMs).
+    Optionally returns the head-mean attention map (cait.py:658-667)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, q2, k2, mask_u8, H, scale, want_mean):
+        _need_cuda(q, k, v)
+        B, Lq, _ = q.shape
+        Lk = k.shape[1]
+        ld = rup(Lk, 8)
+        S = torch.empty((B, H, Lq, ld), dtype=torch.float32, device=q.device)
+        _qk_logits(q, k, H, scale, S, ld, q2, k2)
+        P = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=q.device)
+        pmean = torch.empty((B, Lq, Lk), dtype=torch.float32, device=q.device) if want_mean else None
+        check(lib().spe_softmax_fwd(ptr(S), ptr(P), ptr(mask_u8), B, H, Lq, Lk, ld, ld, ptr(pmean), stream()))
+        del S
+        out = torch.empty((B, Lq, v.shape[2]), dtype=torch.bfloat16, device=q.device)
+        _pv(P, v, H, out, Lq, Lk, ld)
+        ctx.save_for_backward(q, k, v, q2, k2, P)
+        ctx.H, ctx.scale, ctx.ld = H, scale, ld
+        if want_mean:
+            ctx.mark_non_differentiable(pmean)
+            return out, pmean
+        return out
+
+    @staticmethod
+    def backward(ctx, dO, *unused):
+        q, k, v, q2, k2, P = ctx.saved_tensors
+        H, scale, ld = ctx.H, ctx.scale, ctx.ld
+        B, Lq, _ = q.shape
+        Lk = k.shape[1]
+        dO = dO.contiguous()
+        dP, dV = _attn_bwd_common(dO, P, v, H, Lq, Lk, ld)
+        check(lib().spe_softmax_bwd(ptr(P), ptr(dP), ptr(dP), B, H, Lq, Lk, ld, stream()))
+        dq, dk = _dq_dk(dP, q, k, H, scale, Lq, Lk, ld)
+        dq2 = dk2 = None
+        if q2 is not None:
+            dq2, dk2 = _dq_dk(dP, q2, k2, H, scale, Lq, Lk, ld)
+        return dq, dk, dV, dq2, dk2, None, None, None, None
+
+
+def attention(q, k, v, H, scale, mask_u8=None, q2=None, k2=None, want_mean=False):
+    return AttentionFn.apply(q, k, v, q2, k2, mask_u8, H, scale, want_mean)
+
+
+class TalkingHeadsAttentionFn(torch.autograd.Function):
+    """Attention_talking_head core (cait.py:377-389) on a packed qkv [B,N,3D] bf16:
+    S = scale q k^T -> proj_l over heads -> softmax -> proj_w over heads -> @ v."""
+
+    @staticmethod
+    def forward(ctx, qkv, Wl, bl, Ww, bw, H):
+        _need_cuda(qkv, Wl)
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        dh = D // H
+        q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+        ld = rup(N, 8)
+        scale = dh ** -0.5
+        S = torch.empty((B, H, N, ld), dtype=torch.float32, device=qkv.device)
+        _qk_logits(q, k, H, scale, S, ld)
+        A = torch.empty((B, H, N, ld), dtype=torch.bfloat16, device=qkv.device)
+        check(lib().spe_talking_softmax_fwd(ptr(S), ptr(A), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), B, H, N, N, ld, ld, stream()))
+        out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
+        _pv(A, v, H, out, N, N, ld)
+        ctx.save_for_backward(qkv, S, A, Wl, bl, Ww, bw)
+        ctx.H, ctx.ld = H, ld
+        return out
+
+    @staticmethod
+    def backward(ctx, dO):
+        qkv, S, A, Wl, bl, Ww, bw = ctx.saved_tensors
+        H, ld = ctx.H, ctx.ld
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        dh = D // H
+        scale = dh ** -0.5
+        q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+        dO = dO.contiguous()
+        dqkv = torch.empty_like(qkv)
+        # dA = dO v^T ; dV = A^T dO (written straight into the v third of dqkv)
+        dA = torch.empty((B, H, N, ld), dtype=torch.bfloat16, device=qkv.device)
+        gemm(dO, v, dA, N, N, dh, lda=dO.stride(1), a_sb=(dO.stride(0), dh), ldb=v.stride(1), b_sb=(v.stride(0), dh), ldc=ld,
+             c_sb=(H * N * ld, N * ld), batch=(B, H))
+        dv = dqkv[:, :, 2 * D:]
+        gemm(A, dO, dv, N, dh, N, a_major=MAJOR_MN, lda=ld, a_sb=(H * N * ld, N * ld), b_major=MAJOR_MN, ldb=dO.stride(1), b_sb=(dO.stride(0), dh),
+             ldc=dv.stride(1), c_sb=(dv.stride(0), dh), batch=(B, H))
+        dWl, dbl, dWw, dbw = torch.zeros_like(Wl), torch.zeros_like(bl), torch.zeros_like(Ww), torch.zeros_like(bw)
+        nws = lib().spe_talking_softmax_bwd_workspace(B, H, N, N)
+        ws = torch.empty(nws, dtype=torch.float32, device=qkv.device)
+        check(lib().spe_talking_softmax_bwd(ptr(S), ptr(dA), ptr(dA), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), B, H, N, N, ld, ld, ptr(dWl), ptr(dbl),
+                                            ptr(dWw), ptr(dbw), ptr(ws), nws, stream()))
+        _dq_dk(dA, q, k, H, scale, N, N, ld, dq_out=dqkv[:, :, :D], dk_out=dqkv[:, :, D:2 * D])
+        return dqkv, dWl, dbl, dWw, dbw, None
+
+
+def talking_heads_attention(qkv, Wl, bl, Ww, bw, H):
+    return TalkingHeadsAttentionFn.apply(qkv, Wl, bl, Ww, bw, H)
+
+
+# ---- patch embedding / position encodings ---------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    """Conv2d(k=s=p) as im2col + tcgen05 GEMM, with the (bicubic-resized) position embedding added as the
+    fp32 residual of the epilogue (cait.py:527, :598-613, :623-624).  pos_tokens f32 [N, D]."""
+
+    @staticmethod
+    def forward(ctx, img, weight, bias, pos_tokens, p):
+        _need_cuda(img, weight)
+        B, Cc, Hh, Ww = img.shape
+        h, w = Hh // p, Ww // p
+        D = weight.shape[0]
+        Kc = Cc * p * p
+        cols = torch.empty((B * h * w, Kc), dtype=torch.bfloat16, device=img.device)
+        check(lib().spe_im2col_patch(ptr(img.contiguous()), B, Hh, Ww, p, ptr(cols), stream()))
+        w16 = shadow(weight).view(D, Kc)
+        out = torch.empty((B, h * w, D), dtype=torch.float32, device=img.device)
+        # residual = pos tokens broadcast over the batch: batch1 = B with residual batch stride 0
+        gemm(cols, w16, out, h * w, D, Kc, lda=Kc, ldb=Kc, ldc=D, batch=(B, 1), a_sb=(h * w * Kc, 0), b_sb=(0, 0), c_sb=(h * w * D, 0),
+             bias=bias, residual=pos_tokens, ldr=D, r_sb=(0, 0))
+        ctx.save_for_backward(cols, weight)
+        ctx.shape = (B, h * w, D, Kc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cols, weight = ctx.saved_tensors
+        B, N, D, Kc = ctx.shape
+        dout = dout.contiguous()
+        d16 = to_bf16(dout)
+        db = torch.zeros(D, dtype=torch.float32, device=dout.device)
+        colsum_bf16(d16.view(-1, D), db)
+        dw = torch.empty((D, Kc), dtype=torch.float32, device=dout.device)
+        _linear_wgrad(d16.view(-1, D), cols, dw)
+        dpos = dout.sum(0) if B > 1 else dout[0]
+        return None, dw.view(weight.shape), db, dpos, None
+
+
+class BicubicTokensFn(torch.autograd.Function):
+    """F.interpolate(mode='bicubic', align_corners=False) of the pos_embed grid (cait.py:588-600), token-major."""
+
+    @staticmethod
+    def forward(ctx, src, sh, sw, dh, dw):
+        _need_cuda(src)
+        D = src.shape[-1]
+        src2 = src.reshape(sh * sw, D).contiguous()
+        dst = torch.empty((dh * dw, D), dtype=torch.float32, device=src.device)
+        check(lib().spe_bicubic_tokens_fwd(ptr(src2), sh, sw, D, ptr(dst), dh, dw, stream()))
+        ctx.dims = (sh, sw, dh, dw, D, tuple(src.shape))
+        return dst
+
+    @staticmethod
+    def backward(ctx, d):
+        sh, sw, dh, dw, D, shp = ctx.dims
+        dsrc = torch.zeros((sh * sw, D), dtype=torch.float32, device=d.device)
+        check(lib().spe_bicubic_tokens_bwd(ptr(d.contiguous()), dh, dw, D, ptr(dsrc), sh, sw, stream()))
+        return dsrc.view(shp), None, None, None, None
+
+
+def sine_pos_2d(mask_u8, D):
+    """mask u8 [B,h,w] -> (pos f32 [B,h*w,D], pos bf16) (position_encoding.py:37-57). No gradient."""
+    _need_cuda(mask_u8)
+    B, h, w = mask_u8.shape
+    pos = torch.empty((B, h * w, D), dtype=torch.float32, device=mask_u8.device)
+    pos16 = torch.empty((B, h * w, D), dtype=torch.bfloat16, device=mask_u8.device)
+    check(lib().spe_sine_pos_2d(ptr(mask_u8.contiguous()), B, h, w, D, ptr(pos), ptr(pos16), stream()))
+    return pos, pos16
+
+
+class QuerySineFn(torch.autograd.Function):
+    """gen_sineembed_for_position (transformer.py:35-49): ref f32 [...,2] -> f32 [...,D]."""
+
+    @staticmethod
+    def forward(ctx, ref, D):
+        _need_cuda(ref)
+        ref = ref.contiguous()
+        n = ref.numel() // 2
+        emb = torch.empty(ref.shape[:-1] + (D,), dtype=torch.float32, device=ref.device)
+        check(lib().spe_query_sine_fwd(ptr(ref), n, D, ptr(emb), stream()))
+        ctx.save_for_backward(ref)
+        ctx.D = D
+        return emb
+
+    @staticmethod
+    def backward(ctx, d):
+        (ref,) = ctx.saved_tensors
+        dref = torch.empty_like(ref)
+        check(lib().spe_query_sine_bwd(ptr(ref), ptr(d.contiguous()), ref.numel() // 2, ctx.D, ptr(dref), stream()))
+        return dref, None
+
+
+def query_sine_embed(ref, D):
+    return QuerySineFn.apply(ref, D)
