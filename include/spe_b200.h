@@ -25,6 +25,12 @@ const char* spe_last_error(void);
 int spe_version(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t spe_launch_count(void);
+/* Optional device-side timing of kernel families with CUDA events on the launching stream (bench.py roofline).
+ * Families: 0 gemm (work = algorithmic flops), 1 talking-softmax fwd, 2 talking-softmax bwd, 3 softmax,
+ * 4 layernorm (work = algorithmic bytes), 5 matcher LSAP (work = images), 6 other. */
+int spe_prof_enable(int on);
+int spe_prof_collect(double* ms, double* work, int64_t* launches);   /* arrays of spe_prof_family_count() */
+int spe_prof_family_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 GEMM:  C[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )

@@ -73,7 +73,7 @@ CFG4 = SPEConfig(embed_dim=768, depth=36, num_heads=16, img_classes=80, num_quer
 
 def tiny_config(**kw) -> SPEConfig:
     """A small configuration with every code path present; used for fast parity tests."""
-    base = dict(embed_dim=96, depth=2, num_heads=2, img_classes=3, layer_to_det=1, pos_grid=(6, 7),
+    base = dict(embed_dim=128, depth=2, num_heads=2, img_classes=3, layer_to_det=1, pos_grid=(6, 7),
                 det_heads=8, ffn=128, enc_layers=1, dec_layers=2, num_queries=12, det_classes=4)
     base.update(kw)
     return SPEConfig(**base)

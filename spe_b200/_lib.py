@@ -33,6 +33,9 @@ class GemmArgs(C.Structure):
 _SIGS = {
     "spe_version": (c_i, []),
     "spe_launch_count": (c_l, []),
+    "spe_prof_enable": (c_i, [c_i]),
+    "spe_prof_collect": (c_i, [c_p, c_p, c_p]),
+    "spe_prof_family_count": (c_i, []),
     "spe_gemm": (c_i, [C.POINTER(GemmArgs), c_p]),
     "spe_layernorm_fwd": (c_i, [c_p, c_p, c_p, c_f, c_l, c_i, c_p, c_p, c_p, c_p, c_p]),
     "spe_layernorm_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
@@ -98,3 +101,18 @@ def ptr(t):
 
 def launch_count():
     return int(lib().spe_launch_count())
+
+
+PROF_FAMILIES = ["gemm", "talking_softmax_fwd", "talking_softmax_bwd", "softmax", "layernorm", "matcher_lsap", "other"]
+
+
+def prof_enable(on):
+    lib().spe_prof_enable(1 if on else 0)
+
+
+def prof_collect():
+    """{family: (ms, work, launches)} since the last collect (synchronises the device)."""
+    n = lib().spe_prof_family_count()
+    ms, wk, ln = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+    lib().spe_prof_collect(ms, wk, ln)
+    return {PROF_FAMILIES[i]: (ms[i], wk[i], ln[i]) for i in range(n)}

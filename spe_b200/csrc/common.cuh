@@ -27,6 +27,18 @@ extern std::atomic<int64_t> g_spe_launches;
         if (e__ != cudaSuccess) SPE_FAIL("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+// ---- optional per-family device timing (bench.py roofline): CUDA events around launches on their stream ----
+enum { SPE_FAM_GEMM = 0, SPE_FAM_TALKING_FWD = 1, SPE_FAM_TALKING_BWD = 2, SPE_FAM_SOFTMAX = 3, SPE_FAM_LAYERNORM = 4,
+       SPE_FAM_MATCHER = 5, SPE_FAM_OTHER = 6, SPE_FAM_COUNT = 7 };
+extern bool g_spe_prof_on;
+int spe_prof_begin_(int fam, double work, cudaStream_t st, const char* tag = nullptr);
+void spe_prof_end_(int idx, cudaStream_t st);
+struct SpeProfScope {
+    int idx; cudaStream_t st;
+    SpeProfScope(int fam, double work, cudaStream_t s, const char* tag = nullptr) : idx(g_spe_prof_on ? spe_prof_begin_(fam, work, s, tag) : -1), st(s) {}
+    ~SpeProfScope() { if (idx >= 0) spe_prof_end_(idx, st); }
+};
+
 // after a <<<>>> launch
 #define SPE_LAUNCHED()                                                                     \
     do {                                                                                   \

@@ -407,6 +407,9 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     ep.vec_ok = vec ? 1 : 0;
 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    char tag[64];
+    if (g_spe_prof_on) snprintf(tag, sizeof(tag), "M%d N%d K%d b%d a%d b%d c%d", a->M, a->N, a->K, batch, a->a_major, a->b_major, a->c_dtype);
+    SpeProfScope prof(SPE_FAM_GEMM, 2.0 * a->M * a->N * (double)a->K * batch, st, tag);     // algorithmic flops
     if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, ep, batch, st);
     return dispatch_major<128, 3>(a->a_major, a->b_major, tA, tB, ep, batch, st);
 }

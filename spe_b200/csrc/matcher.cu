@@ -250,6 +250,7 @@ extern "C" __attribute__((visibility("default"))) int spe_lsap_batched(const flo
     const size_t smem = lsap_smem_bytes(use_small, mb);
     SPE_CHECK(smem <= 200 * 1024, "spe_lsap_batched: problem too large for shared memory (%zu B)", smem);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SpeProfScope prof(SPE_FAM_MATCHER, (double)B, st);     // work unit = images
     if (big <= 512) {
         static bool done = false;
         if (!done) { SPE_CUDA(cudaFuncSetAttribute(lsap_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }

@@ -679,6 +679,7 @@ extern "C" __attribute__((visibility("default"))) int spe_layernorm_fwd(const fl
     SPE_CHECK(x && w && b && rows > 0, "spe_layernorm_fwd: bad argument");
     SPE_CHECK(D % 4 == 0 && D <= 128 * LN_MAXCH, "spe_layernorm_fwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXCH);
     const int g = (int)((rows + 7) / 8 < (long long)spe_num_sms() * 8 ? (rows + 7) / 8 : (long long)spe_num_sms() * 8);
+    SpeProfScope prof(SPE_FAM_LAYERNORM, (double)rows * D * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)), ST(stream));
     layernorm_fwd_kernel<<<g, 256, 0, ST(stream)>>>(x, w, b, eps, rows, D, reinterpret_cast<uint16_t*>(y_bf16), y_f32, mean, rstd);
     SPE_LAUNCHED();
     return 0;
@@ -690,6 +691,7 @@ extern "C" __attribute__((visibility("default"))) int spe_layernorm_bwd(const vo
     SPE_CHECK(D % 4 == 0 && D <= 128 * LN_MAXCH, "spe_layernorm_bwd: unsupported D=%d", D);
     long long g = (rows + 7) / 8;
     if (g > (long long)spe_num_sms() * 2) g = (long long)spe_num_sms() * 2;
+    SpeProfScope prof(SPE_FAM_LAYERNORM, (double)rows * D * (8.0 + (dy_bf16 ? 2.0 : 0.0) + (dy_f32 ? 4.0 : 0.0)), ST(stream));
     layernorm_bwd_kernel<<<(int)g, 256, 2 * D * sizeof(float), ST(stream)>>>(reinterpret_cast<const uint16_t*>(dy_bf16), dy_f32, dres, x, w, mean, rstd,
                                                                                rows, D, dx, dw, db);
     SPE_LAUNCHED();
@@ -703,6 +705,7 @@ extern "C" __attribute__((visibility("default"))) int spe_softmax_fwd(const floa
     static bool done = false;
     if (!done) { SPE_CUDA(cudaFuncSetAttribute(softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
     if (pmean) SPE_CUDA(cudaMemsetAsync(pmean, 0, (size_t)B * Nq * Nk * 4, ST(stream)));
+    SpeProfScope prof(SPE_FAM_SOFTMAX, (double)B * H * Nq * Nk * 6.0, ST(stream));
     softmax_fwd_kernel<<<(unsigned)((long long)B * H * Nq), 256, (size_t)Nk * 4, ST(stream)>>>(S, reinterpret_cast<uint16_t*>(P), mask, H, Nq, Nk, ldS,
                                                                                                 ldP, pmean);
     SPE_LAUNCHED();
@@ -714,6 +717,7 @@ extern "C" __attribute__((visibility("default"))) int spe_softmax_bwd(const void
     SPE_CHECK((size_t)Nk * 8 <= 200 * 1024, "spe_softmax_bwd: Nk too large");
     static bool done = false;
     if (!done) { SPE_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
+    SpeProfScope prof(SPE_FAM_SOFTMAX, (double)B * H * Nq * Nk * 6.0, ST(stream));
     softmax_bwd_kernel<<<(unsigned)((long long)B * H * Nq), 256, (size_t)Nk * 8, ST(stream)>>>(reinterpret_cast<const uint16_t*>(P),
                                                                                                 reinterpret_cast<const uint16_t*>(dP),
                                                                                                 reinterpret_cast<uint16_t*>(dS), Nk, ldP);
@@ -726,6 +730,7 @@ static int talking_fwd_launch(const float* S, void* A, const float* Wl, const fl
                               int64_t ldS, int64_t ldA, cudaStream_t st) {
     const size_t smem = (size_t)H * ((Nk + 1) & ~1) * 4;
     SPE_CHECK(smem <= 200 * 1024, "spe_talking_softmax_fwd: H*Nk=%d*%d does not fit shared memory", H, Nk);
+    SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 6.0, st);   // algorithmic bytes: S f32 read + A bf16 write
     static bool done = false;
     if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
     talking_fwd_kernel<H><<<B * Nq, 256, smem, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, Nq, Nk, ldS, ldA);
@@ -766,6 +771,7 @@ static int talking_bwd_launch(const float* S, const void* dA, void* dS, const fl
     static bool done = false;
     if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); done = true; }
     const int grid = talking_bwd_grid(B, Nq);
+    SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * 8.0, st);   // S f32 read + dA bf16 read + dS bf16 write
     talking_bwd_kernel<H><<<grid, 256, smem_use, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, B * Nq,
                                                        Nq, Nk, ldS, ldA, ws);
     SPE_LAUNCHED();
