@@ -7,13 +7,18 @@
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) with the
 //     fp32 accumulator in TMEM; tcgen05.commit releases smem stages and signals the epilogue;
 //   * 4 warps read the accumulator with tcgen05.ld (32x32b), apply bias / activation / LayerScale /
-//     residual / head-interleave and store bf16 or fp32;
+//     residual and move every tile-shaped operand of the epilogue through shared memory with TMA
+//     (residual / aux_in: bulk tensor loads; C / aux_out: bulk tensor stores, 128B-swizzled slabs, one
+//     32-row slab per warp) so all epilogue HBM traffic is full-line and asynchronous;
+//   * split-K (small M*N, long K: the wgrad shapes) with TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32);
 //   * <=98 KB smem and BN TMEM columns per CTA -> 2 CTAs per SM, so one CTA's epilogue overlaps the
 //     other's main loop.
 //
 // Reference call sites replaced: see include/spe_b200.h (spe_gemm).
 #include "common.cuh"
 #include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -30,6 +35,9 @@ struct EpiParams {
     int M, N, K, batch2;
     int vec_ok;
     int a_m1, a_m2, b_m1, b_m2;   // 0 = operand broadcast over that batch dim (stride 0), else 1
+    int r_m1, r_m2;
+    int tma_io;                   // epilogue tiles through TMA (else direct per-thread global access)
+    int splits, kb_per_split;     // split-K: blockIdx.z = batch * splits + split
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,6 +72,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// 16-byte chunk j of row r inside a 32-row x 128-byte slab laid out with the TMA SWIZZLE_128B pattern
+__device__ __forceinline__ uint32_t slab_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
 // UMMA shared-memory descriptor, SWIZZLE_128B, version 1 (sm_100).  lbo/sbo in bytes.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -109,8 +128,10 @@ __device__ __forceinline__ float apply_act(float v, int act, float aux) {
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, const EpiParams ep) {
+__global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                                                           const __grid_constant__ CUtensorMap tmXi, const __grid_constant__ CUtensorMap tmXo,
+                                                           const EpiParams ep) {
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -123,12 +144,15 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1 + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int b1 = blockIdx.z / ep.batch2, b2 = blockIdx.z % ep.batch2;
-    const int num_kb = (ep.K + BK - 1) / BK;
+    const int zb = blockIdx.z / ep.splits, split = blockIdx.z % ep.splits;
+    const int b1 = zb / ep.batch2, b2 = zb % ep.batch2;
+    const int total_kb = (ep.K + BK - 1) / BK;
+    const int kb0 = split * ep.kb_per_split;
+    const int num_kb = min(ep.kb_per_split, total_kb - kb0);      // >= 1 by construction
 
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
 
@@ -140,6 +164,7 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(tfull, 1);
+        for (int w = 0; w < 4; ++w) mbar_init(tfull + 8 + 8 * w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -163,16 +188,16 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant
                 mbar_expect_tx(fb, A_BYTES + B_BYTES);
                 const uint32_t a_dst = smem_u32(sA + s * A_BYTES), b_dst = smem_u32(sB + s * B_BYTES);
                 if constexpr (!A_MN) {
-                    tma_load_4d(a_dst, &tmA, fb, kb * BK, m0, b2 * ep.a_m2, b1 * ep.a_m1);
+                    tma_load_4d(a_dst, &tmA, fb, (kb0 + kb) * BK, m0, b2 * ep.a_m2, b1 * ep.a_m1);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + c * 64, kb * BK, b2 * ep.a_m2, b1 * ep.a_m1);
+                    for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + c * 64, (kb0 + kb) * BK, b2 * ep.a_m2, b1 * ep.a_m1);
                 }
                 if constexpr (!B_MN) {
-                    tma_load_4d(b_dst, &tmB, fb, kb * BK, n0, b2 * ep.b_m2, b1 * ep.b_m1);
+                    tma_load_4d(b_dst, &tmB, fb, (kb0 + kb) * BK, n0, b2 * ep.b_m2, b1 * ep.b_m1);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + c * 64, kb * BK, b2 * ep.b_m2, b1 * ep.b_m1);
+                    for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + c * 64, (kb0 + kb) * BK, b2 * ep.b_m2, b1 * ep.b_m1);
                 }
             }
         }
@@ -204,6 +229,123 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant
     // ---------------- epilogue: all 4 warps, warp w owns TMEM lanes [32w, 32w+32) ----------------
     mbar_wait(tfull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    if (ep.tma_io) {
+        // ===== TMA epilogue: per warp, 64 accumulator columns at a time, every tile operand via 32-row x 128-byte
+        //       SWIZZLE_128B slabs in the (now idle) pipeline shared memory =====
+        uint8_t* wbase = smem + warp * 6 * 4096;                   // 6 slabs per warp: R0 R1 | Xi | C0 C1 | Xo
+        const uint32_t sR = smem_u32(wbase), sXi = sR + 8192, sC = sR + 12288, sXo = sR + 20480;
+        const uint32_t ebar = tfull + 8 + 8 * warp;
+        const int mrow = m0 + warp * 32;
+        const bool has_r = ep.residual != nullptr, has_xi = ep.aux_in != nullptr, has_xo = ep.aux_out != nullptr;
+        const bool c32 = ep.c_dtype == SPE_DT_F32;
+        const bool lead = split == 0;                              // split-K: bias / residual contributed once
+        uint32_t eph = 0;
+#pragma unroll 1
+        for (int sc = 0; sc < BN / 64; ++sc) {
+            const int nb = n0 + sc * 64;
+            if (nb >= ep.N) break;
+            const bool loads = (has_r && lead) || has_xi;
+            if (loads && lane == 0) {
+                const bool two = nb + 32 < ep.N;
+                uint32_t bytes = 0;
+                if (has_r && lead) bytes += two ? 8192 : 4096;
+                if (has_xi) bytes += 4096;
+                mbar_expect_tx(ebar, bytes);
+                if (has_r && lead) {
+                    tma_load_4d(sR, &tmR, ebar, nb, mrow, b2 * ep.r_m2, b1 * ep.r_m1);
+                    if (two) tma_load_4d(sR + 4096, &tmR, ebar, nb + 32, mrow, b2 * ep.r_m2, b1 * ep.r_m1);
+                }
+                if (has_xi) tma_load_4d(sXi, &tmXi, ebar, nb, mrow, 0, 0);
+            }
+            uint32_t r[64];
+            TMEM_LD_32x32b_X32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sc * 64), r);
+            TMEM_LD_32x32b_X32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sc * 64 + 32), (r + 32));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (loads) { mbar_wait(ebar, eph); eph ^= 1u; }
+            // previous super-chunk's bulk stores must have finished READING the store slabs
+            if (sc > 0) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {                           // 8 groups of 8 columns
+                const int n = nb + g * 8;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * ep.alpha;
+                if (n < ep.N) {                                      // (columns >= N are clipped by the TMA store)
+                    if (ep.bias && lead) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (n + j < ep.N) v[j] += __ldg(ep.bias + n + j);
+                    }
+                    if (has_xo) {
+                        uint4 o;
+                        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sXo + slab_off(lane, g)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                    }
+                    if (ep.act != SPE_ACT_NONE) {
+                        float ax[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        if (has_xi) {
+                            uint4 a;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sXi + slab_off(lane, g)));
+                            float2 t;
+                            t = unpack_bf16x2(a.x); ax[0] = t.x; ax[1] = t.y;
+                            t = unpack_bf16x2(a.y); ax[2] = t.x; ax[3] = t.y;
+                            t = unpack_bf16x2(a.z); ax[4] = t.x; ax[5] = t.y;
+                            t = unpack_bf16x2(a.w); ax[6] = t.x; ax[7] = t.y;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act, ax[j]);
+                    }
+                    if (ep.gamma) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (n + j < ep.N) v[j] *= __ldg(ep.gamma + n + j);
+                    }
+                    if (has_r && lead) {
+                        // fp32 residual: columns g*8..g*8+7 = slab (g/4), 16B chunks (g%4)*2, +1
+                        const uint32_t sl = sR + (g >> 2) * 4096;
+                        float4 r0, r1;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r0.x), "=f"(r0.y), "=f"(r0.z), "=f"(r0.w) : "r"(sl + slab_off(lane, (g & 3) * 2)));
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w) : "r"(sl + slab_off(lane, (g & 3) * 2 + 1)));
+                        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                    }
+                }
+                if (c32) {
+                    const uint32_t sl = sC + (g >> 2) * 4096;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + slab_off(lane, (g & 3) * 2)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + slab_off(lane, (g & 3) * 2 + 1)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+                } else {
+                    uint4 o;
+                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sC + slab_off(lane, g)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                if (ep.splits > 1) {
+                    tma_reduce_add_4d(&tmC, sC, nb, mrow, b2, b1);
+                    if (nb + 32 < ep.N) tma_reduce_add_4d(&tmC, sC + 4096, nb + 32, mrow, b2, b1);
+                } else if (c32) {
+                    tma_store_4d(&tmC, sC, nb, mrow, b2, b1);
+                    if (nb + 32 < ep.N) tma_store_4d(&tmC, sC + 4096, nb + 32, mrow, b2, b1);
+                } else {
+                    tma_store_4d(&tmC, sC, nb, mrow, b2, b1);
+                }
+                if (has_xo) tma_store_4d(&tmXo, sXo, nb, mrow, 0, 0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 1) {
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        }
+        return;
+    }
 
     const int m = m0 + warp * 32 + lane;
     const bool row_ok = m < ep.M;
@@ -350,27 +492,51 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int major, int rows, int K, int6
     return 0;
 }
 
+// epilogue tile operand [M, N] (row pitch ld elements), box = 32 rows x 128 bytes, SWIZZLE_128B. Returns 1 if not TMA-able.
+int make_tmap_io(CUtensorMap* tm, const void* ptr, bool f32, int M, int N, int64_t ld, int64_t sb1, int64_t sb2, int batch1, int batch2) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return 1;
+    const int es = f32 ? 4 : 2;
+    const int per16 = 16 / es;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || ld % per16 != 0) return 1;
+    const bool bc2 = batch2 > 1 && sb2 == 0, bc1 = batch1 > 1 && sb1 == 0;
+    if ((batch1 > 1 && !bc1 && sb1 % per16 != 0) || (batch2 > 1 && !bc2 && sb2 % per16 != 0)) return 1;
+    cuuint64_t gdim[4] = {(cuuint64_t)N, (cuuint64_t)M, bc2 ? 1 : (cuuint64_t)batch2, bc1 ? 1 : (cuuint64_t)batch1};
+    cuuint64_t gstr[3];
+    gstr[0] = (cuuint64_t)ld * es;
+    gstr[1] = (batch2 > 1 && !bc2 ? (cuuint64_t)sb2 : (cuuint64_t)ld * M) * es;
+    gstr[2] = (batch1 > 1 && !bc1 ? (cuuint64_t)sb1 : (cuuint64_t)ld * M) * es;
+    cuuint32_t box[4] = {(cuuint32_t)(128 / es), 32, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+struct IoMaps { CUtensorMap C, R, Xi, Xo; };
+
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& tA, const CUtensorMap& tB, const EpiParams& ep, int batch, cudaStream_t st) {
-    constexpr size_t SMEM = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+int launch(const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const EpiParams& ep, int batch, cudaStream_t st) {
+    constexpr size_t SMEM = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1 + 4) * 8 + 16 + 1024;
+    static_assert((size_t)STAGES * (BM * BK * 2 + BN * BK * 2) >= 4 * 6 * 4096, "epilogue slabs must fit in the pipeline smem");
     static bool attr_done = false;
     auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
     if (!attr_done) {
         SPE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_done = true;
     }
-    dim3 grid((ep.N + BN - 1) / BN, (ep.M + BM - 1) / BM, batch);
-    kfn<<<grid, 128, SMEM, st>>>(tA, tB, ep);
+    dim3 grid((ep.N + BN - 1) / BN, (ep.M + BM - 1) / BM, batch * ep.splits);
+    kfn<<<grid, 128, SMEM, st>>>(tA, tB, io.C, io.R, io.Xi, io.Xo, ep);
     SPE_LAUNCHED();
     return 0;
 }
 
 template <int BN, int STAGES>
-int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB, const EpiParams& ep, int batch, cudaStream_t st) {
-    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_K) return launch<BN, STAGES, false, false>(tA, tB, ep, batch, st);
-    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_MN) return launch<BN, STAGES, false, true>(tA, tB, ep, batch, st);
-    if (am == SPE_MAJOR_MN && bm == SPE_MAJOR_K) return launch<BN, STAGES, true, false>(tA, tB, ep, batch, st);
-    return launch<BN, STAGES, true, true>(tA, tB, ep, batch, st);
+int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const EpiParams& ep, int batch, cudaStream_t st) {
+    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_K) return launch<BN, STAGES, false, false>(tA, tB, io, ep, batch, st);
+    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_MN) return launch<BN, STAGES, false, true>(tA, tB, io, ep, batch, st);
+    if (am == SPE_MAJOR_MN && bm == SPE_MAJOR_K) return launch<BN, STAGES, true, false>(tA, tB, io, ep, batch, st);
+    return launch<BN, STAGES, true, true>(tA, tB, io, ep, batch, st);
 }
 
 }  // namespace
@@ -407,9 +573,36 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     ep.vec_ok = vec ? 1 : 0;
 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // ---- epilogue tiles through TMA when every tile operand is 16-byte regular (else direct global access)
+    IoMaps io;
+    memset(&io, 0, sizeof(io));
+    const bool cf32 = a->c_dtype == SPE_DT_F32;
+    bool tma_io = a->split == 0 && getenv("SPE_GEMM_DIRECT_EPILOGUE") == nullptr;
+    if (tma_io && (a->aux_in || a->aux_out) && batch != 1) tma_io = false;
+    if (tma_io && make_tmap_io(&io.C, a->C, cf32, a->M, a->N, a->ldc, a->c_sb1, a->c_sb2, a->batch1, a->batch2)) tma_io = false;
+    if (tma_io && a->residual && make_tmap_io(&io.R, a->residual, true, a->M, a->N, a->ldr, a->r_sb1, a->r_sb2, a->batch1, a->batch2)) tma_io = false;
+    if (tma_io && a->aux_in && make_tmap_io(&io.Xi, a->aux_in, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
+    if (tma_io && a->aux_out && make_tmap_io(&io.Xo, a->aux_out, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
+    // in-place accumulate (residual == C): the TMA path loads the residual slab before storing the same tile -> fine
+    ep.tma_io = tma_io ? 1 : 0;
+    ep.r_m1 = (a->batch1 > 1 && a->r_sb1 == 0) ? 0 : 1; ep.r_m2 = (a->batch2 > 1 && a->r_sb2 == 0) ? 0 : 1;
+    // ---- split-K: few output tiles but a long reduction (wgrad).  fp32 contiguous C, no activation / aux / gamma.
+    const int total_kb = (a->K + BK - 1) / BK;
+    int splits = 1;
+    const long long tiles = (long long)((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN) * batch;
+    if (tma_io && cf32 && batch == 1 && a->act == SPE_ACT_NONE && !a->aux_in && !a->aux_out && !a->gamma && a->residual != (const float*)a->C &&
+        a->ldc == a->N && tiles * 2 <= spe_num_sms() && total_kb >= 8 && getenv("SPE_GEMM_NO_SPLITK") == nullptr) {
+        splits = (int)((2LL * spe_num_sms() + tiles - 1) / tiles);
+        if (splits > total_kb / 4) splits = total_kb / 4;
+        if (splits < 1) splits = 1;
+    }
+    ep.kb_per_split = (total_kb + splits - 1) / splits;
+    splits = (total_kb + ep.kb_per_split - 1) / ep.kb_per_split;      // no empty split
+    ep.splits = splits;
+    if (splits > 1) SPE_CUDA(cudaMemsetAsync(a->C, 0, (size_t)a->M * a->N * 4, st));
     char tag[64];
     if (g_spe_prof_on) snprintf(tag, sizeof(tag), "M%d N%d K%d b%d a%d b%d c%d", a->M, a->N, a->K, batch, a->a_major, a->b_major, a->c_dtype);
     SpeProfScope prof(SPE_FAM_GEMM, 2.0 * a->M * a->N * (double)a->K * batch, st, tag);     // algorithmic flops
-    if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, ep, batch, st);
-    return dispatch_major<128, 3>(a->a_major, a->b_major, tA, tB, ep, batch, st);
+    if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, io, ep, batch, st);
+    return dispatch_major<128, 3>(a->a_major, a->b_major, tA, tB, io, ep, batch, st);
 }

@@ -192,106 +192,131 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const uint16_t* __rest
 
 // ------------------------------------------------------------------------------------------------
 // talking-heads mix -> softmax -> mix   (cait.py:381-386)
-//   one CTA per (b, q); the H x Nk slab of logits lives in shared memory; 2 adjacent keys per thread
+//   ONE WARP PER (b, q) ROW, streaming: no block-level barriers, no staging of the H x Nk slab.
+//   fwd : sweep A = logits L (head mix) with an online (max, sum) per mixed head; sweep B re-reads S (L2-hot),
+//         recomputes L, P = exp(L-m)/z, second head mix, bf16 store.
+//   bwd : sweep A as above; sweep B: P, dP = Ww^T dA, rho = sum_j P dP (+ dWw, dbw partials);
+//         sweep C: dL = P (dP - rho), dS = Wl^T dL (+ dWl, dbl partials).  Parameter-gradient partials stay in
+//         registers across all rows of a CTA and are reduced once at the end (deterministic two-stage reduction).
+//   The H x H mixes are FP32 FMAs against weights broadcast from shared memory (FP32/MUFU bound).
 // ------------------------------------------------------------------------------------------------
+template <int H>
+struct MixW {
+    float Wl[H * H], Ww[H * H], bl[H], bw[H];
+};
+
+template <int H>
+__device__ __forceinline__ void load_mix(MixW<H>* sm, const float* Wl, const float* bl, const float* Ww, const float* bw) {
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) { sm->Wl[i] = Wl[i]; sm->Ww[i] = Ww[i]; }
+    if (threadIdx.x < H) { sm->bl[threadIdx.x] = bl[threadIdx.x]; sm->bw[threadIdx.x] = bw ? bw[threadIdx.x] : 0.f; }
+    __syncthreads();
+}
+
+// sweep A: per-row softmax statistics of the mixed logits.  Returns m[g] (row max) and iz[g] (1/sum).
+template <int H>
+__device__ __forceinline__ void talking_stats(const float* __restrict__ Sb, long long hS, int Nk, const MixW<H>* w, int lane, float* m, float* iz) {
+    float z[H];
+#pragma unroll
+    for (int g = 0; g < H; ++g) { m[g] = -INFINITY; z[g] = 0.f; }
+    for (int j = 4 * lane; j < Nk; j += 128) {
+        float s[H][4];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float4 t = *reinterpret_cast<const float4*>(Sb + h * hS + j);
+            s[h][0] = t.x; s[h][1] = t.y; s[h][2] = t.z; s[h][3] = t.w;
+        }
+        const int nv = min(4, Nk - j);
+#pragma unroll
+        for (int g = 0; g < H; ++g) {
+            float a[4] = {w->bl[g], w->bl[g], w->bl[g], w->bl[g]};
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float wv = w->Wl[g * H + h];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) a[c] += wv * s[h][c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c >= nv) a[c] = -INFINITY;
+            const float mn = fmaxf(m[g], fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])));
+            z[g] = z[g] * __expf(m[g] - mn) + ((__expf(a[0] - mn) + __expf(a[1] - mn)) + (__expf(a[2] - mn) + __expf(a[3] - mn)));
+            m[g] = mn;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < H; ++g) {
+        const float M = warp_max(m[g]);
+        const float zz = warp_sum(m[g] == -INFINITY ? 0.f : z[g] * __expf(m[g] - M));
+        m[g] = M;
+        iz[g] = 1.f / zz;
+    }
+}
+
 template <int H>
 __global__ void __launch_bounds__(256) talking_fwd_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
                                                           const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
-                                                          int Nq, int Nk, long long ldS, long long ldA) {
-    extern __shared__ float sm[];
-    float* L = sm;                                   // [H][Nkp]
-    const int Nkp = (Nk + 1) & ~1;
-    __shared__ float sWl[H * H], sWw[H * H], sbl[H], sbw[H];
-    __shared__ float redm[H][8], stat[H];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < H * H; i += 256) { sWl[i] = Wl[i]; sWw[i] = Ww[i]; }
-    if (tid < H) { sbl[tid] = bl[tid]; sbw[tid] = bw[tid]; }
-    __syncthreads();
-    const int b = blockIdx.x / Nq, q = blockIdx.x % Nq;
-    const float* Sb = S + ((long long)b * H * Nq + q) * ldS;          // head h at + h*Nq*ldS
-    uint16_t* Ab = A + ((long long)b * H * Nq + q) * ldA;
+                                                          int rows_total, int Nq, int Nk, long long ldS, long long ldA) {
+    __shared__ MixW<H> w;
+    load_mix<H>(&w, Wl, bl, Ww, bw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
-
-    float mx[H];
+    for (int rowi = blockIdx.x * 8 + warp; rowi < rows_total; rowi += gridDim.x * 8) {
+        const int b = rowi / Nq, q = rowi % Nq;
+        const float* Sb = S + ((long long)b * H * Nq + q) * ldS;
+        uint16_t* Ab = A + ((long long)b * H * Nq + q) * ldA;
+        float m[H], iz[H];
+        talking_stats<H>(Sb, hS, Nk, &w, lane, m, iz);
+        for (int j = 4 * lane; j < ldA; j += 128) {
+            if (j >= Nk) {                                  // keep the padding columns [Nk, ldA) zero
 #pragma unroll
-    for (int g = 0; g < H; ++g) mx[g] = -INFINITY;
-    for (int j = 2 * tid; j < Nk; j += 512) {
-        const bool two = (j + 1 < Nk);
-        float s0[H], s1[H];
+                for (int o = 0; o < H; ++o) *reinterpret_cast<uint2*>(Ab + o * hA + j) = make_uint2(0u, 0u);
+                continue;
+            }
+            float s[H][4], p[H][4];
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-            if (two) { const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j); s0[h] = t.x; s1[h] = t.y; }
-            else { s0[h] = Sb[h * hS + j]; s1[h] = -INFINITY; }
-        }
+            for (int h = 0; h < H; ++h) {
+                const float4 t = *reinterpret_cast<const float4*>(Sb + h * hS + j);
+                s[h][0] = t.x; s[h][1] = t.y; s[h][2] = t.z; s[h][3] = t.w;
+            }
+            const int nv = min(4, Nk - j);
 #pragma unroll
-        for (int g = 0; g < H; ++g) {
-            float a0 = sbl[g], a1 = sbl[g];
+            for (int g = 0; g < H; ++g) {
+                float a[4] = {w.bl[g], w.bl[g], w.bl[g], w.bl[g]};
 #pragma unroll
-            for (int h = 0; h < H; ++h) { const float wv = sWl[g * H + h]; a0 += wv * s0[h]; if (two) a1 += wv * s1[h]; }
-            if (!two) a1 = -INFINITY;
-            L[g * Nkp + j] = a0; L[g * Nkp + j + 1] = a1;
-            mx[g] = fmaxf(mx[g], fmaxf(a0, a1));
-        }
-    }
+                for (int h = 0; h < H; ++h) {
+                    const float wv = w.Wl[g * H + h];
 #pragma unroll
-    for (int g = 0; g < H; ++g) { const float m = warp_max(mx[g]); if (lane == 0) redm[g][warp] = m; }
-    __syncthreads();
-    if (tid < H) { float m = redm[tid][0]; for (int w2 = 1; w2 < 8; ++w2) m = fmaxf(m, redm[tid][w2]); stat[tid] = m; }
-    __syncthreads();
-    float sum[H];
+                    for (int c = 0; c < 4; ++c) a[c] += wv * s[h][c];
+                }
 #pragma unroll
-    for (int g = 0; g < H; ++g) { mx[g] = stat[g]; sum[g] = 0.f; }
-    for (int j = 2 * tid; j < Nk; j += 512) {
+                for (int c = 0; c < 4; ++c) p[g][c] = __expf(a[c] - m[g]) * iz[g];
+            }
 #pragma unroll
-        for (int g = 0; g < H; ++g) {
-            const float e0 = __expf(L[g * Nkp + j] - mx[g]), e1 = __expf(L[g * Nkp + j + 1] - mx[g]);   // exp(-inf)=0 for the pad
-            L[g * Nkp + j] = e0; L[g * Nkp + j + 1] = e1;
-            sum[g] += e0 + e1;
-        }
-    }
-    __syncthreads();
+            for (int o = 0; o < H; ++o) {
+                float a[4] = {w.bw[o], w.bw[o], w.bw[o], w.bw[o]};
 #pragma unroll
-    for (int g = 0; g < H; ++g) { const float s = warp_sum(sum[g]); if (lane == 0) redm[g][warp] = s; }
-    __syncthreads();
-    if (tid < H) { float s = 0.f; for (int w2 = 0; w2 < 8; ++w2) s += redm[tid][w2]; stat[tid] = 1.f / s; }
-    __syncthreads();
-    float inv[H];
+                for (int g = 0; g < H; ++g) {
+                    const float wv = w.Ww[o * H + g];
 #pragma unroll
-    for (int g = 0; g < H; ++g) inv[g] = stat[g];
-    for (int j = 2 * tid; j < Nk; j += 512) {
-        float p0[H], p1[H];
+                    for (int c = 0; c < 4; ++c) a[c] += wv * p[g][c];
+                }
 #pragma unroll
-        for (int g = 0; g < H; ++g) { p0[g] = L[g * Nkp + j] * inv[g]; p1[g] = L[g * Nkp + j + 1] * inv[g]; }
-#pragma unroll
-        for (int o = 0; o < H; ++o) {
-            float a0 = sbw[o], a1 = sbw[o];
-#pragma unroll
-            for (int g = 0; g < H; ++g) { const float wv = sWw[o * H + g]; a0 += wv * p0[g]; a1 += wv * p1[g]; }
-            if (j + 1 < Nk) *reinterpret_cast<uint32_t*>(Ab + o * hA + j) = pack_bf16x2(a0, a1);
-            else Ab[o * hA + j] = f_to_bf16(a0);
+                for (int c = 0; c < 4; ++c) if (c >= nv) a[c] = 0.f;
+                *reinterpret_cast<uint2*>(Ab + o * hA + j) = make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
+            }
         }
     }
-    // zero the padding columns [Nk, ldA) so K-tail TMA reads see zeros
-    for (int o = 0; o < H; ++o)
-        for (int j = Nk + tid; j < ldA; j += 256) Ab[o * hA + j] = 0;
 }
 
-// backward: dA (bf16) -> dS (bf16), parameter-gradient partials per CTA in `part` [gridDim.x][2*H*H + 2*H]
+// backward: dA (bf16) -> dS (bf16, may alias dA), parameter-gradient partials per CTA in `part` [gridDim.x][2*H*H + 2*H]
 template <int H>
-__global__ void __launch_bounds__(256, 1) talking_bwd_kernel(const float* __restrict__ S, const uint16_t* __restrict__ dA, uint16_t* __restrict__ dS,
+__global__ void __launch_bounds__(256, 1) talking_bwd_kernel(const float* __restrict__ S, const uint16_t* dA, uint16_t* dS,
                                                              const float* __restrict__ Wl, const float* __restrict__ bl, const float* __restrict__ Ww,
                                                              int rows_total, int Nq, int Nk, long long ldS, long long ldA, float* __restrict__ part) {
-    extern __shared__ float sm[];
-    const int Nkp = (Nk + 1) & ~1;
-    float* Ss = sm;                                   // [H][Nkp] raw logits
-    float* Ps = Ss + (size_t)H * Nkp;                 // [H][Nkp] L -> e -> P
-    float* Ds = Ps + (size_t)H * Nkp;                 // [H][Nkp] dP
-    __shared__ float sWl[H * H], sWw[H * H], sbl[H];
-    __shared__ float redm[H][8], stat[H];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < H * H; i += 256) { sWl[i] = Wl[i]; sWw[i] = Ww[i]; }
-    if (tid < H) sbl[tid] = bl[tid];
-    __syncthreads();
+    __shared__ MixW<H> w;
+    constexpr int NP = 2 * H * H + 2 * H;
+    __shared__ float redbuf[8][NP];
+    load_mix<H>(&w, Wl, bl, Ww, nullptr);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
 
     float aWw[H][H], aWl[H][H], abw[H], abl[H];       // per-thread partial parameter gradients (persist over rows)
@@ -300,138 +325,104 @@ __global__ void __launch_bounds__(256, 1) talking_bwd_kernel(const float* __rest
 #pragma unroll
         for (int c = 0; c < H; ++c) { aWw[a][c] = 0.f; aWl[a][c] = 0.f; } }
 
-    for (int rowi = blockIdx.x; rowi < rows_total; rowi += gridDim.x) {
+    for (int rowi = blockIdx.x * 8 + warp; rowi < rows_total; rowi += gridDim.x * 8) {
         const int b = rowi / Nq, q = rowi % Nq;
         const float* Sb = S + ((long long)b * H * Nq + q) * ldS;
         const uint16_t* dAb = dA + ((long long)b * H * Nq + q) * ldA;
         uint16_t* dSb = dS + ((long long)b * H * Nq + q) * ldA;
-        float mx[H];
+        float m[H], iz[H], rho[H];
+        talking_stats<H>(Sb, hS, Nk, &w, lane, m, iz);
+        // ---- sweep B: rho[g] = sum_j P[g] dP[g];  dWw += dA (x) P;  dbw += dA       (2 keys per lane per step)
 #pragma unroll
-        for (int g = 0; g < H; ++g) mx[g] = -INFINITY;
-        // pass 1: S -> smem, L -> smem, running max
-        for (int j = 2 * tid; j < Nk; j += 512) {
-            const bool two = (j + 1 < Nk);
-            float s0[H], s1[H];
+        for (int g = 0; g < H; ++g) rho[g] = 0.f;
+        for (int j = 2 * lane; j < Nk; j += 64) {
+            const bool two = j + 1 < Nk;
+            float s[H][2], d[H][2];
 #pragma unroll
             for (int h = 0; h < H; ++h) {
-                if (two) { const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j); s0[h] = t.x; s1[h] = t.y; }
-                else { s0[h] = Sb[h * hS + j]; s1[h] = 0.f; }
-                Ss[h * Nkp + j] = s0[h]; Ss[h * Nkp + j + 1] = s1[h];
+                const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j);
+                s[h][0] = t.x; s[h][1] = t.y;
+                const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + h * hA + j));
+                d[h][0] = u.x; d[h][1] = two ? u.y : 0.f;
+                abw[h] += d[h][0] + d[h][1];
             }
 #pragma unroll
             for (int g = 0; g < H; ++g) {
-                float a0 = sbl[g], a1 = sbl[g];
+                float a0 = w.bl[g], a1 = w.bl[g], x0 = 0.f, x1 = 0.f;
 #pragma unroll
-                for (int h = 0; h < H; ++h) { const float wv = sWl[g * H + h]; a0 += wv * s0[h]; a1 += wv * s1[h]; }
-                if (!two) a1 = -INFINITY;
-                Ps[g * Nkp + j] = a0; Ps[g * Nkp + j + 1] = a1;
-                mx[g] = fmaxf(mx[g], fmaxf(a0, a1));
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < H; ++g) { const float m = warp_max(mx[g]); if (lane == 0) redm[g][warp] = m; }
-        __syncthreads();
-        if (tid < H) { float m = redm[tid][0]; for (int w2 = 1; w2 < 8; ++w2) m = fmaxf(m, redm[tid][w2]); stat[tid] = m; }
-        __syncthreads();
-        float sum[H];
-#pragma unroll
-        for (int g = 0; g < H; ++g) { mx[g] = stat[g]; sum[g] = 0.f; }
-        for (int j = 2 * tid; j < Nk; j += 512) {
-#pragma unroll
-            for (int g = 0; g < H; ++g) {
-                const float e0 = __expf(Ps[g * Nkp + j] - mx[g]), e1 = __expf(Ps[g * Nkp + j + 1] - mx[g]);
-                Ps[g * Nkp + j] = e0; Ps[g * Nkp + j + 1] = e1;
-                sum[g] += e0 + e1;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int g = 0; g < H; ++g) { const float s = warp_sum(sum[g]); if (lane == 0) redm[g][warp] = s; }
-        __syncthreads();
-        if (tid < H) { float s = 0.f; for (int w2 = 0; w2 < 8; ++w2) s += redm[tid][w2]; stat[tid] = 1.f / s; }
-        __syncthreads();
-        // pass 3: P, dP = Ww^T dA, rho = sum_j P dP, dWw += dA (x) P, dbw += dA
-        float rho[H];
-#pragma unroll
-        for (int g = 0; g < H; ++g) { sum[g] = stat[g]; rho[g] = 0.f; }
-        for (int j = 2 * tid; j < Nk; j += 512) {
-            const bool two = (j + 1 < Nk);
-            float d0[H], d1[H], p0[H], p1[H];
-#pragma unroll
-            for (int o = 0; o < H; ++o) {
-                if (two) { const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + o * hA + j)); d0[o] = t.x; d1[o] = t.y; }
-                else { d0[o] = bf16_to_f(dAb[o * hA + j]); d1[o] = 0.f; }
-                abw[o] += d0[o] + d1[o];
-            }
-#pragma unroll
-            for (int g = 0; g < H; ++g) {
-                p0[g] = Ps[g * Nkp + j] * sum[g]; p1[g] = Ps[g * Nkp + j + 1] * sum[g];
-                Ps[g * Nkp + j] = p0[g]; Ps[g * Nkp + j + 1] = p1[g];
-                float x0 = 0.f, x1 = 0.f;
-#pragma unroll
-                for (int o = 0; o < H; ++o) {
-                    const float wv = sWw[o * H + g];
-                    x0 += wv * d0[o]; x1 += wv * d1[o];
-                    aWw[o][g] += d0[o] * p0[g] + d1[o] * p1[g];
+                for (int h = 0; h < H; ++h) {
+                    const float wl = w.Wl[g * H + h], ww = w.Ww[h * H + g];
+                    a0 += wl * s[h][0]; a1 += wl * s[h][1];
+                    x0 += ww * d[h][0]; x1 += ww * d[h][1];
                 }
-                Ds[g * Nkp + j] = x0; Ds[g * Nkp + j + 1] = x1;
-                rho[g] += p0[g] * x0 + p1[g] * x1;
+                const float p0 = __expf(a0 - m[g]) * iz[g], p1 = two ? __expf(a1 - m[g]) * iz[g] : 0.f;
+                rho[g] += p0 * x0 + p1 * x1;
+#pragma unroll
+                for (int o = 0; o < H; ++o) aWw[o][g] += d[o][0] * p0 + d[o][1] * p1;
             }
         }
-        __syncthreads();
 #pragma unroll
-        for (int g = 0; g < H; ++g) { const float s = warp_sum(rho[g]); if (lane == 0) redm[g][warp] = s; }
-        __syncthreads();
-        if (tid < H) { float s = 0.f; for (int w2 = 0; w2 < 8; ++w2) s += redm[tid][w2]; stat[tid] = s; }
-        __syncthreads();
+        for (int g = 0; g < H; ++g) rho[g] = warp_sum(rho[g]);
+        // ---- sweep C: dL = P (dP - rho);  dS = Wl^T dL;  dWl += dL (x) S;  dbl += dL
+        for (int j = 2 * lane; j < ldA; j += 64) {
+            if (j >= Nk) {
 #pragma unroll
-        for (int g = 0; g < H; ++g) rho[g] = stat[g];
-        // pass 4: dL = P (dP - rho); dS = Wl^T dL; dWl += dL (x) S; dbl += dL
-        for (int j = 2 * tid; j < Nk; j += 512) {
-            float l0[H], l1[H];
-#pragma unroll
-            for (int g = 0; g < H; ++g) {
-                l0[g] = Ps[g * Nkp + j] * (Ds[g * Nkp + j] - rho[g]);
-                l1[g] = Ps[g * Nkp + j + 1] * (Ds[g * Nkp + j + 1] - rho[g]);
-                abl[g] += l0[g] + l1[g];
+                for (int h = 0; h < H; ++h) *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = 0u;
+                continue;
             }
+            const bool two = j + 1 < Nk;
+            float s[H][2], d[H][2], l[H][2];
 #pragma unroll
             for (int h = 0; h < H; ++h) {
-                const float s0 = Ss[h * Nkp + j], s1 = Ss[h * Nkp + j + 1];
+                const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j);
+                s[h][0] = t.x; s[h][1] = t.y;
+                const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + h * hA + j));
+                d[h][0] = u.x; d[h][1] = two ? u.y : 0.f;
+            }
+#pragma unroll
+            for (int g = 0; g < H; ++g) {
+                float a0 = w.bl[g], a1 = w.bl[g], x0 = 0.f, x1 = 0.f;
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float wl = w.Wl[g * H + h], ww = w.Ww[h * H + g];
+                    a0 += wl * s[h][0]; a1 += wl * s[h][1];
+                    x0 += ww * d[h][0]; x1 += ww * d[h][1];
+                }
+                const float p0 = __expf(a0 - m[g]) * iz[g], p1 = two ? __expf(a1 - m[g]) * iz[g] : 0.f;
+                l[g][0] = p0 * (x0 - rho[g]); l[g][1] = p1 * (x1 - rho[g]);
+                abl[g] += l[g][0] + l[g][1];
+            }
+            // all dA reads of this (row, j) happened above -> safe to overwrite in place when dS aliases dA
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
                 float x0 = 0.f, x1 = 0.f;
+                const float s0 = s[h][0], s1 = two ? s[h][1] : 0.f;
 #pragma unroll
                 for (int g = 0; g < H; ++g) {
-                    const float wv = sWl[g * H + h];
-                    x0 += wv * l0[g]; x1 += wv * l1[g];
-                    aWl[g][h] += l0[g] * s0 + l1[g] * s1;
+                    const float wl = w.Wl[g * H + h];
+                    x0 += wl * l[g][0]; x1 += wl * l[g][1];
+                    aWl[g][h] += l[g][0] * s0 + l[g][1] * s1;
                 }
-                if (j + 1 < Nk) *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = pack_bf16x2(x0, x1);
-                else dSb[h * hA + j] = f_to_bf16(x0);
+                *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = pack_bf16x2(x0, two ? x1 : 0.f);
             }
         }
-        for (int h = 0; h < H; ++h)
-            for (int j = Nk + tid; j < ldA; j += 256) dSb[h * hA + j] = 0;
-        __syncthreads();
     }
     // CTA reduction of the partials -> part[blockIdx.x][...]: layout dWl[H*H], dbl[H], dWw[H*H], dbw[H]
-    float* redbuf = sm;          // reuse: [8 warps][2*H*H+2*H]
-    constexpr int NP = 2 * H * H + 2 * H;
-    __syncthreads();
 #pragma unroll
     for (int a = 0; a < H; ++a) {
 #pragma unroll
         for (int c = 0; c < H; ++c) {
             const float v1 = warp_sum(aWl[a][c]), v2 = warp_sum(aWw[a][c]);
-            if (lane == 0) { redbuf[warp * NP + a * H + c] = v1; redbuf[warp * NP + H * H + H + a * H + c] = v2; }
+            if (lane == 0) { redbuf[warp][a * H + c] = v1; redbuf[warp][H * H + H + a * H + c] = v2; }
         }
         const float v3 = warp_sum(abl[a]), v4 = warp_sum(abw[a]);
-        if (lane == 0) { redbuf[warp * NP + H * H + a] = v3; redbuf[warp * NP + 2 * H * H + H + a] = v4; }
+        if (lane == 0) { redbuf[warp][H * H + a] = v3; redbuf[warp][2 * H * H + H + a] = v4; }
     }
     __syncthreads();
-    for (int i = tid; i < NP; i += 256) {
-        float s = 0.f;
-        for (int w2 = 0; w2 < 8; ++w2) s += redbuf[w2 * NP + i];
-        part[(long long)blockIdx.x * NP + i] = s;
+    for (int i = threadIdx.x; i < NP; i += 256) {
+        float sum = 0.f;
+        for (int w2 = 0; w2 < 8; ++w2) sum += redbuf[w2][i];
+        part[(long long)blockIdx.x * NP + i] = sum;
     }
 }
 
@@ -725,15 +716,17 @@ extern "C" __attribute__((visibility("default"))) int spe_softmax_bwd(const void
     return 0;
 }
 
+static int talking_grid(int B, int Nq, int per_sm) {
+    const long long blocks = ((long long)B * Nq + 7) / 8;
+    const long long cap = (long long)spe_num_sms() * per_sm;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
 template <int H>
 static int talking_fwd_launch(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, int B, int Nq, int Nk,
                               int64_t ldS, int64_t ldA, cudaStream_t st) {
-    const size_t smem = (size_t)H * ((Nk + 1) & ~1) * 4;
-    SPE_CHECK(smem <= 200 * 1024, "spe_talking_softmax_fwd: H*Nk=%d*%d does not fit shared memory", H, Nk);
     SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 6.0, st);   // algorithmic bytes: S f32 read + A bf16 write
-    static bool done = false;
-    if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
-    talking_fwd_kernel<H><<<B * Nq, 256, smem, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, Nq, Nk, ldS, ldA);
+    talking_fwd_kernel<H><<<talking_grid(B, Nq, 4), 256, 0, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, B * Nq, Nq, Nk, ldS, ldA);
     SPE_LAUNCHED();
     return 0;
 }
@@ -741,7 +734,7 @@ static int talking_fwd_launch(const float* S, void* A, const float* Wl, const fl
 extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, int B, int H,
                                        int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream) {
     SPE_CHECK(S && A && Wl && bl && Ww && bw && B > 0 && Nq > 0 && Nk > 0, "spe_talking_softmax_fwd: bad argument");
-    SPE_CHECK(ldS % 2 == 0 && ldA % 2 == 0 && ldS >= Nk && ldA >= Nk, "spe_talking_softmax_fwd: leading dims must be even and >= Nk");
+    SPE_CHECK(ldS % 4 == 0 && ldA % 4 == 0 && ldS >= ((Nk + 3) & ~3) && ldA >= ((Nk + 3) & ~3), "spe_talking_softmax_fwd: leading dims must be multiples of 4 and >= Nk rounded up to 4");
     switch (H) {
         case 2: return talking_fwd_launch<2>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
         case 4: return talking_fwd_launch<4>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
@@ -750,11 +743,7 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(co
     }
 }
 
-static int talking_bwd_grid(int B, int Nq) {
-    long long rows = (long long)B * Nq;
-    long long g = spe_num_sms();
-    return (int)(rows < g ? rows : g);
-}
+static int talking_bwd_grid(int B, int Nq) { return talking_grid(B, Nq, 1); }
 
 extern "C" __attribute__((visibility("default"))) int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk) {
     (void)Nk;
@@ -764,17 +753,13 @@ extern "C" __attribute__((visibility("default"))) int64_t spe_talking_softmax_bw
 template <int H>
 static int talking_bwd_launch(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, int B, int Nq, int Nk,
                               int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* ws, cudaStream_t st) {
-    const size_t smem = (size_t)3 * H * ((Nk + 1) & ~1) * 4;
-    SPE_CHECK(smem <= 220 * 1024, "spe_talking_softmax_bwd: H*Nk=%d*%d does not fit shared memory", H, Nk);
-    SPE_CHECK(smem >= (size_t)8 * (2 * H * H + 2 * H) * 4 || true, "unreachable");
-    const size_t smem_use = smem < (size_t)8 * (2 * H * H + 2 * H) * 4 ? (size_t)8 * (2 * H * H + 2 * H) * 4 : smem;
-    static bool done = false;
-    if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); done = true; }
     const int grid = talking_bwd_grid(B, Nq);
-    SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * 8.0, st);   // S f32 read + dA bf16 read + dS bf16 write
-    talking_bwd_kernel<H><<<grid, 256, smem_use, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, B * Nq,
-                                                       Nq, Nk, ldS, ldA, ws);
-    SPE_LAUNCHED();
+    {
+        SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * 8.0, st);   // S f32 read + dA bf16 read + dS bf16 write
+        talking_bwd_kernel<H><<<grid, 256, 0, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, B * Nq, Nq, Nk,
+                                                    ldS, ldA, ws);
+        SPE_LAUNCHED();
+    }
     const int NP = 2 * H * H + 2 * H;
     talking_bwd_finalize_kernel<<<(NP + 127) / 128, 128, 0, st>>>(ws, grid, H, dWl, dbl, dWw, dbw);
     SPE_LAUNCHED();
@@ -786,7 +771,7 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd(co
                                        float* workspace, int64_t workspace_floats, void* stream) {
     (void)bw;
     SPE_CHECK(S && dA && dS && Wl && bl && Ww && dWl && dbl && dWw && dbw && workspace, "spe_talking_softmax_bwd: null argument");
-    SPE_CHECK(ldS % 2 == 0 && ldA % 2 == 0 && ldS >= Nk && ldA >= Nk, "spe_talking_softmax_bwd: leading dims must be even and >= Nk");
+    SPE_CHECK(ldS % 4 == 0 && ldA % 4 == 0 && ldS >= ((Nk + 3) & ~3) && ldA >= ((Nk + 3) & ~3), "spe_talking_softmax_bwd: leading dims must be multiples of 4 and >= Nk rounded up to 4");
     SPE_CHECK(workspace_floats >= spe_talking_softmax_bwd_workspace(B, H, Nq, Nk), "spe_talking_softmax_bwd: workspace too small");
     switch (H) {
         case 2: return talking_bwd_launch<2>(S, dA, dS, Wl, bl, Ww, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));

@@ -5,6 +5,6 @@ log=gpurun_out/$1.log; shift
 : > $log
 for k in "$@"; do
   echo "=== $k" >> $log
-  timeout 900 python -m pytest $k -q -x -p no:cacheprovider 2>&1 | grep -v "Warning\|warnings.html\|Consider using\|return float\|^$" | tail -40 >> $log
+  eval "timeout 900 python -m pytest $k -q -x -p no:cacheprovider" 2>&1 | grep -v "Warning\|warnings.html\|Consider using\|return float\|^$" | tail -40 >> $log
 done
 tail -200 $log
