@@ -38,6 +38,17 @@ class PackedTargets:
             self.scores = torch.cat([t["scores"].reshape(-1) for t in targets]).to(torch.float32).to(device, non_blocking=True).contiguous()
         self.device = device
         self._inv_num_boxes = None
+        self._rep = {}
+
+    def repeated(self, L):
+        """(labels, boxes, offsets, counts) of the same targets repeated L times: lets ONE cost launch + ONE LSAP launch
+        match all L decoder levels (L*B independent problems) instead of L serial launches."""
+        if L not in self._rep:
+            tot = max(self.total, 0)
+            off = torch.cat([self.offsets_host[:-1] + l * tot for l in range(L)] + [torch.tensor([L * tot], dtype=torch.int32)])
+            self._rep[L] = (self.labels[:max(tot, 1)].repeat(L) if tot else self.labels, self.boxes[:max(tot, 1)].repeat(L, 1) if tot else self.boxes,
+                            off.to(self.device, non_blocking=True), self.counts_host.repeat(L).to(self.device, non_blocking=True))
+        return self._rep[L]
 
     def inv_num_boxes(self):
         """1 / clamp(all_reduce(num_boxes)/world, 1) as a device scalar (conditional_detr.py:436-440), no .item()."""
@@ -84,6 +95,20 @@ def lsap(cost, T):
 def match(logits, boxes, T, weights):
     """dense query->gt assignment i32 [B,Q] (-1 = unmatched), on device."""
     return lsap(match_cost(logits, boxes, T, weights), T)
+
+
+def match_levels(logits_levels, boxes_levels, T, weights):
+    """logits [L,B,Q,C], boxes [L,B,Q,4] -> dense assignment i32 [L,B,Q]; one cost + one LSAP launch for all levels."""
+    L, B, Q, C = logits_levels.shape
+    if T.max_g == 0:
+        return torch.full((L, B, Q), -1, dtype=torch.int32, device=logits_levels.device)
+    labels, boxes, off, counts = T.repeated(L)
+    ld = T.max_g
+    cost = torch.empty((L * B, Q, ld), dtype=torch.float32, device=logits_levels.device)
+    w_class, w_bbox, w_giou = weights
+    check(lib().spe_match_cost(ptr(logits_levels.detach().float().contiguous()), ptr(boxes_levels.detach().float().contiguous()), ptr(labels), ptr(boxes),
+                               ptr(off), L * B, Q, C, float(w_class), float(w_bbox), float(w_giou), ptr(cost), ld, stream()))
+    return lsap_raw(cost, counts).view(L, B, Q)
 
 
 def indices_from_dense(r2g_cpu):

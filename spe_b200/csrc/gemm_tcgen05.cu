@@ -1,18 +1,19 @@
-// tcgen05 / TMEM / TMA GEMM for sm_100a:  C = epilogue(alpha * A * B^T)
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C = epilogue(alpha * A * B^T)        (persistent, warp-specialised)
 //
-//   * operands bf16, staged global->shared by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a
-//     STAGES-deep mbarrier ring; both K-major and MN-major operand layouts are consumed directly
-//     (UMMA descriptor major bits), so dgrad (B = weight as MN-major) and wgrad (both MN-major)
-//     need no transposed copies;
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) with the
-//     fp32 accumulator in TMEM; tcgen05.commit releases smem stages and signals the epilogue;
-//   * 4 warps read the accumulator with tcgen05.ld (32x32b), apply bias / activation / LayerScale /
-//     residual and move every tile-shaped operand of the epilogue through shared memory with TMA
-//     (residual / aux_in: bulk tensor loads; C / aux_out: bulk tensor stores, 128B-swizzled slabs, one
-//     32-row slab per warp) so all epilogue HBM traffic is full-line and asynchronous;
-//   * split-K (small M*N, long K: the wgrad shapes) with TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32);
-//   * <=98 KB smem and BN TMEM columns per CTA -> 2 CTAs per SM, so one CTA's epilogue overlaps the
-//     other's main loop.
+//   * one persistent CTA per SM walks the output tiles (128 x BN); 12 warps:
+//       warp 0  : TMA producer  -- bf16 operand tiles global->shared (cp.async.bulk.tensor, SWIZZLE_128B) into a
+//                 STAGES-deep mbarrier ring that runs continuously across tiles;
+//       warp 1  : MMA issuer    -- one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
+//                 fp32 accumulator in TMEM, DOUBLE BUFFERED (2 x BN columns) so tile i+1's main loop overlaps tile i's
+//                 epilogue; tcgen05.commit releases smem stages and publishes the accumulator;
+//       warp 2  : TMEM allocator;   warps 4..11 : epilogue (warp%4 = TMEM lane quarter, (warp-4)/4 = 64-column half);
+//   * both K-major and MN-major operand layouts are consumed directly (UMMA descriptor major bits), so dgrad
+//     (B = the weight, MN-major) and wgrad (both MN-major) need no transposed copies;
+//   * epilogue: tcgen05.ld (32x32b) -> bias / activation / LayerScale / residual in registers; every tile-shaped
+//     operand moves through 32-row x 128-byte SWIZZLE_128B shared-memory slabs with TMA (residual / aux_in: bulk tensor
+//     loads; C / aux_out: bulk tensor stores) so epilogue HBM traffic is full-line and asynchronous; operands that are
+//     not 16-byte regular (e.g. the 81-wide logits) fall back to direct per-thread global accesses;
+//   * split-K for few-tile / long-K shapes (wgrad) with TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32).
 //
 // Reference call sites replaced: see include/spe_b200.h (spe_gemm).
 #include "common.cuh"
@@ -24,7 +25,12 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_WARPS = 8;
 constexpr uint32_t CHUNK_BYTES = 64 * BK * 2;   // one 64(mn) x 64(k) MN-major TMA box
+constexpr uint32_t SLAB = 4096;                 // 32 rows x 128 B
+constexpr uint32_t EPI_SMEM = NUM_EPI_WARPS * 3 * SLAB;
 
 struct EpiParams {
     void* C; int c_dtype; long long ldc, c_sb1, c_sb2;
@@ -33,11 +39,11 @@ struct EpiParams {
     const float* gamma; const float* residual; long long ldr, r_sb1, r_sb2;
     int split, split_stride;
     int M, N, K, batch2;
-    int vec_ok;
     int a_m1, a_m2, b_m1, b_m2;   // 0 = operand broadcast over that batch dim (stride 0), else 1
     int r_m1, r_m2;
     int tma_io;                   // epilogue tiles through TMA (else direct per-thread global access)
-    int splits, kb_per_split;     // split-K: blockIdx.z = batch * splits + split
+    int splits, kb_per_split;     // split-K
+    int tiles_m, tiles_n, num_tiles;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -47,6 +53,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -72,7 +81,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -111,10 +119,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
+        : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]),     \
+          "=r"((r)[8]), "=r"((r)[9]), "=r"((r)[10]), "=r"((r)[11]), "=r"((r)[12]), "=r"((r)[13]), "=r"((r)[14]), "=r"((r)[15]), \
+          "=r"((r)[16]), "=r"((r)[17]), "=r"((r)[18]), "=r"((r)[19]), "=r"((r)[20]), "=r"((r)[21]), "=r"((r)[22]), "=r"((r)[23]), \
+          "=r"((r)[24]), "=r"((r)[25]), "=r"((r)[26]), "=r"((r)[27]), "=r"((r)[28]), "=r"((r)[29]), "=r"((r)[30]), "=r"((r)[31]) \
+        : "r"(taddr))
+
+#define TMEM_LD_32x32b_X16(taddr, r)                                                                         \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                     \
+        : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]),     \
+          "=r"((r)[8]), "=r"((r)[9]), "=r"((r)[10]), "=r"((r)[11]), "=r"((r)[12]), "=r"((r)[13]), "=r"((r)[14]), "=r"((r)[15]) \
         : "r"(taddr))
 
 __device__ __forceinline__ float apply_act(float v, int act, float aux) {
@@ -127,14 +143,40 @@ __device__ __forceinline__ float apply_act(float v, int act, float aux) {
     }
 }
 
+// direct (non-TMA) epilogue of one row x 64 accumulator columns: operands that are not 16-byte regular
+__device__ __noinline__ void epilogue_direct(const EpiParams& ep, const uint32_t* r, int m, int nb, int b1, int b2, bool lead) {
+    if (m >= ep.M) return;
+    const long long boff_c = (long long)b1 * ep.c_sb1 + (long long)b2 * ep.c_sb2;
+    const long long boff_r = (long long)(b1 * ep.r_m1) * ep.r_sb1 + (long long)(b2 * ep.r_m2) * ep.r_sb2;
+    float* Cf = reinterpret_cast<float*>(ep.C) + boff_c + (long long)m * ep.ldc;
+    uint16_t* Cb = reinterpret_cast<uint16_t*>(ep.C) + boff_c + (long long)m * ep.ldc;
+    const float* Rr = (ep.residual && lead) ? ep.residual + boff_r + (long long)m * ep.ldr : nullptr;
+    const uint16_t* auxi = ep.aux_in ? ep.aux_in + (long long)m * ep.ld_aux : nullptr;
+    uint16_t* auxo = ep.aux_out ? ep.aux_out + (long long)m * ep.ld_aux : nullptr;
+    for (int j = 0; j < 64; ++j) {
+        const int n = nb + j;
+        if (n >= ep.N) break;
+        float x = __uint_as_float(r[j]) * ep.alpha;
+        if (ep.bias && lead) x += __ldg(ep.bias + n);
+        if (auxo) auxo[n] = f_to_bf16(x);
+        if (ep.act != SPE_ACT_NONE) x = apply_act(x, ep.act, auxi ? bf16_to_f(auxi[n]) : 0.f);
+        if (ep.gamma) x *= __ldg(ep.gamma + n);
+        if (Rr) x += Rr[n];
+        const int dn = ep.split > 0 ? (n / ep.split) * ep.split_stride + (n % ep.split) : n;
+        if (ep.splits > 1) atomicAdd(Cf + dn, x);
+        else if (ep.c_dtype == SPE_DT_F32) Cf[dn] = x;
+        else Cb[dn] = f_to_bf16(x);
+    }
+}
+
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                                                           const __grid_constant__ CUtensorMap tmXi, const __grid_constant__ CUtensorMap tmXo,
-                                                           const EpiParams ep) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                                                                      const __grid_constant__ CUtensorMap tmXi, const __grid_constant__ CUtensorMap tmXo,
+                                                                      const EpiParams ep) {
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = 2 * BN;               // double-buffered accumulator (BN in {64,128} -> 128 / 256 columns)
     // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -143,18 +185,13 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1 + 4);
+    uint8_t* sEpi = sB + STAGES * B_BYTES;                                  // 8 warps x 3 slabs
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_SMEM);          // full[S], empty[S], tfull[2], tempty[2], ebar[8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int zb = blockIdx.z / ep.splits, split = blockIdx.z % ep.splits;
-    const int b1 = zb / ep.batch2, b2 = zb % ep.batch2;
     const int total_kb = (ep.K + BK - 1) / BK;
-    const int kb0 = split * ep.kb_per_split;
-    const int num_kb = min(ep.kb_per_split, total_kb - kb0);      // >= 1 by construction
-
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 16, ebar0 = tempty0 + 16;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -163,12 +200,15 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(tfull, 1);
-        for (int w = 0; w < 4; ++w) mbar_init(tfull + 8 + 8 * w, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull0 + 8 * b, 1);
+            mbar_init(tempty0 + 8 * b, NUM_EPI_WARPS);
+        }
+        for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(ebar0 + 8 * w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -177,27 +217,46 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile -> coordinates (n fastest: consecutive CTAs share the A rows in L2)
+    auto decode = [&](int t, int& m0, int& n0, int& b1, int& b2, int& kb0, int& nkb, int& split) {
+        const int tn = t % ep.tiles_n;
+        const int tm = (t / ep.tiles_n) % ep.tiles_m;
+        const int z = t / (ep.tiles_n * ep.tiles_m);
+        const int zb = z / ep.splits;
+        split = z % ep.splits;
+        b1 = zb / ep.batch2; b2 = zb % ep.batch2;
+        m0 = tm * BM; n0 = tn * BN;
+        kb0 = split * ep.kb_per_split;
+        nkb = min(ep.kb_per_split, total_kb - kb0);
+    };
+
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const uint32_t fb = full0 + 8 * s;
-                mbar_expect_tx(fb, A_BYTES + B_BYTES);
-                const uint32_t a_dst = smem_u32(sA + s * A_BYTES), b_dst = smem_u32(sB + s * B_BYTES);
-                if constexpr (!A_MN) {
-                    tma_load_4d(a_dst, &tmA, fb, (kb0 + kb) * BK, m0, b2 * ep.a_m2, b1 * ep.a_m1);
-                } else {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < ep.num_tiles; t += gridDim.x) {
+                int m0, n0, b1, b2, kb0, nkb, split;
+                decode(t, m0, n0, b1, b2, kb0, nkb, split);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    const uint32_t fb = full0 + 8 * s;
+                    mbar_expect_tx(fb, A_BYTES + B_BYTES);
+                    const uint32_t a_dst = smem_u32(sA + s * A_BYTES), b_dst = smem_u32(sB + s * B_BYTES);
+                    const int kc = (kb0 + kb) * BK;
+                    if constexpr (!A_MN) {
+                        tma_load_4d(a_dst, &tmA, fb, kc, m0, b2 * ep.a_m2, b1 * ep.a_m1);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + c * 64, (kb0 + kb) * BK, b2 * ep.a_m2, b1 * ep.a_m1);
-                }
-                if constexpr (!B_MN) {
-                    tma_load_4d(b_dst, &tmB, fb, (kb0 + kb) * BK, n0, b2 * ep.b_m2, b1 * ep.b_m1);
-                } else {
+                        for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + c * 64, kc, b2 * ep.a_m2, b1 * ep.a_m1);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_4d(b_dst, &tmB, fb, kc, n0, b2 * ep.b_m2, b1 * ep.b_m1);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + c * 64, (kb0 + kb) * BK, b2 * ep.b_m2, b1 * ep.b_m1);
+                        for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + c * 64, kc, b2 * ep.b_m2, b1 * ep.b_m1);
+                    }
                 }
             }
         }
@@ -205,242 +264,208 @@ __global__ void __launch_bounds__(128) gemm_tcgen05_kernel(const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < ep.num_tiles; t += gridDim.x, ++ti) {
+                int m0, n0, b1, b2, kb0, nkb, split;
+                decode(t, m0, n0, b1, b2, kb0, nkb, split);
+                const uint32_t buf = ti & 1u, use = ti >> 1;
+                mbar_wait(tempty0 + 8 * buf, (use & 1u) ^ 1u);            // epilogue has drained this accumulator buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
+                const uint32_t tacc = tmem_base + buf * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // K-major: 16 k-elements = 32 B inside the 128B swizzle row; SBO = 8 rows * 128 B.
-                    // MN-major: 16 k-rows = 2 groups of 8 rows (SBO = 1024 B); LBO = next 64-wide MN chunk.
-                    const uint64_t ad = A_MN ? umma_desc(a_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(a_base + k * 32, 0, 1024);
-                    const uint64_t bd = B_MN ? umma_desc(b_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(b_base + k * 32, 0, 1024);
-                    umma_f16(tmem_base, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // K-major: 16 k-elements = 32 B inside the 128B swizzle row; SBO = 8 rows * 128 B.
+                        // MN-major: 16 k-rows = 2 groups of 8 rows (SBO = 1024 B); LBO = next 64-wide MN chunk.
+                        const uint64_t ad = A_MN ? umma_desc(a_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(a_base + k * 32, 0, 1024);
+                        const uint64_t bd = B_MN ? umma_desc(b_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(b_base + k * 32, 0, 1024);
+                        umma_f16(tacc, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs retire
                 }
-                umma_commit(empty0 + 8 * s);   // frees the smem stage when these MMAs retire
+                umma_commit(tfull0 + 8 * buf);         // accumulator of this tile complete
             }
-            umma_commit(tfull);                // accumulator complete
         }
         __syncwarp();
-    }
-
-    // ---------------- epilogue: all 4 warps, warp w owns TMEM lanes [32w, 32w+32) ----------------
-    mbar_wait(tfull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    if (ep.tma_io) {
-        // ===== TMA epilogue: per warp, 64 accumulator columns at a time, every tile operand via 32-row x 128-byte
-        //       SWIZZLE_128B slabs in the (now idle) pipeline shared memory =====
-        uint8_t* wbase = smem + warp * 6 * 4096;                   // 6 slabs per warp: R0 R1 | Xi | C0 C1 | Xo
-        const uint32_t sR = smem_u32(wbase), sXi = sR + 8192, sC = sR + 12288, sXo = sR + 20480;
-        const uint32_t ebar = tfull + 8 + 8 * warp;
-        const int mrow = m0 + warp * 32;
+    } else if (warp >= EPI_WARP0) {
+        // ---------------- epilogue warps ----------------
+        const int e = warp - EPI_WARP0;
+        const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)   (hardware: warp%4)
+        const int half = e >> 2;                      // which 64-column super-chunks this warp owns
+        const uint32_t sRC = smem_u32(sEpi + e * 3 * SLAB), sX = sRC + 2 * SLAB;
+        const uint32_t ebar = ebar0 + 8 * e;
         const bool has_r = ep.residual != nullptr, has_xi = ep.aux_in != nullptr, has_xo = ep.aux_out != nullptr;
         const bool c32 = ep.c_dtype == SPE_DT_F32;
-        const bool lead = split == 0;                              // split-K: bias / residual contributed once
-        uint32_t eph = 0;
+        uint32_t eph = 0, ti = 0;
+        bool stores_pending = false;
+        for (int t = blockIdx.x; t < ep.num_tiles; t += gridDim.x, ++ti) {
+            int m0, n0, b1, b2, kb0, nkb, split;
+            decode(t, m0, n0, b1, b2, kb0, nkb, split);
+            const uint32_t buf = ti & 1u, use = ti >> 1;
+            const bool lead = split == 0;             // split-K: bias / residual contributed once
+            const int mrow = m0 + quarter * 32;
+            mbar_wait(tfull0 + 8 * buf, use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            bool arrived = false;
 #pragma unroll 1
-        for (int sc = 0; sc < BN / 64; ++sc) {
-            const int nb = n0 + sc * 64;
-            if (nb >= ep.N) break;
-            const bool loads = (has_r && lead) || has_xi;
-            if (loads && lane == 0) {
-                const bool two = nb + 32 < ep.N;
-                uint32_t bytes = 0;
-                if (has_r && lead) bytes += two ? 8192 : 4096;
-                if (has_xi) bytes += 4096;
-                mbar_expect_tx(ebar, bytes);
-                if (has_r && lead) {
-                    tma_load_4d(sR, &tmR, ebar, nb, mrow, b2 * ep.r_m2, b1 * ep.r_m1);
-                    if (two) tma_load_4d(sR + 4096, &tmR, ebar, nb + 32, mrow, b2 * ep.r_m2, b1 * ep.r_m1);
+            for (int sc = half; sc < BN / 64; sc += 2) {
+                const int nb = n0 + sc * 64;
+                const bool live = nb < ep.N && mrow < ep.M;
+                const bool loads = live && ep.tma_io && ((has_r && lead) || has_xi);
+                if (live && ep.tma_io && stores_pending) {
+                    // the previous bulk stores must have finished READING this warp's slabs before they are refilled
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                    stores_pending = false;
                 }
-                if (has_xi) tma_load_4d(sXi, &tmXi, ebar, nb, mrow, 0, 0);
-            }
-            uint32_t r[64];
-            TMEM_LD_32x32b_X32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sc * 64), r);
-            TMEM_LD_32x32b_X32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sc * 64 + 32), (r + 32));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (loads) { mbar_wait(ebar, eph); eph ^= 1u; }
-            // previous super-chunk's bulk stores must have finished READING the store slabs
-            if (sc > 0) {
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-            }
+                if (loads && lane == 0) {
+                    const bool two = nb + 32 < ep.N;
+                    uint32_t bytes = 0;
+                    if (has_r && lead) bytes += two ? 2 * SLAB : SLAB;
+                    if (has_xi) bytes += SLAB;
+                    mbar_expect_tx(ebar, bytes);
+                    if (has_r && lead) {
+                        tma_load_4d(sRC, &tmR, ebar, nb, mrow, b2 * ep.r_m2, b1 * ep.r_m1);
+                        if (two) tma_load_4d(sRC + SLAB, &tmR, ebar, nb + 32, mrow, b2 * ep.r_m2, b1 * ep.r_m1);
+                    }
+                    if (has_xi) tma_load_4d(sX, &tmXi, ebar, nb, mrow, 0, 0);
+                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + (uint32_t)(sc * 64);
+                const bool last_sc = sc + 2 >= BN / 64;
+                if (!live || !ep.tma_io) {
+                    uint32_t r[64];
+                    TMEM_LD_32x32b_X32(taddr, r);
+                    TMEM_LD_32x32b_X32(taddr + 32, r + 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (last_sc) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                        arrived = true;
+                    }
+                    if (live) epilogue_direct(ep, r, mrow + lane, nb, b1, b2, lead);
+                    continue;
+                }
+                if (loads) { mbar_wait(ebar, eph); eph ^= 1u; }
+                // NOTE on code size: every condition below is warp-uniform and is tested once per 8-column group (never per
+                // element); the N-tail takes the same code with clamped vector loads.  (An earlier per-element-branch version
+                // compiled to ~5000 SASS instructions per super-chunk and made every GEMM issue-bound in its epilogue.)
+                const bool use_bias = ep.bias != nullptr && lead, use_res = has_r && lead;
+                const int act = ep.act;
+#pragma unroll 1
+                for (int gg = 0; gg < 4; ++gg) {                        // rolled: 4 x 16 accumulator columns (keeps the code in the I-cache)
+                uint32_t r[16];
+                TMEM_LD_32x32b_X16(taddr + gg * 16, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (gg == 3 && last_sc) {
+                    // last TMEM read of this warp for this tile: hand the accumulator buffer back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                    arrived = true;
+                }
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {                           // 8 groups of 8 columns
-                const int n = nb + g * 8;
-                float v[8];
+                for (int g2 = 0; g2 < 2; ++g2) {                        // 2 groups of 8 columns
+                    const int g = gg * 2 + g2;
+                    const int n = nb + g * 8;
+                    // columns >= N are clipped by the TMA stores; keep their loads in bounds by clamping the vector address
+                    const int nl = min(n, ep.N - 8 >= 0 ? ((ep.N - 8) & ~3) : 0);
+                    float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * ep.alpha;
-                if (n < ep.N) {                                      // (columns >= N are clipped by the TMA store)
-                    if (ep.bias && lead) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) if (n + j < ep.N) v[j] += __ldg(ep.bias + n + j);
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g2 * 8 + j]) * ep.alpha;
+                    if (use_bias) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + nl)), b1v = __ldg(reinterpret_cast<const float4*>(ep.bias + nl + 4));
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1v.x; v[5] += b1v.y; v[6] += b1v.z; v[7] += b1v.w;
                     }
                     if (has_xo) {
-                        uint4 o;
-                        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sXo + slab_off(lane, g)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sX + slab_off(lane, g)), "r"(pack_bf16x2(v[0], v[1])),
+                                     "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
                     }
-                    if (ep.act != SPE_ACT_NONE) {
-                        float ax[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                        if (has_xi) {
-                            uint4 a;
-                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sXi + slab_off(lane, g)));
-                            float2 t;
-                            t = unpack_bf16x2(a.x); ax[0] = t.x; ax[1] = t.y;
-                            t = unpack_bf16x2(a.y); ax[2] = t.x; ax[3] = t.y;
-                            t = unpack_bf16x2(a.z); ax[4] = t.x; ax[5] = t.y;
-                            t = unpack_bf16x2(a.w); ax[6] = t.x; ax[7] = t.y;
-                        }
+                    if (act != SPE_ACT_NONE) {
+                        if (act == SPE_ACT_RELU) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act, ax[j]);
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                        } else if (act == SPE_ACT_GELU) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+                        } else {
+                            uint4 a;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sX + slab_off(lane, g)));
+                            float ax[8];
+                            float2 tt;
+                            tt = unpack_bf16x2(a.x); ax[0] = tt.x; ax[1] = tt.y;
+                            tt = unpack_bf16x2(a.y); ax[2] = tt.x; ax[3] = tt.y;
+                            tt = unpack_bf16x2(a.z); ax[4] = tt.x; ax[5] = tt.y;
+                            tt = unpack_bf16x2(a.w); ax[6] = tt.x; ax[7] = tt.y;
+                            if (act == SPE_ACT_RELU_GRAD) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = ax[j] > 0.f ? v[j] : 0.f;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(ax[j]);
+                            }
+                        }
                     }
                     if (ep.gamma) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) if (n + j < ep.N) v[j] *= __ldg(ep.gamma + n + j);
+                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + nl)), g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + nl + 4));
+                        v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
                     }
-                    if (has_r && lead) {
-                        // fp32 residual: columns g*8..g*8+7 = slab (g/4), 16B chunks (g%4)*2, +1
-                        const uint32_t sl = sR + (g >> 2) * 4096;
+                    if (use_res) {
+                        // fp32 residual: columns g*8..g*8+7 = slab (g/4), 16B chunks (g%4)*2, +1.  The C tile aliases these slabs:
+                        // every thread reads its residual chunk for group g before it writes any C chunk of group g (see below).
+                        const uint32_t sl = sRC + (g >> 2) * SLAB;
                         float4 r0, r1;
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r0.x), "=f"(r0.y), "=f"(r0.z), "=f"(r0.w) : "r"(sl + slab_off(lane, (g & 3) * 2)));
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w) : "r"(sl + slab_off(lane, (g & 3) * 2 + 1)));
                         v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
                     }
-                }
-                if (c32) {
-                    const uint32_t sl = sC + (g >> 2) * 4096;
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + slab_off(lane, (g & 3) * 2)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + slab_off(lane, (g & 3) * 2 + 1)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-                } else {
-                    uint4 o;
-                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sC + slab_off(lane, g)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                if (ep.splits > 1) {
-                    tma_reduce_add_4d(&tmC, sC, nb, mrow, b2, b1);
-                    if (nb + 32 < ep.N) tma_reduce_add_4d(&tmC, sC + 4096, nb + 32, mrow, b2, b1);
-                } else if (c32) {
-                    tma_store_4d(&tmC, sC, nb, mrow, b2, b1);
-                    if (nb + 32 < ep.N) tma_store_4d(&tmC, sC + 4096, nb + 32, mrow, b2, b1);
-                } else {
-                    tma_store_4d(&tmC, sC, nb, mrow, b2, b1);
-                }
-                if (has_xo) tma_store_4d(&tmXo, sXo, nb, mrow, 0, 0);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (warp == 1) {
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-        }
-        return;
-    }
-
-    const int m = m0 + warp * 32 + lane;
-    const bool row_ok = m < ep.M;
-    const long long boff_c = (long long)b1 * ep.c_sb1 + (long long)b2 * ep.c_sb2;
-    const long long boff_r = (long long)b1 * ep.r_sb1 + (long long)b2 * ep.r_sb2;
-    float* Cf = reinterpret_cast<float*>(ep.C) + boff_c + (long long)m * ep.ldc;
-    uint16_t* Cb = reinterpret_cast<uint16_t*>(ep.C) + boff_c + (long long)m * ep.ldc;
-    const float* Rr = ep.residual ? ep.residual + boff_r + (long long)m * ep.ldr : nullptr;
-    const uint16_t* auxi = ep.aux_in ? ep.aux_in + (long long)m * ep.ld_aux : nullptr;
-    uint16_t* auxo = ep.aux_out ? ep.aux_out + (long long)m * ep.ld_aux : nullptr;
-
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= ep.N) break;                    // uniform across the CTA
-        uint32_t r[32];
-        TMEM_LD_32x32b_X32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!row_ok) continue;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int n = n0 + c0 + g * 8;
-            if (n >= ep.N) break;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * ep.alpha;
-            const bool full = (n + 8 <= ep.N) && ep.vec_ok;
-            const int dn = ep.split > 0 ? (n / ep.split) * ep.split_stride + (n % ep.split) : n;
-            if (full) {
-                if (ep.bias) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-                    const float4 b1v = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
-                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                    v[4] += b1v.x; v[5] += b1v.y; v[6] += b1v.z; v[7] += b1v.w;
-                }
-                if (auxo) {
-                    uint4 o;
-                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(auxo + n) = o;
-                }
-                if (ep.act != SPE_ACT_NONE) {
-                    float ax[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    if (auxi) {
-                        const uint4 a = __ldg(reinterpret_cast<const uint4*>(auxi + n));
-                        float2 t;
-                        t = unpack_bf16x2(a.x); ax[0] = t.x; ax[1] = t.y;
-                        t = unpack_bf16x2(a.y); ax[2] = t.x; ax[3] = t.y;
-                        t = unpack_bf16x2(a.z); ax[4] = t.x; ax[5] = t.y;
-                        t = unpack_bf16x2(a.w); ax[6] = t.x; ax[7] = t.y;
+                    if (c32) {
+                        const uint32_t sl = sRC + (g >> 2) * SLAB;
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + slab_off(lane, (g & 3) * 2)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + slab_off(lane, (g & 3) * 2 + 1)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+                    } else {
+                        // bf16 C chunk g overlays residual columns 4g..4g+3, which this thread consumed at group g/2 <= g
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sRC + slab_off(lane, g)), "r"(pack_bf16x2(v[0], v[1])),
+                                     "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
                     }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act, ax[j]);
                 }
-                if (ep.gamma) {
-                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
-                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
-                    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-                    v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
                 }
-                if (Rr) {
-                    const float4 r0 = *reinterpret_cast<const float4*>(Rr + n);
-                    const float4 r1 = *reinterpret_cast<const float4*>(Rr + n + 4);
-                    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-                    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (ep.splits > 1) {
+                        tma_reduce_add_4d(&tmC, sRC, nb, mrow, b2, b1);
+                        if (nb + 32 < ep.N) tma_reduce_add_4d(&tmC, sRC + SLAB, nb + 32, mrow, b2, b1);
+                    } else if (c32) {
+                        tma_store_4d(&tmC, sRC, nb, mrow, b2, b1);
+                        if (nb + 32 < ep.N) tma_store_4d(&tmC, sRC + SLAB, nb + 32, mrow, b2, b1);
+                    } else {
+                        tma_store_4d(&tmC, sRC, nb, mrow, b2, b1);
+                    }
+                    if (has_xo) tma_store_4d(&tmXo, sX, nb, mrow, 0, 0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if (ep.c_dtype == SPE_DT_F32) {
-                    *reinterpret_cast<float4*>(Cf + dn) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(Cf + dn + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-                    uint4 o;
-                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(Cb + dn) = o;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int nj = n + j;
-                    if (nj >= ep.N) break;
-                    float x = v[j];
-                    if (ep.bias) x += __ldg(ep.bias + nj);
-                    if (auxo) auxo[nj] = f_to_bf16(x);
-                    if (ep.act != SPE_ACT_NONE) x = apply_act(x, ep.act, auxi ? bf16_to_f(auxi[nj]) : 0.f);
-                    if (ep.gamma) x *= __ldg(ep.gamma + nj);
-                    if (Rr) x += Rr[nj];
-                    const int dj = ep.split > 0 ? (nj / ep.split) * ep.split_stride + (nj % ep.split) : nj;
-                    if (ep.c_dtype == SPE_DT_F32) Cf[dj] = x; else Cb[dj] = f_to_bf16(x);
-                }
+                stores_pending = true;
+            }
+            if (!arrived) {
+                // this warp owns no super-chunk of the tile (BN = 64, upper half): still release the buffer
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
@@ -516,27 +541,27 @@ int make_tmap_io(CUtensorMap* tm, const void* ptr, bool f32, int M, int N, int64
 struct IoMaps { CUtensorMap C, R, Xi, Xo; };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const EpiParams& ep, int batch, cudaStream_t st) {
-    constexpr size_t SMEM = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1 + 4) * 8 + 16 + 1024;
-    static_assert((size_t)STAGES * (BM * BK * 2 + BN * BK * 2) >= 4 * 6 * 4096, "epilogue slabs must fit in the pipeline smem");
+int launch(const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const EpiParams& ep, cudaStream_t st) {
+    constexpr size_t SMEM = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + EPI_SMEM + (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + 1024;
+    static_assert(SMEM <= 232448, "shared memory budget (227 KB) exceeded");
     static bool attr_done = false;
     auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
     if (!attr_done) {
         SPE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_done = true;
     }
-    dim3 grid((ep.N + BN - 1) / BN, (ep.M + BM - 1) / BM, batch * ep.splits);
-    kfn<<<grid, 128, SMEM, st>>>(tA, tB, io.C, io.R, io.Xi, io.Xo, ep);
+    const int grid = ep.num_tiles < spe_num_sms() ? ep.num_tiles : spe_num_sms();
+    kfn<<<grid, NUM_THREADS, SMEM, st>>>(tA, tB, io.C, io.R, io.Xi, io.Xo, ep);
     SPE_LAUNCHED();
     return 0;
 }
 
 template <int BN, int STAGES>
-int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const EpiParams& ep, int batch, cudaStream_t st) {
-    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_K) return launch<BN, STAGES, false, false>(tA, tB, io, ep, batch, st);
-    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_MN) return launch<BN, STAGES, false, true>(tA, tB, io, ep, batch, st);
-    if (am == SPE_MAJOR_MN && bm == SPE_MAJOR_K) return launch<BN, STAGES, true, false>(tA, tB, io, ep, batch, st);
-    return launch<BN, STAGES, true, true>(tA, tB, io, ep, batch, st);
+int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const EpiParams& ep, cudaStream_t st) {
+    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_K) return launch<BN, STAGES, false, false>(tA, tB, io, ep, st);
+    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_MN) return launch<BN, STAGES, false, true>(tA, tB, io, ep, st);
+    if (am == SPE_MAJOR_MN && bm == SPE_MAJOR_K) return launch<BN, STAGES, true, false>(tA, tB, io, ep, st);
+    return launch<BN, STAGES, true, true>(tA, tB, io, ep, st);
 }
 
 }  // namespace
@@ -544,15 +569,16 @@ int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB,
 extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_args* a, void* stream) {
     SPE_CHECK(a && a->A && a->B && a->C, "spe_gemm: null argument");
     SPE_CHECK(a->M > 0 && a->N > 0 && a->K > 0 && a->batch1 > 0 && a->batch2 > 0, "spe_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
-    SPE_CHECK((long long)a->batch1 * a->batch2 <= 65535, "spe_gemm: batch too large");
     SPE_CHECK(a->act == SPE_ACT_NONE || a->act == SPE_ACT_RELU || a->act == SPE_ACT_GELU || a->aux_in, "spe_gemm: *_GRAD activation needs aux_in");
     const int BN = a->N <= 64 ? 64 : 128;
     const int batch = a->batch1 * a->batch2;
+    SPE_CHECK(batch == 1 || !(a->aux_in || a->aux_out), "spe_gemm: aux_in / aux_out are not batched");
     CUtensorMap tA, tB;
     if (make_tmap(&tA, a->A, a->a_major, a->M, a->K, a->lda, a->a_sb1, a->a_sb2, a->batch1, a->batch2, BM)) return -1;
     if (make_tmap(&tB, a->B, a->b_major, a->N, a->K, a->ldb, a->b_sb1, a->b_sb2, a->batch1, a->batch2, BN)) return -1;
 
     EpiParams ep;
+    memset(&ep, 0, sizeof(ep));
     ep.C = a->C; ep.c_dtype = a->c_dtype; ep.ldc = a->ldc; ep.c_sb1 = a->c_sb1; ep.c_sb2 = a->c_sb2;
     ep.alpha = a->alpha; ep.bias = a->bias; ep.act = a->act;
     ep.aux_in = reinterpret_cast<const uint16_t*>(a->aux_in); ep.aux_out = reinterpret_cast<uint16_t*>(a->aux_out); ep.ld_aux = a->ld_aux;
@@ -561,48 +587,42 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     ep.M = a->M; ep.N = a->N; ep.K = a->K; ep.batch2 = a->batch2;
     ep.a_m1 = (a->batch1 > 1 && a->a_sb1 == 0) ? 0 : 1; ep.a_m2 = (a->batch2 > 1 && a->a_sb2 == 0) ? 0 : 1;
     ep.b_m1 = (a->batch1 > 1 && a->b_sb1 == 0) ? 0 : 1; ep.b_m2 = (a->batch2 > 1 && a->b_sb2 == 0) ? 0 : 1;
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    const int celt = a->c_dtype == SPE_DT_F32 ? 4 : 8;      // elements per 16 B
-    bool vec = al16(a->C) && a->ldc % celt == 0 && a->c_sb1 % celt == 0 && a->c_sb2 % celt == 0;
-    if (a->bias) vec = vec && al16(a->bias);
-    if (a->gamma) vec = vec && al16(a->gamma);
-    if (a->residual) vec = vec && al16(a->residual) && a->ldr % 4 == 0 && a->r_sb1 % 4 == 0 && a->r_sb2 % 4 == 0;
-    if (a->aux_in) vec = vec && al16(a->aux_in) && a->ld_aux % 8 == 0;
-    if (a->aux_out) vec = vec && al16(a->aux_out) && a->ld_aux % 8 == 0;
-    if (a->split > 0) vec = vec && a->split % 8 == 0 && a->split_stride % 8 == 0;
-    ep.vec_ok = vec ? 1 : 0;
+    ep.r_m1 = (a->batch1 > 1 && a->r_sb1 == 0) ? 0 : 1; ep.r_m2 = (a->batch2 > 1 && a->r_sb2 == 0) ? 0 : 1;
 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // ---- epilogue tiles through TMA when every tile operand is 16-byte regular (else direct global access)
     IoMaps io;
     memset(&io, 0, sizeof(io));
     const bool cf32 = a->c_dtype == SPE_DT_F32;
-    bool tma_io = a->split == 0 && getenv("SPE_GEMM_DIRECT_EPILOGUE") == nullptr;
-    if (tma_io && (a->aux_in || a->aux_out) && batch != 1) tma_io = false;
+    const bool bias_ok = !a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
+    const bool gamma_ok = !a->gamma || (reinterpret_cast<uintptr_t>(a->gamma) & 15) == 0;
+    bool tma_io = a->split == 0 && getenv("SPE_GEMM_DIRECT_EPILOGUE") == nullptr && !(a->aux_in && a->aux_out) && bias_ok && gamma_ok;
     if (tma_io && make_tmap_io(&io.C, a->C, cf32, a->M, a->N, a->ldc, a->c_sb1, a->c_sb2, a->batch1, a->batch2)) tma_io = false;
     if (tma_io && a->residual && make_tmap_io(&io.R, a->residual, true, a->M, a->N, a->ldr, a->r_sb1, a->r_sb2, a->batch1, a->batch2)) tma_io = false;
     if (tma_io && a->aux_in && make_tmap_io(&io.Xi, a->aux_in, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
     if (tma_io && a->aux_out && make_tmap_io(&io.Xo, a->aux_out, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
-    // in-place accumulate (residual == C): the TMA path loads the residual slab before storing the same tile -> fine
     ep.tma_io = tma_io ? 1 : 0;
-    ep.r_m1 = (a->batch1 > 1 && a->r_sb1 == 0) ? 0 : 1; ep.r_m2 = (a->batch2 > 1 && a->r_sb2 == 0) ? 0 : 1;
     // ---- split-K: few output tiles but a long reduction (wgrad).  fp32 contiguous C, no activation / aux / gamma.
     const int total_kb = (a->K + BK - 1) / BK;
+    ep.tiles_m = (a->M + BM - 1) / BM;
+    ep.tiles_n = (a->N + BN - 1) / BN;
     int splits = 1;
-    const long long tiles = (long long)((a->M + BM - 1) / BM) * ((a->N + BN - 1) / BN) * batch;
-    if (tma_io && cf32 && batch == 1 && a->act == SPE_ACT_NONE && !a->aux_in && !a->aux_out && !a->gamma && a->residual != (const float*)a->C &&
-        a->ldc == a->N && tiles * 2 <= spe_num_sms() && total_kb >= 8 && getenv("SPE_GEMM_NO_SPLITK") == nullptr) {
-        splits = (int)((2LL * spe_num_sms() + tiles - 1) / tiles);
+    const long long tiles = (long long)ep.tiles_m * ep.tiles_n * batch;
+    SPE_CHECK(tiles < (1LL << 30), "spe_gemm: too many tiles");
+    if (cf32 && batch == 1 && a->act == SPE_ACT_NONE && !a->aux_in && !a->aux_out && !a->gamma && a->residual != (const float*)a->C &&
+        a->ldc == a->N && a->split == 0 && tiles * 2 <= spe_num_sms() && total_kb >= 8 && getenv("SPE_GEMM_NO_SPLITK") == nullptr) {
+        splits = (int)((spe_num_sms() + tiles - 1) / tiles);
         if (splits > total_kb / 4) splits = total_kb / 4;
         if (splits < 1) splits = 1;
     }
     ep.kb_per_split = (total_kb + splits - 1) / splits;
     splits = (total_kb + ep.kb_per_split - 1) / ep.kb_per_split;      // no empty split
     ep.splits = splits;
+    ep.num_tiles = (int)(tiles * splits);
     if (splits > 1) SPE_CUDA(cudaMemsetAsync(a->C, 0, (size_t)a->M * a->N * 4, st));
     char tag[64];
     if (g_spe_prof_on) snprintf(tag, sizeof(tag), "M%d N%d K%d b%d a%d b%d c%d", a->M, a->N, a->K, batch, a->a_major, a->b_major, a->c_dtype);
     SpeProfScope prof(SPE_FAM_GEMM, 2.0 * a->M * a->N * (double)a->K * batch, st, tag);     // algorithmic flops
-    if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, io, ep, batch, st);
-    return dispatch_major<128, 3>(a->a_major, a->b_major, tA, tB, io, ep, batch, st);
+    if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);
+    return dispatch_major<128, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);
 }

@@ -200,45 +200,70 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const uint16_t* __rest
 //         registers across all rows of a CTA and are reduced once at the end (deterministic two-stage reduction).
 //   The H x H mixes are FP32 FMAs against weights broadcast from shared memory (FP32/MUFU bound).
 // ------------------------------------------------------------------------------------------------
+// mixed logits of 2 adjacent keys for all heads: a[g][c] = bl[g] + sum_h Wl[g][h] s[h][c]   (weights: 16-byte broadcast LDS)
 template <int H>
-struct MixW {
-    float Wl[H * H], Ww[H * H], bl[H], bw[H];
+__device__ __forceinline__ void mix2(const float* __restrict__ W, const float* __restrict__ bias, const float (&x)[H][2], float (&a)[H][2]) {
+#pragma unroll
+    for (int g = 0; g < H; ++g) {
+        float a0 = bias ? bias[g] : 0.f, a1 = a0;
+        if constexpr (H % 4 == 0) {
+#pragma unroll
+            for (int h = 0; h < H; h += 4) {
+                const float4 wv = *reinterpret_cast<const float4*>(W + g * H + h);
+                a0 += wv.x * x[h][0]; a1 += wv.x * x[h][1];
+                a0 += wv.y * x[h + 1][0]; a1 += wv.y * x[h + 1][1];
+                a0 += wv.z * x[h + 2][0]; a1 += wv.z * x[h + 2][1];
+                a0 += wv.w * x[h + 3][0]; a1 += wv.w * x[h + 3][1];
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < H; ++h) { const float wv = W[g * H + h]; a0 += wv * x[h][0]; a1 += wv * x[h][1]; }
+        }
+        a[g][0] = a0; a[g][1] = a1;
+    }
+}
+
+template <int H>
+struct __align__(16) MixWT {       // weights + transposed copies (so both W x and W^T x read contiguous float4 rows)
+    float Wl[H * H], Ww[H * H], WlT[H * H], WwT[H * H], bl[H], bw[H];
 };
 
 template <int H>
-__device__ __forceinline__ void load_mix(MixW<H>* sm, const float* Wl, const float* bl, const float* Ww, const float* bw) {
-    for (int i = threadIdx.x; i < H * H; i += blockDim.x) { sm->Wl[i] = Wl[i]; sm->Ww[i] = Ww[i]; }
+__device__ __forceinline__ void load_mixT(MixWT<H>* sm, const float* Wl, const float* bl, const float* Ww, const float* bw) {
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+        const int r = i / H, c = i % H;
+        sm->Wl[i] = Wl[i]; sm->Ww[i] = Ww[i];
+        sm->WlT[c * H + r] = Wl[i]; sm->WwT[c * H + r] = Ww[i];
+    }
     if (threadIdx.x < H) { sm->bl[threadIdx.x] = bl[threadIdx.x]; sm->bw[threadIdx.x] = bw ? bw[threadIdx.x] : 0.f; }
     __syncthreads();
 }
 
+template <int H>
+__device__ __forceinline__ void load_s2(const float* __restrict__ Sb, long long hS, int j, bool two, float pad, float (&s)[H][2]) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j);
+        s[h][0] = t.x; s[h][1] = two ? t.y : pad;
+    }
+}
+
 // sweep A: per-row softmax statistics of the mixed logits.  Returns m[g] (row max) and iz[g] (1/sum).
 template <int H>
-__device__ __forceinline__ void talking_stats(const float* __restrict__ Sb, long long hS, int Nk, const MixW<H>* w, int lane, float* m, float* iz) {
+__device__ __forceinline__ void talking_stats(const float* __restrict__ Sb, long long hS, int Nk, const MixWT<H>* w, int lane, float* m, float* iz) {
     float z[H];
 #pragma unroll
     for (int g = 0; g < H; ++g) { m[g] = -INFINITY; z[g] = 0.f; }
-    for (int j = 4 * lane; j < Nk; j += 128) {
-        float s[H][4];
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-            const float4 t = *reinterpret_cast<const float4*>(Sb + h * hS + j);
-            s[h][0] = t.x; s[h][1] = t.y; s[h][2] = t.z; s[h][3] = t.w;
-        }
-        const int nv = min(4, Nk - j);
+    for (int j = 2 * lane; j < Nk; j += 64) {
+        const bool two = j + 1 < Nk;
+        float s[H][2], a[H][2];
+        load_s2<H>(Sb, hS, j, two, 0.f, s);
+        mix2<H>(w->Wl, w->bl, s, a);
 #pragma unroll
         for (int g = 0; g < H; ++g) {
-            float a[4] = {w->bl[g], w->bl[g], w->bl[g], w->bl[g]};
-#pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const float wv = w->Wl[g * H + h];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) a[c] += wv * s[h][c];
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) if (c >= nv) a[c] = -INFINITY;
-            const float mn = fmaxf(m[g], fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])));
-            z[g] = z[g] * __expf(m[g] - mn) + ((__expf(a[0] - mn) + __expf(a[1] - mn)) + (__expf(a[2] - mn) + __expf(a[3] - mn)));
+            const float a1 = two ? a[g][1] : -INFINITY;
+            const float mn = fmaxf(m[g], fmaxf(a[g][0], a1));
+            z[g] = z[g] * __expf(m[g] - mn) + (__expf(a[g][0] - mn) + __expf(a1 - mn));
             m[g] = mn;
         }
     }
@@ -252,11 +277,11 @@ __device__ __forceinline__ void talking_stats(const float* __restrict__ Sb, long
 }
 
 template <int H>
-__global__ void __launch_bounds__(256) talking_fwd_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
-                                                          const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
-                                                          int rows_total, int Nq, int Nk, long long ldS, long long ldA) {
-    __shared__ MixW<H> w;
-    load_mix<H>(&w, Wl, bl, Ww, bw);
+__global__ void __launch_bounds__(256, 2) talking_fwd_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
+                                                             const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
+                                                             int rows_total, int Nq, int Nk, long long ldS, long long ldA) {
+    __shared__ MixWT<H> w;
+    load_mixT<H>(&w, Wl, bl, Ww, bw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
     for (int rowi = blockIdx.x * 8 + warp; rowi < rows_total; rowi += gridDim.x * 8) {
@@ -265,65 +290,66 @@ __global__ void __launch_bounds__(256) talking_fwd_kernel(const float* __restric
         uint16_t* Ab = A + ((long long)b * H * Nq + q) * ldA;
         float m[H], iz[H];
         talking_stats<H>(Sb, hS, Nk, &w, lane, m, iz);
-        for (int j = 4 * lane; j < ldA; j += 128) {
+        for (int j = 2 * lane; j < ldA; j += 64) {
             if (j >= Nk) {                                  // keep the padding columns [Nk, ldA) zero
 #pragma unroll
-                for (int o = 0; o < H; ++o) *reinterpret_cast<uint2*>(Ab + o * hA + j) = make_uint2(0u, 0u);
+                for (int o = 0; o < H; ++o) *reinterpret_cast<uint32_t*>(Ab + o * hA + j) = 0u;
                 continue;
             }
-            float s[H][4], p[H][4];
+            const bool two = j + 1 < Nk;
+            float s[H][2], p[H][2], a[H][2];
+            load_s2<H>(Sb, hS, j, two, 0.f, s);
+            mix2<H>(w.Wl, w.bl, s, a);
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const float4 t = *reinterpret_cast<const float4*>(Sb + h * hS + j);
-                s[h][0] = t.x; s[h][1] = t.y; s[h][2] = t.z; s[h][3] = t.w;
-            }
-            const int nv = min(4, Nk - j);
+            for (int g = 0; g < H; ++g) { p[g][0] = __expf(a[g][0] - m[g]) * iz[g]; p[g][1] = two ? __expf(a[g][1] - m[g]) * iz[g] : 0.f; }
+            mix2<H>(w.Ww, w.bw, p, a);
 #pragma unroll
-            for (int g = 0; g < H; ++g) {
-                float a[4] = {w.bl[g], w.bl[g], w.bl[g], w.bl[g]};
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    const float wv = w.Wl[g * H + h];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) a[c] += wv * s[h][c];
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) p[g][c] = __expf(a[c] - m[g]) * iz[g];
-            }
-#pragma unroll
-            for (int o = 0; o < H; ++o) {
-                float a[4] = {w.bw[o], w.bw[o], w.bw[o], w.bw[o]};
-#pragma unroll
-                for (int g = 0; g < H; ++g) {
-                    const float wv = w.Ww[o * H + g];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) a[c] += wv * p[g][c];
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) if (c >= nv) a[c] = 0.f;
-                *reinterpret_cast<uint2*>(Ab + o * hA + j) = make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
-            }
+            for (int o = 0; o < H; ++o) *reinterpret_cast<uint32_t*>(Ab + o * hA + j) = pack_bf16x2(a[o][0], two ? a[o][1] : 0.f);
         }
+    }
+}
+
+// ---- warp-level outer-product accumulation  D[x_row][y_row] += sum_cols X[x_row][c] * Y[y_row][c]  on the legacy tensor path
+// (mma.sync m16n8k16 bf16, fp32 accumulate): the H x H parameter-gradient sums of the head mixes cost ~12 instructions per
+// 64 keys instead of 128 FMAs + 128 persistent accumulator registers per thread.
+constexpr int TP = 72;                      // bf16 row pitch (144 B): ldmatrix rows land in distinct banks
+__device__ __forceinline__ void outer_acc_64(const uint16_t* X, const uint16_t* Y, const uint16_t* Z, int H, int lane, float (&acc)[4]) {
+    // X, Y: [8][TP] bf16 (rows >= H unused), Z: zero row.  4 k-steps of 16 columns.
+    const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const uint16_t* pa = ((mi & 1) || r >= H) ? Z : X + r * TP + kk * 16 + (mi >> 1) * 8;
+        const uint16_t* pb = (r >= H) ? Z : Y + r * TP + kk * 16 + (mi & 1) * 8;
+        uint32_t a0, a1, a2, a3, b0, b1;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"((uint32_t)__cvta_generic_to_shared(pa)));
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"((uint32_t)__cvta_generic_to_shared(pb)));
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
     }
 }
 
 // backward: dA (bf16) -> dS (bf16, may alias dA), parameter-gradient partials per CTA in `part` [gridDim.x][2*H*H + 2*H]
 template <int H>
-__global__ void __launch_bounds__(256, 1) talking_bwd_kernel(const float* __restrict__ S, const uint16_t* dA, uint16_t* dS,
+__global__ void __launch_bounds__(256, 2) talking_bwd_kernel(const float* __restrict__ S, const uint16_t* dA, uint16_t* dS,
                                                              const float* __restrict__ Wl, const float* __restrict__ bl, const float* __restrict__ Ww,
                                                              int rows_total, int Nq, int Nk, long long ldS, long long ldA, float* __restrict__ part) {
-    __shared__ MixW<H> w;
+    __shared__ MixWT<H> w;
     constexpr int NP = 2 * H * H + 2 * H;
     __shared__ float redbuf[8][NP];
-    load_mix<H>(&w, Wl, bl, Ww, nullptr);
+    __shared__ __align__(16) uint16_t tiles[8][17][TP];      // per warp: X rows 0..7, Y rows 8..15, zero row 16
+    load_mixT<H>(&w, Wl, bl, Ww, nullptr);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
+    uint16_t* X = &tiles[warp][0][0];
+    uint16_t* Y = &tiles[warp][8][0];
+    uint16_t* Z = &tiles[warp][16][0];
+    for (int i = lane; i < 17 * TP; i += 32) X[i] = 0;
+    __syncwarp();
 
-    float aWw[H][H], aWl[H][H], abw[H], abl[H];       // per-thread partial parameter gradients (persist over rows)
+    float accWw[4] = {0.f, 0.f, 0.f, 0.f}, accWl[4] = {0.f, 0.f, 0.f, 0.f};     // mma fragments: rows lane/4, cols (lane%4)*2+{0,1}
+    float abw[H], abl[H];
 #pragma unroll
-    for (int a = 0; a < H; ++a) { abw[a] = 0.f; abl[a] = 0.f;
-#pragma unroll
-        for (int c = 0; c < H; ++c) { aWw[a][c] = 0.f; aWl[a][c] = 0.f; } }
+    for (int a = 0; a < H; ++a) { abw[a] = 0.f; abl[a] = 0.f; }
 
     for (int rowi = blockIdx.x * 8 + warp; rowi < rows_total; rowi += gridDim.x * 8) {
         const int b = rowi / Nq, q = rowi % Nq;
@@ -332,89 +358,91 @@ __global__ void __launch_bounds__(256, 1) talking_bwd_kernel(const float* __rest
         uint16_t* dSb = dS + ((long long)b * H * Nq + q) * ldA;
         float m[H], iz[H], rho[H];
         talking_stats<H>(Sb, hS, Nk, &w, lane, m, iz);
-        // ---- sweep B: rho[g] = sum_j P[g] dP[g];  dWw += dA (x) P;  dbw += dA       (2 keys per lane per step)
+        // ---- sweep B: rho[g] = sum_j P[g] dP[g];  dWw += dA (x) P;  dbw += dA
 #pragma unroll
         for (int g = 0; g < H; ++g) rho[g] = 0.f;
-        for (int j = 2 * lane; j < Nk; j += 64) {
-            const bool two = j + 1 < Nk;
-            float s[H][2], d[H][2];
-#pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j);
-                s[h][0] = t.x; s[h][1] = t.y;
-                const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + h * hA + j));
-                d[h][0] = u.x; d[h][1] = two ? u.y : 0.f;
-                abw[h] += d[h][0] + d[h][1];
-            }
-#pragma unroll
-            for (int g = 0; g < H; ++g) {
-                float a0 = w.bl[g], a1 = w.bl[g], x0 = 0.f, x1 = 0.f;
+        const int Nk64 = (Nk + 63) & ~63;
+        for (int j = 2 * lane; j < Nk64; j += 64) {
+            const bool one = j < Nk, two = j + 1 < Nk;
+            float s[H][2], d[H][2], a[H][2], x[H][2];
+            if (one) {
+                load_s2<H>(Sb, hS, j, two, 0.f, s);
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
-                    const float wl = w.Wl[g * H + h], ww = w.Ww[h * H + g];
-                    a0 += wl * s[h][0]; a1 += wl * s[h][1];
-                    x0 += ww * d[h][0]; x1 += ww * d[h][1];
+                    const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + h * hA + j));
+                    d[h][0] = u.x; d[h][1] = two ? u.y : 0.f;
+                    abw[h] += d[h][0] + d[h][1];
                 }
-                const float p0 = __expf(a0 - m[g]) * iz[g], p1 = two ? __expf(a1 - m[g]) * iz[g] : 0.f;
-                rho[g] += p0 * x0 + p1 * x1;
+                mix2<H>(w.Wl, w.bl, s, a);
+                mix2<H>(w.WwT, nullptr, d, x);                          // dP = Ww^T dA
 #pragma unroll
-                for (int o = 0; o < H; ++o) aWw[o][g] += d[o][0] * p0 + d[o][1] * p1;
+                for (int g = 0; g < H; ++g) {
+                    const float p0 = __expf(a[g][0] - m[g]) * iz[g], p1 = two ? __expf(a[g][1] - m[g]) * iz[g] : 0.f;
+                    rho[g] += p0 * x[g][0] + p1 * x[g][1];
+                    *reinterpret_cast<uint32_t*>(X + g * TP + 2 * lane) = pack_bf16x2(d[g][0], d[g][1]);
+                    *reinterpret_cast<uint32_t*>(Y + g * TP + 2 * lane) = pack_bf16x2(p0, p1);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < H; ++g) { *reinterpret_cast<uint32_t*>(X + g * TP + 2 * lane) = 0u; *reinterpret_cast<uint32_t*>(Y + g * TP + 2 * lane) = 0u; }
             }
+            __syncwarp();
+            outer_acc_64(X, Y, Z, H, lane, accWw);
+            __syncwarp();
         }
 #pragma unroll
         for (int g = 0; g < H; ++g) rho[g] = warp_sum(rho[g]);
         // ---- sweep C: dL = P (dP - rho);  dS = Wl^T dL;  dWl += dL (x) S;  dbl += dL
-        for (int j = 2 * lane; j < ldA; j += 64) {
-            if (j >= Nk) {
-#pragma unroll
-                for (int h = 0; h < H; ++h) *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = 0u;
-                continue;
-            }
-            const bool two = j + 1 < Nk;
-            float s[H][2], d[H][2], l[H][2];
-#pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j);
-                s[h][0] = t.x; s[h][1] = t.y;
-                const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + h * hA + j));
-                d[h][0] = u.x; d[h][1] = two ? u.y : 0.f;
-            }
-#pragma unroll
-            for (int g = 0; g < H; ++g) {
-                float a0 = w.bl[g], a1 = w.bl[g], x0 = 0.f, x1 = 0.f;
+        const int Nc = ((int)ldA + 63) & ~63;
+        for (int j = 2 * lane; j < Nc; j += 64) {
+            const bool one = j < Nk, two = j + 1 < Nk;
+            if (one) {
+                float s[H][2], d[H][2], a[H][2], x[H][2], l[H][2];
+                load_s2<H>(Sb, hS, j, two, 0.f, s);
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
-                    const float wl = w.Wl[g * H + h], ww = w.Ww[h * H + g];
-                    a0 += wl * s[h][0]; a1 += wl * s[h][1];
-                    x0 += ww * d[h][0]; x1 += ww * d[h][1];
+                    const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + h * hA + j));
+                    d[h][0] = u.x; d[h][1] = two ? u.y : 0.f;
                 }
-                const float p0 = __expf(a0 - m[g]) * iz[g], p1 = two ? __expf(a1 - m[g]) * iz[g] : 0.f;
-                l[g][0] = p0 * (x0 - rho[g]); l[g][1] = p1 * (x1 - rho[g]);
-                abl[g] += l[g][0] + l[g][1];
-            }
-            // all dA reads of this (row, j) happened above -> safe to overwrite in place when dS aliases dA
-#pragma unroll
-            for (int h = 0; h < H; ++h) {
-                float x0 = 0.f, x1 = 0.f;
-                const float s0 = s[h][0], s1 = two ? s[h][1] : 0.f;
+                mix2<H>(w.Wl, w.bl, s, a);
+                mix2<H>(w.WwT, nullptr, d, x);
 #pragma unroll
                 for (int g = 0; g < H; ++g) {
-                    const float wl = w.Wl[g * H + h];
-                    x0 += wl * l[g][0]; x1 += wl * l[g][1];
-                    aWl[g][h] += l[g][0] * s0 + l[g][1] * s1;
+                    const float p0 = __expf(a[g][0] - m[g]) * iz[g], p1 = two ? __expf(a[g][1] - m[g]) * iz[g] : 0.f;
+                    l[g][0] = p0 * (x[g][0] - rho[g]); l[g][1] = p1 * (x[g][1] - rho[g]);
+                    abl[g] += l[g][0] + l[g][1];
+                    *reinterpret_cast<uint32_t*>(X + g * TP + 2 * lane) = pack_bf16x2(l[g][0], l[g][1]);
+                    *reinterpret_cast<uint32_t*>(Y + g * TP + 2 * lane) = pack_bf16x2(s[g][0], s[g][1]);
                 }
-                *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = pack_bf16x2(x0, two ? x1 : 0.f);
+                mix2<H>(w.WlT, nullptr, l, x);                          // dS = Wl^T dL
+                // all dA reads of this (row, j) happened above -> safe to overwrite in place when dS aliases dA
+#pragma unroll
+                for (int h = 0; h < H; ++h) *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = pack_bf16x2(x[h][0], two ? x[h][1] : 0.f);
+            } else {
+#pragma unroll
+                for (int g = 0; g < H; ++g) { *reinterpret_cast<uint32_t*>(X + g * TP + 2 * lane) = 0u; *reinterpret_cast<uint32_t*>(Y + g * TP + 2 * lane) = 0u; }
+                if (j < ldA) {
+#pragma unroll
+                    for (int h = 0; h < H; ++h) *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = 0u;     // padding columns stay zero
+                }
             }
+            __syncwarp();
+            if (j - 2 * lane < Nk64) outer_acc_64(X, Y, Z, H, lane, accWl);
+            __syncwarp();
         }
     }
     // CTA reduction of the partials -> part[blockIdx.x][...]: layout dWl[H*H], dbl[H], dWw[H*H], dbw[H]
+    for (int i = lane; i < NP; i += 32) redbuf[warp][i] = 0.f;
+    __syncwarp();
+    {
+        const int row = lane >> 2, col = (lane & 3) * 2;
+        if (row < H) {
+            if (col < H) { redbuf[warp][row * H + col] = accWl[0]; redbuf[warp][H * H + H + row * H + col] = accWw[0]; }
+            if (col + 1 < H) { redbuf[warp][row * H + col + 1] = accWl[1]; redbuf[warp][H * H + H + row * H + col + 1] = accWw[1]; }
+        }
+    }
 #pragma unroll
     for (int a = 0; a < H; ++a) {
-#pragma unroll
-        for (int c = 0; c < H; ++c) {
-            const float v1 = warp_sum(aWl[a][c]), v2 = warp_sum(aWw[a][c]);
-            if (lane == 0) { redbuf[warp][a * H + c] = v1; redbuf[warp][H * H + H + a * H + c] = v2; }
-        }
         const float v3 = warp_sum(abl[a]), v4 = warp_sum(abw[a]);
         if (lane == 0) { redbuf[warp][H * H + a] = v3; redbuf[warp][2 * H * H + H + a] = v4; }
     }
@@ -726,7 +754,7 @@ template <int H>
 static int talking_fwd_launch(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, int B, int Nq, int Nk,
                               int64_t ldS, int64_t ldA, cudaStream_t st) {
     SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 6.0, st);   // algorithmic bytes: S f32 read + A bf16 write
-    talking_fwd_kernel<H><<<talking_grid(B, Nq, 4), 256, 0, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, B * Nq, Nq, Nk, ldS, ldA);
+    talking_fwd_kernel<H><<<talking_grid(B, Nq, 2), 256, 0, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, B * Nq, Nq, Nk, ldS, ldA);
     SPE_LAUNCHED();
     return 0;
 }
@@ -743,7 +771,7 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(co
     }
 }
 
-static int talking_bwd_grid(int B, int Nq) { return talking_grid(B, Nq, 1); }
+static int talking_bwd_grid(int B, int Nq) { return talking_grid(B, Nq, 2); }
 
 extern "C" __attribute__((visibility("default"))) int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk) {
     (void)Nk;

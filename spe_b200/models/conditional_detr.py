@@ -149,16 +149,21 @@ class SetCriterion(nn.Module):
         det = tuple(l for l in self.losses if l in ("labels", "boxes", "cardinality"))
         losses = {}
 
-        def level(o, suffix, log):
-            res = CO.set_losses(o["pred_logits"], o["pred_boxes"], T, mw, self.focal_alpha, self.gamma, refine=self.refine, losses=det, log=log)
+        levels = [outputs] + list(outputs.get("aux_outputs", []))
+        # all decoder levels are matched by ONE cost launch + ONE batched LSAP launch (L*B independent problems)
+        r2g = CO.match_levels(torch.stack([l["pred_logits"].detach() for l in levels]), torch.stack([l["pred_boxes"].detach() for l in levels]), T, mw)
+
+        def level(i, o, suffix, log):
+            res = CO.set_losses(o["pred_logits"], o["pred_boxes"], T, mw, self.focal_alpha, self.gamma, refine=self.refine, losses=det, log=log,
+                                r2g=r2g[i])
             res.pop("_r2g")
             losses.update({k + suffix: v for k, v in res.items()})
 
-        level(outputs, "", True)
+        level(0, outputs, "", True)
         if "image_label" in self.losses:
             losses.update(self.loss_img_label(outputs, tg))
-        for i, aux in enumerate(outputs.get("aux_outputs", [])):
-            level(aux, f"_{i}", False)
+        for i in range(1, len(levels)):
+            level(i, levels[i], f"_{i - 1}", False)
         return losses
 
 

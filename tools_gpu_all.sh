@@ -1,7 +1,7 @@
 #!/bin/bash
 # full GPU validation: kernel tests, model tests, smoke, short bench with per-shape GEMM profile
 mkdir -p gpurun_out
-./tools_gpu_run.sh all "tests/test_kernels_gpu.py -k gemm" "tests/test_kernels_gpu.py -k 'not gemm'" "tests/test_model_gpu.py" > /dev/null 2>&1
+./tools_gpu_run.sh all "tests/test_kernels_gpu.py -k gemm" "tests/test_kernels_gpu.py -k 'not gemm'" "tests/test_model_gpu.py -k tiny" "tests/test_model_gpu.py -k 'not tiny'" > /dev/null 2>&1
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 rm -f gpurun_out/gemm_shapes.csv
 SPE_PROF_CSV=gpurun_out/gemm_shapes.csv timeout 1200 python bench.py --steps 4 --warmup 3 ${BENCH_ARGS:---no-cpu-baseline} > gpurun_out/bench.json 2> gpurun_out/bench.err
