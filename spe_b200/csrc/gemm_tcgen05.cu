@@ -373,14 +373,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 for (int g2 = 0; g2 < 2; ++g2) {                        // 2 groups of 8 columns
                     const int g = gg * 2 + g2;
                     const int n = nb + g * 8;
-                    // columns >= N are clipped by the TMA stores; keep their loads in bounds by clamping the vector address
-                    const int nl = min(n, ep.N - 8 >= 0 ? ((ep.N - 8) & ~3) : 0);
+                    // columns >= N are clipped by the TMA stores.  Per-column vectors (bias / gamma) of a group that straddles
+                    // or lies beyond N are fetched element-wise (warp-uniform rare path).
+                    const bool gfull = n + 8 <= ep.N;
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g2 * 8 + j]) * ep.alpha;
                     if (use_bias) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + nl)), b1v = __ldg(reinterpret_cast<const float4*>(ep.bias + nl + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1v.x; v[5] += b1v.y; v[6] += b1v.z; v[7] += b1v.w;
+                        if (gfull) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n)), b1v = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+                            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1v.x; v[5] += b1v.y; v[6] += b1v.z; v[7] += b1v.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) if (n + j < ep.N) v[j] += __ldg(ep.bias + n + j);
+                        }
                     }
                     if (has_xo) {
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sX + slab_off(lane, g)), "r"(pack_bf16x2(v[0], v[1])),
@@ -412,8 +418,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         }
                     }
                     if (ep.gamma) {
-                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + nl)), g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + nl + 4));
-                        v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+                        if (gfull) {
+                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n)), g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
+                            v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) if (n + j < ep.N) v[j] *= __ldg(ep.gamma + n + j);
+                        }
                     }
                     if (use_res) {
                         // fp32 residual: columns g*8..g*8+7 = slab (g/4), 16B chunks (g%4)*2, +1.  The C tile aliases these slabs:

@@ -37,14 +37,21 @@ def rup(x, m):
 # ------------------------------------------------------------------------------------------------
 # bf16 shadows of fp32 parameters (H4: reference-named fp32 nn.Parameters stay the source of truth)
 # ------------------------------------------------------------------------------------------------
-_shadow = {}
-
-
 def shadow(p):
-    """bf16 copy of an fp32 parameter (or of a slice view of one), refreshed when the parameter changes."""
-    key = (p.data_ptr(), tuple(p.shape))
-    ent = _shadow.get(key)
-    ver = p._version
+    """bf16 copy of an fp32 parameter (or of a slice view of one), refreshed when the parameter changes.
+    The cache lives ON the (base) parameter object, so it can never be confused with another tensor that later
+    reuses the same device address."""
+    base = p._base if p._base is not None else p
+    cache = base.__dict__.get("_spe_shadow")
+    if cache is None:
+        cache = {}
+        try:
+            base._spe_shadow = cache
+        except Exception:
+            pass
+    key = (p.storage_offset(), tuple(p.shape), tuple(p.stride()))
+    ver = base._version
+    ent = cache.get(key)
     if ent is not None and ent[0] == ver and ent[1].device == p.device:
         return ent[1]
     src = p.detach()
@@ -52,12 +59,13 @@ def shadow(p):
         src = src.contiguous()
     out = ent[1] if ent is not None and ent[1].device == p.device else torch.empty(p.shape, dtype=torch.bfloat16, device=p.device)
     axpby_cast(src, None, 1.0, 0.0, out_bf16=out)
-    _shadow[key] = (ver, out)
+    cache[key] = (ver, out)
     return out
 
 
 def clear_shadows():
-    _shadow.clear()
+    """kept for API stability: shadows are owned by their parameters and die with them."""
+    return None
 
 
 # ------------------------------------------------------------------------------------------------
