@@ -107,6 +107,8 @@ int spe_layerscale_bwd(const float* dout, const void* y_bf16, const float* gamma
                        void* dy_bf16, float* dgamma, float* dbias, void* stream);
 /* column sums of a bf16 [rows, N] (ld) matrix, accumulated into out f32 [N] (bias gradients) */
 int spe_colsum_bf16(const void* x, int64_t rows, int N, int64_t ld, float* out, void* stream);
+/* batched: x bf16 [batch][rows][N] (row pitch ld, batch pitch batch_stride) -> out f32 [batch][N] (accumulated) */
+int spe_colsum_bf16_batched(const void* x, int batch, int64_t rows, int N, int64_t ld, int64_t batch_stride, float* out, void* stream);
 /* y_bf16 = (a*x + b*y) with f32 inputs (y may be NULL); also optional f32 output */
 int spe_axpby_cast(const float* x, const float* y, float a, float b, int64_t n, void* out_bf16, float* out_f32,
                    void* stream);
@@ -159,9 +161,10 @@ int spe_lsap_batched(const float* cost, int B, int nr, int64_t ldc, const int32_
  *   inv_num_boxes: device f32 scalar (1/num_boxes, conditional_detr.py:436-440)
  * outputs: out[0]=loss_ce, out[1]=class_error, out[2]=cardinality_error (f32[3]);
  *          dlogits f32 [B,Q,C] = d loss_ce / d logits (may be NULL). */
+int64_t spe_focal_loss_workspace_bytes(int B, int Q);
 int spe_focal_loss(const float* logits, const int32_t* row_to_gt, const int32_t* gt_labels, const int32_t* gt_off,
                    const float* gt_scores, const float* inv_num_boxes, int B, int Q, int C, float alpha, float gamma,
-                   float* out, float* dlogits, void* stream);
+                   float* out, float* dlogits, void* workspace, void* stream);
 /* L1 + GIoU on matched pairs (diag only; conditional_detr.py:300-319 / :540-561).
  * out[0]=loss_bbox, out[1]=loss_giou; dboxes f32 [B,Q,4] receives w_l1*dL1 + w_giou*dGIoU?  No: two planes
  * dboxes_l1 and dboxes_giou (each [B,Q,4], zero on unmatched rows; may be NULL). */

@@ -47,6 +47,7 @@ _SIGS = {
     "spe_softmax_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_p]),
     "spe_layerscale_bwd": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
     "spe_colsum_bf16": (c_i, [c_p, c_l, c_i, c_l, c_p, c_p]),
+    "spe_colsum_bf16_batched": (c_i, [c_p, c_i, c_l, c_i, c_l, c_l, c_p, c_p]),
     "spe_axpby_cast": (c_i, [c_p, c_p, c_f, c_f, c_l, c_p, c_p, c_p]),
     "spe_cast_bf16_to_f32": (c_i, [c_p, c_p, c_l, c_p]),
     "spe_add_bf16_into_f32": (c_i, [c_p, c_p, c_l, c_p]),
@@ -60,7 +61,8 @@ _SIGS = {
     "spe_match_cost": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_l, c_p]),
     "spe_lsap_workspace_bytes": (c_l, [c_i, c_i, c_i]),
     "spe_lsap_batched": (c_i, [c_p, c_i, c_i, c_l, c_p, c_i, c_p, c_p, c_p]),
-    "spe_focal_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
+    "spe_focal_loss_workspace_bytes": (c_l, [c_i, c_i]),
+    "spe_focal_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p]),
     "spe_box_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "spe_bce_logits": (c_i, [c_p, c_p, c_l, c_p, c_p, c_p]),
     "spe_box_iou_pairwise": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),

@@ -128,8 +128,9 @@ class FocalLossFn(torch.autograd.Function):
         out = torch.empty(3, dtype=torch.float32, device=logits.device)
         dl = torch.empty_like(lg)
         sc = T.scores if use_scores else None
+        ws = torch.empty(lib().spe_focal_loss_workspace_bytes(B, Q), dtype=torch.uint8, device=logits.device)
         check(lib().spe_focal_loss(ptr(lg), ptr(r2g), ptr(T.labels), ptr(T.offsets), ptr(sc), ptr(T.inv_num_boxes()), B, Q, C, float(alpha),
-                                   float(gamma), ptr(out), ptr(dl), stream()))
+                                   float(gamma), ptr(out), ptr(dl), ptr(ws), stream()))
         ctx.save_for_backward(dl)
         return out
 

@@ -8,19 +8,17 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // focal classification loss + class_error + cardinality_error  (single CTA: B*Q*C is ~2e5 elements)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) focal_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__ row_to_gt,
-                                                          const int32_t* __restrict__ gt_labels, const int32_t* __restrict__ gt_off,
-                                                          const float* __restrict__ gt_scores, const float* __restrict__ inv_num_boxes,
-                                                          int B, int Q, int C, float alpha, float gamma, float* __restrict__ out,
-                                                          float* __restrict__ dlogits) {
+// stage 1: one warp per (b,q) row -> per-CTA partials {loss, correct, matched} + per-image "object" counts (atomics on ints)
+__global__ void __launch_bounds__(256) focal_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__ row_to_gt,
+                                                         const int32_t* __restrict__ gt_labels, const int32_t* __restrict__ gt_off,
+                                                         const float* __restrict__ gt_scores, const float* __restrict__ inv_num_boxes,
+                                                         int B, int Q, int C, float alpha, float gamma, float* __restrict__ part,
+                                                         int* __restrict__ card, float* __restrict__ dlogits) {
     __shared__ float red[32];
-    __shared__ int card[1024];          // per-image count of "object" predictions (B <= 1024)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int b = tid; b < B; b += blockDim.x) card[b] = 0;
-    __syncthreads();
     const float inb = *inv_num_boxes;
     float loss_sum = 0.f, correct = 0.f, matched = 0.f;
-    for (int row = warp; row < B * Q; row += nwarps) {
+    for (int row = blockIdx.x * nwarps + warp; row < B * Q; row += gridDim.x * nwarps) {
         const int b = row / Q;
         const int g = row_to_gt[row];
         const int g0 = gt_off[b];
@@ -53,7 +51,7 @@ __global__ void __launch_bounds__(1024) focal_loss_kernel(const float* __restric
             if (dlogits) {
                 const float dce = p - t;                                   // d ce / dx
                 const float dpt = (t > 0.5f ? 1.f : -1.f) * p * (1.f - p);  // d p_t / dx
-                const float dmod = clamped ? 0.f : -gamma * powf(om, gamma - 1.f) * dpt;
+                const float dmod = clamped ? 0.f : -gamma * (mod / om) * dpt;
                 dlogits[(long long)row * C + c] = w * at * (dce * mod + ce * dmod) * inb;
             }
             if (xv > best || (xv == best && c < besti)) { best = xv; besti = c; }
@@ -65,20 +63,29 @@ __global__ void __launch_bounds__(1024) focal_loss_kernel(const float* __restric
             if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
         }
         if (lane == 0) {
-            if (besti != C - 1) atomicAdd(&card[b], 1);            // :293-295
+            if (besti != C - 1) atomicAdd(&card[b], 1);            // :293-295 (integer atomics: deterministic)
             if (g >= 0) { matched += 1.f; if (besti == label) correct += 1.f; }
         }
     }
     loss_sum = block_sum(loss_sum, red);
     correct = block_sum(correct, red);
     matched = block_sum(matched, red);
-    float cerr = 0.f;
-    for (int b = tid; b < B; b += blockDim.x) cerr += fabsf((float)card[b] - (float)(gt_off[b + 1] - gt_off[b]));
-    cerr = block_sum(cerr, red);
-    if (tid == 0) {
-        out[0] = loss_sum * inb;                                                    // mean(1).sum()/num_boxes*Q
-        out[1] = matched > 0.f ? 100.f - correct * (100.f / matched) : 100.f;       // util/misc.py:440-455
-        out[2] = cerr / (float)B;                                                   // F.l1_loss mean
+    if (tid == 0) { part[blockIdx.x * 3 + 0] = loss_sum; part[blockIdx.x * 3 + 1] = correct; part[blockIdx.x * 3 + 2] = matched; }
+}
+
+// stage 2: deterministic reduction of the per-CTA partials
+__global__ void __launch_bounds__(256) focal_loss_finalize_kernel(const float* __restrict__ part, int nblocks, const int* __restrict__ card,
+                                                                  const int32_t* __restrict__ gt_off, const float* __restrict__ inv_num_boxes, int B,
+                                                                  float* __restrict__ out) {
+    __shared__ float red[32];
+    float l = 0.f, c = 0.f, m = 0.f, e = 0.f;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) { l += part[i * 3]; c += part[i * 3 + 1]; m += part[i * 3 + 2]; }
+    for (int b = threadIdx.x; b < B; b += blockDim.x) e += fabsf((float)card[b] - (float)(gt_off[b + 1] - gt_off[b]));
+    l = block_sum(l, red); c = block_sum(c, red); m = block_sum(m, red); e = block_sum(e, red);
+    if (threadIdx.x == 0) {
+        out[0] = l * (*inv_num_boxes);                                             // mean(1).sum()/num_boxes*Q
+        out[1] = m > 0.f ? 100.f - c * (100.f / m) : 100.f;                        // util/misc.py:440-455
+        out[2] = e / (float)B;                                                     // F.l1_loss mean
     }
 }
 
@@ -177,13 +184,24 @@ __global__ void box_iou_pairwise_kernel(const float* __restrict__ a, int N, cons
 
 }  // namespace
 
+extern "C" __attribute__((visibility("default"))) int64_t spe_focal_loss_workspace_bytes(int B, int Q) {
+    const int blocks = (B * Q + 7) / 8 < 4 * spe_num_sms() ? (B * Q + 7) / 8 : 4 * spe_num_sms();
+    return (int64_t)blocks * 3 * 4 + (int64_t)B * 4;
+}
+
 extern "C" __attribute__((visibility("default"))) int spe_focal_loss(const float* logits, const int32_t* row_to_gt, const int32_t* gt_labels, const int32_t* gt_off,
                               const float* gt_scores, const float* inv_num_boxes, int B, int Q, int C, float alpha, float gamma, float* out,
-                              float* dlogits, void* stream) {
-    SPE_CHECK(logits && row_to_gt && gt_labels && gt_off && inv_num_boxes && out, "spe_focal_loss: null argument");
-    SPE_CHECK(B > 0 && B <= 1024 && Q > 0 && C > 0, "spe_focal_loss: bad shape (B<=1024)");
-    focal_loss_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, row_to_gt, gt_labels, gt_off, gt_scores, inv_num_boxes, B, Q,
-                                                                              C, alpha, gamma, out, dlogits);
+                              float* dlogits, void* workspace, void* stream) {
+    SPE_CHECK(logits && row_to_gt && gt_labels && gt_off && inv_num_boxes && out && workspace, "spe_focal_loss: null argument");
+    SPE_CHECK(B > 0 && Q > 0 && C > 0, "spe_focal_loss: bad shape");
+    const int blocks = (B * Q + 7) / 8 < 4 * spe_num_sms() ? (B * Q + 7) / 8 : 4 * spe_num_sms();
+    float* part = reinterpret_cast<float*>(workspace);
+    int* card = reinterpret_cast<int*>(part + (size_t)blocks * 3);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SPE_CUDA(cudaMemsetAsync(card, 0, (size_t)B * 4, st));
+    focal_loss_kernel<<<blocks, 256, 0, st>>>(logits, row_to_gt, gt_labels, gt_off, gt_scores, inv_num_boxes, B, Q, C, alpha, gamma, part, card, dlogits);
+    SPE_LAUNCHED();
+    focal_loss_finalize_kernel<<<1, 256, 0, st>>>(part, blocks, card, gt_off, inv_num_boxes, B, out);
     SPE_LAUNCHED();
     return 0;
 }

@@ -30,7 +30,8 @@ constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr uint32_t CHUNK_BYTES = 64 * BK * 2;   // one 64(mn) x 64(k) MN-major TMA box
 constexpr uint32_t SLAB = 4096;                 // 32 rows x 128 B
-constexpr uint32_t EPI_SMEM = NUM_EPI_WARPS * 3 * SLAB;
+constexpr int EPI_SLABS = 4;                   // per epilogue warp: two sets of {RC0, RC1|X} so TMA stores of tile i overlap tile i+1
+constexpr uint32_t EPI_SMEM = NUM_EPI_WARPS * EPI_SLABS * SLAB;
 
 struct EpiParams {
     void* C; int c_dtype; long long ldc, c_sb1, c_sb2;
@@ -44,6 +45,7 @@ struct EpiParams {
     int tma_io;                   // epilogue tiles through TMA (else direct per-thread global access)
     int splits, kb_per_split;     // split-K
     int tiles_m, tiles_n, num_tiles;
+    int dbg;                      // timing experiments only (SPE_GEMM_DBG bitmask): 1 no TMA store, 2 no smem writes, 4 no TMEM load, 8 no proxy fence
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    uint8_t* sEpi = sB + STAGES * B_BYTES;                                  // 8 warps x 3 slabs
+    uint8_t* sEpi = sB + STAGES * B_BYTES;                                  // 8 warps x 4 slabs
     uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_SMEM);          // full[S], empty[S], tfull[2], tempty[2], ebar[8]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NUM_EPI_WARPS);
 
@@ -297,7 +299,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         const int e = warp - EPI_WARP0;
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)   (hardware: warp%4)
         const int half = e >> 2;                      // which 64-column super-chunks this warp owns
-        const uint32_t sRC = smem_u32(sEpi + e * 3 * SLAB), sX = sRC + 2 * SLAB;
+        const uint32_t sBase = smem_u32(sEpi + e * EPI_SLABS * SLAB);
+        // slab assignment: C (+ residual, which it overlays) needs 2 slabs when fp32 is involved, aux needs 1.
+        //   footprint <= 2 slabs -> two alternating sets {0,1} / {2,3}: the bulk stores of one super-chunk drain while the next is
+        //   produced (wait_group.read 1);  footprint 3 -> slabs {0,1} + {2}, single-buffered (wait_group.read 0).
+        const bool wide = ep.c_dtype == SPE_DT_F32 || ep.residual != nullptr;
+        const bool alternate = !(wide && (ep.aux_in != nullptr || ep.aux_out != nullptr));
+        uint32_t set = 0;
         const uint32_t ebar = ebar0 + 8 * e;
         const bool has_r = ep.residual != nullptr, has_xi = ep.aux_in != nullptr, has_xo = ep.aux_out != nullptr;
         const bool c32 = ep.c_dtype == SPE_DT_F32;
@@ -317,11 +325,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 const int nb = n0 + sc * 64;
                 const bool live = nb < ep.N && mrow < ep.M;
                 const bool loads = live && ep.tma_io && ((has_r && lead) || has_xi);
+                const uint32_t sRC = sBase + (alternate ? set * 2 * SLAB : 0u);
+                const uint32_t sX = alternate ? sRC + SLAB : sBase + 2 * SLAB;
                 if (live && ep.tma_io && stores_pending) {
-                    // the previous bulk stores must have finished READING this warp's slabs before they are refilled
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    // earlier bulk stores must have finished READING the slabs that are refilled now
+                    if (lane == 0) {
+                        if (alternate) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     __syncwarp();
-                    stores_pending = false;
                 }
                 if (loads && lane == 0) {
                     const bool two = nb + 32 < ep.N;
@@ -360,8 +372,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 #pragma unroll 1
                 for (int gg = 0; gg < 4; ++gg) {                        // rolled: 4 x 16 accumulator columns (keeps the code in the I-cache)
                 uint32_t r[16];
-                TMEM_LD_32x32b_X16(taddr + gg * 16, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!(ep.dbg & 4)) {
+                    TMEM_LD_32x32b_X16(taddr + gg * 16, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = 0u;
+                }
                 if (gg == 3 && last_sc) {
                     // last TMEM read of this warp for this tile: hand the accumulator buffer back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -435,7 +452,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w) : "r"(sl + slab_off(lane, (g & 3) * 2 + 1)));
                         v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
                     }
-                    if (c32) {
+                    if (ep.dbg & 2) {
+                        if (v[0] == 123.456f) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRC), "f"(v[1] + v[2] + v[3] + v[4] + v[5] + v[6] + v[7]) : "memory");
+                    } else if (c32) {
                         const uint32_t sl = sRC + (g >> 2) * SLAB;
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + slab_off(lane, (g & 3) * 2)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + slab_off(lane, (g & 3) * 2 + 1)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
@@ -446,9 +465,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     }
                 }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (!(ep.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !(ep.dbg & 1)) {
                     if (ep.splits > 1) {
                         tma_reduce_add_4d(&tmC, sRC, nb, mrow, b2, b1);
                         if (nb + 32 < ep.N) tma_reduce_add_4d(&tmC, sRC + SLAB, nb + 32, mrow, b2, b1);
@@ -462,6 +481,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 stores_pending = true;
+                set ^= 1u;
             }
             if (!arrived) {
                 // this warp owns no super-chunk of the tile (BN = 64, upper half): still release the buffer
@@ -613,6 +633,7 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     if (tma_io && a->aux_in && make_tmap_io(&io.Xi, a->aux_in, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
     if (tma_io && a->aux_out && make_tmap_io(&io.Xo, a->aux_out, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
     ep.tma_io = tma_io ? 1 : 0;
+    { const char* d = getenv("SPE_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; }
     // ---- split-K: few output tiles but a long reduction (wgrad).  fp32 contiguous C, no activation / aux / gamma.
     const int total_kb = (a->K + BK - 1) / BK;
     ep.tiles_m = (a->M + BM - 1) / BM;
@@ -635,5 +656,5 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     if (g_spe_prof_on) snprintf(tag, sizeof(tag), "M%d N%d K%d b%d a%d b%d c%d", a->M, a->N, a->K, batch, a->a_major, a->b_major, a->c_dtype);
     SpeProfScope prof(SPE_FAM_GEMM, 2.0 * a->M * a->N * (double)a->K * batch, st, tag);     // algorithmic flops
     if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);
-    return dispatch_major<128, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);
+    return dispatch_major<128, 3>(a->a_major, a->b_major, tA, tB, io, ep, st);
 }

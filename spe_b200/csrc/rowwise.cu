@@ -200,131 +200,161 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const uint16_t* __rest
 //         registers across all rows of a CTA and are reduced once at the end (deterministic two-stage reduction).
 //   The H x H mixes are FP32 FMAs against weights broadcast from shared memory (FP32/MUFU bound).
 // ------------------------------------------------------------------------------------------------
-// mixed logits of 2 adjacent keys for all heads: a[g][c] = bl[g] + sum_h Wl[g][h] s[h][c]   (weights: 16-byte broadcast LDS)
+// =================================================================================================
+// Talking-heads kernels, tensor-path formulation.
+// One warp per (b, q) row, 32 keys per step.  Every H x H head mix runs as mma.sync.m16n8k16 (bf16 inputs, fp32
+// accumulate) with split-precision operands so the result keeps ~16 mantissa bits:
+//     A (16 x 16) = [ W_hi | W_hi ]   rows 0-7       B (16 x 8) = [ x_hi ]  k 0-7   (x = logits / probabilities, fp32)
+//                   [ W_lo | W_lo ]   rows 8-15                   [ x_lo ]  k 8-15
+//     D rows 0-7 + D rows 8-15  =  (W_hi + W_lo)(x_hi + x_lo)
+// Lane (q4 = lane/4, r4 = lane%4) owns head q4 and 8 contiguous keys [base + 8 r4, +8) in the accumulator layout, and heads
+// (2 r4, 2 r4 + 1) at 4 keys [base + 4 q4, +4) in the B-operand layout; tile t of a step maps mma column n to key
+// base + 4 n + t, so both layouts are contiguous in memory.  movmatrix.trans converts accumulator -> B-operand layout.
+// The H x H parameter-gradient outer products are mma.sync accumulations over the keys as well.
+// =================================================================================================
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+// split (x, y) into packed bf16 hi parts and packed bf16 lo (residual) parts
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(x, y);
+    const float2 h = unpack_bf16x2(hi);
+    lo = pack_bf16x2(x - h.x, y - h.y);
+}
+
+struct MixFrag { uint32_t hi, lo; };     // A-operand registers of one H x H matrix M[row][k]: a0 = a2 = hi, a1 = a3 = lo
+
 template <int H>
-__device__ __forceinline__ void mix2(const float* __restrict__ W, const float* __restrict__ bias, const float (&x)[H][2], float (&a)[H][2]) {
+__device__ __forceinline__ MixFrag load_mix_frag(const float* __restrict__ M, bool transpose, float scale, int q4, int r4) {
+    float w0 = 0.f, w1 = 0.f;
+    if (q4 < H) {
+        const int k0 = 2 * r4, k1 = 2 * r4 + 1;
+        if (k0 < H) w0 = scale * (transpose ? M[k0 * H + q4] : M[q4 * H + k0]);
+        if (k1 < H) w1 = scale * (transpose ? M[k1 * H + q4] : M[q4 * H + k1]);
+    }
+    MixFrag f;
+    split2(w0, w1, f.hi, f.lo);
+    return f;
+}
+// x (B-operand layout, split precision) -> W x for the lane's head q4 at mma columns 2 r4, 2 r4 + 1
+__device__ __forceinline__ void mix_tile(const MixFrag& W, uint32_t bhi, uint32_t blo, float bias, float& o0, float& o1) {
+    float d[4] = {bias, bias, 0.f, 0.f};
+    mma16816(d, W.hi, W.lo, W.hi, W.lo, bhi, blo);
+    o0 = d[0] + d[2]; o1 = d[1] + d[3];
+}
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+// raw S of one 32-key step in the B-operand layout: 4 keys [base + 4 q4, +4) of heads 2 r4 and 2 r4 + 1
+struct SRaw { float4 s0, s1; };
+template <int H>
+__device__ __forceinline__ SRaw load_sraw(const float* __restrict__ Sb, long long hS, int base, long long ldS, int q4, int r4) {
+    SRaw r;
+    r.s0 = make_float4(0.f, 0.f, 0.f, 0.f); r.s1 = r.s0;
+    const int cb = base + 4 * q4;
+    if (cb + 4 <= ldS) {
+        if (2 * r4 < H) r.s0 = __ldg(reinterpret_cast<const float4*>(Sb + (2 * r4) * hS + cb));
+        if (2 * r4 + 1 < H) r.s1 = __ldg(reinterpret_cast<const float4*>(Sb + (2 * r4 + 1) * hS + cb));
+    }
+    return r;
+}
+// logits of one 32-key step in the accumulator layout: L2[i] = log2(e) * L[q4][base + 8 r4 + i]   (-inf beyond Nk)
+// also returns the hi parts of the split B-operand registers of S (reused by the dWl outer product)
+template <int H>
+__device__ __forceinline__ void step_logits(const SRaw& raw, int base, int Nk, const MixFrag& Wl, float bl2, int q4, int r4, float (&L2)[8],
+                                            uint32_t (&shi)[4]) {
+    const int cb = base + 4 * q4;
+    const float a0[4] = {raw.s0.x, raw.s0.y, raw.s0.z, raw.s0.w}, a1[4] = {raw.s1.x, raw.s1.y, raw.s1.z, raw.s1.w};
 #pragma unroll
-    for (int g = 0; g < H; ++g) {
-        float a0 = bias ? bias[g] : 0.f, a1 = a0;
-        if constexpr (H % 4 == 0) {
+    for (int t = 0; t < 4; ++t) {
+        const bool ok = cb + t < Nk;                // padding columns of S are never written: sanitise
+        uint32_t lo;
+        split2(ok ? a0[t] : 0.f, ok ? a1[t] : 0.f, shi[t], lo);
+        mix_tile(Wl, shi[t], lo, bl2, L2[t], L2[4 + t]);
+    }
+    const int c8 = base + 8 * r4;
 #pragma unroll
-            for (int h = 0; h < H; h += 4) {
-                const float4 wv = *reinterpret_cast<const float4*>(W + g * H + h);
-                a0 += wv.x * x[h][0]; a1 += wv.x * x[h][1];
-                a0 += wv.y * x[h + 1][0]; a1 += wv.y * x[h + 1][1];
-                a0 += wv.z * x[h + 2][0]; a1 += wv.z * x[h + 2][1];
-                a0 += wv.w * x[h + 3][0]; a1 += wv.w * x[h + 3][1];
-            }
-        } else {
+    for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) L2[i] = -INFINITY;
+}
+
+// sweep A: m2[q4] = max_j L2, iz = 1 / sum_j 2^(L2 - m2)     (values for the lane's head q4, identical in its 4 lanes)
+template <int H>
+__device__ __forceinline__ void talking_stats2(const float* __restrict__ Sb, long long hS, int Nk, long long ldS, const MixFrag& Wl, float bl2, int q4,
+                                               int r4, float& m2, float& iz) {
+    float m = -INFINITY, z = 0.f;
+    SRaw nxt = load_sraw<H>(Sb, hS, 0, ldS, q4, r4);
+    for (int base = 0; base < Nk; base += 32) {
+        const SRaw cur = nxt;
+        if (base + 32 < Nk) nxt = load_sraw<H>(Sb, hS, base + 32, ldS, q4, r4);      // prefetch one step ahead
+        float L2[8];
+        uint32_t shi[4];
+        step_logits<H>(cur, base, Nk, Wl, bl2, q4, r4, L2, shi);
+        float mx = L2[0];
 #pragma unroll
-            for (int h = 0; h < H; ++h) { const float wv = W[g * H + h]; a0 += wv * x[h][0]; a1 += wv * x[h][1]; }
+        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, L2[i]);
+        const float mn = fmaxf(m, mx);
+        if (mn > -INFINITY) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc += exp2f(L2[i] - mn);
+            z = z * exp2f(m - mn) + acc;
+            m = mn;
         }
-        a[g][0] = a0; a[g][1] = a1;
     }
+    float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 2));
+    float zz = (m == -INFINITY) ? 0.f : z * exp2f(m - M);
+    zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+    zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+    m2 = M;
+    iz = 1.f / zz;
 }
 
 template <int H>
-struct __align__(16) MixWT {       // weights + transposed copies (so both W x and W^T x read contiguous float4 rows)
-    float Wl[H * H], Ww[H * H], WlT[H * H], WwT[H * H], bl[H], bw[H];
-};
-
-template <int H>
-__device__ __forceinline__ void load_mixT(MixWT<H>* sm, const float* Wl, const float* bl, const float* Ww, const float* bw) {
-    for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
-        const int r = i / H, c = i % H;
-        sm->Wl[i] = Wl[i]; sm->Ww[i] = Ww[i];
-        sm->WlT[c * H + r] = Wl[i]; sm->WwT[c * H + r] = Ww[i];
-    }
-    if (threadIdx.x < H) { sm->bl[threadIdx.x] = bl[threadIdx.x]; sm->bw[threadIdx.x] = bw ? bw[threadIdx.x] : 0.f; }
-    __syncthreads();
-}
-
-template <int H>
-__device__ __forceinline__ void load_s2(const float* __restrict__ Sb, long long hS, int j, bool two, float pad, float (&s)[H][2]) {
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-        const float2 t = *reinterpret_cast<const float2*>(Sb + h * hS + j);
-        s[h][0] = t.x; s[h][1] = two ? t.y : pad;
-    }
-}
-
-// sweep A: per-row softmax statistics of the mixed logits.  Returns m[g] (row max) and iz[g] (1/sum).
-template <int H>
-__device__ __forceinline__ void talking_stats(const float* __restrict__ Sb, long long hS, int Nk, const MixWT<H>* w, int lane, float* m, float* iz) {
-    float z[H];
-#pragma unroll
-    for (int g = 0; g < H; ++g) { m[g] = -INFINITY; z[g] = 0.f; }
-    for (int j = 2 * lane; j < Nk; j += 64) {
-        const bool two = j + 1 < Nk;
-        float s[H][2], a[H][2];
-        load_s2<H>(Sb, hS, j, two, 0.f, s);
-        mix2<H>(w->Wl, w->bl, s, a);
-#pragma unroll
-        for (int g = 0; g < H; ++g) {
-            const float a1 = two ? a[g][1] : -INFINITY;
-            const float mn = fmaxf(m[g], fmaxf(a[g][0], a1));
-            z[g] = z[g] * __expf(m[g] - mn) + (__expf(a[g][0] - mn) + __expf(a1 - mn));
-            m[g] = mn;
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < H; ++g) {
-        const float M = warp_max(m[g]);
-        const float zz = warp_sum(m[g] == -INFINITY ? 0.f : z[g] * __expf(m[g] - M));
-        m[g] = M;
-        iz[g] = 1.f / zz;
-    }
-}
-
-template <int H>
-__global__ void __launch_bounds__(256, 2) talking_fwd_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
+__global__ void __launch_bounds__(256, 3) talking_fwd_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
                                                              const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
                                                              int rows_total, int Nq, int Nk, long long ldS, long long ldA) {
-    __shared__ MixWT<H> w;
-    load_mixT<H>(&w, Wl, bl, Ww, bw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q4 = lane >> 2, r4 = lane & 3;
+    const MixFrag fWl = load_mix_frag<H>(Wl, false, LOG2E, q4, r4), fWw = load_mix_frag<H>(Ww, false, 1.f, q4, r4);
+    const float bl2 = q4 < H ? bl[q4] * LOG2E : 0.f, bwv = q4 < H ? bw[q4] : 0.f;
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
     for (int rowi = blockIdx.x * 8 + warp; rowi < rows_total; rowi += gridDim.x * 8) {
         const int b = rowi / Nq, q = rowi % Nq;
         const float* Sb = S + ((long long)b * H * Nq + q) * ldS;
         uint16_t* Ab = A + ((long long)b * H * Nq + q) * ldA;
-        float m[H], iz[H];
-        talking_stats<H>(Sb, hS, Nk, &w, lane, m, iz);
-        for (int j = 2 * lane; j < ldA; j += 64) {
-            if (j >= Nk) {                                  // keep the padding columns [Nk, ldA) zero
+        float m2, iz;
+        talking_stats2<H>(Sb, hS, Nk, ldS, fWl, bl2, q4, r4, m2, iz);
+        const float c2 = m2 - log2f(iz);            // p = 2^(L2 - m2) * iz = 2^(L2 - c2)
+        SRaw nxt = load_sraw<H>(Sb, hS, 0, ldS, q4, r4);
+        for (int base = 0; base < ldA; base += 32) {
+            const SRaw cur = nxt;
+            if (base + 32 < ldA) nxt = load_sraw<H>(Sb, hS, base + 32, ldS, q4, r4);
+            float L2[8], out[8];
+            uint32_t shi[4];
+            step_logits<H>(cur, base, Nk, fWl, bl2, q4, r4, L2, shi);
+            float p[8];
 #pragma unroll
-                for (int o = 0; o < H; ++o) *reinterpret_cast<uint32_t*>(Ab + o * hA + j) = 0u;
-                continue;
+            for (int i = 0; i < 8; ++i) p[i] = exp2f(L2[i] - c2);          // 0 beyond Nk (L2 = -inf)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint32_t hi, lo;
+                split2(p[t], p[4 + t], hi, lo);
+                mix_tile(fWw, movm_trans(hi), movm_trans(lo), bwv, out[t], out[4 + t]);
             }
-            const bool two = j + 1 < Nk;
-            float s[H][2], p[H][2], a[H][2];
-            load_s2<H>(Sb, hS, j, two, 0.f, s);
-            mix2<H>(w.Wl, w.bl, s, a);
+            const int c8 = base + 8 * r4;
+            if (q4 < H && c8 + 8 <= ldA) {
 #pragma unroll
-            for (int g = 0; g < H; ++g) { p[g][0] = __expf(a[g][0] - m[g]) * iz[g]; p[g][1] = two ? __expf(a[g][1] - m[g]) * iz[g] : 0.f; }
-            mix2<H>(w.Ww, w.bw, p, a);
-#pragma unroll
-            for (int o = 0; o < H; ++o) *reinterpret_cast<uint32_t*>(Ab + o * hA + j) = pack_bf16x2(a[o][0], two ? a[o][1] : 0.f);
+                for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) out[i] = 0.f;    // keep the padding columns [Nk, ldA) zero
+                *reinterpret_cast<uint4*>(Ab + q4 * hA + c8) =
+                    make_uint4(pack_bf16x2(out[0], out[1]), pack_bf16x2(out[2], out[3]), pack_bf16x2(out[4], out[5]), pack_bf16x2(out[6], out[7]));
+            }
         }
-    }
-}
-
-// ---- warp-level outer-product accumulation  D[x_row][y_row] += sum_cols X[x_row][c] * Y[y_row][c]  on the legacy tensor path
-// (mma.sync m16n8k16 bf16, fp32 accumulate): the H x H parameter-gradient sums of the head mixes cost ~12 instructions per
-// 64 keys instead of 128 FMAs + 128 persistent accumulator registers per thread.
-constexpr int TP = 72;                      // bf16 row pitch (144 B): ldmatrix rows land in distinct banks
-__device__ __forceinline__ void outer_acc_64(const uint16_t* X, const uint16_t* Y, const uint16_t* Z, int H, int lane, float (&acc)[4]) {
-    // X, Y: [8][TP] bf16 (rows >= H unused), Z: zero row.  4 k-steps of 16 columns.
-    const int mi = lane >> 3, r = lane & 7;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        const uint16_t* pa = ((mi & 1) || r >= H) ? Z : X + r * TP + kk * 16 + (mi >> 1) * 8;
-        const uint16_t* pb = (r >= H) ? Z : Y + r * TP + kk * 16 + (mi & 1) * 8;
-        uint32_t a0, a1, a2, a3, b0, b1;
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"((uint32_t)__cvta_generic_to_shared(pa)));
-        asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"((uint32_t)__cvta_generic_to_shared(pb)));
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                     : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
     }
 }
 
@@ -333,118 +363,118 @@ template <int H>
 __global__ void __launch_bounds__(256, 2) talking_bwd_kernel(const float* __restrict__ S, const uint16_t* dA, uint16_t* dS,
                                                              const float* __restrict__ Wl, const float* __restrict__ bl, const float* __restrict__ Ww,
                                                              int rows_total, int Nq, int Nk, long long ldS, long long ldA, float* __restrict__ part) {
-    __shared__ MixWT<H> w;
     constexpr int NP = 2 * H * H + 2 * H;
     __shared__ float redbuf[8][NP];
-    __shared__ __align__(16) uint16_t tiles[8][17][TP];      // per warp: X rows 0..7, Y rows 8..15, zero row 16
-    load_mixT<H>(&w, Wl, bl, Ww, nullptr);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q4 = lane >> 2, r4 = lane & 3;
+    const MixFrag fWl = load_mix_frag<H>(Wl, false, LOG2E, q4, r4);      // L2 = log2e (Wl S + bl)
+    const MixFrag fWwT = load_mix_frag<H>(Ww, true, 1.f, q4, r4);        // dP = Ww^T dA
+    const MixFrag fWlT = load_mix_frag<H>(Wl, true, 1.f, q4, r4);        // dS = Wl^T dL
+    const float bl2 = q4 < H ? bl[q4] * LOG2E : 0.f;
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
-    uint16_t* X = &tiles[warp][0][0];
-    uint16_t* Y = &tiles[warp][8][0];
-    uint16_t* Z = &tiles[warp][16][0];
-    for (int i = lane; i < 17 * TP; i += 32) X[i] = 0;
-    __syncwarp();
 
-    float accWw[4] = {0.f, 0.f, 0.f, 0.f}, accWl[4] = {0.f, 0.f, 0.f, 0.f};     // mma fragments: rows lane/4, cols (lane%4)*2+{0,1}
-    float abw[H], abl[H];
+    float accWw[4] = {0.f, 0.f, 0.f, 0.f}, accWl[4] = {0.f, 0.f, 0.f, 0.f};     // [row q4][col 2 r4 + {0,1}] of dWw[o][g], dWl[g][h]
+    float abw = 0.f, abl = 0.f;                                                  // dbw[q4], dbl[q4] lane partials
+
+    // dA of one step in the accumulator layout (head q4, 8 contiguous keys), sanitised beyond Nk
+    auto load_dA_raw = [&](const uint16_t* dAb, int base) {
+        const int c8 = base + 8 * r4;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (q4 < H && c8 + 8 <= ldA) v = *reinterpret_cast<const uint4*>(dAb + q4 * hA + c8);
+        return v;
+    };
+    auto unpack_dA = [&](const uint4& v, int base, float (&d)[8]) {
+        const int c8 = base + 8 * r4;
+        float2 t;
+        t = unpack_bf16x2(v.x); d[0] = t.x; d[1] = t.y;
+        t = unpack_bf16x2(v.y); d[2] = t.x; d[3] = t.y;
+        t = unpack_bf16x2(v.z); d[4] = t.x; d[5] = t.y;
+        t = unpack_bf16x2(v.w); d[6] = t.x; d[7] = t.y;
 #pragma unroll
-    for (int a = 0; a < H; ++a) { abw[a] = 0.f; abl[a] = 0.f; }
+        for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) d[i] = 0.f;
+    };
 
     for (int rowi = blockIdx.x * 8 + warp; rowi < rows_total; rowi += gridDim.x * 8) {
         const int b = rowi / Nq, q = rowi % Nq;
         const float* Sb = S + ((long long)b * H * Nq + q) * ldS;
         const uint16_t* dAb = dA + ((long long)b * H * Nq + q) * ldA;
         uint16_t* dSb = dS + ((long long)b * H * Nq + q) * ldA;
-        float m[H], iz[H], rho[H];
-        talking_stats<H>(Sb, hS, Nk, &w, lane, m, iz);
-        // ---- sweep B: rho[g] = sum_j P[g] dP[g];  dWw += dA (x) P;  dbw += dA
+        float m2, iz;
+        talking_stats2<H>(Sb, hS, Nk, ldS, fWl, bl2, q4, r4, m2, iz);
+        const float c2 = m2 - log2f(iz);
+        // ---- sweep B: rho = sum_j P dP;  dWw += dA (x) P;  dbw += dA
+        float rho = 0.f;
+        SRaw nxt = load_sraw<H>(Sb, hS, 0, ldS, q4, r4);
+        uint4 dnxt = load_dA_raw(dAb, 0);
+        for (int base = 0; base < Nk; base += 32) {
+            const SRaw cur = nxt;
+            const uint4 dcur = dnxt;
+            if (base + 32 < Nk) { nxt = load_sraw<H>(Sb, hS, base + 32, ldS, q4, r4); dnxt = load_dA_raw(dAb, base + 32); }
+            float L2[8], d[8], dP[8], p[8];
+            uint32_t shi[4];
+            step_logits<H>(cur, base, Nk, fWl, bl2, q4, r4, L2, shi);
+            unpack_dA(dcur, base, d);
+            uint32_t dpk[4], ppk[4];
 #pragma unroll
-        for (int g = 0; g < H; ++g) rho[g] = 0.f;
-        const int Nk64 = (Nk + 63) & ~63;
-        for (int j = 2 * lane; j < Nk64; j += 64) {
-            const bool one = j < Nk, two = j + 1 < Nk;
-            float s[H][2], d[H][2], a[H][2], x[H][2];
-            if (one) {
-                load_s2<H>(Sb, hS, j, two, 0.f, s);
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + h * hA + j));
-                    d[h][0] = u.x; d[h][1] = two ? u.y : 0.f;
-                    abw[h] += d[h][0] + d[h][1];
-                }
-                mix2<H>(w.Wl, w.bl, s, a);
-                mix2<H>(w.WwT, nullptr, d, x);                          // dP = Ww^T dA
-#pragma unroll
-                for (int g = 0; g < H; ++g) {
-                    const float p0 = __expf(a[g][0] - m[g]) * iz[g], p1 = two ? __expf(a[g][1] - m[g]) * iz[g] : 0.f;
-                    rho[g] += p0 * x[g][0] + p1 * x[g][1];
-                    *reinterpret_cast<uint32_t*>(X + g * TP + 2 * lane) = pack_bf16x2(d[g][0], d[g][1]);
-                    *reinterpret_cast<uint32_t*>(Y + g * TP + 2 * lane) = pack_bf16x2(p0, p1);
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < H; ++g) { *reinterpret_cast<uint32_t*>(X + g * TP + 2 * lane) = 0u; *reinterpret_cast<uint32_t*>(Y + g * TP + 2 * lane) = 0u; }
+            for (int t = 0; t < 4; ++t) {
+                p[t] = exp2f(L2[t] - c2); p[4 + t] = exp2f(L2[4 + t] - c2);
+                dpk[t] = pack_bf16x2(d[t], d[4 + t]);
+                ppk[t] = pack_bf16x2(p[t], p[4 + t]);
+                mix_tile(fWwT, movm_trans(dpk[t]), 0u, 0.f, dP[t], dP[4 + t]);
             }
-            __syncwarp();
-            outer_acc_64(X, Y, Z, H, lane, accWw);
-            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { rho += p[i] * dP[i]; abw += d[i]; }
+            // outer products over this step's 32 keys: rows = dA heads, cols = P heads (the key order inside the k dimension
+            // is the same arbitrary permutation for both operands)
+            mma16816(accWw, dpk[0], 0u, dpk[1], 0u, ppk[0], ppk[1]);
+            mma16816(accWw, dpk[2], 0u, dpk[3], 0u, ppk[2], ppk[3]);
         }
-#pragma unroll
-        for (int g = 0; g < H; ++g) rho[g] = warp_sum(rho[g]);
+        rho += __shfl_xor_sync(0xffffffffu, rho, 1);
+        rho += __shfl_xor_sync(0xffffffffu, rho, 2);
         // ---- sweep C: dL = P (dP - rho);  dS = Wl^T dL;  dWl += dL (x) S;  dbl += dL
-        const int Nc = ((int)ldA + 63) & ~63;
-        for (int j = 2 * lane; j < Nc; j += 64) {
-            const bool one = j < Nk, two = j + 1 < Nk;
-            if (one) {
-                float s[H][2], d[H][2], a[H][2], x[H][2], l[H][2];
-                load_s2<H>(Sb, hS, j, two, 0.f, s);
+        nxt = load_sraw<H>(Sb, hS, 0, ldS, q4, r4);
+        dnxt = load_dA_raw(dAb, 0);
+        for (int base = 0; base < ldA; base += 32) {
+            const SRaw cur = nxt;
+            const uint4 dcur = dnxt;
+            // (in-place dS: the prefetched dA of the next step is read before this step's store; different keys anyway)
+            if (base + 32 < ldA) { nxt = load_sraw<H>(Sb, hS, base + 32, ldS, q4, r4); dnxt = load_dA_raw(dAb, base + 32); }
+            float L2[8], d[8], dP[8], l[8], o[8];
+            uint32_t shi[4];
+            step_logits<H>(cur, base, Nk, fWl, bl2, q4, r4, L2, shi);
+            unpack_dA(dcur, base, d);
+            uint32_t lpk[4], spk[4];
 #pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dAb + h * hA + j));
-                    d[h][0] = u.x; d[h][1] = two ? u.y : 0.f;
-                }
-                mix2<H>(w.Wl, w.bl, s, a);
-                mix2<H>(w.WwT, nullptr, d, x);
+            for (int t = 0; t < 4; ++t) mix_tile(fWwT, movm_trans(pack_bf16x2(d[t], d[4 + t])), 0u, 0.f, dP[t], dP[4 + t]);
 #pragma unroll
-                for (int g = 0; g < H; ++g) {
-                    const float p0 = __expf(a[g][0] - m[g]) * iz[g], p1 = two ? __expf(a[g][1] - m[g]) * iz[g] : 0.f;
-                    l[g][0] = p0 * (x[g][0] - rho[g]); l[g][1] = p1 * (x[g][1] - rho[g]);
-                    abl[g] += l[g][0] + l[g][1];
-                    *reinterpret_cast<uint32_t*>(X + g * TP + 2 * lane) = pack_bf16x2(l[g][0], l[g][1]);
-                    *reinterpret_cast<uint32_t*>(Y + g * TP + 2 * lane) = pack_bf16x2(s[g][0], s[g][1]);
-                }
-                mix2<H>(w.WlT, nullptr, l, x);                          // dS = Wl^T dL
-                // all dA reads of this (row, j) happened above -> safe to overwrite in place when dS aliases dA
+            for (int i = 0; i < 8; ++i) { l[i] = exp2f(L2[i] - c2) * (dP[i] - rho); abl += l[i]; }
 #pragma unroll
-                for (int h = 0; h < H; ++h) *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = pack_bf16x2(x[h][0], two ? x[h][1] : 0.f);
-            } else {
-#pragma unroll
-                for (int g = 0; g < H; ++g) { *reinterpret_cast<uint32_t*>(X + g * TP + 2 * lane) = 0u; *reinterpret_cast<uint32_t*>(Y + g * TP + 2 * lane) = 0u; }
-                if (j < ldA) {
-#pragma unroll
-                    for (int h = 0; h < H; ++h) *reinterpret_cast<uint32_t*>(dSb + h * hA + j) = 0u;     // padding columns stay zero
-                }
+            for (int t = 0; t < 4; ++t) {
+                lpk[t] = pack_bf16x2(l[t], l[4 + t]);
+                spk[t] = movm_trans(shi[t]);                               // S (hi part) back in the accumulator layout: head q4
+                mix_tile(fWlT, movm_trans(lpk[t]), 0u, 0.f, o[t], o[4 + t]);
             }
-            __syncwarp();
-            if (j - 2 * lane < Nk64) outer_acc_64(X, Y, Z, H, lane, accWl);
-            __syncwarp();
+            mma16816(accWl, lpk[0], 0u, lpk[1], 0u, spk[0], spk[1]);
+            mma16816(accWl, lpk[2], 0u, lpk[3], 0u, spk[2], spk[3]);
+            const int c8 = base + 8 * r4;
+            if (q4 < H && c8 + 8 <= ldA) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) o[i] = 0.f;
+                // all dA reads of this (row, keys) happened above (same lanes) -> in-place overwrite is safe when dS aliases dA
+                *reinterpret_cast<uint4*>(dSb + q4 * hA + c8) =
+                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            }
         }
     }
     // CTA reduction of the partials -> part[blockIdx.x][...]: layout dWl[H*H], dbl[H], dWw[H*H], dbw[H]
     for (int i = lane; i < NP; i += 32) redbuf[warp][i] = 0.f;
     __syncwarp();
-    {
-        const int row = lane >> 2, col = (lane & 3) * 2;
-        if (row < H) {
-            if (col < H) { redbuf[warp][row * H + col] = accWl[0]; redbuf[warp][H * H + H + row * H + col] = accWw[0]; }
-            if (col + 1 < H) { redbuf[warp][row * H + col + 1] = accWl[1]; redbuf[warp][H * H + H + row * H + col + 1] = accWw[1]; }
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < H; ++a) {
-        const float v3 = warp_sum(abl[a]), v4 = warp_sum(abw[a]);
-        if (lane == 0) { redbuf[warp][H * H + a] = v3; redbuf[warp][2 * H * H + H + a] = v4; }
+    abw += __shfl_xor_sync(0xffffffffu, abw, 1); abw += __shfl_xor_sync(0xffffffffu, abw, 2);
+    abl += __shfl_xor_sync(0xffffffffu, abl, 1); abl += __shfl_xor_sync(0xffffffffu, abl, 2);
+    if (q4 < H) {
+        const int col = 2 * r4;
+        if (col < H) { redbuf[warp][q4 * H + col] = accWl[0]; redbuf[warp][H * H + H + q4 * H + col] = accWw[0]; }
+        if (col + 1 < H) { redbuf[warp][q4 * H + col + 1] = accWl[1]; redbuf[warp][H * H + H + q4 * H + col + 1] = accWw[1]; }
+        if (r4 == 0) { redbuf[warp][H * H + q4] = abl; redbuf[warp][2 * H * H + H + q4] = abw; }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NP; i += 256) {
@@ -502,8 +532,11 @@ __global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float* __rest
     }
 }
 
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const uint16_t* __restrict__ x, long long rows, int N, long long ld, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const uint16_t* __restrict__ x, long long rows, int N, long long ld, float* __restrict__ out,
+                                                          long long x_bstride, long long out_bstride) {
     __shared__ float2 red[8][32];
+    x += (long long)blockIdx.z * x_bstride;
+    out += (long long)blockIdx.z * out_bstride;
     const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
     float2 acc = make_float2(0.f, 0.f);
     if (c + 1 < N) {
@@ -754,7 +787,7 @@ template <int H>
 static int talking_fwd_launch(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, int B, int Nq, int Nk,
                               int64_t ldS, int64_t ldA, cudaStream_t st) {
     SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 6.0, st);   // algorithmic bytes: S f32 read + A bf16 write
-    talking_fwd_kernel<H><<<talking_grid(B, Nq, 2), 256, 0, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, B * Nq, Nq, Nk, ldS, ldA);
+    talking_fwd_kernel<H><<<talking_grid(B, Nq, 4), 256, 0, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, B * Nq, Nq, Nk, ldS, ldA);
     SPE_LAUNCHED();
     return 0;
 }
@@ -762,7 +795,7 @@ static int talking_fwd_launch(const float* S, void* A, const float* Wl, const fl
 extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, int B, int H,
                                        int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream) {
     SPE_CHECK(S && A && Wl && bl && Ww && bw && B > 0 && Nq > 0 && Nk > 0, "spe_talking_softmax_fwd: bad argument");
-    SPE_CHECK(ldS % 4 == 0 && ldA % 4 == 0 && ldS >= ((Nk + 3) & ~3) && ldA >= ((Nk + 3) & ~3), "spe_talking_softmax_fwd: leading dims must be multiples of 4 and >= Nk rounded up to 4");
+    SPE_CHECK(ldS % 8 == 0 && ldA % 8 == 0 && ldS >= Nk && ldA >= Nk, "spe_talking_softmax_fwd: leading dims must be multiples of 8 and >= Nk");
     switch (H) {
         case 2: return talking_fwd_launch<2>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
         case 4: return talking_fwd_launch<4>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
@@ -771,7 +804,7 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(co
     }
 }
 
-static int talking_bwd_grid(int B, int Nq) { return talking_grid(B, Nq, 2); }
+static int talking_bwd_grid(int B, int Nq) { return talking_grid(B, Nq, 4); }
 
 extern "C" __attribute__((visibility("default"))) int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk) {
     (void)Nk;
@@ -799,7 +832,7 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd(co
                                        float* workspace, int64_t workspace_floats, void* stream) {
     (void)bw;
     SPE_CHECK(S && dA && dS && Wl && bl && Ww && dWl && dbl && dWw && dbw && workspace, "spe_talking_softmax_bwd: null argument");
-    SPE_CHECK(ldS % 4 == 0 && ldA % 4 == 0 && ldS >= ((Nk + 3) & ~3) && ldA >= ((Nk + 3) & ~3), "spe_talking_softmax_bwd: leading dims must be multiples of 4 and >= Nk rounded up to 4");
+    SPE_CHECK(ldS % 8 == 0 && ldA % 8 == 0 && ldS >= Nk && ldA >= Nk, "spe_talking_softmax_bwd: leading dims must be multiples of 8 and >= Nk");
     SPE_CHECK(workspace_floats >= spe_talking_softmax_bwd_workspace(B, H, Nq, Nk), "spe_talking_softmax_bwd: workspace too small");
     switch (H) {
         case 2: return talking_bwd_launch<2>(S, dA, dS, Wl, bl, Ww, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
@@ -828,7 +861,19 @@ extern "C" __attribute__((visibility("default"))) int spe_colsum_bf16(const void
     long long gy = (rows + 7) / 8;
     const long long cap = ((long long)spe_num_sms() * 4 + gx - 1) / gx;
     if (gy > cap) gy = cap;
-    colsum_bf16_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(x), rows, N, ld, out);
+    colsum_bf16_kernel<<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(x), rows, N, ld, out, 0, 0);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_colsum_bf16_batched(const void* x, int batch, int64_t rows, int N, int64_t ld, int64_t batch_stride,
+                                                                             float* out, void* stream) {
+    SPE_CHECK(x && out && batch > 0 && rows > 0 && N > 0 && ld % 2 == 0 && batch_stride % 2 == 0, "spe_colsum_bf16_batched: bad argument");
+    const int gx = (N + 63) / 64;
+    long long gy = (rows + 7) / 8;
+    const long long cap = ((long long)spe_num_sms() * 4 + (long long)gx * batch - 1) / ((long long)gx * batch);
+    if (gy > cap) gy = cap < 1 ? 1 : cap;
+    colsum_bf16_kernel<<<dim3(gx, (unsigned)gy, batch), dim3(32, 8), 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(x), rows, N, ld, out, batch_stride, N);
     SPE_LAUNCHED();
     return 0;
 }

@@ -528,6 +528,13 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         check(lib().spe_talking_softmax_bwd(ptr(S), ptr(dA), ptr(dA), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), B, H, N, N, ld, ld, ptr(dWl), ptr(dbl),
                                             ptr(dWw), ptr(dbw), ptr(ws), nws, stream()))
         _dq_dk(dA, q, k, H, scale, N, N, ld, dq_out=dqkv[:, :, :D], dk_out=dqkv[:, :, D:2 * D])
+        # exact bias gradients (the kernel's own sums of bf16 dA over B*N*N keys cancel catastrophically):
+        #   dbw[o] = sum_{b,i,j} dA[b,o,i,j] = sum_b colsum_i(dO[b,:,o]) . colsum_j(V[b,:,o]);   dbl = 0 (softmax is shift invariant)
+        cs = torch.zeros((2, B, D), dtype=torch.float32, device=qkv.device)
+        check(lib().spe_colsum_bf16_batched(ptr(dO), B, N, D, dO.stride(1), dO.stride(0), ptr(cs[0]), stream()))
+        check(lib().spe_colsum_bf16_batched(ptr(v), B, N, D, v.stride(1), v.stride(0), ptr(cs[1]), stream()))
+        dbw = (cs[0] * cs[1]).view(B, H, dh).sum((0, 2))
+        dbl = torch.zeros_like(bl)
         return dqkv, dWl, dbl, dWw, dbw, None
 
 
