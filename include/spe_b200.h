@@ -84,11 +84,12 @@ int spe_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dre
 /* Talking-heads mix + softmax + mix (cait.py:381-386):
  *   L[g] = sum_h Wl[g,h] S[h] + bl[g];  P = softmax_j(L);  A[g] = sum_h Ww[g,h] P[h] + bw[g]
  * S f32 [B,H,Nq,ldS] (Nk valid columns) -> A bf16 same layout (ldA).  */
+/* stats (may be NULL): f32 [B*Nq, H] receives log2-domain softmax normalisers (row max + log2 sum) for the backward */
 int spe_talking_softmax_fwd(const float* S, void* A, const float* Wl, const float* bl, const float* Ww,
-                            const float* bw, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream);
+                            const float* bw, float* stats, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream);
 /* backward: dA bf16 -> dS bf16 (may alias dA); parameter grads accumulated (+=) */
 int spe_talking_softmax_bwd(const float* S, const void* dA, void* dS, const float* Wl, const float* bl,
-                            const float* Ww, const float* bw, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA,
+                            const float* Ww, const float* bw, const float* stats, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA,
                             float* dWl, float* dbl, float* dWw, float* dbw, float* workspace, int64_t workspace_floats,
                             void* stream);
 int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk);

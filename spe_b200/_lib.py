@@ -39,8 +39,8 @@ _SIGS = {
     "spe_gemm": (c_i, [C.POINTER(GemmArgs), c_p]),
     "spe_layernorm_fwd": (c_i, [c_p, c_p, c_p, c_f, c_l, c_i, c_p, c_p, c_p, c_p, c_p]),
     "spe_layernorm_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
-    "spe_talking_softmax_fwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p]),
-    "spe_talking_softmax_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p, c_p, c_p,
+    "spe_talking_softmax_fwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p]),
+    "spe_talking_softmax_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p, c_p, c_p,
                                       c_p, c_l, c_p]),
     "spe_talking_softmax_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i]),
     "spe_softmax_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p]),

@@ -30,7 +30,7 @@ constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr uint32_t CHUNK_BYTES = 64 * BK * 2;   // one 64(mn) x 64(k) MN-major TMA box
 constexpr uint32_t SLAB = 4096;                 // 32 rows x 128 B
-constexpr int EPI_SLABS = 4;                   // per epilogue warp: two sets of {RC0, RC1|X} so TMA stores of tile i overlap tile i+1
+constexpr int EPI_SLABS = 3;                   // per epilogue warp: {RC0, RC1, X}
 constexpr uint32_t EPI_SMEM = NUM_EPI_WARPS * EPI_SLABS * SLAB;
 
 struct EpiParams {
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         //   footprint <= 2 slabs -> two alternating sets {0,1} / {2,3}: the bulk stores of one super-chunk drain while the next is
         //   produced (wait_group.read 1);  footprint 3 -> slabs {0,1} + {2}, single-buffered (wait_group.read 0).
         const bool wide = ep.c_dtype == SPE_DT_F32 || ep.residual != nullptr;
-        const bool alternate = !(wide && (ep.aux_in != nullptr || ep.aux_out != nullptr));
+        const bool alternate = false;   // (two alternating slab sets were measured: no gain -- the GEMMs are SM<->L2 fabric bound)
         uint32_t set = 0;
         const uint32_t ebar = ebar0 + 8 * e;
         const bool has_r = ep.residual != nullptr, has_xi = ep.aux_in != nullptr, has_xo = ep.aux_out != nullptr;
@@ -656,5 +656,5 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     if (g_spe_prof_on) snprintf(tag, sizeof(tag), "M%d N%d K%d b%d a%d b%d c%d", a->M, a->N, a->K, batch, a->a_major, a->b_major, a->c_dtype);
     SpeProfScope prof(SPE_FAM_GEMM, 2.0 * a->M * a->N * (double)a->K * batch, st, tag);     // algorithmic flops
     if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);
-    return dispatch_major<128, 3>(a->a_major, a->b_major, tA, tB, io, ep, st);
+    return dispatch_major<128, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);
 }

@@ -250,6 +250,11 @@ __device__ __forceinline__ void mix_tile(const MixFrag& W, uint32_t bhi, uint32_
 }
 
 constexpr float LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float fast_ex2(float x) {           // single MUFU.EX2 (flushes denormals; 2^-inf = 0)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // raw S of one 32-key step in the B-operand layout: 4 keys [base + 4 q4, +4) of heads 2 r4 and 2 r4 + 1
 struct SRaw { float4 s0, s1; };
@@ -259,8 +264,8 @@ __device__ __forceinline__ SRaw load_sraw(const float* __restrict__ Sb, long lon
     r.s0 = make_float4(0.f, 0.f, 0.f, 0.f); r.s1 = r.s0;
     const int cb = base + 4 * q4;
     if (cb + 4 <= ldS) {
-        if (2 * r4 < H) r.s0 = __ldg(reinterpret_cast<const float4*>(Sb + (2 * r4) * hS + cb));
-        if (2 * r4 + 1 < H) r.s1 = __ldg(reinterpret_cast<const float4*>(Sb + (2 * r4 + 1) * hS + cb));
+        if (2 * r4 < H) r.s0 = *reinterpret_cast<const float4*>(Sb + (2 * r4) * hS + cb);
+        if (2 * r4 + 1 < H) r.s1 = *reinterpret_cast<const float4*>(Sb + (2 * r4 + 1) * hS + cb);
     }
     return r;
 }
@@ -271,16 +276,19 @@ __device__ __forceinline__ void step_logits(const SRaw& raw, int base, int Nk, c
                                             uint32_t (&shi)[4]) {
     const int cb = base + 4 * q4;
     const float a0[4] = {raw.s0.x, raw.s0.y, raw.s0.z, raw.s0.w}, a1[4] = {raw.s1.x, raw.s1.y, raw.s1.z, raw.s1.w};
+    const bool tail = base + 32 > Nk;               // warp-uniform: only the last step of a row has invalid keys
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-        const bool ok = cb + t < Nk;                // padding columns of S are never written: sanitise
+        const bool ok = !tail || cb + t < Nk;       // padding columns of S are never written: sanitise
         uint32_t lo;
         split2(ok ? a0[t] : 0.f, ok ? a1[t] : 0.f, shi[t], lo);
         mix_tile(Wl, shi[t], lo, bl2, L2[t], L2[4 + t]);
     }
-    const int c8 = base + 8 * r4;
+    if (tail) {
+        const int c8 = base + 8 * r4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) L2[i] = -INFINITY;
+        for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) L2[i] = -INFINITY;
+    }
 }
 
 // sweep A: m2[q4] = max_j L2, iz = 1 / sum_j 2^(L2 - m2)     (values for the lane's head q4, identical in its 4 lanes)
@@ -319,7 +327,7 @@ __device__ __forceinline__ void talking_stats2(const float* __restrict__ Sb, lon
 template <int H>
 __global__ void __launch_bounds__(256, 3) talking_fwd_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
                                                              const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
-                                                             int rows_total, int Nq, int Nk, long long ldS, long long ldA) {
+                                                             float* __restrict__ stats, int rows_total, int Nq, int Nk, long long ldS, long long ldA) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q4 = lane >> 2, r4 = lane & 3;
     const MixFrag fWl = load_mix_frag<H>(Wl, false, LOG2E, q4, r4), fWw = load_mix_frag<H>(Ww, false, 1.f, q4, r4);
     const float bl2 = q4 < H ? bl[q4] * LOG2E : 0.f, bwv = q4 < H ? bw[q4] : 0.f;
@@ -331,6 +339,7 @@ __global__ void __launch_bounds__(256, 3) talking_fwd_kernel(const float* __rest
         float m2, iz;
         talking_stats2<H>(Sb, hS, Nk, ldS, fWl, bl2, q4, r4, m2, iz);
         const float c2 = m2 - log2f(iz);            // p = 2^(L2 - m2) * iz = 2^(L2 - c2)
+        if (stats && r4 == 0 && q4 < H) stats[(long long)rowi * H + q4] = c2;
         SRaw nxt = load_sraw<H>(Sb, hS, 0, ldS, q4, r4);
         for (int base = 0; base < ldA; base += 32) {
             const SRaw cur = nxt;
@@ -475,6 +484,272 @@ __global__ void __launch_bounds__(256, 2) talking_bwd_kernel(const float* __rest
         if (col < H) { redbuf[warp][q4 * H + col] = accWl[0]; redbuf[warp][H * H + H + q4 * H + col] = accWw[0]; }
         if (col + 1 < H) { redbuf[warp][q4 * H + col + 1] = accWl[1]; redbuf[warp][H * H + H + q4 * H + col + 1] = accWw[1]; }
         if (r4 == 0) { redbuf[warp][H * H + q4] = abl; redbuf[warp][2 * H * H + H + q4] = abw; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NP; i += 256) {
+        float sum = 0.f;
+        for (int w2 = 0; w2 < 8; ++w2) sum += redbuf[w2][i];
+        part[(long long)blockIdx.x * NP + i] = sum;
+    }
+}
+
+// =================================================================================================
+// Row-staged variants (the default): ONE persistent CTA per SM slot, 8 warps share one (b, q) row.  The row's operands
+// (S: H x ld fp32, and dA: H x ld bf16 in the backward) are brought into shared memory ONCE by bulk async copies
+// (cp.async.bulk + mbarrier), double buffered so row r+1 streams in while row r is processed; the 2-3 sweeps then read
+// shared memory only.  SM<->L2 traffic per row drops from 3 x (S + dA) to 1 x, which is what bounds these kernels.
+// The keys of a row are split into 8 contiguous segments (one per warp); softmax statistics / rho are combined through
+// shared memory.  The forward also saves the statistics so the backward needs no statistics sweep.
+// =================================================================================================
+__device__ __forceinline__ uint32_t rw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rw_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void rw_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rw_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void rw_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int H>
+__global__ void __launch_bounds__(256, 2) talking_fwd_rows_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
+                                                                  const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
+                                                                  float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
+    extern __shared__ __align__(128) uint8_t rsm[];
+    float* Sbuf = reinterpret_cast<float*>(rsm);                       // [2][H][ldS]
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ float red[8][8][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q4 = lane >> 2, r4 = lane & 3;
+    const MixFrag fWl = load_mix_frag<H>(Wl, false, LOG2E, q4, r4), fWw = load_mix_frag<H>(Ww, false, 1.f, q4, r4);
+    const float bl2 = q4 < H ? bl[q4] * LOG2E : 0.f, bwv = q4 < H ? bw[q4] : 0.f;
+    const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
+    const uint32_t bar0 = rw_smem_u32(bars);
+    if (tid == 0) {
+        rw_mbar_init(bar0, 1); rw_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int row, int buf) {                                 // thread 0 only
+        const int b = row / Nq, q = row % Nq;
+        const uint32_t bar = bar0 + 8 * buf;
+        rw_mbar_expect_tx(bar, (uint32_t)(H * ldS * 4));
+        for (int h = 0; h < H; ++h)
+            rw_bulk_g2s(rw_smem_u32(Sbuf + ((size_t)buf * H + h) * ldS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar);
+    };
+    const int nsteps = (Nk + 31) / 32, nsteps_o = (ldA + 31) / 32;
+    const int spw = (nsteps + 7) / 8, spwo = (nsteps_o + 7) / 8;
+    const int s0 = min(warp * spw, nsteps), s1 = min(s0 + spw, nsteps);
+    const int o0 = min(warp * spwo, nsteps_o), o1 = min(o0 + spwo, nsteps_o);
+    if (tid == 0 && blockIdx.x < rows_total) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x, buf ^ 1);
+        rw_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        const float* Sb = Sbuf + (size_t)buf * H * ldS;
+        const int b = row / Nq, q = row % Nq;
+        uint16_t* Ab = A + ((long long)b * H * Nq + q) * ldA;
+        // ---- sweep A (this warp's key segment): online (max, sum) of the mixed logits
+        float m = -INFINITY, z = 0.f;
+        for (int st = s0; st < s1; ++st) {
+            const int base = st * 32;
+            float L2[8];
+            uint32_t shi[4];
+            step_logits<H>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+            float mx = L2[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) mx = fmaxf(mx, L2[i]);
+            const float mn = fmaxf(m, mx);
+            if (mn > -INFINITY) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc += fast_ex2(L2[i] - mn);
+                z = z * fast_ex2(m - mn) + acc;
+                m = mn;
+            }
+        }
+        {
+            float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 2));
+            float zz = (m == -INFINITY) ? 0.f : z * fast_ex2(m - M);
+            zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+            zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+            if (r4 == 0) { red[warp][q4][0] = M; red[warp][q4][1] = zz; }
+        }
+        __syncthreads();
+        float m2 = -INFINITY, zt = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) m2 = fmaxf(m2, red[w2][q4][0]);
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) { const float mw = red[w2][q4][0]; zt += (mw == -INFINITY) ? 0.f : red[w2][q4][1] * fast_ex2(mw - m2); }
+        const float c2 = m2 + log2f(zt);                                // p = 2^(L2 - m2) / zt = 2^(L2 - c2)
+        if (stats && warp == 0 && r4 == 0 && q4 < H) stats[(long long)row * H + q4] = c2;
+        // ---- sweep B: P -> second mix -> bf16
+        for (int st = o0; st < o1; ++st) {
+            const int base = st * 32;
+            float L2[8], out[8], p[8];
+            uint32_t shi[4];
+            step_logits<H>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p[i] = fast_ex2(L2[i] - c2);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint32_t hi, lo;
+                split2(p[t], p[4 + t], hi, lo);
+                mix_tile(fWw, movm_trans(hi), movm_trans(lo), bwv, out[t], out[4 + t]);
+            }
+            const int c8 = base + 8 * r4;
+            if (q4 < H && c8 + 8 <= ldA) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) out[i] = 0.f;
+                *reinterpret_cast<uint4*>(Ab + q4 * hA + c8) =
+                    make_uint4(pack_bf16x2(out[0], out[1]), pack_bf16x2(out[2], out[3]), pack_bf16x2(out[4], out[5]), pack_bf16x2(out[6], out[7]));
+            }
+        }
+        __syncthreads();                                               // row buffer and `red` are free again
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(256, 2) talking_bwd_rows_kernel(const float* __restrict__ S, const uint16_t* dA, uint16_t* dS, const float* __restrict__ Wl,
+                                                                  const float* __restrict__ bl, const float* __restrict__ Ww,
+                                                                  const float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA,
+                                                                  float* __restrict__ part) {
+    extern __shared__ __align__(128) uint8_t rsm[];
+    // single row buffer per CTA; TWO CTAs share an SM, so one CTA's row load overlaps the other's math (16 warps / SM)
+    float* Sbuf = reinterpret_cast<float*>(rsm);                                            // [H][ldS]
+    uint16_t* Dbuf = reinterpret_cast<uint16_t*>(rsm + (size_t)H * ldS * 4);                // [H][ldA]
+    constexpr int NP = 2 * H * H + 2 * H;
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ float red[8][8];
+    __shared__ float redbuf[8][NP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q4 = lane >> 2, r4 = lane & 3;
+    const MixFrag fWl = load_mix_frag<H>(Wl, false, LOG2E, q4, r4);
+    const MixFrag fWwT = load_mix_frag<H>(Ww, true, 1.f, q4, r4);
+    const MixFrag fWlT = load_mix_frag<H>(Wl, true, 1.f, q4, r4);
+    const float bl2 = q4 < H ? bl[q4] * LOG2E : 0.f;
+    const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
+    const uint32_t bar0 = rw_smem_u32(bars);
+    if (tid == 0) {
+        rw_mbar_init(bar0, 1); rw_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int row) {
+        const int b = row / Nq, q = row % Nq;
+        rw_mbar_expect_tx(bar0, (uint32_t)(H * ldS * 4 + H * ldA * 2));
+        for (int h = 0; h < H; ++h) {
+            rw_bulk_g2s(rw_smem_u32(Sbuf + (size_t)h * ldS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar0);
+            rw_bulk_g2s(rw_smem_u32(Dbuf + (size_t)h * ldA), dA + ((long long)b * H * Nq + q) * ldA + h * hA, (uint32_t)(ldA * 2), bar0);
+        }
+    };
+    const int nsteps = (Nk + 31) / 32, nsteps_o = (ldA + 31) / 32;
+    const int spw = (nsteps + 7) / 8, spwo = (nsteps_o + 7) / 8;
+    const int s0 = min(warp * spw, nsteps), s1 = min(s0 + spw, nsteps);
+    const int o0 = min(warp * spwo, nsteps_o), o1 = min(o0 + spwo, nsteps_o);
+
+    float accWw[4] = {0.f, 0.f, 0.f, 0.f}, accWl[4] = {0.f, 0.f, 0.f, 0.f};
+    float abl = 0.f;
+    auto get_dA = [&](const uint16_t* Db, int base, float (&d)[8]) {
+        const int c8 = base + 8 * r4;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (q4 < H && c8 + 8 <= ldA) v = *reinterpret_cast<const uint4*>(Db + q4 * ldA + c8);
+        float2 t;
+        t = unpack_bf16x2(v.x); d[0] = t.x; d[1] = t.y;
+        t = unpack_bf16x2(v.y); d[2] = t.x; d[3] = t.y;
+        t = unpack_bf16x2(v.z); d[4] = t.x; d[5] = t.y;
+        t = unpack_bf16x2(v.w); d[6] = t.x; d[7] = t.y;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) d[i] = 0.f;
+    };
+
+    if (tid == 0 && blockIdx.x < rows_total) issue(blockIdx.x);
+    int it = 0;
+    for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
+        const float c2 = q4 < H ? stats[(long long)row * H + q4] : 0.f;
+        rw_mbar_wait(bar0, (uint32_t)it & 1u);
+        const float* Sb = Sbuf;
+        const uint16_t* Db = Dbuf;
+        const int b = row / Nq, q = row % Nq;
+        uint16_t* dSb = dS + ((long long)b * H * Nq + q) * ldA;
+        // ---- sweep B: rho = sum_j P dP;  dWw += dA (x) P
+        float rho = 0.f;
+        for (int st = s0; st < s1; ++st) {
+            const int base = st * 32;
+            float L2[8], d[8], dP[8], p[8];
+            uint32_t shi[4], dpk[4], ppk[4];
+            step_logits<H>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+            get_dA(Db, base, d);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                p[t] = fast_ex2(L2[t] - c2); p[4 + t] = fast_ex2(L2[4 + t] - c2);
+                dpk[t] = pack_bf16x2(d[t], d[4 + t]);
+                ppk[t] = pack_bf16x2(p[t], p[4 + t]);
+                mix_tile(fWwT, movm_trans(dpk[t]), 0u, 0.f, dP[t], dP[4 + t]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rho += p[i] * dP[i];
+            mma16816(accWw, dpk[0], 0u, dpk[1], 0u, ppk[0], ppk[1]);
+            mma16816(accWw, dpk[2], 0u, dpk[3], 0u, ppk[2], ppk[3]);
+        }
+        rho += __shfl_xor_sync(0xffffffffu, rho, 1);
+        rho += __shfl_xor_sync(0xffffffffu, rho, 2);
+        if (r4 == 0) red[warp][q4] = rho;
+        __syncthreads();
+        rho = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) rho += red[w2][q4];
+        // ---- sweep C: dL = P (dP - rho);  dS = Wl^T dL;  dWl += dL (x) S;  dbl += dL
+        for (int st = o0; st < o1; ++st) {
+            const int base = st * 32;
+            float L2[8], d[8], dP[8], l[8], o[8];
+            uint32_t shi[4], lpk[4], spk[4];
+            step_logits<H>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+            get_dA(Db, base, d);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) mix_tile(fWwT, movm_trans(pack_bf16x2(d[t], d[4 + t])), 0u, 0.f, dP[t], dP[4 + t]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { l[i] = fast_ex2(L2[i] - c2) * (dP[i] - rho); abl += l[i]; }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                lpk[t] = pack_bf16x2(l[t], l[4 + t]);
+                spk[t] = movm_trans(shi[t]);
+                mix_tile(fWlT, movm_trans(lpk[t]), 0u, 0.f, o[t], o[4 + t]);
+            }
+            if (base < Nk) {
+                mma16816(accWl, lpk[0], 0u, lpk[1], 0u, spk[0], spk[1]);
+                mma16816(accWl, lpk[2], 0u, lpk[3], 0u, spk[2], spk[3]);
+            }
+            const int c8 = base + 8 * r4;
+            if (q4 < H && c8 + 8 <= ldA) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) o[i] = 0.f;
+                *reinterpret_cast<uint4*>(dSb + q4 * hA + c8) =
+                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            }
+        }
+        __syncthreads();                                               // every warp is done with the row buffer
+        if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x);
+    }
+    // CTA reduction of the partials -> part[blockIdx.x][...]: layout dWl[H*H], dbl[H], dWw[H*H], dbw[H] (dbw: see ops.py, exact formula)
+    for (int i = lane; i < NP; i += 32) redbuf[warp][i] = 0.f;
+    __syncwarp();
+    abl += __shfl_xor_sync(0xffffffffu, abl, 1); abl += __shfl_xor_sync(0xffffffffu, abl, 2);
+    if (q4 < H) {
+        const int col = 2 * r4;
+        if (col < H) { redbuf[warp][q4 * H + col] = accWl[0]; redbuf[warp][H * H + H + q4 * H + col] = accWw[0]; }
+        if (col + 1 < H) { redbuf[warp][q4 * H + col + 1] = accWl[1]; redbuf[warp][H * H + H + q4 * H + col + 1] = accWw[1]; }
+        if (r4 == 0) redbuf[warp][H * H + q4] = abl;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NP; i += 256) {
@@ -784,41 +1059,66 @@ static int talking_grid(int B, int Nq, int per_sm) {
 }
 
 template <int H>
-static int talking_fwd_launch(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, int B, int Nq, int Nk,
-                              int64_t ldS, int64_t ldA, cudaStream_t st) {
+static int talking_fwd_launch(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats, int B, int Nq,
+                              int Nk, int64_t ldS, int64_t ldA, cudaStream_t st) {
     SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 6.0, st);   // algorithmic bytes: S f32 read + A bf16 write
-    talking_fwd_kernel<H><<<talking_grid(B, Nq, 4), 256, 0, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, B * Nq, Nq, Nk, ldS, ldA);
+    const size_t smem = (size_t)2 * H * ldS * 4;
+    if (stats && smem <= 100 * 1024 + 4096 && getenv("SPE_TALKING_WARP_ROWS") == nullptr) {
+        static bool done = false;
+        if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); done = true; }
+        const long long rows = (long long)B * Nq;
+        const int grid = (int)(rows < 2LL * spe_num_sms() ? rows : 2LL * spe_num_sms());
+        talking_fwd_rows_kernel<H><<<grid, 256, smem, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
+    } else {
+        talking_fwd_kernel<H><<<talking_grid(B, Nq, 4), 256, 0, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, ldS, ldA);
+    }
     SPE_LAUNCHED();
     return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, int B, int H,
-                                       int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream) {
+extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats,
+                                       int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream) {
     SPE_CHECK(S && A && Wl && bl && Ww && bw && B > 0 && Nq > 0 && Nk > 0, "spe_talking_softmax_fwd: bad argument");
     SPE_CHECK(ldS % 8 == 0 && ldA % 8 == 0 && ldS >= Nk && ldA >= Nk, "spe_talking_softmax_fwd: leading dims must be multiples of 8 and >= Nk");
     switch (H) {
-        case 2: return talking_fwd_launch<2>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
-        case 4: return talking_fwd_launch<4>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
-        case 8: return talking_fwd_launch<8>(S, A, Wl, bl, Ww, bw, B, Nq, Nk, ldS, ldA, ST(stream));
+        case 2: return talking_fwd_launch<2>(S, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
+        case 4: return talking_fwd_launch<4>(S, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
+        case 8: return talking_fwd_launch<8>(S, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
         default: SPE_FAIL("spe_talking_softmax_fwd: unsupported head count %d (2/4/8)", H);
     }
 }
 
 static int talking_bwd_grid(int B, int Nq) { return talking_grid(B, Nq, 4); }
 
+static int talking_bwd_rows_grid(int B, int Nq);
 extern "C" __attribute__((visibility("default"))) int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk) {
     (void)Nk;
-    return (int64_t)talking_bwd_grid(B, Nq) * (2 * H * H + 2 * H);
+    const int g1 = talking_bwd_grid(B, Nq), g2 = talking_bwd_rows_grid(B, Nq);
+    return (int64_t)(g1 > g2 ? g1 : g2) * (2 * H * H + 2 * H);
+}
+
+static int talking_bwd_rows_grid(int B, int Nq) {
+    const long long rows = (long long)B * Nq;
+    return (int)(rows < 2LL * spe_num_sms() ? rows : 2LL * spe_num_sms());
 }
 
 template <int H>
-static int talking_bwd_launch(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, int B, int Nq, int Nk,
-                              int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* ws, cudaStream_t st) {
-    const int grid = talking_bwd_grid(B, Nq);
+static int talking_bwd_launch(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B,
+                              int Nq, int Nk, int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* ws, cudaStream_t st) {
+    const size_t smem = (size_t)H * (ldS * 4 + ldA * 2);
+    const bool rows_ok = stats && smem <= 100 * 1024 && getenv("SPE_TALKING_WARP_ROWS") == nullptr;
+    const int grid = rows_ok ? talking_bwd_rows_grid(B, Nq) : talking_bwd_grid(B, Nq);
     {
         SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * 8.0, st);   // S f32 read + dA bf16 read + dS bf16 write
-        talking_bwd_kernel<H><<<grid, 256, 0, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, B * Nq, Nq, Nk,
-                                                    ldS, ldA, ws);
+        if (rows_ok) {
+            static bool done = false;
+            if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); done = true; }
+            talking_bwd_rows_kernel<H><<<grid, 256, smem, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, stats,
+                                                                 B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
+        } else {
+            talking_bwd_kernel<H><<<grid, 256, 0, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, B * Nq, Nq, Nk,
+                                                        ldS, ldA, ws);
+        }
         SPE_LAUNCHED();
     }
     const int NP = 2 * H * H + 2 * H;
@@ -828,16 +1128,16 @@ static int talking_bwd_launch(const float* S, const void* dA, void* dS, const fl
 }
 
 extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* bw,
-                                       int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw,
-                                       float* workspace, int64_t workspace_floats, void* stream) {
+                                       const float* stats, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw,
+                                       float* dbw, float* workspace, int64_t workspace_floats, void* stream) {
     (void)bw;
     SPE_CHECK(S && dA && dS && Wl && bl && Ww && dWl && dbl && dWw && dbw && workspace, "spe_talking_softmax_bwd: null argument");
     SPE_CHECK(ldS % 8 == 0 && ldA % 8 == 0 && ldS >= Nk && ldA >= Nk, "spe_talking_softmax_bwd: leading dims must be multiples of 8 and >= Nk");
     SPE_CHECK(workspace_floats >= spe_talking_softmax_bwd_workspace(B, H, Nq, Nk), "spe_talking_softmax_bwd: workspace too small");
     switch (H) {
-        case 2: return talking_bwd_launch<2>(S, dA, dS, Wl, bl, Ww, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
-        case 4: return talking_bwd_launch<4>(S, dA, dS, Wl, bl, Ww, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
-        case 8: return talking_bwd_launch<8>(S, dA, dS, Wl, bl, Ww, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
+        case 2: return talking_bwd_launch<2>(S, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
+        case 4: return talking_bwd_launch<4>(S, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
+        case 8: return talking_bwd_launch<8>(S, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
         default: SPE_FAIL("spe_talking_softmax_bwd: unsupported head count %d (2/4/8)", H);
     }
 }

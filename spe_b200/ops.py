@@ -497,16 +497,17 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         S = torch.empty((B, H, N, ld), dtype=torch.float32, device=qkv.device)
         _qk_logits(q, k, H, scale, S, ld)
         A = torch.empty((B, H, N, ld), dtype=torch.bfloat16, device=qkv.device)
-        check(lib().spe_talking_softmax_fwd(ptr(S), ptr(A), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), B, H, N, N, ld, ld, stream()))
+        stats = torch.empty((B * N, H), dtype=torch.float32, device=qkv.device)
+        check(lib().spe_talking_softmax_fwd(ptr(S), ptr(A), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, stream()))
         out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
         _pv(A, v, H, out, N, N, ld)
-        ctx.save_for_backward(qkv, S, A, Wl, bl, Ww, bw)
+        ctx.save_for_backward(qkv, S, A, Wl, bl, Ww, bw, stats)
         ctx.H, ctx.ld = H, ld
         return out
 
     @staticmethod
     def backward(ctx, dO):
-        qkv, S, A, Wl, bl, Ww, bw = ctx.saved_tensors
+        qkv, S, A, Wl, bl, Ww, bw, stats = ctx.saved_tensors
         H, ld = ctx.H, ctx.ld
         B, N, D3 = qkv.shape
         D = D3 // 3
@@ -525,7 +526,7 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         dWl, dbl, dWw, dbw = torch.zeros_like(Wl), torch.zeros_like(bl), torch.zeros_like(Ww), torch.zeros_like(bw)
         nws = lib().spe_talking_softmax_bwd_workspace(B, H, N, N)
         ws = torch.empty(nws, dtype=torch.float32, device=qkv.device)
-        check(lib().spe_talking_softmax_bwd(ptr(S), ptr(dA), ptr(dA), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), B, H, N, N, ld, ld, ptr(dWl), ptr(dbl),
+        check(lib().spe_talking_softmax_bwd(ptr(S), ptr(dA), ptr(dA), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, ptr(dWl), ptr(dbl),
                                             ptr(dWw), ptr(dbw), ptr(ws), nws, stream()))
         _dq_dk(dA, q, k, H, scale, N, N, ld, dq_out=dqkv[:, :, :D], dk_out=dqkv[:, :, D:2 * D])
         # exact bias gradients (the kernel's own sums of bf16 dA over B*N*N keys cancel catastrophically):
