@@ -167,14 +167,10 @@ def run_ours(args):
     crit_ref = factory.build_criterion(cfg, ("labels", "boxes", "cardinality"), gamma=2.0, refine=True, device=dev)
     crit.eval(); crit_ref.eval()                                    # deterministic targets: repeats pre-applied
     wd = crit.weight_dict
-    params = [p for p in model.parameters() if p.requires_grad]
-    # flat gradient buffer: p.grad are views, so ONE all-reduce per step covers every parameter
-    sizes = [(p.numel() + 7) // 8 * 8 for p in params]
-    flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-    off = 0
-    for p, s in zip(params, sizes):
-        p.grad = flat_grad[off:off + p.numel()].view_as(p)
-        off += s
+    # flat gradient buffer: ONE all-reduce per step covers every parameter.  Gradients are produced free-standing by
+    # autograd and packed with one multi-tensor copy (world > 1 only; a single GPU needs no exchange, like DDP at world 1).
+    from spe_b200.dp import FlatGradBuffer
+    gbuf = FlatGradBuffer(model.parameters(), mode="gather")
 
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
@@ -185,14 +181,13 @@ def run_ours(args):
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def step(images, targets):
-        flat_grad.zero_()
+        gbuf.zero_()
         out = model(images)
         ld = crit(out[0], targets)
         ld2 = crit_ref(out[1], targets)
         loss = sum(ld[k] * wd[k] for k in ld if k in wd) + sum(ld2[k] * wd[k] for k in ld2 if k in wd)
         loss.backward()
-        if world > 1:
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+        gbuf.all_reduce_mean()          # no-op at world 1
         return loss
 
     def e2e_step():

@@ -191,6 +191,103 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const uint16_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// softmax, warp-per-row variants (Nk <= NV*128): the whole row lives in registers, all loads are issued up front, no
+// shared memory and no block barriers.  The CTA-per-row kernels above remain for longer rows.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256, 2) softmax_fwd_warp_kernel(const float* __restrict__ S, uint16_t* __restrict__ P, const uint8_t* __restrict__ mask,
+                                                               long long rows_total, int H, int Nq, int Nk, long long ldS, long long ldP,
+                                                               float* __restrict__ pmean) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_total; r += warps) {
+        const int q = (int)(r % Nq);
+        const int b = (int)(r / ((long long)H * Nq));
+        const float* s = S + r * ldS;
+        const uint8_t* mk = mask ? mask + (long long)b * Nk : nullptr;
+        float4 v[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = 4 * lane + 128 * i;
+            v[i] = (j + 4 <= ldS) ? *reinterpret_cast<const float4*>(s + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = 4 * lane + 128 * i;
+            float* e = reinterpret_cast<float*>(&v[i]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (j + c >= Nk || (mk && mk[j + c])) e[c] = -INFINITY;
+                mx = fmaxf(mx, e[c]);
+            }
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float* e = reinterpret_cast<float*>(&v[i]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { e[c] = __expf(e[c] - mx); sum += e[c]; }
+        }
+        const float inv = 1.f / warp_sum(sum);
+        uint16_t* p = P + r * ldP;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = 4 * lane + 128 * i;
+            if (j + 4 <= ldP) {
+                const float a0 = v[i].x * inv, a1 = v[i].y * inv, a2 = v[i].z * inv, a3 = v[i].w * inv;     // exactly 0 beyond Nk
+                *reinterpret_cast<uint2*>(p + j) = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
+                if (pmean) {
+                    const float av[4] = {a0, a1, a2, a3};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (j + c < Nk) atomicAdd(pmean + ((long long)b * Nq + q) * Nk + j + c, av[c] / (float)H);
+                }
+            }
+        }
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256, 2) softmax_bwd_warp_kernel(const uint16_t* __restrict__ P, const uint16_t* dP, uint16_t* dS, long long rows_total, int Nk,
+                                                               long long ldP) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_total; r += warps) {
+        const uint16_t* p = P + r * ldP;
+        const uint16_t* dp = dP + r * ldP;
+        uint2 pv[NV], dv[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = 4 * lane + 128 * i;
+            const bool in = j + 4 <= ldP;
+            pv[i] = in ? *reinterpret_cast<const uint2*>(p + j) : make_uint2(0u, 0u);
+            dv[i] = in ? *reinterpret_cast<const uint2*>(dp + j) : make_uint2(0u, 0u);
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = 4 * lane + 128 * i;
+            const float2 p0 = unpack_bf16x2(pv[i].x), p1 = unpack_bf16x2(pv[i].y), d0 = unpack_bf16x2(dv[i].x), d1 = unpack_bf16x2(dv[i].y);
+            // P is exactly 0 in the padding; dP's padding was never written -> guard the products
+            dot += (j < Nk ? p0.x * d0.x : 0.f) + (j + 1 < Nk ? p0.y * d0.y : 0.f) + (j + 2 < Nk ? p1.x * d1.x : 0.f) + (j + 3 < Nk ? p1.y * d1.y : 0.f);
+        }
+        dot = warp_sum(dot);
+        uint16_t* o = dS + r * ldP;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = 4 * lane + 128 * i;
+            if (j + 4 <= ldP) {
+                const float2 p0 = unpack_bf16x2(pv[i].x), p1 = unpack_bf16x2(pv[i].y), d0 = unpack_bf16x2(dv[i].x), d1 = unpack_bf16x2(dv[i].y);
+                const float a0 = j < Nk ? p0.x * (d0.x - dot) : 0.f, a1 = j + 1 < Nk ? p0.y * (d0.y - dot) : 0.f;
+                const float a2 = j + 2 < Nk ? p1.x * (d1.x - dot) : 0.f, a3 = j + 3 < Nk ? p1.y * (d1.y - dot) : 0.f;
+                *reinterpret_cast<uint2*>(o + j) = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // talking-heads mix -> softmax -> mix   (cait.py:381-386)
 //   ONE WARP PER (b, q) ROW, streaming: no block-level barriers, no staging of the H x Nk slab.
 //   fwd : sweep A = logits L (head mix) with an online (max, sum) per mixed head; sweep B re-reads S (L2-hot),
@@ -1033,6 +1130,15 @@ extern "C" __attribute__((visibility("default"))) int spe_softmax_fwd(const floa
     if (!done) { SPE_CUDA(cudaFuncSetAttribute(softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
     if (pmean) SPE_CUDA(cudaMemsetAsync(pmean, 0, (size_t)B * Nq * Nk * 4, ST(stream)));
     SpeProfScope prof(SPE_FAM_SOFTMAX, (double)B * H * Nq * Nk * 6.0, ST(stream));
+    if (ldS % 4 == 0 && ldP % 4 == 0 && Nk <= 2048 && getenv("SPE_SOFTMAX_CTA_ROWS") == nullptr) {
+        const long long rows = (long long)B * H * Nq;
+        long long g = (rows + 7) / 8;
+        if (g > (long long)spe_num_sms() * 8) g = (long long)spe_num_sms() * 8;
+        if (Nk <= 512) softmax_fwd_warp_kernel<4><<<(unsigned)g, 256, 0, ST(stream)>>>(S, reinterpret_cast<uint16_t*>(P), mask, rows, H, Nq, Nk, ldS, ldP, pmean);
+        else softmax_fwd_warp_kernel<16><<<(unsigned)g, 256, 0, ST(stream)>>>(S, reinterpret_cast<uint16_t*>(P), mask, rows, H, Nq, Nk, ldS, ldP, pmean);
+        SPE_LAUNCHED();
+        return 0;
+    }
     softmax_fwd_kernel<<<(unsigned)((long long)B * H * Nq), 256, (size_t)Nk * 4, ST(stream)>>>(S, reinterpret_cast<uint16_t*>(P), mask, H, Nq, Nk, ldS,
                                                                                                 ldP, pmean);
     SPE_LAUNCHED();
@@ -1045,6 +1151,15 @@ extern "C" __attribute__((visibility("default"))) int spe_softmax_bwd(const void
     static bool done = false;
     if (!done) { SPE_CUDA(cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
     SpeProfScope prof(SPE_FAM_SOFTMAX, (double)B * H * Nq * Nk * 6.0, ST(stream));
+    if (ldP % 4 == 0 && Nk <= 2048 && getenv("SPE_SOFTMAX_CTA_ROWS") == nullptr) {
+        const long long rows = (long long)B * H * Nq;
+        long long g = (rows + 7) / 8;
+        if (g > (long long)spe_num_sms() * 8) g = (long long)spe_num_sms() * 8;
+        if (Nk <= 512) softmax_bwd_warp_kernel<4><<<(unsigned)g, 256, 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(P), reinterpret_cast<const uint16_t*>(dP), reinterpret_cast<uint16_t*>(dS), rows, Nk, ldP);
+        else softmax_bwd_warp_kernel<16><<<(unsigned)g, 256, 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(P), reinterpret_cast<const uint16_t*>(dP), reinterpret_cast<uint16_t*>(dS), rows, Nk, ldP);
+        SPE_LAUNCHED();
+        return 0;
+    }
     softmax_bwd_kernel<<<(unsigned)((long long)B * H * Nq), 256, (size_t)Nk * 8, ST(stream)>>>(reinterpret_cast<const uint16_t*>(P),
                                                                                                 reinterpret_cast<const uint16_t*>(dP),
                                                                                                 reinterpret_cast<uint16_t*>(dS), Nk, ldP);

@@ -5,22 +5,52 @@ import torch.distributed as dist
 
 
 class FlatGradBuffer:
-    def __init__(self, params, align=8):
+    """mode 'views'  : p.grad ARE slices of the flat buffer (autograd accumulates into them; one add kernel per parameter);
+       mode 'gather' : autograd produces free-standing gradients (no per-parameter add), `gather()` packs them into the flat
+                       buffer with ONE multi-tensor copy before the all-reduce, and re-points p.grad at the reduced slices."""
+
+    def __init__(self, params, align=8, mode="views"):
         self.params = [p for p in params if p.requires_grad]
+        self.mode = mode
         sizes = [(p.numel() + align - 1) // align * align for p in self.params]
         dev = self.params[0].device
         self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.views = []
         off = 0
         for p, s in zip(self.params, sizes):
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += s
+        if mode == "views":
+            for p, v in zip(self.params, self.views):
+                p.grad = v
 
     def zero_(self):
-        self.flat.zero_()
+        if self.mode == "views":
+            self.flat.zero_()
+        else:
+            for p in self.params:
+                p.grad = None
+
+    def gather(self):
+        if self.mode != "gather":
+            return
+        src, dst, missing = [], [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                missing.append(v)
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad); dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        if missing:
+            torch._foreach_zero_(missing)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def all_reduce_mean(self):
         """grad <- mean over ranks (what DDP does, main.py:171-173).  No-op when not distributed."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.gather()
             if self.flat.is_cuda:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
             else:
