@@ -254,13 +254,15 @@ def run_ours(args):
                             "share_of_step": (t / nprof) / (ms_prof / nprof)}
     gm = fam["gemm"]
     g_tflops = gm[1] / (gm[0] * 1e-3) / 1e12 if gm[0] > 0 else 0.0
-    hbm = {k: (fam[k][1] / (fam[k][0] * 1e-3) / 1e9 if fam[k][0] > 0 else 0.0) for k in ("talking_softmax_fwd", "talking_softmax_bwd", "softmax", "layernorm")}
+    hbm = {k: (fam[k][1] / (fam[k][0] * 1e-3) / 1e9 if fam[k][0] > 0 else 0.0)
+           for k in ("gemm_attention", "talking_softmax_fwd", "talking_softmax_bwd", "softmax", "layernorm")}
     dominant = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"]) if breakdown else "gemm"
     if dominant == "gemm" or dominant not in hbm:
-        roof = {"kernel": "gemm_tcgen05_kernel (all GEMM launches of a step)", "bound": "tensor", "achieved": g_tflops, "peak": peaks["tflops"],
+        roof = {"kernel": "gemm_tcgen05_kernel (all dense/linear GEMM launches of a step)", "bound": "tensor", "achieved": g_tflops, "peak": peaks["tflops"],
                 "unit": "TFLOP/s", "frac": g_tflops / peaks["tflops"], "traffic": None}
     else:
-        roof = {"kernel": dominant, "bound": "hbm", "achieved": hbm[dominant], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        kname = "gemm_tcgen05_kernel (batched attention GEMMs: QK^T / PV and gradients)" if dominant == "gemm_attention" else dominant
+        roof = {"kernel": kname, "bound": "hbm", "achieved": hbm[dominant], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": hbm[dominant] / peaks["hbm_gbs"], "traffic": None}
     roof["peak_source"] = peaks["src"] + " -- of measured"
     roof["how"] = "CUDA events on the launch stream around every launch of the family during %d profiled steps; achieved = sum(algorithmic work)/sum(time)" % nprof

@@ -27,7 +27,8 @@ int spe_version(void);
 int64_t spe_launch_count(void);
 /* Optional device-side timing of kernel families with CUDA events on the launching stream (bench.py roofline).
  * Families: 0 gemm (work = algorithmic flops), 1 talking-softmax fwd, 2 talking-softmax bwd, 3 softmax,
- * 4 layernorm (work = algorithmic bytes), 5 matcher LSAP (work = images), 6 other. */
+ * 4 layernorm (work = algorithmic bytes), 5 matcher LSAP (work = images), 6 other, 7 batched attention GEMMs (QK^T / PV and
+ * gradients; work = algorithmic bytes: they are bound by the N^2 operand in HBM). */
 int spe_prof_enable(int on);
 int spe_prof_collect(double* ms, double* work, int64_t* launches);   /* arrays of spe_prof_family_count() */
 int spe_prof_family_count(void);

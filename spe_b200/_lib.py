@@ -105,7 +105,7 @@ def launch_count():
     return int(lib().spe_launch_count())
 
 
-PROF_FAMILIES = ["gemm", "talking_softmax_fwd", "talking_softmax_bwd", "softmax", "layernorm", "matcher_lsap", "other"]
+PROF_FAMILIES = ["gemm", "talking_softmax_fwd", "talking_softmax_bwd", "softmax", "layernorm", "matcher_lsap", "other", "gemm_attention"]
 
 
 def prof_enable(on):

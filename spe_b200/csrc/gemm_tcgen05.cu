@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                                                                       const EpiParams ep) {
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
-    constexpr uint32_t TMEM_COLS = 2 * BN;               // double-buffered accumulator (BN in {64,128} -> 128 / 256 columns)
+    constexpr uint32_t TMEM_COLS = 2 * BN;               // double-buffered accumulator (BN in {64,128,256} -> 128 / 256 / 512 columns)
+    static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
     // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -601,7 +602,9 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     SPE_CHECK(a && a->A && a->B && a->C, "spe_gemm: null argument");
     SPE_CHECK(a->M > 0 && a->N > 0 && a->K > 0 && a->batch1 > 0 && a->batch2 > 0, "spe_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
     SPE_CHECK(a->act == SPE_ACT_NONE || a->act == SPE_ACT_RELU || a->act == SPE_ACT_GELU || a->aux_in, "spe_gemm: *_GRAD activation needs aux_in");
-    const int BN = a->N <= 64 ? 64 : 128;
+    // 128x256 tiles (fewer A re-reads, 2 pipeline stages) were measured: S-type GEMMs -6%, fc1 +15% -> opt-in only (SPE_GEMM_BN256=1)
+    const bool wideN = a->N >= 512 && (((a->N + 255) / 256) * 256 - a->N) * 8 <= a->N && getenv("SPE_GEMM_BN256") != nullptr;
+    const int BN = a->N <= 64 ? 64 : (wideN ? 256 : 128);
     const int batch = a->batch1 * a->batch2;
     SPE_CHECK(batch == 1 || !(a->aux_in || a->aux_out), "spe_gemm: aux_in / aux_out are not batched");
     CUtensorMap tA, tB;
@@ -654,7 +657,13 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     if (splits > 1) SPE_CUDA(cudaMemsetAsync(a->C, 0, (size_t)a->M * a->N * 4, st));
     char tag[64];
     if (g_spe_prof_on) snprintf(tag, sizeof(tag), "M%d N%d K%d b%d a%d b%d c%d", a->M, a->N, a->K, batch, a->a_major, a->b_major, a->c_dtype);
-    SpeProfScope prof(SPE_FAM_GEMM, 2.0 * a->M * a->N * (double)a->K * batch, st, tag);     // algorithmic flops
+    // batched attention GEMMs (QK^T / PV and their gradients: K or N = head dim) are bound by their N^2 operand in HBM, not by the
+    // tensor pipe: they are accounted as their own family with algorithmic BYTES; all other GEMMs with algorithmic FLOPs.
+    const bool attn = batch > 1 && (a->K <= 128 || a->N <= 128);
+    const double elt_c = cf32 ? 4.0 : 2.0;
+    const double attn_bytes = ((double)a->M * a->K + (double)a->N * a->K) * 2.0 * batch + (double)a->M * a->N * elt_c * batch;
+    SpeProfScope prof(attn ? SPE_FAM_GEMM_ATTN : SPE_FAM_GEMM, attn ? attn_bytes : 2.0 * a->M * a->N * (double)a->K * batch, st, tag);
     if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);
+    if (BN == 256) return dispatch_major<256, 2>(a->a_major, a->b_major, tA, tB, io, ep, st);
     return dispatch_major<128, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);
 }
