@@ -45,6 +45,7 @@ struct EpiParams {
     int tma_io;                   // epilogue tiles through TMA (else direct per-thread global access)
     int splits, kb_per_split;     // split-K
     int tiles_m, tiles_n, num_tiles;
+    int mode, mode_nl;            // EM_* epilogue specialisation for lead / non-lead (split-K) tiles
     int dbg;                      // timing experiments only (SPE_GEMM_DBG bitmask): 1 no TMA store, 2 no smem writes, 4 no TMEM load, 8 no proxy fence
 };
 
@@ -171,6 +172,76 @@ __device__ __noinline__ void epilogue_direct(const EpiParams& ep, const uint32_t
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue math for one 64-column super-chunk of one row (thread = row), accumulator already in registers.
+// Fully specialised at compile time: no branches, all 64 columns unrolled -> ~150 independent instructions per warp.
+// (The previous run-time-flag version executed ~500 dependent, branchy instructions per super-chunk; with 2 epilogue
+//  warps per scheduler that made EVERY GEMM epilogue-latency bound: the MMA warp spent its time waiting on `tempty`.)
+//   ACT: 0 none, 1 relu, 2 gelu, 3 relu_grad (needs Xi), 4 gelu_grad (needs Xi)
+// ------------------------------------------------------------------------------------------------
+template <bool C32, bool BIAS, int ACT, bool GAMMA, bool RES, bool XO>
+__device__ __forceinline__ void epi_fast(const EpiParams& ep, const uint32_t (&r)[64], int nb, int lane, uint32_t sRC, uint32_t sX) {
+    const uint32_t rowoff = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const int n = nb + g * 8;
+        float v[8];
+        if constexpr (BIAS) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[g * 8 + j]), ep.alpha, bb[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * ep.alpha;
+        }
+        if constexpr (XO) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sX + rowoff + (((uint32_t)g ^ sw) << 4)), "r"(pack_bf16x2(v[0], v[1])),
+                         "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
+        }
+        if constexpr (ACT == SPE_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if constexpr (ACT == SPE_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+        } else if constexpr (ACT == SPE_ACT_RELU_GRAD || ACT == SPE_ACT_GELU_GRAD) {
+            uint4 a;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sX + rowoff + (((uint32_t)g ^ sw) << 4)));
+            const float2 t0 = unpack_bf16x2(a.x), t1 = unpack_bf16x2(a.y), t2 = unpack_bf16x2(a.z), t3 = unpack_bf16x2(a.w);
+            const float ax[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (ACT == SPE_ACT_RELU_GRAD) ? (ax[j] > 0.f ? v[j] : 0.f) : v[j] * gelu_erf_grad(ax[j]);
+        }
+        if constexpr (GAMMA) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n)), g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
+            v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+        }
+        if constexpr (RES) {
+            // fp32 residual slabs; the C tile overlays them (each thread reads its chunk for group g before writing group g)
+            const uint32_t sl = sRC + (g >> 2) * SLAB + rowoff;
+            float4 r0, r1;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r0.x), "=f"(r0.y), "=f"(r0.z), "=f"(r0.w) : "r"(sl + (((uint32_t)((g & 3) * 2) ^ sw) << 4)));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r1.x), "=f"(r1.y), "=f"(r1.z), "=f"(r1.w) : "r"(sl + (((uint32_t)((g & 3) * 2 + 1) ^ sw) << 4)));
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+        if constexpr (C32) {
+            const uint32_t sl = sRC + (g >> 2) * SLAB + rowoff;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + (((uint32_t)((g & 3) * 2) ^ sw) << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + (((uint32_t)((g & 3) * 2 + 1) ^ sw) << 4)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+        } else {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sRC + rowoff + (((uint32_t)g ^ sw) << 4)), "r"(pack_bf16x2(v[0], v[1])),
+                         "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
+        }
+    }
+}
+
+// the specialisations that exist (host picks one; anything else takes the generic run-time path)
+enum { EM_GENERIC = 0, EM_F32, EM_BF16, EM_BF16_BIAS, EM_F32_BIAS, EM_F32_BIAS_GAMMA_RES_XO, EM_F32_BIAS_RES, EM_F32_RES, EM_BF16_BIAS_RES,
+       EM_BF16_BIAS_GELU_XO, EM_BF16_BIAS_RELU, EM_BF16_RELUGRAD, EM_BF16_GELUGRAD };
+
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -245,16 +316,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     const uint32_t fb = full0 + 8 * s;
-                    mbar_expect_tx(fb, A_BYTES + B_BYTES);
+                    const bool skipA = (ep.dbg & 16) != 0, skipB = (ep.dbg & 32) != 0;      // timing experiments only
+                    mbar_expect_tx(fb, (skipA ? 0u : A_BYTES) + (skipB ? 0u : B_BYTES));
                     const uint32_t a_dst = smem_u32(sA + s * A_BYTES), b_dst = smem_u32(sB + s * B_BYTES);
                     const int kc = (kb0 + kb) * BK;
-                    if constexpr (!A_MN) {
+                    if (skipA) {
+                    } else if constexpr (!A_MN) {
                         tma_load_4d(a_dst, &tmA, fb, kc, m0, b2 * ep.a_m2, b1 * ep.a_m1);
                     } else {
 #pragma unroll
                         for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + c * 64, kc, b2 * ep.a_m2, b1 * ep.a_m1);
                     }
-                    if constexpr (!B_MN) {
+                    if (skipB) {
+                    } else if constexpr (!B_MN) {
                         tma_load_4d(b_dst, &tmB, fb, kc, n0, b2 * ep.b_m2, b1 * ep.b_m1);
                     } else {
 #pragma unroll
@@ -365,6 +439,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     continue;
                 }
                 if (loads) { mbar_wait(ebar, eph); eph ^= 1u; }
+                const int emode = (nb + 64 <= ep.N && ep.dbg == 0) ? (lead ? ep.mode : ep.mode_nl) : EM_GENERIC;
+                if (emode != EM_GENERIC) {
+                    uint32_t r[64];
+                    TMEM_LD_32x32b_X32(taddr, r);
+                    TMEM_LD_32x32b_X32(taddr + 32, r + 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (last_sc) {
+                        // last TMEM read of this warp for this tile: hand the accumulator buffer back to the MMA warp
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                        arrived = true;
+                    }
+                    switch (emode) {
+                        case EM_F32: epi_fast<true, false, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_BF16: epi_fast<false, false, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_BF16_BIAS: epi_fast<false, true, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_F32_BIAS: epi_fast<true, true, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_F32_BIAS_GAMMA_RES_XO: epi_fast<true, true, 0, true, true, true>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_F32_BIAS_RES: epi_fast<true, true, 0, false, true, false>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_F32_RES: epi_fast<true, false, 0, false, true, false>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_BF16_BIAS_RES: epi_fast<false, true, 0, false, true, false>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_BF16_BIAS_GELU_XO: epi_fast<false, true, SPE_ACT_GELU, false, false, true>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_BF16_BIAS_RELU: epi_fast<false, true, SPE_ACT_RELU, false, false, false>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_BF16_RELUGRAD: epi_fast<false, false, SPE_ACT_RELU_GRAD, false, false, false>(ep, r, nb, lane, sRC, sX); break;
+                        default: epi_fast<false, false, SPE_ACT_GELU_GRAD, false, false, false>(ep, r, nb, lane, sRC, sX); break;
+                    }
+                } else {
                 // NOTE on code size: every condition below is warp-uniform and is tested once per 8-column group (never per
                 // element); the N-tail takes the same code with clamped vector loads.  (An earlier per-element-branch version
                 // compiled to ~5000 SASS instructions per super-chunk and made every GEMM issue-bound in its epilogue.)
@@ -466,6 +568,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     }
                 }
                 }
+                }   // generic path
                 if (!(ep.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0 && !(ep.dbg & 1)) {
@@ -637,6 +740,27 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     if (tma_io && a->aux_out && make_tmap_io(&io.Xo, a->aux_out, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
     ep.tma_io = tma_io ? 1 : 0;
     { const char* d = getenv("SPE_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; }
+    {
+        const bool bi = a->bias != nullptr, ga = a->gamma != nullptr, re = a->residual != nullptr, xo = a->aux_out != nullptr, xi = a->aux_in != nullptr;
+        int m = EM_GENERIC;
+        if (tma_io && getenv("SPE_GEMM_GENERIC_EPILOGUE") == nullptr) {
+            if (a->act == SPE_ACT_NONE && !xi) {
+                if (cf32 && !bi && !ga && !re && !xo) m = EM_F32;
+                else if (!cf32 && !bi && !ga && !re && !xo) m = EM_BF16;
+                else if (!cf32 && bi && !ga && !re && !xo) m = EM_BF16_BIAS;
+                else if (cf32 && bi && !ga && !re && !xo) m = EM_F32_BIAS;
+                else if (cf32 && bi && ga && re && xo) m = EM_F32_BIAS_GAMMA_RES_XO;
+                else if (cf32 && bi && !ga && re && !xo) m = EM_F32_BIAS_RES;
+                else if (cf32 && !bi && !ga && re && !xo) m = EM_F32_RES;
+                else if (!cf32 && bi && !ga && re && !xo) m = EM_BF16_BIAS_RES;
+            } else if (a->act == SPE_ACT_GELU && !cf32 && bi && !ga && !re && xo && !xi) m = EM_BF16_BIAS_GELU_XO;
+            else if (a->act == SPE_ACT_RELU && !cf32 && bi && !ga && !re && !xo && !xi) m = EM_BF16_BIAS_RELU;
+            else if (a->act == SPE_ACT_RELU_GRAD && !cf32 && !bi && !ga && !re && !xo && xi) m = EM_BF16_RELUGRAD;
+            else if (a->act == SPE_ACT_GELU_GRAD && !cf32 && !bi && !ga && !re && !xo && xi) m = EM_BF16_GELUGRAD;
+        }
+        ep.mode = m;
+        ep.mode_nl = (m != EM_GENERIC && cf32) ? EM_F32 : EM_GENERIC;      // split-K partial tiles: plain accumulate
+    }
     // ---- split-K: few output tiles but a long reduction (wgrad).  fp32 contiguous C, no activation / aux / gamma.
     const int total_kb = (a->K + BK - 1) / BK;
     ep.tiles_m = (a->M + BM - 1) / BM;
