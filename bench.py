@@ -167,10 +167,10 @@ def run_ours(args):
     crit_ref = factory.build_criterion(cfg, ("labels", "boxes", "cardinality"), gamma=2.0, refine=True, device=dev)
     crit.eval(); crit_ref.eval()                                    # deterministic targets: repeats pre-applied
     wd = crit.weight_dict
-    # flat gradient buffer: ONE all-reduce per step covers every parameter.  Gradients are produced free-standing by
-    # autograd and packed with one multi-tensor copy (world > 1 only; a single GPU needs no exchange, like DDP at world 1).
+    # flat gradient buffer: ONE all-reduce per step covers every parameter.  p.grad are slices of it and the backward
+    # kernels accumulate straight into them (wgrad GEMM reduce-add / atomics: no temporaries, no per-parameter add kernels).
     from spe_b200.dp import FlatGradBuffer
-    gbuf = FlatGradBuffer(model.parameters(), mode="gather")
+    gbuf = FlatGradBuffer(model.parameters(), mode=os.environ.get("SPE_GRAD_MODE", "views"))
 
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)

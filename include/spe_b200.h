@@ -63,7 +63,8 @@ typedef struct {
     void* aux_out;                    /* bf16 [M,N] (ld = ld_aux) or NULL: v after bias, BEFORE act */
     int64_t ld_aux;
     const float* gamma;               /* [N] or NULL : v = gamma[n]*v   (LayerScale, cait.py:414)  */
-    const float* residual;            /* f32 [M,N] (ld = ldr) or NULL : v += residual[m][n]        */
+    const float* residual;            /* f32 [M,N] (ld = ldr) or NULL : v += residual[m][n].  residual == C (same pitch, f32, no gamma/act)
+                                         means C += alpha A B (+bias): tiles are reduce-added in place (gradient accumulation) */
     int64_t ldr, r_sb1, r_sb2;
     int split, split_stride;          /* if split>0: dest column = (n/split)*split_stride + n%split */
 } spe_gemm_args;

@@ -44,6 +44,7 @@ struct EpiParams {
     int r_m1, r_m2;
     int tma_io;                   // epilogue tiles through TMA (else direct per-thread global access)
     int splits, kb_per_split;     // split-K
+    int accum;                    // C += ... (residual aliased C on entry): every tile is stored with a reduce-add
     int tiles_m, tiles_n, num_tiles;
     int mode, mode_nl;            // EM_* epilogue specialisation for lead / non-lead (split-K) tiles
     int dbg;                      // timing experiments only (SPE_GEMM_DBG bitmask): 1 no TMA store, 2 no smem writes, 4 no TMEM load, 8 no proxy fence
@@ -166,7 +167,7 @@ __device__ __noinline__ void epilogue_direct(const EpiParams& ep, const uint32_t
         if (ep.gamma) x *= __ldg(ep.gamma + n);
         if (Rr) x += Rr[n];
         const int dn = ep.split > 0 ? (n / ep.split) * ep.split_stride + (n % ep.split) : n;
-        if (ep.splits > 1) atomicAdd(Cf + dn, x);
+        if (ep.splits > 1 || ep.accum) atomicAdd(Cf + dn, x);
         else if (ep.c_dtype == SPE_DT_F32) Cf[dn] = x;
         else Cb[dn] = f_to_bf16(x);
     }
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 if (!(ep.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0 && !(ep.dbg & 1)) {
-                    if (ep.splits > 1) {
+                    if (ep.splits > 1 || ep.accum) {
                         tma_reduce_add_4d(&tmC, sRC, nb, mrow, b2, b1);
                         if (nb + 32 < ep.N) tma_reduce_add_4d(&tmC, sRC + SLAB, nb + 32, mrow, b2, b1);
                     } else if (c32) {
@@ -720,6 +721,12 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     ep.alpha = a->alpha; ep.bias = a->bias; ep.act = a->act;
     ep.aux_in = reinterpret_cast<const uint16_t*>(a->aux_in); ep.aux_out = reinterpret_cast<uint16_t*>(a->aux_out); ep.ld_aux = a->ld_aux;
     ep.gamma = a->gamma; ep.residual = a->residual; ep.ldr = a->ldr; ep.r_sb1 = a->r_sb1; ep.r_sb2 = a->r_sb2;
+    // residual aliasing C (same pointer and pitch) = in-place accumulation C += alpha A B [+ bias]: no residual tile is loaded,
+    // every tile (and every K split) is reduce-added into C by the TMA store engine.  This is how wgrad accumulates into .grad.
+    const bool accum = a->residual && a->residual == (const float*)a->C && a->c_dtype == SPE_DT_F32 && a->ldr == a->ldc &&
+                       (batch == 1 || (a->r_sb1 == a->c_sb1 && a->r_sb2 == a->c_sb2)) && !a->gamma && a->act == SPE_ACT_NONE;
+    if (accum) { ep.residual = nullptr; ep.accum = 1; }
+    const float* residual = accum ? nullptr : a->residual;
     ep.split = a->split; ep.split_stride = a->split_stride;
     ep.M = a->M; ep.N = a->N; ep.K = a->K; ep.batch2 = a->batch2;
     ep.a_m1 = (a->batch1 > 1 && a->a_sb1 == 0) ? 0 : 1; ep.a_m2 = (a->batch2 > 1 && a->a_sb2 == 0) ? 0 : 1;
@@ -735,13 +742,13 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     const bool gamma_ok = !a->gamma || (reinterpret_cast<uintptr_t>(a->gamma) & 15) == 0;
     bool tma_io = a->split == 0 && getenv("SPE_GEMM_DIRECT_EPILOGUE") == nullptr && !(a->aux_in && a->aux_out) && bias_ok && gamma_ok;
     if (tma_io && make_tmap_io(&io.C, a->C, cf32, a->M, a->N, a->ldc, a->c_sb1, a->c_sb2, a->batch1, a->batch2)) tma_io = false;
-    if (tma_io && a->residual && make_tmap_io(&io.R, a->residual, true, a->M, a->N, a->ldr, a->r_sb1, a->r_sb2, a->batch1, a->batch2)) tma_io = false;
+    if (tma_io && residual && make_tmap_io(&io.R, residual, true, a->M, a->N, a->ldr, a->r_sb1, a->r_sb2, a->batch1, a->batch2)) tma_io = false;
     if (tma_io && a->aux_in && make_tmap_io(&io.Xi, a->aux_in, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
     if (tma_io && a->aux_out && make_tmap_io(&io.Xo, a->aux_out, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
     ep.tma_io = tma_io ? 1 : 0;
     { const char* d = getenv("SPE_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; }
     {
-        const bool bi = a->bias != nullptr, ga = a->gamma != nullptr, re = a->residual != nullptr, xo = a->aux_out != nullptr, xi = a->aux_in != nullptr;
+        const bool bi = a->bias != nullptr, ga = a->gamma != nullptr, re = residual != nullptr, xo = a->aux_out != nullptr, xi = a->aux_in != nullptr;
         int m = EM_GENERIC;
         if (tma_io && getenv("SPE_GEMM_GENERIC_EPILOGUE") == nullptr) {
             if (a->act == SPE_ACT_NONE && !xi) {
@@ -768,7 +775,7 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     int splits = 1;
     const long long tiles = (long long)ep.tiles_m * ep.tiles_n * batch;
     SPE_CHECK(tiles < (1LL << 30), "spe_gemm: too many tiles");
-    if (cf32 && batch == 1 && a->act == SPE_ACT_NONE && !a->aux_in && !a->aux_out && !a->gamma && a->residual != (const float*)a->C &&
+    if (cf32 && batch == 1 && a->act == SPE_ACT_NONE && !a->aux_in && !a->aux_out && !a->gamma && (accum || a->residual != (const float*)a->C) &&
         a->ldc == a->N && a->split == 0 && tiles * 2 <= spe_num_sms() && total_kb >= 8 && getenv("SPE_GEMM_NO_SPLITK") == nullptr) {
         splits = (int)((spe_num_sms() + tiles - 1) / tiles);
         if (splits > total_kb / 4) splits = total_kb / 4;
@@ -778,7 +785,7 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     splits = (total_kb + ep.kb_per_split - 1) / ep.kb_per_split;      // no empty split
     ep.splits = splits;
     ep.num_tiles = (int)(tiles * splits);
-    if (splits > 1) SPE_CUDA(cudaMemsetAsync(a->C, 0, (size_t)a->M * a->N * 4, st));
+    if (splits > 1 && !accum) SPE_CUDA(cudaMemsetAsync(a->C, 0, (size_t)a->M * a->N * 4, st));
     char tag[64];
     if (g_spe_prof_on) snprintf(tag, sizeof(tag), "M%d N%d K%d b%d a%d b%d c%d", a->M, a->N, a->K, batch, a->a_major, a->b_major, a->c_dtype);
     // batched attention GEMMs (QK^T / PV and their gradients: K or N = head dim) are bound by their N^2 operand in HBM, not by the

@@ -5,11 +5,13 @@ import torch.distributed as dist
 
 
 class FlatGradBuffer:
-    """mode 'views'  : p.grad ARE slices of the flat buffer (autograd accumulates into them; one add kernel per parameter);
+    """mode 'views'  : p.grad ARE slices of the flat buffer.  With fused_accumulate (default) the spe_b200 backward kernels add
+                       their results straight into the slices (wgrad GEMM reduce-add, atomics) and autograd sees None for those
+                       parameters; otherwise autograd accumulates (one temporary + one add kernel per parameter);
        mode 'gather' : autograd produces free-standing gradients (no per-parameter add), `gather()` packs them into the flat
                        buffer with ONE multi-tensor copy before the all-reduce, and re-points p.grad at the reduced slices."""
 
-    def __init__(self, params, align=8, mode="views"):
+    def __init__(self, params, align=8, mode="views", fused_accumulate=True):
         self.params = [p for p in params if p.requires_grad]
         self.mode = mode
         sizes = [(p.numel() + align - 1) // align * align for p in self.params]
@@ -23,6 +25,7 @@ class FlatGradBuffer:
         if mode == "views":
             for p, v in zip(self.params, self.views):
                 p.grad = v
+                p._spe_accum = fused_accumulate     # ops.grad_sink: backward kernels accumulate straight into the slice
 
     def zero_(self):
         if self.mode == "views":

@@ -127,10 +127,43 @@ def _linear_dgrad(dy, w16, out, **kw):
 
 
 # dw[N,K] = dy[M,N]^T @ x[M,K]   (fp32 out)
-def _linear_wgrad(dy, x, out):
+def _linear_wgrad(dy, x, out, accumulate=False):
     M, N = _rows(dy), dy.shape[-1]
     K = x.shape[-1]
-    return gemm(dy, x, out, N, K, M, a_major=MAJOR_MN, lda=dy.stride(-2), b_major=MAJOR_MN, ldb=x.stride(-2), ldc=K)
+    return gemm(dy, x, out, N, K, M, a_major=MAJOR_MN, lda=dy.stride(-2), b_major=MAJOR_MN, ldb=x.stride(-2), ldc=K,
+                residual=out if accumulate else None, ldr=K)
+
+
+def grad_sink(p):
+    """The fp32 gradient accumulator of parameter `p` when its owner opted in (dp.FlatGradBuffer 'views' mode sets
+    p._spe_accum): backward kernels then accumulate straight into p.grad (wgrad GEMM reduce-adds its tiles, the column-sum
+    kernels use atomics) and hand autograd None for p -- no temporary, no zero-fill, no AccumulateGrad add kernel.
+    Anything else (no .grad yet, views of a packed parameter, foreign dtype) takes the ordinary autograd route."""
+    if p is None or not p.is_leaf or not getattr(p, "_spe_accum", False):
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device or g.shape != p.shape:
+        return None
+    return g
+
+
+def _grad_out(p, shape, dev):
+    """(buffer to accumulate into, value to return to autograd)."""
+    g = grad_sink(p)
+    if g is not None:
+        return g, None
+    z = torch.zeros(shape, dtype=torch.float32, device=dev)
+    return z, z
+
+
+def _wgrad_into(p, dy, x):
+    g = grad_sink(p)
+    if g is not None:
+        _linear_wgrad(dy, x, g, accumulate=True)
+        return None
+    dw = torch.empty(p.shape, dtype=torch.float32, device=x.device)
+    _linear_wgrad(dy, x, dw)
+    return dw
 
 
 def _pad_cols(t2d):
@@ -177,7 +210,7 @@ class LinearFn(torch.autograd.Function):
                  act=_ACT[act], residual=residual, ldr=N, r_sb=(0, 0))
         else:
             _linear_fwd(x, w16, bias, out, gamma=gamma, residual=residual, ldr=N, aux_out=y, ld_aux=N, act=_ACT[act])
-        ctx.save_for_backward(x, weight, gamma, y, out if act is not None else None)
+        ctx.save_for_backward(x, weight, gamma, y, out if act is not None else None, bias)
         ctx.has_bias = bias is not None
         ctx.res = None if residual is None else ("b" if bcast else "f")
         ctx.act = act
@@ -185,20 +218,22 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, gamma, y, h = ctx.saved_tensors
+        x, weight, gamma, y, h, bias = ctx.saved_tensors
         w16 = shadow(weight)
         N, K = weight.shape
         dout = dout.contiguous()
         dgamma = dbias = None
+        dgamma_b = dbias_b = None
         dres = None
         if ctx.res is not None:
             d32 = dout if dout.dtype == torch.float32 else _to_f32(dout)
             dres = d32 if ctx.res == "f" else d32.sum(0)
         if gamma is not None:
             dy = torch.empty(dout.shape, dtype=torch.bfloat16, device=dout.device)
-            dgamma = torch.zeros_like(gamma)
-            dbias = torch.zeros(N, dtype=torch.float32, device=dout.device) if ctx.has_bias else None
-            check(lib().spe_layerscale_bwd(ptr(dout), ptr(y), ptr(gamma), _rows(dout), N, ptr(dy), ptr(dgamma), ptr(dbias), stream()))
+            dgamma_b, dgamma = _grad_out(gamma, gamma.shape, dout.device)
+            if ctx.has_bias:
+                dbias_b, dbias = _grad_out(bias, (N,), dout.device)
+            check(lib().spe_layerscale_bwd(ptr(dout), ptr(y), ptr(gamma), _rows(dout), N, ptr(dy), ptr(dgamma_b), ptr(dbias_b), stream()))
         else:
             dy = dout if dout.dtype == torch.bfloat16 else to_bf16(dout)
             if ctx.act is not None:
@@ -208,15 +243,14 @@ class LinearFn(torch.autograd.Function):
                 check(lib().spe_relu_bwd_bf16(ptr(dy), ptr(h16), ptr(dpre), dy.numel(), stream()))
                 dy = dpre
             if ctx.has_bias:
-                dbias = torch.zeros(N, dtype=torch.float32, device=dout.device)
-                colsum_bf16(_pad_cols(dy.view(-1, N)), dbias)
+                dbias_b, dbias = _grad_out(bias, (N,), dout.device)
+                colsum_bf16(_pad_cols(dy.view(-1, N)), dbias_b)
         dy = _pad_cols(dy.view(-1, N))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
             _linear_dgrad(dy, w16, dx)
-        dw = torch.empty((N, K), dtype=torch.float32, device=x.device)
-        _linear_wgrad(dy, x, dw)
+        dw = _wgrad_into(weight, dy, x)
         return dx, dw, dbias, dres, dgamma, None, None
 
 
@@ -247,37 +281,35 @@ class FfnFn(torch.autograd.Function):
         out = torch.empty(lead + (w2.shape[0],), dtype=torch.float32, device=x.device)
         y = torch.empty(lead + (w2.shape[0],), dtype=torch.bfloat16, device=x.device) if gamma is not None else None
         _linear_fwd(h, w2_16, b2, out, gamma=gamma, residual=residual, ldr=w2.shape[0], aux_out=y, ld_aux=w2.shape[0])
-        ctx.save_for_backward(x, w1, w2, gamma, a, h, y)
+        ctx.save_for_backward(x, w1, w2, gamma, a, h, y, b1, b2)
         ctx.act = act
         ctx.has_res = residual is not None
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, w1, w2, gamma, a, h, y = ctx.saved_tensors
+        x, w1, w2, gamma, a, h, y, b1, b2 = ctx.saved_tensors
         w1_16, w2_16 = shadow(w1), shadow(w2)
         Fh, D = w1.shape
         Do = w2.shape[0]
         dout = dout.contiguous()
         dev = dout.device
         dgamma = None
-        db2 = torch.zeros(Do, dtype=torch.float32, device=dev)
+        db2_b, db2 = _grad_out(b2, (Do,), dev)
         if gamma is not None:
             dy = torch.empty(dout.shape, dtype=torch.bfloat16, device=dev)
-            dgamma = torch.zeros_like(gamma)
-            check(lib().spe_layerscale_bwd(ptr(dout), ptr(y), ptr(gamma), _rows(dout), Do, ptr(dy), ptr(dgamma), ptr(db2), stream()))
+            dgamma_b, dgamma = _grad_out(gamma, gamma.shape, dev)
+            check(lib().spe_layerscale_bwd(ptr(dout), ptr(y), ptr(gamma), _rows(dout), Do, ptr(dy), ptr(dgamma_b), ptr(db2_b), stream()))
         else:
             dy = to_bf16(dout)
-            colsum_bf16(dy.view(-1, Do), db2)
-        dw2 = torch.empty((Do, Fh), dtype=torch.float32, device=dev)
-        _linear_wgrad(dy, h, dw2)
+            colsum_bf16(dy.view(-1, Do), db2_b)
+        dw2 = _wgrad_into(w2, dy, h)
         da = torch.empty(h.shape, dtype=torch.bfloat16, device=dev)
         aux = a if ctx.act == "gelu" else h
         _linear_dgrad(dy, w2_16, da, act=_ACT_GRAD[ctx.act], aux_in=aux, ld_aux=Fh)
-        db1 = torch.zeros(Fh, dtype=torch.float32, device=dev)
-        colsum_bf16(da.view(-1, Fh), db1)
-        dw1 = torch.empty((Fh, D), dtype=torch.float32, device=dev)
-        _linear_wgrad(da, x, dw1)
+        db1_b, db1 = _grad_out(b1, (Fh,), dev)
+        colsum_bf16(da.view(-1, Fh), db1_b)
+        dw1 = _wgrad_into(w1, da, x)
         dx = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
         _linear_dgrad(da, w1_16, dx)
         return dx, dw1, db1, dw2, db2, (dout if ctx.has_res else None), dgamma, None
@@ -301,7 +333,7 @@ class LayerNormFn(torch.autograd.Function):
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
         check(lib().spe_layernorm_fwd(ptr(x), ptr(weight), ptr(bias), eps, rows, D, ptr(y16), ptr(y32), ptr(mean), ptr(rstd), stream()))
-        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.save_for_backward(x, weight, mean, rstd, bias)
         ctx.want_f32 = want_f32
         if want_f32:
             return y32, y16
@@ -309,7 +341,7 @@ class LayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        x, weight, mean, rstd = ctx.saved_tensors
+        x, weight, mean, rstd, bias = ctx.saved_tensors
         if ctx.want_f32:
             d32, d16 = grads
         else:
@@ -320,9 +352,9 @@ class LayerNormFn(torch.autograd.Function):
         d32 = d32.contiguous() if d32 is not None else None
         d16 = d16.contiguous() if d16 is not None else None
         dx = torch.empty_like(x)
-        dw = torch.zeros(D, dtype=torch.float32, device=x.device)
-        db = torch.zeros(D, dtype=torch.float32, device=x.device)
-        check(lib().spe_layernorm_bwd(ptr(d16), ptr(d32), 0, ptr(x), ptr(weight), ptr(mean), ptr(rstd), _rows(x), D, ptr(dx), ptr(dw), ptr(db),
+        dw_b, dw = _grad_out(weight, (D,), x.device)
+        db_b, db = _grad_out(bias, (D,), x.device)
+        check(lib().spe_layernorm_bwd(ptr(d16), ptr(d32), 0, ptr(x), ptr(weight), ptr(mean), ptr(rstd), _rows(x), D, ptr(dx), ptr(dw_b), ptr(db_b),
                                       stream()))
         return dx, dw, db, None, None
 
@@ -523,11 +555,13 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         dv = dqkv[:, :, 2 * D:]
         gemm(A, dO, dv, N, dh, N, a_major=MAJOR_MN, lda=ld, a_sb=(H * N * ld, N * ld), b_major=MAJOR_MN, ldb=dO.stride(1), b_sb=(dO.stride(0), dh),
              ldc=dv.stride(1), c_sb=(dv.stride(0), dh), batch=(B, H))
-        dWl, dbl, dWw, dbw = torch.zeros_like(Wl), torch.zeros_like(bl), torch.zeros_like(Ww), torch.zeros_like(bw)
+        dWl_b, dWl = _grad_out(Wl, Wl.shape, qkv.device)
+        dWw_b, dWw = _grad_out(Ww, Ww.shape, qkv.device)
+        junk = torch.zeros((2, H), dtype=torch.float32, device=qkv.device)      # the kernel's own bias sums (not used, see below)
         nws = lib().spe_talking_softmax_bwd_workspace(B, H, N, N)
         ws = torch.empty(nws, dtype=torch.float32, device=qkv.device)
-        check(lib().spe_talking_softmax_bwd(ptr(S), ptr(dA), ptr(dA), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, ptr(dWl), ptr(dbl),
-                                            ptr(dWw), ptr(dbw), ptr(ws), nws, stream()))
+        check(lib().spe_talking_softmax_bwd(ptr(S), ptr(dA), ptr(dA), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, ptr(dWl_b), ptr(junk[0]),
+                                            ptr(dWw_b), ptr(junk[1]), ptr(ws), nws, stream()))
         _dq_dk(dA, q, k, H, scale, N, N, ld, dq_out=dqkv[:, :, :D], dk_out=dqkv[:, :, D:2 * D])
         # exact bias gradients (the kernel's own sums of bf16 dA over B*N*N keys cancel catastrophically):
         #   dbw[o] = sum_{b,i,j} dA[b,o,i,j] = sum_b colsum_i(dO[b,:,o]) . colsum_j(V[b,:,o]);   dbl = 0 (softmax is shift invariant)
@@ -535,7 +569,7 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         check(lib().spe_colsum_bf16_batched(ptr(dO), B, N, D, dO.stride(1), dO.stride(0), ptr(cs[0]), stream()))
         check(lib().spe_colsum_bf16_batched(ptr(v), B, N, D, v.stride(1), v.stride(0), ptr(cs[1]), stream()))
         dbw = (cs[0] * cs[1]).view(B, H, dh).sum((0, 2))
-        dbl = torch.zeros_like(bl)
+        dbl = None if grad_sink(bl) is not None else torch.zeros_like(bl)
         return dqkv, dWl, dbl, dWw, dbw, None
 
 
@@ -574,10 +608,9 @@ class PatchEmbedFn(torch.autograd.Function):
         d16 = to_bf16(dout)
         db = torch.zeros(D, dtype=torch.float32, device=dout.device)
         colsum_bf16(d16.view(-1, D), db)
-        dw = torch.empty((D, Kc), dtype=torch.float32, device=dout.device)
-        _linear_wgrad(d16.view(-1, D), cols, dw)
+        dw = _wgrad_into(weight, d16.view(-1, D), cols)
         dpos = dout.sum(0) if B > 1 else dout[0]
-        return None, dw.view(weight.shape), db, dpos, None
+        return None, dw, db, dpos, None
 
 
 class BicubicTokensFn(torch.autograd.Function):

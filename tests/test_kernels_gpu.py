@@ -56,6 +56,27 @@ def test_gemm_majors_and_tails(K, a_major, b_major, M, N, K_):
     assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
 
 
+@pytest.mark.parametrize("M,N,K_,mn", [(384, 384, 2400, 1), (304, 200, 136, 1), (1536, 384, 12800, 1), (88, 384, 640, 1), (8, 384, 2400, 1),
+                                       (300, 130, 64, 0), (77, 81, 1600, 0), (4, 384, 2400, 0)])
+def test_gemm_accumulate_in_place(K, M, N, K_, mn):
+    """residual aliasing C = C += A B (wgrad into .grad): TMA reduce-add path, split-K path and the direct (unaligned pitch) path."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K_)
+    A = bf(torch.randn(M, K_, generator=g)).to(dev())
+    B = bf(torch.randn(N, K_, generator=g)).to(dev())
+    c0 = torch.randn(M, N, generator=g).to(dev())
+    prod = A.float() @ B.float().t()
+    out = c0.clone()
+    if mn:      # wgrad layout: A = dy [K_, M], B = x [K_, N], both MN-major
+        a_st, b_st, kw = A.t().contiguous(), B.t().contiguous(), dict(a_major=K.MAJOR_MN, lda=M, b_major=K.MAJOR_MN, ldb=N)
+    else:
+        a_st, b_st, kw = A, B, dict(lda=K_, ldb=K_)
+    for reps in (1, 2):
+        K.gemm(a_st, b_st, out, M, N, K_, ldc=N, residual=out, ldr=N, **kw)
+        torch.cuda.synchronize()
+        want = c0 + reps * prod
+        assert rel_err(out, want) < 3e-5, (reps, rel_err(out, want))
+
+
 def test_gemm_epilogue_features(K):
     g = torch.Generator().manual_seed(3)
     M, N, Kd = 300, 384, 192

@@ -147,3 +147,34 @@ def test_training_mode_criterion_and_refine_dict():
     idx = crit.matcher(out[0], crit._jitter_repeat(tg))
     for (i, j), t in zip(idx, targets):
         assert len(i) == min(cfg.num_queries, 5 * len(t["labels"]))
+
+
+def test_fused_grad_accumulation_matches_autograd():
+    """dp.FlatGradBuffer('views'): backward kernels accumulate straight into the flat buffer (ops.grad_sink) -- the gradients
+    must equal the ordinary autograd route, after one AND after two accumulated backward passes."""
+    from spe_b200 import factory
+    from spe_b200.dp import FlatGradBuffer
+    cfg = O.tiny_config()
+    params = O.make_params(cfg, 5)
+    images, targets = O.make_inputs(cfg, 2, 48, 64, seed=5)
+    dev = torch.device("cuda")
+    tg = [{k: v.to(dev) for k, v in t.items()} for t in targets]
+    crit = factory.build_criterion(cfg, device=dev).eval()
+    wd = crit.weight_dict
+
+    def run(fused, passes):
+        model = factory.build_detector(cfg, dev).train()
+        model.load_state_dict(params)
+        buf = FlatGradBuffer(model.parameters(), fused_accumulate=fused)
+        for _ in range(passes):
+            ld = crit(model(images.to(dev))[0], tg)
+            sum(ld[k] * wd[k] for k in ld if k in wd).backward()
+        return {n: p.grad.clone() for n, p in model.named_parameters()}, buf
+
+    for passes in (1, 2):
+        ref, _ = run(False, passes)
+        got, buf = run(True, passes)
+        assert float(buf.flat.abs().sum()) > 0
+        for n in ref:
+            scale = float(ref[n].abs().max()) + 1e-6
+            assert float((got[n] - ref[n]).abs().max()) <= 2e-3 * scale + 1e-6, (n, passes)
