@@ -368,12 +368,12 @@ __device__ __forceinline__ SRaw load_sraw(const float* __restrict__ Sb, long lon
 }
 // logits of one 32-key step in the accumulator layout: L2[i] = log2(e) * L[q4][base + 8 r4 + i]   (-inf beyond Nk)
 // also returns the hi parts of the split B-operand registers of S (reused by the dWl outer product)
-template <int H>
+template <int H, bool TAIL = true>
 __device__ __forceinline__ void step_logits(const SRaw& raw, int base, int Nk, const MixFrag& Wl, float bl2, int q4, int r4, float (&L2)[8],
                                             uint32_t (&shi)[4]) {
     const int cb = base + 4 * q4;
     const float a0[4] = {raw.s0.x, raw.s0.y, raw.s0.z, raw.s0.w}, a1[4] = {raw.s1.x, raw.s1.y, raw.s1.z, raw.s1.w};
-    const bool tail = base + 32 > Nk;               // warp-uniform: only the last step of a row has invalid keys
+    const bool tail = TAIL && base + 32 > Nk;       // warp-uniform: only the last step of a row has invalid keys
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const bool ok = !tail || cb + t < Nk;       // padding columns of S are never written: sanitise
@@ -616,14 +616,70 @@ __device__ __forceinline__ void rw_bulk_g2s(uint32_t dst, const void* src, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int H>
-__global__ void __launch_bounds__(256, 2) talking_fwd_rows_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
-                                                                  const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
-                                                                  float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
+// ---- per-step bodies (TAIL = false: all 32 keys of the step are valid, no masking code at all) ----
+// forward sweep A: mixed logits of one step -> online (max, sum); the logits are written back over S in shared memory
+// (accumulator layout: head q4, keys base + 8 r4 .. +7) so sweep B needs neither the split nor the mix again.
+template <int H, bool TAIL>
+__device__ __forceinline__ void tfwd_step_a(float* Sb, int ldS, int base, int Nk, const MixFrag& fWl, float bl2, int q4, int r4, float& m, float& z) {
+    float L2[8];
+    uint32_t shi[4];
+    step_logits<H, TAIL>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+    __syncwarp();                                                    // every lane's reads of this step's S precede the overwrite
+    const int c8 = base + 8 * r4;
+    if (q4 < H && c8 + 8 <= ldS) {
+        float4* d = reinterpret_cast<float4*>(Sb + q4 * ldS + c8);
+        d[0] = make_float4(L2[0], L2[1], L2[2], L2[3]);
+        d[1] = make_float4(L2[4], L2[5], L2[6], L2[7]);
+    }
+    float mx = fmaxf(fmaxf(fmaxf(L2[0], L2[1]), fmaxf(L2[2], L2[3])), fmaxf(fmaxf(L2[4], L2[5]), fmaxf(L2[6], L2[7])));
+    const float mn = fmaxf(m, mx);
+    if (!TAIL || mn > -INFINITY) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += fast_ex2(L2[i] - mn);
+        z = z * fast_ex2(m - mn) + acc;
+        m = mn;
+    }
+}
+// forward sweep B: P = 2^(L2 - c2) from the cached logits -> second mix -> bf16
+template <int H, bool TAIL>
+__device__ __forceinline__ void tfwd_step_b(const float* Sb, int ldS, int base, int Nk, const MixFrag& fWw, float bwv, float c2, uint16_t* Ab, long long hA,
+                                            int ldA, int q4, int r4) {
+    const int c8 = base + 8 * r4;
+    float p[8], out[8];
+    if (q4 < H && c8 + 8 <= ldS) {
+        const float4 u = *reinterpret_cast<const float4*>(Sb + q4 * ldS + c8), w = *reinterpret_cast<const float4*>(Sb + q4 * ldS + c8 + 4);
+        p[0] = fast_ex2(u.x - c2); p[1] = fast_ex2(u.y - c2); p[2] = fast_ex2(u.z - c2); p[3] = fast_ex2(u.w - c2);
+        p[4] = fast_ex2(w.x - c2); p[5] = fast_ex2(w.y - c2); p[6] = fast_ex2(w.z - c2); p[7] = fast_ex2(w.w - c2);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        uint32_t hi, lo;
+        split2(p[t], p[4 + t], hi, lo);
+        mix_tile(fWw, movm_trans(hi), movm_trans(lo), bwv, out[t], out[4 + t]);
+    }
+    if (q4 < H && c8 + 8 <= ldA) {
+        if (TAIL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) out[i] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(Ab + q4 * hA + c8) =
+            make_uint4(pack_bf16x2(out[0], out[1]), pack_bf16x2(out[2], out[3]), pack_bf16x2(out[4], out[5]), pack_bf16x2(out[6], out[7]));
+    }
+}
+
+// NW warps share one row; the steps of a row are dealt out evenly (NW = 10 fits the 50 steps of N = 1600 exactly).
+template <int H, int NW>
+__global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
+                                                                      const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
+                                                                      float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
     extern __shared__ __align__(128) uint8_t rsm[];
     float* Sbuf = reinterpret_cast<float*>(rsm);                       // [2][H][ldS]
     __shared__ __align__(8) uint64_t bars[2];
-    __shared__ float red[8][8][2];
+    __shared__ float red[NW][8][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q4 = lane >> 2, r4 = lane & 3;
     const MixFrag fWl = load_mix_frag<H>(Wl, false, LOG2E, q4, r4), fWw = load_mix_frag<H>(Ww, false, 1.f, q4, r4);
     const float bl2 = q4 < H ? bl[q4] * LOG2E : 0.f, bwv = q4 < H ? bw[q4] : 0.f;
@@ -638,41 +694,30 @@ __global__ void __launch_bounds__(256, 2) talking_fwd_rows_kernel(const float* _
     auto issue = [&](int row, int buf) {                                 // thread 0 only
         const int b = row / Nq, q = row % Nq;
         const uint32_t bar = bar0 + 8 * buf;
+        // the generic-proxy writes (cached logits) of the row that used this buffer before are ordered before the async-proxy refill
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         rw_mbar_expect_tx(bar, (uint32_t)(H * ldS * 4));
         for (int h = 0; h < H; ++h)
             rw_bulk_g2s(rw_smem_u32(Sbuf + ((size_t)buf * H + h) * ldS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar);
     };
-    const int nsteps = (Nk + 31) / 32, nsteps_o = (ldA + 31) / 32;
-    const int spw = (nsteps + 7) / 8, spwo = (nsteps_o + 7) / 8;
-    const int s0 = min(warp * spw, nsteps), s1 = min(s0 + spw, nsteps);
-    const int o0 = min(warp * spwo, nsteps_o), o1 = min(o0 + spwo, nsteps_o);
+    const int nst = (ldA + 31) / 32;                                   // steps of 32 keys; both sweeps use the same deal
+    const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;
     if (tid == 0 && blockIdx.x < rows_total) issue(blockIdx.x, 0);
     int it = 0;
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
         const int buf = it & 1;
+        // buffer buf^1 was last touched in the previous iteration, which ended with __syncthreads
         if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x, buf ^ 1);
         rw_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
-        const float* Sb = Sbuf + (size_t)buf * H * ldS;
+        float* Sb = Sbuf + (size_t)buf * H * ldS;
         const int b = row / Nq, q = row % Nq;
         uint16_t* Ab = A + ((long long)b * H * Nq + q) * ldA;
-        // ---- sweep A (this warp's key segment): online (max, sum) of the mixed logits
+        // ---- sweep A (this warp's steps): mixed logits -> smem, online (max, sum)
         float m = -INFINITY, z = 0.f;
         for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            float L2[8];
-            uint32_t shi[4];
-            step_logits<H>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
-            float mx = L2[0];
-#pragma unroll
-            for (int i = 1; i < 8; ++i) mx = fmaxf(mx, L2[i]);
-            const float mn = fmaxf(m, mx);
-            if (mn > -INFINITY) {
-                float acc = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc += fast_ex2(L2[i] - mn);
-                z = z * fast_ex2(m - mn) + acc;
-                m = mn;
-            }
+            if (base + 32 <= Nk) tfwd_step_a<H, false>(Sb, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
+            else tfwd_step_a<H, true>(Sb, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
         }
         {
             float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
@@ -685,50 +730,122 @@ __global__ void __launch_bounds__(256, 2) talking_fwd_rows_kernel(const float* _
         __syncthreads();
         float m2 = -INFINITY, zt = 0.f;
 #pragma unroll
-        for (int w2 = 0; w2 < 8; ++w2) m2 = fmaxf(m2, red[w2][q4][0]);
+        for (int w2 = 0; w2 < NW; ++w2) m2 = fmaxf(m2, red[w2][q4][0]);
 #pragma unroll
-        for (int w2 = 0; w2 < 8; ++w2) { const float mw = red[w2][q4][0]; zt += (mw == -INFINITY) ? 0.f : red[w2][q4][1] * fast_ex2(mw - m2); }
+        for (int w2 = 0; w2 < NW; ++w2) { const float mw = red[w2][q4][0]; zt += (mw == -INFINITY) ? 0.f : red[w2][q4][1] * fast_ex2(mw - m2); }
         const float c2 = m2 + log2f(zt);                                // p = 2^(L2 - m2) / zt = 2^(L2 - c2)
         if (stats && warp == 0 && r4 == 0 && q4 < H) stats[(long long)row * H + q4] = c2;
         // ---- sweep B: P -> second mix -> bf16
-        for (int st = o0; st < o1; ++st) {
+        for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            float L2[8], out[8], p[8];
-            uint32_t shi[4];
-            step_logits<H>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) p[i] = fast_ex2(L2[i] - c2);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                uint32_t hi, lo;
-                split2(p[t], p[4 + t], hi, lo);
-                mix_tile(fWw, movm_trans(hi), movm_trans(lo), bwv, out[t], out[4 + t]);
-            }
-            const int c8 = base + 8 * r4;
-            if (q4 < H && c8 + 8 <= ldA) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) out[i] = 0.f;
-                *reinterpret_cast<uint4*>(Ab + q4 * hA + c8) =
-                    make_uint4(pack_bf16x2(out[0], out[1]), pack_bf16x2(out[2], out[3]), pack_bf16x2(out[4], out[5]), pack_bf16x2(out[6], out[7]));
-            }
+            if (base + 32 <= Nk) tfwd_step_b<H, false>(Sb, ldS, base, Nk, fWw, bwv, c2, Ab, hA, ldA, q4, r4);
+            else tfwd_step_b<H, true>(Sb, ldS, base, Nk, fWw, bwv, c2, Ab, hA, ldA, q4, r4);
         }
         __syncthreads();                                               // row buffer and `red` are free again
     }
 }
 
-template <int H>
-__global__ void __launch_bounds__(256, 2) talking_bwd_rows_kernel(const float* __restrict__ S, const uint16_t* dA, uint16_t* dS, const float* __restrict__ Wl,
-                                                                  const float* __restrict__ bl, const float* __restrict__ Ww,
-                                                                  const float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA,
-                                                                  float* __restrict__ part) {
+// ---- backward step bodies.  Sweep B leaves everything sweep C needs in shared memory, in place:
+//   dP (fp32, accumulator layout)       over the step's S values            (same H x 32 footprint),
+//   P  (bf16, the lane's 8 keys)        over the lane's own 16-byte dA slot,
+//   S_hi (bf16, B-operand layout)       in the lane-private side buffer X   (16 bytes per lane and step).
+template <int H, bool TAIL>
+__device__ __forceinline__ void tbwd_step_b(float* Sb, uint16_t* Db, uint4* Xst, int ldS, int ldA, int base, int Nk, const MixFrag& fWl, const MixFrag& fWwT,
+                                            float bl2, float c2, int q4, int r4, int lane, float& rho, float (&accWw)[4]) {
+    float L2[8], d[8], dP[8], p[8];
+    uint32_t shi[4], dpk[4], ppk[4];
+    step_logits<H, TAIL>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+    const int c8 = base + 8 * r4;
+    const bool slot = q4 < H && c8 + 8 <= ldA;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (slot) v = *reinterpret_cast<const uint4*>(Db + q4 * ldA + c8);
+    {
+        float2 t;
+        t = unpack_bf16x2(v.x); d[0] = t.x; d[1] = t.y;
+        t = unpack_bf16x2(v.y); d[2] = t.x; d[3] = t.y;
+        t = unpack_bf16x2(v.z); d[4] = t.x; d[5] = t.y;
+        t = unpack_bf16x2(v.w); d[6] = t.x; d[7] = t.y;
+    }
+    if (TAIL) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) d[i] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        p[t] = fast_ex2(L2[t] - c2); p[4 + t] = fast_ex2(L2[4 + t] - c2);
+        dpk[t] = pack_bf16x2(d[t], d[4 + t]);
+        ppk[t] = pack_bf16x2(p[t], p[4 + t]);
+        mix_tile(fWwT, movm_trans(dpk[t]), 0u, 0.f, dP[t], dP[4 + t]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rho += p[i] * dP[i];
+    mma16816(accWw, dpk[0], 0u, dpk[1], 0u, ppk[0], ppk[1]);
+    mma16816(accWw, dpk[2], 0u, dpk[3], 0u, ppk[2], ppk[3]);
+    __syncwarp();                                                    // all lanes have consumed this step's S before it is overwritten
+    if (slot) {
+        *reinterpret_cast<uint4*>(Db + q4 * ldA + c8) = make_uint4(ppk[0], ppk[1], ppk[2], ppk[3]);
+        if (c8 + 8 <= ldS) {
+            float4* dst = reinterpret_cast<float4*>(Sb + q4 * ldS + c8);
+            dst[0] = make_float4(dP[0], dP[1], dP[2], dP[3]);
+            dst[1] = make_float4(dP[4], dP[5], dP[6], dP[7]);
+        }
+    }
+    Xst[lane] = make_uint4(shi[0], shi[1], shi[2], shi[3]);
+}
+template <int H, bool TAIL>
+__device__ __forceinline__ void tbwd_step_c(const float* Sb, const uint16_t* Db, const uint4* Xst, int ldS, int ldA, int base, int Nk, const MixFrag& fWlT,
+                                            float rho, uint16_t* dSb, long long hA, int q4, int r4, int lane, float (&accWl)[4]) {
+    const int c8 = base + 8 * r4;
+    const bool slot = q4 < H && c8 + 8 <= ldA && c8 + 8 <= ldS;
+    float l[8], o[8];
+    uint32_t lpk[4];
+    if (slot) {
+        const uint4 pp = *reinterpret_cast<const uint4*>(Db + q4 * ldA + c8);
+        const float4 u = *reinterpret_cast<const float4*>(Sb + q4 * ldS + c8), w = *reinterpret_cast<const float4*>(Sb + q4 * ldS + c8 + 4);
+        const float2 p0 = unpack_bf16x2(pp.x), p1 = unpack_bf16x2(pp.y), p2 = unpack_bf16x2(pp.z), p3 = unpack_bf16x2(pp.w);   // (p[t], p[4+t])
+        l[0] = p0.x * (u.x - rho); l[4] = p0.y * (w.x - rho);
+        l[1] = p1.x * (u.y - rho); l[5] = p1.y * (w.y - rho);
+        l[2] = p2.x * (u.z - rho); l[6] = p2.y * (w.z - rho);
+        l[3] = p3.x * (u.w - rho); l[7] = p3.y * (w.w - rho);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) l[i] = 0.f;
+    }
+    const uint4 sx = Xst[lane];
+    const uint32_t shi[4] = {sx.x, sx.y, sx.z, sx.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        lpk[t] = pack_bf16x2(l[t], l[4 + t]);
+        mix_tile(fWlT, movm_trans(lpk[t]), 0u, 0.f, o[t], o[4 + t]);
+    }
+    if (!TAIL || base < Nk) {
+        mma16816(accWl, lpk[0], 0u, lpk[1], 0u, movm_trans(shi[0]), movm_trans(shi[1]));
+        mma16816(accWl, lpk[2], 0u, lpk[3], 0u, movm_trans(shi[2]), movm_trans(shi[3]));
+    }
+    if (q4 < H && c8 + 8 <= ldA) {
+        if (TAIL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) o[i] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(dSb + q4 * hA + c8) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+}
+
+template <int H, int NW>
+__global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const float* __restrict__ S, const uint16_t* dA, uint16_t* dS, const float* __restrict__ Wl,
+                                                                      const float* __restrict__ bl, const float* __restrict__ Ww,
+                                                                      const float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA,
+                                                                      float* __restrict__ part) {
     extern __shared__ __align__(128) uint8_t rsm[];
-    // single row buffer per CTA; TWO CTAs share an SM, so one CTA's row load overlaps the other's math (16 warps / SM)
-    float* Sbuf = reinterpret_cast<float*>(rsm);                                            // [H][ldS]
-    uint16_t* Dbuf = reinterpret_cast<uint16_t*>(rsm + (size_t)H * ldS * 4);                // [H][ldA]
+    // single row buffer per CTA; TWO CTAs share an SM, so one CTA's row load overlaps the other's math
+    float* Sbuf = reinterpret_cast<float*>(rsm);                                            // [H][ldS]   S, then dP
+    uint16_t* Dbuf = reinterpret_cast<uint16_t*>(rsm + (size_t)H * ldS * 4);                // [H][ldA]   dA, then P
+    uint4* Xbuf = reinterpret_cast<uint4*>(rsm + (size_t)H * ldS * 4 + (size_t)H * ldA * 2);  // [steps][32]  S_hi fragments
     constexpr int NP = 2 * H * H + 2 * H;
     __shared__ __align__(8) uint64_t bars[2];
-    __shared__ float red[8][8];
-    __shared__ float redbuf[8][NP];
+    __shared__ float red[NW][8];
+    __shared__ float redbuf[NW][NP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q4 = lane >> 2, r4 = lane & 3;
     const MixFrag fWl = load_mix_frag<H>(Wl, false, LOG2E, q4, r4);
     const MixFrag fWwT = load_mix_frag<H>(Ww, true, 1.f, q4, r4);
@@ -744,60 +861,30 @@ __global__ void __launch_bounds__(256, 2) talking_bwd_rows_kernel(const float* _
     __syncthreads();
     auto issue = [&](int row) {
         const int b = row / Nq, q = row % Nq;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of the previous row before the async refill
         rw_mbar_expect_tx(bar0, (uint32_t)(H * ldS * 4 + H * ldA * 2));
         for (int h = 0; h < H; ++h) {
             rw_bulk_g2s(rw_smem_u32(Sbuf + (size_t)h * ldS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar0);
             rw_bulk_g2s(rw_smem_u32(Dbuf + (size_t)h * ldA), dA + ((long long)b * H * Nq + q) * ldA + h * hA, (uint32_t)(ldA * 2), bar0);
         }
     };
-    const int nsteps = (Nk + 31) / 32, nsteps_o = (ldA + 31) / 32;
-    const int spw = (nsteps + 7) / 8, spwo = (nsteps_o + 7) / 8;
-    const int s0 = min(warp * spw, nsteps), s1 = min(s0 + spw, nsteps);
-    const int o0 = min(warp * spwo, nsteps_o), o1 = min(o0 + spwo, nsteps_o);
+    const int nst = (ldA + 31) / 32;
+    const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;
 
     float accWw[4] = {0.f, 0.f, 0.f, 0.f}, accWl[4] = {0.f, 0.f, 0.f, 0.f};
-    float abl = 0.f;
-    auto get_dA = [&](const uint16_t* Db, int base, float (&d)[8]) {
-        const int c8 = base + 8 * r4;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (q4 < H && c8 + 8 <= ldA) v = *reinterpret_cast<const uint4*>(Db + q4 * ldA + c8);
-        float2 t;
-        t = unpack_bf16x2(v.x); d[0] = t.x; d[1] = t.y;
-        t = unpack_bf16x2(v.y); d[2] = t.x; d[3] = t.y;
-        t = unpack_bf16x2(v.z); d[4] = t.x; d[5] = t.y;
-        t = unpack_bf16x2(v.w); d[6] = t.x; d[7] = t.y;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) d[i] = 0.f;
-    };
-
     if (tid == 0 && blockIdx.x < rows_total) issue(blockIdx.x);
     int it = 0;
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
         const float c2 = q4 < H ? stats[(long long)row * H + q4] : 0.f;
         rw_mbar_wait(bar0, (uint32_t)it & 1u);
-        const float* Sb = Sbuf;
-        const uint16_t* Db = Dbuf;
         const int b = row / Nq, q = row % Nq;
         uint16_t* dSb = dS + ((long long)b * H * Nq + q) * ldA;
-        // ---- sweep B: rho = sum_j P dP;  dWw += dA (x) P
+        // ---- sweep B: rho = sum_j P dP;  dWw += dA (x) P;  leaves dP / P / S_hi in shared memory
         float rho = 0.f;
         for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            float L2[8], d[8], dP[8], p[8];
-            uint32_t shi[4], dpk[4], ppk[4];
-            step_logits<H>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
-            get_dA(Db, base, d);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                p[t] = fast_ex2(L2[t] - c2); p[4 + t] = fast_ex2(L2[4 + t] - c2);
-                dpk[t] = pack_bf16x2(d[t], d[4 + t]);
-                ppk[t] = pack_bf16x2(p[t], p[4 + t]);
-                mix_tile(fWwT, movm_trans(dpk[t]), 0u, 0.f, dP[t], dP[4 + t]);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rho += p[i] * dP[i];
-            mma16816(accWw, dpk[0], 0u, dpk[1], 0u, ppk[0], ppk[1]);
-            mma16816(accWw, dpk[2], 0u, dpk[3], 0u, ppk[2], ppk[3]);
+            if (base + 32 <= Nk) tbwd_step_b<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, lane, rho, accWw);
+            else tbwd_step_b<H, true>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, lane, rho, accWw);
         }
         rho += __shfl_xor_sync(0xffffffffu, rho, 1);
         rho += __shfl_xor_sync(0xffffffffu, rho, 2);
@@ -805,64 +892,42 @@ __global__ void __launch_bounds__(256, 2) talking_bwd_rows_kernel(const float* _
         __syncthreads();
         rho = 0.f;
 #pragma unroll
-        for (int w2 = 0; w2 < 8; ++w2) rho += red[w2][q4];
-        // ---- sweep C: dL = P (dP - rho);  dS = Wl^T dL;  dWl += dL (x) S;  dbl += dL
-        for (int st = o0; st < o1; ++st) {
+        for (int w2 = 0; w2 < NW; ++w2) rho += red[w2][q4];
+        // ---- sweep C: dL = P (dP - rho);  dS = Wl^T dL;  dWl += dL (x) S     (dbl = sum dL is identically 0: not accumulated)
+        for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            float L2[8], d[8], dP[8], l[8], o[8];
-            uint32_t shi[4], lpk[4], spk[4];
-            step_logits<H>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
-            get_dA(Db, base, d);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) mix_tile(fWwT, movm_trans(pack_bf16x2(d[t], d[4 + t])), 0u, 0.f, dP[t], dP[4 + t]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { l[i] = fast_ex2(L2[i] - c2) * (dP[i] - rho); abl += l[i]; }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                lpk[t] = pack_bf16x2(l[t], l[4 + t]);
-                spk[t] = movm_trans(shi[t]);
-                mix_tile(fWlT, movm_trans(lpk[t]), 0u, 0.f, o[t], o[4 + t]);
-            }
-            if (base < Nk) {
-                mma16816(accWl, lpk[0], 0u, lpk[1], 0u, spk[0], spk[1]);
-                mma16816(accWl, lpk[2], 0u, lpk[3], 0u, spk[2], spk[3]);
-            }
-            const int c8 = base + 8 * r4;
-            if (q4 < H && c8 + 8 <= ldA) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) o[i] = 0.f;
-                *reinterpret_cast<uint4*>(dSb + q4 * hA + c8) =
-                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-            }
+            if (base + 32 <= Nk) tbwd_step_c<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, lane, accWl);
+            else tbwd_step_c<H, true>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, lane, accWl);
         }
         __syncthreads();                                               // every warp is done with the row buffer
         if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x);
     }
-    // CTA reduction of the partials -> part[blockIdx.x][...]: layout dWl[H*H], dbl[H], dWw[H*H], dbw[H] (dbw: see ops.py, exact formula)
+    // CTA reduction of the partials -> part[blockIdx.x][...]: layout dWl[H*H], dbl[H] (= 0), dWw[H*H], dbw[H] (= 0: see ops.py, exact formula)
     for (int i = lane; i < NP; i += 32) redbuf[warp][i] = 0.f;
     __syncwarp();
-    abl += __shfl_xor_sync(0xffffffffu, abl, 1); abl += __shfl_xor_sync(0xffffffffu, abl, 2);
     if (q4 < H) {
         const int col = 2 * r4;
         if (col < H) { redbuf[warp][q4 * H + col] = accWl[0]; redbuf[warp][H * H + H + q4 * H + col] = accWw[0]; }
         if (col + 1 < H) { redbuf[warp][q4 * H + col + 1] = accWl[1]; redbuf[warp][H * H + H + q4 * H + col + 1] = accWw[1]; }
-        if (r4 == 0) redbuf[warp][H * H + q4] = abl;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NP; i += 256) {
+    for (int i = threadIdx.x; i < NP; i += NW * 32) {
         float sum = 0.f;
-        for (int w2 = 0; w2 < 8; ++w2) sum += redbuf[w2][i];
+        for (int w2 = 0; w2 < NW; ++w2) sum += redbuf[w2][i];
         part[(long long)blockIdx.x * NP + i] = sum;
     }
 }
 
-__global__ void talking_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int H, float* __restrict__ dWl, float* __restrict__ dbl,
-                                            float* __restrict__ dWw, float* __restrict__ dbw) {
+// one warp per output element: lanes stride over the per-CTA partials
+__global__ void __launch_bounds__(256) talking_bwd_finalize_kernel(const float* __restrict__ part, int nblocks, int H, float* __restrict__ dWl,
+                                                                   float* __restrict__ dbl, float* __restrict__ dWw, float* __restrict__ dbw) {
     const int NP = 2 * H * H + 2 * H;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= NP) return;
     float s = 0.f;
-    for (int k = 0; k < nblocks; ++k) s += part[(long long)k * NP + i];
+    for (int k = lane; k < nblocks; k += 32) s += part[(long long)k * NP + i];
+    s = warp_sum(s);
+    if (lane != 0) return;
     if (i < H * H) dWl[i] += s;
     else if (i < H * H + H) dbl[i - H * H] += s;
     else if (i < 2 * H * H + H) dWw[i - H * H - H] += s;
@@ -1167,6 +1232,15 @@ extern "C" __attribute__((visibility("default"))) int spe_softmax_bwd(const void
     return 0;
 }
 
+// warps per row-staged CTA: 8 or 10, whichever deals the 32-key steps of a row out more evenly (ties: 8)
+static int talking_warps(int ld) {
+    const int nst = (ld + 31) / 32;
+    const int w8 = (nst + 7) / 8 * 8 - nst, w10 = (nst + 9) / 10 * 10 - nst;
+    const char* e = getenv("SPE_TALKING_WARPS");
+    if (e) return atoi(e) == 10 ? 10 : 8;
+    return (w10 * 8 < w8 * 10 && nst >= 10) ? 10 : 8;
+}
+
 static int talking_grid(int B, int Nq, int per_sm) {
     const long long blocks = ((long long)B * Nq + 7) / 8;
     const long long cap = (long long)spe_num_sms() * per_sm;
@@ -1180,10 +1254,17 @@ static int talking_fwd_launch(const float* S, void* A, const float* Wl, const fl
     const size_t smem = (size_t)2 * H * ldS * 4;
     if (stats && smem <= 100 * 1024 + 4096 && getenv("SPE_TALKING_WARP_ROWS") == nullptr) {
         static bool done = false;
-        if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); done = true; }
+        if (!done) {
+            SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            done = true;
+        }
         const long long rows = (long long)B * Nq;
         const int grid = (int)(rows < 2LL * spe_num_sms() ? rows : 2LL * spe_num_sms());
-        talking_fwd_rows_kernel<H><<<grid, 256, smem, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
+        if (talking_warps((int)ldA) == 10)
+            talking_fwd_rows_kernel<H, 10><<<grid, 320, smem, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
+        else
+            talking_fwd_rows_kernel<H, 8><<<grid, 256, smem, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
     } else {
         talking_fwd_kernel<H><<<talking_grid(B, Nq, 4), 256, 0, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, ldS, ldA);
     }
@@ -1220,16 +1301,24 @@ static int talking_bwd_rows_grid(int B, int Nq) {
 template <int H>
 static int talking_bwd_launch(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B,
                               int Nq, int Nk, int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* ws, cudaStream_t st) {
-    const size_t smem = (size_t)H * (ldS * 4 + ldA * 2);
-    const bool rows_ok = stats && smem <= 100 * 1024 && getenv("SPE_TALKING_WARP_ROWS") == nullptr;
+    const size_t smem = (size_t)H * (ldS * 4 + ldA * 2) + (size_t)((ldA + 31) / 32) * 512;
+    const bool rows_ok = stats && smem <= 104 * 1024 && getenv("SPE_TALKING_WARP_ROWS") == nullptr;
     const int grid = rows_ok ? talking_bwd_rows_grid(B, Nq) : talking_bwd_grid(B, Nq);
     {
         SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * 8.0, st);   // S f32 read + dA bf16 read + dS bf16 write
         if (rows_ok) {
             static bool done = false;
-            if (!done) { SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); done = true; }
-            talking_bwd_rows_kernel<H><<<grid, 256, smem, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, stats,
-                                                                 B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
+            if (!done) {
+                SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
+                SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
+                done = true;
+            }
+            if (talking_warps((int)ldA) == 10)
+                talking_bwd_rows_kernel<H, 10><<<grid, 320, smem, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww,
+                                                                          stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
+            else
+                talking_bwd_rows_kernel<H, 8><<<grid, 256, smem, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww,
+                                                                         stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
         } else {
             talking_bwd_kernel<H><<<grid, 256, 0, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, B * Nq, Nq, Nk,
                                                         ldS, ldA, ws);
@@ -1237,7 +1326,7 @@ static int talking_bwd_launch(const float* S, const void* dA, void* dS, const fl
         SPE_LAUNCHED();
     }
     const int NP = 2 * H * H + 2 * H;
-    talking_bwd_finalize_kernel<<<(NP + 127) / 128, 128, 0, st>>>(ws, grid, H, dWl, dbl, dWw, dbw);
+    talking_bwd_finalize_kernel<<<(NP + 7) / 8, 256, 0, st>>>(ws, grid, H, dWl, dbl, dWw, dbw);
     SPE_LAUNCHED();
     return 0;
 }
