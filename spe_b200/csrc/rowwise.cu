@@ -616,18 +616,24 @@ __device__ __forceinline__ void rw_bulk_g2s(uint32_t dst, const void* src, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// shared-memory row pitches of the row-staged kernels.  fp32 rows: pitch = 4 (mod 16) words, so the four heads a quarter-warp touches
+// in the B-operand layout (rows 2 r4) and the two heads it touches in the accumulator layout fall into disjoint bank groups
+// (N = 1600 unpadded put every head on the same banks: 56% of the shared wavefronts were conflicts).  bf16 rows: pitch = 32 (mod 64).
+__host__ __device__ __forceinline__ int talking_pitch_f32(int ld) { return ld + ((20 - ld % 16) % 16); }
+__host__ __device__ __forceinline__ int talking_pitch_bf16(int ld) { return ld + ((96 - ld % 64) % 64); }
+
 // ---- per-step bodies (TAIL = false: all 32 keys of the step are valid, no masking code at all) ----
 // forward sweep A: mixed logits of one step -> online (max, sum); the logits are written back over S in shared memory
 // (accumulator layout: head q4, keys base + 8 r4 .. +7) so sweep B needs neither the split nor the mix again.
 template <int H, bool TAIL>
-__device__ __forceinline__ void tfwd_step_a(float* Sb, int ldS, int base, int Nk, const MixFrag& fWl, float bl2, int q4, int r4, float& m, float& z) {
+__device__ __forceinline__ void tfwd_step_a(float* Sb, int pS, int ldS, int base, int Nk, const MixFrag& fWl, float bl2, int q4, int r4, float& m, float& z) {
     float L2[8];
     uint32_t shi[4];
-    step_logits<H, TAIL>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+    step_logits<H, TAIL>(load_sraw<H>(Sb, pS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
     __syncwarp();                                                    // every lane's reads of this step's S precede the overwrite
     const int c8 = base + 8 * r4;
     if (q4 < H && c8 + 8 <= ldS) {
-        float4* d = reinterpret_cast<float4*>(Sb + q4 * ldS + c8);
+        float4* d = reinterpret_cast<float4*>(Sb + q4 * pS + c8);
         d[0] = make_float4(L2[0], L2[1], L2[2], L2[3]);
         d[1] = make_float4(L2[4], L2[5], L2[6], L2[7]);
     }
@@ -643,12 +649,12 @@ __device__ __forceinline__ void tfwd_step_a(float* Sb, int ldS, int base, int Nk
 }
 // forward sweep B: P = 2^(L2 - c2) from the cached logits -> second mix -> bf16
 template <int H, bool TAIL>
-__device__ __forceinline__ void tfwd_step_b(const float* Sb, int ldS, int base, int Nk, const MixFrag& fWw, float bwv, float c2, uint16_t* Ab, long long hA,
+__device__ __forceinline__ void tfwd_step_b(const float* Sb, int pS, int ldS, int base, int Nk, const MixFrag& fWw, float bwv, float c2, uint16_t* Ab, long long hA,
                                             int ldA, int q4, int r4) {
     const int c8 = base + 8 * r4;
     float p[8], out[8];
     if (q4 < H && c8 + 8 <= ldS) {
-        const float4 u = *reinterpret_cast<const float4*>(Sb + q4 * ldS + c8), w = *reinterpret_cast<const float4*>(Sb + q4 * ldS + c8 + 4);
+        const float4 u = *reinterpret_cast<const float4*>(Sb + q4 * pS + c8), w = *reinterpret_cast<const float4*>(Sb + q4 * pS + c8 + 4);
         p[0] = fast_ex2(u.x - c2); p[1] = fast_ex2(u.y - c2); p[2] = fast_ex2(u.z - c2); p[3] = fast_ex2(u.w - c2);
         p[4] = fast_ex2(w.x - c2); p[5] = fast_ex2(w.y - c2); p[6] = fast_ex2(w.z - c2); p[7] = fast_ex2(w.w - c2);
     } else {
@@ -677,7 +683,8 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const floa
                                                                       const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
                                                                       float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
     extern __shared__ __align__(128) uint8_t rsm[];
-    float* Sbuf = reinterpret_cast<float*>(rsm);                       // [2][H][ldS]
+    float* Sbuf = reinterpret_cast<float*>(rsm);                       // [2][H][pS]
+    const int pS = talking_pitch_f32(ldS);                             // padded row pitch: conflict-free in both fragment layouts
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ float red[NW][8][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q4 = lane >> 2, r4 = lane & 3;
@@ -698,7 +705,7 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const floa
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         rw_mbar_expect_tx(bar, (uint32_t)(H * ldS * 4));
         for (int h = 0; h < H; ++h)
-            rw_bulk_g2s(rw_smem_u32(Sbuf + ((size_t)buf * H + h) * ldS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar);
+            rw_bulk_g2s(rw_smem_u32(Sbuf + ((size_t)buf * H + h) * pS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar);
     };
     const int nst = (ldA + 31) / 32;                                   // steps of 32 keys; both sweeps use the same deal
     const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;
@@ -709,15 +716,15 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const floa
         // buffer buf^1 was last touched in the previous iteration, which ended with __syncthreads
         if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x, buf ^ 1);
         rw_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
-        float* Sb = Sbuf + (size_t)buf * H * ldS;
+        float* Sb = Sbuf + (size_t)buf * H * pS;
         const int b = row / Nq, q = row % Nq;
         uint16_t* Ab = A + ((long long)b * H * Nq + q) * ldA;
         // ---- sweep A (this warp's steps): mixed logits -> smem, online (max, sum)
         float m = -INFINITY, z = 0.f;
         for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            if (base + 32 <= Nk) tfwd_step_a<H, false>(Sb, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
-            else tfwd_step_a<H, true>(Sb, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
+            if (base + 32 <= Nk) tfwd_step_a<H, false>(Sb, pS, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
+            else tfwd_step_a<H, true>(Sb, pS, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
         }
         {
             float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
@@ -738,8 +745,8 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const floa
         // ---- sweep B: P -> second mix -> bf16
         for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            if (base + 32 <= Nk) tfwd_step_b<H, false>(Sb, ldS, base, Nk, fWw, bwv, c2, Ab, hA, ldA, q4, r4);
-            else tfwd_step_b<H, true>(Sb, ldS, base, Nk, fWw, bwv, c2, Ab, hA, ldA, q4, r4);
+            if (base + 32 <= Nk) tfwd_step_b<H, false>(Sb, pS, ldS, base, Nk, fWw, bwv, c2, Ab, hA, ldA, q4, r4);
+            else tfwd_step_b<H, true>(Sb, pS, ldS, base, Nk, fWw, bwv, c2, Ab, hA, ldA, q4, r4);
         }
         __syncthreads();                                               // row buffer and `red` are free again
     }
@@ -750,15 +757,15 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const floa
 //   P  (bf16, the lane's 8 keys)        over the lane's own 16-byte dA slot,
 //   S_hi (bf16, B-operand layout)       in the lane-private side buffer X   (16 bytes per lane and step).
 template <int H, bool TAIL>
-__device__ __forceinline__ void tbwd_step_b(float* Sb, uint16_t* Db, uint4* Xst, int ldS, int ldA, int base, int Nk, const MixFrag& fWl, const MixFrag& fWwT,
+__device__ __forceinline__ void tbwd_step_b(float* Sb, uint16_t* Db, uint4* Xst, int pS, int pA, int ldS, int ldA, int base, int Nk, const MixFrag& fWl, const MixFrag& fWwT,
                                             float bl2, float c2, int q4, int r4, int lane, float& rho, float (&accWw)[4]) {
     float L2[8], d[8], dP[8], p[8];
     uint32_t shi[4], dpk[4], ppk[4];
-    step_logits<H, TAIL>(load_sraw<H>(Sb, ldS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+    step_logits<H, TAIL>(load_sraw<H>(Sb, pS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
     const int c8 = base + 8 * r4;
     const bool slot = q4 < H && c8 + 8 <= ldA;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (slot) v = *reinterpret_cast<const uint4*>(Db + q4 * ldA + c8);
+    if (slot) v = *reinterpret_cast<const uint4*>(Db + q4 * pA + c8);
     {
         float2 t;
         t = unpack_bf16x2(v.x); d[0] = t.x; d[1] = t.y;
@@ -783,9 +790,9 @@ __device__ __forceinline__ void tbwd_step_b(float* Sb, uint16_t* Db, uint4* Xst,
     mma16816(accWw, dpk[2], 0u, dpk[3], 0u, ppk[2], ppk[3]);
     __syncwarp();                                                    // all lanes have consumed this step's S before it is overwritten
     if (slot) {
-        *reinterpret_cast<uint4*>(Db + q4 * ldA + c8) = make_uint4(ppk[0], ppk[1], ppk[2], ppk[3]);
+        *reinterpret_cast<uint4*>(Db + q4 * pA + c8) = make_uint4(ppk[0], ppk[1], ppk[2], ppk[3]);
         if (c8 + 8 <= ldS) {
-            float4* dst = reinterpret_cast<float4*>(Sb + q4 * ldS + c8);
+            float4* dst = reinterpret_cast<float4*>(Sb + q4 * pS + c8);
             dst[0] = make_float4(dP[0], dP[1], dP[2], dP[3]);
             dst[1] = make_float4(dP[4], dP[5], dP[6], dP[7]);
         }
@@ -793,15 +800,15 @@ __device__ __forceinline__ void tbwd_step_b(float* Sb, uint16_t* Db, uint4* Xst,
     Xst[lane] = make_uint4(shi[0], shi[1], shi[2], shi[3]);
 }
 template <int H, bool TAIL>
-__device__ __forceinline__ void tbwd_step_c(const float* Sb, const uint16_t* Db, const uint4* Xst, int ldS, int ldA, int base, int Nk, const MixFrag& fWlT,
+__device__ __forceinline__ void tbwd_step_c(const float* Sb, const uint16_t* Db, const uint4* Xst, int pS, int pA, int ldS, int ldA, int base, int Nk, const MixFrag& fWlT,
                                             float rho, uint16_t* dSb, long long hA, int q4, int r4, int lane, float (&accWl)[4]) {
     const int c8 = base + 8 * r4;
     const bool slot = q4 < H && c8 + 8 <= ldA && c8 + 8 <= ldS;
     float l[8], o[8];
     uint32_t lpk[4];
     if (slot) {
-        const uint4 pp = *reinterpret_cast<const uint4*>(Db + q4 * ldA + c8);
-        const float4 u = *reinterpret_cast<const float4*>(Sb + q4 * ldS + c8), w = *reinterpret_cast<const float4*>(Sb + q4 * ldS + c8 + 4);
+        const uint4 pp = *reinterpret_cast<const uint4*>(Db + q4 * pA + c8);
+        const float4 u = *reinterpret_cast<const float4*>(Sb + q4 * pS + c8), w = *reinterpret_cast<const float4*>(Sb + q4 * pS + c8 + 4);
         const float2 p0 = unpack_bf16x2(pp.x), p1 = unpack_bf16x2(pp.y), p2 = unpack_bf16x2(pp.z), p3 = unpack_bf16x2(pp.w);   // (p[t], p[4+t])
         l[0] = p0.x * (u.x - rho); l[4] = p0.y * (w.x - rho);
         l[1] = p1.x * (u.y - rho); l[5] = p1.y * (w.y - rho);
@@ -839,9 +846,10 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const floa
                                                                       float* __restrict__ part) {
     extern __shared__ __align__(128) uint8_t rsm[];
     // single row buffer per CTA; TWO CTAs share an SM, so one CTA's row load overlaps the other's math
-    float* Sbuf = reinterpret_cast<float*>(rsm);                                            // [H][ldS]   S, then dP
-    uint16_t* Dbuf = reinterpret_cast<uint16_t*>(rsm + (size_t)H * ldS * 4);                // [H][ldA]   dA, then P
-    uint4* Xbuf = reinterpret_cast<uint4*>(rsm + (size_t)H * ldS * 4 + (size_t)H * ldA * 2);  // [steps][32]  S_hi fragments
+    const int pS = talking_pitch_f32(ldS), pA = talking_pitch_bf16(ldA);                     // padded pitches: no bank conflicts
+    float* Sbuf = reinterpret_cast<float*>(rsm);                                            // [H][pS]   S, then dP
+    uint16_t* Dbuf = reinterpret_cast<uint16_t*>(rsm + (size_t)H * pS * 4);                 // [H][pA]   dA, then P
+    uint4* Xbuf = reinterpret_cast<uint4*>(rsm + (size_t)H * pS * 4 + (size_t)H * pA * 2);  // [steps][32]  S_hi fragments
     constexpr int NP = 2 * H * H + 2 * H;
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ float red[NW][8];
@@ -864,8 +872,8 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const floa
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of the previous row before the async refill
         rw_mbar_expect_tx(bar0, (uint32_t)(H * ldS * 4 + H * ldA * 2));
         for (int h = 0; h < H; ++h) {
-            rw_bulk_g2s(rw_smem_u32(Sbuf + (size_t)h * ldS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar0);
-            rw_bulk_g2s(rw_smem_u32(Dbuf + (size_t)h * ldA), dA + ((long long)b * H * Nq + q) * ldA + h * hA, (uint32_t)(ldA * 2), bar0);
+            rw_bulk_g2s(rw_smem_u32(Sbuf + (size_t)h * pS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar0);
+            rw_bulk_g2s(rw_smem_u32(Dbuf + (size_t)h * pA), dA + ((long long)b * H * Nq + q) * ldA + h * hA, (uint32_t)(ldA * 2), bar0);
         }
     };
     const int nst = (ldA + 31) / 32;
@@ -874,8 +882,10 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const floa
     float accWw[4] = {0.f, 0.f, 0.f, 0.f}, accWl[4] = {0.f, 0.f, 0.f, 0.f};
     if (tid == 0 && blockIdx.x < rows_total) issue(blockIdx.x);
     int it = 0;
+    float c2n = (q4 < H && blockIdx.x < rows_total) ? stats[(long long)blockIdx.x * H + q4] : 0.f;
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
-        const float c2 = q4 < H ? stats[(long long)row * H + q4] : 0.f;
+        const float c2 = c2n;
+        if (q4 < H && row + (int)gridDim.x < rows_total) c2n = stats[(long long)(row + gridDim.x) * H + q4];     // consumed one row later
         rw_mbar_wait(bar0, (uint32_t)it & 1u);
         const int b = row / Nq, q = row % Nq;
         uint16_t* dSb = dS + ((long long)b * H * Nq + q) * ldA;
@@ -883,8 +893,8 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const floa
         float rho = 0.f;
         for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            if (base + 32 <= Nk) tbwd_step_b<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, lane, rho, accWw);
-            else tbwd_step_b<H, true>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, lane, rho, accWw);
+            if (base + 32 <= Nk) tbwd_step_b<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, lane, rho, accWw);
+            else tbwd_step_b<H, true>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, lane, rho, accWw);
         }
         rho += __shfl_xor_sync(0xffffffffu, rho, 1);
         rho += __shfl_xor_sync(0xffffffffu, rho, 2);
@@ -896,8 +906,8 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const floa
         // ---- sweep C: dL = P (dP - rho);  dS = Wl^T dL;  dWl += dL (x) S     (dbl = sum dL is identically 0: not accumulated)
         for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            if (base + 32 <= Nk) tbwd_step_c<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, lane, accWl);
-            else tbwd_step_c<H, true>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, lane, accWl);
+            if (base + 32 <= Nk) tbwd_step_c<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, lane, accWl);
+            else tbwd_step_c<H, true>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, lane, accWl);
         }
         __syncthreads();                                               // every warp is done with the row buffer
         if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x);
@@ -1251,7 +1261,7 @@ template <int H>
 static int talking_fwd_launch(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats, int B, int Nq,
                               int Nk, int64_t ldS, int64_t ldA, cudaStream_t st) {
     SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 6.0, st);   // algorithmic bytes: S f32 read + A bf16 write
-    const size_t smem = (size_t)2 * H * ldS * 4;
+    const size_t smem = (size_t)2 * H * talking_pitch_f32((int)ldS) * 4;
     if (stats && smem <= 100 * 1024 + 4096 && getenv("SPE_TALKING_WARP_ROWS") == nullptr) {
         static bool done = false;
         if (!done) {
@@ -1301,7 +1311,7 @@ static int talking_bwd_rows_grid(int B, int Nq) {
 template <int H>
 static int talking_bwd_launch(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B,
                               int Nq, int Nk, int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* ws, cudaStream_t st) {
-    const size_t smem = (size_t)H * (ldS * 4 + ldA * 2) + (size_t)((ldA + 31) / 32) * 512;
+    const size_t smem = (size_t)H * (talking_pitch_f32((int)ldS) * 4 + talking_pitch_bf16((int)ldA) * 2) + (size_t)((ldA + 31) / 32) * 512;
     const bool rows_ok = stats && smem <= 104 * 1024 && getenv("SPE_TALKING_WARP_ROWS") == nullptr;
     const int grid = rows_ok ? talking_bwd_rows_grid(B, Nq) : talking_bwd_grid(B, Nq);
     {
