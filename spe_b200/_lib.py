@@ -93,7 +93,15 @@ def check(rc):
         raise RuntimeError("libspe_b200: " + lib().spe_last_error().decode())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream():
+    """cudaStream_t of torch's current stream on the current device.  (torch.cuda.current_stream() builds a Python Stream
+    object through several layers, ~10 us; this is called once per kernel launch, several thousand times a step.)"""
+    if _raw_stream is not None and _cur_device is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
 
 

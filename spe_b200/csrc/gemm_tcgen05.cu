@@ -702,12 +702,27 @@ int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB,
 
 }  // namespace
 
+// debugging / experiment switches, read once (getenv scans the whole environment: ~0.5 us each, five per call adds up at 1300 GEMMs a step)
+struct GemmEnv {
+    bool bn256, direct_epilogue, generic_epilogue, no_splitk;
+    int dbg;
+    GemmEnv() {
+        bn256 = getenv("SPE_GEMM_BN256") != nullptr;
+        direct_epilogue = getenv("SPE_GEMM_DIRECT_EPILOGUE") != nullptr;
+        generic_epilogue = getenv("SPE_GEMM_GENERIC_EPILOGUE") != nullptr;
+        no_splitk = getenv("SPE_GEMM_NO_SPLITK") != nullptr;
+        const char* d = getenv("SPE_GEMM_DBG");
+        dbg = d ? atoi(d) : 0;
+    }
+};
+
 extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_args* a, void* stream) {
+    static const GemmEnv env;
     SPE_CHECK(a && a->A && a->B && a->C, "spe_gemm: null argument");
     SPE_CHECK(a->M > 0 && a->N > 0 && a->K > 0 && a->batch1 > 0 && a->batch2 > 0, "spe_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
     SPE_CHECK(a->act == SPE_ACT_NONE || a->act == SPE_ACT_RELU || a->act == SPE_ACT_GELU || a->aux_in, "spe_gemm: *_GRAD activation needs aux_in");
     // 128x256 tiles (fewer A re-reads, 2 pipeline stages) were measured: S-type GEMMs -6%, fc1 +15% -> opt-in only (SPE_GEMM_BN256=1)
-    const bool wideN = a->N >= 512 && (((a->N + 255) / 256) * 256 - a->N) * 8 <= a->N && getenv("SPE_GEMM_BN256") != nullptr;
+    const bool wideN = a->N >= 512 && (((a->N + 255) / 256) * 256 - a->N) * 8 <= a->N && env.bn256;
     const int BN = a->N <= 64 ? 64 : (wideN ? 256 : 128);
     const int batch = a->batch1 * a->batch2;
     SPE_CHECK(batch == 1 || !(a->aux_in || a->aux_out), "spe_gemm: aux_in / aux_out are not batched");
@@ -740,17 +755,17 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     const bool cf32 = a->c_dtype == SPE_DT_F32;
     const bool bias_ok = !a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
     const bool gamma_ok = !a->gamma || (reinterpret_cast<uintptr_t>(a->gamma) & 15) == 0;
-    bool tma_io = a->split == 0 && getenv("SPE_GEMM_DIRECT_EPILOGUE") == nullptr && !(a->aux_in && a->aux_out) && bias_ok && gamma_ok;
+    bool tma_io = a->split == 0 && !env.direct_epilogue && !(a->aux_in && a->aux_out) && bias_ok && gamma_ok;
     if (tma_io && make_tmap_io(&io.C, a->C, cf32, a->M, a->N, a->ldc, a->c_sb1, a->c_sb2, a->batch1, a->batch2)) tma_io = false;
     if (tma_io && residual && make_tmap_io(&io.R, residual, true, a->M, a->N, a->ldr, a->r_sb1, a->r_sb2, a->batch1, a->batch2)) tma_io = false;
     if (tma_io && a->aux_in && make_tmap_io(&io.Xi, a->aux_in, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
     if (tma_io && a->aux_out && make_tmap_io(&io.Xo, a->aux_out, false, a->M, a->N, a->ld_aux, 0, 0, 1, 1)) tma_io = false;
     ep.tma_io = tma_io ? 1 : 0;
-    { const char* d = getenv("SPE_GEMM_DBG"); ep.dbg = d ? atoi(d) : 0; }
+    ep.dbg = env.dbg;
     {
         const bool bi = a->bias != nullptr, ga = a->gamma != nullptr, re = residual != nullptr, xo = a->aux_out != nullptr, xi = a->aux_in != nullptr;
         int m = EM_GENERIC;
-        if (tma_io && getenv("SPE_GEMM_GENERIC_EPILOGUE") == nullptr) {
+        if (tma_io && !env.generic_epilogue) {
             if (a->act == SPE_ACT_NONE && !xi) {
                 if (cf32 && !bi && !ga && !re && !xo) m = EM_F32;
                 else if (!cf32 && !bi && !ga && !re && !xo) m = EM_BF16;
@@ -776,7 +791,7 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     const long long tiles = (long long)ep.tiles_m * ep.tiles_n * batch;
     SPE_CHECK(tiles < (1LL << 30), "spe_gemm: too many tiles");
     if (cf32 && batch == 1 && a->act == SPE_ACT_NONE && !a->aux_in && !a->aux_out && !a->gamma && (accum || a->residual != (const float*)a->C) &&
-        a->ldc == a->N && a->split == 0 && tiles * 2 <= spe_num_sms() && total_kb >= 8 && getenv("SPE_GEMM_NO_SPLITK") == nullptr) {
+        a->ldc == a->N && a->split == 0 && tiles * 2 <= spe_num_sms() && total_kb >= 8 && !env.no_splitk) {
         splits = (int)((spe_num_sms() + tiles - 1) / tiles);
         if (splits > total_kb / 4) splits = total_kb / 4;
         if (splits < 1) splits = 1;

@@ -24,6 +24,15 @@ _ACT = {None: ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU}
 _ACT_GRAD = {"relu": ACT_RELU_GRAD, "gelu": ACT_GELU_GRAD}
 
 
+_spe_gemm = None
+
+
+def _bind_gemm():
+    global _spe_gemm
+    _spe_gemm = lib().spe_gemm
+    return _spe_gemm
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -74,19 +83,20 @@ def clear_shadows():
 def gemm(a, b, c, M, N, K, *, a_major=MAJOR_K, lda=None, b_major=MAJOR_K, ldb=None, ldc=None, batch=(1, 1),
          a_sb=(0, 0), b_sb=(0, 0), c_sb=(0, 0), alpha=1.0, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, ld_aux=0,
          gamma=None, residual=None, ldr=0, r_sb=(0, 0), split=0, split_stride=0):
-    _need_cuda(a, b, c)
+    if not (a.is_cuda and b.is_cuda and c.is_cuda):
+        _need_cuda(a, b, c)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
-    g = GemmArgs()
-    g.M, g.N, g.K, g.batch1, g.batch2 = M, N, K, batch[0], batch[1]
-    g.A, g.a_major, g.lda, g.a_sb1, g.a_sb2 = a.data_ptr(), a_major, lda, a_sb[0], a_sb[1]
-    g.B, g.b_major, g.ldb, g.b_sb1, g.b_sb2 = b.data_ptr(), b_major, ldb, b_sb[0], b_sb[1]
-    g.C, g.c_dtype = c.data_ptr(), (DT_F32 if c.dtype == torch.float32 else DT_BF16)
-    g.ldc, g.c_sb1, g.c_sb2 = ldc, c_sb[0], c_sb[1]
-    g.alpha, g.bias, g.act = alpha, ptr(bias), act
-    g.aux_in, g.aux_out, g.ld_aux = ptr(aux_in), ptr(aux_out), ld_aux
-    g.gamma, g.residual, g.ldr, g.r_sb1, g.r_sb2 = ptr(gamma), ptr(residual), ldr, r_sb[0], r_sb[1]
-    g.split, g.split_stride = split, split_stride
-    check(lib().spe_gemm(C.byref(g), stream()))
+    # positional init in field order (one C call instead of ~35 attribute stores)
+    g = GemmArgs(M, N, K, batch[0], batch[1],
+                 a.data_ptr(), a_major, lda, a_sb[0], a_sb[1],
+                 b.data_ptr(), b_major, ldb, b_sb[0], b_sb[1],
+                 c.data_ptr(), (DT_F32 if c.dtype == torch.float32 else DT_BF16), ldc, c_sb[0], c_sb[1],
+                 alpha, ptr(bias), act, ptr(aux_in), ptr(aux_out), ld_aux,
+                 ptr(gamma), ptr(residual), ldr, r_sb[0], r_sb[1],
+                 split, split_stride)
+    rc = (_spe_gemm or _bind_gemm())(C.byref(g), stream())
+    if rc:
+        check(rc)
     return c
 
 
