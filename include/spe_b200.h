@@ -115,6 +115,10 @@ int spe_colsum_bf16_batched(const void* x, int batch, int64_t rows, int N, int64
 /* y_bf16 = (a*x + b*y) with f32 inputs (y may be NULL); also optional f32 output */
 int spe_axpby_cast(const float* x, const float* y, float a, float b, int64_t n, void* out_bf16, float* out_f32,
                    void* stream);
+/* bf16 shadows of many fp32 tensors in ONE launch (the per-step refresh of every weight's GEMM operand after the optimizer
+ * moved the fp32 masters): segs = device array of `count` {src f32*, dst bf16*, n} records, max_n = largest n. */
+typedef struct spe_cast_seg { const float* src; void* dst; int64_t n; } spe_cast_seg;
+int spe_cast_f32_to_bf16_multi(const spe_cast_seg* segs, int count, int64_t max_n, void* stream);
 int spe_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
 /* ReLU backward for an activation fused into a GEMM epilogue: out = dout * (h > 0), all bf16 (transformer.py:21-33 MLP) */
 int spe_relu_bwd_bf16(const void* dout, const void* h, void* out, int64_t n, void* stream);
@@ -142,10 +146,12 @@ int spe_query_sine_bwd(const float* ref, const float* demb, int64_t n, int D, fl
  * ------------------------------------------------------------------------------------------- */
 /* Block-diagonal cost only: for image b, cost[b][q][g], g < G_b = gt_off[b+1]-gt_off[b].
  * logits f32 [B,Q,C], boxes f32 [B,Q,4] cxcywh, gt_labels i32 [sumG], gt_boxes f32 [sumG,4],
- * gt_off i32 [B+1]; cost f32 [B,Q,ldc] (ldc >= max G_b).  fp32, reference op order, no FMA contraction. */
+ * gt_off i32 [B+1]; cost f32 [B,Q,ldc] (ldc >= max G_b).  fp32, reference op order, no FMA contraction.
+ * gt_images > 0: the targets describe gt_images images and problem b uses image b % gt_images (the L decoder levels of
+ * conditional_detr.py:444-452 stacked along the batch, B = L * gt_images, share one target set); 0: one image per problem. */
 int spe_match_cost(const float* logits, const float* boxes, const int32_t* gt_labels, const float* gt_boxes,
                    const int32_t* gt_off, int B, int Q, int C, float w_class, float w_bbox, float w_giou,
-                   float* cost, int64_t ldc, void* stream);
+                   float* cost, int64_t ldc, int gt_images, void* stream);
 /* scipy.optimize.linear_sum_assignment (matcher.py:86) for B independent problems: cost f32 [B,nr,ldc],
  * problem b uses the first nc[b] columns (nc = NULL -> all ldc).  Output query_to_col i32 [B,nr]
  * (-1 = unassigned row; when nr <= nc[b] every row is assigned).  Identical indices to scipy incl. ties:

@@ -58,7 +58,8 @@ _SIGS = {
     "spe_sine_pos_2d": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "spe_query_sine_fwd": (c_i, [c_p, c_l, c_i, c_p, c_p]),
     "spe_query_sine_bwd": (c_i, [c_p, c_p, c_l, c_i, c_p, c_p]),
-    "spe_match_cost": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_l, c_p]),
+    "spe_match_cost": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_l, c_i, c_p]),
+    "spe_cast_f32_to_bf16_multi": (c_i, [c_p, c_i, c_l, c_p]),
     "spe_lsap_workspace_bytes": (c_l, [c_i, c_i, c_i]),
     "spe_lsap_batched": (c_i, [c_p, c_i, c_i, c_l, c_p, c_i, c_p, c_p, c_p]),
     "spe_focal_loss_workspace_bytes": (c_l, [c_i, c_i]),

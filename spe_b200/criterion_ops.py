@@ -38,17 +38,9 @@ class PackedTargets:
             self.scores = torch.cat([t["scores"].reshape(-1) for t in targets]).to(torch.float32).to(device, non_blocking=True).contiguous()
         self.device = device
         self._inv_num_boxes = None
-        self._rep = {}
-
-    def repeated(self, L):
-        """(labels, boxes, offsets, counts) of the same targets repeated L times: lets ONE cost launch + ONE LSAP launch
-        match all L decoder levels (L*B independent problems) instead of L serial launches."""
-        if L not in self._rep:
-            tot = max(self.total, 0)
-            off = torch.cat([self.offsets_host[:-1] + l * tot for l in range(L)] + [torch.tensor([L * tot], dtype=torch.int32)])
-            self._rep[L] = (self.labels[:max(tot, 1)].repeat(L) if tot else self.labels, self.boxes[:max(tot, 1)].repeat(L, 1) if tot else self.boxes,
-                            off.to(self.device, non_blocking=True), self.counts_host.repeat(L).to(self.device, non_blocking=True))
-        return self._rep[L]
+        self.img_label = None
+        if targets and all("img_label" in t for t in targets):
+            self.img_label = torch.stack([t["img_label"] for t in targets]).to(device, non_blocking=True).float()
 
     def inv_num_boxes(self):
         """1 / clamp(all_reduce(num_boxes)/world, 1) as a device scalar (conditional_detr.py:436-440), no .item()."""
@@ -61,8 +53,71 @@ class PackedTargets:
         return self._inv_num_boxes
 
 
+class StaticTargets(PackedTargets):
+    """Fixed-capacity target buffers at fixed device addresses (what a captured CUDA graph needs): `update(targets)` refills
+    them in place from pinned staging memory, outside the graph.  Layout is the same compact CSR (labels, boxes, offsets);
+    `max_g` (the cost-matrix pitch) is the static per-image capacity, the real counts live on the device."""
+
+    def __init__(self, batch, max_gt, device, with_scores=False, img_classes=0):
+        self.B = int(batch)
+        self.cap = int(max_gt)
+        self.max_g = self.cap
+        self.device = device
+        ct = max(self.B * self.cap, 1)
+        pin = torch.cuda.is_available()
+        self._h_labels = torch.zeros(ct, dtype=torch.int32, pin_memory=pin)
+        self._h_boxes = torch.zeros(ct, 4, dtype=torch.float32, pin_memory=pin)
+        self._h_scores = torch.ones(ct, dtype=torch.float32, pin_memory=pin) if with_scores else None
+        self._h_off = torch.zeros(self.B + 1, dtype=torch.int32, pin_memory=pin)
+        self._h_cnt = torch.zeros(self.B, dtype=torch.int32, pin_memory=pin)
+        self._h_inv = torch.ones(1, dtype=torch.float32, pin_memory=pin)
+        self.labels = torch.zeros(ct, dtype=torch.int32, device=device)
+        self.boxes = torch.zeros(ct, 4, dtype=torch.float32, device=device)
+        self.scores = torch.ones(ct, dtype=torch.float32, device=device) if with_scores else None
+        self.offsets = torch.zeros(self.B + 1, dtype=torch.int32, device=device)
+        self.counts = torch.zeros(self.B, dtype=torch.int32, device=device)
+        self._inv_num_boxes = torch.ones(1, dtype=torch.float32, device=device)
+        self.img_label = torch.zeros(self.B, img_classes, dtype=torch.float32, device=device) if img_classes else None
+        self.sizes, self.total = [0] * self.B, 0
+
+    def update(self, targets):
+        assert len(targets) == self.B, "StaticTargets: batch size changed"
+        sizes = [int(t["labels"].shape[0]) for t in targets]
+        if max(sizes, default=0) > self.cap:
+            raise ValueError("StaticTargets: %d targets in one image exceed the static capacity %d" % (max(sizes), self.cap))
+        self.sizes, self.total = sizes, sum(sizes)
+        o = 0
+        for b, (t, n) in enumerate(zip(targets, sizes)):
+            self._h_off[b] = o
+            self._h_cnt[b] = n
+            if n:
+                self._h_labels[o:o + n].copy_(t["labels"].reshape(-1))
+                self._h_boxes[o:o + n].copy_(t["boxes"].reshape(-1, 4))
+                if self._h_scores is not None:
+                    self._h_scores[o:o + n].copy_(t["scores"].reshape(-1))
+            o += n
+        self._h_off[self.B] = o
+        self.labels.copy_(self._h_labels, non_blocking=True)
+        self.boxes.copy_(self._h_boxes, non_blocking=True)
+        if self.scores is not None:
+            self.scores.copy_(self._h_scores, non_blocking=True)
+        self.offsets.copy_(self._h_off, non_blocking=True)
+        self.counts.copy_(self._h_cnt, non_blocking=True)
+        if self.img_label is not None and targets and "img_label" in targets[0]:
+            self.img_label.copy_(torch.stack([t["img_label"] for t in targets]).float(), non_blocking=True)
+        # 1 / clamp(all_reduce(num_boxes) / world, 1)   (conditional_detr.py:436-440), refreshed in place
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            nb = torch.tensor([float(self.total)], dtype=torch.float32, device=self.device)
+            torch.distributed.all_reduce(nb)
+            self._inv_num_boxes.copy_(1.0 / torch.clamp(nb / torch.distributed.get_world_size(), min=1.0))
+        else:
+            self._h_inv[0] = 1.0 / max(float(self.total), 1.0)
+            self._inv_num_boxes.copy_(self._h_inv, non_blocking=True)
+        return self
+
+
 def pack_targets(targets, device):
-    return PackedTargets(targets, device)
+    return targets if isinstance(targets, PackedTargets) else PackedTargets(targets, device)
 
 
 def match_cost(logits, boxes, T, weights):
@@ -74,7 +129,7 @@ def match_cost(logits, boxes, T, weights):
     cost = torch.empty((B, Q, ld), dtype=torch.float32, device=logits.device)
     w_class, w_bbox, w_giou = weights
     check(lib().spe_match_cost(ptr(logits.detach().float().contiguous()), ptr(boxes.detach().float().contiguous()), ptr(T.labels), ptr(T.boxes),
-                               ptr(T.offsets), B, Q, C, float(w_class), float(w_bbox), float(w_giou), ptr(cost), ld, stream()))
+                               ptr(T.offsets), B, Q, C, float(w_class), float(w_bbox), float(w_giou), ptr(cost), ld, 0, stream()))
     return cost
 
 
@@ -98,17 +153,17 @@ def match(logits, boxes, T, weights):
 
 
 def match_levels(logits_levels, boxes_levels, T, weights):
-    """logits [L,B,Q,C], boxes [L,B,Q,4] -> dense assignment i32 [L,B,Q]; one cost + one LSAP launch for all levels."""
+    """logits [L,B,Q,C], boxes [L,B,Q,4] -> dense assignment i32 [L,B,Q]; one cost + one LSAP launch for all levels
+    (L*B independent problems; problem p uses the targets of image p % B)."""
     L, B, Q, C = logits_levels.shape
     if T.max_g == 0:
         return torch.full((L, B, Q), -1, dtype=torch.int32, device=logits_levels.device)
-    labels, boxes, off, counts = T.repeated(L)
     ld = T.max_g
     cost = torch.empty((L * B, Q, ld), dtype=torch.float32, device=logits_levels.device)
     w_class, w_bbox, w_giou = weights
-    check(lib().spe_match_cost(ptr(logits_levels.detach().float().contiguous()), ptr(boxes_levels.detach().float().contiguous()), ptr(labels), ptr(boxes),
-                               ptr(off), L * B, Q, C, float(w_class), float(w_bbox), float(w_giou), ptr(cost), ld, stream()))
-    return lsap_raw(cost, counts).view(L, B, Q)
+    check(lib().spe_match_cost(ptr(logits_levels.detach().float().contiguous()), ptr(boxes_levels.detach().float().contiguous()), ptr(T.labels),
+                               ptr(T.boxes), ptr(T.offsets), L * B, Q, C, float(w_class), float(w_bbox), float(w_giou), ptr(cost), ld, B, stream()))
+    return lsap_raw(cost, T.counts.repeat(L)).view(L, B, Q)
 
 
 def indices_from_dense(r2g_cpu):

@@ -16,12 +16,13 @@ namespace {
 __global__ void match_cost_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
                                   const int32_t* __restrict__ gt_labels, const float* __restrict__ gt_boxes,
                                   const int32_t* __restrict__ gt_off, int Q, int C, float w_class, float w_bbox, float w_giou,
-                                  float* __restrict__ cost, long long ldc) {
+                                  float* __restrict__ cost, long long ldc, int gt_images) {
     const int b = blockIdx.y;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= Q) return;
-    const int g0 = gt_off[b], G = gt_off[b + 1] - g0;
+    const int bt = gt_images > 0 ? b % gt_images : b;      // decoder levels stacked along the batch share the targets
+    const int g0 = gt_off[bt], G = gt_off[bt + 1] - g0;
     const float4 bx = *reinterpret_cast<const float4*>(boxes + ((long long)b * Q + q) * 4);
     // box_cxcywh_to_xyxy (util/box_ops.py:18-22)
     const float ax0 = bx.x - 0.5f * bx.z, ay0 = bx.y - 0.5f * bx.w, ax1 = bx.x + 0.5f * bx.z, ay1 = bx.y + 0.5f * bx.w;
@@ -218,13 +219,13 @@ size_t lsap_smem_bytes(int small, int big) {
 
 extern "C" __attribute__((visibility("default"))) int spe_match_cost(const float* logits, const float* boxes, const int32_t* gt_labels, const float* gt_boxes,
                               const int32_t* gt_off, int B, int Q, int C, float w_class, float w_bbox, float w_giou, float* cost,
-                              int64_t ldc, void* stream) {
+                              int64_t ldc, int gt_images, void* stream) {
     SPE_CHECK(logits && boxes && gt_labels && gt_boxes && gt_off && cost, "spe_match_cost: null argument");
-    SPE_CHECK(B > 0 && Q > 0 && C > 0, "spe_match_cost: bad shape");
+    SPE_CHECK(B > 0 && Q > 0 && C > 0 && gt_images >= 0, "spe_match_cost: bad shape");
     const int warps = 4;
     dim3 grid((Q + warps - 1) / warps, B);
     match_cost_kernel<<<grid, warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, boxes, gt_labels, gt_boxes, gt_off, Q, C, w_class,
-                                                                                         w_bbox, w_giou, cost, ldc);
+                                                                                         w_bbox, w_giou, cost, ldc, gt_images);
     SPE_LAUNCHED();
     return 0;
 }

@@ -1399,6 +1399,38 @@ extern "C" __attribute__((visibility("default"))) int spe_axpby_cast(const float
     return 0;
 }
 
+namespace {
+__global__ void __launch_bounds__(256) cast_multi_kernel(const spe_cast_seg* __restrict__ segs) {
+    const spe_cast_seg sg = segs[blockIdx.y];
+    const float* __restrict__ src = sg.src;
+    uint16_t* __restrict__ dst = reinterpret_cast<uint16_t*>(sg.dst);
+    const long long n = sg.n;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (vec) {
+        const long long n4 = n >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+            reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        }
+        for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = f_to_bf16(src[i]);
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = f_to_bf16(src[i]);
+    }
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int spe_cast_f32_to_bf16_multi(const spe_cast_seg* segs, int count, int64_t max_n, void* stream) {
+    SPE_CHECK(segs && count > 0 && max_n > 0, "spe_cast_f32_to_bf16_multi: bad argument");
+    SPE_CHECK(count <= 65535, "spe_cast_f32_to_bf16_multi: too many segments");
+    long long gx = (max_n / 4 + 255) / 256;
+    if (gx > 32) gx = 32;
+    if (gx < 1) gx = 1;
+    cast_multi_kernel<<<dim3((unsigned)gx, (unsigned)count), 256, 0, ST(stream)>>>(segs);
+    SPE_LAUNCHED();
+    return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int spe_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream) {
     SPE_CHECK(x && y && n > 0, "spe_cast_bf16_to_f32: bad argument");
     cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint16_t*>(x), y, n, 0);

@@ -1,0 +1,106 @@
+"""The training iteration of the reference's engine (engine.py:train_one_epoch_refine, :100-170: forward -> criterion(outputs[0]) +
+criterion_refine(outputs[1]) -> weighted sum -> backward) as ONE object, optionally captured into a CUDA graph.
+
+Eager mode is what the reference's loop does line by line.  Graph mode (graph=True) records the same work once -- for a fixed
+image shape and a fixed per-image target capacity -- and replays it: the ~3200 kernel launches of a step then cost the host one
+cudaGraphLaunch, which is what keeps the step device-bound (eager, the Python/launch path needs ~57 ms per step next to
+~70 ms of device work).  Inputs are copied into static buffers before each replay; the matcher, the losses and the gradient
+accumulation all run on the device with no host synchronisation, so the captured step is the complete step.
+
+The gradient all-reduce (one NCCL call on the flat buffer) stays outside the graph."""
+import torch
+
+from . import criterion_ops as CO
+from . import ops
+from .dp import FlatGradBuffer
+from .util.misc import NestedTensor
+
+
+class TrainStep:
+    def __init__(self, model, criterion, criterion_refine=None, weight_dict=None, grad_buffer=None, graph=False, max_gt=None,
+                 refresh_shadows=True):
+        self.model, self.criterion, self.criterion_refine = model, criterion, criterion_refine
+        self.weight_dict = dict(weight_dict if weight_dict is not None else criterion.weight_dict)
+        self.gbuf = grad_buffer if grad_buffer is not None else FlatGradBuffer(model.parameters())
+        self.graph = bool(graph)
+        self.max_gt = max_gt
+        self.shadows = ops.ShadowSet(model.parameters()) if refresh_shadows else None
+        self._g = {}            # (B, H, W, cap) -> captured state
+
+    # ---- the step body (identical in both modes) ----
+    def _body(self, images, T, T_refine):
+        self.gbuf.zero_()
+        if self.shadows is not None:
+            self.shadows.refresh()
+        out = self.model(images)
+        ld = self.criterion(out[0], T)
+        wd = self.weight_dict
+        loss = sum(ld[k] * wd[k] for k in ld if k in wd)
+        ld2 = None
+        if self.criterion_refine is not None:
+            ld2 = self.criterion_refine(out[1], T_refine)
+            loss = loss + sum(ld2[k] * wd[k] for k in ld2 if k in wd)
+        loss.backward()
+        return loss.detach(), {k: v.detach() for k, v in ld.items()}, (None if ld2 is None else {k: v.detach() for k, v in ld2.items()})
+
+    def __call__(self, samples, targets, targets_refine=None):
+        """samples: float tensor [B,3,H,W] (or NestedTensor / list, eager only); targets: list of dicts as the reference's
+        data loader yields them; targets_refine: the pseudo-label targets of the refine stage (default: targets).
+        Returns (loss, loss_dict, loss_dict_refine) -- device scalars; gradients are in the flat buffer, all-reduced."""
+        if targets_refine is None:
+            targets_refine = targets
+        if not self.graph or not torch.is_tensor(samples):
+            tg = self.criterion.prepare_targets(targets)
+            tr = self.criterion_refine.prepare_targets(targets_refine) if self.criterion_refine is not None else None
+            res = self._body(samples, tg, tr)
+        else:
+            res = self._replay(samples, targets, targets_refine)
+        self.gbuf.all_reduce_mean()
+        return res
+
+    # ---- graph mode ----
+    def _replay(self, images, targets, targets_refine):
+        tg = self.criterion.prepare_targets(targets)
+        tr = self.criterion_refine.prepare_targets(targets_refine) if self.criterion_refine is not None else None
+        need = max([len(t["labels"]) for t in tg] + ([len(t["labels"]) for t in tr] if tr is not None else []) + [1])
+        cap = self.max_gt if self.max_gt is not None else need
+        if need > cap:
+            raise ValueError("TrainStep(graph=True): %d targets in one image exceed max_gt=%d" % (need, cap))
+        key = (tuple(images.shape), cap)
+        st = self._g.get(key)
+        if st is None:
+            st = self._capture(images, tg, tr, cap)
+            self._g[key] = st
+        st["images"].copy_(images, non_blocking=True)
+        st["T"].update(tg)
+        if st["Tr"] is not None:
+            st["Tr"].update(tr)
+        st["graph"].replay()
+        return st["out"]
+
+    def _capture(self, images, tg, tr, cap):
+        dev = next(self.model.parameters()).device
+        B = images.shape[0]
+        ncls = tg[0]["img_label"].numel() if tg and "img_label" in tg[0] else 0
+        st = {"images": torch.empty(images.shape, dtype=torch.float32, device=dev),
+              "T": CO.StaticTargets(B, cap, dev, with_scores=all("scores" in t for t in tg), img_classes=ncls),
+              "Tr": None}
+        if tr is not None:
+            st["Tr"] = CO.StaticTargets(B, cap, dev, with_scores=all("scores" in t for t in tr), img_classes=ncls)
+        st["images"].copy_(images)
+        st["T"].update(tg)
+        if st["Tr"] is not None:
+            st["Tr"].update(tr)
+        # warm-up on a side stream (lazy one-time initialisation: shadows, kernel attributes, autograd buffers), then capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._body(st["images"], st["T"], st["Tr"])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st["out"] = self._body(st["images"], st["T"], st["Tr"])
+        st["graph"] = g
+        return st

@@ -133,8 +133,15 @@ class SetCriterion(nn.Module):
                 t["scores"] = t["scores"].unsqueeze(1).repeat(1, r).reshape(-1)
         return out
 
+    def prepare_targets(self, targets):
+        """the target list the losses see: jittered + repeated GT in training mode (:410-431), unchanged in eval mode."""
+        return self._jitter_repeat(targets) if self.training else targets
+
     def loss_img_label(self, outputs, targets):
-        y = torch.stack([t["img_label"] for t in targets]).to(outputs["x_logits"].device).float()
+        if isinstance(targets, CO.PackedTargets):
+            y = targets.img_label
+        else:
+            y = torch.stack([t["img_label"] for t in targets]).to(outputs["x_logits"].device).float()
         return {"img_label_logits": CO.BceLogitsFn.apply(outputs["x_logits"], y)[0],
                 "img_label_logits_tokens": CO.BceLogitsFn.apply(outputs["x_cls_logits"], y)[0]}
 
@@ -142,9 +149,12 @@ class SetCriterion(nn.Module):
         """conditional_detr.py:399-466."""
         if isinstance(outputs, RefineOutputs):
             outputs = outputs[0]
-        tg = self._jitter_repeat(targets) if self.training else targets
         dev = outputs["pred_logits"].device
-        T = CO.pack_targets(tg, dev)
+        if isinstance(targets, CO.PackedTargets):
+            tg = T = targets            # pre-packed (engine.TrainStep: static buffers; jitter/repeat already applied by prepare_targets)
+        else:
+            tg = self.prepare_targets(targets)
+            T = CO.pack_targets(tg, dev)
         mw = self.matcher.weights
         det = tuple(l for l in self.losses if l in ("labels", "boxes", "cardinality"))
         losses = {}

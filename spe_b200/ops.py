@@ -72,6 +72,52 @@ def shadow(p):
     return out
 
 
+class ShadowSet:
+    """All bf16 shadows of a set of parameters, refreshed by ONE multi-tensor cast launch (spe_cast_f32_to_bf16_multi) --
+    what a training loop does right after optimizer.step() instead of ~400 single casts on first use.  Inside a captured
+    CUDA graph the refresh is part of the graph, so replays always see the current fp32 masters."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        self._sig = None
+        self._desc = None
+        self._entries = []
+        self._max_n = 1
+
+    def _collect(self):
+        ents = []
+        for p in self.params:
+            cache = p.__dict__.get("_spe_shadow")
+            if not cache:
+                continue
+            for key, (ver, out) in cache.items():
+                off, shape, stride = key
+                src = p.detach().as_strided(shape, stride, off)
+                if src.is_contiguous() and out.is_contiguous() and out.device == p.device:
+                    ents.append((p, key, src, out))
+        return ents
+
+    def refresh(self):
+        """re-cast every known shadow from its fp32 master (no version check: one launch covers them all)."""
+        ents = self._collect()
+        if not ents:
+            return 0
+        sig = tuple((e[2].data_ptr(), e[3].data_ptr()) for e in ents)
+        if sig != self._sig:
+            import numpy as np
+            tab = np.zeros((len(ents), 3), dtype=np.int64)
+            for i, (_, _, src, out) in enumerate(ents):
+                tab[i] = (src.data_ptr(), out.data_ptr(), src.numel())
+            self._desc = torch.from_numpy(tab).to(ents[0][3].device)
+            self._max_n = int(tab[:, 2].max())
+            self._sig = sig
+        self._entries = ents
+        check(lib().spe_cast_f32_to_bf16_multi(ptr(self._desc), len(ents), self._max_n, stream()))
+        for p, key, _, out in ents:
+            p._spe_shadow[key] = (p._version, out)
+        return len(ents)
+
+
 def clear_shadows():
     """kept for API stability: shadows are owned by their parameters and die with them."""
     return None

@@ -178,3 +178,45 @@ def test_fused_grad_accumulation_matches_autograd():
         for n in ref:
             scale = float(ref[n].abs().max()) + 1e-6
             assert float((got[n] - ref[n]).abs().max()) <= 2e-3 * scale + 1e-6, (n, passes)
+
+
+def test_train_step_graph_matches_eager():
+    """engine.TrainStep: the CUDA-graph replay (static image / target buffers, per-step shadow refresh) produces the losses and
+    gradients of the eager step, also after the targets AND the weights changed between replays."""
+    from spe_b200 import factory
+    from spe_b200.engine import TrainStep
+    cfg = O.tiny_config()
+    params = O.make_params(cfg, 11)
+    dev = torch.device("cuda")
+    batches = []
+    for seed in (11, 12, 13):
+        images, targets = O.make_inputs(cfg, 2, 48, 64, seed=seed, max_gt=4)
+        batches.append((images.to(dev), [{k: v.to(dev) for k, v in t.items()} for t in targets]))
+
+    def run(graph):
+        model = factory.build_detector(cfg, dev).train()
+        model.load_state_dict(params)
+        crit = factory.build_criterion(cfg, device=dev).eval()
+        crit_r = factory.build_criterion(cfg, refine=True, device=dev).eval()
+        step = TrainStep(model, crit, crit_r, graph=graph, max_gt=8)
+        res = []
+        for i, (im, tg) in enumerate(batches):
+            tr = [dict(t, scores=torch.full((len(t["labels"]),), 0.5 + 0.1 * i, device=dev)) for t in tg]
+            loss, ld, ld2 = step(im, tg, tr)
+            grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+            res.append((float(loss), {k: float(v) for k, v in ld.items()}, {k: float(v) for k, v in ld2.items()}, grads))
+            with torch.no_grad():                       # an "optimizer step": the next replay must see the new weights
+                for p in model.parameters():
+                    p.add_(p.grad, alpha=-1e-3)
+        return res
+
+    eager, graphed = run(False), run(True)
+    for (l0, d0, r0, g0), (l1, d1, r1, g1) in zip(eager, graphed):
+        assert abs(l0 - l1) <= 2e-3 * abs(l0) + 1e-5, (l0, l1)
+        for k in d0:
+            assert abs(d0[k] - d1[k]) <= 2e-3 * abs(d0[k]) + 1e-4, (k, d0[k], d1[k])
+        for k in r0:
+            assert abs(r0[k] - r1[k]) <= 2e-3 * abs(r0[k]) + 1e-4, (k, r0[k], r1[k])
+        for n in g0:
+            scale = float(g0[n].abs().max()) + 1e-6
+            assert float((g0[n] - g1[n]).abs().max()) <= 5e-3 * scale + 1e-6, n
