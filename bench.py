@@ -170,7 +170,13 @@ def run_ours(args):
     # flat gradient buffer: ONE all-reduce per step covers every parameter.  p.grad are slices of it and the backward
     # kernels accumulate straight into them (wgrad GEMM reduce-add / atomics: no temporaries, no per-parameter add kernels).
     from spe_b200.dp import FlatGradBuffer
+    from spe_b200.engine import TrainStep
     gbuf = FlatGradBuffer(model.parameters(), mode=os.environ.get("SPE_GRAD_MODE", "views"))
+    # the step = engine.TrainStep: zero grads, refresh bf16 weight shadows, model, both criteria (12 Hungarian matchings), weighted
+    # sum, backward, grad all-reduce.  Default: captured once into a CUDA graph and replayed (inputs copied into its static buffers
+    # every step); --eager runs the same body launch by launch from Python.
+    step_graph = TrainStep(model, crit, crit_ref, wd, gbuf, graph=not args.eager, max_gt=64)
+    step_eager = TrainStep(model, crit, crit_ref, wd, gbuf, graph=False)
 
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
@@ -181,20 +187,13 @@ def run_ours(args):
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def step(images, targets):
-        gbuf.zero_()
-        out = model(images)
-        ld = crit(out[0], targets)
-        ld2 = crit_ref(out[1], targets)
-        loss = sum(ld[k] * wd[k] for k in ld if k in wd) + sum(ld2[k] * wd[k] for k in ld2 if k in wd)
-        loss.backward()
-        gbuf.all_reduce_mean()          # no-op at world 1
-        return loss
+        return step_graph(images, targets)[0]
 
     def e2e_step():
-        images = host_images.to(dev, non_blocking=True)                                   # H2D inside the timed region
-        targets = [{k: v.to(dev, non_blocking=True) for k, v in t.items()} for t in targets_host]
-        loss = step(images, targets)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)                      # D2H of the step's result
+        # H2D inside the timed region: the pinned host image batch and the host target lists go straight into the step
+        loss = step_graph(host_images, targets_host)[0] if not args.eager else step_eager(
+            host_images.to(dev, non_blocking=True), [{k: v.to(dev, non_blocking=True) for k, v in t.items()} for t in targets_host])[0]
+        loss_host.copy_(loss.reshape(1), non_blocking=True)                               # D2H of the step's result
         return loss
 
     def timed(fn, n, prof=False):
@@ -234,8 +233,11 @@ def run_ours(args):
     for _ in range(2):
         e2e_step()
     ms_e2e, _, _ = timed(e2e_step, args.steps)
-    # separate profiled pass (events around every launch of the main kernel families) -> roofline numbers
-    ms_prof, _, fam = timed(lambda: step(dev_images, dev_targets), max(1, min(args.steps, 3)), prof=True)
+    # separate profiled EAGER pass (events around every launch of the main kernel families) -> roofline numbers; also counts the
+    # library's launches per step (a graph replay issues the same kernels without passing through the counter)
+    ms_prof, launches_prof, fam = timed(lambda: step_eager(dev_images, dev_targets), max(1, min(args.steps, 3)), prof=True)
+    if not args.eager:
+        launches = launches_prof // max(1, min(args.steps, 3)) * args.steps
     nprof = max(1, min(args.steps, 3))
 
     if rank != 0:
@@ -284,7 +286,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": imgs, "parallelism": "dp%d" % world,
                        "losses": "det(out[0]) + refine(out[1]), 12 Hungarian matchings/step, hung_match_ratio 5",
                        "l2": "working set per step >> 126 MB L2 (activations ~20 GB), no explicit flush",
-                       "weights": "random init (architecture default)"},
+                       "weights": "random init (architecture default)",
+                       "step": ("engine.TrainStep, whole step captured in a CUDA graph and replayed" if not args.eager else "engine.TrainStep, eager launches")},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_breakdown": breakdown, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
@@ -300,6 +303,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -86,21 +86,28 @@ class StaticTargets(PackedTargets):
         if max(sizes, default=0) > self.cap:
             raise ValueError("StaticTargets: %d targets in one image exceed the static capacity %d" % (max(sizes), self.cap))
         self.sizes, self.total = sizes, sum(sizes)
-        o = 0
-        for b, (t, n) in enumerate(zip(targets, sizes)):
+        tot, o = self.total, 0
+        for b, n in enumerate(sizes):
             self._h_off[b] = o
             self._h_cnt[b] = n
-            if n:
-                self._h_labels[o:o + n].copy_(t["labels"].reshape(-1))
-                self._h_boxes[o:o + n].copy_(t["boxes"].reshape(-1, 4))
-                if self._h_scores is not None:
-                    self._h_scores[o:o + n].copy_(t["scores"].reshape(-1))
             o += n
         self._h_off[self.B] = o
-        self.labels.copy_(self._h_labels, non_blocking=True)
-        self.boxes.copy_(self._h_boxes, non_blocking=True)
-        if self.scores is not None:
-            self.scores.copy_(self._h_scores, non_blocking=True)
+        if tot:
+            live = [t for t, n in zip(targets, sizes) if n]
+            on_dev = live[0]["labels"].is_cuda
+
+            def fill(dst, host, parts):
+                src = torch.cat(parts)
+                if on_dev:                                   # already resident: device-side pack, no host round trip
+                    dst[:tot].copy_(src)
+                else:
+                    host[:tot].copy_(src)
+                    dst[:tot].copy_(host[:tot], non_blocking=True)
+
+            fill(self.labels, self._h_labels, [t["labels"].reshape(-1) for t in live])
+            fill(self.boxes, self._h_boxes, [t["boxes"].reshape(-1, 4) for t in live])
+            if self.scores is not None:
+                fill(self.scores, self._h_scores, [t["scores"].reshape(-1) for t in live])
         self.offsets.copy_(self._h_off, non_blocking=True)
         self.counts.copy_(self._h_cnt, non_blocking=True)
         if self.img_label is not None and targets and "img_label" in targets[0]:
