@@ -44,6 +44,7 @@ struct EpiParams {
     int r_m1, r_m2;
     int tma_io;                   // epilogue tiles through TMA (else direct per-thread global access)
     int splits, kb_per_split;     // split-K
+    uint32_t fd_n[2], fd_m[2], fd_s[2], fd_b[2];   // {mul, shift} of the divisions by tiles_n / tiles_m / splits / batch2 (tile decode)
     int accum;                    // C += ... (residual aliased C on entry): every tile is stored with a reduce-add
     int tiles_m, tiles_n, num_tiles;
     int mode, mode_nl;            // EM_* epilogue specialisation for lead / non-lead (split-K) tiles
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull0 + 8 * b, 1);
-            mbar_init(tempty0 + 8 * b, NUM_EPI_WARPS);
+            mbar_init(tempty0 + 8 * b, NUM_EPI_WARPS / 2);    // one epilogue group (4 warps = 128 TMEM lanes) owns a buffer
         }
         for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(ebar0 + 8 * w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -293,13 +294,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     const uint32_t tmem_base = *tmem_slot;
 
     // tile -> coordinates (n fastest: consecutive CTAs share the A rows in L2)
+    // (every role decodes every tile: the divisions are multiply-shift with host-made magics -- real divisions cost each epilogue
+    //  warp ~5 dependent I2F/RCP/F2I chains per tile, which was a third of the per-tile epilogue latency on the K = 48 GEMMs)
+    auto fdiv = [](uint32_t n, const uint32_t (&fd)[2]) -> uint32_t { return (__umulhi(n, fd[0]) + n) >> fd[1]; };
     auto decode = [&](int t, int& m0, int& n0, int& b1, int& b2, int& kb0, int& nkb, int& split) {
-        const int tn = t % ep.tiles_n;
-        const int tm = (t / ep.tiles_n) % ep.tiles_m;
-        const int z = t / (ep.tiles_n * ep.tiles_m);
-        const int zb = z / ep.splits;
-        split = z % ep.splits;
-        b1 = zb / ep.batch2; b2 = zb % ep.batch2;
+        const uint32_t q1 = fdiv((uint32_t)t, ep.fd_n);
+        const int tn = t - (int)q1 * ep.tiles_n;
+        const uint32_t z = fdiv(q1, ep.fd_m);
+        const int tm = (int)q1 - (int)z * ep.tiles_m;
+        const uint32_t zb = fdiv(z, ep.fd_s);
+        split = (int)z - (int)zb * ep.splits;
+        const uint32_t q4 = fdiv(zb, ep.fd_b);
+        b1 = (int)q4; b2 = (int)zb - (int)q4 * ep.batch2;
         m0 = tm * BM; n0 = tn * BN;
         kb0 = split * ep.kb_per_split;
         nkb = min(ep.kb_per_split, total_kb - kb0);
@@ -374,7 +380,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         // ---------------- epilogue warps ----------------
         const int e = warp - EPI_WARP0;
         const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)   (hardware: warp%4)
-        const int half = e >> 2;                      // which 64-column super-chunks this warp owns
+        const int grp = e >> 2;                       // epilogue group: group g drains accumulator buffer g = every second tile of this CTA,
+                                                      // so two tiles' epilogue latency chains (TMEM load, math, fence, bulk store) overlap
         const uint32_t sBase = smem_u32(sEpi + e * EPI_SLABS * SLAB);
         // slab assignment: C (+ residual, which it overlays) needs 2 slabs when fp32 is involved, aux needs 1.
         //   footprint <= 2 slabs -> two alternating sets {0,1} / {2,3}: the bulk stores of one super-chunk drain while the next is
@@ -385,32 +392,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         const uint32_t ebar = ebar0 + 8 * e;
         const bool has_r = ep.residual != nullptr, has_xi = ep.aux_in != nullptr, has_xo = ep.aux_out != nullptr;
         const bool c32 = ep.c_dtype == SPE_DT_F32;
-        uint32_t eph = 0, ti = 0;
+        uint32_t eph = 0, use = 0;
         bool stores_pending = false;
-        for (int t = blockIdx.x; t < ep.num_tiles; t += gridDim.x, ++ti) {
+        for (int t = blockIdx.x + grp * (int)gridDim.x; t < ep.num_tiles; t += 2 * (int)gridDim.x, ++use) {
             int m0, n0, b1, b2, kb0, nkb, split;
             decode(t, m0, n0, b1, b2, kb0, nkb, split);
-            const uint32_t buf = ti & 1u, use = ti >> 1;
+            const uint32_t buf = (uint32_t)grp;
             const bool lead = split == 0;             // split-K: bias / residual contributed once
             const int mrow = m0 + quarter * 32;
             mbar_wait(tfull0 + 8 * buf, use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             bool arrived = false;
 #pragma unroll 1
-            for (int sc = half; sc < BN / 64; sc += 2) {
+            for (int sc = 0; sc < BN / 64; ++sc) {
                 const int nb = n0 + sc * 64;
                 const bool live = nb < ep.N && mrow < ep.M;
                 const bool loads = live && ep.tma_io && ((has_r && lead) || has_xi);
                 const uint32_t sRC = sBase + (alternate ? set * 2 * SLAB : 0u);
                 const uint32_t sX = alternate ? sRC + SLAB : sBase + 2 * SLAB;
-                if (live && ep.tma_io && stores_pending) {
-                    // earlier bulk stores must have finished READING the slabs that are refilled now
-                    if (lane == 0) {
-                        if (alternate) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    }
+                // earlier bulk stores must have finished READING the slabs before they are refilled.  With tile operands to load
+                // (residual / aux) that is now; otherwise only right before the first st.shared, after the TMEM load latency.
+                const bool need_drain = live && ep.tma_io && stores_pending;
+                auto drain = [&]() {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
-                }
+                };
+                if (need_drain && loads) drain();
                 if (loads && lane == 0) {
                     const bool two = nb + 32 < ep.N;
                     uint32_t bytes = 0;
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     if (has_xi) tma_load_4d(sX, &tmXi, ebar, nb, mrow, 0, 0);
                 }
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + (uint32_t)(sc * 64);
-                const bool last_sc = sc + 2 >= BN / 64;
+                const bool last_sc = sc + 1 >= BN / 64;
                 if (!live || !ep.tma_io) {
                     uint32_t r[64];
                     TMEM_LD_32x32b_X32(taddr, r);
@@ -453,6 +460,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
                         arrived = true;
                     }
+                    if (need_drain && !loads) drain();
                     switch (emode) {
                         case EM_F32: epi_fast<true, false, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
                         case EM_BF16: epi_fast<false, false, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
@@ -473,6 +481,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 // compiled to ~5000 SASS instructions per super-chunk and made every GEMM issue-bound in its epilogue.)
                 const bool use_bias = ep.bias != nullptr && lead, use_res = has_r && lead;
                 const int act = ep.act;
+                if (need_drain && !loads) drain();
 #pragma unroll 1
                 for (int gg = 0; gg < 4; ++gg) {                        // rolled: 4 x 16 accumulator columns (keeps the code in the I-cache)
                 uint32_t r[16];
@@ -702,6 +711,14 @@ int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB,
 
 }  // namespace
 
+// n / d == (umulhi(n, mul) + n) >> shr for every n < 2^31 (d >= 1):  shr = ceil(log2 d), mul = floor(2^32 (2^shr - d) / d) + 1
+static void fastdiv_magic(uint32_t d, uint32_t (&out)[2]) {
+    uint32_t shr = 0;
+    while ((1ull << shr) < d) ++shr;
+    out[0] = (uint32_t)((((1ull << shr) - d) << 32) / d + 1);
+    out[1] = shr;
+}
+
 // debugging / experiment switches, read once (getenv scans the whole environment: ~0.5 us each, five per call adds up at 1300 GEMMs a step)
 struct GemmEnv {
     bool bn256, direct_epilogue, generic_epilogue, no_splitk;
@@ -799,6 +816,8 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     ep.kb_per_split = (total_kb + splits - 1) / splits;
     splits = (total_kb + ep.kb_per_split - 1) / ep.kb_per_split;      // no empty split
     ep.splits = splits;
+    fastdiv_magic((uint32_t)ep.tiles_n, ep.fd_n); fastdiv_magic((uint32_t)ep.tiles_m, ep.fd_m);
+    fastdiv_magic((uint32_t)splits, ep.fd_s); fastdiv_magic((uint32_t)a->batch2, ep.fd_b);
     ep.num_tiles = (int)(tiles * splits);
     if (splits > 1 && !accum) SPE_CUDA(cudaMemsetAsync(a->C, 0, (size_t)a->M * a->N * 4, st));
     char tag[64];
