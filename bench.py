@@ -47,6 +47,47 @@ def synth_targets(batch, seed, repeat=5, det_classes=81):
     return out
 
 
+def cfg5_inputs(batch=256, queries=300, n_gt=1000, classes=81, seed=5):
+    """BASELINE configs[4] / SURVEY §8d cfg5: the Hungarian-matcher microbenchmark inputs (300 queries x 1000 GT, batch 256)."""
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(batch, queries, classes, generator=g)
+    boxes = torch.cat([torch.rand(batch, queries, 2, generator=g) * 0.8 + 0.1, torch.rand(batch, queries, 2, generator=g) * 0.48 + 0.02], -1)
+    targets = []
+    for _ in range(batch):
+        targets.append({"labels": torch.randint(0, classes, (n_gt,), generator=g),
+                        "boxes": torch.cat([torch.rand(n_gt, 2, generator=g) * 0.8 + 0.1, torch.rand(n_gt, 2, generator=g) * 0.48 + 0.02], -1)})
+    return logits, boxes, targets
+
+
+def matcher_microbench(dev, reps=5):
+    """GPU leg of cfg5: cost-matrix build + batched assignment for 256 images, device-resident inputs, CUDA events."""
+    from spe_b200 import criterion_ops as CO
+    logits, boxes, targets = cfg5_inputs()
+    lg, bx = logits.to(dev), boxes.to(dev)
+    packed = CO.pack_targets(targets, dev)
+    w = (2.0, 5.0, 2.0)
+    for _ in range(2):
+        CO.match(lg, bx, packed, w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        CO.match(lg, bx, packed, w)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps / logits.shape[0]
+    return {"us_per_img": us, "workload": "cfg5: 300 queries x 1000 GT, batch 256, cost build + assignment on the device (CUDA events, %d reps)" % reps}
+
+
+def matcher_cpu_us_per_img(n_img=24):
+    """reference matcher on the host: models/matcher.py:62-86 per image (cost matrix in torch + scipy LSAP), oracle port."""
+    from oracle import spe_oracle as O
+    logits, boxes, targets = cfg5_inputs(batch=n_img)
+    t0 = time.perf_counter()
+    O.hungarian_match(logits, boxes, targets)
+    return (time.perf_counter() - t0) * 1e6 / n_img
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -272,6 +313,7 @@ def run_ours(args):
     roof["gemm_frac_of_bf16_peak"] = g_tflops / peaks["tflops"]
     roof["hbm_families_gbs"] = hbm
 
+    matcher = matcher_microbench(dev)
     cpu = None
     if args.cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -280,7 +322,8 @@ def run_ours(args):
         cstep()
         dt = time.perf_counter() - t0
         cpu = {"value": 1.0 / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "oracle (fp32 PyTorch restatement, scipy LSAP): ONE cold bs=1 fwd+criteria+bwd step of the same config (%.1f s)" % dt}
+               "sample": "oracle (fp32 PyTorch restatement, scipy LSAP): ONE cold bs=1 fwd+criteria+bwd step of the same config (%.1f s)" % dt,
+               "matcher_us_per_img": matcher_cpu_us_per_img(), "matcher_sample": "cfg5 shapes, 24 images, torch cost matrix + scipy LSAP per image"}
     line = {"metric": "images/sec fwd+bwd", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": imgs, "parallelism": "dp%d" % world,
@@ -289,7 +332,8 @@ def run_ours(args):
                        "weights": "random init (architecture default)",
                        "step": ("engine.TrainStep, whole step captured in a CUDA graph and replayed" if not args.eager else "engine.TrainStep, eager launches")},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_breakdown": breakdown, "cpu_baseline": cpu}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_breakdown": breakdown, "matcher": matcher,
+            "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -101,6 +101,11 @@ int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk);
  * If pmean != NULL also writes the head-mean of P, f32 [B,Nq,Nk] (cait.py:658-667 cams). */
 int spe_softmax_fwd(const float* S, void* P, const uint8_t* mask, int B, int H, int Nq, int Nk, int64_t ldS,
                     int64_t ldP, float* pmean, void* stream);
+/* TSCAM_cait_two_branch.std_reweighting (cait.py:801-806, :827): CAMs from the per-head class-attention probabilities.
+ * P bf16 [B,H,Lq,ldP];  out f32 [B,C,N]:  out[b,c,n] = sum_h P[b,h,q0+c,k0+n] * w[b,h,c],
+ * w = (std_h - min_h std) / max_h(std - min_h std),  std_h = unbiased std over the N keys.  No gradient. */
+int spe_cam_std_reweight(const void* P_bf16, int B, int H, int Lq, int64_t ldP, int q0, int C, int k0, int N, float* out,
+                         void* stream);
 /* dS = P * (dP - sum_j P dP), bf16 in / bf16 out (dS may alias dP) */
 int spe_softmax_bwd(const void* P, const void* dP, void* dS, int B, int H, int Nq, int Nk, int64_t ldP, void* stream);
 

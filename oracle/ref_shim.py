@@ -126,7 +126,8 @@ def build_reference_model(cfg, params=None):
     ref = load_reference()
     # img_size such that the initial pos_embed has pos_grid tokens
     img_size = (cfg.pos_grid[0] * cfg.patch, cfg.pos_grid[1] * cfg.patch)
-    body = ref.cait.TSCAM_cait(img_size=img_size, patch_size=cfg.patch, embed_dim=cfg.embed_dim, depth=cfg.depth,
+    body_cls = ref.cait.TSCAM_cait_two_branch if getattr(cfg, "two_branch", False) else ref.cait.TSCAM_cait
+    body = body_cls(img_size=img_size, patch_size=cfg.patch, embed_dim=cfg.embed_dim, depth=cfg.depth,
                                num_heads=cfg.num_heads, mlp_ratio=cfg.mlp_ratio, qkv_bias=True,
                                norm_layer=partial(nn.LayerNorm, eps=cfg.ln_eps_backbone), init_scale=1e-5,
                                depth_token_only=cfg.depth_token_only, num_classes=cfg.img_classes,

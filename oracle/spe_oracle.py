@@ -59,6 +59,8 @@ class SPEConfig:
     num_refines: int = 1
     ln_eps_backbone: float = 1e-6
     ln_eps_detr: float = 1e-5
+    two_branch: bool = False      # TSCAM_cait_two_branch (cait.py:674-831): blocks_det branch, norm_det, std-reweighted CAMs;
+                                  # the tap is then taken after block layer_to_det - 1 (cait.py:776-777)
 
     @property
     def d_model(self) -> int:
@@ -127,7 +129,22 @@ def param_shapes(cfg: SPEConfig) -> Dict[str, Tuple[int, ...]]:
     lin(bb + "head", C, D)
     lin(bb + "cls_head", 1, D)
     lin(bb + "cls_head_multi_cls", C, D)
-    ln(bb + "norm_to_det", D)
+    if cfg.two_branch:
+        for j in range(cfg.depth - cfg.layer_to_det):                 # cait.py:707-713
+            p = f"{bb}blocks_det.{j}."
+            s[p + "gamma_1"] = (D,)
+            s[p + "gamma_2"] = (D,)
+            ln(p + "norm1", D)
+            ln(p + "norm2", D)
+            lin(p + "attn.qkv", 3 * D, D)
+            lin(p + "attn.proj", D, D)
+            lin(p + "attn.proj_l", H, H)
+            lin(p + "attn.proj_w", H, H)
+            lin(p + "mlp.fc1", Dh, D)
+            lin(p + "mlp.fc2", D, Dh)
+        ln(bb + "norm_det", D)
+    else:
+        ln(bb + "norm_to_det", D)
 
     Dd, Fd = cfg.d_model, cfg.ffn
     for i in range(cfg.enc_layers):
@@ -268,6 +285,15 @@ def class_attention(p, pre, u, H, T):
     return _lin(p, pre + "proj", o), a
 
 
+def std_reweighting(cam: torch.Tensor) -> torch.Tensor:
+    """TSCAM_cait_two_branch.std_reweighting (cait.py:801-806): cam [B,H,C,N] per-head class-attention maps -> [B,C,N];
+    head weight = the head's (unbiased) std over the N keys, min-max normalised over the heads."""
+    std = cam.std(dim=-1, keepdim=True)
+    std = std - std.min(dim=1, keepdim=True)[0]
+    std = std / std.max(dim=1, keepdim=True)[0]
+    return (cam * std).sum(1)
+
+
 def tscam_forward(p, cfg: SPEConfig, images: torch.Tensor):
     """TSCAM_cait.forward (cait.py:615-670) -> dict(x_logits, x_cls_logits, cams_cls, x_patch[B,D,h,w])."""
     bb = "backbone.0.body."
@@ -284,8 +310,16 @@ def tscam_forward(p, cfg: SPEConfig, images: torch.Tensor):
         pre = f"{bb}blocks.{i}."
         x = x + p[pre + "gamma_1"] * talking_heads_attention(p, pre + "attn.", _ln(p, pre + "norm1", x, eps), cfg.num_heads)
         x = x + p[pre + "gamma_2"] * mlp_gelu(p, pre + "mlp.", _ln(p, pre + "norm2", x, eps))
-        if i == cfg.layer_to_det:
+        if not cfg.two_branch and i == cfg.layer_to_det:
             x_feat = _ln(p, bb + "norm_to_det", x, eps)
+        if cfg.two_branch and i + 1 == cfg.layer_to_det:                   # cait.py:776-777
+            x_feat = x
+    if cfg.two_branch:                                                     # cait.py:779-782
+        for j in range(cfg.depth - cfg.layer_to_det):
+            pre = f"{bb}blocks_det.{j}."
+            x_feat = x_feat + p[pre + "gamma_1"] * talking_heads_attention(p, pre + "attn.", _ln(p, pre + "norm1", x_feat, eps), cfg.num_heads)
+            x_feat = x_feat + p[pre + "gamma_2"] * mlp_gelu(p, pre + "mlp.", _ln(p, pre + "norm2", x_feat, eps))
+        x_feat = _ln(p, bb + "norm_det", x_feat, eps)
     cls = torch.cat([p[bb + "cls_token"].expand(B, -1, -1), p[bb + "extra_cls_token"].expand(B, -1, -1)], 1)
     T = 1 + C
     amap0 = None
@@ -300,7 +334,10 @@ def tscam_forward(p, cfg: SPEConfig, images: torch.Tensor):
     xa = _ln(p, bb + "norm", torch.cat([cls, x], 1), eps)
     x_logits = _lin(p, bb + "cls_head", xa[:, 1:1 + C]).squeeze(-1)
     x_cls_logits = _lin(p, bb + "cls_head_multi_cls", xa[:, 0])
-    cams = amap0.mean(1)[:, 1:1 + C, 1 + C:].reshape(B, C, h, w)
+    if cfg.two_branch:
+        cams = std_reweighting(amap0[:, :, 1:1 + C, 1 + C:]).reshape(B, C, h, w)      # cait.py:827-828
+    else:
+        cams = amap0.mean(1)[:, 1:1 + C, 1 + C:].reshape(B, C, h, w)
     x_patch = x_feat.transpose(1, 2).reshape(B, D, h, w)
     return {"x_logits": x_logits, "x_cls_logits": x_cls_logits, "cams_cls": cams, "x_patch": x_patch}
 

@@ -44,6 +44,7 @@ _SIGS = {
                                       c_p, c_l, c_p]),
     "spe_talking_softmax_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i]),
     "spe_softmax_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p]),
+    "spe_cam_std_reweight": (c_i, [c_p, c_i, c_i, c_i, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "spe_softmax_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_p]),
     "spe_layerscale_bwd": (c_i, [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
     "spe_colsum_bf16": (c_i, [c_p, c_l, c_i, c_l, c_p, c_p]),

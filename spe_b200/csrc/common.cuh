@@ -57,6 +57,13 @@ static inline int spe_num_sms() {
     return n;
 }
 
+// talking-heads kernels for head counts outside {2, 4, 8} (talking_generic.cu)
+int spe_talking_generic_grid(int B, int Nq);
+int spe_talking_generic_fwd(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats, int B, int H, int Nq,
+                            int Nk, long long ldS, long long ldA, cudaStream_t st);
+int spe_talking_generic_bwd(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B, int H,
+                            int Nq, int Nk, long long ldS, long long ldA, float* part, cudaStream_t st);
+
 __device__ __forceinline__ float bf16_to_f(uint16_t v) { return __uint_as_float(((uint32_t)v) << 16); }
 __device__ __forceinline__ uint16_t f_to_bf16(float f) {
     __nv_bfloat16 b = __float2bfloat16_rn(f);

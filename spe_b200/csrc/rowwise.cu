@@ -1290,7 +1290,11 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(co
         case 2: return talking_fwd_launch<2>(S, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
         case 4: return talking_fwd_launch<4>(S, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
         case 8: return talking_fwd_launch<8>(S, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
-        default: SPE_FAIL("spe_talking_softmax_fwd: unsupported head count %d (2/4/8)", H);
+        default: {
+            // other head counts (H = 16 of CaiT-M36, 6 / 12 of the XS variants): CUDA-core formulation in talking_generic.cu
+            SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 6.0, ST(stream));
+            return spe_talking_generic_fwd(S, A, Wl, bl, Ww, bw, stats, B, H, Nq, Nk, ldS, ldA, ST(stream));
+        }
     }
 }
 
@@ -1352,7 +1356,17 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd(co
         case 2: return talking_bwd_launch<2>(S, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
         case 4: return talking_bwd_launch<4>(S, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
         case 8: return talking_bwd_launch<8>(S, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
-        default: SPE_FAIL("spe_talking_softmax_bwd: unsupported head count %d (2/4/8)", H);
+        default: {
+            const int grid = spe_talking_generic_grid(B, Nq);
+            {
+                SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * 8.0, ST(stream));
+                if (spe_talking_generic_bwd(S, dA, dS, Wl, bl, Ww, stats, B, H, Nq, Nk, ldS, ldA, workspace, ST(stream))) return -1;
+            }
+            const int NP = 2 * H * H + 2 * H;
+            talking_bwd_finalize_kernel<<<(NP + 7) / 8, 256, 0, ST(stream)>>>(workspace, grid, H, dWl, dbl, dWw, dbw);
+            SPE_LAUNCHED();
+            return 0;
+        }
     }
 }
 

@@ -5,7 +5,7 @@ from functools import partial
 import torch
 from torch import nn
 
-from .models.cait import TSCAM_cait
+from .models.cait import TSCAM_cait, TSCAM_cait_two_branch
 from .models.cait_backbone import Backbone, Joiner
 from .models.conditional_detr import ConditionalDETR_Refine, SetCriterion, SetCriterionRefine
 from .models.matcher import HungarianMatcher
@@ -16,9 +16,10 @@ from .models.transformer import Transformer
 def build_detector(cfg, device="cuda"):
     """cfg: any object with the attributes of oracle.spe_oracle.SPEConfig (embed_dim, depth, num_heads, img_classes,
     patch, layer_to_det, depth_token_only, mlp_ratio, pos_grid, det_heads, ffn, enc_layers, dec_layers, num_queries,
-    det_classes, num_refines, ln_eps_backbone)."""
+    det_classes, num_refines, ln_eps_backbone[, two_branch])."""
     img_size = (cfg.pos_grid[0] * cfg.patch, cfg.pos_grid[1] * cfg.patch)
-    body = TSCAM_cait(img_size=img_size, patch_size=cfg.patch, embed_dim=cfg.embed_dim, depth=cfg.depth, num_heads=cfg.num_heads,
+    body_cls = TSCAM_cait_two_branch if getattr(cfg, "two_branch", False) else TSCAM_cait
+    body = body_cls(img_size=img_size, patch_size=cfg.patch, embed_dim=cfg.embed_dim, depth=cfg.depth, num_heads=cfg.num_heads,
                       mlp_ratio=cfg.mlp_ratio, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=cfg.ln_eps_backbone), init_scale=1e-5,
                       depth_token_only=cfg.depth_token_only, num_classes=cfg.img_classes, layer_to_det=cfg.layer_to_det)
     body.img_size = img_size

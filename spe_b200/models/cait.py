@@ -2,7 +2,8 @@
 
 Same class names, constructor arguments and state_dict keys as the reference:
   Attention_talking_head (cait.py:344-393), LayerScale_Block (:396-416), Multi_Class_Attention (:91-139),
-  LayerScale_Block_CA_MultiClass (:311-328), PatchEmbedMine (:518-528), TSCAM_cait (:531-670).
+  LayerScale_Block_CA_MultiClass (:311-328), PatchEmbedMine (:518-528), TSCAM_cait (:531-670),
+  TSCAM_cait_two_branch (:674-831, the backbone the reference's launch scripts train).
 Internally activations are token-major: fp32 residual stream [B,N,D], bf16 GEMM operands.
 Dropout / DropPath / attention dropout are p=0 only (BASELINE configs): a non-zero rate raises.
 """
@@ -15,7 +16,8 @@ from .. import ops
 from ..util.misc import NestedTensor
 
 __all__ = ["Mlp", "PatchEmbedMine", "Attention_talking_head", "LayerScale_Block", "Multi_Class_Attention",
-           "LayerScale_Block_CA_MultiClass", "TSCAM_cait", "tscam_cait_xxs24", "tscam_cait_s24", "tscam_cait_m36"]
+           "LayerScale_Block_CA_MultiClass", "TSCAM_cait", "TSCAM_cait_two_branch", "tscam_cait_xxs24", "tscam_cait_xxs36", "tscam_cait_s24", "tscam_cait_m36",
+           "tscam_cait_xxs24_two_branch", "tscam_cait_xxs36_two_branch"]
 
 
 def _no_drop(**rates):
@@ -115,8 +117,9 @@ class Multi_Class_Attention(nn.Module):
         k = ops.linear(u16, self.k.weight, self.k.bias)
         v = ops.linear(u16, self.v.weight, self.v.bias)
         if want_map:
-            o, pmean = ops.attention(q, k, v, self.num_heads, self.scale, want_mean=True)
-            self.attention_map = pmean          # head-mean [B,T,T+N] (all cait.py:658-667 consumes)
+            # True: head-mean f32 [B,T,T+N] (all cait.py:658-667 consumes);  "probs": per-head bf16 [B,H,T,ld] (std_reweighting, :827)
+            o, amap = ops.attention(q, k, v, self.num_heads, self.scale, want_mean=want_map)
+            self.attention_map = amap
             return o
         return ops.attention(q, k, v, self.num_heads, self.scale)
 
@@ -239,6 +242,71 @@ class TSCAM_cait(nn.Module):
         return {"x_logits": x_logits, "x_cls_logits": x_cls_logits, "cams_cls": cams_cls, "x_patch": x_patch}
 
 
+class TSCAM_cait_two_branch(TSCAM_cait):
+    """TSCAM_cait_two_branch (cait.py:674-831): the trunk keeps feeding the class-attention / CAM branch, while a copy of its
+    last depth - layer_to_det talking-heads blocks (`blocks_det`, initialised from the trunk by init_blocks_det_weight,
+    :724-726) continues from the tap after block layer_to_det - 1 (:776-777) and, through `norm_det`, feeds the detector.
+    CAMs are the std-reweighted per-head class-attention maps of class-attention block 0 (:801-806, :827).
+    state_dict keys = the reference's: everything of the trunk + blocks_det.* + norm_det.* (no norm_to_det)."""
+
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4.0,
+                 qkv_bias=False, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0, norm_layer=nn.LayerNorm,
+                 global_pool=None, block_layers=LayerScale_Block, block_layers_token=LayerScale_Block_CA_MultiClass,
+                 Patch_layer=PatchEmbedMine, act_layer=nn.GELU, Attention_block=Attention_talking_head, Mlp_block=Mlp, init_scale=1e-4,
+                 Attention_block_token_only=Multi_Class_Attention, Mlp_block_token_only=Mlp, depth_token_only=2, mlp_ratio_clstk=4.0,
+                 layer_to_det=23, **kwargs):
+        super().__init__(img_size=img_size, patch_size=patch_size, in_chans=in_chans, num_classes=num_classes, embed_dim=embed_dim, depth=depth,
+                         num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop_rate=drop_rate,
+                         attn_drop_rate=attn_drop_rate, drop_path_rate=drop_path_rate, norm_layer=norm_layer, global_pool=global_pool,
+                         block_layers=block_layers, block_layers_token=block_layers_token, Patch_layer=Patch_layer, act_layer=act_layer,
+                         Attention_block=Attention_block, Mlp_block=Mlp_block, init_scale=init_scale,
+                         Attention_block_token_only=Attention_block_token_only, Mlp_block_token_only=Mlp_block_token_only,
+                         depth_token_only=depth_token_only, mlp_ratio_clstk=mlp_ratio_clstk, layer_to_det=layer_to_det)
+        del self.norm_to_det
+        assert 1 <= layer_to_det <= depth, "two-branch tap: after block layer_to_det - 1 (cait.py:776-777)"
+        self.blocks_det = nn.ModuleList([
+            block_layers(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate,
+                         attn_drop=attn_drop_rate, drop_path=drop_path_rate, norm_layer=norm_layer, act_layer=act_layer,
+                         Attention_block=Attention_block, Mlp_block=Mlp_block, init_values=init_scale) for _ in range(layer_to_det, depth)])
+        self.norm_det = norm_layer(embed_dim)
+        self.blocks_det.apply(self._init_weights)
+        self.norm_det.apply(self._init_weights)
+
+    def init_blocks_det_weight(self):
+        """cait.py:724-726: the detection branch starts as a copy of the trunk's last blocks."""
+        for i in range(1, 1 + len(self.blocks_det)):
+            self.blocks_det[-i].load_state_dict(self.blocks[-i].state_dict(), strict=True)
+
+    def forward(self, tensor_list: NestedTensor):
+        x_img, _ = tensor_list.decompose()
+        B, _, H, W = x_img.shape
+        p = self.patch_size
+        h, w = H // p, W // p
+        C = self.num_classes
+        ph, pw = self.img_size[0] // p, self.img_size[1] // p
+        pos = ops.BicubicTokensFn.apply(self.pos_embed, ph, pw, h, w)                                   # cait.py:731-745, :767
+        x = ops.PatchEmbedFn.apply(x_img.float(), self.patch_embed.proj.weight, self.patch_embed.proj.bias, pos, p)
+        x_feat = None
+        for i, blk in enumerate(self.blocks):                                                            # :773-777
+            x = blk(x)
+            if i + 1 == self.layer_to_det:
+                x_feat = x
+        for blk in self.blocks_det:                                                                      # :779-780
+            x_feat = blk(x_feat)
+        x_feat, x_feat16 = ops.layernorm(x_feat, self.norm_det.weight, self.norm_det.bias, self.norm_det.eps, want_f32=True)   # :782
+        cls = torch.cat((self.cls_token.expand(B, -1, -1), self.extra_cls_token.expand(B, -1, -1)), dim=1)
+        for i, blk in enumerate(self.blocks_token_only):                                                 # :787-789
+            cls = blk(x, cls, want_map=("probs" if i == 0 else False))
+        xa = ops.layernorm(cls, self.norm.weight, self.norm.bias, self.norm.eps)                         # :796 (class tokens only are consumed)
+        x_logits = ops.linear(xa[:, 1:1 + C].contiguous(), self.cls_head.weight, self.cls_head.bias, out_f32=True).squeeze(-1)
+        x_cls_logits = ops.linear(xa[:, 0].contiguous(), self.cls_head_multi_cls.weight, self.cls_head_multi_cls.bias, out_f32=True)
+        probs = self.blocks_token_only[0].attn.get_attention_map()                                       # per head, bf16 [B,heads,1+C,ld]
+        cams_cls = ops.cam_std_reweight(probs, 1, C, 1 + C, h * w).reshape(B, C, h, w)                   # :827-828
+        x_patch = x_feat.transpose(1, 2).reshape(B, self.embed_dim, h, w)
+        x_patch.tokens32, x_patch.tokens16 = x_feat, x_feat16
+        return {"x_logits": x_logits, "x_cls_logits": x_cls_logits, "cams_cls": cams_cls, "x_patch": x_patch}
+
+
 def _tscam(embed_dim, depth, num_heads, init_scale, **kw):
     kw.setdefault("img_size", 384)
     kw.pop("pretrained", None)
@@ -251,6 +319,11 @@ def tscam_cait_xxs24(**kw):
     return _tscam(192, 24, 4, 1e-5, **kw)
 
 
+def tscam_cait_xxs36(**kw):
+    """TSCAM_cait_XXS36 (cait.py:1595-1613 hyper-parameters)."""
+    return _tscam(192, 36, 4, 1e-5, **kw)
+
+
 def tscam_cait_s24(**kw):
     """TSCAM_cait with the S24 hyper-parameters of cait.py:1860-1880."""
     return _tscam(384, 24, 8, 1e-5, **kw)
@@ -259,3 +332,22 @@ def tscam_cait_s24(**kw):
 def tscam_cait_m36(**kw):
     """TSCAM_cait with the M36 hyper-parameters of cait.py:1905-1925."""
     return _tscam(768, 36, 16, 1e-6, **kw)
+
+
+def _tscam_two_branch(embed_dim, depth, num_heads, init_scale, **kw):
+    kw.setdefault("img_size", 384)
+    kw.pop("pretrained", None)
+    m = TSCAM_cait_two_branch(patch_size=16, embed_dim=embed_dim, depth=depth, num_heads=num_heads, mlp_ratio=4, qkv_bias=True,
+                              norm_layer=partial(nn.LayerNorm, eps=1e-6), init_scale=init_scale, depth_token_only=2, **kw)
+    m.init_blocks_det_weight()                       # cait.py:1663 does this once the (pretrained) trunk weights are in place
+    return m
+
+
+def tscam_cait_xxs24_two_branch(**kw):
+    """TSCAM_cait_two_branch with the XXS24 hyper-parameters."""
+    return _tscam_two_branch(192, 24, 4, 1e-5, **kw)
+
+
+def tscam_cait_xxs36_two_branch(**kw):
+    """TSCAM_cait_XXS36_Two_Branch (cait.py:1631-1664), the backbone of scripts/run_coco17.py:26 / run_voc0712.py:28."""
+    return _tscam_two_branch(192, 36, 4, 1e-5, **kw)

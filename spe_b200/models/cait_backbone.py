@@ -13,6 +13,9 @@ BACKBONES = {
     "TSCAM_cait_XXS24": (cait.tscam_cait_xxs24, 192),
     "TSCAM_cait_S24": (cait.tscam_cait_s24, 384),
     "TSCAM_cait_M36": (cait.tscam_cait_m36, 768),
+    "TSCAM_cait_XXS36": (cait.tscam_cait_xxs36, 192),                            # cait.py:1595
+    "TSCAM_cait_XXS36_Two_Branch": (cait.tscam_cait_xxs36_two_branch, 192),      # cait.py:1631; scripts/run_coco17.py:26, run_voc0712.py:28
+    "TSCAM_cait_XXS24_Two_Branch": (cait.tscam_cait_xxs24_two_branch, 192),
 }
 
 

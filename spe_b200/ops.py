@@ -537,6 +537,8 @@ class AttentionFn(torch.autograd.Function):
         S = torch.empty((B, H, Lq, ld), dtype=torch.float32, device=q.device)
         _qk_logits(q, k, H, scale, S, ld, q2, k2)
         P = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=q.device)
+        want_probs = want_mean == "probs"              # per-head probabilities (bf16 [B,H,Lq,ld]) instead of their head mean
+        want_mean = bool(want_mean) and not want_probs
         pmean = torch.empty((B, Lq, Lk), dtype=torch.float32, device=q.device) if want_mean else None
         check(lib().spe_softmax_fwd(ptr(S), ptr(P), ptr(mask_u8), B, H, Lq, Lk, ld, ld, ptr(pmean), stream()))
         del S
@@ -544,6 +546,10 @@ class AttentionFn(torch.autograd.Function):
         _pv(P, v, H, out, Lq, Lk, ld)
         ctx.save_for_backward(q, k, v, q2, k2, P)
         ctx.H, ctx.scale, ctx.ld = H, scale, ld
+        if want_probs:
+            Pv = P.detach()
+            ctx.mark_non_differentiable(Pv)
+            return out, Pv
         if want_mean:
             ctx.mark_non_differentiable(pmean)
             return out, pmean
@@ -566,7 +572,17 @@ class AttentionFn(torch.autograd.Function):
 
 
 def attention(q, k, v, H, scale, mask_u8=None, q2=None, k2=None, want_mean=False):
+    """want_mean: False | True (also return the head-mean map f32 [B,Lq,Lk]) | "probs" (also return P bf16 [B,H,Lq,ld])."""
     return AttentionFn.apply(q, k, v, q2, k2, mask_u8, H, scale, want_mean)
+
+
+def cam_std_reweight(P, q0, C, k0, N):
+    """TSCAM_cait_two_branch.std_reweighting (cait.py:801-806) on per-head probabilities P bf16 [B,H,Lq,ld] -> f32 [B,C,N]."""
+    _need_cuda(P)
+    B, H, Lq, ld = P.shape
+    out = torch.empty((B, C, N), dtype=torch.float32, device=P.device)
+    check(lib().spe_cam_std_reweight(ptr(P), B, H, Lq, ld, q0, C, k0, N, ptr(out), stream()))
+    return out
 
 
 class TalkingHeadsAttentionFn(torch.autograd.Function):

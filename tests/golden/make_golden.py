@@ -90,5 +90,11 @@ if __name__ == "__main__":
     tiny = O.tiny_config()
     run_case("tiny_det", tiny, 2, 48, 64, 0, ("labels", "boxes", "cardinality"), 2.0, repeat=2)
     run_case("tiny_refine", tiny, 2, 48, 64, 1, ("labels", "boxes", "cardinality"), 0.5, repeat=1, refine_idx=1)
+    # TSCAM_cait_two_branch (the scripts' backbone, cait.py:674-831): 3 trunk blocks, tap after block 1, 2 blocks_det
+    run_case("tiny_two_branch", O.tiny_config(depth=3, layer_to_det=1, two_branch=True, num_heads=4), 2, 48, 64, 2,
+             ("labels", "boxes", "cardinality"), 2.0, repeat=1)
+    # CaiT-M36 head geometry (16 heads x 48, BASELINE configs[3]) on a 2-block trunk: exercises the H = 16 talking-heads kernels
+    run_case("tiny_h16", O.tiny_config(embed_dim=768, num_heads=16, pos_grid=(4, 5)), 2, 48, 64, 4,
+             ("labels", "boxes", "cardinality"), 2.0, repeat=1)
     run_case("cfg1_xxs24_224", O.CFG1, 1, 224, 224, 0, ("labels", "boxes", "cardinality"), 2.0, repeat=1, max_gt=2)
     lsap_vectors()

@@ -259,7 +259,7 @@ def test_attention_fn(K, masked, two):
         assert rel_err(a, b_) < 3e-2, rel_err(a, b_)
 
 
-@pytest.mark.parametrize("H,N,dh", [(2, 35, 64), (4, 196, 48), (8, 130, 48)])
+@pytest.mark.parametrize("H,N,dh", [(2, 35, 64), (4, 196, 48), (8, 130, 48), (16, 300, 48), (6, 77, 48), (12, 261, 32)])   # 16 = CaiT-M36 (cfg4), 6/12: generic-H kernels
 def test_talking_heads_attention_fn(K, H, N, dh):
     g = torch.Generator().manual_seed(15)
     B, D = 2, H * dh
@@ -364,6 +364,25 @@ def test_match_cost_and_lsap_vs_oracle():
         i, j = O.lsap(cref)
         rows = torch.nonzero(r2g[b] >= 0).flatten()
         assert torch.equal(rows, i) and torch.equal(r2g[b][rows].long(), j)
+
+
+def test_matcher_cfg5_full_size_bit_exact():
+    """BASELINE configs[4]: 300 queries x 1000 GT, batch 256, through HungarianMatcher.forward (the reference API).  Every image is
+    compared with the oracle (reference cost arithmetic in torch + scipy) -- indices bit-exact -- plus the size-independent
+    properties of an assignment: min(Q, G) pairs, no query and no GT used twice, predictions sorted (scipy's transposed branch)."""
+    import bench
+    from oracle import spe_oracle as O
+    from spe_b200.models.matcher import HungarianMatcher
+    logits, boxes, targets = bench.cfg5_inputs()
+    m = HungarianMatcher(cost_class=2, cost_bbox=5, cost_giou=2)
+    got = m({"pred_logits": logits.to(dev()), "pred_boxes": boxes.to(dev())}, [{k: v.to(dev()) for k, v in t.items()} for t in targets])
+    assert len(got) == 256
+    ref = O.hungarian_match(logits, boxes, targets)
+    for (i, j), (ri, rj) in zip(got, ref):
+        assert i.dtype == torch.int64 and j.dtype == torch.int64 and not i.is_cuda
+        assert len(i) == 300 and len(set(i.tolist())) == 300 and len(set(j.tolist())) == 300
+        assert torch.equal(i, torch.arange(300))
+        assert torch.equal(i, ri) and torch.equal(j, rj)
 
 
 def test_lsap_kernel_bit_exact_on_scipy_vectors(golden_dir):

@@ -36,7 +36,7 @@ def maxerr(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
-@pytest.mark.parametrize("name", ["tiny_det", "tiny_refine", "cfg1_xxs24_224"])
+@pytest.mark.parametrize("name", ["tiny_det", "tiny_refine", "tiny_two_branch", "tiny_h16", "cfg1_xxs24_224"])
 def test_detector_matches_reference_golden(golden_dir, name):
     gold = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
     cfg, params, images, targets, model, crit = _setup(gold)
@@ -118,9 +118,10 @@ def _oracle_refine(params, cfg, images, targets, gold):
     return out, ld, None, {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}, loss.detach()
 
 
-def test_state_dict_keys_match_reference(golden_dir):
+@pytest.mark.parametrize("name", ["tiny_det", "tiny_two_branch"])
+def test_state_dict_keys_match_reference(golden_dir, name):
     from spe_b200 import factory
-    gold = torch.load(os.path.join(golden_dir, "tiny_det.pt"), weights_only=False)
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
     cfg = O.SPEConfig(**gold["meta"]["cfg"])
     model = factory.build_detector(cfg, "cuda")
     assert set(model.state_dict().keys()) == set(gold["grad_fingerprint"].keys())
