@@ -8,8 +8,11 @@ Internal layout is batch-first token-major ([B,N,D]; the reference is sequence-f
 streams + bf16 GEMM operands.  Only what the reference actually runs is implemented: post-norm layers, ReLU
 FFN, dropout 0, return_intermediate decoder.  Work the reference repeats is done once:
   * query_pos-only projections are batch invariant -> computed on [Q,D] and broadcast in the GEMM epilogue;
-  * the memory-side cross-attention projections (k_content, v, k_pos) are identical in both decoder passes
-    (SURVEY F7 / a10) -> cached across the passes of one forward;
+  * the decoder passes of forward_refine (transformer.py:147-155: same weights, same memory, different query embeddings) run as
+    ONE pass over the concatenated queries [B, P*Q, D]: every token-wise GEMM / LayerNorm and the cross-attention see P*Q
+    queries per image (queries never interact there), self-attention runs per pass on the [B*P, Q, D] view.  The memory-side
+    cross-attention projections (k_content, v, k_pos) are thereby computed once, and the ~100 small
+    launches of a decoder layer are issued once instead of once per pass;
   * the per-head [content | position] concat (transformer.py:408-414) is never materialised: the logits are
     two QK^T GEMMs accumulated into one S.
 """
@@ -142,16 +145,22 @@ class TransformerDecoderLayer(nn.Module):
             kc = lin(memory16, self.ca_kcontent_proj.weight, self.ca_kcontent_proj.bias)
         return kc, v, kpos16
 
-    def forward_tokens(self, tgt32, tgt16, mem_side, mask_u8, qpos16, qsine16, is_first):
-        """forward_post (transformer.py:355-427).  tgt [B,Q,D]; qpos16 [Q,D] (batch invariant); qsine16 [B,Q,D]."""
+    def forward_tokens(self, tgt32, tgt16, mem_side, mask_u8, qpos16, qsine16, is_first, passes=1):
+        """forward_post (transformer.py:355-427).  tgt [B,P*Q,D] (P decoder passes side by side); qpos16 [P*Q,D] (batch
+        invariant); qsine16 [B,P*Q,D]."""
         lin = ops.linear
+        B, PQ, D = tgt16.shape
         # ---- self-attention: q = Wqc tgt + Wqp qpos, k likewise, v = Wv tgt  (:368-381)
         qp = lin(qpos16, self.sa_qpos_proj.weight, self.sa_qpos_proj.bias, out_f32=True)        # [Q,D] fp32
         kp = lin(qpos16, self.sa_kpos_proj.weight, self.sa_kpos_proj.bias, out_f32=True)
         q = lin(tgt16, self.sa_qcontent_proj.weight, self.sa_qcontent_proj.bias, residual=qp)
         k = lin(tgt16, self.sa_kcontent_proj.weight, self.sa_kcontent_proj.bias, residual=kp)
         v = lin(tgt16, self.sa_v_proj.weight, self.sa_v_proj.bias)
-        a = self.self_attn.core(q, k, v)
+        if passes > 1:                                  # queries attend to each other within their own pass only
+            Q = PQ // passes
+            a = self.self_attn.core(q.view(B * passes, Q, D), k.view(B * passes, Q, D), v.view(B * passes, Q, D)).view(B, PQ, D)
+        else:
+            a = self.self_attn.core(q, k, v)
         x = lin(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, residual=tgt32, out_f32=True)
         t32, t16 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, want_f32=True)
         # ---- conditional cross-attention (:389-423)
@@ -183,14 +192,21 @@ class TransformerDecoder(nn.Module):
         for layer_id in range(num_layers - 1):
             self.layers[layer_id + 1].ca_qpos_proj = None                      # transformer.py:203-204
 
-    def forward_tokens(self, memory16, pos16, mask_u8, query_embed, batch, mem_cache):
-        """TransformerDecoder.forward (transformer.py:206-250) -> hs fp32 [L,B,Q,D] (+ .tokens16), reference points [B,Q,2]."""
-        B, (Q, D) = batch, query_embed.shape
-        qpos16 = ops.cast_bf16(query_embed)                                     # [Q,D], batch invariant (:127 .repeat)
-        ref = self.ref_point_head(qpos16).sigmoid()                             # [Q,2]  (:216-217)
-        sine = ops.query_sine_embed(ref, self.d_model)                          # [Q,D]
-        out32 = torch.zeros((B, Q, D), dtype=torch.float32, device=query_embed.device)     # tgt = 0 (:129)
-        out16 = torch.zeros((B, Q, D), dtype=torch.bfloat16, device=query_embed.device)
+    def forward_tokens(self, memory16, pos16, mask_u8, query_embeds, batch, mem_cache=None):
+        """TransformerDecoder.forward (transformer.py:206-250) for P query-embedding tables at once (one decoder pass of the
+        reference each) -> per pass: hs fp32 [L,B,Q,D] (+ .tokens16) and reference points [B,Q,2]."""
+        if isinstance(query_embeds, torch.Tensor):
+            query_embeds = [query_embeds]
+        mem_cache = {} if mem_cache is None else mem_cache
+        P = len(query_embeds)
+        B, (Q, D) = batch, query_embeds[0].shape
+        query_embed = torch.cat(list(query_embeds), 0) if P > 1 else query_embeds[0]     # [P*Q, D]
+        PQ = P * Q
+        qpos16 = ops.cast_bf16(query_embed)                                     # batch invariant (:127 .repeat)
+        ref = self.ref_point_head(qpos16).sigmoid()                             # [P*Q,2]  (:216-217)
+        sine = ops.query_sine_embed(ref, self.d_model)                          # [P*Q,D]
+        out32 = torch.zeros((B, PQ, D), dtype=torch.float32, device=query_embed.device)     # tgt = 0 (:129)
+        out16 = torch.zeros((B, PQ, D), dtype=torch.bfloat16, device=query_embed.device)
         inter32, inter16 = [], []
         for layer_id, layer in enumerate(self.layers):
             if layer_id == 0:
@@ -200,13 +216,18 @@ class TransformerDecoder(nn.Module):
             qsine16 = ops.cast_bf16(qsine.contiguous())
             if layer_id not in mem_cache:
                 mem_cache[layer_id] = layer.memory_side(memory16, pos16, layer_id == 0)
-            out32, out16 = layer.forward_tokens(out32, out16, mem_cache[layer_id], mask_u8, qpos16, qsine16, layer_id == 0)
+            out32, out16 = layer.forward_tokens(out32, out16, mem_cache[layer_id], mask_u8, qpos16, qsine16, layer_id == 0, passes=P)
             n32, n16 = ops.layernorm(out32, self.norm.weight, self.norm.bias, self.norm.eps, want_f32=True)     # shared norm (:239)
             inter32.append(n32)
             inter16.append(n16)
-        hs = torch.stack(inter32)
-        hs.tokens16 = torch.stack(inter16)
-        return hs, ref.unsqueeze(0).expand(B, -1, -1)
+        hs_list, ref_list = [], []
+        for p in range(P):                                                      # un-interleave the passes (the stack is the copy)
+            sl = slice(p * Q, (p + 1) * Q)
+            hs = torch.stack([t[:, sl] for t in inter32])
+            hs.tokens16 = torch.stack([t[:, sl] for t in inter16])
+            hs_list.append(hs)
+            ref_list.append(ref[sl].unsqueeze(0).expand(B, -1, -1))
+        return hs_list, ref_list
 
 
 class Transformer(nn.Module):
@@ -254,16 +275,11 @@ class Transformer(nn.Module):
         pos32, pos16 = self._tokens(pos_embed)
         mask_u8 = mask.flatten(1).to(torch.uint8).contiguous()
         mem32, mem16 = self.encoder.forward_tokens(src32, src16, pos32, mask_u8)
-        cache = {}
-        hs0, ref0 = self.decoder.forward_tokens(mem16, pos16, mask_u8, query_embed, B, cache)
         if queries_embed_refine is None:
-            return hs0, ref0
-        hs, refs = [hs0], [ref0]
-        for qe in queries_embed_refine:
-            h, r = self.decoder.forward_tokens(mem16, pos16, mask_u8, qe.weight, B, cache)
-            hs.append(h)
-            refs.append(r)
-        return hs, refs
+            hs, refs = self.decoder.forward_tokens(mem16, pos16, mask_u8, [query_embed], B)
+            return hs[0], refs[0]
+        # forward_refine (:147-155): the num_refines + 1 decoder passes run side by side (see the module docstring)
+        return self.decoder.forward_tokens(mem16, pos16, mask_u8, [query_embed] + [qe.weight for qe in queries_embed_refine], B)
 
 
 def _get_clones(module, N):
