@@ -72,6 +72,34 @@ typedef struct {
 int spe_gemm(const spe_gemm_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused multi-head attention forward (TMA -> tcgen05 QK^T -> softmax in registers -> tcgen05 PV; logits stay in TMEM):
+ *   O[b,:,h] = softmax_keys( scale * (Q_h K_h^T [+ Q2_h K2_h^T]) + key_padding_mask ) V_h
+ * Replaces nn.MultiheadAttention's core (transformer.py:280) and models/attention.py:345-378 -- incl. the conditional
+ * cross-attention, whose per-head [content | position] concat (transformer.py:408-414) is the sum of two QK^T products.
+ * Heads are packed along the feature dim: q [B,Lq,H*d], k [B,Lk,H*d], v [B,Lk,H*dv] (bf16; *_ld = token stride,
+ * *_sb = image stride, in elements; head h starts at column h*d).  d, d2, dv: multiples of 16, <= 64.
+ * mask u8 [B,Lk] (1 = padded key) or NULL.  out bf16 [B,Lq,H*dv].  Optional outputs: P bf16 [B,H,Lq,ldP] (normalised
+ * probabilities, zero in the padding columns; what the backward GEMMs consume), lse f32 [B,H,Lq] = log2-domain
+ * log-sum-exp of the scaled logits (p = 2^(scale*log2e*s - lse)).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int B, H, Lq, Lk;
+    int d, d2, dv;                         /* per-head dims: QK segment 1, QK segment 2 (0 if q2 == NULL), V */
+    const void* q; int64_t q_ld, q_sb;
+    const void* k; int64_t k_ld, k_sb;
+    const void* v; int64_t v_ld, v_sb;
+    const void* q2; int64_t q2_ld, q2_sb;  /* optional second QK segment (NULL: none)                        */
+    const void* k2; int64_t k2_ld, k2_sb;
+    const uint8_t* mask;
+    float scale;
+    void* out; int64_t out_ld, out_sb;
+    void* P; int64_t ldP;                  /* optional */
+    float* lse;                            /* optional */
+} spe_attention_args;
+
+int spe_attention_fwd(const spe_attention_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Row-wise / elementwise kernels of the backbone + transformer
  * ------------------------------------------------------------------------------------------- */
 /* LayerNorm over the last dim (cait.py:414-415 eps 1e-6; transformer.py:284,288,384,425,427 eps 1e-5).

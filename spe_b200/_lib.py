@@ -30,6 +30,15 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("B", c_i), ("H", c_i), ("Lq", c_i), ("Lk", c_i), ("d", c_i), ("d2", c_i), ("dv", c_i),
+        ("q", c_p), ("q_ld", c_l), ("q_sb", c_l), ("k", c_p), ("k_ld", c_l), ("k_sb", c_l), ("v", c_p), ("v_ld", c_l), ("v_sb", c_l),
+        ("q2", c_p), ("q2_ld", c_l), ("q2_sb", c_l), ("k2", c_p), ("k2_ld", c_l), ("k2_sb", c_l),
+        ("mask", c_p), ("scale", c_f), ("out", c_p), ("out_ld", c_l), ("out_sb", c_l), ("P", c_p), ("ldP", c_l), ("lse", c_p),
+    ]
+
+
 _SIGS = {
     "spe_version": (c_i, []),
     "spe_launch_count": (c_l, []),
@@ -37,6 +46,7 @@ _SIGS = {
     "spe_prof_collect": (c_i, [c_p, c_p, c_p]),
     "spe_prof_family_count": (c_i, []),
     "spe_gemm": (c_i, [C.POINTER(GemmArgs), c_p]),
+    "spe_attention_fwd": (c_i, [C.POINTER(AttentionArgs), c_p]),
     "spe_layernorm_fwd": (c_i, [c_p, c_p, c_p, c_f, c_l, c_i, c_p, c_p, c_p, c_p, c_p]),
     "spe_layernorm_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
     "spe_talking_softmax_fwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p]),
@@ -115,7 +125,7 @@ def launch_count():
     return int(lib().spe_launch_count())
 
 
-PROF_FAMILIES = ["gemm", "talking_softmax_fwd", "talking_softmax_bwd", "softmax", "layernorm", "matcher_lsap", "other", "gemm_attention"]
+PROF_FAMILIES = ["gemm", "talking_softmax_fwd", "talking_softmax_bwd", "softmax", "layernorm", "matcher_lsap", "other", "gemm_attention", "attention_fused"]
 
 
 def prof_enable(on):

@@ -1,0 +1,439 @@
+// Fused multi-head attention forward for sm_100a:  O = softmax(scale (Q K^T [+ Q2 K2^T]) + key_padding_mask) V
+//   (nn.MultiheadAttention core, transformer.py:280;  models/attention.py:345-378 incl. the conditional cross-attention's
+//    [content | position] concat expressed as two accumulated QK^T products, transformer.py:408-414)
+//
+// One CTA per (128-query block, head, image); the logits never touch HBM:
+//   warp 0      : TMA producer -- Q (once), then K / V 128-key blocks through mbarrier rings (SWIZZLE_128B tiles);
+//   warp 1      : one thread issues tcgen05.mma.cta_group::1.kind::f16:  S = Q K^T (+ Q2 K2^T) into a double-buffered TMEM
+//                 accumulator (2 x 128 columns), and O += P V (A = P from shared memory, B = V consumed MN-major straight from
+//                 the packed [B, Lk, H*dv] activation) into 64 further TMEM columns;
+//   warp 2      : TMEM allocator;
+//   warps 4..7  : softmax, one thread per query row (no cross-lane reductions): tcgen05.ld of its S row, exp2 with the
+//                 statistics, bf16 P into the swizzled K-major shared tile that the PV MMA (and the TMA store of P) read.
+// Two sweeps over the keys: sweep 1 = row statistics (online max / sum on the S tiles), sweep 2 = exact normalised P -> PV.
+// The second QK^T costs 1/8 of the MUFU-bound softmax time and buys: no accumulator rescaling, and P that is already final when
+// it is produced -- it is written once (bf16, TMA bulk stores) for the backward GEMMs, which is the only N^2 HBM traffic left
+// in the forward (was: S f32 write + read, P write + read).  lse2 = max + log2(sum) per row is saved for a fused backward.
+#include "common.cuh"
+#include <cuda.h>
+#include <string.h>
+
+int spe_make_tmap_bf16(CUtensorMap* tm, const void* ptr, int major, int rows, int K, int64_t ld, int64_t sb1, int64_t sb2, int batch1, int batch2, int box_rows);
+void* spe_tmap_encode_fn();
+
+namespace {
+
+constexpr int BQ = 128;                 // query rows per CTA (= TMEM lanes)
+constexpr int BKV = 128;                // keys per block
+constexpr int KS = 2;                   // K ring stages
+constexpr int VS = 2;                   // V ring stages
+constexpr uint32_t TILE_B = 128 * 64 * 2;      // one [128 rows x 64 cols] bf16 SWIZZLE_128B tile (Q, K, half of P)
+constexpr uint32_t VBOX_B = 64 * 64 * 2;       // one MN-major V box: 64 keys x 64 (dv, zero filled beyond dv)
+constexpr int AT_THREADS = 256;
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+struct AttnParams {
+    int Lq, Lk, H;
+    int nkb;                 // key blocks
+    int two;                 // second QK segment present
+    int ksteps1, ksteps2;    // UMMA k-steps (16 elements) of the two segments
+    int dv;                  // value head dim (multiple of 16, <= 64)
+    float scale2;            // scale * log2(e)
+    const uint8_t* mask;     // [B, Lk] or null
+    uint16_t* out; long long out_ld, out_sb;     // [B, Lq, H*dv] bf16
+    float* lse;              // [B, H, Lq] or null
+    int store_p, ldP;
+};
+
+__device__ __forceinline__ uint32_t a_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void a_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void a_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void a_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool a_mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void a_mbar_wait(uint32_t bar, uint32_t parity) {
+    if (a_mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!a_mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void a_tma_load(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void a_tma_store(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ uint64_t a_umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;       // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void a_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void a_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float a_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+#define A_TMEM_LD32(taddr, r)                                                                                 \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+        : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]),     \
+          "=r"((r)[8]), "=r"((r)[9]), "=r"((r)[10]), "=r"((r)[11]), "=r"((r)[12]), "=r"((r)[13]), "=r"((r)[14]), "=r"((r)[15]), \
+          "=r"((r)[16]), "=r"((r)[17]), "=r"((r)[18]), "=r"((r)[19]), "=r"((r)[20]), "=r"((r)[21]), "=r"((r)[22]), "=r"((r)[23]), \
+          "=r"((r)[24]), "=r"((r)[25]), "=r"((r)[26]), "=r"((r)[27]), "=r"((r)[28]), "=r"((r)[29]), "=r"((r)[30]), "=r"((r)[31]) \
+        : "r"(taddr))
+#define A_TMEM_LD16(taddr, r)                                                                                 \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                     \
+        : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]),     \
+          "=r"((r)[8]), "=r"((r)[9]), "=r"((r)[10]), "=r"((r)[11]), "=r"((r)[12]), "=r"((r)[13]), "=r"((r)[14]), "=r"((r)[15]) \
+        : "r"(taddr))
+
+// smem layout (all tiles 1024-byte aligned):  Q | Q2 | K[KS] | K2[KS] | V[VS] (2 boxes each) | P[2] (2 tiles each) | barriers | mask bits
+constexpr uint32_t OFF_Q = 0, OFF_Q2 = OFF_Q + TILE_B, OFF_K = OFF_Q2 + TILE_B, OFF_K2 = OFF_K + KS * TILE_B, OFF_V = OFF_K2 + KS * TILE_B,
+                   OFF_P = OFF_V + VS * 2 * VBOX_B, OFF_BAR = OFF_P + 2 * 2 * TILE_B;
+constexpr int NBAR = 1 + 2 * KS + 2 * VS + 4 + 4 + 1;      // qfull, kfull/kempty, vfull/vempty, sfull/sempty[2], pfull/pempty[2], ofull
+constexpr uint32_t OFF_TSLOT = OFF_BAR + NBAR * 8, OFF_MBITS = OFF_TSLOT + 16;
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ2,
+                                                                 const __grid_constant__ CUtensorMap tmK2, const __grid_constant__ CUtensorMap tmP,
+                                                                 const AttnParams ap) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = a_smem_u32(smem);
+    const uint32_t bar0 = sbase + OFF_BAR;
+    const uint32_t qfull = bar0, kfull0 = qfull + 8, kempty0 = kfull0 + 8 * KS, vfull0 = kempty0 + 8 * KS, vempty0 = vfull0 + 8 * VS,
+                   sfull0 = vempty0 + 8 * VS, sempty0 = sfull0 + 16, pfull0 = sempty0 + 16, pempty0 = pfull0 + 16, ofull = pempty0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TSLOT);
+    uint32_t* mbits = reinterpret_cast<uint32_t*>(smem + OFF_MBITS);          // [nkb][4]: bit set = key masked (padding or >= Lk)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+    const int nkb = ap.nkb;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+        a_mbar_init(qfull, 1);
+        for (int s = 0; s < KS; ++s) { a_mbar_init(kfull0 + 8 * s, 1); a_mbar_init(kempty0 + 8 * s, 1); }
+        for (int s = 0; s < VS; ++s) { a_mbar_init(vfull0 + 8 * s, 1); a_mbar_init(vempty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) {
+            a_mbar_init(sfull0 + 8 * s, 1); a_mbar_init(sempty0 + 8 * s, 4);
+            a_mbar_init(pfull0 + 8 * s, 1); a_mbar_init(pempty0 + 8 * s, 1);
+        }
+        a_mbar_init(ofull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // key mask bits: one ballot per 32 keys
+    for (int w = warp; w < nkb * 4; w += AT_THREADS / 32) {
+        const int j = w * 32 + lane;
+        const bool masked = j >= ap.Lk || (ap.mask != nullptr && ap.mask[(long long)b * ap.Lk + j] != 0);
+        const uint32_t bits = __ballot_sync(0xffffffffu, masked);
+        if (lane == 0) mbits[w] = bits;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tO = tmem_base + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            a_mbar_expect_tx(qfull, ap.two ? 2 * TILE_B : TILE_B);
+            a_tma_load(sbase + OFF_Q, &tmQ, qfull, 0, q0, h, b);
+            if (ap.two) a_tma_load(sbase + OFF_Q2, &tmQ2, qfull, 0, q0, h, b);
+            uint32_t kit = 0;
+            for (int sweep = 0; sweep < 2; ++sweep) {
+                for (int j = 0; j < nkb; ++j, ++kit) {
+                    const int ks = kit % KS;
+                    a_mbar_wait(kempty0 + 8 * ks, ((kit / KS) & 1u) ^ 1u);
+                    a_mbar_expect_tx(kfull0 + 8 * ks, ap.two ? 2 * TILE_B : TILE_B);
+                    a_tma_load(sbase + OFF_K + ks * TILE_B, &tmK, kfull0 + 8 * ks, 0, j * BKV, h, b);
+                    if (ap.two) a_tma_load(sbase + OFF_K2 + ks * TILE_B, &tmK2, kfull0 + 8 * ks, 0, j * BKV, h, b);
+                    if (sweep == 1) {
+                        const int vs = j % VS;
+                        a_mbar_wait(vempty0 + 8 * vs, ((j / VS) & 1u) ^ 1u);
+                        a_mbar_expect_tx(vfull0 + 8 * vs, 2 * VBOX_B);
+                        // V tile MN-major: two boxes of [64 keys x 64 (dv, zero filled beyond dv)]
+                        a_tma_load(sbase + OFF_V + vs * 2 * VBOX_B, &tmV, vfull0 + 8 * vs, 0, j * BKV, h, b);
+                        a_tma_load(sbase + OFF_V + vs * 2 * VBOX_B + VBOX_B, &tmV, vfull0 + 8 * vs, 0, j * BKV + 64, h, b);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            // instruction descriptors: D f32, A/B bf16; S: both K-major, N = 128;  PV: A K-major, B MN-major, N = dv
+            const uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+            const uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(ap.dv >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+            a_mbar_wait(qfull, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t kit = 0, sit = 0;
+            auto issue_s = [&]() {
+                const int ks = kit % KS;
+                const uint32_t sb = sit & 1u;
+                a_mbar_wait(kfull0 + 8 * ks, (kit / KS) & 1u);
+                a_mbar_wait(sempty0 + 8 * sb, ((sit >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t qa = sbase + OFF_Q, ka = sbase + OFF_K + ks * TILE_B;
+                for (int k = 0; k < ap.ksteps1; ++k) a_umma(tS + sb * 128, a_umma_desc(qa + k * 32, 0, 1024), a_umma_desc(ka + k * 32, 0, 1024), IDESC_S, k != 0);
+                if (ap.two) {
+                    const uint32_t qa2 = sbase + OFF_Q2, ka2 = sbase + OFF_K2 + ks * TILE_B;
+                    for (int k = 0; k < ap.ksteps2; ++k) a_umma(tS + sb * 128, a_umma_desc(qa2 + k * 32, 0, 1024), a_umma_desc(ka2 + k * 32, 0, 1024), IDESC_S, 1u);
+                }
+                a_commit(kempty0 + 8 * ks);
+                a_commit(sfull0 + 8 * sb);
+                ++kit; ++sit;
+            };
+            for (int j = 0; j < nkb; ++j) issue_s();                  // sweep 1
+            issue_s();                                                // sweep 2: S_0
+            for (int j = 0; j < nkb; ++j) {
+                if (j + 1 < nkb) issue_s();                           // S_{j+1} overlaps the softmax of block j
+                const uint32_t pb = (uint32_t)j & 1u;
+                const int vs = j % VS;
+                a_mbar_wait(pfull0 + 8 * pb, ((uint32_t)j >> 1) & 1u);
+                a_mbar_wait(vfull0 + 8 * vs, ((uint32_t)j / VS) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t pa = sbase + OFF_P + pb * 2 * TILE_B, va = sbase + OFF_V + vs * 2 * VBOX_B;
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    // P: K-major, 64-key halves (k / 4), 32 bytes per k-step inside the 128-byte swizzle row
+                    // V: MN-major, 64-key halves, 16 key rows = 2 groups of 8 rows (SBO 1024 B) per k-step
+                    const uint64_t ad = a_umma_desc(pa + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024);
+                    const uint64_t bd = a_umma_desc(va + (k >> 2) * VBOX_B + (k & 3) * 2048, VBOX_B, 1024);
+                    a_umma(tO, ad, bd, IDESC_PV, (j | k) != 0 ? 1u : 0u);
+                }
+                a_commit(vempty0 + 8 * vs);
+                a_commit(pempty0 + 8 * pb);
+            }
+            a_commit(ofull);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ---------------- softmax warps: thread = query row ----------------
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;                   // row inside the block = TMEM lane
+        const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+        const bool tid0 = threadIdx.x == 128;
+        float m = -INFINITY, l = 0.f;
+        uint32_t sit = 0;
+        // ---- sweep 1: statistics
+        for (int j = 0; j < nkb; ++j, ++sit) {
+            const uint32_t sb = sit & 1u;
+            a_mbar_wait(sfull0 + 8 * sb, (sit >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float mx = -INFINITY;
+            float part = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t r[32];
+                A_TMEM_LD32(tS + tlane + sb * 128 + c4 * 32, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c4 == 3) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) a_mbar_arrive(sempty0 + 8 * sb);
+                }
+                const uint32_t bits = mbits[j * 4 + c4];
+                float x[32];
+                float cmx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    x[i] = ((bits >> i) & 1u) ? -INFINITY : __uint_as_float(r[i]) * ap.scale2;
+                    cmx = fmaxf(cmx, x[i]);
+                }
+                const float mn = fmaxf(mx, cmx);
+                if (mn > -INFINITY) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc += a_ex2(x[i] - mn);
+                    part = part * a_ex2(mx - mn) + acc;
+                    mx = mn;
+                }
+            }
+            const float mn = fmaxf(m, mx);
+            if (mn > -INFINITY) {
+                l = l * a_ex2(m - mn) + part * a_ex2(mx - mn);
+                m = mn;
+            }
+        }
+        const float lse2 = m + log2f(l);                       // p = 2^(x - lse2)
+        if (ap.lse != nullptr && q0 + row < ap.Lq) ap.lse[((long long)b * ap.H + h) * ap.Lq + q0 + row] = lse2;
+        // ---- sweep 2: P -> shared (-> HBM), PV by the MMA warp
+        for (int j = 0; j < nkb; ++j, ++sit) {
+            const uint32_t sb = sit & 1u, pb = (uint32_t)j & 1u;
+            a_mbar_wait(sfull0 + 8 * sb, (sit >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t pk[64];                                   // 128 probabilities, packed bf16 pairs
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t r[32];
+                A_TMEM_LD32(tS + tlane + sb * 128 + c4 * 32, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c4 == 3) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) a_mbar_arrive(sempty0 + 8 * sb);
+                }
+                const uint32_t bits = mbits[j * 4 + c4];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = ((bits >> i) & 1u) ? 0.f : a_ex2(fmaf(__uint_as_float(r[i]), ap.scale2, -lse2));
+                    const float p1 = ((bits >> (i + 1)) & 1u) ? 0.f : a_ex2(fmaf(__uint_as_float(r[i + 1]), ap.scale2, -lse2));
+                    pk[c4 * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+                }
+            }
+            // the P buffer is free once the PV MMA of block j-2 has retired and its bulk store has finished reading it
+            a_mbar_wait(pempty0 + 8 * pb, (((uint32_t)j >> 1) & 1u) ^ 1u);
+            if (tid0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint32_t pa = sbase + OFF_P + pb * 2 * TILE_B + (uint32_t)row * 128u;
+            const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {                     // 16-byte chunk g: keys 8g..8g+7; half g / 8, chunk-in-row g % 8
+                const uint32_t addr = pa + (uint32_t)(g >> 3) * TILE_B + ((((uint32_t)g & 7u) ^ sw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]), "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid0) {
+                if (ap.store_p) {
+                    a_tma_store(&tmP, sbase + OFF_P + pb * 2 * TILE_B, j * BKV, q0, h, b);
+                    if (j * BKV + 64 < ap.ldP) a_tma_store(&tmP, sbase + OFF_P + pb * 2 * TILE_B + TILE_B, j * BKV + 64, q0, h, b);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                a_mbar_arrive(pfull0 + 8 * pb);
+            }
+        }
+        // ---- output
+        a_mbar_wait(ofull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            uint32_t o[64];
+            A_TMEM_LD16(tO + tlane, o);
+            A_TMEM_LD16(tO + tlane + 16, o + 16);
+            A_TMEM_LD16(tO + tlane + 32, o + 32);
+            A_TMEM_LD16(tO + tlane + 48, o + 48);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (q0 + row < ap.Lq) {
+                uint16_t* dst = ap.out + (long long)b * ap.out_sb + (long long)(q0 + row) * ap.out_ld + (long long)h * ap.dv;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    if (g * 8 < ap.dv) {
+                        const uint4 v = make_uint4(pack_bf16x2(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1])),
+                                                   pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
+                                                   pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
+                                                   pack_bf16x2(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7])));
+                        *reinterpret_cast<uint4*>(dst + g * 8) = v;
+                    }
+                }
+            }
+        }
+        if (tid0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int spe_attention_fwd(const spe_attention_args* a, void* stream) {
+    SPE_CHECK(a && a->q && a->k && a->v && a->out, "spe_attention_fwd: null argument");
+    SPE_CHECK(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "spe_attention_fwd: bad shape");
+    SPE_CHECK(a->d > 0 && a->d <= 64 && a->d % 16 == 0, "spe_attention_fwd: head dim %d must be a multiple of 16 and <= 64", a->d);
+    SPE_CHECK(a->dv > 0 && a->dv <= 64 && a->dv % 16 == 0, "spe_attention_fwd: value head dim %d must be a multiple of 16 and <= 64", a->dv);
+    const bool two = a->q2 != nullptr;
+    SPE_CHECK(!two || (a->k2 && a->d2 > 0 && a->d2 <= 64 && a->d2 % 16 == 0), "spe_attention_fwd: bad second QK segment");
+    SPE_CHECK((a->out_ld % 8) == 0 && (a->out_sb % 8) == 0 && ((a->H * a->dv) % 8) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+              "spe_attention_fwd: output must be 16-byte regular");
+    CUtensorMap tQ, tK, tV, tQ2, tK2, tP;
+    memset(&tQ2, 0, sizeof(tQ2)); memset(&tK2, 0, sizeof(tK2)); memset(&tP, 0, sizeof(tP));
+    // 4-D maps (d, token, head, image); K-major boxes [64 x 128 tokens], the V map is MN-major: boxes [64 (dv) x 64 keys]
+    if (spe_make_tmap_bf16(&tQ, a->q, SPE_MAJOR_K, a->Lq, a->d, a->q_ld, a->q_sb, a->d, a->B, a->H, BQ)) return -1;
+    if (spe_make_tmap_bf16(&tK, a->k, SPE_MAJOR_K, a->Lk, a->d, a->k_ld, a->k_sb, a->d, a->B, a->H, BKV)) return -1;
+    if (spe_make_tmap_bf16(&tV, a->v, SPE_MAJOR_MN, a->dv, a->Lk, a->v_ld, a->v_sb, a->dv, a->B, a->H, 64)) return -1;
+    if (two) {
+        if (spe_make_tmap_bf16(&tQ2, a->q2, SPE_MAJOR_K, a->Lq, a->d2, a->q2_ld, a->q2_sb, a->d2, a->B, a->H, BQ)) return -1;
+        if (spe_make_tmap_bf16(&tK2, a->k2, SPE_MAJOR_K, a->Lk, a->d2, a->k2_ld, a->k2_sb, a->d2, a->B, a->H, BKV)) return -1;
+    }
+    if (a->P) {
+        PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(spe_tmap_encode_fn());
+        SPE_CHECK(enc, "cuTensorMapEncodeTiled not available");
+        SPE_CHECK(a->ldP % 8 == 0 && a->ldP >= a->Lk && (reinterpret_cast<uintptr_t>(a->P) & 15) == 0, "spe_attention_fwd: P must be 16-byte regular, ldP >= Lk");
+        cuuint64_t gdim[4] = {(cuuint64_t)a->ldP, (cuuint64_t)a->Lq, (cuuint64_t)a->H, (cuuint64_t)a->B};
+        cuuint64_t gstr[3] = {(cuuint64_t)a->ldP * 2, (cuuint64_t)a->Lq * a->ldP * 2, (cuuint64_t)a->H * a->Lq * a->ldP * 2};
+        cuuint32_t box[4] = {64, 128, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->P, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SPE_CHECK(r == CUDA_SUCCESS, "spe_attention_fwd: tensor map for P failed (%d)", (int)r);
+    }
+    AttnParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.Lq = a->Lq; ap.Lk = a->Lk; ap.H = a->H;
+    ap.nkb = (a->Lk + BKV - 1) / BKV;
+    ap.two = two ? 1 : 0;
+    ap.ksteps1 = a->d / 16; ap.ksteps2 = two ? a->d2 / 16 : 0;
+    ap.dv = a->dv;
+    ap.scale2 = a->scale * LOG2E_F;
+    ap.mask = a->mask;
+    ap.out = reinterpret_cast<uint16_t*>(a->out); ap.out_ld = a->out_ld; ap.out_sb = a->out_sb;
+    ap.lse = a->lse;
+    ap.store_p = a->P ? 1 : 0;
+    ap.ldP = (int)a->ldP;
+    const size_t smem = OFF_MBITS + (size_t)ap.nkb * 16 + 1024;
+    SPE_CHECK(smem <= 232448, "spe_attention_fwd: Lk = %d too long for the mask table", a->Lk);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        SPE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // algorithmic bytes: Q, K, V (+Q2, K2) read, O written, P written (bf16) -- the logits never reach HBM
+    const double bytes = 2.0 * a->B * a->H * ((double)a->Lq * (a->d + (two ? a->d2 : 0) + a->dv) + (double)a->Lk * (a->d + (two ? a->d2 : 0) + a->dv)) +
+                         (a->P ? 2.0 * a->B * a->H * (double)a->Lq * a->Lk : 0.0);
+    SpeProfScope prof(SPE_FAM_ATTN_FUSED, bytes, st);
+    dim3 grid((a->Lq + BQ - 1) / BQ, a->H, a->B);
+    attn_fwd_kernel<<<grid, AT_THREADS, smem, st>>>(tQ, tK, tV, tQ2, tK2, tP, ap);
+    SPE_LAUNCHED();
+    return 0;
+}

@@ -29,7 +29,7 @@ extern std::atomic<int64_t> g_spe_launches;
 
 // ---- optional per-family device timing (bench.py roofline): CUDA events around launches on their stream ----
 enum { SPE_FAM_GEMM = 0, SPE_FAM_TALKING_FWD = 1, SPE_FAM_TALKING_BWD = 2, SPE_FAM_SOFTMAX = 3, SPE_FAM_LAYERNORM = 4,
-       SPE_FAM_MATCHER = 5, SPE_FAM_OTHER = 6, SPE_FAM_GEMM_ATTN = 7, SPE_FAM_COUNT = 8 };
+       SPE_FAM_MATCHER = 5, SPE_FAM_OTHER = 6, SPE_FAM_GEMM_ATTN = 7, SPE_FAM_ATTN_FUSED = 8, SPE_FAM_COUNT = 9 };
 extern bool g_spe_prof_on;
 int spe_prof_begin_(int fam, double work, cudaStream_t st, const char* tag = nullptr);
 void spe_prof_end_(int idx, cudaStream_t st);

@@ -711,6 +711,12 @@ int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB,
 
 }  // namespace
 
+// tensor-map helpers shared with the fused attention kernels (attn_fused.cu)
+int spe_make_tmap_bf16(CUtensorMap* tm, const void* ptr, int major, int rows, int K, int64_t ld, int64_t sb1, int64_t sb2, int batch1, int batch2, int box_rows) {
+    return make_tmap(tm, ptr, major, rows, K, ld, sb1, sb2, batch1, batch2, box_rows);
+}
+void* spe_tmap_encode_fn() { return reinterpret_cast<void*>(get_encode()); }
+
 // n / d == (umulhi(n, mul) + n) >> shr for every n < 2^31 (d >= 1):  shr = ceil(log2 d), mul = floor(2^32 (2^shr - d) / d) + 1
 static void fastdiv_magic(uint32_t d, uint32_t (&out)[2]) {
     uint32_t shr = 0;

@@ -59,29 +59,31 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm backward: warp per row, per-lane column accumulators for dw/db, one atomic per column per CTA
+// LayerNorm backward: warp per row, per-lane column accumulators for dw/db, one atomic per column per CTA.
+// NCH = number of 128-column chunks, compile time: the run-time-bounded version kept 4 x LN_MAXCH float4 arrays live (164 registers,
+// ONE 8-warp CTA per SM -> ~5 MB of loads in flight chip-wide, a third of what HBM needs).  D = 384 (NCH 3) now runs 3 CTAs per SM.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __restrict__ dy16, const float* __restrict__ dy32,
+template <int NCH>
+__global__ void __launch_bounds__(256, (NCH <= 2 ? 4 : (NCH == 3 ? 3 : (NCH <= 6 ? 2 : 1)))) layernorm_bwd_kernel(const uint16_t* __restrict__ dy16, const float* __restrict__ dy32,
                                                             const float* __restrict__ dres, const float* __restrict__ x,
                                                             const float* __restrict__ w, const float* __restrict__ mean_i,
                                                             const float* __restrict__ rstd_i, long long rows, int D, float* __restrict__ dx,
                                                             float* __restrict__ dw, float* __restrict__ db) {
     extern __shared__ float sm[];     // [2][D] per-CTA column sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int nch = (D + 127) / 128;
     for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) sm[c] = 0.f;
     __syncthreads();
-    float4 aw[LN_MAXCH], ab[LN_MAXCH];
+    float4 aw[NCH], ab[NCH];
 #pragma unroll
-    for (int k = 0; k < LN_MAXCH; ++k) { aw[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = aw[k]; }
+    for (int k = 0; k < NCH; ++k) { aw[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = aw[k]; }
     for (long long row = (long long)blockIdx.x * nw + warp; row < rows; row += (long long)gridDim.x * nw) {
         const float mean = mean_i[row], rstd = rstd_i[row];
-        float4 g[LN_MAXCH], xh[LN_MAXCH];
+        float4 g[NCH], xh[NCH];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < LN_MAXCH; ++k) {
+        for (int k = 0; k < NCH; ++k) {
             const int c = k * 128 + lane * 4;
-            if (k < nch && c < D) {
+            if (c < D) {
                 float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (dy32) d = *reinterpret_cast<const float4*>(dy32 + row * D + c);
                 if (dy16) {
@@ -101,9 +103,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __re
         }
         const float c1 = warp_sum(s1) / (float)D, c2 = warp_sum(s2) / (float)D;
 #pragma unroll
-        for (int k = 0; k < LN_MAXCH; ++k) {
+        for (int k = 0; k < NCH; ++k) {
             const int c = k * 128 + lane * 4;
-            if (k < nch && c < D) {
+            if (c < D) {
                 float4 o;
                 o.x = rstd * (g[k].x - c1 - xh[k].x * c2);
                 o.y = rstd * (g[k].y - c1 - xh[k].y * c2);
@@ -118,9 +120,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const uint16_t* __re
         }
     }
 #pragma unroll
-    for (int k = 0; k < LN_MAXCH; ++k) {
+    for (int k = 0; k < NCH; ++k) {
         const int c = k * 128 + lane * 4;
-        if (k < nch && c < D) {
+        if (c < D) {
             atomicAdd(&sm[c + 0], aw[k].x); atomicAdd(&sm[c + 1], aw[k].y); atomicAdd(&sm[c + 2], aw[k].z); atomicAdd(&sm[c + 3], aw[k].w);
             atomicAdd(&sm[D + c + 0], ab[k].x); atomicAdd(&sm[D + c + 1], ab[k].y); atomicAdd(&sm[D + c + 2], ab[k].z); atomicAdd(&sm[D + c + 3], ab[k].w);
         }
@@ -1188,11 +1190,22 @@ extern "C" __attribute__((visibility("default"))) int spe_layernorm_bwd(const vo
                                  const float* rstd, int64_t rows, int D, float* dx, float* dw, float* db, void* stream) {
     SPE_CHECK((dy_bf16 || dy_f32) && x && w && mean && rstd && dx && rows > 0, "spe_layernorm_bwd: bad argument");
     SPE_CHECK(D % 4 == 0 && D <= 128 * LN_MAXCH, "spe_layernorm_bwd: unsupported D=%d", D);
+    const int nch = (D + 127) / 128;
+    const int per_sm = nch <= 2 ? 4 : (nch == 3 ? 3 : (nch <= 6 ? 2 : 1));
     long long g = (rows + 7) / 8;
-    if (g > (long long)spe_num_sms() * 2) g = (long long)spe_num_sms() * 2;
+    if (g > (long long)spe_num_sms() * per_sm) g = (long long)spe_num_sms() * per_sm;
     SpeProfScope prof(SPE_FAM_LAYERNORM, (double)rows * D * (8.0 + (dy_bf16 ? 2.0 : 0.0) + (dy_f32 ? 4.0 : 0.0)), ST(stream));
-    layernorm_bwd_kernel<<<(int)g, 256, 2 * D * sizeof(float), ST(stream)>>>(reinterpret_cast<const uint16_t*>(dy_bf16), dy_f32, dres, x, w, mean, rstd,
-                                                                               rows, D, dx, dw, db);
+#define SPE_LN_BWD(NCH_) layernorm_bwd_kernel<NCH_><<<(int)g, 256, 2 * D * sizeof(float), ST(stream)>>>(reinterpret_cast<const uint16_t*>(dy_bf16), dy_f32, dres, x, w, \
+                                                                                                      mean, rstd, rows, D, dx, dw, db)
+    switch (nch) {
+        case 1: SPE_LN_BWD(1); break;
+        case 2: SPE_LN_BWD(2); break;
+        case 3: SPE_LN_BWD(3); break;
+        case 4: SPE_LN_BWD(4); break;
+        case 5: case 6: SPE_LN_BWD(6); break;
+        default: SPE_LN_BWD(8); break;
+    }
+#undef SPE_LN_BWD
     SPE_LAUNCHED();
     return 0;
 }

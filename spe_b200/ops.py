@@ -522,6 +522,41 @@ def _dq_dk(dS, q, k, H, alpha, Lq, Lk, ldP, dq_out=None, dk_out=None):
     return dq, dk
 
 
+_UNFUSED_ATTN = None
+
+
+def _fused_attention_ok(q, k, v, q2, k2, H):
+    """shapes / layouts the fused forward kernel takes (everything on the detector path); SPE_ATTN_UNFUSED=1 forces the
+    GEMM -> softmax -> GEMM pipeline (A/B timing)."""
+    global _UNFUSED_ATTN
+    if _UNFUSED_ATTN is None:
+        import os
+        _UNFUSED_ATTN = os.environ.get("SPE_ATTN_UNFUSED", "0") == "1"
+    if _UNFUSED_ATTN:
+        return False
+    d, dv = q.shape[2] // H, v.shape[2] // H
+    ok = d % 16 == 0 and d <= 64 and dv % 16 == 0 and dv <= 64 and k.shape[1] <= 8192
+    if q2 is not None:
+        d2 = q2.shape[2] // H
+        ok = ok and d2 % 16 == 0 and d2 <= 64
+    for t in (q, k, v, q2, k2):
+        if t is not None:
+            ok = ok and t.stride(2) == 1 and t.stride(1) % 8 == 0 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0
+    return ok
+
+
+def fused_attention_fwd(q, k, v, q2, k2, mask_u8, H, scale, out, P=None, lse=None):
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    a = _lib.AttentionArgs(B, H, Lq, Lk, E // H, (q2.shape[2] // H if q2 is not None else 0), v.shape[2] // H,
+                           q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0), v.data_ptr(), v.stride(1), v.stride(0),
+                           ptr(q2), (q2.stride(1) if q2 is not None else 0), (q2.stride(0) if q2 is not None else 0),
+                           ptr(k2), (k2.stride(1) if k2 is not None else 0), (k2.stride(0) if k2 is not None else 0),
+                           ptr(mask_u8), scale, out.data_ptr(), out.stride(1), out.stride(0), ptr(P), (P.shape[3] if P is not None else 0), ptr(lse))
+    check(lib().spe_attention_fwd(C.byref(a), stream()))
+    return out
+
+
 class AttentionFn(torch.autograd.Function):
     """softmax(scale * (q k^T [+ q2 k2^T]) + key_padding_mask) v, heads packed along the feature dim.
     nn.MultiheadAttention core (transformer.py:280) and models/attention.py:345-378 (d_qk != d_v, the
@@ -534,6 +569,14 @@ class AttentionFn(torch.autograd.Function):
         B, Lq, _ = q.shape
         Lk = k.shape[1]
         ld = rup(Lk, 8)
+        if not want_mean and _fused_attention_ok(q, k, v, q2, k2, H):
+            # fused forward (attn_fused.cu): logits stay in TMEM; P (bf16) is written once for the backward GEMMs
+            P = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=q.device)
+            out = torch.empty((B, Lq, v.shape[2]), dtype=torch.bfloat16, device=q.device)
+            fused_attention_fwd(q, k, v, q2, k2, mask_u8, H, scale, out, P=P)
+            ctx.save_for_backward(q, k, v, q2, k2, P)
+            ctx.H, ctx.scale, ctx.ld = H, scale, ld
+            return out
         S = torch.empty((B, H, Lq, ld), dtype=torch.float32, device=q.device)
         _qk_logits(q, k, H, scale, S, ld, q2, k2)
         P = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=q.device)

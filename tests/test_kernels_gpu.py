@@ -259,6 +259,61 @@ def test_attention_fn(K, masked, two):
         assert rel_err(a, b_) < 3e-2, rel_err(a, b_)
 
 
+@pytest.mark.parametrize("masked,two,Lq,Lk,d,dv,packed", [(False, False, 60, 100, 48, 48, False), (True, False, 300, 300, 48, 48, False),
+                                                          (True, True, 600, 1600, 48, 48, False), (False, False, 1600, 1600, 48, 48, True),
+                                                          (True, True, 130, 257, 32, 16, False), (False, False, 128, 128, 64, 64, False)])
+def test_fused_attention_fwd(K, masked, two, Lq, Lk, d, dv, packed):
+    """attn_fused.cu through ops.attention (no head-mean requested -> fused forward): output, the saved probabilities P (incl. zero
+    padding columns) and the log-sum-exp against an fp32 reference; gradients flow through the (GEMM) backward from the saved P."""
+    g = torch.Generator().manual_seed(140 + Lq)
+    B, H = 2, 8
+    mk = lambda *s: bf(torch.randn(*s, generator=g)).to(dev())
+    if packed:       # q | k | v as strided views of one packed projection output (the encoder / backbone layout)
+        qkv = mk(B, Lq, 3 * H * d)
+        q, k, v = [qkv[:, :, i * H * d:(i + 1) * H * d].requires_grad_(True) for i in range(3)]
+    else:
+        q, k, v = mk(B, Lq, H * d).requires_grad_(True), mk(B, Lk, H * d).requires_grad_(True), mk(B, Lk, H * dv).requires_grad_(True)
+    q2, k2 = (mk(B, Lq, H * d).requires_grad_(True), mk(B, Lk, H * d).requires_grad_(True)) if two else (None, None)
+    mask = None
+    if masked:
+        mask = torch.zeros(B, Lk, dtype=torch.uint8)
+        mask[0, Lk - Lk // 7:] = 1
+        mask[1, Lk // 3:Lk // 2] = 1
+        mask = mask.to(dev())
+    scale = (2 * d if two else d) ** -0.5
+    assert K._fused_attention_ok(q, k, v, q2, k2, H)
+    # raw kernel: P and lse
+    ld = K.rup(Lk, 8)
+    P = torch.full((B, H, Lq, ld), 7.0, dtype=torch.bfloat16, device=dev())
+    lse = torch.empty((B, H, Lq), dtype=torch.float32, device=dev())
+    out0 = torch.empty((B, Lq, H * dv), dtype=torch.bfloat16, device=dev())
+    K.fused_attention_fwd(q.detach(), k.detach(), v.detach(), None if q2 is None else q2.detach(), None if k2 is None else k2.detach(), mask, H, scale,
+                          out0, P=P, lse=lse)
+    out = K.attention(q, k, v, H, scale, mask_u8=mask, q2=q2, k2=k2)
+    assert torch.equal(out.detach(), out0)
+    go = bf(torch.randn(out.shape, generator=g)).to(dev())
+    ins = [q, k, v] + ([q2, k2] if two else [])
+    got = _grads((out.float() * go.float()).sum(), *ins)
+    fr = [t.detach().float().requires_grad_(True) for t in ins]
+    hd = lambda t, L, dd: t.reshape(B, L, H, dd).transpose(1, 2)
+    S = hd(fr[0], Lq, d) @ hd(fr[1], Lk, d).transpose(-1, -2)
+    if two:
+        S = S + hd(fr[3], Lq, d) @ hd(fr[4], Lk, d).transpose(-1, -2)
+    S = S * scale
+    if masked:
+        S = S.masked_fill(mask.bool()[:, None, None, :], float("-inf"))
+    Pm = S.softmax(-1)
+    outr = (Pm @ hd(fr[2], Lk, dv)).transpose(1, 2).reshape(B, Lq, H * dv)
+    ref = _grads((outr * go.float()).sum(), *fr)
+    assert rel_err(out, outr) < 2e-2, rel_err(out, outr)
+    assert rel_err(P[..., :Lk], Pm) < 1e-2, rel_err(P[..., :Lk], Pm)
+    assert float(P[..., Lk:].float().abs().max()) == 0.0 if ld > Lk else True
+    lse_ref = torch.logsumexp(S, -1) * 1.4426950408889634
+    assert float((lse.cpu() - lse_ref.cpu()).abs().max()) < 2e-3
+    for a, b_ in zip(got, ref):
+        assert rel_err(a, b_) < 3e-2, rel_err(a, b_)
+
+
 @pytest.mark.parametrize("H,N,dh", [(2, 35, 64), (4, 196, 48), (8, 130, 48), (16, 300, 48), (6, 77, 48), (12, 261, 32)])   # 16 = CaiT-M36 (cfg4), 6/12: generic-H kernels
 def test_talking_heads_attention_fn(K, H, N, dh):
     g = torch.Generator().manual_seed(15)
