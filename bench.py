@@ -294,11 +294,11 @@ def run_ours(args):
     for k, (t, w, n) in fam.items():
         if n:
             breakdown[k] = {"ms_per_step": t / nprof, "launches_per_step": n / nprof, "work_per_step": w / nprof,
-                            "share_of_step": (t / nprof) / (ms_prof / nprof)}
+                            "share_of_step": (t / nprof) / (ms / args.steps)}       # of the TIMED (graph-replayed) step
     gm = fam["gemm"]
     g_tflops = gm[1] / (gm[0] * 1e-3) / 1e12 if gm[0] > 0 else 0.0
     hbm = {k: (fam[k][1] / (fam[k][0] * 1e-3) / 1e9 if fam[k][0] > 0 else 0.0)
-           for k in ("gemm_attention", "talking_softmax_fwd", "talking_softmax_bwd", "softmax", "layernorm")}
+           for k in ("gemm_attention", "talking_softmax_fwd", "talking_softmax_bwd", "softmax", "layernorm", "attention_fused")}
     dominant = max(breakdown, key=lambda k: breakdown[k]["ms_per_step"]) if breakdown else "gemm"
     if dominant == "gemm" or dominant not in hbm:
         roof = {"kernel": "gemm_tcgen05_kernel (all dense/linear GEMM launches of a step)", "bound": "tensor", "achieved": g_tflops, "peak": peaks["tflops"],

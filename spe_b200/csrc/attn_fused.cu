@@ -8,8 +8,9 @@
 //                 accumulator (2 x 128 columns), and O += P V (A = P from shared memory, B = V consumed MN-major straight from
 //                 the packed [B, Lk, H*dv] activation) into 64 further TMEM columns;
 //   warp 2      : TMEM allocator;
-//   warps 4..7  : softmax, one thread per query row (no cross-lane reductions): tcgen05.ld of its S row, exp2 with the
-//                 statistics, bf16 P into the swizzled K-major shared tile that the PV MMA (and the TMA store of P) read.
+//   warps 4..11 : softmax, two groups of 128 threads (thread = query row: no cross-lane reductions) that alternate key blocks:
+//                 tcgen05.ld of the S row, exp2 with the statistics, bf16 P into the swizzled K-major shared tile that the PV
+//                 MMA (and the TMA store of P) read.  The groups run out of phase so the MUFU pipe always has work.
 // Two sweeps over the keys: sweep 1 = row statistics (online max / sum on the S tiles), sweep 2 = exact normalised P -> PV.
 // The second QK^T costs 1/8 of the MUFU-bound softmax time and buys: no accumulator rescaling, and P that is already final when
 // it is produced -- it is written once (bf16, TMA bulk stores) for the backward GEMMs, which is the only N^2 HBM traffic left
@@ -17,6 +18,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 
 int spe_make_tmap_bf16(CUtensorMap* tm, const void* ptr, int major, int rows, int K, int64_t ld, int64_t sb1, int64_t sb2, int batch1, int batch2, int box_rows);
 void* spe_tmap_encode_fn();
@@ -25,11 +27,12 @@ namespace {
 
 constexpr int BQ = 128;                 // query rows per CTA (= TMEM lanes)
 constexpr int BKV = 128;                // keys per block
-constexpr int KS = 2;                   // K ring stages
-constexpr int VS = 2;                   // V ring stages
+constexpr int KS = 2;                   // K ring stages with two QK segments (K and K2 tiles per stage); 2 * KS with one segment
+constexpr int KSMAX = 2 * KS;
+constexpr int VS = 3;                   // V ring stages
 constexpr uint32_t TILE_B = 128 * 64 * 2;      // one [128 rows x 64 cols] bf16 SWIZZLE_128B tile (Q, K, half of P)
 constexpr uint32_t VBOX_B = 64 * 64 * 2;       // one MN-major V box: 64 keys x 64 (dv, zero filled beyond dv)
-constexpr int AT_THREADS = 256;
+constexpr int AT_THREADS = 384;
 constexpr float LOG2E_F = 1.4426950408889634f;
 
 struct AttnParams {
@@ -43,6 +46,7 @@ struct AttnParams {
     uint16_t* out; long long out_ld, out_sb;     // [B, Lq, H*dv] bf16
     float* lse;              // [B, H, Lq] or null
     int store_p, ldP;
+    int dbg;                 // timing experiments only (SPE_ATTN_DBG): 1 = no MUFU (exp2 replaced by a multiply)
 };
 
 __device__ __forceinline__ uint32_t a_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,8 +119,8 @@ __device__ __forceinline__ float a_ex2(float x) {
 // smem layout (all tiles 1024-byte aligned):  Q | Q2 | K[KS] | K2[KS] | V[VS] (2 boxes each) | P[2] (2 tiles each) | barriers | mask bits
 constexpr uint32_t OFF_Q = 0, OFF_Q2 = OFF_Q + TILE_B, OFF_K = OFF_Q2 + TILE_B, OFF_K2 = OFF_K + KS * TILE_B, OFF_V = OFF_K2 + KS * TILE_B,
                    OFF_P = OFF_V + VS * 2 * VBOX_B, OFF_BAR = OFF_P + 2 * 2 * TILE_B;
-constexpr int NBAR = 1 + 2 * KS + 2 * VS + 4 + 4 + 1;      // qfull, kfull/kempty, vfull/vempty, sfull/sempty[2], pfull/pempty[2], ofull
-constexpr uint32_t OFF_TSLOT = OFF_BAR + NBAR * 8, OFF_MBITS = OFF_TSLOT + 16;
+constexpr int NBAR = 1 + 2 * KSMAX + 2 * VS + 4 + 4 + 1;      // qfull, kfull/kempty, vfull/vempty, sfull/sempty[2], pfull/pempty[2], ofull
+constexpr uint32_t OFF_TSLOT = OFF_BAR + NBAR * 8, OFF_XCHG = OFF_TSLOT + 16, OFF_MBITS = OFF_XCHG + 2 * 128 * 8;
 
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ2,
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = a_smem_u32(smem);
     const uint32_t bar0 = sbase + OFF_BAR;
-    const uint32_t qfull = bar0, kfull0 = qfull + 8, kempty0 = kfull0 + 8 * KS, vfull0 = kempty0 + 8 * KS, vempty0 = vfull0 + 8 * VS,
+    const uint32_t qfull = bar0, kfull0 = qfull + 8, kempty0 = kfull0 + 8 * KSMAX, vfull0 = kempty0 + 8 * KSMAX, vempty0 = vfull0 + 8 * VS,
                    sfull0 = vempty0 + 8 * VS, sempty0 = sfull0 + 16, pfull0 = sempty0 + 16, pempty0 = pfull0 + 16, ofull = pempty0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TSLOT);
     uint32_t* mbits = reinterpret_cast<uint32_t*>(smem + OFF_MBITS);          // [nkb][4]: bit set = key masked (padding or >= Lk)
@@ -134,13 +138,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
     const int nkb = ap.nkb;
+    // K ring: with one QK segment the K2 tiles are extra K stages (the two regions are contiguous)
+    const uint32_t nks = ap.two ? (uint32_t)KS : (uint32_t)KSMAX;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
         a_mbar_init(qfull, 1);
-        for (int s = 0; s < KS; ++s) { a_mbar_init(kfull0 + 8 * s, 1); a_mbar_init(kempty0 + 8 * s, 1); }
+        for (int s = 0; s < KSMAX; ++s) { a_mbar_init(kfull0 + 8 * s, 1); a_mbar_init(kempty0 + 8 * s, 1); }
         for (int s = 0; s < VS; ++s) { a_mbar_init(vfull0 + 8 * s, 1); a_mbar_init(vempty0 + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) {
             a_mbar_init(sfull0 + 8 * s, 1); a_mbar_init(sempty0 + 8 * s, 4);
@@ -176,8 +182,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
             uint32_t kit = 0;
             for (int sweep = 0; sweep < 2; ++sweep) {
                 for (int j = 0; j < nkb; ++j, ++kit) {
-                    const int ks = kit % KS;
-                    a_mbar_wait(kempty0 + 8 * ks, ((kit / KS) & 1u) ^ 1u);
+                    const uint32_t ks = kit % nks;
+                    a_mbar_wait(kempty0 + 8 * ks, ((kit / nks) & 1u) ^ 1u);
                     a_mbar_expect_tx(kfull0 + 8 * ks, ap.two ? 2 * TILE_B : TILE_B);
                     a_tma_load(sbase + OFF_K + ks * TILE_B, &tmK, kfull0 + 8 * ks, 0, j * BKV, h, b);
                     if (ap.two) a_tma_load(sbase + OFF_K2 + ks * TILE_B, &tmK2, kfull0 + 8 * ks, 0, j * BKV, h, b);
@@ -203,9 +209,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t kit = 0, sit = 0;
             auto issue_s = [&]() {
-                const int ks = kit % KS;
+                const uint32_t ks = kit % nks;
                 const uint32_t sb = sit & 1u;
-                a_mbar_wait(kfull0 + 8 * ks, (kit / KS) & 1u);
+                a_mbar_wait(kfull0 + 8 * ks, (kit / nks) & 1u);
                 a_mbar_wait(sempty0 + 8 * sb, ((sit >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t qa = sbase + OFF_Q, ka = sbase + OFF_K + ks * TILE_B;
@@ -219,9 +225,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
                 ++kit; ++sit;
             };
             for (int j = 0; j < nkb; ++j) issue_s();                  // sweep 1
-            issue_s();                                                // sweep 2: S_0
+            // sweep 2: the S tiles run TWO blocks ahead of the PV products (a softmax group finds its next tile ready when it
+            // finishes a block; S_{j+2} reuses the TMEM buffer of S_j, which is free as soon as its group has loaded it)
+            issue_s();
+            if (nkb > 1) issue_s();
             for (int j = 0; j < nkb; ++j) {
-                if (j + 1 < nkb) issue_s();                           // S_{j+1} overlaps the softmax of block j
+                if (j + 2 < nkb) issue_s();
                 const uint32_t pb = (uint32_t)j & 1u;
                 const int vs = j % VS;
                 a_mbar_wait(pfull0 + 8 * pb, ((uint32_t)j >> 1) & 1u);
@@ -243,116 +252,164 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ---------------- softmax warps: thread = query row ----------------
-        const int quarter = warp & 3;
+        // ---------------- softmax warps: two groups of 128 threads, thread = query row, groups alternate key blocks ----------------
+        // Group g (warps 4+4g .. 7+4g; warp % 4 = TMEM lane quarter, a hardware rule) owns the key blocks j with j % 2 == g and P
+        // buffer g.  The groups run out of phase: while one sits in its TMEM-load / barrier / store phase the other keeps the MUFU
+        // pipe busy with exp2, which is what bounds this kernel (128 x 128 exponentials per block at 16 per clock per SM).
+        const bool nomufu = (ap.dbg & 1) != 0;
+#define EX(x) (nomufu ? (x) * 0.001f : a_ex2(x))
+        const int quarter = warp & 3, grp = (warp - 4) >> 2;
         const int row = quarter * 32 + lane;                   // row inside the block = TMEM lane
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
-        const bool tid0 = threadIdx.x == 128;
+        const bool gtid0 = (threadIdx.x & 127) == 0;           // first thread of the group: issues the bulk stores of P
+        const uint32_t bar_id = 1u + (uint32_t)grp;
+        float2* xchg = reinterpret_cast<float2*>(smem + OFF_XCHG);      // [2][128] (max, sum) of the two groups' blocks of a row
         float m = -INFINITY, l = 0.f;
-        uint32_t sit = 0;
-        // ---- sweep 1: statistics
-        for (int j = 0; j < nkb; ++j, ++sit) {
-            const uint32_t sb = sit & 1u;
+        // ---- sweep 1: statistics over this group's key blocks
+        for (int j = grp; j < nkb; j += 2) {
+            const uint32_t sit = (uint32_t)j, sb = sit & 1u;
             a_mbar_wait(sfull0 + 8 * sb, (sit >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float mx = -INFINITY;
-            float part = 0.f;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                uint32_t r[32];
-                A_TMEM_LD32(tS + tlane + sb * 128 + c4 * 32, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c4 == 3) {
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t r[64];
+                if (!(ap.dbg & 2)) {
+                    A_TMEM_LD32(tS + tlane + sb * 128 + hh * 64, r);
+                    A_TMEM_LD32(tS + tlane + sb * 128 + hh * 64 + 32, r + 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) r[i] = (uint32_t)(i + lane);
+                }
+                if (hh == 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) a_mbar_arrive(sempty0 + 8 * sb);
                 }
-                const uint32_t bits = mbits[j * 4 + c4];
-                float x[32];
-                float cmx = -INFINITY;
+                const uint32_t bits0 = mbits[j * 4 + hh * 2], bits1 = mbits[j * 4 + hh * 2 + 1];
+                if ((bits0 | bits1) == 0u) {                  // warp-uniform fast path: no masked key in these 64 columns
+                    float cmx = __uint_as_float(r[0]);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    x[i] = ((bits >> i) & 1u) ? -INFINITY : __uint_as_float(r[i]) * ap.scale2;
-                    cmx = fmaxf(cmx, x[i]);
-                }
-                const float mn = fmaxf(mx, cmx);
-                if (mn > -INFINITY) {
-                    float acc = 0.f;
+                    for (int i = 1; i < 64; ++i) cmx = fmaxf(cmx, __uint_as_float(r[i]));
+                    const float mn = fmaxf(m, cmx * ap.scale2);
+                    float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc += a_ex2(x[i] - mn);
-                    part = part * a_ex2(mx - mn) + acc;
-                    mx = mn;
+                    for (int i = 0; i < 64; i += 2) {
+                        acc0 += EX(fmaf(__uint_as_float(r[i]), ap.scale2, -mn));
+                        acc1 += EX(fmaf(__uint_as_float(r[i + 1]), ap.scale2, -mn));
+                    }
+                    l = l * a_ex2(m - mn) + (acc0 + acc1);
+                    m = mn;
+                } else {
+                    float cmx = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        const uint32_t bits = i < 32 ? bits0 : bits1;
+                        if (!((bits >> (i & 31)) & 1u)) cmx = fmaxf(cmx, __uint_as_float(r[i]) * ap.scale2);
+                    }
+                    const float mn = fmaxf(m, cmx);
+                    if (mn > -INFINITY) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) {
+                            const uint32_t bits = i < 32 ? bits0 : bits1;
+                            acc += ((bits >> (i & 31)) & 1u) ? 0.f : a_ex2(fmaf(__uint_as_float(r[i]), ap.scale2, -mn));
+                        }
+                        l = l * a_ex2(m - mn) + acc;          // m = -inf: l = 0 and 2^-inf = 0
+                        m = mn;
+                    }
                 }
             }
-            const float mn = fmaxf(m, mx);
-            if (mn > -INFINITY) {
-                l = l * a_ex2(m - mn) + part * a_ex2(mx - mn);
-                m = mn;
-            }
+        }
+        // combine the two groups' partial statistics of the row
+        xchg[grp * 128 + row] = make_float2(m, l);
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        {
+            const float2 o = xchg[(grp ^ 1) * 128 + row];
+            const float M = fmaxf(m, o.x);
+            l = (m == -INFINITY ? 0.f : l * a_ex2(m - M)) + (o.x == -INFINITY ? 0.f : o.y * a_ex2(o.x - M));
+            m = M;
         }
         const float lse2 = m + log2f(l);                       // p = 2^(x - lse2)
-        if (ap.lse != nullptr && q0 + row < ap.Lq) ap.lse[((long long)b * ap.H + h) * ap.Lq + q0 + row] = lse2;
+        if (grp == 0 && ap.lse != nullptr && q0 + row < ap.Lq) ap.lse[((long long)b * ap.H + h) * ap.Lq + q0 + row] = lse2;
         // ---- sweep 2: P -> shared (-> HBM), PV by the MMA warp
-        for (int j = 0; j < nkb; ++j, ++sit) {
-            const uint32_t sb = sit & 1u, pb = (uint32_t)j & 1u;
+        const uint32_t sw = (uint32_t)(row & 7);
+        const uint32_t pbase = sbase + OFF_P + (uint32_t)grp * 2 * TILE_B;
+        for (int j = grp; j < nkb; j += 2) {
+            const uint32_t sit = (uint32_t)(nkb + j), sb = sit & 1u, use = (uint32_t)j >> 1;
             a_mbar_wait(sfull0 + 8 * sb, (sit >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t pk[64];                                   // 128 probabilities, packed bf16 pairs
+            // P buffer `grp` is free once the PV MMA of this group's previous block has retired and its bulk store has read it
+            a_mbar_wait(pempty0 + 8 * grp, (use & 1u) ^ 1u);
+            if (gtid0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                uint32_t r[32];
-                A_TMEM_LD32(tS + tlane + sb * 128 + c4 * 32, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c4 == 3) {
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t r[64];
+                if (!(ap.dbg & 4)) {
+                    A_TMEM_LD32(tS + tlane + sb * 128 + hh * 64, r);
+                    A_TMEM_LD32(tS + tlane + sb * 128 + hh * 64 + 32, r + 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) r[i] = (uint32_t)(i + lane);
+                }
+                if (hh == 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) a_mbar_arrive(sempty0 + 8 * sb);
                 }
-                const uint32_t bits = mbits[j * 4 + c4];
+                const uint32_t bits0 = mbits[j * 4 + hh * 2], bits1 = mbits[j * 4 + hh * 2 + 1];
+                // 64 keys = one [128 x 64] half tile of P: row `row`, 8 chunks of 16 bytes (SWIZZLE_128B pattern)
+                const uint32_t pa = pbase + (uint32_t)hh * TILE_B + (uint32_t)row * 128u;
+                if ((bits0 | bits1) == 0u) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = ((bits >> i) & 1u) ? 0.f : a_ex2(fmaf(__uint_as_float(r[i]), ap.scale2, -lse2));
-                    const float p1 = ((bits >> (i + 1)) & 1u) ? 0.f : a_ex2(fmaf(__uint_as_float(r[i + 1]), ap.scale2, -lse2));
-                    pk[c4 * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+                    for (int g = 0; g < 8; ++g) {
+                        uint32_t w4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            w4[i] = pack_bf16x2(EX(fmaf(__uint_as_float(r[g * 8 + 2 * i]), ap.scale2, -lse2)), EX(fmaf(__uint_as_float(r[g * 8 + 2 * i + 1]), ap.scale2, -lse2)));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + (((uint32_t)g ^ sw) << 4)), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]), "r"(w4[3]) : "memory");
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        uint32_t w4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int c0 = g * 8 + 2 * i, c1 = c0 + 1;
+                            const uint32_t bits = c0 < 32 ? bits0 : bits1;
+                            const float p0 = ((bits >> (c0 & 31)) & 1u) ? 0.f : a_ex2(fmaf(__uint_as_float(r[c0]), ap.scale2, -lse2));
+                            const float p1 = ((bits >> (c1 & 31)) & 1u) ? 0.f : a_ex2(fmaf(__uint_as_float(r[c1]), ap.scale2, -lse2));
+                            w4[i] = pack_bf16x2(p0, p1);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + (((uint32_t)g ^ sw) << 4)), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]), "r"(w4[3]) : "memory");
+                    }
                 }
-            }
-            // the P buffer is free once the PV MMA of block j-2 has retired and its bulk store has finished reading it
-            a_mbar_wait(pempty0 + 8 * pb, (((uint32_t)j >> 1) & 1u) ^ 1u);
-            if (tid0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const uint32_t pa = sbase + OFF_P + pb * 2 * TILE_B + (uint32_t)row * 128u;
-            const uint32_t sw = (uint32_t)(row & 7);
-#pragma unroll
-            for (int g = 0; g < 16; ++g) {                     // 16-byte chunk g: keys 8g..8g+7; half g / 8, chunk-in-row g % 8
-                const uint32_t addr = pa + (uint32_t)(g >> 3) * TILE_B + ((((uint32_t)g & 7u) ^ sw) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]), "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid0) {
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (gtid0) {
                 if (ap.store_p) {
-                    a_tma_store(&tmP, sbase + OFF_P + pb * 2 * TILE_B, j * BKV, q0, h, b);
-                    if (j * BKV + 64 < ap.ldP) a_tma_store(&tmP, sbase + OFF_P + pb * 2 * TILE_B + TILE_B, j * BKV + 64, q0, h, b);
+                    a_tma_store(&tmP, pbase, j * BKV, q0, h, b);
+                    if (j * BKV + 64 < ap.ldP) a_tma_store(&tmP, pbase + TILE_B, j * BKV + 64, q0, h, b);
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                a_mbar_arrive(pfull0 + 8 * pb);
+                a_mbar_arrive(pfull0 + 8 * grp);
             }
         }
-        // ---- output
+        // ---- output: group 0 stores columns [0, 32), group 1 [32, 64) of the row's dv values
         a_mbar_wait(ofull, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
-            uint32_t o[64];
-            A_TMEM_LD16(tO + tlane, o);
-            A_TMEM_LD16(tO + tlane + 16, o + 16);
-            A_TMEM_LD16(tO + tlane + 32, o + 32);
-            A_TMEM_LD16(tO + tlane + 48, o + 48);
+            uint32_t o[32];
+            A_TMEM_LD32(tO + tlane + (uint32_t)grp * 32u, o);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (q0 + row < ap.Lq) {
-                uint16_t* dst = ap.out + (long long)b * ap.out_sb + (long long)(q0 + row) * ap.out_ld + (long long)h * ap.dv;
+                uint16_t* dst = ap.out + (long long)b * ap.out_sb + (long long)(q0 + row) * ap.out_ld + (long long)h * ap.dv + grp * 32;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    if (g * 8 < ap.dv) {
+                for (int g = 0; g < 4; ++g) {
+                    if (grp * 32 + g * 8 < ap.dv) {
                         const uint4 v = make_uint4(pack_bf16x2(__uint_as_float(o[g * 8]), __uint_as_float(o[g * 8 + 1])),
                                                    pack_bf16x2(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3])),
                                                    pack_bf16x2(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5])),
@@ -362,7 +419,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
                 }
             }
         }
-        if (tid0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (gtid0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -420,6 +477,10 @@ extern "C" __attribute__((visibility("default"))) int spe_attention_fwd(const sp
     ap.lse = a->lse;
     ap.store_p = a->P ? 1 : 0;
     ap.ldP = (int)a->ldP;
+    {
+        static const int dbg = getenv("SPE_ATTN_DBG") ? atoi(getenv("SPE_ATTN_DBG")) : 0;
+        ap.dbg = dbg;
+    }
     const size_t smem = OFF_MBITS + (size_t)ap.nkb * 16 + 1024;
     SPE_CHECK(smem <= 232448, "spe_attention_fwd: Lk = %d too long for the mask table", a->Lk);
     static size_t attr_smem = 0;

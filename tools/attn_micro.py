@@ -1,0 +1,36 @@
+"""Timing of the fused attention forward (attn_fused.cu) at the detector's shapes (CUDA events, rotating buffers > L2)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from spe_b200 import ops
+dev = torch.device("cuda")
+
+def timeit(fn, reps=10):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+def case(name, B, H, Lq, Lk, d, dv, two, store_p=True, masked=False):
+    q = torch.randn(B, Lq, H * d, device=dev).to(torch.bfloat16); k = torch.randn(B, Lk, H * d, device=dev).to(torch.bfloat16)
+    v = torch.randn(B, Lk, H * dv, device=dev).to(torch.bfloat16)
+    q2 = torch.randn_like(q) if two else None; k2 = torch.randn_like(k) if two else None
+    ld = ops.rup(Lk, 8)
+    P = torch.empty(B, H, Lq, ld, device=dev, dtype=torch.bfloat16) if store_p else None
+    out = torch.empty(B, Lq, H * dv, device=dev, dtype=torch.bfloat16)
+    mask = torch.zeros(B, Lk, dtype=torch.uint8, device=dev) if masked else None
+    scale = (d * (2 if two else 1)) ** -0.5
+    ms = timeit(lambda: ops.fused_attention_fwd(q, k, v, q2, k2, mask, H, scale, out, P=P))
+    flops = 4.0 * B * H * Lq * Lk * (d * (2 if two else 1) + dv) / 2 * 1.0   # QK^T (once) + PV, 2*MAC
+    print("%-28s %.3f ms   %.1f TFLOP/s (algorithmic QK^T+PV)   P bytes %.0f MB -> %.0f GB/s" % (
+        name, ms, flops / ms / 1e9, (P.numel() * 2 / 1e6 if P is not None else 0), (P.numel() * 2 / ms / 1e6 if P is not None else 0)))
+
+case("encoder 1600x1600 P", 8, 8, 1600, 1600, 48, 48, False, masked=True)
+case("encoder 1600x1600 noP", 8, 8, 1600, 1600, 48, 48, False, store_p=False, masked=True)
+case("cross 600x1600 two P", 8, 8, 600, 1600, 48, 48, True, masked=True)
+case("cross 600x1600 two noP", 8, 8, 600, 1600, 48, 48, True, store_p=False, masked=True)
+case("self 300x300 x16 P", 16, 8, 300, 300, 48, 48, False)
+case("class 81x1681 P", 8, 8, 81, 1681, 48, 48, False)
