@@ -119,6 +119,38 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: the leader CTA (cluster rank 0) issues the MMAs for both CTAs of the cluster
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {          // shared::cta address -> shared::cluster address in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are signalled on an mbarrier of the LEADER CTA (cluster address), data into this CTA's smem
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {       // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 #define TMEM_LD_32x32b_X32(taddr, r)                                                                         \
     asm volatile(                                                                                            \
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
@@ -244,18 +276,23 @@ __device__ __forceinline__ void epi_fast(const EpiParams& ep, const uint32_t (&r
 enum { EM_GENERIC = 0, EM_F32, EM_BF16, EM_BF16_BIAS, EM_F32_BIAS, EM_F32_BIAS_GAMMA_RES_XO, EM_F32_BIAS_RES, EM_F32_RES, EM_BF16_BIAS_RES,
        EM_BF16_BIAS_GELU_XO, EM_BF16_BIAS_RELU, EM_BF16_RELUGRAD, EM_BF16_GELUGRAD };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+// CG2 = CTA-pair mode: a cluster of 2 CTAs computes a 256 x BN tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows
+// of A and HALF of the B tile (BN/2 rows), the tensor core reads both halves, so the SM<->L2 operand traffic per flop drops by
+// 25% (BN = 128) to 50% (BN = 256) against the single-CTA 128 x 128 tile.  Only the leader CTA issues MMAs; smem stages are
+// released and accumulators published in both CTAs by multicast commits; every other role runs unchanged in both CTAs.
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                                                                       const __grid_constant__ CUtensorMap tmXi, const __grid_constant__ CUtensorMap tmXo,
                                                                       const EpiParams ep) {
+    constexpr int BNL = CG2 ? BN / 2 : BN;             // B rows staged by THIS CTA
     constexpr uint32_t A_BYTES = BM * BK * 2;
-    constexpr uint32_t B_BYTES = BN * BK * 2;
+    constexpr uint32_t B_BYTES = BNL * BK * 2;
     constexpr uint32_t TMEM_COLS = 2 * BN;               // double-buffered accumulator (BN in {64,128,256} -> 128 / 256 / 512 columns)
     static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
     // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((CG2 ? 2 * BM : BM) >> 4) << 24);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -266,6 +303,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;
+    const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;            // first tile / tile stride of this CTA (pair)
+    const int tstride = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int total_kb = (ep.K + BK - 1) / BK;
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 16, ebar0 = tempty0 + 16;
 
@@ -278,18 +318,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull0 + 8 * b, 1);
-            mbar_init(tempty0 + 8 * b, NUM_EPI_WARPS / 2);    // one epilogue group (4 warps = 128 TMEM lanes) owns a buffer
+            // one epilogue group (4 warps = 128 TMEM lanes) owns a buffer; pair mode: the groups of BOTH CTAs report to the leader
+            mbar_init(tempty0 + 8 * b, CG2 ? NUM_EPI_WARPS : NUM_EPI_WARPS / 2);
         }
         for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(ebar0 + 8 * w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (CG2) cluster_sync_all();             // both CTAs' barriers are initialised before any cross-CTA signal
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -306,7 +353,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         split = (int)z - (int)zb * ep.splits;
         const uint32_t q4 = fdiv(zb, ep.fd_b);
         b1 = (int)q4; b2 = (int)zb - (int)q4 * ep.batch2;
-        m0 = tm * BM; n0 = tn * BN;
+        m0 = tm * (CG2 ? 2 * BM : BM) + (int)cta_rank * BM; n0 = tn * BN;
         kb0 = split * ep.kb_per_split;
         nkb = min(ep.kb_per_split, total_kb - kb0);
     };
@@ -315,18 +362,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         if (lane == 0) {
             // ---------------- TMA producer ----------------
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < ep.num_tiles; t += gridDim.x) {
+            for (int t = tile0; t < ep.num_tiles; t += tstride) {
                 int m0, n0, b1, b2, kb0, nkb, split;
                 decode(t, m0, n0, b1, b2, kb0, nkb, split);
+                const int nl0 = n0 + (int)cta_rank * BNL;                  // pair mode: this CTA stages B rows [nl0, nl0 + BN/2)
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    const uint32_t a_dst = smem_u32(sA + s * A_BYTES), b_dst = smem_u32(sB + s * B_BYTES);
+                    const int kc = (kb0 + kb) * BK;
+                    if constexpr (CG2) {
+                        // both CTAs' loads complete on the LEADER's full barrier; the leader alone arms it with the bytes of the pair
+                        const uint32_t fbc = mapa_rank(full0 + 8 * s, 0u);
+                        if (cta_rank == 0) mbar_expect_tx(full0 + 8 * s, 2u * (A_BYTES + B_BYTES));
+                        if constexpr (!A_MN) {
+                            tma_load_4d_pair(a_dst, &tmA, fbc, kc, m0, b2 * ep.a_m2, b1 * ep.a_m1);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < BM / 64; ++c) tma_load_4d_pair(a_dst + c * CHUNK_BYTES, &tmA, fbc, m0 + c * 64, kc, b2 * ep.a_m2, b1 * ep.a_m1);
+                        }
+                        if constexpr (!B_MN) {
+                            tma_load_4d_pair(b_dst, &tmB, fbc, kc, nl0, b2 * ep.b_m2, b1 * ep.b_m1);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < BNL / 64; ++c) tma_load_4d_pair(b_dst + c * CHUNK_BYTES, &tmB, fbc, nl0 + c * 64, kc, b2 * ep.b_m2, b1 * ep.b_m1);
+                        }
+                        continue;
+                    }
                     const uint32_t fb = full0 + 8 * s;
                     const bool skipA = (ep.dbg & 16) != 0, skipB = (ep.dbg & 32) != 0;      // timing experiments only
                     mbar_expect_tx(fb, (skipA ? 0u : A_BYTES) + (skipB ? 0u : B_BYTES));
-                    const uint32_t a_dst = smem_u32(sA + s * A_BYTES), b_dst = smem_u32(sB + s * B_BYTES);
-                    const int kc = (kb0 + kb) * BK;
                     if (skipA) {
                     } else if constexpr (!A_MN) {
                         tma_load_4d(a_dst, &tmA, fb, kc, m0, b2 * ep.a_m2, b1 * ep.a_m1);
@@ -346,10 +412,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
+        if (lane == 0 && cta_rank == 0) {
+            // ---------------- MMA issuer (pair mode: leader CTA only) ----------------
             uint32_t it = 0, ti = 0;
-            for (int t = blockIdx.x; t < ep.num_tiles; t += gridDim.x, ++ti) {
+            for (int t = tile0; t < ep.num_tiles; t += tstride, ++ti) {
                 int m0, n0, b1, b2, kb0, nkb, split;
                 decode(t, m0, n0, b1, b2, kb0, nkb, split);
                 const uint32_t buf = ti & 1u, use = ti >> 1;
@@ -368,11 +434,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         // MN-major: 16 k-rows = 2 groups of 8 rows (SBO = 1024 B); LBO = next 64-wide MN chunk.
                         const uint64_t ad = A_MN ? umma_desc(a_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(a_base + k * 32, 0, 1024);
                         const uint64_t bd = B_MN ? umma_desc(b_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(b_base + k * 32, 0, 1024);
-                        umma_f16(tacc, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        if (ep.dbg & 128) continue;      // timing experiment: no MMA issue
+                        if constexpr (CG2) umma_f16_pair(tacc, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        else umma_f16(tacc, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs retire
+                    if constexpr (CG2) umma_commit_pair(empty0 + 8 * s);
+                    else umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs retire
                 }
-                umma_commit(tfull0 + 8 * buf);         // accumulator of this tile complete
+                if constexpr (CG2) umma_commit_pair(tfull0 + 8 * buf);
+                else umma_commit(tfull0 + 8 * buf);         // accumulator of this tile complete
             }
         }
         __syncwarp();
@@ -394,7 +464,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
         const bool c32 = ep.c_dtype == SPE_DT_F32;
         uint32_t eph = 0, use = 0;
         bool stores_pending = false;
-        for (int t = blockIdx.x + grp * (int)gridDim.x; t < ep.num_tiles; t += 2 * (int)gridDim.x, ++use) {
+        const uint32_t tempty_remote0 = CG2 ? mapa_rank(tempty0, 0u) : 0u;        // the leader's tempty barriers (cluster address)
+        auto release_acc = [&](uint32_t buf) {                                    // lane 0: hand the accumulator buffer back to the MMA warp
+            if constexpr (CG2) mbar_arrive_cluster(tempty_remote0 + 8 * buf);
+            else mbar_arrive(tempty0 + 8 * buf);
+        };
+        for (int t = tile0 + grp * tstride; t < ep.num_tiles; t += 2 * tstride, ++use) {
             int m0, n0, b1, b2, kb0, nkb, split;
             decode(t, m0, n0, b1, b2, kb0, nkb, split);
             const uint32_t buf = (uint32_t)grp;
@@ -402,6 +477,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             const int mrow = m0 + quarter * 32;
             mbar_wait(tfull0 + 8 * buf, use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (ep.dbg & 64) {                        // timing experiment: barrier protocol only, no epilogue work
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) release_acc(buf);
+                continue;
+            }
             bool arrived = false;
 #pragma unroll 1
             for (int sc = 0; sc < BN / 64; ++sc) {
@@ -440,14 +521,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     if (last_sc) {
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                        if (lane == 0) release_acc(buf);
                         arrived = true;
                     }
                     if (live) epilogue_direct(ep, r, mrow + lane, nb, b1, b2, lead);
                     continue;
                 }
                 if (loads) { mbar_wait(ebar, eph); eph ^= 1u; }
-                const int emode = (nb + 64 <= ep.N && ep.dbg == 0) ? (lead ? ep.mode : ep.mode_nl) : EM_GENERIC;
+                const int emode = (nb + 64 <= ep.N && (ep.dbg & 6) == 0) ? (lead ? ep.mode : ep.mode_nl) : EM_GENERIC;
                 if (emode != EM_GENERIC) {
                     uint32_t r[64];
                     TMEM_LD_32x32b_X32(taddr, r);
@@ -457,7 +538,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         // last TMEM read of this warp for this tile: hand the accumulator buffer back to the MMA warp
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                        if (lane == 0) release_acc(buf);
                         arrived = true;
                     }
                     if (need_drain && !loads) drain();
@@ -496,7 +577,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     // last TMEM read of this warp for this tile: hand the accumulator buffer back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                    if (lane == 0) release_acc(buf);
                     arrived = true;
                 }
 #pragma unroll
@@ -601,7 +682,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 // this warp owns no super-chunk of the tile (BN = 64, upper half): still release the buffer
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+                if (lane == 0) release_acc(buf);
             }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -610,8 +691,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (CG2) cluster_sync_all();             // the peer's smem / TMEM / barriers stay alive until the leader's last MMA retired
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -685,28 +768,46 @@ int make_tmap_io(CUtensorMap* tm, const void* ptr, bool f32, int M, int N, int64
 
 struct IoMaps { CUtensorMap C, R, Xi, Xo; };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CG2>
 int launch(const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const EpiParams& ep, cudaStream_t st) {
-    constexpr size_t SMEM = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + EPI_SMEM + (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + 1024;
+    constexpr size_t SMEM = (size_t)STAGES * (BM * BK * 2 + (CG2 ? BN / 2 : BN) * BK * 2) + EPI_SMEM + (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + 1024;
     static_assert(SMEM <= 232448, "shared memory budget (227 KB) exceeded");
     static bool attr_done = false;
-    auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
+    auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN, CG2>;
     if (!attr_done) {
         SPE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_done = true;
     }
-    const int grid = ep.num_tiles < spe_num_sms() ? ep.num_tiles : spe_num_sms();
-    kfn<<<grid, NUM_THREADS, SMEM, st>>>(tA, tB, io.C, io.R, io.Xi, io.Xo, ep);
+    if constexpr (CG2) {
+        // one cluster of 2 CTAs (= one TPC's SM pair) per 256 x BN tile stream
+        const int pairs = spe_num_sms() / 2;
+        const int clusters = ep.num_tiles < pairs ? ep.num_tiles : pairs;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SPE_CUDA(cudaLaunchKernelEx(&cfg, kfn, tA, tB, io.C, io.R, io.Xi, io.Xo, ep));
+    } else {
+        const int grid = ep.num_tiles < spe_num_sms() ? ep.num_tiles : spe_num_sms();
+        kfn<<<grid, NUM_THREADS, SMEM, st>>>(tA, tB, io.C, io.R, io.Xi, io.Xo, ep);
+    }
     SPE_LAUNCHED();
     return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool CG2 = false>
 int dispatch_major(int am, int bm, const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const EpiParams& ep, cudaStream_t st) {
-    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_K) return launch<BN, STAGES, false, false>(tA, tB, io, ep, st);
-    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_MN) return launch<BN, STAGES, false, true>(tA, tB, io, ep, st);
-    if (am == SPE_MAJOR_MN && bm == SPE_MAJOR_K) return launch<BN, STAGES, true, false>(tA, tB, io, ep, st);
-    return launch<BN, STAGES, true, true>(tA, tB, io, ep, st);
+    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_K) return launch<BN, STAGES, false, false, CG2>(tA, tB, io, ep, st);
+    if (am == SPE_MAJOR_K && bm == SPE_MAJOR_MN) return launch<BN, STAGES, false, true, CG2>(tA, tB, io, ep, st);
+    if (am == SPE_MAJOR_MN && bm == SPE_MAJOR_K) return launch<BN, STAGES, true, false, CG2>(tA, tB, io, ep, st);
+    return launch<BN, STAGES, true, true, CG2>(tA, tB, io, ep, st);
 }
 
 }  // namespace
@@ -728,8 +829,13 @@ static void fastdiv_magic(uint32_t d, uint32_t (&out)[2]) {
 // debugging / experiment switches, read once (getenv scans the whole environment: ~0.5 us each, five per call adds up at 1300 GEMMs a step)
 struct GemmEnv {
     bool bn256, direct_epilogue, generic_epilogue, no_splitk;
-    int dbg;
+    int dbg, cg2;
     GemmEnv() {
+        const char* c2 = getenv("SPE_GEMM_CG2");
+        // CTA-pair tiles: 0 (default) never, 1 heuristic (M >= 1024, full 256-row tiles), 2 wherever legal.  Measured on cfg2 (round 1):
+        // parity-green, but no gain yet (59.6 ms/step off vs 60.3 on): at K = 384 the tiles are bound by the MMA-issue/commit chain
+        // and the epilogue, not by operand traffic (skipping ALL operand loads changes no GEMM time by more than 5%) -- see DESIGN.md.
+        cg2 = c2 ? atoi(c2) : 0;
         bn256 = getenv("SPE_GEMM_BN256") != nullptr;
         direct_epilogue = getenv("SPE_GEMM_DIRECT_EPILOGUE") != nullptr;
         generic_epilogue = getenv("SPE_GEMM_GENERIC_EPILOGUE") != nullptr;
@@ -746,12 +852,15 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     SPE_CHECK(a->act == SPE_ACT_NONE || a->act == SPE_ACT_RELU || a->act == SPE_ACT_GELU || a->aux_in, "spe_gemm: *_GRAD activation needs aux_in");
     // 128x256 tiles (fewer A re-reads, 2 pipeline stages) were measured: S-type GEMMs -6%, fc1 +15% -> opt-in only (SPE_GEMM_BN256=1)
     const bool wideN = a->N >= 512 && (((a->N + 255) / 256) * 256 - a->N) * 8 <= a->N && env.bn256;
-    const int BN = a->N <= 64 ? 64 : (wideN ? 256 : 128);
     const int batch = a->batch1 * a->batch2;
+    // CTA-pair (cta_group::2) 256 x BN tiles: dense GEMMs with enough rows that the 256-row tiles fill (see the kernel comment)
+    const bool pair_ok = batch == 1 && a->N > 64 && a->M >= 512;
+    const bool pair = pair_ok && (env.cg2 >= 2 || (env.cg2 == 1 && a->M >= 1024 && (a->M % 256 == 0 || a->M >= 4096)));
+    const int BN = a->N <= 64 ? 64 : (pair ? (a->N >= 1024 ? 256 : 128) : (wideN ? 256 : 128));
     SPE_CHECK(batch == 1 || !(a->aux_in || a->aux_out), "spe_gemm: aux_in / aux_out are not batched");
     CUtensorMap tA, tB;
     if (make_tmap(&tA, a->A, a->a_major, a->M, a->K, a->lda, a->a_sb1, a->a_sb2, a->batch1, a->batch2, BM)) return -1;
-    if (make_tmap(&tB, a->B, a->b_major, a->N, a->K, a->ldb, a->b_sb1, a->b_sb2, a->batch1, a->batch2, BN)) return -1;
+    if (make_tmap(&tB, a->B, a->b_major, a->N, a->K, a->ldb, a->b_sb1, a->b_sb2, a->batch1, a->batch2, pair ? BN / 2 : BN)) return -1;
 
     EpiParams ep;
     memset(&ep, 0, sizeof(ep));
@@ -808,7 +917,7 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     }
     // ---- split-K: few output tiles but a long reduction (wgrad).  fp32 contiguous C, no activation / aux / gamma.
     const int total_kb = (a->K + BK - 1) / BK;
-    ep.tiles_m = (a->M + BM - 1) / BM;
+    ep.tiles_m = pair ? (a->M + 2 * BM - 1) / (2 * BM) : (a->M + BM - 1) / BM;
     ep.tiles_n = (a->N + BN - 1) / BN;
     int splits = 1;
     const long long tiles = (long long)ep.tiles_m * ep.tiles_n * batch;
@@ -834,6 +943,10 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     const double elt_c = cf32 ? 4.0 : 2.0;
     const double attn_bytes = ((double)a->M * a->K + (double)a->N * a->K) * 2.0 * batch + (double)a->M * a->N * elt_c * batch;
     SpeProfScope prof(attn ? SPE_FAM_GEMM_ATTN : SPE_FAM_GEMM, attn ? attn_bytes : 2.0 * a->M * a->N * (double)a->K * batch, st, tag);
+    if (pair) {
+        if (BN == 256) return dispatch_major<256, 4, true>(a->a_major, a->b_major, tA, tB, io, ep, st);
+        return dispatch_major<128, 4, true>(a->a_major, a->b_major, tA, tB, io, ep, st);
+    }
     if (BN == 64) return dispatch_major<64, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);
     if (BN == 256) return dispatch_major<256, 2>(a->a_major, a->b_major, tA, tB, io, ep, st);
     return dispatch_major<128, 4>(a->a_major, a->b_major, tA, tB, io, ep, st);

@@ -86,11 +86,12 @@ class LayerScale_Block(nn.Module):
 
     def forward(self, x):
         """x fp32 [B,N,D] -> fp32 [B,N,D]   (cait.py:413-416)"""
-        y = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        # layernorm_res hands x through so its residual-path gradient is added inside the LayerNorm backward kernel
+        y, xr = ops.layernorm_res(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         o = self.attn.core(y)
-        x = ops.linear(o, self.attn.proj.weight, self.attn.proj.bias, residual=x, gamma=self.gamma_1)
-        y = ops.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return ops.ffn(y, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=x, gamma=self.gamma_2, act="gelu")
+        x = ops.linear(o, self.attn.proj.weight, self.attn.proj.bias, residual=xr, gamma=self.gamma_1)
+        y, xr = ops.layernorm_res(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        return ops.ffn(y, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=xr, gamma=self.gamma_2, act="gelu")
 
 
 class Multi_Class_Attention(nn.Module):

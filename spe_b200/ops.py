@@ -415,6 +415,45 @@ class LayerNormFn(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+class LayerNormResFn(torch.autograd.Function):
+    """Pre-norm residual block entry (cait.py:414-415: x + gamma * f(LN(x))):  x_f32 -> (LN(x) bf16, x).  The second output is x
+    itself, handed on to the block's residual add; in the backward its gradient is added to the LayerNorm input gradient INSIDE
+    the LayerNorm backward kernel (`dres`), instead of by a separate autograd accumulation kernel over the whole residual stream."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        _need_cuda(x, weight, bias)
+        x = x.contiguous()
+        D = x.shape[-1]
+        rows = _rows(x)
+        y16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        check(lib().spe_layernorm_fwd(ptr(x), ptr(weight), ptr(bias), eps, rows, D, ptr(y16), 0, ptr(mean), ptr(rstd), stream()))
+        ctx.save_for_backward(x, weight, mean, rstd, bias)
+        return y16, x.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, d16, dres):
+        x, weight, mean, rstd, bias = ctx.saved_tensors
+        if d16 is None:
+            return dres, None, None, None
+        D = x.shape[-1]
+        d16 = d16.contiguous()
+        dres = dres.contiguous() if dres is not None else None
+        dx = torch.empty_like(x)
+        dw_b, dw = _grad_out(weight, (D,), x.device)
+        db_b, db = _grad_out(bias, (D,), x.device)
+        check(lib().spe_layernorm_bwd(ptr(d16), 0, ptr(dres), ptr(x), ptr(weight), ptr(mean), ptr(rstd), _rows(x), D, ptr(dx), ptr(dw_b), ptr(db_b),
+                                      stream()))
+        return dx, dw, db, None
+
+
+def layernorm_res(x, weight, bias, eps):
+    """returns (LN(x) bf16, x): use the second value as the residual operand of the block (see LayerNormResFn)."""
+    return LayerNormResFn.apply(x, weight, bias, eps)
+
+
 def layernorm(x, weight, bias, eps, want_f32=False):
     """returns y_bf16, or (y_f32, y_bf16) when want_f32."""
     return LayerNormFn.apply(x, weight, bias, eps, want_f32)

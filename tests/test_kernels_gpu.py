@@ -77,6 +77,17 @@ def test_gemm_accumulate_in_place(K, M, N, K_, mn):
         assert rel_err(out, want) < 3e-5, (reps, rel_err(out, want))
 
 
+def test_gemm_cta_pair_mode_subprocess():
+    """cta_group::2 (256 x BN CTA-pair tiles) is opt-in (SPE_GEMM_CG2, read once per process): run the GEMM tests under it."""
+    import os, subprocess, sys
+    env = dict(os.environ, SPE_GEMM_CG2="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_kernels_gpu.py"), "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "gemm_majors_and_tails or gemm_accumulate or gemm_epilogue or linear_fn or ffn_fn"], env=env, cwd=root,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+
+
 def test_gemm_epilogue_features(K):
     g = torch.Generator().manual_seed(3)
     M, N, Kd = 300, 384, 192

@@ -6,11 +6,18 @@ from spe_b200 import ops
 dev = torch.device("cuda")
 
 def timeit(fn, reps=20):
+    """GPU time per launch: the launches are captured into a CUDA graph (eager launches from Python are host-bound at ~15 us each)."""
     for _ in range(3): fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps): fn()
+    g.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps): fn()
+    g.replay()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
