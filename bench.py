@@ -307,6 +307,22 @@ def run_ours(args):
         kname = "gemm_tcgen05_kernel (batched attention GEMMs: QK^T / PV and gradients)" if dominant == "gemm_attention" else dominant
         roof = {"kernel": kname, "bound": "hbm", "achieved": hbm[dominant], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": hbm[dominant] / peaks["hbm_gbs"], "traffic": None}
+    # traffic: DRAM bytes per launch of that kernel from the committed ncu capture of one step (profiles/rNN_kernel_traffic.json)
+    fam_sym = {"talking_softmax_fwd": "talking_fwd", "talking_softmax_bwd": "talking_bwd_rows", "softmax": "softmax_", "layernorm": "layernorm_",
+               "attention_fused": "attn_fwd_kernel", "gemm": "gemm_tcgen05_kernel", "gemm_attention": "gemm_tcgen05_kernel"}
+    try:
+        import glob
+        tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernel_traffic.json")))[-1]
+        kt = json.load(open(tf))["kernels"]
+        sel = [v for k, v in kt.items() if fam_sym.get(dominant, "gemm_tcgen05_kernel") in k]
+        n = sum(v["launches"] for v in sel)
+        roof["traffic"] = sum((v["dram_read_per_launch"] + v["dram_write_per_launch"]) * v["launches"] for v in sel) / max(1, n)
+        roof["traffic_source"] = "%s: mean dram__bytes_read.sum + dram__bytes_write.sum per launch over the %d launches of `%s*` in one step%s" % (
+            os.path.basename(tf), n, fam_sym.get(dominant, "gemm_tcgen05_kernel"),
+            " (dense and batched-attention GEMMs share the kernel symbol)" if dominant.startswith("gemm") else "")
+        roof["algorithmic_per_launch"] = breakdown[dominant]["work_per_step"] / max(1.0, breakdown[dominant]["launches_per_step"])
+    except Exception:
+        pass
     roof["peak_source"] = peaks["src"] + " -- of measured"
     roof["how"] = "CUDA events on the launch stream around every launch of the family during %d profiled steps; achieved = sum(algorithmic work)/sum(time)" % nprof
     roof["gemm_tflops"] = g_tflops

@@ -26,6 +26,7 @@ class TrainStep:
         self.max_gt = max_gt
         self.shadows = ops.ShadowSet(model.parameters()) if refresh_shadows else None
         self._g = {}            # (B, H, W, cap) -> captured state
+        self._side = None       # second stream for the refine criterion's matching
 
     # ---- the step body (identical in both modes) ----
     def _body(self, images, T, T_refine):
@@ -33,12 +34,26 @@ class TrainStep:
         if self.shadows is not None:
             self.shadows.refresh()
         out = self.model(images)
-        ld = self.criterion(out[0], T)
+        m1 = m2 = None
+        packed = isinstance(T, CO.PackedTargets) and (T_refine is None or isinstance(T_refine, CO.PackedTargets))
+        if packed and self.criterion_refine is not None:
+            # the two criteria's Hungarian matchings are independent and each keeps only a few dozen CTAs busy: run them side by side
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                m2 = self.criterion_refine.match_all_levels(out[1], T_refine)
+            m1 = self.criterion.match_all_levels(out[0], T)
+            cur.wait_stream(self._side)
+            if not torch.cuda.is_current_stream_capturing():
+                m2.record_stream(cur)
+        ld = self.criterion(out[0], T, _matches=m1)
         wd = self.weight_dict
         loss = sum(ld[k] * wd[k] for k in ld if k in wd)
         ld2 = None
         if self.criterion_refine is not None:
-            ld2 = self.criterion_refine(out[1], T_refine)
+            ld2 = self.criterion_refine(out[1], T_refine, _matches=m2)
             loss = loss + sum(ld2[k] * wd[k] for k in ld2 if k in wd)
         loss.backward()
         return loss.detach(), {k: v.detach() for k, v in ld.items()}, (None if ld2 is None else {k: v.detach() for k, v in ld2.items()})

@@ -145,8 +145,19 @@ class SetCriterion(nn.Module):
         return {"img_label_logits": CO.BceLogitsFn.apply(outputs["x_logits"], y)[0],
                 "img_label_logits_tokens": CO.BceLogitsFn.apply(outputs["x_cls_logits"], y)[0]}
 
-    def forward(self, outputs, targets):
-        """conditional_detr.py:399-466."""
+    @torch.no_grad()
+    def match_all_levels(self, outputs, packed):
+        """Hungarian matching of the final + every auxiliary decoder level against pre-packed targets: i32 [L,B,Q] query -> gt map
+        (device side, one cost launch + one batched assignment launch).  engine.TrainStep calls this for the two criteria of a
+        step on two streams -- the assignment kernel is latency bound on a few dozen CTAs -- and hands the result to forward()."""
+        if isinstance(outputs, RefineOutputs):
+            outputs = outputs[0]
+        levels = [outputs] + list(outputs.get("aux_outputs", []))
+        return CO.match_levels(torch.stack([l["pred_logits"].detach() for l in levels]), torch.stack([l["pred_boxes"].detach() for l in levels]),
+                               packed, self.matcher.weights)
+
+    def forward(self, outputs, targets, _matches=None):
+        """conditional_detr.py:399-466.  (_matches: optional result of match_all_levels for these outputs / targets.)"""
         if isinstance(outputs, RefineOutputs):
             outputs = outputs[0]
         dev = outputs["pred_logits"].device
@@ -161,7 +172,8 @@ class SetCriterion(nn.Module):
 
         levels = [outputs] + list(outputs.get("aux_outputs", []))
         # all decoder levels are matched by ONE cost launch + ONE batched LSAP launch (L*B independent problems)
-        r2g = CO.match_levels(torch.stack([l["pred_logits"].detach() for l in levels]), torch.stack([l["pred_boxes"].detach() for l in levels]), T, mw)
+        r2g = _matches if _matches is not None else CO.match_levels(torch.stack([l["pred_logits"].detach() for l in levels]),
+                                                                    torch.stack([l["pred_boxes"].detach() for l in levels]), T, mw)
 
         def level(i, o, suffix, log):
             res = CO.set_losses(o["pred_logits"], o["pred_boxes"], T, mw, self.focal_alpha, self.gamma, refine=self.refine, losses=det, log=log,

@@ -1,8 +1,14 @@
 #!/bin/bash
-# round-end evidence: launch list of one step, ncu --set full on the hot kernels, default bench, reference arm
+# round-end evidence: (a) launch list of one step with device time + DRAM bytes per launch, (b) ncu --set full on the hot kernels,
+# (c) default bench (with CPU baseline), (d) reference arm.  Results land in gpurun_out/ (<= 64 MiB: the big .ncu-rep is exported to CSV on the
+# box and dropped); tools/make_profiles.py turns them into profiles/.
 mkdir -p gpurun_out
-timeout 1500 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/step_once.py > gpurun_out/launchlist.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tcgen05|talking|softmax_(fwd|bwd)_warp|layernorm" -s 20 -c 24 -o gpurun_out/prof_hot -f python tools/prof_attn.py 2 > gpurun_out/ncu_hot.log 2>&1
+rm -f gpurun_out/*.ncu-rep
+timeout 1500 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/step_once.py > gpurun_out/launchlist.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:"attn_fwd_kernel|gemm_tcgen05|talking|softmax_bwd_warp|layernorm" -s 30 -c 34 -o gpurun_out/prof_hot -f python tools/prof_attn.py 2 > gpurun_out/ncu_hot.log 2>&1
+ncu -i gpurun_out/prof_hot.ncu-rep --page raw --csv > gpurun_out/prof_hot_raw.csv 2>/dev/null
+rm -f gpurun_out/prof_hot.ncu-rep
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_fwd_kernel" -s 2 -c 1 -o gpurun_out/prof_attn_fused -f python tools/prof_attn.py 2 > gpurun_out/ncu_attn_fused.log 2>&1
 timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-tail -c 1500 gpurun_out/bench_default.json; echo; cat gpurun_out/bench_reference.json | cut -c1-600; wc -l gpurun_out/launches.csv; ls -la gpurun_out/prof_hot.ncu-rep
+tail -c 600 gpurun_out/bench_default.json; echo; cat gpurun_out/bench_reference.json | cut -c1-300; wc -l gpurun_out/launches.csv gpurun_out/prof_hot_raw.csv; du -sh gpurun_out; tail -2 gpurun_out/ncu_hot.log
