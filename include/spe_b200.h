@@ -99,6 +99,27 @@ typedef struct {
 
 int spe_attention_fwd(const spe_attention_args* a, void* stream);
 
+/* Attention backward GEMMs fused (attention.py:345-372 / cait.py:379-389 backward):  ONE pass over the N^2 tensors
+ *   dV[b,:,h] = P[b,h]^T dO[b,:,h]      dK[b,:,h] = alpha dS[b,h]^T Q[b,:,h]      dQ[b,:,h] = alpha dS[b,h] K[b,:,h]
+ * dS, P bf16 [B,H,Lq,ld] (zero in the columns >= Lk); q, k, dO, dq, dk, dv_out bf16 with heads packed in the feature dim
+ * (*_ld token stride, *_sb image stride, elements).  P == NULL: dQ and dK only (second QK segment of the conditional
+ * cross-attention).  workspace: f32 [spe_attention_bwd_gemms_workspace(B,H,Lq,d)] (dQ accumulation, zeroed here). */
+typedef struct {
+    int B, H, Lq, Lk, d, dv;
+    const void* dS; const void* P; int64_t ld;
+    const void* q; int64_t q_ld, q_sb;
+    const void* k; int64_t k_ld, k_sb;
+    const void* dO; int64_t do_ld, do_sb;
+    float alpha;
+    void* dq; int64_t dq_ld, dq_sb;
+    void* dk; int64_t dk_ld, dk_sb;
+    void* dv_out; int64_t dv_ld, dv_sb;
+    float* workspace;
+} spe_attention_bwd_args;
+
+int64_t spe_attention_bwd_gemms_workspace(int B, int H, int Lq, int d);
+int spe_attention_bwd_gemms(const spe_attention_bwd_args* a, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Row-wise / elementwise kernels of the backbone + transformer
  * ------------------------------------------------------------------------------------------- */

@@ -427,6 +427,205 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+
+// ================================================================================================
+// Attention backward GEMMs, fused:  dV = P^T dO,  dK = alpha dS^T Q,  dQ = alpha dS K   in ONE pass over the N^2 tensors dS and P
+// (attention.py:345-372 backward; cait.py:379-389 backward with P := A, the post-mix probabilities).  The three separate batched
+// GEMMs read dS twice and P once; here every [128 q x 128 k] tile of dS and P is staged once by TMA and consumed by three
+// tcgen05 products straight from the same shared-memory tiles -- a K-major tile read as operand A of dS K is, byte for byte, the
+// MN-major operand A of dS^T Q (only the UMMA descriptor differs), and likewise Q / dO / K serve as MN-major B operands.
+//   CTA = (128-key block j, head, image); dK_j and dV_j accumulate in TMEM over the query blocks; the dQ_i partial of each (i, j)
+//   goes TMEM -> registers -> red.global.add.f32 into an fp32 accumulation buffer (L2 resident), cast to bf16 afterwards.
+//   warp 0: TMA producer (2 stages of dS, P, Q, dO tiles; K_j once), warp 1: MMA issuer, warp 2: TMEM allocator,
+//   warps 4..7: dQ drain per query block + final dK / dV stores.
+// Padding: P and dS are exactly zero in the columns >= Lk (softmax / talking kernels) and TMA zero-fills rows >= Lq: no masks.
+// ================================================================================================
+struct BwdParams {
+    int Lq, Lk, H, nqb;
+    int d, dv, do_v;
+    float alpha;
+    float* dq_acc; long long dq_ld, dq_sb;          // fp32 [B, Lq, H*d]
+    uint16_t* dk; long long dk_ld, dk_sb;          // bf16 [B, Lk, H*d]
+    uint16_t* dvp; long long dv_ld, dv_sb;         // bf16 [B, Lk, H*dv]
+};
+
+constexpr int BW_STAGES = 2;
+constexpr uint32_t BW_STAGE_B = 2 * 2 * TILE_B + 2 * TILE_B;                 // dS (2 slabs), P (2 slabs), Q, dO
+constexpr uint32_t BW_OFF_K = 0, BW_OFF_ST = TILE_B, BW_OFF_BAR = BW_OFF_ST + BW_STAGES * BW_STAGE_B;
+constexpr int BW_NBAR = 1 + 2 * BW_STAGES + 4 + 1;                           // kfull, full/empty[S], dqfull/dqempty[2], accfull
+constexpr int BW_THREADS = 256;
+
+__global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmP,
+                                                                       const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                                       const __grid_constant__ CUtensorMap tmDO, const BwdParams bp) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = a_smem_u32(smem);
+    const uint32_t bar0 = sbase + BW_OFF_BAR;
+    const uint32_t kfull = bar0, full0 = kfull + 8, empty0 = full0 + 8 * BW_STAGES, dqfull0 = empty0 + 8 * BW_STAGES, dqempty0 = dqfull0 + 16,
+                   accfull = dqempty0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BW_OFF_BAR + BW_NBAR * 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+    const int nqb = bp.nqb;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDS)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmP)) : "memory");
+        a_mbar_init(kfull, 1);
+        for (int s = 0; s < BW_STAGES; ++s) { a_mbar_init(full0 + 8 * s, 1); a_mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { a_mbar_init(dqfull0 + 8 * s, 1); a_mbar_init(dqempty0 + 8 * s, 4); }
+        a_mbar_init(accfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tDV = tmem_base, tDK = tmem_base + 64, tDQ = tmem_base + 128;        // dQ: 2 x 64 columns
+
+    if (warp == 0) {
+        if (lane == 0) {
+            a_mbar_expect_tx(kfull, TILE_B);
+            a_tma_load(sbase + BW_OFF_K, &tmK, kfull, 0, k0, h, b);
+            for (int i = 0; i < nqb; ++i) {
+                const int s = i % BW_STAGES;
+                a_mbar_wait(empty0 + 8 * s, (((uint32_t)i / BW_STAGES) & 1u) ^ 1u);
+                const uint32_t st = sbase + BW_OFF_ST + s * BW_STAGE_B, fb = full0 + 8 * s;
+                a_mbar_expect_tx(fb, bp.do_v ? BW_STAGE_B : 3 * TILE_B);
+                const int q0 = i * BQ;
+                a_tma_load(st, &tmDS, fb, k0, q0, h, b);
+                a_tma_load(st + TILE_B, &tmDS, fb, k0 + 64, q0, h, b);
+                a_tma_load(st + 4 * TILE_B, &tmQ, fb, 0, q0, h, b);
+                if (bp.do_v) {
+                    a_tma_load(st + 2 * TILE_B, &tmP, fb, k0, q0, h, b);
+                    a_tma_load(st + 3 * TILE_B, &tmP, fb, k0 + 64, q0, h, b);
+                    a_tma_load(st + 5 * TILE_B, &tmDO, fb, 0, q0, h, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D f32, A/B bf16.  dV / dK: A MN-major (bit 15), B MN-major (bit 16);  dQ: A K-major, B MN-major.  M = 128, N = dv | d.
+            const uint32_t ID_T = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BQ >> 4) << 24);
+            const uint32_t ID_DV = ID_T | ((uint32_t)(bp.dv >> 3) << 17), ID_DK = ID_T | ((uint32_t)(bp.d >> 3) << 17);
+            const uint32_t ID_DQ = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(bp.d >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+            a_mbar_wait(kfull, 0);
+            const uint32_t ka = sbase + BW_OFF_K;
+            for (int i = 0; i < nqb; ++i) {
+                const int s = i % BW_STAGES;
+                const uint32_t qb = (uint32_t)i & 1u;
+                a_mbar_wait(full0 + 8 * s, ((uint32_t)i / BW_STAGES) & 1u);
+                a_mbar_wait(dqempty0 + 8 * qb, (((uint32_t)i >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = sbase + BW_OFF_ST + s * BW_STAGE_B;
+                const uint32_t dsa = st, pa = st + 2 * TILE_B, qa = st + 4 * TILE_B, doa = st + 5 * TILE_B;
+#pragma unroll
+                for (int k = 0; k < BQ / 16; ++k) {                    // contraction over the 128 query rows of the block
+                    // A = (dS | P)^T: MN-major, M = keys in two 64-key slabs (LBO = slab stride), 16 query rows per step (2 x SBO)
+                    // B = Q | dO    : MN-major, N = head dim inside the 128-byte rows, 16 query rows per step
+                    if (bp.do_v) a_umma(tDV, a_umma_desc(pa + k * 2048, TILE_B, 1024), a_umma_desc(doa + k * 2048, TILE_B, 1024), ID_DV, (i | k) != 0 ? 1u : 0u);
+                    a_umma(tDK, a_umma_desc(dsa + k * 2048, TILE_B, 1024), a_umma_desc(qa + k * 2048, TILE_B, 1024), ID_DK, (i | k) != 0 ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {                   // contraction over the 128 keys
+                    // A = dS: K-major, 64-key slabs, 32 bytes per step;  B = K_j: MN-major, 16 key rows per step
+                    a_umma(tDQ + qb * 64, a_umma_desc(dsa + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024), a_umma_desc(ka + k * 2048, TILE_B, 1024), ID_DQ,
+                           k != 0 ? 1u : 0u);
+                }
+                a_commit(empty0 + 8 * s);
+                a_commit(dqfull0 + 8 * qb);
+            }
+            a_commit(accfull);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+        for (int i = 0; i < nqb; ++i) {
+            const uint32_t qb = (uint32_t)i & 1u;
+            a_mbar_wait(dqfull0 + 8 * qb, ((uint32_t)i >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[64];
+            A_TMEM_LD32(tDQ + tlane + qb * 64, r);
+            A_TMEM_LD32(tDQ + tlane + qb * 64 + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) a_mbar_arrive(dqempty0 + 8 * qb);
+            const int q = i * BQ + row;
+            if (q < bp.Lq) {
+                float* dst = bp.dq_acc + (long long)b * bp.dq_sb + (long long)q * bp.dq_ld + (long long)h * bp.d;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    if (g * 4 < bp.d)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4), "f"(__uint_as_float(r[g * 4]) * bp.alpha),
+                                     "f"(__uint_as_float(r[g * 4 + 1]) * bp.alpha), "f"(__uint_as_float(r[g * 4 + 2]) * bp.alpha),
+                                     "f"(__uint_as_float(r[g * 4 + 3]) * bp.alpha) : "memory");
+                }
+            }
+        }
+        a_mbar_wait(accfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int key = k0 + row;
+        {
+            uint32_t r[64];
+            A_TMEM_LD32(tDK + tlane, r);
+            A_TMEM_LD32(tDK + tlane + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (key < bp.Lk) {
+                uint16_t* dst = bp.dk + (long long)b * bp.dk_sb + (long long)key * bp.dk_ld + (long long)h * bp.d;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    if (g * 8 < bp.d)
+                        *reinterpret_cast<uint4*>(dst + g * 8) =
+                            make_uint4(pack_bf16x2(__uint_as_float(r[g * 8]) * bp.alpha, __uint_as_float(r[g * 8 + 1]) * bp.alpha),
+                                       pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * bp.alpha, __uint_as_float(r[g * 8 + 3]) * bp.alpha),
+                                       pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * bp.alpha, __uint_as_float(r[g * 8 + 5]) * bp.alpha),
+                                       pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * bp.alpha, __uint_as_float(r[g * 8 + 7]) * bp.alpha));
+            }
+        }
+        if (bp.do_v) {
+            uint32_t r[64];
+            A_TMEM_LD32(tDV + tlane, r);
+            A_TMEM_LD32(tDV + tlane + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (key < bp.Lk) {
+                uint16_t* dst = bp.dvp + (long long)b * bp.dv_sb + (long long)key * bp.dv_ld + (long long)h * bp.dv;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    if (g * 8 < bp.dv)
+                        *reinterpret_cast<uint4*>(dst + g * 8) =
+                            make_uint4(pack_bf16x2(__uint_as_float(r[g * 8]), __uint_as_float(r[g * 8 + 1])), pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
+                                       pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])), pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+}
+
+// fp32 accumulation buffer [rows, E] -> bf16 destination with its own row pitch (the q third of a packed dqkv, for example)
+__global__ void __launch_bounds__(256) dq_cast_kernel(const float* __restrict__ src, long long rows, int E, uint16_t* __restrict__ dst, long long dst_ld, long long dst_sb,
+                                                      long long rows_per_batch) {
+    const long long n4 = rows * (E / 4);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / (E / 4);
+        const int c = (int)(t % (E / 4)) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + r * E + c);
+        const long long bb = r / rows_per_batch, rr = r % rows_per_batch;
+        *reinterpret_cast<uint2*>(dst + bb * dst_sb + rr * dst_ld + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -495,6 +694,72 @@ extern "C" __attribute__((visibility("default"))) int spe_attention_fwd(const sp
     SpeProfScope prof(SPE_FAM_ATTN_FUSED, bytes, st);
     dim3 grid((a->Lq + BQ - 1) / BQ, a->H, a->B);
     attn_fwd_kernel<<<grid, AT_THREADS, smem, st>>>(tQ, tK, tV, tQ2, tK2, tP, ap);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+static int make_tmap_n2(CUtensorMap* tm, const void* ptr, int B, int H, int Lq, int64_t ld) {
+    PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(spe_tmap_encode_fn());
+    SPE_CHECK(enc, "cuTensorMapEncodeTiled not available");
+    SPE_CHECK(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "attention N^2 operand must be 16-byte regular");
+    cuuint64_t gdim[4] = {(cuuint64_t)ld, (cuuint64_t)Lq, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)Lq * ld * 2, (cuuint64_t)H * Lq * ld * 2};
+    cuuint32_t box[4] = {64, 128, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SPE_CHECK(r == CUDA_SUCCESS, "tensor map for an attention N^2 operand failed (%d)", (int)r);
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t spe_attention_bwd_gemms_workspace(int B, int H, int Lq, int d) { return (int64_t)B * Lq * H * d; }
+
+extern "C" __attribute__((visibility("default"))) int spe_attention_bwd_gemms(const spe_attention_bwd_args* a, void* stream) {
+    SPE_CHECK(a && a->dS && a->q && a->k && a->dq && a->dk && a->workspace, "spe_attention_bwd_gemms: null argument");
+    SPE_CHECK(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "spe_attention_bwd_gemms: bad shape");
+    SPE_CHECK(a->d > 0 && a->d <= 64 && a->d % 16 == 0, "spe_attention_bwd_gemms: head dim %d must be a multiple of 16 and <= 64", a->d);
+    const bool do_v = a->P != nullptr;
+    SPE_CHECK(!do_v || (a->dO && a->dv_out && a->dv > 0 && a->dv <= 64 && a->dv % 16 == 0), "spe_attention_bwd_gemms: dV needs P, dO, dv_out and dv in {16..64}");
+    SPE_CHECK(a->ld >= a->Lk, "spe_attention_bwd_gemms: ld < Lk");
+    CUtensorMap tDS, tP, tQ, tK, tDO;
+    memset(&tP, 0, sizeof(tP)); memset(&tDO, 0, sizeof(tDO));
+    if (make_tmap_n2(&tDS, a->dS, a->B, a->H, a->Lq, a->ld)) return -1;
+    if (do_v && make_tmap_n2(&tP, a->P, a->B, a->H, a->Lq, a->ld)) return -1;
+    if (spe_make_tmap_bf16(&tQ, a->q, SPE_MAJOR_K, a->Lq, a->d, a->q_ld, a->q_sb, a->d, a->B, a->H, BQ)) return -1;
+    if (spe_make_tmap_bf16(&tK, a->k, SPE_MAJOR_K, a->Lk, a->d, a->k_ld, a->k_sb, a->d, a->B, a->H, BKV)) return -1;
+    if (do_v && spe_make_tmap_bf16(&tDO, a->dO, SPE_MAJOR_K, a->Lq, a->dv, a->do_ld, a->do_sb, a->dv, a->B, a->H, BQ)) return -1;
+    SPE_CHECK(a->dq_ld % 4 == 0 && a->dq_sb % 4 == 0 && a->dk_ld % 8 == 0 && a->dk_sb % 8 == 0 && (!do_v || (a->dv_ld % 8 == 0 && a->dv_sb % 8 == 0)),
+              "spe_attention_bwd_gemms: output pitches must be 16-byte regular");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int E = a->H * a->d;
+    SPE_CUDA(cudaMemsetAsync(a->workspace, 0, (size_t)a->B * a->Lq * E * 4, st));
+    BwdParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.Lq = a->Lq; bp.Lk = a->Lk; bp.H = a->H; bp.nqb = (a->Lq + BQ - 1) / BQ;
+    bp.d = a->d; bp.dv = do_v ? a->dv : 16; bp.do_v = do_v ? 1 : 0;
+    bp.alpha = a->alpha;
+    bp.dq_acc = a->workspace; bp.dq_ld = E; bp.dq_sb = (long long)a->Lq * E;
+    bp.dk = reinterpret_cast<uint16_t*>(a->dk); bp.dk_ld = a->dk_ld; bp.dk_sb = a->dk_sb;
+    bp.dvp = reinterpret_cast<uint16_t*>(a->dv_out); bp.dv_ld = a->dv_ld; bp.dv_sb = a->dv_sb;
+    constexpr size_t SMEM = BW_OFF_BAR + BW_NBAR * 8 + 16 + 1024;
+    static_assert(SMEM <= 232448, "shared memory budget exceeded");
+    static bool attr_done = false;
+    if (!attr_done) {
+        SPE_CUDA(cudaFuncSetAttribute(attn_bwd_gemms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_done = true;
+    }
+    {
+        // algorithmic bytes: dS (+ P) read once, Q / K / dO read, dQ / dK / dV written
+        const double n2 = 2.0 * a->B * a->H * (double)a->Lq * a->Lk;
+        SpeProfScope prof(SPE_FAM_GEMM_ATTN, n2 * (do_v ? 2.0 : 1.0) + 2.0 * a->B * a->H * ((double)a->Lq * (2 * a->d + a->dv) + (double)a->Lk * (2 * a->d + a->dv)), st);
+        dim3 grid((a->Lk + BKV - 1) / BKV, a->H, a->B);
+        attn_bwd_gemms_kernel<<<grid, BW_THREADS, SMEM, st>>>(tDS, tP, tQ, tK, tDO, bp);
+        SPE_LAUNCHED();
+    }
+    const long long rows = (long long)a->B * a->Lq;
+    long long blocks = (rows * (E / 4) + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    dq_cast_kernel<<<(int)blocks, 256, 0, st>>>(a->workspace, rows, E, reinterpret_cast<uint16_t*>(a->dq), a->dq_ld, a->dq_sb, a->Lq);
     SPE_LAUNCHED();
     return 0;
 }

@@ -596,6 +596,26 @@ def fused_attention_fwd(q, k, v, q2, k2, mask_u8, H, scale, out, P=None, lse=Non
     return out
 
 
+def _fused_bwd_ok(q, k, dO, H):
+    if not _fused_attention_ok(q, k, dO, None, None, H):
+        return False
+    return True
+
+
+def fused_attention_bwd_gemms(dS, P, q, k, dO, H, alpha, dq, dk, dv):
+    """dV = P^T dO, dK = alpha dS^T q, dQ = alpha dS k in one pass over dS / P (attn_fused.cu).  P / dO / dv None: dQ, dK only."""
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    d = E // H
+    ws = torch.empty(int(lib().spe_attention_bwd_gemms_workspace(B, H, Lq, d)), dtype=torch.float32, device=q.device)
+    a = _lib.AttentionBwdArgs(B, H, Lq, Lk, d, (dO.shape[2] // H if dO is not None else 0),
+                              dS.data_ptr(), ptr(P), dS.shape[3], q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                              ptr(dO), (dO.stride(1) if dO is not None else 0), (dO.stride(0) if dO is not None else 0), alpha,
+                              dq.data_ptr(), dq.stride(1), dq.stride(0), dk.data_ptr(), dk.stride(1), dk.stride(0),
+                              ptr(dv), (dv.stride(1) if dv is not None else 0), (dv.stride(0) if dv is not None else 0), ws.data_ptr())
+    check(lib().spe_attention_bwd_gemms(C.byref(a), stream()))
+
+
 class AttentionFn(torch.autograd.Function):
     """softmax(scale * (q k^T [+ q2 k2^T]) + key_padding_mask) v, heads packed along the feature dim.
     nn.MultiheadAttention core (transformer.py:280) and models/attention.py:345-378 (d_qk != d_v, the
@@ -644,6 +664,20 @@ class AttentionFn(torch.autograd.Function):
         B, Lq, _ = q.shape
         Lk = k.shape[1]
         dO = dO.contiguous()
+        if _fused_bwd_ok(q, k, dO, H) and (q2 is None or _fused_bwd_ok(q2, k2, dO, H)):
+            dv_h = v.shape[2] // H
+            dP = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=v.device)
+            gemm(dO, v, dP, Lq, Lk, dv_h, lda=dO.stride(1), a_sb=(dO.stride(0), dv_h), ldb=v.stride(1), b_sb=(v.stride(0), dv_h), ldc=ld,
+                 c_sb=(H * Lq * ld, Lq * ld), batch=(B, H))
+            check(lib().spe_softmax_bwd(ptr(P), ptr(dP), ptr(dP), B, H, Lq, Lk, ld, stream()))
+            dq, dk = torch.empty_like(q, memory_format=torch.contiguous_format), torch.empty_like(k, memory_format=torch.contiguous_format)
+            dV = torch.empty((B, Lk, v.shape[2]), dtype=torch.bfloat16, device=v.device)
+            fused_attention_bwd_gemms(dP, P, q, k, dO, H, scale, dq, dk, dV)       # one pass over dS and P: dQ, dK, dV
+            dq2 = dk2 = None
+            if q2 is not None:
+                dq2, dk2 = torch.empty_like(q2, memory_format=torch.contiguous_format), torch.empty_like(k2, memory_format=torch.contiguous_format)
+                fused_attention_bwd_gemms(dP, None, q2, k2, None, H, scale, dq2, dk2, None)
+            return dq, dk, dV, dq2, dk2, None, None, None, None
         dP, dV = _attn_bwd_common(dO, P, v, H, Lq, Lk, ld)
         check(lib().spe_softmax_bwd(ptr(P), ptr(dP), ptr(dP), B, H, Lq, Lk, ld, stream()))
         dq, dk = _dq_dk(dP, q, k, H, scale, Lq, Lk, ld)
@@ -707,8 +741,10 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         gemm(dO, v, dA, N, N, dh, lda=dO.stride(1), a_sb=(dO.stride(0), dh), ldb=v.stride(1), b_sb=(v.stride(0), dh), ldc=ld,
              c_sb=(H * N * ld, N * ld), batch=(B, H))
         dv = dqkv[:, :, 2 * D:]
-        gemm(A, dO, dv, N, dh, N, a_major=MAJOR_MN, lda=ld, a_sb=(H * N * ld, N * ld), b_major=MAJOR_MN, ldb=dO.stride(1), b_sb=(dO.stride(0), dh),
-             ldc=dv.stride(1), c_sb=(dv.stride(0), dh), batch=(B, H))
+        fused = _fused_bwd_ok(q, k, dO, H)
+        if not fused:
+            gemm(A, dO, dv, N, dh, N, a_major=MAJOR_MN, lda=ld, a_sb=(H * N * ld, N * ld), b_major=MAJOR_MN, ldb=dO.stride(1), b_sb=(dO.stride(0), dh),
+                 ldc=dv.stride(1), c_sb=(dv.stride(0), dh), batch=(B, H))
         dWl_b, dWl = _grad_out(Wl, Wl.shape, qkv.device)
         dWw_b, dWw = _grad_out(Ww, Ww.shape, qkv.device)
         junk = torch.zeros((2, H), dtype=torch.float32, device=qkv.device)      # the kernel's own bias sums (not used, see below)
@@ -716,7 +752,10 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         ws = torch.empty(nws, dtype=torch.float32, device=qkv.device)
         check(lib().spe_talking_softmax_bwd(ptr(S), ptr(dA), ptr(dA), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, ptr(dWl_b), ptr(junk[0]),
                                             ptr(dWw_b), ptr(junk[1]), ptr(ws), nws, stream()))
-        _dq_dk(dA, q, k, H, scale, N, N, ld, dq_out=dqkv[:, :, :D], dk_out=dqkv[:, :, D:2 * D])
+        if fused:       # dQ, dK, dV from one pass over dS (= dA, in place) and A
+            fused_attention_bwd_gemms(dA, A, q, k, dO, H, scale, dqkv[:, :, :D], dqkv[:, :, D:2 * D], dv)
+        else:
+            _dq_dk(dA, q, k, H, scale, N, N, ld, dq_out=dqkv[:, :, :D], dk_out=dqkv[:, :, D:2 * D])
         # exact bias gradients (the kernel's own sums of bf16 dA over B*N*N keys cancel catastrophically):
         #   dbw[o] = sum_{b,i,j} dA[b,o,i,j] = sum_b colsum_i(dO[b,:,o]) . colsum_j(V[b,:,o]);   dbl = 0 (softmax is shift invariant)
         cs = torch.zeros((2, B, D), dtype=torch.float32, device=qkv.device)
