@@ -102,8 +102,11 @@ int spe_attention_fwd(const spe_attention_args* a, void* stream);
 /* Attention backward GEMMs fused (attention.py:345-372 / cait.py:379-389 backward):  ONE pass over the N^2 tensors
  *   dV[b,:,h] = P[b,h]^T dO[b,:,h]      dK[b,:,h] = alpha dS[b,h]^T Q[b,:,h]      dQ[b,:,h] = alpha dS[b,h] K[b,:,h]
  * dS, P bf16 [B,H,Lq,ld] (zero in the columns >= Lk); q, k, dO, dq, dk, dv_out bf16 with heads packed in the feature dim
- * (*_ld token stride, *_sb image stride, elements).  P == NULL: dQ and dK only (second QK segment of the conditional
- * cross-attention).  workspace: f32 [spe_attention_bwd_gemms_workspace(B,H,Lq,d)] (dQ accumulation, zeroed here). */
+ * (*_ld token stride, *_sb image stride, elements).  dv_out == NULL: dQ and dK only (second QK segment of the conditional
+ * cross-attention).  delta != NULL (f32 [B,H,Lq] = rowsum(dO o O), spe_attention_delta): the dS operand holds dP = dO V^T and
+ * the softmax backward dS = P o (dP - delta) is applied to the staged tiles in shared memory (P required) -- no separate
+ * softmax-backward pass over the N^2 tensors.  workspace: f32 [spe_attention_bwd_gemms_workspace(B,H,Lq,d)] (dQ
+ * accumulation, zeroed here). */
 typedef struct {
     int B, H, Lq, Lk, d, dv;
     const void* dS; const void* P; int64_t ld;
@@ -115,10 +118,14 @@ typedef struct {
     void* dk; int64_t dk_ld, dk_sb;
     void* dv_out; int64_t dv_ld, dv_sb;
     float* workspace;
+    const float* delta;
 } spe_attention_bwd_args;
 
 int64_t spe_attention_bwd_gemms_workspace(int B, int H, int Lq, int d);
 int spe_attention_bwd_gemms(const spe_attention_bwd_args* a, void* stream);
+/* delta[b,h,q] = sum_c dO[b,q,h*dv+c] O[b,q,h*dv+c]  (bf16 inputs with heads packed, f32 [B,H,Lq] out) */
+int spe_attention_delta(const void* dO, const void* O, int B, int H, int Lq, int dv, int64_t do_ld, int64_t do_sb, int64_t o_ld,
+                        int64_t o_sb, float* delta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row-wise / elementwise kernels of the backbone + transformer

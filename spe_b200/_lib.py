@@ -44,7 +44,7 @@ class AttentionBwdArgs(C.Structure):
         ("B", c_i), ("H", c_i), ("Lq", c_i), ("Lk", c_i), ("d", c_i), ("dv", c_i),
         ("dS", c_p), ("P", c_p), ("ld", c_l), ("q", c_p), ("q_ld", c_l), ("q_sb", c_l), ("k", c_p), ("k_ld", c_l), ("k_sb", c_l),
         ("dO", c_p), ("do_ld", c_l), ("do_sb", c_l), ("alpha", c_f), ("dq", c_p), ("dq_ld", c_l), ("dq_sb", c_l),
-        ("dk", c_p), ("dk_ld", c_l), ("dk_sb", c_l), ("dv_out", c_p), ("dv_ld", c_l), ("dv_sb", c_l), ("workspace", c_p),
+        ("dk", c_p), ("dk_ld", c_l), ("dk_sb", c_l), ("dv_out", c_p), ("dv_ld", c_l), ("dv_sb", c_l), ("workspace", c_p), ("delta", c_p),
     ]
 
 
@@ -58,6 +58,7 @@ _SIGS = {
     "spe_attention_fwd": (c_i, [C.POINTER(AttentionArgs), c_p]),
     "spe_attention_bwd_gemms": (c_i, [C.POINTER(AttentionBwdArgs), c_p]),
     "spe_attention_bwd_gemms_workspace": (c_l, [c_i, c_i, c_i, c_i]),
+    "spe_attention_delta": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_p, c_p]),
     "spe_layernorm_fwd": (c_i, [c_p, c_p, c_p, c_f, c_l, c_i, c_p, c_p, c_p, c_p, c_p]),
     "spe_layernorm_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),
     "spe_talking_softmax_fwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p]),

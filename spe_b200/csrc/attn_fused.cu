@@ -443,6 +443,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
 struct BwdParams {
     int Lq, Lk, H, nqb;
     int d, dv, do_v;
+    int from_dp;                                    // the "dS" operand holds dP: dS = P o (dP - delta) is formed in shared memory first
+    const float* delta;                             // f32 [B, H, Lq] = rowsum(dO o O), from_dp only
     float alpha;
     float* dq_acc; long long dq_ld, dq_sb;          // fp32 [B, Lq, H*d]
     uint16_t* dk; long long dk_ld, dk_sb;          // bf16 [B, Lk, H*d]
@@ -452,8 +454,8 @@ struct BwdParams {
 constexpr int BW_STAGES = 2;
 constexpr uint32_t BW_STAGE_B = 2 * 2 * TILE_B + 2 * TILE_B;                 // dS (2 slabs), P (2 slabs), Q, dO
 constexpr uint32_t BW_OFF_K = 0, BW_OFF_ST = TILE_B, BW_OFF_BAR = BW_OFF_ST + BW_STAGES * BW_STAGE_B;
-constexpr int BW_NBAR = 1 + 2 * BW_STAGES + 4 + 1;                           // kfull, full/empty[S], dqfull/dqempty[2], accfull
-constexpr int BW_THREADS = 256;
+constexpr int BW_NBAR = 1 + 3 * BW_STAGES + 4 + 1;                           // kfull, full/empty/ready[S], dqfull/dqempty[2], accfull
+constexpr int BW_THREADS = 384;
 
 __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmP,
                                                                        const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -462,8 +464,8 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = a_smem_u32(smem);
     const uint32_t bar0 = sbase + BW_OFF_BAR;
-    const uint32_t kfull = bar0, full0 = kfull + 8, empty0 = full0 + 8 * BW_STAGES, dqfull0 = empty0 + 8 * BW_STAGES, dqempty0 = dqfull0 + 16,
-                   accfull = dqempty0 + 16;
+    const uint32_t kfull = bar0, full0 = kfull + 8, empty0 = full0 + 8 * BW_STAGES, ready0 = empty0 + 8 * BW_STAGES, dqfull0 = ready0 + 8 * BW_STAGES,
+                   dqempty0 = dqfull0 + 16, accfull = dqempty0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BW_OFF_BAR + BW_NBAR * 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDS)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmP)) : "memory");
         a_mbar_init(kfull, 1);
-        for (int s = 0; s < BW_STAGES; ++s) { a_mbar_init(full0 + 8 * s, 1); a_mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < BW_STAGES; ++s) { a_mbar_init(full0 + 8 * s, 1); a_mbar_init(empty0 + 8 * s, 1); a_mbar_init(ready0 + 8 * s, 4); }
         for (int s = 0; s < 2; ++s) { a_mbar_init(dqfull0 + 8 * s, 1); a_mbar_init(dqempty0 + 8 * s, 4); }
         a_mbar_init(accfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -497,16 +499,17 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
                 const int s = i % BW_STAGES;
                 a_mbar_wait(empty0 + 8 * s, (((uint32_t)i / BW_STAGES) & 1u) ^ 1u);
                 const uint32_t st = sbase + BW_OFF_ST + s * BW_STAGE_B, fb = full0 + 8 * s;
-                a_mbar_expect_tx(fb, bp.do_v ? BW_STAGE_B : 3 * TILE_B);
+                const bool need_p = bp.do_v || bp.from_dp;
+                a_mbar_expect_tx(fb, 3 * TILE_B + (need_p ? 2 * TILE_B : 0u) + (bp.do_v ? TILE_B : 0u));
                 const int q0 = i * BQ;
                 a_tma_load(st, &tmDS, fb, k0, q0, h, b);
                 a_tma_load(st + TILE_B, &tmDS, fb, k0 + 64, q0, h, b);
                 a_tma_load(st + 4 * TILE_B, &tmQ, fb, 0, q0, h, b);
-                if (bp.do_v) {
+                if (need_p) {
                     a_tma_load(st + 2 * TILE_B, &tmP, fb, k0, q0, h, b);
                     a_tma_load(st + 3 * TILE_B, &tmP, fb, k0 + 64, q0, h, b);
-                    a_tma_load(st + 5 * TILE_B, &tmDO, fb, 0, q0, h, b);
                 }
+                if (bp.do_v) a_tma_load(st + 5 * TILE_B, &tmDO, fb, 0, q0, h, b);
             }
         }
         __syncwarp();
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
             for (int i = 0; i < nqb; ++i) {
                 const int s = i % BW_STAGES;
                 const uint32_t qb = (uint32_t)i & 1u;
-                a_mbar_wait(full0 + 8 * s, ((uint32_t)i / BW_STAGES) & 1u);
+                a_mbar_wait((bp.from_dp ? ready0 : full0) + 8 * s, ((uint32_t)i / BW_STAGES) & 1u);
                 a_mbar_wait(dqempty0 + 8 * qb, (((uint32_t)i >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = sbase + BW_OFF_ST + s * BW_STAGE_B;
@@ -545,6 +548,37 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
             a_commit(accfull);
         }
         __syncwarp();
+    } else if (warp >= 8) {
+        // ---------------- softmax backward in shared memory (from_dp): dS = P o (dP - delta), thread = query row ----------------
+        if (bp.from_dp) {
+            const int row = (warp - 8) * 32 + lane;
+            const uint32_t sw = (uint32_t)(row & 7);
+            for (int i = 0; i < nqb; ++i) {
+                const int s = i % BW_STAGES;
+                const int q = i * BQ + row;
+                const float dl = q < bp.Lq ? bp.delta[((long long)b * bp.H + h) * bp.Lq + q] : 0.f;
+                a_mbar_wait(full0 + 8 * s, ((uint32_t)i / BW_STAGES) & 1u);
+                const uint32_t st = sbase + BW_OFF_ST + s * BW_STAGE_B + (uint32_t)row * 128u;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {                          // 16-byte chunks: slab c / 8, chunk-in-row c % 8 (same swizzle in both tiles)
+                    const uint32_t off = (uint32_t)(c >> 3) * TILE_B + ((((uint32_t)c & 7u) ^ sw) << 4);
+                    uint4 dp, pp;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dp.x), "=r"(dp.y), "=r"(dp.z), "=r"(dp.w) : "r"(st + off));
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pp.x), "=r"(pp.y), "=r"(pp.z), "=r"(pp.w) : "r"(st + 2 * TILE_B + off));
+                    const uint32_t dpw[4] = {dp.x, dp.y, dp.z, dp.w}, ppw[4] = {pp.x, pp.y, pp.z, pp.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 a = unpack_bf16x2(dpw[e]), p = unpack_bf16x2(ppw[e]);
+                        o[e] = pack_bf16x2(p.x * (a.x - dl), p.y * (a.y - dl));         // P = 0 in the padding -> dS = 0 there
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) a_mbar_arrive(ready0 + 8 * s);
+            }
+        }
     } else if (warp >= 4) {
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
@@ -611,6 +645,23 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+}
+
+// delta[b,h,q] = sum_c dO[b,q,h*dv+c] * O[b,q,h*dv+c]   (= sum_j P dP of the softmax backward); one warp per (b, q) token
+__global__ void __launch_bounds__(256) attn_delta_kernel(const uint16_t* __restrict__ dO, const uint16_t* __restrict__ O, int B, int H, int Lq, int dv, long long do_ld,
+                                                         long long do_sb, long long o_ld, long long o_sb, float* __restrict__ delta) {
+    const int lane = threadIdx.x & 31;
+    const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tok >= (long long)B * Lq) return;
+    const int b = (int)(tok / Lq), q = (int)(tok % Lq);
+    const uint16_t* a = dO + (long long)b * do_sb + (long long)q * do_ld;
+    const uint16_t* o = O + (long long)b * o_sb + (long long)q * o_ld;
+    for (int h = 0; h < H; ++h) {
+        float s = 0.f;
+        for (int c = lane; c < dv; c += 32) s += bf16_to_f(a[h * dv + c]) * bf16_to_f(o[h * dv + c]);
+        s = warp_sum(s);
+        if (lane == 0) delta[((long long)b * H + h) * Lq + q] = s;
+    }
 }
 
 // fp32 accumulation buffer [rows, E] -> bf16 destination with its own row pitch (the q third of a packed dqkv, for example)
@@ -718,13 +769,15 @@ extern "C" __attribute__((visibility("default"))) int spe_attention_bwd_gemms(co
     SPE_CHECK(a && a->dS && a->q && a->k && a->dq && a->dk && a->workspace, "spe_attention_bwd_gemms: null argument");
     SPE_CHECK(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "spe_attention_bwd_gemms: bad shape");
     SPE_CHECK(a->d > 0 && a->d <= 64 && a->d % 16 == 0, "spe_attention_bwd_gemms: head dim %d must be a multiple of 16 and <= 64", a->d);
-    const bool do_v = a->P != nullptr;
-    SPE_CHECK(!do_v || (a->dO && a->dv_out && a->dv > 0 && a->dv <= 64 && a->dv % 16 == 0), "spe_attention_bwd_gemms: dV needs P, dO, dv_out and dv in {16..64}");
+    const bool do_v = a->dv_out != nullptr;
+    SPE_CHECK(!do_v || (a->P && a->dO && a->dv > 0 && a->dv <= 64 && a->dv % 16 == 0), "spe_attention_bwd_gemms: dV needs P, dO, dv_out and dv in {16..64}");
     SPE_CHECK(a->ld >= a->Lk, "spe_attention_bwd_gemms: ld < Lk");
+    const bool from_dp = a->delta != nullptr;
+    SPE_CHECK(!from_dp || a->P, "spe_attention_bwd_gemms: delta given (dS operand holds dP) needs P");
     CUtensorMap tDS, tP, tQ, tK, tDO;
     memset(&tP, 0, sizeof(tP)); memset(&tDO, 0, sizeof(tDO));
     if (make_tmap_n2(&tDS, a->dS, a->B, a->H, a->Lq, a->ld)) return -1;
-    if (do_v && make_tmap_n2(&tP, a->P, a->B, a->H, a->Lq, a->ld)) return -1;
+    if (a->P && make_tmap_n2(&tP, a->P, a->B, a->H, a->Lq, a->ld)) return -1;
     if (spe_make_tmap_bf16(&tQ, a->q, SPE_MAJOR_K, a->Lq, a->d, a->q_ld, a->q_sb, a->d, a->B, a->H, BQ)) return -1;
     if (spe_make_tmap_bf16(&tK, a->k, SPE_MAJOR_K, a->Lk, a->d, a->k_ld, a->k_sb, a->d, a->B, a->H, BKV)) return -1;
     if (do_v && spe_make_tmap_bf16(&tDO, a->dO, SPE_MAJOR_K, a->Lq, a->dv, a->do_ld, a->do_sb, a->dv, a->B, a->H, BQ)) return -1;
@@ -738,6 +791,8 @@ extern "C" __attribute__((visibility("default"))) int spe_attention_bwd_gemms(co
     bp.Lq = a->Lq; bp.Lk = a->Lk; bp.H = a->H; bp.nqb = (a->Lq + BQ - 1) / BQ;
     bp.d = a->d; bp.dv = do_v ? a->dv : 16; bp.do_v = do_v ? 1 : 0;
     bp.alpha = a->alpha;
+    bp.from_dp = from_dp ? 1 : 0;
+    bp.delta = a->delta;
     bp.dq_acc = a->workspace; bp.dq_ld = E; bp.dq_sb = (long long)a->Lq * E;
     bp.dk = reinterpret_cast<uint16_t*>(a->dk); bp.dk_ld = a->dk_ld; bp.dk_sb = a->dk_sb;
     bp.dvp = reinterpret_cast<uint16_t*>(a->dv_out); bp.dv_ld = a->dv_ld; bp.dv_sb = a->dv_sb;
@@ -760,6 +815,16 @@ extern "C" __attribute__((visibility("default"))) int spe_attention_bwd_gemms(co
     long long blocks = (rows * (E / 4) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     dq_cast_kernel<<<(int)blocks, 256, 0, st>>>(a->workspace, rows, E, reinterpret_cast<uint16_t*>(a->dq), a->dq_ld, a->dq_sb, a->Lq);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_attention_delta(const void* dO, const void* O, int B, int H, int Lq, int dv, int64_t do_ld, int64_t do_sb,
+                                                                         int64_t o_ld, int64_t o_sb, float* delta, void* stream) {
+    SPE_CHECK(dO && O && delta && B > 0 && H > 0 && Lq > 0 && dv > 0, "spe_attention_delta: bad argument");
+    const long long toks = (long long)B * Lq;
+    attn_delta_kernel<<<(unsigned)((toks + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint16_t*>(dO), reinterpret_cast<const uint16_t*>(O), B, H, Lq,
+                                                                                                    dv, do_ld, do_sb, o_ld, o_sb, delta);
     SPE_LAUNCHED();
     return 0;
 }

@@ -602,8 +602,9 @@ def _fused_bwd_ok(q, k, dO, H):
     return True
 
 
-def fused_attention_bwd_gemms(dS, P, q, k, dO, H, alpha, dq, dk, dv):
-    """dV = P^T dO, dK = alpha dS^T q, dQ = alpha dS k in one pass over dS / P (attn_fused.cu).  P / dO / dv None: dQ, dK only."""
+def fused_attention_bwd_gemms(dS, P, q, k, dO, H, alpha, dq, dk, dv, delta=None):
+    """dV = P^T dO, dK = alpha dS^T q, dQ = alpha dS k in one pass over dS / P (attn_fused.cu).  dv None: dQ, dK only.
+    delta (f32 [B,H,Lq]) given: `dS` holds dP and the softmax backward P o (dP - delta) is applied in shared memory (needs P)."""
     B, Lq, E = q.shape
     Lk = k.shape[1]
     d = E // H
@@ -612,7 +613,7 @@ def fused_attention_bwd_gemms(dS, P, q, k, dO, H, alpha, dq, dk, dv):
                               dS.data_ptr(), ptr(P), dS.shape[3], q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
                               ptr(dO), (dO.stride(1) if dO is not None else 0), (dO.stride(0) if dO is not None else 0), alpha,
                               dq.data_ptr(), dq.stride(1), dq.stride(0), dk.data_ptr(), dk.stride(1), dk.stride(0),
-                              ptr(dv), (dv.stride(1) if dv is not None else 0), (dv.stride(0) if dv is not None else 0), ws.data_ptr())
+                              ptr(dv), (dv.stride(1) if dv is not None else 0), (dv.stride(0) if dv is not None else 0), ws.data_ptr(), ptr(delta))
     check(lib().spe_attention_bwd_gemms(C.byref(a), stream()))
 
 
@@ -633,7 +634,7 @@ class AttentionFn(torch.autograd.Function):
             P = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=q.device)
             out = torch.empty((B, Lq, v.shape[2]), dtype=torch.bfloat16, device=q.device)
             fused_attention_fwd(q, k, v, q2, k2, mask_u8, H, scale, out, P=P)
-            ctx.save_for_backward(q, k, v, q2, k2, P)
+            ctx.save_for_backward(q, k, v, q2, k2, P, out)
             ctx.H, ctx.scale, ctx.ld = H, scale, ld
             return out
         S = torch.empty((B, H, Lq, ld), dtype=torch.float32, device=q.device)
@@ -646,7 +647,7 @@ class AttentionFn(torch.autograd.Function):
         del S
         out = torch.empty((B, Lq, v.shape[2]), dtype=torch.bfloat16, device=q.device)
         _pv(P, v, H, out, Lq, Lk, ld)
-        ctx.save_for_backward(q, k, v, q2, k2, P)
+        ctx.save_for_backward(q, k, v, q2, k2, P, out)
         ctx.H, ctx.scale, ctx.ld = H, scale, ld
         if want_probs:
             Pv = P.detach()
@@ -659,7 +660,7 @@ class AttentionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dO, *unused):
-        q, k, v, q2, k2, P = ctx.saved_tensors
+        q, k, v, q2, k2, P, out = ctx.saved_tensors
         H, scale, ld = ctx.H, ctx.scale, ctx.ld
         B, Lq, _ = q.shape
         Lk = k.shape[1]
@@ -669,14 +670,16 @@ class AttentionFn(torch.autograd.Function):
             dP = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=v.device)
             gemm(dO, v, dP, Lq, Lk, dv_h, lda=dO.stride(1), a_sb=(dO.stride(0), dv_h), ldb=v.stride(1), b_sb=(v.stride(0), dv_h), ldc=ld,
                  c_sb=(H * Lq * ld, Lq * ld), batch=(B, H))
-            check(lib().spe_softmax_bwd(ptr(P), ptr(dP), ptr(dP), B, H, Lq, Lk, ld, stream()))
+            # softmax backward folded into the fused kernel: dS = P o (dP - delta) is formed on the staged tiles, delta = rowsum(dO o O)
+            delta = torch.empty((B, H, Lq), dtype=torch.float32, device=v.device)
+            check(lib().spe_attention_delta(ptr(dO), ptr(out), B, H, Lq, dv_h, dO.stride(1), dO.stride(0), out.stride(1), out.stride(0), ptr(delta), stream()))
             dq, dk = torch.empty_like(q, memory_format=torch.contiguous_format), torch.empty_like(k, memory_format=torch.contiguous_format)
             dV = torch.empty((B, Lk, v.shape[2]), dtype=torch.bfloat16, device=v.device)
-            fused_attention_bwd_gemms(dP, P, q, k, dO, H, scale, dq, dk, dV)       # one pass over dS and P: dQ, dK, dV
+            fused_attention_bwd_gemms(dP, P, q, k, dO, H, scale, dq, dk, dV, delta=delta)       # one pass over dP and P: dQ, dK, dV
             dq2 = dk2 = None
             if q2 is not None:
                 dq2, dk2 = torch.empty_like(q2, memory_format=torch.contiguous_format), torch.empty_like(k2, memory_format=torch.contiguous_format)
-                fused_attention_bwd_gemms(dP, None, q2, k2, None, H, scale, dq2, dk2, None)
+                fused_attention_bwd_gemms(dP, P, q2, k2, None, H, scale, dq2, dk2, None, delta=delta)
             return dq, dk, dV, dq2, dk2, None, None, None, None
         dP, dV = _attn_bwd_common(dO, P, v, H, Lq, Lk, ld)
         check(lib().spe_softmax_bwd(ptr(P), ptr(dP), ptr(dP), B, H, Lq, Lk, ld, stream()))

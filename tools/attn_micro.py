@@ -34,3 +34,32 @@ case("cross 600x1600 two P", 8, 8, 600, 1600, 48, 48, True, masked=True)
 case("cross 600x1600 two noP", 8, 8, 600, 1600, 48, 48, True, store_p=False, masked=True)
 case("self 300x300 x16 P", 16, 8, 300, 300, 48, 48, False)
 case("class 81x1681 P", 8, 8, 81, 1681, 48, 48, False)
+
+# ---- backward GEMMs: fused (one pass over dS, P) vs softmax-backward folded in (from dP) -- graph-captured timing
+def timeit_graph(fn, reps=10):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph(); s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps): fn()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+def bwd_case(name, B, H, Lq, Lk, d):
+    q = torch.randn(B, Lq, H * d, device=dev).to(torch.bfloat16); k = torch.randn(B, Lk, H * d, device=dev).to(torch.bfloat16)
+    dO = torch.randn(B, Lq, H * d, device=dev).to(torch.bfloat16)
+    ld = ops.rup(Lk, 8)
+    dS = (torch.randn(B, H, Lq, ld, device=dev) * 0.01).to(torch.bfloat16); P = torch.rand(B, H, Lq, ld, device=dev).to(torch.bfloat16)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(k)
+    delta = torch.zeros(B, H, Lq, device=dev)
+    t0 = timeit_graph(lambda: ops.fused_attention_bwd_gemms(dS, P, q, k, dO, H, 0.1, dq, dk, dv))
+    t1 = timeit_graph(lambda: ops.fused_attention_bwd_gemms(dS, P, q, k, dO, H, 0.1, dq, dk, dv, delta=delta))
+    t2 = timeit_graph(lambda: ops.fused_attention_bwd_gemms(dS, None, q, k, None, H, 0.1, dq, dk, None))
+    n2 = B * H * Lq * ld * 2 / 1e6
+    print("%-24s fused dS+P %.3f ms (%.0f GB/s)   from dP %.3f ms   dQ,dK only %.3f ms (%.0f GB/s)" % (name, t0, 2 * n2 / t0 / 1e3, t1, t2, n2 / t2 / 1e3))
+
+bwd_case("bwd 1600x1600", 8, 8, 1600, 1600, 48)
+bwd_case("bwd cross 600x1600", 8, 8, 600, 1600, 48)
