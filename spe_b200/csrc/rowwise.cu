@@ -1044,7 +1044,9 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, int B, int Hi
         const int px = (int)(tok % w), py = (int)((tok / w) % h), b = (int)(tok / ((long long)w * h));
         const int c = k / (p * p), ky = (k / p) % p, kx = k % p;
         const float* src = img + (((long long)b * 3 + c) * Himg + (py * p + ky)) * Wimg + px * p + kx;
-        const float4 v = *reinterpret_cast<const float4*>(src);
+        float4 v;
+        if ((Wimg & 3) == 0) v = *reinterpret_cast<const float4*>(src);
+        else v = make_float4(src[0], src[1], src[2], src[3]);          // image rows not 16-byte aligned (e.g. W = 1333, COCO shape): scalar loads
         *reinterpret_cast<uint2*>(out + e) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
 }
@@ -1473,7 +1475,7 @@ extern "C" __attribute__((visibility("default"))) int spe_add_bf16_into_f32(cons
 }
 
 extern "C" __attribute__((visibility("default"))) int spe_im2col_patch(const float* img, int B, int H, int W, int p, void* out_bf16, void* stream) {
-    SPE_CHECK(img && out_bf16 && B > 0 && p % 4 == 0 && H >= p && W >= p && W % 4 == 0, "spe_im2col_patch: bad argument");
+    SPE_CHECK(img && out_bf16 && B > 0 && p % 4 == 0 && H >= p && W >= p, "spe_im2col_patch: bad argument");      // H, W need not be multiples of p (conv floors)
     const long long total = (long long)B * (H / p) * (W / p) * 3 * p * p / 4;
     im2col_patch_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(img, B, H, W, p, reinterpret_cast<uint16_t*>(out_bf16));
     SPE_LAUNCHED();

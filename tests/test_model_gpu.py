@@ -130,6 +130,25 @@ def test_state_dict_keys_match_reference(golden_dir, name):
     assert model.backbone[0].body.patch_size == 16
 
 
+def test_image_size_not_a_multiple_of_the_patch():
+    """COCO-shaped inputs (800 x 1333, BASELINE configs[3]) are not multiples of 16 and their rows are not 16-byte aligned: the patch
+    embedding floors like the reference's Conv2d (cait.py:527).  Forward parity against the oracle on a 50 x 67 image."""
+    from spe_b200 import factory
+    cfg = O.tiny_config()
+    params = O.make_params(cfg, 21)
+    model = factory.build_detector(cfg, "cuda").train()
+    model.load_state_dict(params)
+    g = torch.Generator().manual_seed(21)
+    images = torch.randn(2, 3, 50, 67, generator=g)
+    out = model(images.cuda())
+    ref = O.model_forward(params, cfg, images)
+    for r in (0, 1):
+        assert maxerr(out[r]["pred_logits"], ref[r]["pred_logits"]) < 1e-2
+        assert maxerr(out[r]["pred_boxes"], ref[r]["pred_boxes"]) < 1e-2
+    assert out[0]["cams_cls"].shape == ref[0]["cams_cls"].shape == (2, cfg.img_classes, 3, 4)
+    assert maxerr(out[0]["cams_cls"], ref[0]["cams_cls"]) < 2e-2
+
+
 def test_training_mode_criterion_and_refine_dict():
     """criterion.train(): GT jitter/repeat path (conditional_detr.py:410-431) runs, counts are ratio x G, losses finite."""
     from spe_b200 import factory
