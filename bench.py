@@ -276,7 +276,11 @@ def run_ours(args):
     ms_e2e, _, _ = timed(e2e_step, args.steps)
     # separate profiled EAGER pass (events around every launch of the main kernel families) -> roofline numbers; also counts the
     # library's launches per step (a graph replay issues the same kernels without passing through the counter)
+    # (kernels are serialised for this pass -- the timed step runs the weight-gradient GEMMs next to the data-gradient GEMMs on a second
+    #  stream, which would make the per-launch event times of overlapping kernels overlap too)
+    ops._OVERLAP = False
     ms_prof, launches_prof, fam = timed(lambda: step_eager(dev_images, dev_targets), max(1, min(args.steps, 3)), prof=True)
+    ops._OVERLAP = None
     if not args.eager:
         launches = launches_prof // max(1, min(args.steps, 3)) * args.steps
     nprof = max(1, min(args.steps, 3))

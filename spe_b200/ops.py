@@ -212,6 +212,51 @@ def _grad_out(p, shape, dev):
     return z, z
 
 
+_SIDE = {}
+_OVERLAP = None
+
+
+def _overlap_wgrad():
+    global _OVERLAP
+    if _OVERLAP is None:
+        import os
+        _OVERLAP = os.environ.get("SPE_WGRAD_OVERLAP", "1") == "1"
+    return _OVERLAP
+
+
+class _SideStream:
+    """Run the weight-gradient GEMM (+ bias column sum) of a layer on a second stream, next to the data-gradient GEMM of the same
+    layer: the two are independent, each is a persistent kernel with one CTA per SM (or fewer: the decoder's GEMMs have 19-57
+    tiles), so on one stream every launch pays its own ramp-up and tail (~8 us of a 15-25 us kernel); side by side the second
+    kernel's CTAs start on the SMs the first one has already left.  Works eagerly and inside CUDA-graph capture (fork / join)."""
+
+    def __init__(self):
+        self.cur = torch.cuda.current_stream()
+        dev = self.cur.device
+        side = _SIDE.get(dev)
+        if side is None:
+            side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+        self.side = side
+        self.ctx = None
+
+    def __enter__(self):
+        self.side.wait_stream(self.cur)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        self.cur.wait_stream(self.side)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.cur)
+
+
 def _wgrad_into(p, dy, x):
     g = grad_sink(p)
     if g is not None:
@@ -303,6 +348,13 @@ class LinearFn(torch.autograd.Function):
                 colsum_bf16(_pad_cols(dy.view(-1, N)), dbias_b)
         dy = _pad_cols(dy.view(-1, N))
         dx = None
+        if ctx.needs_input_grad[0] and _overlap_wgrad():
+            with _SideStream() as ss:                      # wgrad next to dgrad
+                dw = _wgrad_into(weight, dy, x)
+            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            _linear_dgrad(dy, w16, dx)
+            ss.join(dw)
+            return dx, dw, dbias, dres, dgamma, None, None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
             _linear_dgrad(dy, w16, dx)
@@ -359,9 +411,23 @@ class FfnFn(torch.autograd.Function):
         else:
             dy = to_bf16(dout)
             colsum_bf16(dy.view(-1, Do), db2_b)
+        aux = a if ctx.act == "gelu" else h
+        if _overlap_wgrad():
+            with _SideStream() as ss:                      # dW2 next to the fc2 data gradient
+                dw2 = _wgrad_into(w2, dy, h)
+            da = torch.empty(h.shape, dtype=torch.bfloat16, device=dev)
+            _linear_dgrad(dy, w2_16, da, act=_ACT_GRAD[ctx.act], aux_in=aux, ld_aux=Fh)
+            ss.join(dw2)
+            db1_b, db1 = _grad_out(b1, (Fh,), dev)
+            with _SideStream() as ss:                      # db1, dW1 next to the fc1 data gradient
+                colsum_bf16(da.view(-1, Fh), db1_b)
+                dw1 = _wgrad_into(w1, da, x)
+            dx = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
+            _linear_dgrad(da, w1_16, dx)
+            ss.join(dw1, db1)
+            return dx, dw1, db1, dw2, db2, (dout if ctx.has_res else None), dgamma, None
         dw2 = _wgrad_into(w2, dy, h)
         da = torch.empty(h.shape, dtype=torch.bfloat16, device=dev)
-        aux = a if ctx.act == "gelu" else h
         _linear_dgrad(dy, w2_16, da, act=_ACT_GRAD[ctx.act], aux_in=aux, ld_aux=Fh)
         db1_b, db1 = _grad_out(b1, (Fh,), dev)
         colsum_bf16(da.view(-1, Fh), db1_b)
