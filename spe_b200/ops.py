@@ -326,6 +326,7 @@ class LinearFn(torch.autograd.Function):
         dgamma = dbias = None
         dgamma_b = dbias_b = None
         dres = None
+        late_colsum = False
         if ctx.res is not None:
             d32 = dout if dout.dtype == torch.float32 else _to_f32(dout)
             dres = d32 if ctx.res == "f" else d32.sum(0)
@@ -345,15 +346,19 @@ class LinearFn(torch.autograd.Function):
                 dy = dpre
             if ctx.has_bias:
                 dbias_b, dbias = _grad_out(bias, (N,), dout.device)
-                colsum_bf16(_pad_cols(dy.view(-1, N)), dbias_b)
+                late_colsum = ctx.needs_input_grad[0] and _overlap_wgrad()
+                if not late_colsum:
+                    colsum_bf16(_pad_cols(dy.view(-1, N)), dbias_b)
         dy = _pad_cols(dy.view(-1, N))
         dx = None
         if ctx.needs_input_grad[0] and _overlap_wgrad():
-            with _SideStream() as ss:                      # wgrad next to dgrad
+            with _SideStream() as ss:                      # bias column sum + wgrad next to dgrad
+                if late_colsum:
+                    colsum_bf16(dy, dbias_b)
                 dw = _wgrad_into(weight, dy, x)
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
             _linear_dgrad(dy, w16, dx)
-            ss.join(dw)
+            ss.join(dw, dbias)
             return dx, dw, dbias, dres, dgamma, None, None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
@@ -805,6 +810,19 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
         dO = dO.contiguous()
         dqkv = torch.empty_like(qkv)
+
+        # exact bias gradients (the kernel's own sums of bf16 dA over B*N*N keys cancel catastrophically):
+        #   dbw[o] = sum_{b,i,j} dA[b,o,i,j] = sum_b colsum_i(dO[b,:,o]) . colsum_j(V[b,:,o]);   dbl = 0 (softmax is shift invariant)
+        def _dbw():
+            cs = torch.zeros((2, B, D), dtype=torch.float32, device=qkv.device)
+            check(lib().spe_colsum_bf16_batched(ptr(dO), B, N, D, dO.stride(1), dO.stride(0), ptr(cs[0]), stream()))
+            check(lib().spe_colsum_bf16_batched(ptr(v), B, N, D, v.stride(1), v.stride(0), ptr(cs[1]), stream()))
+            return (cs[0] * cs[1]).view(B, H, dh).sum((0, 2))
+
+        ss = None
+        if _overlap_wgrad():                                  # needs dO and v only: runs beside the N^2 chain on the second stream
+            with _SideStream() as ss:
+                dbw = _dbw()
         # dA = dO v^T ; dV = A^T dO (written straight into the v third of dqkv)
         dA = torch.empty((B, H, N, ld), dtype=torch.bfloat16, device=qkv.device)
         gemm(dO, v, dA, N, N, dh, lda=dO.stride(1), a_sb=(dO.stride(0), dh), ldb=v.stride(1), b_sb=(v.stride(0), dh), ldc=ld,
@@ -825,12 +843,10 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
             fused_attention_bwd_gemms(dA, A, q, k, dO, H, scale, dqkv[:, :, :D], dqkv[:, :, D:2 * D], dv)
         else:
             _dq_dk(dA, q, k, H, scale, N, N, ld, dq_out=dqkv[:, :, :D], dk_out=dqkv[:, :, D:2 * D])
-        # exact bias gradients (the kernel's own sums of bf16 dA over B*N*N keys cancel catastrophically):
-        #   dbw[o] = sum_{b,i,j} dA[b,o,i,j] = sum_b colsum_i(dO[b,:,o]) . colsum_j(V[b,:,o]);   dbl = 0 (softmax is shift invariant)
-        cs = torch.zeros((2, B, D), dtype=torch.float32, device=qkv.device)
-        check(lib().spe_colsum_bf16_batched(ptr(dO), B, N, D, dO.stride(1), dO.stride(0), ptr(cs[0]), stream()))
-        check(lib().spe_colsum_bf16_batched(ptr(v), B, N, D, v.stride(1), v.stride(0), ptr(cs[1]), stream()))
-        dbw = (cs[0] * cs[1]).view(B, H, dh).sum((0, 2))
+        if ss is not None:
+            ss.join(dbw)
+        else:
+            dbw = _dbw()
         dbl = None if grad_sink(bl) is not None else torch.zeros_like(bl)
         return dqkv, dWl, dbl, dWw, dbw, None
 
