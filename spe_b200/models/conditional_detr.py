@@ -212,6 +212,51 @@ class PostProcess(nn.Module):
         return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(topk_values, labels, boxes)]
 
 
+class PostProcessRefine(nn.Module):
+    """conditional_detr.py:641-677: per image and per class PRESENT in targets[i]['labels'], the best-scoring query's (score, box,
+    class) -- the pseudo labels of the refine stage (engine.py:122, :271-308).  Host-side glue on [B,Q,C] tensors (no_grad); the
+    reference's double Python loop is replaced by one gather per image, results identical (classes in ascending order)."""
+
+    @torch.no_grad()
+    def forward(self, outputs, target_sizes, targets=None):
+        out_logits, out_bbox = outputs["pred_logits"], outputs["pred_boxes"]
+        assert len(out_logits) == len(target_sizes) and target_sizes.shape[1] == 2
+        prob = out_logits.sigmoid()
+        top_values, top_indexes = torch.max(prob, dim=1)                                        # [B,C]
+        top_boxes = torch.gather(out_bbox, 1, top_indexes.unsqueeze(-1).repeat(1, 1, 4))        # [B,C,4]
+        C = out_logits.shape[2]
+        results = []
+        for ii in range(len(targets)):
+            present = torch.zeros(C, dtype=torch.bool, device=out_logits.device)
+            lab = targets[ii]["labels"].to(out_logits.device).long()
+            present[lab[(lab >= 0) & (lab < C)]] = True
+            cls = torch.nonzero(present).flatten()
+            results.append({"scores": top_values[ii][cls], "labels": cls, "boxes": top_boxes[ii][cls].reshape(-1, 4)})
+        return results
+
+
+class PostProcessRefineMulti(nn.Module):
+    """conditional_detr.py:680-715: like PostProcessRefine, but every query whose class probability reaches half of the class's best
+    probability is kept (queries in ascending order within a class)."""
+
+    @torch.no_grad()
+    def forward(self, outputs, target_sizes, targets=None):
+        out_logits, out_bbox = outputs["pred_logits"], outputs["pred_boxes"]
+        assert len(out_logits) == len(target_sizes) and target_sizes.shape[1] == 2
+        prob = out_logits.sigmoid()
+        top_values, _ = torch.max(prob, dim=1)
+        keep = prob >= 0.5 * top_values.unsqueeze(1).expand_as(prob)                            # [B,Q,C]
+        C = out_logits.shape[2]
+        results = []
+        for ii in range(len(targets)):
+            present = torch.zeros(C, dtype=torch.bool, device=out_logits.device)
+            lab = targets[ii]["labels"].to(out_logits.device).long()
+            present[lab[(lab >= 0) & (lab < C)]] = True
+            cq = torch.nonzero((keep[ii] & present.unsqueeze(0)).t())                          # rows (class, query), class-major ascending
+            results.append({"scores": prob[ii, cq[:, 1], cq[:, 0]], "labels": cq[:, 0], "boxes": out_bbox[ii, cq[:, 1]]})
+        return results
+
+
 def build(args):
     """conditional_detr.py:733-802: (model, criterion, criterion_refine, postprocessors, refine_postprocessors)."""
     num_classes = 21 if args.dataset_file != "coco" else 91
@@ -235,4 +280,4 @@ def build(args):
     device = torch.device(args.device)
     criterion.to(device)
     criterion_refine.to(device)
-    return model, criterion, criterion_refine, {"bbox": PostProcess()}, {"bbox": PostProcess()}
+    return model, criterion, criterion_refine, {"bbox": PostProcess()}, {"bbox": PostProcessRefine()}       # :788-790
