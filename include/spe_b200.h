@@ -123,6 +123,32 @@ typedef struct {
 
 int64_t spe_attention_bwd_gemms_workspace(int B, int H, int Lq, int d);
 int spe_attention_bwd_gemms(const spe_attention_bwd_args* a, void* stream);
+/* Fused attention backward, recomputing flavour (standard attention): given q, k, v (+ q2, k2), dO and the forward's row statistics
+ * lse (spe_attention_fwd) and delta (spe_attention_delta), produces dq, dk, dv (+ dq2, dk2) without reading or writing any N^2
+ * tensor: per (128-key block, head, image) the logits and dP = dO V^T are recomputed into TMEM, P = 2^(scale*log2e*S - lse) and
+ * dS = P o (dP - delta) go to shared memory as bf16 tiles, and dV += P^T dO, dK += dS^T Q, dQ += dS K run on them (tcgen05).
+ * Layout conventions as spe_attention_fwd.  workspace: f32 [B * Lq * H * max(d, d2)]. */
+typedef struct {
+    int B, H, Lq, Lk, d, d2, dv;
+    const void* q; int64_t q_ld, q_sb;
+    const void* k; int64_t k_ld, k_sb;
+    const void* v; int64_t v_ld, v_sb;
+    const void* q2; int64_t q2_ld, q2_sb;
+    const void* k2; int64_t k2_ld, k2_sb;
+    const void* dO; int64_t do_ld, do_sb;
+    const uint8_t* mask;
+    float scale;
+    const float* lse; const float* delta;
+    void* dq; int64_t dq_ld, dq_sb;
+    void* dk; int64_t dk_ld, dk_sb;
+    void* dv_out; int64_t dv_ld, dv_sb;
+    void* dq2; int64_t dq2_ld, dq2_sb;
+    void* dk2; int64_t dk2_ld, dk2_sb;
+    float* workspace;
+} spe_attention_bwd2_args;
+
+int spe_attention_bwd(const spe_attention_bwd2_args* a, void* stream);
+
 /* delta[b,h,q] = sum_c dO[b,q,h*dv+c] O[b,q,h*dv+c]  (bf16 inputs with heads packed, f32 [B,H,Lq] out) */
 int spe_attention_delta(const void* dO, const void* O, int B, int H, int Lq, int dv, int64_t do_ld, int64_t do_sb, int64_t o_ld,
                         int64_t o_sb, float* delta, void* stream);

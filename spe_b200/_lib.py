@@ -48,6 +48,15 @@ class AttentionBwdArgs(C.Structure):
     ]
 
 
+class AttentionBwd2Args(C.Structure):
+    _fields_ = [("B", c_i), ("H", c_i), ("Lq", c_i), ("Lk", c_i), ("d", c_i), ("d2", c_i), ("dv", c_i)] + \
+               [f for n in ("q", "k", "v", "q2", "k2") for f in ((n, c_p), (n + "_ld", c_l), (n + "_sb", c_l))] + \
+               [("dO", c_p), ("do_ld", c_l), ("do_sb", c_l), ("mask", c_p), ("scale", c_f), ("lse", c_p), ("delta", c_p)] + \
+               [f for n in ("dq", "dk") for f in ((n, c_p), (n + "_ld", c_l), (n + "_sb", c_l))] + \
+               [("dv_out", c_p), ("dv_ld", c_l), ("dv_sb", c_l)] + \
+               [f for n in ("dq2", "dk2") for f in ((n, c_p), (n + "_ld", c_l), (n + "_sb", c_l))] + [("workspace", c_p)]
+
+
 _SIGS = {
     "spe_version": (c_i, []),
     "spe_launch_count": (c_l, []),
@@ -58,6 +67,7 @@ _SIGS = {
     "spe_attention_fwd": (c_i, [C.POINTER(AttentionArgs), c_p]),
     "spe_attention_bwd_gemms": (c_i, [C.POINTER(AttentionBwdArgs), c_p]),
     "spe_attention_bwd_gemms_workspace": (c_l, [c_i, c_i, c_i, c_i]),
+    "spe_attention_bwd": (c_i, [C.POINTER(AttentionBwd2Args), c_p]),
     "spe_attention_delta": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_l, c_l, c_p, c_p]),
     "spe_layernorm_fwd": (c_i, [c_p, c_p, c_p, c_f, c_l, c_i, c_p, c_p, c_p, c_p, c_p]),
     "spe_layernorm_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p]),

@@ -677,6 +677,257 @@ __global__ void __launch_bounds__(256) dq_cast_kernel(const float* __restrict__ 
     }
 }
 
+
+// ================================================================================================
+// Fused attention BACKWARD (standard attention; recomputing flavour): nothing N^2 is read from or written to HBM.
+//   per (128-key block j, head, image):  for every 128-query block i
+//     S   = Qa_i Ka_j^T [+ Qb_i Kb_j^T]        (tcgen05, TMEM)        P  = 2^(scale2 S - lse_i), masked keys / rows -> 0
+//     dP  = dO_i V_j^T                          (tcgen05, TMEM)        dS = P o (dP - delta_i)
+//     P, dS -> bf16 swizzled shared tiles (8 transform warps, two threads per query row)
+//     dV_j += P^T dO_i,  dK_j += dS^T Qa_i   (TMEM accumulators over i),   dQ_i partial = dS Ka_j -> red.global.add.f32
+//   With two QK segments (conditional cross-attention) the kernel is launched twice with the segments swapped: each launch produces
+//   the gradients of ITS segment `a` (the logits always use both); dV only in the first.
+//   warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 transform, 12..15 dQ drain + dK / dV stores.
+// ================================================================================================
+struct Bwd2Params {
+    int Lq, Lk, H, nqb;
+    int ksa, ksb, ksv;          // UMMA k-steps: segment a, segment b (0: none), V
+    int d, dv, do_v;
+    float scale2, alpha;
+    const uint8_t* mask;
+    const float* lse; const float* delta;           // f32 [B,H,Lq]
+    float* dq_acc; long long dq_ld, dq_sb;
+    uint16_t* dk; long long dk_ld, dk_sb;
+    uint16_t* dvp; long long dv_ld, dv_sb;
+};
+constexpr uint32_t B2_OFF_KA = 0, B2_OFF_KB = TILE_B, B2_OFF_V = 2 * TILE_B, B2_OFF_ST = 3 * TILE_B;      // stage: Qa, Qb, dO
+constexpr uint32_t B2_STAGE_B = 3 * TILE_B;
+constexpr uint32_t B2_OFF_P = B2_OFF_ST + 2 * B2_STAGE_B, B2_OFF_DS = B2_OFF_P + 2 * TILE_B, B2_OFF_BAR = B2_OFF_DS + 2 * TILE_B;
+constexpr int B2_NBAR = 1 + 4 + 4 + 4 + 1;           // kfull, full/empty[2], spfull/spempty/pdready/pdempty, dqfull/dqempty[2], accfull
+constexpr int B2_THREADS = 512;
+
+__global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmKa,
+                                                                 const __grid_constant__ CUtensorMap tmQb, const __grid_constant__ CUtensorMap tmKb,
+                                                                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                                                                 const Bwd2Params bp) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = a_smem_u32(smem);
+    const uint32_t bar0 = sbase + B2_OFF_BAR;
+    const uint32_t kfull = bar0, full0 = kfull + 8, empty0 = full0 + 16, spfull = empty0 + 16, spempty = spfull + 8, pdready = spempty + 8,
+                   pdempty = pdready + 8, dqfull0 = pdempty + 8, dqempty0 = dqfull0 + 16, accfull = dqempty0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B2_OFF_BAR + B2_NBAR * 8);
+    uint32_t* mbits = tmem_slot + 4;                  // 4 words: masked keys of this block
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+    const int nqb = bp.nqb;
+    const bool two = bp.ksb > 0;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQa)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDO)) : "memory");
+        a_mbar_init(kfull, 1);
+        for (int s = 0; s < 2; ++s) { a_mbar_init(full0 + 8 * s, 1); a_mbar_init(empty0 + 8 * s, 1); a_mbar_init(dqfull0 + 8 * s, 1); a_mbar_init(dqempty0 + 8 * s, 4); }
+        a_mbar_init(spfull, 1); a_mbar_init(spempty, 8); a_mbar_init(pdready, 8); a_mbar_init(pdempty, 1);
+        a_mbar_init(accfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 3) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int j = k0 + w * 32 + lane;
+            const bool masked = j >= bp.Lk || (bp.mask != nullptr && bp.mask[(long long)b * bp.Lk + j] != 0);
+            const uint32_t bits = __ballot_sync(0xffffffffu, masked);
+            if (lane == 0) mbits[w] = bits;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;     // dQ: 2 x 64
+
+    if (warp == 0) {
+        if (lane == 0) {
+            a_mbar_expect_tx(kfull, (two ? 3u : 2u) * TILE_B);
+            a_tma_load(sbase + B2_OFF_KA, &tmKa, kfull, 0, k0, h, b);
+            if (two) a_tma_load(sbase + B2_OFF_KB, &tmKb, kfull, 0, k0, h, b);
+            a_tma_load(sbase + B2_OFF_V, &tmV, kfull, 0, k0, h, b);
+            for (int i = 0; i < nqb; ++i) {
+                const int s = i & 1;
+                a_mbar_wait(empty0 + 8 * s, (((uint32_t)i >> 1) & 1u) ^ 1u);
+                const uint32_t st = sbase + B2_OFF_ST + s * B2_STAGE_B, fb = full0 + 8 * s;
+                a_mbar_expect_tx(fb, (two ? 3u : 2u) * TILE_B);
+                a_tma_load(st, &tmQa, fb, 0, i * BQ, h, b);
+                if (two) a_tma_load(st + TILE_B, &tmQb, fb, 0, i * BQ, h, b);
+                a_tma_load(st + 2 * TILE_B, &tmDO, fb, 0, i * BQ, h, b);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t ID_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);            // K-major x K-major, N = 128
+            const uint32_t ID_T = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BQ >> 4) << 24);                 // MN-major A and B
+            const uint32_t ID_DV = ID_T | ((uint32_t)(bp.dv >> 3) << 17), ID_DK = ID_T | ((uint32_t)(bp.d >> 3) << 17);
+            const uint32_t ID_DQ = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(bp.d >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+            const uint32_t ka = sbase + B2_OFF_KA, kb = sbase + B2_OFF_KB, va = sbase + B2_OFF_V, pa = sbase + B2_OFF_P, dsa = sbase + B2_OFF_DS;
+            auto issue_sdp = [&](int i) {
+                const uint32_t st = sbase + B2_OFF_ST + (uint32_t)(i & 1) * B2_STAGE_B;
+                a_mbar_wait(full0 + 8 * (i & 1), ((uint32_t)i >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int k = 0; k < bp.ksa; ++k) a_umma(tS, a_umma_desc(st + k * 32, 0, 1024), a_umma_desc(ka + k * 32, 0, 1024), ID_S, k != 0);
+                for (int k = 0; k < bp.ksb; ++k) a_umma(tS, a_umma_desc(st + TILE_B + k * 32, 0, 1024), a_umma_desc(kb + k * 32, 0, 1024), ID_S, 1u);
+                for (int k = 0; k < bp.ksv; ++k) a_umma(tDP, a_umma_desc(st + 2 * TILE_B + k * 32, 0, 1024), a_umma_desc(va + k * 32, 0, 1024), ID_S, k != 0);
+                a_commit(spfull);
+            };
+            a_mbar_wait(kfull, 0);
+            issue_sdp(0);
+            for (int i = 0; i < nqb; ++i) {
+                const uint32_t qb = (uint32_t)i & 1u;
+                if (i + 1 < nqb) {
+                    a_mbar_wait(spempty, (uint32_t)i & 1u);                 // the transform warps have loaded S_i / dP_i out of TMEM
+                    issue_sdp(i + 1);
+                }
+                a_mbar_wait(pdready, (uint32_t)i & 1u);                     // P_i / dS_i tiles are in shared memory
+                a_mbar_wait(dqempty0 + 8 * qb, (((uint32_t)i >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = sbase + B2_OFF_ST + qb * B2_STAGE_B;
+                const uint32_t qa = st, doa = st + 2 * TILE_B;
+#pragma unroll
+                for (int k = 0; k < BQ / 16; ++k) {
+                    if (bp.do_v) a_umma(tDV, a_umma_desc(pa + k * 2048, TILE_B, 1024), a_umma_desc(doa + k * 2048, TILE_B, 1024), ID_DV, (i | k) != 0 ? 1u : 0u);
+                    a_umma(tDK, a_umma_desc(dsa + k * 2048, TILE_B, 1024), a_umma_desc(qa + k * 2048, TILE_B, 1024), ID_DK, (i | k) != 0 ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k)
+                    a_umma(tDQ + qb * 64, a_umma_desc(dsa + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024), a_umma_desc(ka + k * 2048, TILE_B, 1024), ID_DQ, k != 0 ? 1u : 0u);
+                a_commit(empty0 + 8 * qb);
+                a_commit(dqfull0 + 8 * qb);
+                a_commit(pdempty);
+            }
+            a_commit(accfull);
+        }
+        __syncwarp();
+    } else if (warp >= 4 && warp < 12) {
+        // ---------------- transform warps: two threads per query row (64 keys each) ----------------
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t tl = ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * 64u;
+        const uint32_t sw = (uint32_t)(row & 7);
+        const uint32_t bits0 = mbits[half * 2], bits1 = mbits[half * 2 + 1];
+        const uint32_t prow = sbase + B2_OFF_P + (uint32_t)half * TILE_B + (uint32_t)row * 128u;
+        const uint32_t drow = sbase + B2_OFF_DS + (uint32_t)half * TILE_B + (uint32_t)row * 128u;
+        const long long stat0 = ((long long)b * bp.H + h) * bp.Lq;
+        for (int i = 0; i < nqb; ++i) {
+            const int q = i * BQ + row;
+            // rows beyond Lq: lse = +inf -> P = 0 (their Q / dO rows are zero-filled by TMA)
+            const float lse = q < bp.Lq ? bp.lse[stat0 + q] : INFINITY;
+            const float dl = q < bp.Lq ? bp.delta[stat0 + q] : 0.f;
+            a_mbar_wait(spfull, (uint32_t)i & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t pk[32], dk[32];                      // packed bf16 pairs of this thread's 64 P and dS values
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t rs[32], rd[32];
+                A_TMEM_LD32(tS + tl + hh * 32, rs);
+                A_TMEM_LD32(tDP + tl + hh * 32, rd);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t bits = hh == 0 ? bits0 : bits1;
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float p0 = ((bits >> c) & 1u) ? 0.f : a_ex2(fmaf(__uint_as_float(rs[c]), bp.scale2, -lse));
+                    const float p1 = ((bits >> (c + 1)) & 1u) ? 0.f : a_ex2(fmaf(__uint_as_float(rs[c + 1]), bp.scale2, -lse));
+                    pk[hh * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
+                    dk[hh * 16 + (c >> 1)] = pack_bf16x2(p0 * (__uint_as_float(rd[c]) - dl), p1 * (__uint_as_float(rd[c + 1]) - dl));
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) a_mbar_arrive(spempty);
+            a_mbar_wait(pdempty, ((uint32_t)i & 1u) ^ 1u);            // the output MMAs of block i-1 have read the tiles
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const uint32_t off = (((uint32_t)g ^ sw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + off), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]), "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(drow + off), "r"(dk[g * 4]), "r"(dk[g * 4 + 1]), "r"(dk[g * 4 + 2]), "r"(dk[g * 4 + 3]) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) a_mbar_arrive(pdready);
+        }
+    } else if (warp >= 12) {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+        for (int i = 0; i < nqb; ++i) {
+            const uint32_t qb = (uint32_t)i & 1u;
+            a_mbar_wait(dqfull0 + 8 * qb, ((uint32_t)i >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[64];
+            A_TMEM_LD32(tDQ + tlane + qb * 64, r);
+            A_TMEM_LD32(tDQ + tlane + qb * 64 + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) a_mbar_arrive(dqempty0 + 8 * qb);
+            const int q = i * BQ + row;
+            if (q < bp.Lq) {
+                float* dst = bp.dq_acc + (long long)b * bp.dq_sb + (long long)q * bp.dq_ld + (long long)h * bp.d;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    if (g * 4 < bp.d)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4), "f"(__uint_as_float(r[g * 4]) * bp.alpha),
+                                     "f"(__uint_as_float(r[g * 4 + 1]) * bp.alpha), "f"(__uint_as_float(r[g * 4 + 2]) * bp.alpha),
+                                     "f"(__uint_as_float(r[g * 4 + 3]) * bp.alpha) : "memory");
+                }
+            }
+        }
+        a_mbar_wait(accfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int key = k0 + row;
+        {
+            uint32_t r[64];
+            A_TMEM_LD32(tDK + tlane, r);
+            A_TMEM_LD32(tDK + tlane + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (key < bp.Lk) {
+                uint16_t* dst = bp.dk + (long long)b * bp.dk_sb + (long long)key * bp.dk_ld + (long long)h * bp.d;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    if (g * 8 < bp.d)
+                        *reinterpret_cast<uint4*>(dst + g * 8) =
+                            make_uint4(pack_bf16x2(__uint_as_float(r[g * 8]) * bp.alpha, __uint_as_float(r[g * 8 + 1]) * bp.alpha),
+                                       pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * bp.alpha, __uint_as_float(r[g * 8 + 3]) * bp.alpha),
+                                       pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * bp.alpha, __uint_as_float(r[g * 8 + 5]) * bp.alpha),
+                                       pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * bp.alpha, __uint_as_float(r[g * 8 + 7]) * bp.alpha));
+            }
+        }
+        if (bp.do_v) {
+            uint32_t r[64];
+            A_TMEM_LD32(tDV + tlane, r);
+            A_TMEM_LD32(tDV + tlane + 32, r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (key < bp.Lk) {
+                uint16_t* dst = bp.dvp + (long long)b * bp.dv_sb + (long long)key * bp.dv_ld + (long long)h * bp.dv;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    if (g * 8 < bp.dv)
+                        *reinterpret_cast<uint4*>(dst + g * 8) =
+                            make_uint4(pack_bf16x2(__uint_as_float(r[g * 8]), __uint_as_float(r[g * 8 + 1])), pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
+                                       pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])), pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -826,5 +1077,68 @@ extern "C" __attribute__((visibility("default"))) int spe_attention_delta(const 
     attn_delta_kernel<<<(unsigned)((toks + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint16_t*>(dO), reinterpret_cast<const uint16_t*>(O), B, H, Lq,
                                                                                                     dv, do_ld, do_sb, o_ld, o_sb, delta);
     SPE_LAUNCHED();
+    return 0;
+}
+
+// one launch of attn_bwd_kernel: gradients of segment (qa, ka) [+ dV]; the logits use both segments
+static int attn_bwd_launch(const spe_attention_bwd2_args* a, const void* qa, int64_t qa_ld, int64_t qa_sb, const void* ka, int64_t ka_ld, int64_t ka_sb, int da,
+                           const void* qb, int64_t qb_ld, int64_t qb_sb, const void* kb, int64_t kb_ld, int64_t kb_sb, int db, bool do_v,
+                           void* dq, int64_t dq_ld, int64_t dq_sb, void* dk, int64_t dk_ld, int64_t dk_sb, cudaStream_t st) {
+    CUtensorMap tQa, tKa, tQb, tKb, tV, tDO;
+    memset(&tQb, 0, sizeof(tQb)); memset(&tKb, 0, sizeof(tKb));
+    if (spe_make_tmap_bf16(&tQa, qa, SPE_MAJOR_K, a->Lq, da, qa_ld, qa_sb, da, a->B, a->H, BQ)) return -1;
+    if (spe_make_tmap_bf16(&tKa, ka, SPE_MAJOR_K, a->Lk, da, ka_ld, ka_sb, da, a->B, a->H, BKV)) return -1;
+    if (qb) {
+        if (spe_make_tmap_bf16(&tQb, qb, SPE_MAJOR_K, a->Lq, db, qb_ld, qb_sb, db, a->B, a->H, BQ)) return -1;
+        if (spe_make_tmap_bf16(&tKb, kb, SPE_MAJOR_K, a->Lk, db, kb_ld, kb_sb, db, a->B, a->H, BKV)) return -1;
+    }
+    if (spe_make_tmap_bf16(&tV, a->v, SPE_MAJOR_K, a->Lk, a->dv, a->v_ld, a->v_sb, a->dv, a->B, a->H, BKV)) return -1;
+    if (spe_make_tmap_bf16(&tDO, a->dO, SPE_MAJOR_K, a->Lq, a->dv, a->do_ld, a->do_sb, a->dv, a->B, a->H, BQ)) return -1;
+    const int E = a->H * da;
+    SPE_CUDA(cudaMemsetAsync(a->workspace, 0, (size_t)a->B * a->Lq * E * 4, st));
+    Bwd2Params bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.Lq = a->Lq; bp.Lk = a->Lk; bp.H = a->H; bp.nqb = (a->Lq + BQ - 1) / BQ;
+    bp.ksa = da / 16; bp.ksb = qb ? db / 16 : 0; bp.ksv = a->dv / 16;
+    bp.d = da; bp.dv = a->dv; bp.do_v = do_v ? 1 : 0;
+    bp.scale2 = a->scale * LOG2E_F; bp.alpha = a->scale;
+    bp.mask = a->mask; bp.lse = a->lse; bp.delta = a->delta;
+    bp.dq_acc = a->workspace; bp.dq_ld = E; bp.dq_sb = (long long)a->Lq * E;
+    bp.dk = reinterpret_cast<uint16_t*>(dk); bp.dk_ld = dk_ld; bp.dk_sb = dk_sb;
+    bp.dvp = reinterpret_cast<uint16_t*>(a->dv_out); bp.dv_ld = a->dv_ld; bp.dv_sb = a->dv_sb;
+    constexpr size_t SMEM = B2_OFF_BAR + B2_NBAR * 8 + 16 + 16 + 1024;
+    static_assert(SMEM <= 232448, "shared memory budget exceeded");
+    static bool attr_done = false;
+    if (!attr_done) {
+        SPE_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_done = true;
+    }
+    {
+        // algorithmic bytes: Q, K, V, dO read, dQ, dK, dV written -- no N^2 tensor touches HBM
+        const double bytes = 2.0 * a->B * a->H * ((double)a->Lq * (2 * da + (qb ? db : 0) + a->dv) + (double)a->Lk * (2 * da + (qb ? db : 0) + 2 * a->dv));
+        SpeProfScope prof(SPE_FAM_ATTN_FUSED, bytes, st);
+        dim3 grid((a->Lk + BKV - 1) / BKV, a->H, a->B);
+        attn_bwd_kernel<<<grid, B2_THREADS, SMEM, st>>>(tQa, tKa, tQb, tKb, tV, tDO, bp);
+        SPE_LAUNCHED();
+    }
+    const long long rows = (long long)a->B * a->Lq;
+    long long blocks = (rows * (E / 4) + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    dq_cast_kernel<<<(int)blocks, 256, 0, st>>>(a->workspace, rows, E, reinterpret_cast<uint16_t*>(dq), dq_ld, dq_sb, a->Lq);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_attention_bwd(const spe_attention_bwd2_args* a, void* stream) {
+    SPE_CHECK(a && a->q && a->k && a->v && a->dO && a->lse && a->delta && a->dq && a->dk && a->dv_out && a->workspace, "spe_attention_bwd: null argument");
+    SPE_CHECK(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "spe_attention_bwd: bad shape");
+    SPE_CHECK(a->d > 0 && a->d <= 64 && a->d % 16 == 0 && a->dv > 0 && a->dv <= 64 && a->dv % 16 == 0, "spe_attention_bwd: head dims must be multiples of 16 and <= 64");
+    const bool two = a->q2 != nullptr;
+    SPE_CHECK(!two || (a->k2 && a->dq2 && a->dk2 && a->d2 > 0 && a->d2 <= 64 && a->d2 % 16 == 0), "spe_attention_bwd: bad second QK segment");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (attn_bwd_launch(a, a->q, a->q_ld, a->q_sb, a->k, a->k_ld, a->k_sb, a->d, a->q2, a->q2_ld, a->q2_sb, a->k2, a->k2_ld, a->k2_sb, a->d2, true,
+                        a->dq, a->dq_ld, a->dq_sb, a->dk, a->dk_ld, a->dk_sb, st)) return -1;
+    if (two && attn_bwd_launch(a, a->q2, a->q2_ld, a->q2_sb, a->k2, a->k2_ld, a->k2_sb, a->d2, a->q, a->q_ld, a->q_sb, a->k, a->k_ld, a->k_sb, a->d, false,
+                               a->dq2, a->dq2_ld, a->dq2_sb, a->dk2, a->dk2_ld, a->dk2_sb, st)) return -1;
     return 0;
 }

@@ -701,13 +701,22 @@ class AttentionFn(torch.autograd.Function):
         Lk = k.shape[1]
         ld = rup(Lk, 8)
         if not want_mean and _fused_attention_ok(q, k, v, q2, k2, H):
-            # fused forward (attn_fused.cu): logits stay in TMEM; P (bf16) is written once for the backward GEMMs
-            P = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=q.device)
+            # fused forward (attn_fused.cu): logits stay in TMEM.  With the recomputing backward only the row statistics are kept
+            # (nothing N^2 reaches HBM in either direction); SPE_ATTN_BWD=gemm keeps P (bf16) for the GEMM-based backward.
             out = torch.empty((B, Lq, v.shape[2]), dtype=torch.bfloat16, device=q.device)
-            fused_attention_fwd(q, k, v, q2, k2, mask_u8, H, scale, out, P=P)
-            ctx.save_for_backward(q, k, v, q2, k2, P, out)
+            if _recompute_bwd():
+                lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+                fused_attention_fwd(q, k, v, q2, k2, mask_u8, H, scale, out, lse=lse)
+                ctx.save_for_backward(q, k, v, q2, k2, lse, out, mask_u8)
+                ctx.recompute = True
+            else:
+                P = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=q.device)
+                fused_attention_fwd(q, k, v, q2, k2, mask_u8, H, scale, out, P=P)
+                ctx.save_for_backward(q, k, v, q2, k2, P, out)
+                ctx.recompute = False
             ctx.H, ctx.scale, ctx.ld = H, scale, ld
             return out
+        ctx.recompute = False
         S = torch.empty((B, H, Lq, ld), dtype=torch.float32, device=q.device)
         _qk_logits(q, k, H, scale, S, ld, q2, k2)
         P = torch.empty((B, H, Lq, ld), dtype=torch.bfloat16, device=q.device)
@@ -731,6 +740,8 @@ class AttentionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dO, *unused):
+        if ctx.recompute:
+            return AttentionFn._backward_recompute(ctx, dO)
         q, k, v, q2, k2, P, out = ctx.saved_tensors
         H, scale, ld = ctx.H, ctx.scale, ctx.ld
         B, Lq, _ = q.shape
@@ -759,6 +770,42 @@ class AttentionFn(torch.autograd.Function):
         if q2 is not None:
             dq2, dk2 = _dq_dk(dP, q2, k2, H, scale, Lq, Lk, ld)
         return dq, dk, dV, dq2, dk2, None, None, None, None
+
+
+def _attention_backward_recompute(ctx, dO):
+    """fully fused backward (attn_bwd_kernel): dq, dk, dv (+ dq2, dk2) from q, k, v, dO and the saved row statistics."""
+    q, k, v, q2, k2, lse, out, mask_u8 = ctx.saved_tensors
+    H, scale = ctx.H, ctx.scale
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    d, dv_h = E // H, v.shape[2] // H
+    d2 = q2.shape[2] // H if q2 is not None else 0
+    dO = dO.contiguous()
+    delta = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    check(lib().spe_attention_delta(ptr(dO), ptr(out), B, H, Lq, dv_h, dO.stride(1), dO.stride(0), out.stride(1), out.stride(0), ptr(delta), stream()))
+    cf = torch.contiguous_format
+    dq, dk, dV = torch.empty_like(q, memory_format=cf), torch.empty_like(k, memory_format=cf), torch.empty_like(v, memory_format=cf)
+    dq2 = torch.empty_like(q2, memory_format=cf) if q2 is not None else None
+    dk2 = torch.empty_like(k2, memory_format=cf) if k2 is not None else None
+    ws = torch.empty(B * Lq * H * max(d, d2), dtype=torch.float32, device=q.device)
+    st = lambda t: (t.data_ptr(), t.stride(1), t.stride(0)) if t is not None else (0, 0, 0)
+    a = _lib.AttentionBwd2Args(B, H, Lq, Lk, d, d2, dv_h, *st(q), *st(k), *st(v), *st(q2), *st(k2), *st(dO), ptr(mask_u8), scale, ptr(lse), ptr(delta),
+                               *st(dq), *st(dk), *st(dV), *st(dq2), *st(dk2), ws.data_ptr())
+    check(lib().spe_attention_bwd(C.byref(a), stream()))
+    return dq, dk, dV, dq2, dk2, None, None, None, None
+
+
+AttentionFn._backward_recompute = staticmethod(_attention_backward_recompute)
+
+_RECOMPUTE = None
+
+
+def _recompute_bwd():
+    global _RECOMPUTE
+    if _RECOMPUTE is None:
+        import os
+        _RECOMPUTE = os.environ.get("SPE_ATTN_BWD", "recompute") != "gemm"
+    return _RECOMPUTE
 
 
 def attention(q, k, v, H, scale, mask_u8=None, q2=None, k2=None, want_mean=False):

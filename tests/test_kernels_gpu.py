@@ -323,6 +323,14 @@ def test_fused_attention_fwd(K, masked, two, Lq, Lk, d, dv, packed):
     assert float((lse.cpu() - lse_ref.cpu()).abs().max()) < 2e-3
     for a, b_ in zip(got, ref):
         assert rel_err(a, b_) < 3e-2, rel_err(a, b_)
+    # the GEMM-flavoured fused backward (attn_bwd_gemms_kernel with the softmax backward folded in): dP and P from HBM
+    dP = torch.zeros((B, H, Lq, ld), dtype=torch.bfloat16, device=dev())
+    dP[..., :Lk] = (hd(go.float(), Lq, dv) @ hd(fr[2].detach(), Lk, dv).transpose(-1, -2)).to(torch.bfloat16)
+    delta = (go.float() * out0.float()).view(B, Lq, H, dv).sum(-1).permute(0, 2, 1).contiguous()
+    dq, dk, dvv = torch.empty_like(q.detach()).contiguous(), torch.empty_like(k.detach()).contiguous(), torch.empty_like(v.detach()).contiguous()
+    K.fused_attention_bwd_gemms(dP, P, q.detach(), k.detach(), go, H, scale, dq, dk, dvv, delta=delta)
+    for a, b_ in zip((dq, dk, dvv), ref[:3]):
+        assert rel_err(a, b_) < 3e-2, rel_err(a, b_)
 
 
 @pytest.mark.parametrize("H,N,dh", [(2, 35, 64), (4, 196, 48), (8, 130, 48), (16, 300, 48), (6, 77, 48), (12, 261, 32)])   # 16 = CaiT-M36 (cfg4), 6/12: generic-H kernels
