@@ -92,6 +92,13 @@ __device__ __forceinline__ void a_umma(uint32_t tmem_d, uint64_t adesc, uint64_t
 __device__ __forceinline__ void a_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// one lane of a CONVERGED warp issues (tcgen05.mma / TMA operands live in uniform registers: issued from inside an `if (lane == 0)`
+// region the compiler cannot prove uniformity and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall, ~140 cycles per MMA)
+__device__ __forceinline__ bool a_elect() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float a_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -174,34 +181,41 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     const uint32_t tS = tmem_base, tO = tmem_base + 256;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer ----------------
+        // ---------------- TMA producer: the whole warp walks the loop, one elected lane issues ----------------
+        if (a_elect()) {
             a_mbar_expect_tx(qfull, ap.two ? 2 * TILE_B : TILE_B);
             a_tma_load(sbase + OFF_Q, &tmQ, qfull, 0, q0, h, b);
             if (ap.two) a_tma_load(sbase + OFF_Q2, &tmQ2, qfull, 0, q0, h, b);
-            uint32_t kit = 0;
-            for (int sweep = 0; sweep < 2; ++sweep) {
-                for (int j = 0; j < nkb; ++j, ++kit) {
-                    const uint32_t ks = kit % nks;
-                    a_mbar_wait(kempty0 + 8 * ks, ((kit / nks) & 1u) ^ 1u);
+        }
+        __syncwarp();
+        uint32_t kit = 0;
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            for (int j = 0; j < nkb; ++j, ++kit) {
+                const uint32_t ks = kit % nks;
+                a_mbar_wait(kempty0 + 8 * ks, ((kit / nks) & 1u) ^ 1u);
+                if (a_elect()) {
                     a_mbar_expect_tx(kfull0 + 8 * ks, ap.two ? 2 * TILE_B : TILE_B);
                     a_tma_load(sbase + OFF_K + ks * TILE_B, &tmK, kfull0 + 8 * ks, 0, j * BKV, h, b);
                     if (ap.two) a_tma_load(sbase + OFF_K2 + ks * TILE_B, &tmK2, kfull0 + 8 * ks, 0, j * BKV, h, b);
-                    if (sweep == 1) {
-                        const int vs = j % VS;
-                        a_mbar_wait(vempty0 + 8 * vs, ((j / VS) & 1u) ^ 1u);
+                }
+                __syncwarp();
+                if (sweep == 1) {
+                    const int vs = j % VS;
+                    a_mbar_wait(vempty0 + 8 * vs, ((j / VS) & 1u) ^ 1u);
+                    if (a_elect()) {
                         a_mbar_expect_tx(vfull0 + 8 * vs, 2 * VBOX_B);
                         // V tile MN-major: two boxes of [64 keys x 64 (dv, zero filled beyond dv)]
                         a_tma_load(sbase + OFF_V + vs * 2 * VBOX_B, &tmV, vfull0 + 8 * vs, 0, j * BKV, h, b);
                         a_tma_load(sbase + OFF_V + vs * 2 * VBOX_B + VBOX_B, &tmV, vfull0 + 8 * vs, 0, j * BKV + 64, h, b);
                     }
+                    __syncwarp();
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
+        {
+            // ---------------- MMA issuer: the whole warp walks the loop, one elected lane issues ----------------
             // instruction descriptors: D f32, A/B bf16; S: both K-major, N = 128;  PV: A K-major, B MN-major, N = dv
             const uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
             const uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(ap.dv >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
@@ -214,14 +228,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
                 a_mbar_wait(kfull0 + 8 * ks, (kit / nks) & 1u);
                 a_mbar_wait(sempty0 + 8 * sb, ((sit >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t qa = sbase + OFF_Q, ka = sbase + OFF_K + ks * TILE_B;
-                for (int k = 0; k < ap.ksteps1; ++k) a_umma(tS + sb * 128, a_umma_desc(qa + k * 32, 0, 1024), a_umma_desc(ka + k * 32, 0, 1024), IDESC_S, k != 0);
-                if (ap.two) {
-                    const uint32_t qa2 = sbase + OFF_Q2, ka2 = sbase + OFF_K2 + ks * TILE_B;
-                    for (int k = 0; k < ap.ksteps2; ++k) a_umma(tS + sb * 128, a_umma_desc(qa2 + k * 32, 0, 1024), a_umma_desc(ka2 + k * 32, 0, 1024), IDESC_S, 1u);
+                if (a_elect()) {
+                    const uint32_t qa = sbase + OFF_Q, ka = sbase + OFF_K + ks * TILE_B;
+                    for (int k = 0; k < ap.ksteps1; ++k) a_umma(tS + sb * 128, a_umma_desc(qa + k * 32, 0, 1024), a_umma_desc(ka + k * 32, 0, 1024), IDESC_S, k != 0);
+                    if (ap.two) {
+                        const uint32_t qa2 = sbase + OFF_Q2, ka2 = sbase + OFF_K2 + ks * TILE_B;
+                        for (int k = 0; k < ap.ksteps2; ++k) a_umma(tS + sb * 128, a_umma_desc(qa2 + k * 32, 0, 1024), a_umma_desc(ka2 + k * 32, 0, 1024), IDESC_S, 1u);
+                    }
+                    a_commit(kempty0 + 8 * ks);
+                    a_commit(sfull0 + 8 * sb);
                 }
-                a_commit(kempty0 + 8 * ks);
-                a_commit(sfull0 + 8 * sb);
+                __syncwarp();
                 ++kit; ++sit;
             };
             for (int j = 0; j < nkb; ++j) issue_s();                  // sweep 1
@@ -236,19 +253,22 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
                 a_mbar_wait(pfull0 + 8 * pb, ((uint32_t)j >> 1) & 1u);
                 a_mbar_wait(vfull0 + 8 * vs, ((uint32_t)j / VS) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t pa = sbase + OFF_P + pb * 2 * TILE_B, va = sbase + OFF_V + vs * 2 * VBOX_B;
+                if (a_elect()) {
+                    const uint32_t pa = sbase + OFF_P + pb * 2 * TILE_B, va = sbase + OFF_V + vs * 2 * VBOX_B;
 #pragma unroll
-                for (int k = 0; k < BKV / 16; ++k) {
-                    // P: K-major, 64-key halves (k / 4), 32 bytes per k-step inside the 128-byte swizzle row
-                    // V: MN-major, 64-key halves, 16 key rows = 2 groups of 8 rows (SBO 1024 B) per k-step
-                    const uint64_t ad = a_umma_desc(pa + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024);
-                    const uint64_t bd = a_umma_desc(va + (k >> 2) * VBOX_B + (k & 3) * 2048, VBOX_B, 1024);
-                    a_umma(tO, ad, bd, IDESC_PV, (j | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BKV / 16; ++k) {
+                        // P: K-major, 64-key halves (k / 4), 32 bytes per k-step inside the 128-byte swizzle row
+                        // V: MN-major, 64-key halves, 16 key rows = 2 groups of 8 rows (SBO 1024 B) per k-step
+                        const uint64_t ad = a_umma_desc(pa + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024);
+                        const uint64_t bd = a_umma_desc(va + (k >> 2) * VBOX_B + (k & 3) * 2048, VBOX_B, 1024);
+                        a_umma(tO, ad, bd, IDESC_PV, (j | k) != 0 ? 1u : 0u);
+                    }
+                    a_commit(vempty0 + 8 * vs);
+                    a_commit(pempty0 + 8 * pb);
                 }
-                a_commit(vempty0 + 8 * vs);
-                a_commit(pempty0 + 8 * pb);
+                __syncwarp();
             }
-            a_commit(ofull);
+            if (a_elect()) a_commit(ofull);
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -449,6 +469,7 @@ struct BwdParams {
     float* dq_acc; long long dq_ld, dq_sb;          // fp32 [B, Lq, H*d]
     uint16_t* dk; long long dk_ld, dk_sb;          // bf16 [B, Lk, H*d]
     uint16_t* dvp; long long dv_ld, dv_sb;         // bf16 [B, Lk, H*dv]
+    int dbg;                                        // timing experiments (SPE_ATTN_DBG): 8 = skip the dQ red.add
 };
 
 constexpr int BW_STAGES = 2;
@@ -492,12 +513,15 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
     const uint32_t tDV = tmem_base, tDK = tmem_base + 64, tDQ = tmem_base + 128;        // dQ: 2 x 64 columns
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (a_elect()) {
             a_mbar_expect_tx(kfull, TILE_B);
             a_tma_load(sbase + BW_OFF_K, &tmK, kfull, 0, k0, h, b);
-            for (int i = 0; i < nqb; ++i) {
-                const int s = i % BW_STAGES;
-                a_mbar_wait(empty0 + 8 * s, (((uint32_t)i / BW_STAGES) & 1u) ^ 1u);
+        }
+        __syncwarp();
+        for (int i = 0; i < nqb; ++i) {
+            const int s = i % BW_STAGES;
+            a_mbar_wait(empty0 + 8 * s, (((uint32_t)i / BW_STAGES) & 1u) ^ 1u);
+            if (a_elect()) {
                 const uint32_t st = sbase + BW_OFF_ST + s * BW_STAGE_B, fb = full0 + 8 * s;
                 const bool need_p = bp.do_v || bp.from_dp;
                 a_mbar_expect_tx(fb, 3 * TILE_B + (need_p ? 2 * TILE_B : 0u) + (bp.do_v ? TILE_B : 0u));
@@ -511,10 +535,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
                 }
                 if (bp.do_v) a_tma_load(st + 5 * TILE_B, &tmDO, fb, 0, q0, h, b);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             // D f32, A/B bf16.  dV / dK: A MN-major (bit 15), B MN-major (bit 16);  dQ: A K-major, B MN-major.  M = 128, N = dv | d.
             const uint32_t ID_T = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BQ >> 4) << 24);
             const uint32_t ID_DV = ID_T | ((uint32_t)(bp.dv >> 3) << 17), ID_DK = ID_T | ((uint32_t)(bp.d >> 3) << 17);
@@ -529,6 +553,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = sbase + BW_OFF_ST + s * BW_STAGE_B;
                 const uint32_t dsa = st, pa = st + 2 * TILE_B, qa = st + 4 * TILE_B, doa = st + 5 * TILE_B;
+                if (a_elect()) {
 #pragma unroll
                 for (int k = 0; k < BQ / 16; ++k) {                    // contraction over the 128 query rows of the block
                     // A = (dS | P)^T: MN-major, M = keys in two 64-key slabs (LBO = slab stride), 16 query rows per step (2 x SBO)
@@ -544,8 +569,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
                 }
                 a_commit(empty0 + 8 * s);
                 a_commit(dqfull0 + 8 * qb);
+                }
+                __syncwarp();
             }
-            a_commit(accfull);
+            if (a_elect()) a_commit(accfull);
         }
         __syncwarp();
     } else if (warp >= 8) {
@@ -595,7 +622,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) attn_bwd_gemms_kernel(const __g
             __syncwarp();
             if (lane == 0) a_mbar_arrive(dqempty0 + 8 * qb);
             const int q = i * BQ + row;
-            if (q < bp.Lq) {
+            if (q < bp.Lq && !(bp.dbg & 8)) {
                 float* dst = bp.dq_acc + (long long)b * bp.dq_sb + (long long)q * bp.dq_ld + (long long)h * bp.d;
 #pragma unroll
                 for (int g = 0; g < 16; ++g) {
@@ -699,6 +726,7 @@ struct Bwd2Params {
     float* dq_acc; long long dq_ld, dq_sb;
     uint16_t* dk; long long dk_ld, dk_sb;
     uint16_t* dvp; long long dv_ld, dv_sb;
+    int dbg;
 };
 constexpr uint32_t B2_OFF_KA = 0, B2_OFF_KB = TILE_B, B2_OFF_V = 2 * TILE_B, B2_OFF_ST = 3 * TILE_B;      // stage: Qa, Qb, dO
 constexpr uint32_t B2_STAGE_B = 3 * TILE_B;
@@ -753,24 +781,27 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_kernel(const __grid_co
     const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;     // dQ: 2 x 64
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (a_elect()) {
             a_mbar_expect_tx(kfull, (two ? 3u : 2u) * TILE_B);
             a_tma_load(sbase + B2_OFF_KA, &tmKa, kfull, 0, k0, h, b);
             if (two) a_tma_load(sbase + B2_OFF_KB, &tmKb, kfull, 0, k0, h, b);
             a_tma_load(sbase + B2_OFF_V, &tmV, kfull, 0, k0, h, b);
-            for (int i = 0; i < nqb; ++i) {
-                const int s = i & 1;
-                a_mbar_wait(empty0 + 8 * s, (((uint32_t)i >> 1) & 1u) ^ 1u);
+        }
+        __syncwarp();
+        for (int i = 0; i < nqb; ++i) {
+            const int s = i & 1;
+            a_mbar_wait(empty0 + 8 * s, (((uint32_t)i >> 1) & 1u) ^ 1u);
+            if (a_elect()) {
                 const uint32_t st = sbase + B2_OFF_ST + s * B2_STAGE_B, fb = full0 + 8 * s;
                 a_mbar_expect_tx(fb, (two ? 3u : 2u) * TILE_B);
                 a_tma_load(st, &tmQa, fb, 0, i * BQ, h, b);
                 if (two) a_tma_load(st + TILE_B, &tmQb, fb, 0, i * BQ, h, b);
                 a_tma_load(st + 2 * TILE_B, &tmDO, fb, 0, i * BQ, h, b);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t ID_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);            // K-major x K-major, N = 128
             const uint32_t ID_T = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BQ >> 4) << 24);                 // MN-major A and B
             const uint32_t ID_DV = ID_T | ((uint32_t)(bp.dv >> 3) << 17), ID_DK = ID_T | ((uint32_t)(bp.d >> 3) << 17);
@@ -780,10 +811,13 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_kernel(const __grid_co
                 const uint32_t st = sbase + B2_OFF_ST + (uint32_t)(i & 1) * B2_STAGE_B;
                 a_mbar_wait(full0 + 8 * (i & 1), ((uint32_t)i >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int k = 0; k < bp.ksa; ++k) a_umma(tS, a_umma_desc(st + k * 32, 0, 1024), a_umma_desc(ka + k * 32, 0, 1024), ID_S, k != 0);
-                for (int k = 0; k < bp.ksb; ++k) a_umma(tS, a_umma_desc(st + TILE_B + k * 32, 0, 1024), a_umma_desc(kb + k * 32, 0, 1024), ID_S, 1u);
-                for (int k = 0; k < bp.ksv; ++k) a_umma(tDP, a_umma_desc(st + 2 * TILE_B + k * 32, 0, 1024), a_umma_desc(va + k * 32, 0, 1024), ID_S, k != 0);
-                a_commit(spfull);
+                if (a_elect()) {
+                    for (int k = 0; k < bp.ksa; ++k) a_umma(tS, a_umma_desc(st + k * 32, 0, 1024), a_umma_desc(ka + k * 32, 0, 1024), ID_S, k != 0);
+                    for (int k = 0; k < bp.ksb; ++k) a_umma(tS, a_umma_desc(st + TILE_B + k * 32, 0, 1024), a_umma_desc(kb + k * 32, 0, 1024), ID_S, 1u);
+                    for (int k = 0; k < bp.ksv; ++k) a_umma(tDP, a_umma_desc(st + 2 * TILE_B + k * 32, 0, 1024), a_umma_desc(va + k * 32, 0, 1024), ID_S, k != 0);
+                    a_commit(spfull);
+                }
+                __syncwarp();
             };
             a_mbar_wait(kfull, 0);
             issue_sdp(0);
@@ -798,19 +832,22 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_kernel(const __grid_co
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = sbase + B2_OFF_ST + qb * B2_STAGE_B;
                 const uint32_t qa = st, doa = st + 2 * TILE_B;
+                if (a_elect()) {
 #pragma unroll
-                for (int k = 0; k < BQ / 16; ++k) {
-                    if (bp.do_v) a_umma(tDV, a_umma_desc(pa + k * 2048, TILE_B, 1024), a_umma_desc(doa + k * 2048, TILE_B, 1024), ID_DV, (i | k) != 0 ? 1u : 0u);
-                    a_umma(tDK, a_umma_desc(dsa + k * 2048, TILE_B, 1024), a_umma_desc(qa + k * 2048, TILE_B, 1024), ID_DK, (i | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BQ / 16; ++k) {
+                        if (bp.do_v) a_umma(tDV, a_umma_desc(pa + k * 2048, TILE_B, 1024), a_umma_desc(doa + k * 2048, TILE_B, 1024), ID_DV, (i | k) != 0 ? 1u : 0u);
+                        a_umma(tDK, a_umma_desc(dsa + k * 2048, TILE_B, 1024), a_umma_desc(qa + k * 2048, TILE_B, 1024), ID_DK, (i | k) != 0 ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < BKV / 16; ++k)
+                        a_umma(tDQ + qb * 64, a_umma_desc(dsa + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024), a_umma_desc(ka + k * 2048, TILE_B, 1024), ID_DQ, k != 0 ? 1u : 0u);
+                    a_commit(empty0 + 8 * qb);
+                    a_commit(dqfull0 + 8 * qb);
+                    a_commit(pdempty);
                 }
-#pragma unroll
-                for (int k = 0; k < BKV / 16; ++k)
-                    a_umma(tDQ + qb * 64, a_umma_desc(dsa + (k >> 2) * TILE_B + (k & 3) * 32, 0, 1024), a_umma_desc(ka + k * 2048, TILE_B, 1024), ID_DQ, k != 0 ? 1u : 0u);
-                a_commit(empty0 + 8 * qb);
-                a_commit(dqfull0 + 8 * qb);
-                a_commit(pdempty);
+                __syncwarp();
             }
-            a_commit(accfull);
+            if (a_elect()) a_commit(accfull);
         }
         __syncwarp();
     } else if (warp >= 4 && warp < 12) {
@@ -876,7 +913,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) a_mbar_arrive(dqempty0 + 8 * qb);
             const int q = i * BQ + row;
-            if (q < bp.Lq) {
+            if (q < bp.Lq && !(bp.dbg & 8)) {
                 float* dst = bp.dq_acc + (long long)b * bp.dq_sb + (long long)q * bp.dq_ld + (long long)h * bp.d;
 #pragma unroll
                 for (int g = 0; g < 16; ++g) {
@@ -1044,6 +1081,7 @@ extern "C" __attribute__((visibility("default"))) int spe_attention_bwd_gemms(co
     bp.alpha = a->alpha;
     bp.from_dp = from_dp ? 1 : 0;
     bp.delta = a->delta;
+    { static const int dbg = getenv("SPE_ATTN_DBG") ? atoi(getenv("SPE_ATTN_DBG")) : 0; bp.dbg = dbg; }
     bp.dq_acc = a->workspace; bp.dq_ld = E; bp.dq_sb = (long long)a->Lq * E;
     bp.dk = reinterpret_cast<uint16_t*>(a->dk); bp.dk_ld = a->dk_ld; bp.dk_sb = a->dk_sb;
     bp.dvp = reinterpret_cast<uint16_t*>(a->dv_out); bp.dv_ld = a->dv_ld; bp.dv_sb = a->dv_sb;
@@ -1103,6 +1141,7 @@ static int attn_bwd_launch(const spe_attention_bwd2_args* a, const void* qa, int
     bp.d = da; bp.dv = a->dv; bp.do_v = do_v ? 1 : 0;
     bp.scale2 = a->scale * LOG2E_F; bp.alpha = a->scale;
     bp.mask = a->mask; bp.lse = a->lse; bp.delta = a->delta;
+    { static const int dbg = getenv("SPE_ATTN_DBG") ? atoi(getenv("SPE_ATTN_DBG")) : 0; bp.dbg = dbg; }
     bp.dq_acc = a->workspace; bp.dq_ld = E; bp.dq_sb = (long long)a->Lq * E;
     bp.dk = reinterpret_cast<uint16_t*>(dk); bp.dk_ld = dk_ld; bp.dk_sb = dk_sb;
     bp.dvp = reinterpret_cast<uint16_t*>(a->dv_out); bp.dv_ld = a->dv_ld; bp.dv_sb = a->dv_sb;

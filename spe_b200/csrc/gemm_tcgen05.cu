@@ -151,6 +151,14 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {       // arrive
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// one lane of a CONVERGED warp (the tcgen05.mma operands must be warp-uniform: issued from inside an `if (lane == 0)` region the
+// compiler cannot prove that and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall loop, ~140 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 #define TMEM_LD_32x32b_X32(taddr, r)                                                                         \
     asm volatile(                                                                                            \
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
@@ -359,8 +367,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer ----------------
+        {
+            // ---------------- TMA producer: the whole (converged) warp walks the loop, one elected lane issues ----------------
             uint32_t it = 0;
             for (int t = tile0; t < ep.num_tiles; t += tstride) {
                 int m0, n0, b1, b2, kb0, nkb, split;
@@ -372,48 +380,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     const uint32_t a_dst = smem_u32(sA + s * A_BYTES), b_dst = smem_u32(sB + s * B_BYTES);
                     const int kc = (kb0 + kb) * BK;
-                    if constexpr (CG2) {
-                        // both CTAs' loads complete on the LEADER's full barrier; the leader alone arms it with the bytes of the pair
-                        const uint32_t fbc = mapa_rank(full0 + 8 * s, 0u);
-                        if (cta_rank == 0) mbar_expect_tx(full0 + 8 * s, 2u * (A_BYTES + B_BYTES));
-                        if constexpr (!A_MN) {
-                            tma_load_4d_pair(a_dst, &tmA, fbc, kc, m0, b2 * ep.a_m2, b1 * ep.a_m1);
+                    if (elect_one()) {
+                        if constexpr (CG2) {
+                            // both CTAs' loads complete on the LEADER's full barrier; the leader alone arms it with the bytes of the pair
+                            const uint32_t fbc = mapa_rank(full0 + 8 * s, 0u);
+                            if (cta_rank == 0) mbar_expect_tx(full0 + 8 * s, 2u * (A_BYTES + B_BYTES));
+                            if constexpr (!A_MN) {
+                                tma_load_4d_pair(a_dst, &tmA, fbc, kc, m0, b2 * ep.a_m2, b1 * ep.a_m1);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < BM / 64; ++c) tma_load_4d_pair(a_dst + c * CHUNK_BYTES, &tmA, fbc, m0 + c * 64, kc, b2 * ep.a_m2, b1 * ep.a_m1);
+                            }
+                            if constexpr (!B_MN) {
+                                tma_load_4d_pair(b_dst, &tmB, fbc, kc, nl0, b2 * ep.b_m2, b1 * ep.b_m1);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < BNL / 64; ++c) tma_load_4d_pair(b_dst + c * CHUNK_BYTES, &tmB, fbc, nl0 + c * 64, kc, b2 * ep.b_m2, b1 * ep.b_m1);
+                            }
                         } else {
+                            const uint32_t fb = full0 + 8 * s;
+                            const bool skipA = (ep.dbg & 16) != 0, skipB = (ep.dbg & 32) != 0;      // timing experiments only
+                            mbar_expect_tx(fb, (skipA ? 0u : A_BYTES) + (skipB ? 0u : B_BYTES));
+                            if (skipA) {
+                            } else if constexpr (!A_MN) {
+                                tma_load_4d(a_dst, &tmA, fb, kc, m0, b2 * ep.a_m2, b1 * ep.a_m1);
+                            } else {
 #pragma unroll
-                            for (int c = 0; c < BM / 64; ++c) tma_load_4d_pair(a_dst + c * CHUNK_BYTES, &tmA, fbc, m0 + c * 64, kc, b2 * ep.a_m2, b1 * ep.a_m1);
+                                for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + c * 64, kc, b2 * ep.a_m2, b1 * ep.a_m1);
+                            }
+                            if (skipB) {
+                            } else if constexpr (!B_MN) {
+                                tma_load_4d(b_dst, &tmB, fb, kc, n0, b2 * ep.b_m2, b1 * ep.b_m1);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + c * 64, kc, b2 * ep.b_m2, b1 * ep.b_m1);
+                            }
                         }
-                        if constexpr (!B_MN) {
-                            tma_load_4d_pair(b_dst, &tmB, fbc, kc, nl0, b2 * ep.b_m2, b1 * ep.b_m1);
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < BNL / 64; ++c) tma_load_4d_pair(b_dst + c * CHUNK_BYTES, &tmB, fbc, nl0 + c * 64, kc, b2 * ep.b_m2, b1 * ep.b_m1);
-                        }
-                        continue;
                     }
-                    const uint32_t fb = full0 + 8 * s;
-                    const bool skipA = (ep.dbg & 16) != 0, skipB = (ep.dbg & 32) != 0;      // timing experiments only
-                    mbar_expect_tx(fb, (skipA ? 0u : A_BYTES) + (skipB ? 0u : B_BYTES));
-                    if (skipA) {
-                    } else if constexpr (!A_MN) {
-                        tma_load_4d(a_dst, &tmA, fb, kc, m0, b2 * ep.a_m2, b1 * ep.a_m1);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < BM / 64; ++c) tma_load_4d(a_dst + c * CHUNK_BYTES, &tmA, fb, m0 + c * 64, kc, b2 * ep.a_m2, b1 * ep.a_m1);
-                    }
-                    if (skipB) {
-                    } else if constexpr (!B_MN) {
-                        tma_load_4d(b_dst, &tmB, fb, kc, n0, b2 * ep.b_m2, b1 * ep.b_m1);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < BN / 64; ++c) tma_load_4d(b_dst + c * CHUNK_BYTES, &tmB, fb, n0 + c * 64, kc, b2 * ep.b_m2, b1 * ep.b_m1);
-                    }
+                    __syncwarp();
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && cta_rank == 0) {
-            // ---------------- MMA issuer (pair mode: leader CTA only) ----------------
+        if (cta_rank == 0) {
+            // ---------------- MMA issuer (pair mode: leader CTA only): the whole warp walks the loop, one elected lane issues ----------------
             uint32_t it = 0, ti = 0;
             for (int t = tile0; t < ep.num_tiles; t += tstride, ++ti) {
                 int m0, n0, b1, b2, kb0, nkb, split;
@@ -428,21 +439,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     mbar_wait(full0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // K-major: 16 k-elements = 32 B inside the 128B swizzle row; SBO = 8 rows * 128 B.
-                        // MN-major: 16 k-rows = 2 groups of 8 rows (SBO = 1024 B); LBO = next 64-wide MN chunk.
-                        const uint64_t ad = A_MN ? umma_desc(a_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(a_base + k * 32, 0, 1024);
-                        const uint64_t bd = B_MN ? umma_desc(b_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(b_base + k * 32, 0, 1024);
-                        if (ep.dbg & 128) continue;      // timing experiment: no MMA issue
-                        if constexpr (CG2) umma_f16_pair(tacc, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
-                        else umma_f16(tacc, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // K-major: 16 k-elements = 32 B inside the 128B swizzle row; SBO = 8 rows * 128 B.
+                            // MN-major: 16 k-rows = 2 groups of 8 rows (SBO = 1024 B); LBO = next 64-wide MN chunk.
+                            const uint64_t ad = A_MN ? umma_desc(a_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(a_base + k * 32, 0, 1024);
+                            const uint64_t bd = B_MN ? umma_desc(b_base + k * 2048, CHUNK_BYTES, 1024) : umma_desc(b_base + k * 32, 0, 1024);
+                            if (ep.dbg & 128) continue;      // timing experiment: no MMA issue
+                            if constexpr (CG2) umma_f16_pair(tacc, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
+                            else umma_f16(tacc, ad, bd, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        if constexpr (CG2) umma_commit_pair(empty0 + 8 * s);
+                        else umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs retire
                     }
-                    if constexpr (CG2) umma_commit_pair(empty0 + 8 * s);
-                    else umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs retire
+                    __syncwarp();
                 }
-                if constexpr (CG2) umma_commit_pair(tfull0 + 8 * buf);
-                else umma_commit(tfull0 + 8 * buf);         // accumulator of this tile complete
+                if (elect_one()) {
+                    if constexpr (CG2) umma_commit_pair(tfull0 + 8 * buf);
+                    else umma_commit(tfull0 + 8 * buf);         // accumulator of this tile complete
+                }
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -495,11 +512,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 // (residual / aux) that is now; otherwise only right before the first st.shared, after the TMEM load latency.
                 const bool need_drain = live && ep.tma_io && stores_pending;
                 auto drain = [&]() {
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
                 };
                 if (need_drain && loads) drain();
-                if (loads && lane == 0) {
+                if (loads && elect_one()) {
                     const bool two = nb + 32 < ep.N;
                     uint32_t bytes = 0;
                     if (has_r && lead) bytes += two ? 2 * SLAB : SLAB;
@@ -662,7 +679,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 }   // generic path
                 if (!(ep.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0 && !(ep.dbg & 1)) {
+                if (!(ep.dbg & 1) && elect_one()) {
                     if (ep.splits > 1 || ep.accum) {
                         tma_reduce_add_4d(&tmC, sRC, nb, mrow, b2, b1);
                         if (nb + 32 < ep.N) tma_reduce_add_4d(&tmC, sRC + SLAB, nb + 32, mrow, b2, b1);
@@ -685,7 +702,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                 if (lane == 0) release_acc(buf);
             }
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncwarp();
     }
 

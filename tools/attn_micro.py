@@ -63,3 +63,23 @@ def bwd_case(name, B, H, Lq, Lk, d):
 
 bwd_case("bwd 1600x1600", 8, 8, 1600, 1600, 48)
 bwd_case("bwd cross 600x1600", 8, 8, 600, 1600, 48)
+
+# ---- fully fused backward (recompute)
+from spe_b200 import _lib
+import ctypes as C
+def bwd2_case(name, B, H, Lq, Lk, d, two):
+    mk = lambda *s: torch.randn(*s, device=dev).to(torch.bfloat16)
+    q, k, v, dO = mk(B, Lq, H * d), mk(B, Lk, H * d), mk(B, Lk, H * d), mk(B, Lq, H * d)
+    q2, k2 = (mk(B, Lq, H * d), mk(B, Lk, H * d)) if two else (None, None)
+    out = torch.empty_like(dO); lse = torch.empty(B, H, Lq, device=dev)
+    scale = (d * (2 if two else 1)) ** -0.5
+    mask = torch.zeros(B, Lk, dtype=torch.uint8, device=dev)
+    ops.fused_attention_fwd(q, k, v, q2, k2, mask, H, scale, out, lse=lse)
+    class Ctx: pass
+    ctx = Ctx(); ctx.saved_tensors = (q, k, v, q2, k2, lse, out, mask); ctx.H, ctx.scale = H, scale
+    t = timeit_graph(lambda: ops._attention_backward_recompute(ctx, dO))
+    flops = 2.0 * B * H * Lq * Lk * (d * (2 if two else 1) * 3 + d * 2) * (2 if two else 1)
+    print("%-28s fused recompute bwd %.3f ms" % (name, t))
+bwd2_case("bwd2 encoder 1600x1600", 8, 8, 1600, 1600, 48, False)
+bwd2_case("bwd2 cross 600x1600 two", 8, 8, 600, 1600, 48, True)
+bwd2_case("bwd2 self 300x300 x16", 16, 8, 300, 300, 48, False)
