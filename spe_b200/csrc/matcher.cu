@@ -96,7 +96,7 @@ struct LsapShared {
 
 template <int T>
 __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_all, int nr, long long ldc, const int32_t* __restrict__ nc_arr,
-                                                 int max_nc, int32_t* __restrict__ row_to_col, int max_small, int max_big) {
+                                                 int max_nc, int32_t* __restrict__ row_to_col, int max_small, int max_big, int stage_cost) {
     extern __shared__ double smem_d[];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int nc = nc_arr ? nc_arr[b] : max_nc;
@@ -119,6 +119,17 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
     int* col4row = remaining + max_big;           // [max_small]
     unsigned char* SR = reinterpret_cast<unsigned char*>(col4row + max_small);   // [max_small]
     unsigned char* SC = SR + max_small;           // [max_big]
+    // optional: the problem's cost matrix staged in shared memory in INTERNAL orientation [R][Cn] -- every scan step of the transposed
+    // case (the usual one: fewer GT than queries) reads one cost per lane at stride ldc from global memory, and the algorithm is a
+    // chain of such scans: with the matrix on chip the kernel is no longer bound by that load latency.  Same values, same order.
+    float* costS = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(SC + max_big) + 15) & ~uintptr_t(15));
+    if (stage_cost) {
+        if (transposed) {
+            for (int e = tid; e < R * Cn; e += T) { const int j = e / R, i = e - j * R; costS[i * Cn + j] = __ldg(cost + (long long)j * ldc + i); }
+        } else {
+            for (int e = tid; e < R * Cn; e += T) { const int i = e / Cn, j = e - i * Cn; costS[e] = __ldg(cost + (long long)i * ldc + j); }
+        }
+    }
     __shared__ LsapShared sh;
     __shared__ Cand wbest[T / 32 > 0 ? T / 32 : 1];
 
@@ -139,7 +150,7 @@ __global__ void __launch_bounds__(T) lsap_kernel(const float* __restrict__ cost_
             Cand best; best.val = INFINITY; best.it = -1; best.unassigned = 0;
             for (int it = tid; it < num_remaining; it += T) {
                 const int j = remaining[it];
-                const float cf = transposed ? __ldg(cost + (long long)j * ldc + i) : __ldg(cost + (long long)i * ldc + j);
+                const float cf = stage_cost ? costS[i * Cn + j] : (transposed ? __ldg(cost + (long long)j * ldc + i) : __ldg(cost + (long long)i * ldc + j));
                 const double r = ((min_val + (double)cf) - ui) - v[j];
                 double s = spc[j];
                 if (r < s) { path[j] = i; spc[j] = r; s = r; }
@@ -248,18 +259,22 @@ extern "C" __attribute__((visibility("default"))) int spe_lsap_batched(const flo
     // per problem R = min(nr, nc[b]) <= small and Cn = max(nr, nc[b]) <= big
     const int mb = big;
     const int use_small = small;
-    const size_t smem = lsap_smem_bytes(use_small, mb);
+    size_t smem = lsap_smem_bytes(use_small, mb);
     SPE_CHECK(smem <= 200 * 1024, "spe_lsap_batched: problem too large for shared memory (%zu B)", smem);
+    // stage the cost matrix on chip when it fits next to the solver state (300 x 50 training problems: 60 KB; 300 x 1000 does not)
+    const size_t cost_bytes = (size_t)use_small * mb * 4 + 16;
+    const int stage_cost = smem + cost_bytes <= 160 * 1024 ? 1 : 0;
+    if (stage_cost) smem += cost_bytes;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     SpeProfScope prof(SPE_FAM_MATCHER, (double)B, st);     // work unit = images
     if (big <= 512) {
         static bool done = false;
         if (!done) { SPE_CUDA(cudaFuncSetAttribute(lsap_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
-        lsap_kernel<32><<<B, 32, smem, st>>>(cost, nr, ldc, nc, max_nc, row_to_col, use_small, mb);
+        lsap_kernel<32><<<B, 32, smem, st>>>(cost, nr, ldc, nc, max_nc, row_to_col, use_small, mb, stage_cost);
     } else {
         static bool done = false;
         if (!done) { SPE_CUDA(cudaFuncSetAttribute(lsap_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done = true; }
-        lsap_kernel<256><<<B, 256, smem, st>>>(cost, nr, ldc, nc, max_nc, row_to_col, use_small, mb);
+        lsap_kernel<256><<<B, 256, smem, st>>>(cost, nr, ldc, nc, max_nc, row_to_col, use_small, mb, stage_cost);
     }
     SPE_LAUNCHED();
     return 0;
