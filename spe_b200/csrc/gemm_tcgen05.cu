@@ -851,7 +851,7 @@ struct GemmEnv {
     GemmEnv() {
         const char* c2 = getenv("SPE_GEMM_CG2");
         // CTA-pair tiles: 0 (default) never, 1 heuristic (M >= 1024, full 256-row tiles), 2 wherever legal.  Measured on cfg2 (round 1):
-        // parity-green, but no gain yet (59.6 ms/step off vs 60.3 on): at K = 384 the tiles are bound by the MMA-issue/commit chain
+        // parity-green, but no gain yet (52.0 ms/step off vs 53.6 on): at K = 384 a launch is dominated by its ramp / barrier skeleton
         // and the epilogue, not by operand traffic (skipping ALL operand loads changes no GEMM time by more than 5%) -- see DESIGN.md.
         cg2 = c2 ? atoi(c2) : 0;
         bn256 = getenv("SPE_GEMM_BN256") != nullptr;
