@@ -348,6 +348,36 @@ __device__ __forceinline__ void mix_tile(const MixFrag& W, uint32_t bhi, uint32_
     o0 = d[0] + d[2]; o1 = d[1] + d[3];
 }
 
+// ---- single-pass fp16 variant of the two FORWARD mixes (logits S and probabilities P) ----
+// The split-precision scheme above keeps ~16 mantissa bits; the forward does not need them: S carries ~2^-9 relative noise from its bf16
+// Q / K inputs already, fp16 rounding adds 2^-11 (tools/tf32_mix_numerics.py: +2e-3 on the attention output against a 3e-3..1e-2
+// floor), and A = Ww P is rounded to bf16 on output anyway.  One cvt.rn.f16x2 per operand pair replaces pack / unpack / subtract / pack
+// and the lo-part movmatrix.  (The backward keeps the bf16 split: its dA / dL operands need the bf16 exponent range.)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void mma16816_f16(float (&d)[4], uint32_t a0, uint32_t b0) {       // rows 8-15 of A and k 8-15 are zero
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(0u), "r"(0u), "r"(0u), "r"(b0), "r"(0u));
+}
+template <int H>
+__device__ __forceinline__ uint32_t load_mix_frag16(const float* __restrict__ M, float scale, int q4, int r4) {
+    float w0 = 0.f, w1 = 0.f;
+    if (q4 < H) {
+        const int k0 = 2 * r4, k1 = 2 * r4 + 1;
+        if (k0 < H) w0 = scale * M[q4 * H + k0];
+        if (k1 < H) w1 = scale * M[q4 * H + k1];
+    }
+    return pack_f16x2(w0, w1);
+}
+__device__ __forceinline__ void mix_tile16(uint32_t W16, uint32_t b16, float bias, float& o0, float& o1) {
+    float d[4] = {bias, bias, 0.f, 0.f};
+    mma16816_f16(d, W16, b16);
+    o0 = d[0]; o1 = d[1];
+}
+
 constexpr float LOG2E = 1.4426950408889634f;
 __device__ __forceinline__ float fast_ex2(float x) {           // single MUFU.EX2 (flushes denormals; 2^-inf = 0)
     float y;
@@ -382,6 +412,24 @@ __device__ __forceinline__ void step_logits(const SRaw& raw, int base, int Nk, c
         uint32_t lo;
         split2(ok ? a0[t] : 0.f, ok ? a1[t] : 0.f, shi[t], lo);
         mix_tile(Wl, shi[t], lo, bl2, L2[t], L2[4 + t]);
+    }
+    if (tail) {
+        const int c8 = base + 8 * r4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) L2[i] = -INFINITY;
+    }
+}
+
+// fp16 single-pass version of step_logits (forward only)
+template <int H, bool TAIL = true>
+__device__ __forceinline__ void step_logits16(const SRaw& raw, int base, int Nk, uint32_t Wl16, float bl2, int q4, int r4, float (&L2)[8]) {
+    const int cb = base + 4 * q4;
+    const float a0[4] = {raw.s0.x, raw.s0.y, raw.s0.z, raw.s0.w}, a1[4] = {raw.s1.x, raw.s1.y, raw.s1.z, raw.s1.w};
+    const bool tail = TAIL && base + 32 > Nk;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const bool ok = !tail || cb + t < Nk;       // padding columns of S are never written: sanitise
+        mix_tile16(Wl16, pack_f16x2(ok ? a0[t] : 0.f, ok ? a1[t] : 0.f), bl2, L2[t], L2[4 + t]);
     }
     if (tail) {
         const int c8 = base + 8 * r4;
@@ -628,10 +676,9 @@ __host__ __device__ __forceinline__ int talking_pitch_bf16(int ld) { return ld +
 // forward sweep A: mixed logits of one step -> online (max, sum); the logits are written back over S in shared memory
 // (accumulator layout: head q4, keys base + 8 r4 .. +7) so sweep B needs neither the split nor the mix again.
 template <int H, bool TAIL>
-__device__ __forceinline__ void tfwd_step_a(float* Sb, int pS, int ldS, int base, int Nk, const MixFrag& fWl, float bl2, int q4, int r4, float& m, float& z) {
+__device__ __forceinline__ void tfwd_step_a(float* Sb, int pS, int ldS, int base, int Nk, uint32_t fWl, float bl2, int q4, int r4, float& m, float& z) {
     float L2[8];
-    uint32_t shi[4];
-    step_logits<H, TAIL>(load_sraw<H>(Sb, pS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+    step_logits16<H, TAIL>(load_sraw<H>(Sb, pS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2);
     __syncwarp();                                                    // every lane's reads of this step's S precede the overwrite
     const int c8 = base + 8 * r4;
     if (q4 < H && c8 + 8 <= ldS) {
@@ -651,7 +698,7 @@ __device__ __forceinline__ void tfwd_step_a(float* Sb, int pS, int ldS, int base
 }
 // forward sweep B: P = 2^(L2 - c2) from the cached logits -> second mix -> bf16
 template <int H, bool TAIL>
-__device__ __forceinline__ void tfwd_step_b(const float* Sb, int pS, int ldS, int base, int Nk, const MixFrag& fWw, float bwv, float c2, uint16_t* Ab, long long hA,
+__device__ __forceinline__ void tfwd_step_b(const float* Sb, int pS, int ldS, int base, int Nk, uint32_t fWw, float bwv, float c2, uint16_t* Ab, long long hA,
                                             int ldA, int q4, int r4) {
     const int c8 = base + 8 * r4;
     float p[8], out[8];
@@ -664,11 +711,7 @@ __device__ __forceinline__ void tfwd_step_b(const float* Sb, int pS, int ldS, in
         for (int i = 0; i < 8; ++i) p[i] = 0.f;
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        uint32_t hi, lo;
-        split2(p[t], p[4 + t], hi, lo);
-        mix_tile(fWw, movm_trans(hi), movm_trans(lo), bwv, out[t], out[4 + t]);
-    }
+    for (int t = 0; t < 4; ++t) mix_tile16(fWw, movm_trans(pack_f16x2(p[t], p[4 + t])), bwv, out[t], out[4 + t]);
     if (q4 < H && c8 + 8 <= ldA) {
         if (TAIL) {
 #pragma unroll
@@ -690,7 +733,7 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const floa
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ float red[NW][8][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q4 = lane >> 2, r4 = lane & 3;
-    const MixFrag fWl = load_mix_frag<H>(Wl, false, LOG2E, q4, r4), fWw = load_mix_frag<H>(Ww, false, 1.f, q4, r4);
+    const uint32_t fWl = load_mix_frag16<H>(Wl, LOG2E, q4, r4), fWw = load_mix_frag16<H>(Ww, 1.f, q4, r4);     // fp16 single-pass mixes (forward)
     const float bl2 = q4 < H ? bl[q4] * LOG2E : 0.f, bwv = q4 < H ? bw[q4] : 0.f;
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
     const uint32_t bar0 = rw_smem_u32(bars);
