@@ -438,6 +438,27 @@ __device__ __forceinline__ void step_logits16(const SRaw& raw, int base, int Nk,
     }
 }
 
+// backward flavour: logits through the fp16 single pass (identical to what the forward computed its statistics from), plus the
+// bf16-packed S of the step in the B-operand layout for the dWl outer product
+template <int H, bool TAIL = true>
+__device__ __forceinline__ void step_logits16_shi(const SRaw& raw, int base, int Nk, uint32_t Wl16, float bl2, int q4, int r4, float (&L2)[8], uint32_t (&shi)[4]) {
+    const int cb = base + 4 * q4;
+    const float a0[4] = {raw.s0.x, raw.s0.y, raw.s0.z, raw.s0.w}, a1[4] = {raw.s1.x, raw.s1.y, raw.s1.z, raw.s1.w};
+    const bool tail = TAIL && base + 32 > Nk;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const bool ok = !tail || cb + t < Nk;
+        const float x0 = ok ? a0[t] : 0.f, x1 = ok ? a1[t] : 0.f;
+        shi[t] = pack_bf16x2(x0, x1);
+        mix_tile16(Wl16, pack_f16x2(x0, x1), bl2, L2[t], L2[4 + t]);
+    }
+    if (tail) {
+        const int c8 = base + 8 * r4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) L2[i] = -INFINITY;
+    }
+}
+
 // sweep A: m2[q4] = max_j L2, iz = 1 / sum_j 2^(L2 - m2)     (values for the lane's head q4, identical in its 4 lanes)
 template <int H>
 __device__ __forceinline__ void talking_stats2(const float* __restrict__ Sb, long long hS, int Nk, long long ldS, const MixFrag& Wl, float bl2, int q4,
@@ -802,11 +823,11 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const floa
 //   P  (bf16, the lane's 8 keys)        over the lane's own 16-byte dA slot,
 //   S_hi (bf16, B-operand layout)       in the lane-private side buffer X   (16 bytes per lane and step).
 template <int H, bool TAIL>
-__device__ __forceinline__ void tbwd_step_b(float* Sb, uint16_t* Db, uint4* Xst, int pS, int pA, int ldS, int ldA, int base, int Nk, const MixFrag& fWl, const MixFrag& fWwT,
+__device__ __forceinline__ void tbwd_step_b(float* Sb, uint16_t* Db, uint4* Xst, int pS, int pA, int ldS, int ldA, int base, int Nk, uint32_t fWl, const MixFrag& fWwT,
                                             float bl2, float c2, int q4, int r4, int lane, float& rho, float (&accWw)[4]) {
     float L2[8], d[8], dP[8], p[8];
     uint32_t shi[4], dpk[4], ppk[4];
-    step_logits<H, TAIL>(load_sraw<H>(Sb, pS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
+    step_logits16_shi<H, TAIL>(load_sraw<H>(Sb, pS, base, ldS, q4, r4), base, Nk, fWl, bl2, q4, r4, L2, shi);
     const int c8 = base + 8 * r4;
     const bool slot = q4 < H && c8 + 8 <= ldA;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -900,7 +921,7 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const floa
     __shared__ float red[NW][8];
     __shared__ float redbuf[NW][NP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q4 = lane >> 2, r4 = lane & 3;
-    const MixFrag fWl = load_mix_frag<H>(Wl, false, LOG2E, q4, r4);
+    const uint32_t fWl = load_mix_frag16<H>(Wl, LOG2E, q4, r4);          // logits: the forward's fp16 single pass
     const MixFrag fWwT = load_mix_frag<H>(Ww, true, 1.f, q4, r4);
     const MixFrag fWlT = load_mix_frag<H>(Wl, true, 1.f, q4, r4);
     const float bl2 = q4 < H ? bl[q4] * LOG2E : 0.f;
