@@ -178,6 +178,32 @@ int spe_talking_softmax_bwd(const float* S, const void* dA, void* dS, const floa
                             void* stream);
 int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk);
 
+/* ---------------------------------------------------------------------------------------------
+ * FUSED talking-heads attention (csrc/talking_fused.cu): the whole of Attention_talking_head.forward between the qkv and
+ * the proj linears (cait.py:377-389) and its backward, with NO [B,H,N,N] tensor in HBM:
+ *   O[b,:,g] = ( sum_h Ww[g,h] softmax_keys( sum_h' Wl[h,h'] scale Q_h' K_h'^T + bl[h] ) + bw[g] ) V_g
+ * q / k / v: bf16 [B,N,H*dh] views (*_ld = token stride, *_sb = image stride, elements; head h at column h*dh), typically the
+ * three thirds of the packed qkv projection.  Logits live in TMEM (tcgen05.mma, M = 64), the H x H head mixes run on
+ * mma.sync from the tcgen05.ld fragments, the mixed probabilities feed tcgen05.mma P V from shared memory.
+ * lse2 (f32 [B,H,N], out): log2-domain logsumexp of the mixed logits, the only thing the backward needs besides q, k, v.
+ * Supported head geometry: spe_talking_fused_supported(H, dh) (H in {4, 8}, dh = 48 = every CaiT variant up to S); other
+ * shapes take the unfused spe_gemm + spe_talking_softmax_* pipeline.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int B, H, N, dh;
+    const void* q; int64_t q_ld, q_sb;
+    const void* k; int64_t k_ld, k_sb;
+    const void* v; int64_t v_ld, v_sb;
+    const float *Wl, *bl, *Ww, *bw;       /* proj_l / proj_w weights [H,H] (out, in) and biases [H], f32 */
+    float scale;                          /* qk scale (dh^-0.5) */
+    void* out; int64_t out_ld, out_sb;    /* bf16 [B,N,H*dh] */
+    float* lse2;                          /* f32 [B,H,N] */
+    void* workspace; int64_t workspace_bytes;
+} spe_talking_fused_args;
+int spe_talking_fused_supported(int H, int dh);
+int64_t spe_talking_fused_fwd_workspace(int B, int H, int N, int dh);
+int spe_talking_fused_fwd(const spe_talking_fused_args* a, void* stream);
+
 /* Plain softmax over keys with optional key-padding mask (attention.py:363-371, nn.MultiheadAttention).
  * S f32 [B,H,Nq,ldS] -> P bf16 [B,H,Nq,ldP]; mask u8 [B,Nk] (1 = padded -> -inf) or NULL.
  * If pmean != NULL also writes the head-mean of P, f32 [B,Nq,Nk] (cait.py:658-667 cams). */

@@ -57,6 +57,13 @@ class AttentionBwd2Args(C.Structure):
                [f for n in ("dq2", "dk2") for f in ((n, c_p), (n + "_ld", c_l), (n + "_sb", c_l))] + [("workspace", c_p)]
 
 
+class TalkingFusedArgs(C.Structure):
+    _fields_ = [("B", c_i), ("H", c_i), ("N", c_i), ("dh", c_i),
+                ("q", c_p), ("q_ld", c_l), ("q_sb", c_l), ("k", c_p), ("k_ld", c_l), ("k_sb", c_l), ("v", c_p), ("v_ld", c_l), ("v_sb", c_l),
+                ("Wl", c_p), ("bl", c_p), ("Ww", c_p), ("bw", c_p), ("scale", c_f),
+                ("out", c_p), ("out_ld", c_l), ("out_sb", c_l), ("lse2", c_p), ("workspace", c_p), ("workspace_bytes", c_l)]
+
+
 _SIGS = {
     "spe_version": (c_i, []),
     "spe_launch_count": (c_l, []),
@@ -75,6 +82,9 @@ _SIGS = {
     "spe_talking_softmax_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p, c_p, c_p,
                                       c_p, c_l, c_p]),
     "spe_talking_softmax_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i]),
+    "spe_talking_fused_supported": (c_i, [c_i, c_i]),
+    "spe_talking_fused_fwd_workspace": (c_l, [c_i, c_i, c_i, c_i]),
+    "spe_talking_fused_fwd": (c_i, [C.POINTER(TalkingFusedArgs), c_p]),
     "spe_softmax_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p]),
     "spe_cam_std_reweight": (c_i, [c_p, c_i, c_i, c_i, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "spe_softmax_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_p]),

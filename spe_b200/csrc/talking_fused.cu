@@ -1,0 +1,588 @@
+// Fused talking-heads attention for sm_100a (Attention_talking_head.forward, /root/reference/models/cait.py:374-393):
+//   S_h = scale Q_h K_h^T,  L_g = sum_h Wl[g,h] S_h + bl[g],  P_g = softmax_keys(L_g),  A_g = sum_h Ww[g,h] P_h + bw[g],  O_g = A_g V_g
+// No [B,H,N,N] tensor ever reaches HBM (the unfused pipeline moved ~4.4 GB of them per layer, forward + backward).
+//
+// Tile geometry (all kernels of this file): a CTA owns RB = 64 "stationary" rows (queries; keys in the key-stationary backward
+// kernel) of one image for ALL heads and streams the other side in blocks of CB = 16 columns:
+//   * tcgen05.mma M = 64, N = 16, K = 16 (bf16, f32 accumulate) per head: the H logit tiles of a block land side by side in
+//     H x 16 TMEM columns.  An M = 64 accumulator occupies lanes [32 i, 32 i + 16) of the four lane quarters; a second tile
+//     (the other buffer of the double-buffered S, or dA = dO V^T in the backward) interleaves into lanes [32 i + 16, 32 i + 32)
+//     of the SAME columns, so one tcgen05.ld.16x256b per head and tile hands a thread S and dA of the same four positions.
+//   * position warps (8: two per TMEM lane quarter, one per 8-column half): tcgen05.ld.16x256b gives thread (gid, tig) the rows
+//     {gid, gid + 8} x columns {2 tig, 2 tig + 1} of every head = the mma.sync m16n8 accumulator layout.  The H x H head mixes run
+//     on mma.sync.m16n8k16 straight from those registers: the thread's heads fill its own k-slots of the A fragment and the
+//     weight operand is block diagonal over the quad (B[(t, i), (t', gs)] = [t == t'] W[2 gp + gs, head(i)]), so every output
+//     lands in the thread that owns the position -- no shuffles, no shared-memory transposes (1024 MAC / clk / SM on the legacy
+//     tensor path against 128 on the FMA pipe; measured with tools/micro/pipes.cu).  exp2 on the MUFU pipe with the softmax
+//     statistics folded into the accumulator initialiser (C operand) of the first mix.
+//   * the mixed probabilities (bf16) go to a [64 x 16] K-major no-swizzle tile per head in shared memory and feed
+//     tcgen05.mma O_g += A_g V_g (V consumed MN-major from the streamed block); O for all heads: 64 x 384 f32 in TMEM.
+// Forward = two launches: `stats` (row max / sum of the mixed logits, per column chunk) and `main` (exact P -> A -> A V).  The
+// streamed range is split into `nchunk` chunks per row block so that the grid fills the 148 SMs; partial statistics are merged in
+// the main kernel's prologue, partial outputs are reduce-added in fp32 when nchunk > 1.
+#include "common.cuh"
+#include "umma.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+void* spe_tmap_encode_fn();
+
+namespace {
+using namespace umma;
+
+constexpr int RB = 64;                  // stationary rows per CTA
+constexpr int CB = 16;                  // streamed columns per block
+constexpr int DHD = 48;                 // head dim (every CaiT variant: 192/4, 288/6, 384/8, 768/16)
+constexpr int NSTG = 3;                 // stages of the streamed-block rings
+constexpr int TF_THREADS = 320;         // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 positions (quarter = warp % 4)
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float P_SHIFT = 8.f;          // probabilities are carried as 2^8 P (fp16 operand of the second mix stays normal)
+constexpr uint32_t XT_B = RB * 128;     // one [64 rows x 64 cols] bf16 SWIZZLE_128B tile of the stationary operand
+constexpr uint32_t YT_B = CB * 128;     // one [16 rows x 64 cols] tile of a streamed block
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// [B, N, D] bf16 view (token stride ld, image stride sb, elements): box = 64 columns x `rows` tokens, SWIZZLE_128B, OOB rows read as zero
+int make_map(CUtensorMap* tm, const void* ptr, int D, int N, int B, int64_t ld, int64_t sb, int rows) {
+    PFN_encodeTiled enc = reinterpret_cast<PFN_encodeTiled>(spe_tmap_encode_fn());
+    SPE_CHECK(enc, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    SPE_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0 && (B == 1 || sb % 8 == 0), "talking_fused: operand not 16-byte aligned");
+    cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(B > 1 ? sb : ld * N) * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SPE_CHECK(r == CUDA_SUCCESS, "talking_fused: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// head mix on mma.sync:  y[g][i] = c(g, i) + sum_h W[g][h] x[h][i]   for the thread's four positions i = rowsel * 2 + j
+// ---------------------------------------------------------------------------------------------------------------------------
+// B fragments of a mix matrix W (out g x in h, row-major f32 in global memory, times `mul`): [hq][gp][2] packed 16-bit pairs.
+// Thread (gid, tig) holds column n = gid of the block-diagonal operand: non-zero only for the k-slots of thread gid >> 1.
+template <int H, bool BF16, bool TRANSPOSE>
+__device__ __forceinline__ void load_wfrag(const float* __restrict__ W, float mul, int lane, uint32_t (&wf)[(H / 4) * (H / 2)][2]) {
+    const int gid = lane >> 2, tig = lane & 3;
+    const bool active = tig == (gid >> 1);
+#pragma unroll
+    for (int hq = 0; hq < H / 4; ++hq)
+#pragma unroll
+        for (int gp = 0; gp < H / 2; ++gp) {
+            const int g = 2 * gp + (gid & 1);
+            float w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int h = 4 * hq + i;
+                w[i] = active ? mul * (TRANSPOSE ? W[h * H + g] : W[g * H + h]) : 0.f;
+            }
+            wf[hq * (H / 2) + gp][0] = BF16 ? pack_bf16(w[0], w[1]) : pack_f16(w[0], w[1]);
+            wf[hq * (H / 2) + gp][1] = BF16 ? pack_bf16(w[2], w[3]) : pack_f16(w[2], w[3]);
+        }
+}
+
+template <int H, bool BF16, class CInit>
+__device__ __forceinline__ void head_mix(const float (&x)[H][4], const uint32_t (&wf)[(H / 4) * (H / 2)][2], CInit cinit, float (&y)[H][4]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        uint32_t a[H / 4][4];
+#pragma unroll
+        for (int hq = 0; hq < H / 4; ++hq) {
+            if (BF16) {
+                a[hq][0] = pack_bf16(x[4 * hq][j], x[4 * hq + 1][j]);
+                a[hq][1] = pack_bf16(x[4 * hq][2 + j], x[4 * hq + 1][2 + j]);
+                a[hq][2] = pack_bf16(x[4 * hq + 2][j], x[4 * hq + 3][j]);
+                a[hq][3] = pack_bf16(x[4 * hq + 2][2 + j], x[4 * hq + 3][2 + j]);
+            } else {
+                a[hq][0] = pack_f16(x[4 * hq][j], x[4 * hq + 1][j]);
+                a[hq][1] = pack_f16(x[4 * hq][2 + j], x[4 * hq + 1][2 + j]);
+                a[hq][2] = pack_f16(x[4 * hq + 2][j], x[4 * hq + 3][j]);
+                a[hq][3] = pack_f16(x[4 * hq + 2][2 + j], x[4 * hq + 3][2 + j]);
+            }
+        }
+#pragma unroll
+        for (int gp = 0; gp < H / 2; ++gp) {
+            float d[4] = {cinit(2 * gp, j), cinit(2 * gp + 1, j), cinit(2 * gp, 2 + j), cinit(2 * gp + 1, 2 + j)};
+#pragma unroll
+            for (int hq = 0; hq < H / 4; ++hq) {
+                if (BF16) hmma_bf16(d, a[hq], wf[hq * (H / 2) + gp][0], wf[hq * (H / 2) + gp][1], d);
+                else hmma_f16(d, a[hq], wf[hq * (H / 2) + gp][0], wf[hq * (H / 2) + gp][1], d);
+            }
+            y[2 * gp][j] = d[0]; y[2 * gp + 1][j] = d[1]; y[2 * gp][2 + j] = d[2]; y[2 * gp + 1][2 + j] = d[3];
+        }
+    }
+}
+
+// the H tiles of one block: head h at column h * CB (+ this warp's 8-column half), lanes [lane_base, lane_base + 16)
+template <int H>
+__device__ __forceinline__ void ld_tiles(uint32_t taddr, float (&x)[H][4]) {
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        uint32_t r[4];
+        UMMA_LD_16x256(taddr + (uint32_t)(h * CB), r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[h][i] = __uint_as_float(r[i]);
+    }
+}
+
+// bf16 operand tiles for the accumulating tcgen05.mma: [8 row groups][H][2 column halves][8 rows][16 B]  (K-major, no swizzle:
+// LBO = 128 between the column halves, SBO = H * 256 between the 8-row groups; head g starts at g * 256)
+template <int H>
+__device__ __forceinline__ void st_tiles(uint32_t tile, int quarter, int colhalf, int lane, const float (&y)[H][4]) {
+    const int gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+    for (int g = 0; g < H; ++g)
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+            const uint32_t addr = tile + (uint32_t)((quarter * 2 + rs) * (H * 256) + g * 256 + colhalf * 128 + gid * 16 + tig * 4);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16(y[g][rs * 2], y[g][rs * 2 + 1])) : "memory");
+        }
+}
+
+struct TfFwdParams {
+    int N, nblk, nchunk, bpc;            // tokens; column blocks in total / chunks / blocks per chunk
+    int Npad;                            // row blocks * 64
+    const float *Wl, *bl, *Ww, *bw;
+    float scale;
+    float2* part;                        // [B][nchunk][H][Npad] (max, sum) of 2^(log2e L) per row, chunk-local
+    float* lse2;                         // [B][H][N]  log2-domain logsumexp (main kernel, chunk 0; saved for the backward)
+    uint16_t* out; long long out_ld, out_sb;      // bf16 [B, N, D]   (nchunk == 1)
+    float* out32;                        // f32 [B, N, D] reduce-add target (nchunk > 1)
+    int dbg;                             // timing experiments only (SPE_TF_DBG)
+};
+
+template <int H>
+struct FwdSmem {
+    static constexpr int D = H * DHD, NT = D / 64;
+    static constexpr uint32_t X = 0;                                   // Q: NT tiles
+    static constexpr uint32_t Y = X + NT * XT_B;                       // K ring
+    static constexpr uint32_t Z = Y + NSTG * NT * YT_B;                // V ring (main only)
+    static constexpr uint32_t A = Z + NSTG * NT * YT_B;                // 2 probability tiles
+    static constexpr uint32_t A_B = 8 * H * 256;
+    static constexpr uint32_t BAR = A + 2 * A_B;
+    static constexpr int NBAR = 1 + 4 * NSTG + 8 + 1;
+    static constexpr uint32_t TSLOT = BAR + NBAR * 8;
+    static constexpr uint32_t XCHG = TSLOT + 16;                       // stats exchange between the two column-half warps: [64][H] float2
+    static constexpr uint32_t TOTAL = XCHG + RB * H * 8 + 1024;        // + alignment slack
+};
+
+// merge (m, l) pairs of the log2-domain running statistics; m = -1e30 (finite) means "nothing seen"
+__device__ __forceinline__ void stat_merge(float& m, float& l, float m2, float l2) {
+    const float M = fmaxf(m, m2);
+    const float s1 = (m == M) ? 1.f : ex2(m - M), s2 = (m2 == M) ? 1.f : ex2(m2 - M);
+    l = l * s1 + l2 * s2;
+    m = M;
+}
+
+template <int H, bool STATS>
+__global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                               const __grid_constant__ CUtensorMap tmV, const TfFwdParams p) {
+    using SM = FwdSmem<H>;
+    constexpr int D = SM::D, NT = SM::NT;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + SM::BAR;
+    const uint32_t xfull = bar0, yfull0 = xfull + 8, yempty0 = yfull0 + 8 * NSTG, zfull0 = yempty0 + 8 * NSTG, zempty0 = zfull0 + 8 * NSTG,
+                   sfull0 = zempty0 + 8 * NSTG, sempty0 = sfull0 + 16, afull0 = sempty0 + 16, aempty0 = afull0 + 16, ofull = aempty0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::TSLOT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * RB, chunk = blockIdx.y, b = blockIdx.z;
+    const int blk0 = chunk * p.bpc;
+    const int nb = min(p.bpc, p.nblk - blk0);                 // blocks of this CTA (>= 1 by construction)
+    constexpr uint32_t TMEM_COLS = STATS ? (H * CB <= 32 ? 32 : (H * CB <= 64 ? 64 : 128)) : 512;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+        if (!STATS) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+        mbar_init(xfull, 1);
+        for (int s = 0; s < NSTG; ++s) { mbar_init(yfull0 + 8 * s, 1); mbar_init(yempty0 + 8 * s, 1); mbar_init(zfull0 + 8 * s, 1); mbar_init(zempty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(sfull0 + 8 * s, 1); mbar_init(sempty0 + 8 * s, 8); mbar_init(afull0 + 8 * s, 8); mbar_init(aempty0 + 8 * s, 1); }
+        mbar_init(ofull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base;                             // S: H * 16 columns, buffer sb in lanes [32 i + 16 sb, +16)
+    const uint32_t tO = tmem_base + 128;                       // O: D columns (main only)
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (elect()) {
+            mbar_expect_tx(xfull, NT * XT_B);
+            for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::X + t * XT_B, &tmQ, xfull, t * 64, r0, b);
+        }
+        __syncwarp();
+        for (int jl = 0; jl < nb; ++jl) {
+            const int s = jl % NSTG;
+            const uint32_t ph = ((uint32_t)(jl / NSTG) & 1u) ^ 1u;
+            const int c0 = (blk0 + jl) * CB;
+            mbar_wait(yempty0 + 8 * s, ph);
+            if (elect()) {
+                if ((p.dbg & 64) && jl >= NSTG) mbar_arrive(yfull0 + 8 * s);
+                else {
+                mbar_expect_tx(yfull0 + 8 * s, NT * YT_B);
+                for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::Y + (s * NT + t) * YT_B, &tmK, yfull0 + 8 * s, t * 64, c0, b);
+                }
+            }
+            __syncwarp();
+            if (!STATS) {
+                mbar_wait(zempty0 + 8 * s, ph);
+                if (elect()) {
+                    if ((p.dbg & 64) && jl >= NSTG) mbar_arrive(zfull0 + 8 * s);
+                    else {
+                    mbar_expect_tx(zfull0 + 8 * s, NT * YT_B);
+                    for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::Z + (s * NT + t) * YT_B, &tmV, zfull0 + 8 * s, t * 64, c0, b);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t ID_S = idesc_bf16(RB, CB, false, false);
+        mbar_wait(xfull, 0);
+        fence_after();
+        for (int jl = 0; jl <= nb; ++jl) {
+            if (jl < nb) {
+                const int s = jl % NSTG;
+                const uint32_t sb = (uint32_t)jl & 1u;
+                mbar_wait(yfull0 + 8 * s, (uint32_t)(jl / NSTG) & 1u);
+                mbar_wait(sempty0 + 8 * sb, (((uint32_t)jl >> 1) & 1u) ^ 1u);
+                fence_after();
+                if (elect()) {
+                    if (!(p.dbg & 1) || jl == 0)
+#pragma unroll
+                    for (int h = 0; h < H; ++h)
+#pragma unroll
+                        for (int ks = 0; ks < DHD / 16; ++ks) {
+                            const int e = h * DHD + ks * 16;
+                            const uint64_t ad = desc(sbase + SM::X + (e >> 6) * XT_B + (e & 63) * 2, 0, 1024, 2);
+                            const uint64_t bd = desc(sbase + SM::Y + (s * NT + (e >> 6)) * YT_B + (e & 63) * 2, 0, 1024, 2);
+                            mma_f16(tS + ((sb * 16u) << 16) + (uint32_t)(h * CB), ad, bd, ID_S, ks != 0);
+                        }
+                    commit(yempty0 + 8 * s);
+                    commit(sfull0 + 8 * sb);
+                }
+                __syncwarp();
+            }
+            if (!STATS && jl >= 1) {
+                const int jp = jl - 1;
+                const int s = jp % NSTG;
+                const uint32_t ab = (uint32_t)jp & 1u;
+                mbar_wait(afull0 + 8 * ab, ((uint32_t)jp >> 1) & 1u);
+                mbar_wait(zfull0 + 8 * s, (uint32_t)(jp / NSTG) & 1u);
+                fence_after();
+                if (elect()) {
+                    if (!(p.dbg & 2) || jp == 0)
+#pragma unroll
+                    for (int g = 0; g < H; ++g) {
+                        // A_g tile: K-major no-swizzle, K = 16 columns (one k-step); V_g: MN-major inside the 64-column tiles of the
+                        // streamed block -- a head that straddles a tile boundary takes two MMAs
+                        const uint64_t ad = desc(sbase + SM::A + ab * SM::A_B + g * 256, 128, H * 256, 0);
+                        int e = g * DHD, left = DHD;
+                        while (left > 0) {
+                            const int n = min(left, 64 - (e & 63));
+                            const uint64_t bd = desc(sbase + SM::Z + (s * NT + (e >> 6)) * YT_B + (e & 63) * 2, YT_B, 1024, 2);
+                            mma_f16(tO + (uint32_t)e, ad, bd, idesc_bf16(RB, n, false, true), jp != 0);
+                            e += n; left -= n;
+                        }
+                    }
+                    commit(zempty0 + 8 * s);
+                    commit(aempty0 + 8 * ab);
+                }
+                __syncwarp();
+            }
+        }
+        if (!STATS) {
+            if (elect()) commit(ofull);
+            __syncwarp();
+        }
+    } else {
+        // ---------------- position warps ----------------
+        const int quarter = warp & 3, colhalf = (warp - 2) >> 2;
+        const int gid = lane >> 2, tig = lane & 3;
+        const uint32_t tl = (uint32_t)(quarter * 32) << 16;
+        uint32_t wl[(H / 4) * (H / 2)][2];
+        load_wfrag<H, false, false>(p.Wl, LOG2E * p.scale, lane, wl);
+        const int row_a = r0 + quarter * 16 + gid;             // + 8 for rowsel 1
+        if (STATS) {
+            float c1[H];
+#pragma unroll
+            for (int g = 0; g < H; ++g) c1[g] = LOG2E * p.bl[g];
+            float m[H][2], l[H][2];
+#pragma unroll
+            for (int g = 0; g < H; ++g) { m[g][0] = m[g][1] = -1e30f; l[g][0] = l[g][1] = 0.f; }      // finite "nothing seen": no inf - inf
+            for (int jl = 0; jl < nb; ++jl) {
+                const uint32_t sb = (uint32_t)jl & 1u;
+                mbar_wait(sfull0 + 8 * sb, ((uint32_t)jl >> 1) & 1u);
+                fence_after();
+                float x[H][4];
+                ld_tiles<H>(tS + tl + ((sb * 16u) << 16) + (uint32_t)(colhalf * 8), x);
+                ld_wait();
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sempty0 + 8 * sb);
+                float y[H][4];
+                head_mix<H, false>(x, wl, [&](int g, int) { return c1[g]; }, y);
+                const int col = (blk0 + jl) * CB + colhalf * 8 + 2 * tig;
+                if (col + 1 >= p.N) {                               // tail block: columns beyond N do not exist
+#pragma unroll
+                    for (int g = 0; g < H; ++g) {
+                        if (col >= p.N) { y[g][0] = -INFINITY; y[g][2] = -INFINITY; }
+                        y[g][1] = -INFINITY; y[g][3] = -INFINITY;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < H; ++g)
+#pragma unroll
+                    for (int rs = 0; rs < 2; ++rs) {
+                        const float bm = fmaxf(y[g][rs * 2], y[g][rs * 2 + 1]);
+                        if (bm > m[g][rs] + 8.f) {                  // lazy reference update: the sum tolerates 2^8 headroom
+                            l[g][rs] *= ex2(m[g][rs] - bm);
+                            m[g][rs] = bm;
+                        }
+                        l[g][rs] += ex2(y[g][rs * 2] - m[g][rs]) + ex2(y[g][rs * 2 + 1] - m[g][rs]);
+                    }
+            }
+            // combine: the four threads of a quad, then the two column-half warps of the quarter
+#pragma unroll
+            for (int g = 0; g < H; ++g)
+#pragma unroll
+                for (int rs = 0; rs < 2; ++rs) {
+#pragma unroll
+                    for (int o = 1; o <= 2; o <<= 1) {
+                        const float m2 = __shfl_xor_sync(0xffffffffu, m[g][rs], o), l2 = __shfl_xor_sync(0xffffffffu, l[g][rs], o);
+                        stat_merge(m[g][rs], l[g][rs], m2, l2);
+                    }
+                }
+            float2* xc = reinterpret_cast<float2*>(smem + SM::XCHG);
+            if (colhalf == 1 && tig == 0) {
+#pragma unroll
+                for (int g = 0; g < H; ++g)
+#pragma unroll
+                    for (int rs = 0; rs < 2; ++rs) xc[(quarter * 16 + rs * 8 + gid) * H + g] = make_float2(m[g][rs], l[g][rs]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (colhalf == 0 && tig == 0) {
+#pragma unroll
+                for (int g = 0; g < H; ++g)
+#pragma unroll
+                    for (int rs = 0; rs < 2; ++rs) {
+                        const float2 o = xc[(quarter * 16 + rs * 8 + gid) * H + g];
+                        stat_merge(m[g][rs], l[g][rs], o.x, o.y);
+                        p.part[(((long long)b * p.nchunk + chunk) * H + g) * p.Npad + (row_a - 0) + rs * 8] = make_float2(m[g][rs], l[g][rs]);
+                    }
+            }
+        } else {
+            uint32_t ww[(H / 4) * (H / 2)][2];
+            load_wfrag<H, false, false>(p.Ww, 1.f, lane, ww);
+            // merged statistics of this thread's two rows: c1[g][rs] = log2e bl[g] - lse2 + P_SHIFT
+            float c1[H][2], c2[H];
+#pragma unroll
+            for (int g = 0; g < H; ++g) {
+                c2[g] = p.bw[g] * 256.f;                            // 2^P_SHIFT bw
+#pragma unroll
+                for (int rs = 0; rs < 2; ++rs) {
+                    float m = -1e30f, l = 0.f;
+                    for (int c = 0; c < p.nchunk; ++c) {
+                        const float2 o = p.part[(((long long)b * p.nchunk + c) * H + g) * p.Npad + row_a + rs * 8];
+                        stat_merge(m, l, o.x, o.y);
+                    }
+                    const float lse = m + log2f(l);
+                    c1[g][rs] = LOG2E * p.bl[g] - lse + P_SHIFT;
+                    if (chunk == 0 && colhalf == 0 && tig == 0 && row_a + rs * 8 < p.N) p.lse2[((long long)b * H + g) * p.N + row_a + rs * 8] = lse;
+                }
+            }
+            for (int jl = 0; jl < nb; ++jl) {
+                const uint32_t sb = (uint32_t)jl & 1u;
+                mbar_wait(sfull0 + 8 * sb, ((uint32_t)jl >> 1) & 1u);
+                fence_after();
+                float x[H][4];
+                if (!(p.dbg & 128)) {
+                ld_tiles<H>(tS + tl + ((sb * 16u) << 16) + (uint32_t)(colhalf * 8), x);
+                ld_wait();
+                } else {
+#pragma unroll
+                    for (int g = 0; g < H; ++g)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) x[g][i] = (float)(g + i + jl);
+                }
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sempty0 + 8 * sb);
+                float y[H][4];
+                if (!(p.dbg & 4)) head_mix<H, false>(x, wl, [&](int g, int i) { return c1[g][i >> 1]; }, y);
+                else {
+#pragma unroll
+                    for (int g = 0; g < H; ++g)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) y[g][i] = x[g][i] + c1[g][i >> 1];
+                }
+#pragma unroll
+                for (int g = 0; g < H; ++g)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) y[g][i] = (p.dbg & 8) ? y[g][i] * 0.001f : ex2(y[g][i]);
+                if (!(p.dbg & 16)) head_mix<H, false>(y, ww, [&](int g, int) { return c2[g]; }, x);
+                else {
+#pragma unroll
+                    for (int g = 0; g < H; ++g)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) x[g][i] = y[g][i] + c2[g];
+                }
+                mbar_wait(aempty0 + 8 * sb, (((uint32_t)jl >> 1) & 1u) ^ 1u);
+                if (!(p.dbg & 32)) st_tiles<H>(sbase + SM::A + sb * SM::A_B, quarter, colhalf, lane, x);
+                if (!(p.dbg & 256)) fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull0 + 8 * sb);
+            }
+            // ---- output: O rows of this quarter are TMEM lanes [32 q, 32 q + 16); each column-half warp takes D / 2 columns
+            mbar_wait(ofull, 0);
+            fence_after();
+            const int row = r0 + quarter * 16 + lane;
+            const float inv = 1.f / 256.f;
+#pragma unroll 1
+            for (int c = 0; c < D / 2; c += 16) {
+                uint32_t o[16];
+                const int col = colhalf * (D / 2) + c;
+                UMMA_LD_32x32_X16(tO + tl + (uint32_t)col, o);
+                ld_wait();
+                if (lane < 16 && row < p.N) {
+                    if (p.out32 != nullptr) {
+                        float* dst = p.out32 + ((long long)b * p.N + row) * D + col;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q4 * 4), "f"(__uint_as_float(o[q4 * 4]) * inv),
+                                         "f"(__uint_as_float(o[q4 * 4 + 1]) * inv), "f"(__uint_as_float(o[q4 * 4 + 2]) * inv),
+                                         "f"(__uint_as_float(o[q4 * 4 + 3]) * inv) : "memory");
+                    } else {
+                        uint16_t* dst = p.out + (long long)b * p.out_sb + (long long)row * p.out_ld + col;
+                        uint4 v0, v1;
+                        v0.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+                        v0.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+                        v0.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+                        v0.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+                        v1.x = pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+                        v1.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+                        v1.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+                        v1.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+                        *reinterpret_cast<uint4*>(dst) = v0;
+                        *reinterpret_cast<uint4*>(dst + 8) = v1;
+                    }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+__global__ void tf_cast_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long rows, int D, long long dst_ld, int N, long long dst_sb) {
+    // src [B*N, D] f32 contiguous -> dst bf16 view; 4 elements per thread
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= rows * D) return;
+    const long long r = i / D;
+    const int c = (int)(i - r * D);
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    const long long bimg = r / N, n = r - bimg * N;
+    uint2 o = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    *reinterpret_cast<uint2*>(dst + bimg * dst_sb + n * dst_ld + c) = o;
+}
+
+int pick_nchunk(int ctas0, int nblk) {
+    static const char* env = getenv("SPE_TF_NCHUNK");
+    if (env) { int v = atoi(env); if (v >= 1) return v > nblk ? nblk : v; }
+    const int sms = spe_num_sms();
+    int best = 1;
+    double best_cost = 1e30;
+    for (int nc = 1; nc <= 8 && nc <= nblk; ++nc) {
+        const int bpc = (nblk + nc - 1) / nc;
+        const int real_nc = (nblk + bpc - 1) / bpc;
+        const double waves = (double)((ctas0 * real_nc + sms - 1) / sms);
+        const double cost = waves * (bpc + 6.0);               // ~6 blocks' worth of per-CTA prologue / epilogue
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = real_nc; }
+    }
+    return best;
+}
+
+template <int H>
+int launch_fwd(const spe_talking_fused_args* a, cudaStream_t st) {
+    using SM = FwdSmem<H>;
+    const int D = H * DHD, N = a->N, B = a->B;
+    const int nrb = (N + RB - 1) / RB, nblk = (N + CB - 1) / CB;
+    const int Npad = nrb * RB;
+    int nchunk = pick_nchunk(nrb * B, nblk);
+    const int bpc = (nblk + nchunk - 1) / nchunk;
+    nchunk = (nblk + bpc - 1) / bpc;
+    const size_t part_b = (size_t)B * nchunk * H * Npad * sizeof(float2);
+    const size_t o32_b = nchunk > 1 ? (size_t)B * N * D * sizeof(float) : 0;
+    SPE_CHECK(a->workspace && (size_t)a->workspace_bytes >= ((part_b + 255) / 256) * 256 + o32_b, "spe_talking_fused_fwd: workspace too small");
+    CUtensorMap tq, tk, tv;
+    if (make_map(&tq, a->q, D, N, B, a->q_ld, a->q_sb, RB)) return -1;
+    if (make_map(&tk, a->k, D, N, B, a->k_ld, a->k_sb, CB)) return -1;
+    if (make_map(&tv, a->v, D, N, B, a->v_ld, a->v_sb, CB)) return -1;
+    TfFwdParams p;
+    p.N = N; p.nblk = nblk; p.nchunk = nchunk; p.bpc = bpc; p.Npad = Npad;
+    p.Wl = a->Wl; p.bl = a->bl; p.Ww = a->Ww; p.bw = a->bw; p.scale = a->scale;
+    p.part = reinterpret_cast<float2*>(a->workspace);
+    p.lse2 = a->lse2;
+    p.out = reinterpret_cast<uint16_t*>(a->out); p.out_ld = a->out_ld; p.out_sb = a->out_sb;
+    p.out32 = nchunk > 1 ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + ((part_b + 255) / 256) * 256) : nullptr;
+    static const char* dbg_env = getenv("SPE_TF_DBG");
+    p.dbg = dbg_env ? atoi(dbg_env) : 0;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SPE_CUDA(cudaFuncSetAttribute(tf_fwd_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL));
+        SPE_CUDA(cudaFuncSetAttribute(tf_fwd_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL));
+        attr_done = true;
+    }
+    const dim3 grid(nrb, nchunk, B);
+    const double pos = (double)B * N * N;
+    {
+        SpeProfScope ps(SPE_FAM_TALKING_FWD, pos * H * 4.0, st, "tf_stats");
+        tf_fwd_kernel<H, true><<<grid, TF_THREADS, SM::TOTAL, st>>>(tq, tk, tv, p);
+        SPE_LAUNCHED();
+    }
+    if (p.out32) SPE_CUDA(cudaMemsetAsync(p.out32, 0, o32_b, st));
+    {
+        SpeProfScope ps(SPE_FAM_TALKING_FWD, pos * H * 4.0, st, "tf_main");
+        tf_fwd_kernel<H, false><<<grid, TF_THREADS, SM::TOTAL, st>>>(tq, tk, tv, p);
+        SPE_LAUNCHED();
+    }
+    if (p.out32) {
+        const long long tot = (long long)B * N * D / 4;
+        tf_cast_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.out32, p.out, (long long)B * N, D, a->out_ld, N, a->out_sb);
+        SPE_LAUNCHED();
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int spe_talking_fused_supported(int H, int dh) { return (H == 4 || H == 8) && dh == DHD ? 1 : 0; }
+
+extern "C" __attribute__((visibility("default"))) int64_t spe_talking_fused_fwd_workspace(int B, int H, int N, int dh) {
+    const int nrb = (N + RB - 1) / RB;
+    const int64_t part = (((int64_t)B * 8 * H * nrb * RB * 8 + 255) / 256) * 256;       // up to 8 chunks
+    return part + (int64_t)B * N * H * dh * 4;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_talking_fused_fwd(const spe_talking_fused_args* a, void* stream) {
+    SPE_CHECK(a && a->q && a->k && a->v && a->out && a->lse2 && a->Wl && a->bl && a->Ww && a->bw, "spe_talking_fused_fwd: null argument");
+    SPE_CHECK(spe_talking_fused_supported(a->H, a->dh), "spe_talking_fused_fwd: unsupported head geometry H=%d dh=%d", a->H, a->dh);
+    SPE_CHECK(a->B > 0 && a->N > 0 && a->B <= 65535, "spe_talking_fused_fwd: bad shape");
+    SPE_CHECK(a->out_ld % 8 == 0 && a->out_sb % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "spe_talking_fused_fwd: output not 16-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return a->H == 8 ? launch_fwd<8>(a, st) : launch_fwd<4>(a, st);
+}
