@@ -31,14 +31,15 @@ namespace {
 using namespace umma;
 
 constexpr int RB = 64;                  // stationary rows per CTA
-constexpr int CB = 16;                  // streamed columns per block
 constexpr int DHD = 48;                 // head dim (every CaiT variant: 192/4, 288/6, 384/8, 768/16)
-constexpr int NSTG = 3;                 // stages of the streamed-block rings
 constexpr int TF_THREADS = 320;         // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 positions (quarter = warp % 4)
+constexpr int TF_THREADS_STATS = 576;   // statistics kernel: 16 position warps (80 registers per thread)
+#ifndef TF_NPW_MAIN
+#define TF_NPW_MAIN 8
+#endif
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float P_SHIFT = 8.f;          // probabilities are carried as 2^8 P (fp16 operand of the second mix stays normal)
 constexpr uint32_t XT_B = RB * 128;     // one [64 rows x 64 cols] bf16 SWIZZLE_128B tile of the stationary operand
-constexpr uint32_t YT_B = CB * 128;     // one [16 rows x 64 cols] tile of a streamed block
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -116,7 +117,7 @@ __device__ __forceinline__ void head_mix(const float (&x)[H][4], const uint32_t 
 }
 
 // the H tiles of one block: head h at column h * CB (+ this warp's 8-column half), lanes [lane_base, lane_base + 16)
-template <int H>
+template <int H, int CB>
 __device__ __forceinline__ void ld_tiles(uint32_t taddr, float (&x)[H][4]) {
 #pragma unroll
     for (int h = 0; h < H; ++h) {
@@ -127,45 +128,69 @@ __device__ __forceinline__ void ld_tiles(uint32_t taddr, float (&x)[H][4]) {
     }
 }
 
-// bf16 operand tiles for the accumulating tcgen05.mma: [8 row groups][H][2 column halves][8 rows][16 B]  (K-major, no swizzle:
-// LBO = 128 between the column halves, SBO = H * 256 between the 8-row groups; head g starts at g * 256)
-template <int H>
-__device__ __forceinline__ void st_tiles(uint32_t tile, int quarter, int colhalf, int lane, const float (&y)[H][4]) {
+// bf16 operand tiles for the accumulating tcgen05.mma: [8 row groups][H][CB / 8 column chunks][8 rows][16 B]  (K-major, no swizzle:
+// LBO = 128 between the 8-column chunks, SBO = H * (CB / 8) * 128 between the 8-row groups; head g starts at g * (CB / 8) * 128)
+template <int H, int CB>
+__device__ __forceinline__ void st_tiles(uint32_t tile, int quarter, int chunk8, int lane, const float (&y)[H][4]) {
     const int gid = lane >> 2, tig = lane & 3;
 #pragma unroll
     for (int g = 0; g < H; ++g)
 #pragma unroll
         for (int rs = 0; rs < 2; ++rs) {
-            const uint32_t addr = tile + (uint32_t)((quarter * 2 + rs) * (H * 256) + g * 256 + colhalf * 128 + gid * 16 + tig * 4);
+            const uint32_t addr = tile + (uint32_t)((quarter * 2 + rs) * (H * (CB / 8) * 128) + g * ((CB / 8) * 128) + chunk8 * 128 + gid * 16 + tig * 4);
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16(y[g][rs * 2], y[g][rs * 2 + 1])) : "memory");
         }
 }
 
 struct TfFwdParams {
-    int N, nblk, nchunk, bpc;            // tokens; column blocks in total / chunks / blocks per chunk
+    int N, nblk, nchunk, bpc;            // tokens; column blocks in total / chunks / blocks per chunk (this launch's block size)
     int Npad;                            // row blocks * 64
     const float *Wl, *bl, *Ww, *bw;
     float scale;
-    float2* part;                        // [B][nchunk][H][Npad] (max, sum) of 2^(log2e L) per row, chunk-local
-    float* lse2;                         // [B][H][N]  log2-domain logsumexp (main kernel, chunk 0; saved for the backward)
+    float2* part;                        // stats out: [B][nchunk][H][Npad] (max, sum) of 2^(log2e L) per row, chunk-local
+    float* lse2;                         // main in: [B][H][N] log2-domain logsumexp (written by tf_merge_kernel; saved for the backward)
     uint16_t* out; long long out_ld, out_sb;      // bf16 [B, N, D]   (nchunk == 1)
     float* out32;                        // f32 [B, N, D] reduce-add target (nchunk > 1)
     int dbg;                             // timing experiments only (SPE_TF_DBG)
+    long long* trace;                    // dbg & 512: clock64 stamps of CTA (0,0,0): [role][block][event]
 };
 
-template <int H>
+#ifndef TF_CB_STATS
+#define TF_CB_STATS 64
+#endif
+#ifndef TF_NSTG_STATS
+#define TF_NSTG_STATS 2
+#endif
+#ifndef TF_NSTG_MAIN
+#define TF_NSTG_MAIN 2
+#endif
+#ifndef TF_NABUF
+#define TF_NABUF 2
+#endif
+constexpr int CB_STATS = TF_CB_STATS, CB_MAIN = 32;
+#define TF_TRACE(role, blk, ev) do { if (p.trace && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (blk) < 32 && lane == 0) p.trace[((role) * 32 + (blk)) * 8 + (ev)] = clock64(); } while (0)
+
+template <int H, int CB, bool STATS>
 struct FwdSmem {
     static constexpr int D = H * DHD, NT = D / 64;
-    static constexpr uint32_t X = 0;                                   // Q: NT tiles
+    static constexpr int NSTG = STATS ? TF_NSTG_STATS : TF_NSTG_MAIN;  // stages of the streamed-block rings
+    static constexpr int NABUF = TF_NABUF;
+    static constexpr uint32_t YT = CB * 128;                           // one [CB rows x 64 cols] tile of a streamed block
+    static constexpr uint32_t X = 0;                                   // Q: NT tiles [64 x 64]
     static constexpr uint32_t Y = X + NT * XT_B;                       // K ring
-    static constexpr uint32_t Z = Y + NSTG * NT * YT_B;                // V ring (main only)
-    static constexpr uint32_t A = Z + NSTG * NT * YT_B;                // 2 probability tiles
-    static constexpr uint32_t A_B = 8 * H * 256;
-    static constexpr uint32_t BAR = A + 2 * A_B;
+    static constexpr uint32_t Z = Y + NSTG * NT * YT;                  // V ring (main only)
+    static constexpr uint32_t A = Z + (STATS ? 0 : NSTG * NT * YT);    // probability tiles [8 row groups][H][CB/8][8 rows][16 B]
+    static constexpr uint32_t A_B = 8 * H * (CB / 8) * 128;
+    static constexpr uint32_t BAR = A + (STATS ? 0 : NABUF * A_B);
     static constexpr int NBAR = 1 + 4 * NSTG + 8 + 1;
     static constexpr uint32_t TSLOT = BAR + NBAR * 8;
-    static constexpr uint32_t XCHG = TSLOT + 16;                       // stats exchange between the two column-half warps: [64][H] float2
-    static constexpr uint32_t TOTAL = XCHG + RB * H * 8 + 1024;        // + alignment slack
+    static constexpr uint32_t WSM = TSLOT + 16;                        // Wl, Ww [H*H], bl, bw [H] (f32)
+    static constexpr uint32_t LSE = WSM + (2 * H * H + 2 * H) * 4;     // main: lse2 of the CTA's rows [H][64];  stats: exchange [64][H] float2
+    static constexpr uint32_t TOTAL = LSE + 3 * RB * H * 8 + 1024;     // + alignment slack
+    static constexpr uint32_t S_COLS = H * CB;                         // TMEM: S tile, the two buffers in the two lane halves
+    static constexpr uint32_t O_CAP = 512 - S_COLS;                    // O columns that fit lane half 0 beside S; the rest goes to lane half 1
+    static_assert(STATS || (D <= 2 * (int)O_CAP && O_CAP % 64 == 0), "O does not fit TMEM");
+    static constexpr uint32_t TMEM_COLS = STATS ? (S_COLS <= 32 ? 32 : S_COLS <= 64 ? 64 : S_COLS <= 128 ? 128 : S_COLS <= 256 ? 256 : 512) : 512;
 };
 
 // merge (m, l) pairs of the log2-domain running statistics; m = -1e30 (finite) means "nothing seen"
@@ -176,11 +201,15 @@ __device__ __forceinline__ void stat_merge(float& m, float& l, float m2, float l
     m = M;
 }
 
-template <int H, bool STATS>
+template <int H, int CB, bool STATS>
 __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                                const __grid_constant__ CUtensorMap tmV, const TfFwdParams p) {
-    using SM = FwdSmem<H>;
-    constexpr int D = SM::D, NT = SM::NT;
+    using SM = FwdSmem<H, CB, STATS>;
+    constexpr int D = SM::D, NT = SM::NT, NSTG = SM::NSTG;
+    constexpr int NPW = 8;                                    // position warps: two per lane quarter = per SM sub-partition
+    constexpr int NCG = NPW / 4;                              // column groups (warps per lane quarter)
+    constexpr int NSUB = CB / (8 * NCG);                      // 8-column sub-tiles per warp and block
+    constexpr uint32_t YT = SM::YT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
@@ -188,11 +217,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
     const uint32_t xfull = bar0, yfull0 = xfull + 8, yempty0 = yfull0 + 8 * NSTG, zfull0 = yempty0 + 8 * NSTG, zempty0 = zfull0 + 8 * NSTG,
                    sfull0 = zempty0 + 8 * NSTG, sempty0 = sfull0 + 16, afull0 = sempty0 + 16, aempty0 = afull0 + 16, ofull = aempty0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::TSLOT);
+    float* wsm = reinterpret_cast<float*>(smem + SM::WSM);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = blockIdx.x * RB, chunk = blockIdx.y, b = blockIdx.z;
     const int blk0 = chunk * p.bpc;
     const int nb = min(p.bpc, p.nblk - blk0);                 // blocks of this CTA (>= 1 by construction)
-    constexpr uint32_t TMEM_COLS = STATS ? (H * CB <= 32 ? 32 : (H * CB <= 64 ? 64 : 128)) : 512;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
@@ -200,21 +229,34 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
         if (!STATS) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
         mbar_init(xfull, 1);
         for (int s = 0; s < NSTG; ++s) { mbar_init(yfull0 + 8 * s, 1); mbar_init(yempty0 + 8 * s, 1); mbar_init(zfull0 + 8 * s, 1); mbar_init(zempty0 + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(sfull0 + 8 * s, 1); mbar_init(sempty0 + 8 * s, 8); mbar_init(afull0 + 8 * s, 8); mbar_init(aempty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(sfull0 + 8 * s, 1); mbar_init(sempty0 + 8 * s, NPW); mbar_init(afull0 + 8 * s, NPW); mbar_init(aempty0 + 8 * s, 1); }
         mbar_init(ofull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(SM::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        // mix weights and (main) the rows' statistics into shared memory: a handful of coalesced loads instead of ~150 dependent ones per thread
+        const int t = threadIdx.x - 64;
+        if (t < H * H) { wsm[t] = p.Wl[t] * (LOG2E * p.scale); wsm[H * H + t] = p.Ww[t]; }
+        if (t < H) { wsm[2 * H * H + t] = p.bl[t] * LOG2E; wsm[2 * H * H + H + t] = p.bw[t] * 256.f; }       // 2^P_SHIFT bw
+        if (!STATS) {
+            float* ls = reinterpret_cast<float*>(smem + SM::LSE);
+            for (int i = t; i < H * RB; i += NPW * 32) {
+                const int g = i / RB, r = i % RB;
+                ls[i] = r0 + r < p.N ? p.lse2[((long long)b * H + g) * p.N + r0 + r] : 0.f;
+            }
+        }
     }
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base;                             // S: H * 16 columns, buffer sb in lanes [32 i + 16 sb, +16)
-    const uint32_t tO = tmem_base + 128;                       // O: D columns (main only)
+    const uint32_t tS = tmem_base;                             // S: H * CB columns, buffer sb in lanes [32 i + 16 sb, +16)
+    const uint32_t tO = tmem_base + SM::S_COLS;                // O (main): columns [0, O_CAP) in lane half 0, the rest in lane half 1
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
@@ -228,22 +270,18 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
             const uint32_t ph = ((uint32_t)(jl / NSTG) & 1u) ^ 1u;
             const int c0 = (blk0 + jl) * CB;
             mbar_wait(yempty0 + 8 * s, ph);
+            TF_TRACE(0, jl, 0);
             if (elect()) {
-                if ((p.dbg & 64) && jl >= NSTG) mbar_arrive(yfull0 + 8 * s);
-                else {
-                mbar_expect_tx(yfull0 + 8 * s, NT * YT_B);
-                for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::Y + (s * NT + t) * YT_B, &tmK, yfull0 + 8 * s, t * 64, c0, b);
-                }
+                mbar_expect_tx(yfull0 + 8 * s, NT * YT);
+                for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::Y + (s * NT + t) * YT, &tmK, yfull0 + 8 * s, t * 64, c0, b);
             }
             __syncwarp();
             if (!STATS) {
                 mbar_wait(zempty0 + 8 * s, ph);
+                TF_TRACE(0, jl, 1);
                 if (elect()) {
-                    if ((p.dbg & 64) && jl >= NSTG) mbar_arrive(zfull0 + 8 * s);
-                    else {
-                    mbar_expect_tx(zfull0 + 8 * s, NT * YT_B);
-                    for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::Z + (s * NT + t) * YT_B, &tmV, zfull0 + 8 * s, t * 64, c0, b);
-                    }
+                    mbar_expect_tx(zfull0 + 8 * s, NT * YT);
+                    for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::Z + (s * NT + t) * YT, &tmV, zfull0 + 8 * s, t * 64, c0, b);
                 }
                 __syncwarp();
             }
@@ -251,57 +289,74 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t ID_S = idesc_bf16(RB, CB, false, false);
+        const uint64_t dX = desc(sbase + SM::X, 0, 1024, 2);
         mbar_wait(xfull, 0);
         fence_after();
         for (int jl = 0; jl <= nb; ++jl) {
             if (jl < nb) {
                 const int s = jl % NSTG;
                 const uint32_t sb = (uint32_t)jl & 1u;
+                TF_TRACE(1, jl, 0);
                 mbar_wait(yfull0 + 8 * s, (uint32_t)(jl / NSTG) & 1u);
+                TF_TRACE(1, jl, 1);
                 mbar_wait(sempty0 + 8 * sb, (((uint32_t)jl >> 1) & 1u) ^ 1u);
+                TF_TRACE(1, jl, 2);
                 fence_after();
                 if (elect()) {
+                    const uint64_t dY = desc(sbase + SM::Y + s * NT * YT, 0, 1024, 2);
+                    const uint32_t td = tS + ((sb * 16u) << 16);
                     if (!(p.dbg & 1) || jl == 0)
 #pragma unroll
                     for (int h = 0; h < H; ++h)
 #pragma unroll
                         for (int ks = 0; ks < DHD / 16; ++ks) {
+                            constexpr int dummy = 0; (void)dummy;
                             const int e = h * DHD + ks * 16;
-                            const uint64_t ad = desc(sbase + SM::X + (e >> 6) * XT_B + (e & 63) * 2, 0, 1024, 2);
-                            const uint64_t bd = desc(sbase + SM::Y + (s * NT + (e >> 6)) * YT_B + (e & 63) * 2, 0, 1024, 2);
-                            mma_f16(tS + ((sb * 16u) << 16) + (uint32_t)(h * CB), ad, bd, ID_S, ks != 0);
+                            mma_f16(td + (uint32_t)(h * CB), dX + (uint64_t)(((e >> 6) * XT_B + (e & 63) * 2) >> 4),
+                                    dY + (uint64_t)(((e >> 6) * YT + (e & 63) * 2) >> 4), ID_S, ks != 0);
                         }
                     commit(yempty0 + 8 * s);
                     commit(sfull0 + 8 * sb);
                 }
                 __syncwarp();
+                TF_TRACE(1, jl, 3);
             }
             if (!STATS && jl >= 1) {
                 const int jp = jl - 1;
                 const int s = jp % NSTG;
-                const uint32_t ab = (uint32_t)jp & 1u;
-                mbar_wait(afull0 + 8 * ab, ((uint32_t)jp >> 1) & 1u);
+                const uint32_t ab = (uint32_t)jp % SM::NABUF;
+                mbar_wait(afull0 + 8 * ab, ((uint32_t)jp / SM::NABUF) & 1u);
+                TF_TRACE(1, jp, 4);
                 mbar_wait(zfull0 + 8 * s, (uint32_t)(jp / NSTG) & 1u);
+                TF_TRACE(1, jp, 5);
                 fence_after();
                 if (elect()) {
+                    // A_g tile: K-major no-swizzle (LBO 128 between the 8-column chunks, SBO between the 8-row groups), one k-step per
+                    // 16 columns; V_g: MN-major inside the 64-column tiles of the streamed block -- a head that straddles a tile
+                    // boundary takes two MMAs
+                    const uint64_t dA = desc(sbase + SM::A + ab * SM::A_B, 128, H * (CB / 8) * 128, 0);
+                    const uint64_t dZ = desc(sbase + SM::Z + s * NT * YT, YT, 1024, 2);
                     if (!(p.dbg & 2) || jp == 0)
 #pragma unroll
-                    for (int g = 0; g < H; ++g) {
-                        // A_g tile: K-major no-swizzle, K = 16 columns (one k-step); V_g: MN-major inside the 64-column tiles of the
-                        // streamed block -- a head that straddles a tile boundary takes two MMAs
-                        const uint64_t ad = desc(sbase + SM::A + ab * SM::A_B + g * 256, 128, H * 256, 0);
-                        int e = g * DHD, left = DHD;
-                        while (left > 0) {
-                            const int n = min(left, 64 - (e & 63));
-                            const uint64_t bd = desc(sbase + SM::Z + (s * NT + (e >> 6)) * YT_B + (e & 63) * 2, YT_B, 1024, 2);
-                            mma_f16(tO + (uint32_t)e, ad, bd, idesc_bf16(RB, n, false, true), jp != 0);
-                            e += n; left -= n;
+                    for (int g = 0; g < H; ++g)
+#pragma unroll
+                        for (int seg = 0; seg < 2; ++seg) {
+                            const int e0 = g * DHD;
+                            const int n0 = (64 - (e0 & 63)) < DHD ? (64 - (e0 & 63)) : DHD;
+                            const int e = seg == 0 ? e0 : e0 + n0, n = seg == 0 ? n0 : DHD - n0;
+                            if (n > 0) {
+                                const uint32_t td = (uint32_t)e < SM::O_CAP ? tO + (uint32_t)e : tO + (uint32_t)(e - SM::O_CAP) + (16u << 16);
+#pragma unroll
+                                for (int ks = 0; ks < CB / 16; ++ks)
+                                    mma_f16(td, dA + (uint64_t)((g * (CB / 8) * 128 + ks * 256) >> 4),
+                                            dZ + (uint64_t)(((e >> 6) * YT + ks * 2048 + (e & 63) * 2) >> 4), idesc_bf16(RB, n, false, true), (jp | ks) != 0);
+                            }
                         }
-                    }
                     commit(zempty0 + 8 * s);
                     commit(aempty0 + 8 * ab);
                 }
                 __syncwarp();
+                TF_TRACE(1, jp, 6);
             }
         }
         if (!STATS) {
@@ -310,32 +365,53 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
         }
     } else {
         // ---------------- position warps ----------------
-        const int quarter = warp & 3, colhalf = (warp - 2) >> 2;
+        const int quarter = warp & 3, cg = (warp - 2) >> 2;     // lane quarter; column group of the block
         const int gid = lane >> 2, tig = lane & 3;
         const uint32_t tl = (uint32_t)(quarter * 32) << 16;
         uint32_t wl[(H / 4) * (H / 2)][2];
-        load_wfrag<H, false, false>(p.Wl, LOG2E * p.scale, lane, wl);
+        load_wfrag<H, false, false>(wsm, 1.f, lane, wl);
         const int row_a = r0 + quarter * 16 + gid;             // + 8 for rowsel 1
+        // The two warps of a lane quarter share one SM sub-partition, i.e. one mma.sync pipe and one MUFU pipe.  Left alone they run
+        // in lockstep (every block barrier re-aligns them) and the pipes take turns idling: measured 3100 clocks per block against
+        // ~1000 of work on either pipe.  A token (named barrier pair, FA3-style ping-pong) serialises their tensor phases
+        // [store / load / head mixes], so that one warp's exponentials always run under the other warp's mixes.
+        const uint32_t tok_mine = 2u + 2u * (uint32_t)quarter + (uint32_t)cg, tok_other = 2u + 2u * (uint32_t)quarter + (uint32_t)(cg ^ 1);
+        auto tok_acquire = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(tok_mine) : "memory"); };
+        auto tok_release = [&]() { asm volatile("bar.arrive %0, 64;" ::"r"(tok_other) : "memory"); };
+        const int T = nb * NSUB;                                // sub-tiles of this warp
+        if (cg == 1) tok_release();                             // the cg = 0 warp starts
         if (STATS) {
             float c1[H];
 #pragma unroll
-            for (int g = 0; g < H; ++g) c1[g] = LOG2E * p.bl[g];
+            for (int g = 0; g < H; ++g) c1[g] = wsm[2 * H * H + g];
+            // running statistics of the thread's own columns: reference m (log2 domain), l = sum 2^(L - m).  The reference rides in
+            // the accumulator initialiser of the mix (C = log2e bl - m), so a value costs one EX2 and one FADD; it is re-based only
+            // when a logit exceeds it by more than 2^8 (warp-uniform branch, rare after the first blocks)
             float m[H][2], l[H][2];
 #pragma unroll
-            for (int g = 0; g < H; ++g) { m[g][0] = m[g][1] = -1e30f; l[g][0] = l[g][1] = 0.f; }      // finite "nothing seen": no inf - inf
-            for (int jl = 0; jl < nb; ++jl) {
+            for (int g = 0; g < H; ++g) { m[g][0] = m[g][1] = -1e30f; l[g][0] = l[g][1] = 0.f; }
+            float y[H][4];
+            auto load_mix = [&](int t, bool first) {            // tensor phase: S tile of sub-tile t -> y = log2e L - m
+                const int jl = t / NSUB, sub = t % NSUB;
                 const uint32_t sb = (uint32_t)jl & 1u;
-                mbar_wait(sfull0 + 8 * sb, ((uint32_t)jl >> 1) & 1u);
-                fence_after();
+                if (sub == 0) { mbar_wait(sfull0 + 8 * sb, ((uint32_t)jl >> 1) & 1u); fence_after(); }
                 float x[H][4];
-                ld_tiles<H>(tS + tl + ((sb * 16u) << 16) + (uint32_t)(colhalf * 8), x);
+                ld_tiles<H, CB>(tS + tl + ((sb * 16u) << 16) + (uint32_t)((cg * NSUB + sub) * 8), x);
                 ld_wait();
-                fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(sempty0 + 8 * sb);
-                float y[H][4];
-                head_mix<H, false>(x, wl, [&](int g, int) { return c1[g]; }, y);
-                const int col = (blk0 + jl) * CB + colhalf * 8 + 2 * tig;
+                if (sub == NSUB - 1) {
+                    fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sempty0 + 8 * sb);
+                }
+                if (first) head_mix<H, false>(x, wl, [&](int g, int) { return c1[g]; }, y);
+                else head_mix<H, false>(x, wl, [&](int g, int i) { return c1[g] - m[g][i >> 1]; }, y);
+            };
+            tok_acquire();
+            load_mix(0, true);
+            tok_release();
+            for (int t = 0; t < T; ++t) {
+                const int jl = t / NSUB, sub = t % NSUB;
+                const int col = (blk0 + jl) * CB + (cg * NSUB + sub) * 8 + 2 * tig;
                 if (col + 1 >= p.N) {                               // tail block: columns beyond N do not exist
 #pragma unroll
                     for (int g = 0; g < H; ++g) {
@@ -343,19 +419,43 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
                         y[g][1] = -INFINITY; y[g][3] = -INFINITY;
                     }
                 }
+                if (t == 0) {
 #pragma unroll
-                for (int g = 0; g < H; ++g)
+                    for (int g = 0; g < H; ++g)
 #pragma unroll
-                    for (int rs = 0; rs < 2; ++rs) {
-                        const float bm = fmaxf(y[g][rs * 2], y[g][rs * 2 + 1]);
-                        if (bm > m[g][rs] + 8.f) {                  // lazy reference update: the sum tolerates 2^8 headroom
-                            l[g][rs] *= ex2(m[g][rs] - bm);
-                            m[g][rs] = bm;
+                        for (int rs = 0; rs < 2; ++rs) {
+                            m[g][rs] = fmaxf(fmaxf(y[g][rs * 2], y[g][rs * 2 + 1]), -1e30f);
+                            l[g][rs] = ex2(y[g][rs * 2] - m[g][rs]) + ex2(y[g][rs * 2 + 1] - m[g][rs]);
                         }
-                        l[g][rs] += ex2(y[g][rs * 2] - m[g][rs]) + ex2(y[g][rs * 2 + 1] - m[g][rs]);
+                } else {
+                    bool up = false;
+#pragma unroll
+                    for (int g = 0; g < H; ++g)
+#pragma unroll
+                        for (int rs = 0; rs < 2; ++rs) up = up || fmaxf(y[g][rs * 2], y[g][rs * 2 + 1]) > 8.f;
+                    if (__any_sync(0xffffffffu, up)) {
+#pragma unroll
+                        for (int g = 0; g < H; ++g)
+#pragma unroll
+                            for (int rs = 0; rs < 2; ++rs) {
+                                const float bm = fmaxf(y[g][rs * 2], y[g][rs * 2 + 1]);
+                                if (bm > 8.f) {
+                                    l[g][rs] *= ex2(-bm);
+                                    m[g][rs] += bm;
+                                    y[g][rs * 2] -= bm; y[g][rs * 2 + 1] -= bm;
+                                }
+                            }
                     }
+#pragma unroll
+                    for (int g = 0; g < H; ++g)
+#pragma unroll
+                        for (int rs = 0; rs < 2; ++rs) l[g][rs] += ex2(y[g][rs * 2]) + ex2(y[g][rs * 2 + 1]);
+                }
+                tok_acquire();
+                if (t + 1 < T) load_mix(t + 1, false);
+                tok_release();
             }
-            // combine: the four threads of a quad, then the two column-half warps of the quarter
+            // combine: the four threads of a quad, then the two column-group warps of the quarter
 #pragma unroll
             for (int g = 0; g < H; ++g)
 #pragma unroll
@@ -366,98 +466,98 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
                         stat_merge(m[g][rs], l[g][rs], m2, l2);
                     }
                 }
-            float2* xc = reinterpret_cast<float2*>(smem + SM::XCHG);
-            if (colhalf == 1 && tig == 0) {
+            float2* xc = reinterpret_cast<float2*>(smem + SM::LSE);                 // [NCG - 1][64][H]
+            if (cg > 0 && tig == 0) {
 #pragma unroll
                 for (int g = 0; g < H; ++g)
 #pragma unroll
-                    for (int rs = 0; rs < 2; ++rs) xc[(quarter * 16 + rs * 8 + gid) * H + g] = make_float2(m[g][rs], l[g][rs]);
+                    for (int rs = 0; rs < 2; ++rs) xc[((cg - 1) * RB + quarter * 16 + rs * 8 + gid) * H + g] = make_float2(m[g][rs], l[g][rs]);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (colhalf == 0 && tig == 0) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
+            if (cg == 0 && tig == 0) {
 #pragma unroll
                 for (int g = 0; g < H; ++g)
 #pragma unroll
                     for (int rs = 0; rs < 2; ++rs) {
-                        const float2 o = xc[(quarter * 16 + rs * 8 + gid) * H + g];
-                        stat_merge(m[g][rs], l[g][rs], o.x, o.y);
-                        p.part[(((long long)b * p.nchunk + chunk) * H + g) * p.Npad + (row_a - 0) + rs * 8] = make_float2(m[g][rs], l[g][rs]);
+                        for (int c = 0; c < NCG - 1; ++c) {
+                            const float2 o = xc[(c * RB + quarter * 16 + rs * 8 + gid) * H + g];
+                            stat_merge(m[g][rs], l[g][rs], o.x, o.y);
+                        }
+                        p.part[(((long long)b * p.nchunk + chunk) * H + g) * p.Npad + row_a + rs * 8] = make_float2(m[g][rs], l[g][rs]);
                     }
             }
         } else {
             uint32_t ww[(H / 4) * (H / 2)][2];
-            load_wfrag<H, false, false>(p.Ww, 1.f, lane, ww);
-            // merged statistics of this thread's two rows: c1[g][rs] = log2e bl[g] - lse2 + P_SHIFT
+            load_wfrag<H, false, false>(wsm + H * H, 1.f, lane, ww);
+            // c1[g][rs] = log2e bl[g] - lse2 + P_SHIFT (the first mix then yields the exponent of 2^8 P directly);  c2[g] = 2^8 bw[g]
             float c1[H][2], c2[H];
+            const float* ls = reinterpret_cast<const float*>(smem + SM::LSE);
 #pragma unroll
             for (int g = 0; g < H; ++g) {
-                c2[g] = p.bw[g] * 256.f;                            // 2^P_SHIFT bw
+                c2[g] = wsm[2 * H * H + H + g];
 #pragma unroll
-                for (int rs = 0; rs < 2; ++rs) {
-                    float m = -1e30f, l = 0.f;
-                    for (int c = 0; c < p.nchunk; ++c) {
-                        const float2 o = p.part[(((long long)b * p.nchunk + c) * H + g) * p.Npad + row_a + rs * 8];
-                        stat_merge(m, l, o.x, o.y);
-                    }
-                    const float lse = m + log2f(l);
-                    c1[g][rs] = LOG2E * p.bl[g] - lse + P_SHIFT;
-                    if (chunk == 0 && colhalf == 0 && tig == 0 && row_a + rs * 8 < p.N) p.lse2[((long long)b * H + g) * p.N + row_a + rs * 8] = lse;
-                }
+                for (int rs = 0; rs < 2; ++rs) c1[g][rs] = wsm[2 * H * H + g] - ls[g * RB + quarter * 16 + rs * 8 + gid] + P_SHIFT;
             }
+            // (the token ping-pong of the statistics kernel does not pay here: with the accumulating tcgen05.mma stream competing for the
+            //  tensor cores a serialised mix phase takes ~2100 clocks per sub-tile, measured; the warps run free instead)
+            tok_acquire();
+            tok_release();
             for (int jl = 0; jl < nb; ++jl) {
-                const uint32_t sb = (uint32_t)jl & 1u;
+                const uint32_t sb = (uint32_t)jl & 1u, ab = (uint32_t)jl % SM::NABUF;
+                if (warp == 2) TF_TRACE(2, jl, 0);
                 mbar_wait(sfull0 + 8 * sb, ((uint32_t)jl >> 1) & 1u);
+                mbar_wait(aempty0 + 8 * ab, (((uint32_t)jl / SM::NABUF) & 1u) ^ 1u);
                 fence_after();
-                float x[H][4];
-                if (!(p.dbg & 128)) {
-                ld_tiles<H>(tS + tl + ((sb * 16u) << 16) + (uint32_t)(colhalf * 8), x);
+                float xs[NSUB][H][4];
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub) ld_tiles<H, CB>(tS + tl + ((sb * 16u) << 16) + (uint32_t)((cg * NSUB + sub) * 8), xs[sub]);
                 ld_wait();
-                } else {
-#pragma unroll
-                    for (int g = 0; g < H; ++g)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) x[g][i] = (float)(g + i + jl);
-                }
                 fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sempty0 + 8 * sb);
-                float y[H][4];
-                if (!(p.dbg & 4)) head_mix<H, false>(x, wl, [&](int g, int i) { return c1[g][i >> 1]; }, y);
-                else {
+                if (warp == 2) TF_TRACE(2, jl, 1);
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub) {
+                    float y[H][4];
+                    if (!(p.dbg & 4)) head_mix<H, false>(xs[sub], wl, [&](int g, int i) { return c1[g][i >> 1]; }, y);
+                    else {
+#pragma unroll
+                        for (int g = 0; g < H; ++g)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) y[g][i] = xs[sub][g][i] + c1[g][i >> 1];
+                    }
 #pragma unroll
                     for (int g = 0; g < H; ++g)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) y[g][i] = x[g][i] + c1[g][i >> 1];
+                        for (int i = 0; i < 4; ++i) y[g][i] = (p.dbg & 8) ? y[g][i] * 0.001f : ex2(y[g][i]);
+                    if (!(p.dbg & 16)) head_mix<H, false>(y, ww, [&](int g, int) { return c2[g]; }, xs[sub]);
+                    else {
+#pragma unroll
+                        for (int g = 0; g < H; ++g)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) xs[sub][g][i] = y[g][i] + c2[g];
+                    }
+                    if (!(p.dbg & 32)) st_tiles<H, CB>(sbase + SM::A + ab * SM::A_B, quarter, cg * NSUB + sub, lane, xs[sub]);
                 }
-#pragma unroll
-                for (int g = 0; g < H; ++g)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) y[g][i] = (p.dbg & 8) ? y[g][i] * 0.001f : ex2(y[g][i]);
-                if (!(p.dbg & 16)) head_mix<H, false>(y, ww, [&](int g, int) { return c2[g]; }, x);
-                else {
-#pragma unroll
-                    for (int g = 0; g < H; ++g)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) x[g][i] = y[g][i] + c2[g];
-                }
-                mbar_wait(aempty0 + 8 * sb, (((uint32_t)jl >> 1) & 1u) ^ 1u);
-                if (!(p.dbg & 32)) st_tiles<H>(sbase + SM::A + sb * SM::A_B, quarter, colhalf, lane, x);
-                if (!(p.dbg & 256)) fence_async_smem();
+                if (warp == 2) TF_TRACE(2, jl, 2);
+                fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(afull0 + 8 * sb);
+                if (lane == 0) mbar_arrive(afull0 + 8 * ab);
             }
-            // ---- output: O rows of this quarter are TMEM lanes [32 q, 32 q + 16); each column-half warp takes D / 2 columns
+            // ---- output: lanes [0, 16) of the quarter hold O columns [0, O_CAP), lanes [16, 32) the columns [O_CAP, D) of the same
+            // 16 rows; each column-group warp takes half of the TMEM columns
             mbar_wait(ofull, 0);
             fence_after();
-            const int row = r0 + quarter * 16 + lane;
+            const int row = r0 + quarter * 16 + (lane & 15);
             const float inv = 1.f / 256.f;
+            constexpr int OC = D < (int)SM::O_CAP ? D : (int)SM::O_CAP;     // TMEM columns in use
 #pragma unroll 1
-            for (int c = 0; c < D / 2; c += 16) {
+            for (int c = cg * (OC / NCG); c < (cg + 1) * (OC / NCG); c += 16) {
                 uint32_t o[16];
-                const int col = colhalf * (D / 2) + c;
-                UMMA_LD_32x32_X16(tO + tl + (uint32_t)col, o);
+                UMMA_LD_32x32_X16(tO + tl + (uint32_t)c, o);
                 ld_wait();
-                if (lane < 16 && row < p.N) {
+                const int col = lane < 16 ? c : (int)SM::O_CAP + c;
+                if (row < p.N && col < D) {
                     if (p.out32 != nullptr) {
                         float* dst = p.out32 + ((long long)b * p.N + row) * D + col;
 #pragma unroll
@@ -485,7 +585,22 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
     }
     fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(SM::TMEM_COLS) : "memory");
+}
+
+// lse2[b][g][row] = log2-domain logsumexp merged over the column chunks of the stats kernel
+__global__ void tf_merge_kernel(const float2* __restrict__ part, float* __restrict__ lse2, int B, int H, int N, int Npad, int nchunk) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * H * N) return;
+    const int row = (int)(i % N);
+    const int g = (int)((i / N) % H);
+    const int b = (int)(i / ((long long)N * H));
+    float m = -1e30f, l = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+        const float2 o = part[(((long long)b * nchunk + c) * H + g) * Npad + row];
+        stat_merge(m, l, o.x, o.y);
+    }
+    lse2[i] = m + log2f(l);
 }
 
 __global__ void tf_cast_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long rows, int D, long long dst_ld, int N, long long dst_sb) {
@@ -500,7 +615,8 @@ __global__ void tf_cast_bf16_kernel(const float* __restrict__ src, uint16_t* __r
     *reinterpret_cast<uint2*>(dst + bimg * dst_sb + n * dst_ld + c) = o;
 }
 
-int pick_nchunk(int ctas0, int nblk) {
+// chunks of the streamed range per row block: fill the SMs (waves x per-CTA time), ~`fixed` blocks' worth of per-CTA prologue / epilogue
+int pick_nchunk(int ctas0, int nblk, double fixed) {
     static const char* env = getenv("SPE_TF_NCHUNK");
     if (env) { int v = atoi(env); if (v >= 1) return v > nblk ? nblk : v; }
     const int sms = spe_num_sms();
@@ -510,54 +626,67 @@ int pick_nchunk(int ctas0, int nblk) {
         const int bpc = (nblk + nc - 1) / nc;
         const int real_nc = (nblk + bpc - 1) / bpc;
         const double waves = (double)((ctas0 * real_nc + sms - 1) / sms);
-        const double cost = waves * (bpc + 6.0);               // ~6 blocks' worth of per-CTA prologue / epilogue
+        const double cost = waves * (bpc + fixed);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = real_nc; }
     }
     return best;
 }
 
+long long* g_tf_trace = nullptr;
+
 template <int H>
 int launch_fwd(const spe_talking_fused_args* a, cudaStream_t st) {
-    using SM = FwdSmem<H>;
+    using SMS = FwdSmem<H, CB_STATS, true>;
+    using SMM = FwdSmem<H, CB_MAIN, false>;
     const int D = H * DHD, N = a->N, B = a->B;
-    const int nrb = (N + RB - 1) / RB, nblk = (N + CB - 1) / CB;
+    const int nrb = (N + RB - 1) / RB;
     const int Npad = nrb * RB;
-    int nchunk = pick_nchunk(nrb * B, nblk);
-    const int bpc = (nblk + nchunk - 1) / nchunk;
-    nchunk = (nblk + bpc - 1) / bpc;
-    const size_t part_b = (size_t)B * nchunk * H * Npad * sizeof(float2);
-    const size_t o32_b = nchunk > 1 ? (size_t)B * N * D * sizeof(float) : 0;
-    SPE_CHECK(a->workspace && (size_t)a->workspace_bytes >= ((part_b + 255) / 256) * 256 + o32_b, "spe_talking_fused_fwd: workspace too small");
-    CUtensorMap tq, tk, tv;
+    const int nblk_s = (N + CB_STATS - 1) / CB_STATS, nblk_m = (N + CB_MAIN - 1) / CB_MAIN;
+    int nc_s = pick_nchunk(nrb * B, nblk_s, 3.0), nc_m = pick_nchunk(nrb * B, nblk_m, 4.0);
+    const int bpc_s = (nblk_s + nc_s - 1) / nc_s, bpc_m = (nblk_m + nc_m - 1) / nc_m;
+    nc_s = (nblk_s + bpc_s - 1) / bpc_s;
+    nc_m = (nblk_m + bpc_m - 1) / bpc_m;
+    const size_t part_b = (((size_t)B * nc_s * H * Npad * sizeof(float2)) + 255) / 256 * 256;
+    const size_t o32_b = nc_m > 1 ? (size_t)B * N * D * sizeof(float) : 0;
+    SPE_CHECK(a->workspace && (size_t)a->workspace_bytes >= part_b + o32_b, "spe_talking_fused_fwd: workspace too small");
+    CUtensorMap tq, tks, tkm, tv;
     if (make_map(&tq, a->q, D, N, B, a->q_ld, a->q_sb, RB)) return -1;
-    if (make_map(&tk, a->k, D, N, B, a->k_ld, a->k_sb, CB)) return -1;
-    if (make_map(&tv, a->v, D, N, B, a->v_ld, a->v_sb, CB)) return -1;
+    if (make_map(&tks, a->k, D, N, B, a->k_ld, a->k_sb, CB_STATS)) return -1;
+    if (make_map(&tkm, a->k, D, N, B, a->k_ld, a->k_sb, CB_MAIN)) return -1;
+    if (make_map(&tv, a->v, D, N, B, a->v_ld, a->v_sb, CB_MAIN)) return -1;
     TfFwdParams p;
-    p.N = N; p.nblk = nblk; p.nchunk = nchunk; p.bpc = bpc; p.Npad = Npad;
+    p.N = N; p.Npad = Npad;
     p.Wl = a->Wl; p.bl = a->bl; p.Ww = a->Ww; p.bw = a->bw; p.scale = a->scale;
     p.part = reinterpret_cast<float2*>(a->workspace);
     p.lse2 = a->lse2;
     p.out = reinterpret_cast<uint16_t*>(a->out); p.out_ld = a->out_ld; p.out_sb = a->out_sb;
-    p.out32 = nchunk > 1 ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + ((part_b + 255) / 256) * 256) : nullptr;
+    p.out32 = nc_m > 1 ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + part_b) : nullptr;
     static const char* dbg_env = getenv("SPE_TF_DBG");
     p.dbg = dbg_env ? atoi(dbg_env) : 0;
+    if ((p.dbg & 512) && !g_tf_trace) { cudaMalloc(&g_tf_trace, 4 * 32 * 8 * 8); cudaMemset(g_tf_trace, 0, 4 * 32 * 8 * 8); }
+    p.trace = nullptr;
     static bool attr_done = false;
     if (!attr_done) {
-        SPE_CUDA(cudaFuncSetAttribute(tf_fwd_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL));
-        SPE_CUDA(cudaFuncSetAttribute(tf_fwd_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL));
+        SPE_CUDA(cudaFuncSetAttribute(tf_fwd_kernel<H, CB_STATS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMS::TOTAL));
+        SPE_CUDA(cudaFuncSetAttribute(tf_fwd_kernel<H, CB_MAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMM::TOTAL));
         attr_done = true;
     }
-    const dim3 grid(nrb, nchunk, B);
     const double pos = (double)B * N * N;
     {
         SpeProfScope ps(SPE_FAM_TALKING_FWD, pos * H * 4.0, st, "tf_stats");
-        tf_fwd_kernel<H, true><<<grid, TF_THREADS, SM::TOTAL, st>>>(tq, tk, tv, p);
+        p.nblk = nblk_s; p.nchunk = nc_s; p.bpc = bpc_s;
+        tf_fwd_kernel<H, CB_STATS, true><<<dim3(nrb, nc_s, B), TF_THREADS, SMS::TOTAL, st>>>(tq, tks, tks, p);
+        SPE_LAUNCHED();
+        const long long tot = (long long)B * H * N;
+        tf_merge_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.part, p.lse2, B, H, N, Npad, nc_s);
         SPE_LAUNCHED();
     }
     if (p.out32) SPE_CUDA(cudaMemsetAsync(p.out32, 0, o32_b, st));
     {
         SpeProfScope ps(SPE_FAM_TALKING_FWD, pos * H * 4.0, st, "tf_main");
-        tf_fwd_kernel<H, false><<<grid, TF_THREADS, SM::TOTAL, st>>>(tq, tk, tv, p);
+        p.nblk = nblk_m; p.nchunk = nc_m; p.bpc = bpc_m;
+        p.trace = (p.dbg & 512) ? g_tf_trace : nullptr;
+        tf_fwd_kernel<H, CB_MAIN, false><<<dim3(nrb, nc_m, B), TF_THREADS, SMM::TOTAL, st>>>(tq, tkm, tv, p);
         SPE_LAUNCHED();
     }
     if (p.out32) {
@@ -570,6 +699,12 @@ int launch_fwd(const spe_talking_fused_args* a, cudaStream_t st) {
 
 }  // namespace
 
+// timing experiments: copies the clock64 trace of the last main-kernel launch (SPE_TF_DBG & 512) to host memory [4][32][8]
+extern "C" __attribute__((visibility("default"))) int spe_talking_fused_trace(long long* host_out) {
+    if (!g_tf_trace) return -1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host_out, g_tf_trace, 4 * 32 * 8 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
 extern "C" __attribute__((visibility("default"))) int spe_talking_fused_supported(int H, int dh) { return (H == 4 || H == 8) && dh == DHD ? 1 : 0; }
 
 extern "C" __attribute__((visibility("default"))) int64_t spe_talking_fused_fwd_workspace(int B, int H, int N, int dh) {

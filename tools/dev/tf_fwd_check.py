@@ -61,4 +61,16 @@ if __name__ == "__main__":
                 f = line.strip().split(",")
                 acc[f[1]].append(float(f[3]))
             print("DBG", os.environ.get("SPE_TF_DBG"), "NCHUNK", os.environ.get("SPE_TF_NCHUNK"), {k: round(1000 * sum(v) / len(v), 1) for k, v in acc.items()}, "us")
+    if int(os.environ.get("SPE_TF_DBG", "0")) & 512:
+        import numpy as np
+        buf = (C.c_longlong * (4 * 32 * 8))()
+        lib().spe_talking_fused_trace.argtypes = [C.c_void_p]
+        lib().spe_talking_fused_trace(buf)
+        t = np.array(buf[:]).reshape(4, 32, 8)
+        t0 = t[t > 0].min()
+        names = {0: "TMA  [yempty, zempty]", 1: "MMA  [top, yfull, sempty, S issued, afull, zfull, PV issued]", 2: "POS  [top, exp done, token, mix2+st done, next load+mix1 done, next load done]"}
+        for role in (0, 1, 2):
+            print(names[role])
+            for blk in range(4, 14):
+                print("   blk %2d " % blk, " ".join("%7d" % (v - t0 if v else -1) for v in t[role, blk, :7]))
     print("FAIL" if bad else "OK")
