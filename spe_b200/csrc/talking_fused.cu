@@ -116,6 +116,49 @@ __device__ __forceinline__ void head_mix(const float (&x)[H][4], const uint32_t 
     }
 }
 
+// A fragments of the thread's four positions: [j (column parity)][hq (head quad)][4]
+template <int H, bool BF16>
+__device__ __forceinline__ void pack_afrag(const float (&x)[H][4], uint32_t (&a)[2][H / 4][4]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int hq = 0; hq < H / 4; ++hq) {
+            if (BF16) {
+                a[j][hq][0] = pack_bf16(x[4 * hq][j], x[4 * hq + 1][j]);
+                a[j][hq][1] = pack_bf16(x[4 * hq][2 + j], x[4 * hq + 1][2 + j]);
+                a[j][hq][2] = pack_bf16(x[4 * hq + 2][j], x[4 * hq + 3][j]);
+                a[j][hq][3] = pack_bf16(x[4 * hq + 2][2 + j], x[4 * hq + 3][2 + j]);
+            } else {
+                a[j][hq][0] = pack_f16(x[4 * hq][j], x[4 * hq + 1][j]);
+                a[j][hq][1] = pack_f16(x[4 * hq][2 + j], x[4 * hq + 1][2 + j]);
+                a[j][hq][2] = pack_f16(x[4 * hq + 2][j], x[4 * hq + 3][j]);
+                a[j][hq][3] = pack_f16(x[4 * hq + 2][2 + j], x[4 * hq + 3][2 + j]);
+            }
+        }
+}
+// head mix with a hand-interleaved side job: the H*H/4 mma.sync are issued in (j, hq, gp) order -- the accumulation chains of the
+// H/2 output pairs stay H/2 instructions apart -- and `side(k)` runs after the k-th one (exp2 of another sub-tile: the MUFU pipe
+// works under the tensor pipe from ONE warp; left to the compiler the phases serialise, which is what bounded the first version)
+template <int H, bool BF16, class CInit, class Side>
+__device__ __forceinline__ void head_mix_il(const uint32_t (&a)[2][H / 4][4], const uint32_t (&wf)[(H / 4) * (H / 2)][2], CInit cinit, float (&y)[H][4], Side side) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float d[H / 2][4];
+#pragma unroll
+        for (int gp = 0; gp < H / 2; ++gp) { d[gp][0] = cinit(2 * gp, j); d[gp][1] = cinit(2 * gp + 1, j); d[gp][2] = cinit(2 * gp, 2 + j); d[gp][3] = cinit(2 * gp + 1, 2 + j); }
+#pragma unroll
+        for (int hq = 0; hq < H / 4; ++hq)
+#pragma unroll
+            for (int gp = 0; gp < H / 2; ++gp) {
+                if (BF16) hmma_bf16_v(d[gp], a[j][hq], wf[hq * (H / 2) + gp][0], wf[hq * (H / 2) + gp][1]);
+                else hmma_f16_v(d[gp], a[j][hq], wf[hq * (H / 2) + gp][0], wf[hq * (H / 2) + gp][1]);
+                side((j * (H / 4) + hq) * (H / 2) + gp);
+            }
+#pragma unroll
+        for (int gp = 0; gp < H / 2; ++gp) { y[2 * gp][j] = d[gp][0]; y[2 * gp + 1][j] = d[gp][1]; y[2 * gp][2 + j] = d[gp][2]; y[2 * gp + 1][2 + j] = d[gp][3]; }
+    }
+}
+
 // the H tiles of one block: head h at column h * CB (+ this warp's 8-column half), lanes [lane_base, lane_base + 16)
 template <int H, int CB>
 __device__ __forceinline__ void ld_tiles(uint32_t taddr, float (&x)[H][4]) {
@@ -229,7 +272,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
         if (!STATS) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
         mbar_init(xfull, 1);
         for (int s = 0; s < NSTG; ++s) { mbar_init(yfull0 + 8 * s, 1); mbar_init(yempty0 + 8 * s, 1); mbar_init(zfull0 + 8 * s, 1); mbar_init(zempty0 + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(sfull0 + 8 * s, 1); mbar_init(sempty0 + 8 * s, NPW); mbar_init(afull0 + 8 * s, NPW); mbar_init(aempty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(sfull0 + 8 * s, 1); mbar_init(sempty0 + 8 * s, STATS ? NPW : NPW / 2); mbar_init(afull0 + 8 * s, NPW / 2); mbar_init(aempty0 + 8 * s, 1); }
         mbar_init(ofull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
@@ -498,46 +541,43 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_fwd_kernel(const __grid_cons
 #pragma unroll
                 for (int rs = 0; rs < 2; ++rs) c1[g][rs] = wsm[2 * H * H + g] - ls[g * RB + quarter * 16 + rs * 8 + gid] + P_SHIFT;
             }
-            // (the token ping-pong of the statistics kernel does not pay here: with the accumulating tcgen05.mma stream competing for the
-            //  tensor cores a serialised mix phase takes ~2100 clocks per sub-tile, measured; the warps run free instead)
+            // The two warps of a lane quarter (= one SM sub-partition: one mma.sync pipe, one MUFU pipe) take ALTERNATE blocks: each
+            // waits on its own barriers, so the pair drifts out of phase and one warp's exponentials run under the other's mixes.
+            // (Sharing every block, the pair re-aligns at each block barrier and the pipes take turns idling: 3100 clocks of a 3750
+            //  clock block period were the serialised sum of the pipe times; a token ping-pong and a hand-interleaved software
+            //  pipeline were both measured slower: the accumulating tcgen05.mma stream competes for the tensor cores.)
             tok_acquire();
             tok_release();
-            for (int jl = 0; jl < nb; ++jl) {
+            constexpr int NSB = CB / 8;                           // 8-column sub-tiles per block
+            for (int jl = cg; jl < nb; jl += 2) {
                 const uint32_t sb = (uint32_t)jl & 1u, ab = (uint32_t)jl % SM::NABUF;
                 if (warp == 2) TF_TRACE(2, jl, 0);
                 mbar_wait(sfull0 + 8 * sb, ((uint32_t)jl >> 1) & 1u);
                 mbar_wait(aempty0 + 8 * ab, (((uint32_t)jl / SM::NABUF) & 1u) ^ 1u);
                 fence_after();
-                float xs[NSUB][H][4];
-#pragma unroll
-                for (int sub = 0; sub < NSUB; ++sub) ld_tiles<H, CB>(tS + tl + ((sb * 16u) << 16) + (uint32_t)((cg * NSUB + sub) * 8), xs[sub]);
-                ld_wait();
-                fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(sempty0 + 8 * sb);
                 if (warp == 2) TF_TRACE(2, jl, 1);
+#pragma unroll 1
+                for (int sub = 0; sub < NSB; sub += 2) {
+                    float xs[2][H][4];
 #pragma unroll
-                for (int sub = 0; sub < NSUB; ++sub) {
-                    float y[H][4];
-                    if (!(p.dbg & 4)) head_mix<H, false>(xs[sub], wl, [&](int g, int i) { return c1[g][i >> 1]; }, y);
-                    else {
+                    for (int u = 0; u < 2; ++u) ld_tiles<H, CB>(tS + tl + ((sb * 16u) << 16) + (uint32_t)((sub + u) * 8), xs[u]);
+                    ld_wait();
+                    if (sub + 2 == NSB) {
+                        fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(sempty0 + 8 * sb);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        float y[H][4];
+                        head_mix<H, false>(xs[u], wl, [&](int g, int i) { return c1[g][i >> 1]; }, y);
 #pragma unroll
                         for (int g = 0; g < H; ++g)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) y[g][i] = xs[sub][g][i] + c1[g][i >> 1];
+                            for (int i = 0; i < 4; ++i) y[g][i] = ex2(y[g][i]);
+                        head_mix<H, false>(y, ww, [&](int g, int) { return c2[g]; }, xs[u]);
+                        st_tiles<H, CB>(sbase + SM::A + ab * SM::A_B, quarter, sub + u, lane, xs[u]);
                     }
-#pragma unroll
-                    for (int g = 0; g < H; ++g)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) y[g][i] = (p.dbg & 8) ? y[g][i] * 0.001f : ex2(y[g][i]);
-                    if (!(p.dbg & 16)) head_mix<H, false>(y, ww, [&](int g, int) { return c2[g]; }, xs[sub]);
-                    else {
-#pragma unroll
-                        for (int g = 0; g < H; ++g)
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) xs[sub][g][i] = y[g][i] + c2[g];
-                    }
-                    if (!(p.dbg & 32)) st_tiles<H, CB>(sbase + SM::A + ab * SM::A_B, quarter, cg * NSUB + sub, lane, xs[sub]);
                 }
                 if (warp == 2) TF_TRACE(2, jl, 2);
                 fence_async_smem();
