@@ -203,6 +203,24 @@ typedef struct {
 int spe_talking_fused_supported(int H, int dh);
 int64_t spe_talking_fused_fwd_workspace(int B, int H, int N, int dh);
 int spe_talking_fused_fwd(const spe_talking_fused_args* a, void* stream);
+/* backward: dO bf16 [B,N,H*dh] -> dqkv bf16 [B,N,3*H*dh] (token stride dqkv_ld; dq | dk | dv thirds), dWl / dWw f32 [H,H]
+ * ACCUMULATED (+=).  dbl is identically 0 (softmax is shift invariant) and dbw = sum_b colsum(dO) . colsum(V) is exact outside.
+ * Recomputes the logits from q, k and lse2 in three launches (delta + dWw; dQ + dWl; dK + dV). */
+typedef struct {
+    int B, H, N, dh;
+    const void* q; int64_t q_ld, q_sb;
+    const void* k; int64_t k_ld, k_sb;
+    const void* v; int64_t v_ld, v_sb;
+    const void* dO; int64_t do_ld, do_sb;
+    const float *Wl, *bl, *Ww, *bw;
+    float scale;
+    const float* lse2;                    /* f32 [B,H,N] from spe_talking_fused_fwd */
+    void* dqkv; int64_t dqkv_ld;          /* bf16 [B*N, 3*H*dh], rows contiguous over (b, n) */
+    float *dWl, *dWw;                     /* f32 [H,H], += */
+    void* workspace; int64_t workspace_bytes;
+} spe_talking_fused_bwd_args;
+int64_t spe_talking_fused_bwd_workspace(int B, int H, int N, int dh);
+int spe_talking_fused_bwd(const spe_talking_fused_bwd_args* a, void* stream);
 
 /* Plain softmax over keys with optional key-padding mask (attention.py:363-371, nn.MultiheadAttention).
  * S f32 [B,H,Nq,ldS] -> P bf16 [B,H,Nq,ldP]; mask u8 [B,Nk] (1 = padded -> -inf) or NULL.

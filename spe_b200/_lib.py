@@ -64,6 +64,13 @@ class TalkingFusedArgs(C.Structure):
                 ("out", c_p), ("out_ld", c_l), ("out_sb", c_l), ("lse2", c_p), ("workspace", c_p), ("workspace_bytes", c_l)]
 
 
+class TalkingFusedBwdArgs(C.Structure):
+    _fields_ = [("B", c_i), ("H", c_i), ("N", c_i), ("dh", c_i),
+                ("q", c_p), ("q_ld", c_l), ("q_sb", c_l), ("k", c_p), ("k_ld", c_l), ("k_sb", c_l), ("v", c_p), ("v_ld", c_l), ("v_sb", c_l),
+                ("dO", c_p), ("do_ld", c_l), ("do_sb", c_l), ("Wl", c_p), ("bl", c_p), ("Ww", c_p), ("bw", c_p), ("scale", c_f), ("lse2", c_p),
+                ("dqkv", c_p), ("dqkv_ld", c_l), ("dWl", c_p), ("dWw", c_p), ("workspace", c_p), ("workspace_bytes", c_l)]
+
+
 _SIGS = {
     "spe_version": (c_i, []),
     "spe_launch_count": (c_l, []),
@@ -85,6 +92,8 @@ _SIGS = {
     "spe_talking_fused_supported": (c_i, [c_i, c_i]),
     "spe_talking_fused_fwd_workspace": (c_l, [c_i, c_i, c_i, c_i]),
     "spe_talking_fused_fwd": (c_i, [C.POINTER(TalkingFusedArgs), c_p]),
+    "spe_talking_fused_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i]),
+    "spe_talking_fused_bwd": (c_i, [C.POINTER(TalkingFusedBwdArgs), c_p]),
     "spe_softmax_fwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p]),
     "spe_cam_std_reweight": (c_i, [c_p, c_i, c_i, c_i, c_l, c_i, c_i, c_i, c_i, c_p, c_p]),
     "spe_softmax_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_p]),

@@ -737,6 +737,428 @@ int launch_fwd(const spe_talking_fused_args* a, cudaStream_t st) {
     return 0;
 }
 
+// parameter gradients: accumulate (+=) the launch's sums into the caller's gradient buffers
+__global__ void tf_addw_kernel(const float* __restrict__ dw, float* __restrict__ dWw, float* __restrict__ dWl, int n) {
+    const int i = threadIdx.x;
+    if (i < n) dWw[i] += dw[i];
+    else if (i < 2 * n) dWl[i - n] += dw[i];
+}
+
+// =============================================================================================================================
+// Backward.  With p = softmax(L) (per mixed head g), A = Ww p + bw, O = A V:
+//   dA_g = dO_g V_g^T,  dP_h = sum_g Ww[g,h] dA_g,  delta_h = rowsum(p_h dP_h),  dL_h = p_h (dP_h - delta_h),
+//   dS_h = sum_g Wl[g,h] dL_g,  dQ_h = scale dS_h K_h,  dK_h = scale dS_h^T Q_h,  dV_g = A_g^T dO_g,
+//   dWw[g,h] = sum dA_g p_h,  dWl[g,h] = sum dL_g S_h      (dbl = 0: softmax is shift invariant; dbw is exact outside)
+// Three launches, all recomputing S and p from q, k and the saved lse2 (no N^2 tensor in HBM):
+//   DELTA (query-stationary): delta, dWw          DQ (query-stationary): dQ, dWl          DKV (key-stationary): dK, dV
+// Same tile geometry as the forward with 16-column blocks: the S tile sits in lane half 0 and the dA tile in lane half 1 of the
+// same H x 16 TMEM columns (one tcgen05.ld.16x256b per head and tile gives a thread S and dA of the same four positions); the
+// 64 x 384 accumulators (dQ | dK and dV) use the two lane halves of the remaining 384 columns.  The parameter gradients are
+// tcgen05 products as well: D[(g, c), (h, c')] = sum_rows dL_g[row, c] S_h[row, c'] from the bf16 tiles read MN-major; only the
+// c = c' diagonal is kept (8x redundant tensor work, but no 64-accumulator FMA loop in the position threads).
+// Probabilities are carried as p' = 2^8 p (see the forward); every result that is linear in p' is scaled by 2^-8 when it leaves.
+// =============================================================================================================================
+enum { BW_DELTA = 0, BW_DQ = 1, BW_DKV = 2 };
+constexpr int CBB = 16;
+
+struct TfBwdParams {
+    int N, nblk, nchunk, bpc, Npad;
+    const float *Wl, *bl, *Ww, *bw;
+    float scale;
+    const float* lse2;                   // [B][H][N]
+    float* delta;                        // [B][H][N]   DELTA: += (zeroed by the caller)   DQ / DKV: read
+    float* dwacc;                        // [H*H]       DELTA: dWw +=    DQ: dWl +=
+    float* out0;                         // f32 [B][N][D]  DQ: dq +=    DKV: dk +=
+    float* out1;                         //                              DKV: dv +=
+};
+
+template <int H, int MODE>
+struct BwdSmem {
+    static constexpr int D = H * DHD, NT = D / 64, NSTG = 2;
+    static constexpr int NTILE = MODE == BW_DQ ? 3 : 2;
+    static constexpr uint32_t YT = CBB * 128;
+    static constexpr uint32_t X1 = 0, X2 = X1 + NT * XT_B;
+    static constexpr uint32_t Y1 = X2 + NT * XT_B, Y2 = Y1 + NSTG * NT * YT;
+    static constexpr uint32_t T_B = 8 * H * (CBB / 8) * 128;           // one bf16 tile [8 row groups][H][2][8 rows][16 B]
+    static constexpr uint32_t T0 = Y2 + NSTG * NT * YT;
+    static constexpr uint32_t BAR = T0 + NTILE * T_B;
+    static constexpr int NBAR = 1 + 2 * NSTG + 5;
+    static constexpr uint32_t TSLOT = BAR + NBAR * 8;
+    static constexpr uint32_t WSM = TSLOT + 16;                        // Wl' [H*H], Ww [H*H], bl' [H], bw' [H]
+    static constexpr uint32_t RC = WSM + (2 * H * H + 2 * H) * 4;      // row constants: lse2 [H][64], delta [H][64]
+    static constexpr uint32_t TOTAL = RC + 2 * H * RB * 4 + 1024;
+    static constexpr uint32_t S_COLS = H * CBB;
+};
+
+// D[(g, c), (h, c')] accumulator (64 x 64, f32) -> dst[g * H + h] += mul * sum_c D[(g, c), (h, c)].  `half`: TMEM lane half.
+template <int H>
+__device__ __forceinline__ void trick_epilogue(uint32_t taddr_q, int quarter, int lane, int half, float* dst, float mul) {
+    constexpr int CW = 64 / H;                                          // columns per head in the trick tile (8 or 16)
+    const int m = quarter * 16 + (lane & 15), gr = m / CW, c = m % CW;
+    float v[H];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t r[16];
+        UMMA_LD_32x32_X16(taddr_q + (uint32_t)(k * 16), r);
+        ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int n = k * 16 + i;                                   // column (h, c')
+            if (n % CW == 0) v[n / CW] = 0.f;
+            if ((n % CW) == c) v[n / CW] = __uint_as_float(r[i]);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+#pragma unroll
+        for (int o = 1; o < CW; o <<= 1) v[h] += __shfl_xor_sync(0xffffffffu, v[h], o);
+        if (c == 0 && (lane >> 4) == half) atomicAdd(dst + gr * H + h, v[h] * mul);
+    }
+}
+
+template <int H, int MODE>
+__global__ void __launch_bounds__(TF_THREADS, 1) tf_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                                                               const __grid_constant__ CUtensorMap tmY1, const __grid_constant__ CUtensorMap tmY2,
+                                                               const TfBwdParams p) {
+    using SM = BwdSmem<H, MODE>;
+    constexpr int D = SM::D, NT = SM::NT, NSTG = SM::NSTG;
+    constexpr uint32_t YT = SM::YT;
+    constexpr bool KEYST = MODE == BW_DKV;                            // key-stationary: rows = keys, columns = queries
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + SM::BAR;
+    const uint32_t xfull = bar0, yfull0 = xfull + 8, yempty0 = yfull0 + 8 * NSTG, sfull = yempty0 + 8 * NSTG, sempty = sfull + 8, tfull = sempty + 8,
+                   tempty = tfull + 8, accfull = tempty + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::TSLOT);
+    float* wsm = reinterpret_cast<float*>(smem + SM::WSM);
+    float* rc = reinterpret_cast<float*>(smem + SM::RC);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * RB, chunk = blockIdx.y, b = blockIdx.z;
+    const int blk0 = chunk * p.bpc;
+    const int nb = min(p.bpc, p.nblk - blk0);
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX1)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY1)) : "memory");
+        mbar_init(xfull, 1);
+        for (int s = 0; s < NSTG; ++s) { mbar_init(yfull0 + 8 * s, 1); mbar_init(yempty0 + 8 * s, 1); }
+        mbar_init(sfull, 1); mbar_init(sempty, 8); mbar_init(tfull, 8); mbar_init(tempty, 1); mbar_init(accfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        if (t < H * H) { wsm[t] = p.Wl[t] * (LOG2E * p.scale); wsm[H * H + t] = p.Ww[t]; }
+        if (t < H) { wsm[2 * H * H + t] = p.bl[t] * LOG2E; wsm[2 * H * H + H + t] = p.bw[t] * 256.f; }
+        if (!KEYST) {
+            for (int i = t; i < H * RB; i += 256) {
+                const int g = i / RB, r = i % RB;
+                const bool ok = r0 + r < p.N;
+                rc[i] = ok ? p.lse2[((long long)b * H + g) * p.N + r0 + r] : 0.f;
+                rc[H * RB + i] = (ok && MODE == BW_DQ) ? p.delta[((long long)b * H + g) * p.N + r0 + r] : 0.f;
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tT0 = tmem_base, tT1 = tmem_base + (16u << 16);               // S tile | dA tile
+    const uint32_t tA0 = tmem_base + SM::S_COLS, tA1 = tA0 + (16u << 16);         // accumulators: lane half 0 | 1
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (elect()) {
+            mbar_expect_tx(xfull, 2 * NT * XT_B);
+            for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::X1 + t * XT_B, &tmX1, xfull, t * 64, r0, b);
+            for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::X2 + t * XT_B, &tmX2, xfull, t * 64, r0, b);
+        }
+        __syncwarp();
+        for (int jl = 0; jl < nb; ++jl) {
+            const int s = jl % NSTG;
+            const int c0 = (blk0 + jl) * CBB;
+            mbar_wait(yempty0 + 8 * s, ((uint32_t)(jl / NSTG) & 1u) ^ 1u);
+            if (elect()) {
+                mbar_expect_tx(yfull0 + 8 * s, 2 * NT * YT);
+                for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::Y1 + (s * NT + t) * YT, &tmY1, yfull0 + 8 * s, t * 64, c0, b);
+                for (int t = 0; t < NT; ++t) tma_load_3d(sbase + SM::Y2 + (s * NT + t) * YT, &tmY2, yfull0 + 8 * s, t * 64, c0, b);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t ID_S = idesc_bf16(RB, CBB, false, false);
+        constexpr uint32_t ID_TRICK = idesc_bf16(64, 64, true, true);
+        constexpr int CW = 64 / H;                                      // columns per head in a parameter-gradient product
+        const uint64_t dX1 = desc(sbase + SM::X1, 0, 1024, 2), dX2 = desc(sbase + SM::X2, 0, 1024, 2);
+        auto issue_tiles = [&](int jl) {                                 // S -> lane half 0, dA -> lane half 1
+            const int s = jl % NSTG;
+            const uint64_t dY1 = desc(sbase + SM::Y1 + s * NT * YT, 0, 1024, 2), dY2 = desc(sbase + SM::Y2 + s * NT * YT, 0, 1024, 2);
+#pragma unroll
+            for (int h = 0; h < H; ++h)
+#pragma unroll
+                for (int ks = 0; ks < DHD / 16; ++ks) {
+                    const int e = h * DHD + ks * 16;
+                    const uint64_t oa = (uint64_t)(((e >> 6) * XT_B + (e & 63) * 2) >> 4), ob = (uint64_t)(((e >> 6) * YT + (e & 63) * 2) >> 4);
+                    mma_f16(tT0 + (uint32_t)(h * CBB), dX1 + oa, dY1 + ob, ID_S, ks != 0);
+                    mma_f16(tT1 + (uint32_t)(h * CBB), dX2 + oa, dY2 + ob, ID_S, ks != 0);
+                }
+        };
+        // acc[:, head g] += tile_g (K-major, one k-step) x Y_g (MN-major inside the 64-column tiles of the streamed block)
+        auto issue_acc = [&](uint32_t tile, uint32_t ybase, uint32_t tacc, bool accum) {
+            const uint64_t dT = desc(tile, 128, H * (CBB / 8) * 128, 0);
+            const uint64_t dY = desc(ybase, YT, 1024, 2);
+#pragma unroll
+            for (int g = 0; g < H; ++g)
+#pragma unroll
+                for (int seg = 0; seg < 2; ++seg) {
+                    const int e0 = g * DHD;
+                    const int n0 = (64 - (e0 & 63)) < DHD ? (64 - (e0 & 63)) : DHD;
+                    const int e = seg == 0 ? e0 : e0 + n0, n = seg == 0 ? n0 : DHD - n0;
+                    if (n > 0)
+                        mma_f16(tacc + (uint32_t)e, dT + (uint64_t)((g * (CBB / 8) * 128) >> 4), dY + (uint64_t)(((e >> 6) * YT + (e & 63) * 2) >> 4),
+                                idesc_bf16(RB, n, false, true), accum);
+                }
+        };
+        // parameter-gradient product: D[(g, c), (h, c')] += sum_rows TA_g[row, c] TB_h[row, c'] (both tiles read MN-major, K = rows)
+        auto issue_trick = [&](uint32_t ta, uint32_t tb, uint32_t tacc, bool accum) {
+#pragma unroll
+            for (int grp = 0; grp < CBB / CW; ++grp) {
+                const uint64_t dA = desc(ta + grp * 128, 8 * H * (CBB / 8) * 16, (CW == 8 ? (CBB / 8) * 128 : 128), 0);
+                const uint64_t dB = desc(tb + grp * 128, 8 * H * (CBB / 8) * 16, (CW == 8 ? (CBB / 8) * 128 : 128), 0);
+#pragma unroll
+                for (int ks = 0; ks < RB / 16; ++ks) {
+                    const uint64_t o = (uint64_t)((ks * 2 * H * (CBB / 8) * 128) >> 4);
+                    mma_f16(tacc, dA + o, dB + o, ID_TRICK, accum || grp != 0 || ks != 0);
+                }
+            }
+        };
+        mbar_wait(xfull, 0);
+        mbar_wait(yfull0, 0);
+        fence_after();
+        if (elect()) { issue_tiles(0); commit(sfull); }
+        __syncwarp();
+        for (int jl = 0; jl < nb; ++jl) {
+            const int s = jl % NSTG;
+            if (jl + 1 < nb) {
+                mbar_wait(yfull0 + 8 * ((jl + 1) % NSTG), (uint32_t)((jl + 1) / NSTG) & 1u);
+                mbar_wait(sempty, (uint32_t)jl & 1u);                    // both tiles of block jl are in registers
+                fence_after();
+                if (elect()) { issue_tiles(jl + 1); commit(sfull); }
+                __syncwarp();
+            }
+            mbar_wait(tfull, (uint32_t)jl & 1u);
+            fence_after();
+            if (elect()) {
+                const uint32_t t0 = sbase + SM::T0, t1 = t0 + SM::T_B, t2 = t1 + SM::T_B;
+                const uint32_t y1 = sbase + SM::Y1 + s * NT * YT, y2 = sbase + SM::Y2 + s * NT * YT;
+                if (MODE == BW_DELTA) issue_trick(t1, t0, tA0, jl != 0);                       // dWw: dA (x) p
+                if (MODE == BW_DQ) { issue_acc(t0, y1, tA0, jl != 0); issue_trick(t1, t2, tA1, jl != 0); }     // dQ += dS K ; dWl: dL (x) S
+                if (MODE == BW_DKV) { issue_acc(t0, y1, tA0, jl != 0); issue_acc(t1, y2, tA1, jl != 0); }      // dK += dS^T Q ; dV += A^T dO
+                commit(tempty);
+                commit(yempty0 + 8 * s);
+            }
+            __syncwarp();
+        }
+        if (elect()) commit(accfull);
+        __syncwarp();
+    } else {
+        // ---------------- position warps: quarter = lane quarter, cg = 8-column half of the block ----------------
+        const int quarter = warp & 3, cg = (warp - 2) >> 2;
+        const int gid = lane >> 2, tig = lane & 3;
+        const uint32_t tl = (uint32_t)(quarter * 32) << 16;
+        uint32_t wl[(H / 4) * (H / 2)][2], wwT[(H / 4) * (H / 2)][2];
+        load_wfrag<H, false, false>(wsm, 1.f, lane, wl);                               // log2e scale Wl          (f16)
+        load_wfrag<H, true, true>(wsm + H * H, 1.f, lane, wwT);                        // Ww^T: dP = Ww^T dA      (bf16)
+        float c1[H][2], dl_[H][2];                                                     // query-stationary: per row
+        float dsum[H][2];
+#pragma unroll
+        for (int g = 0; g < H; ++g)
+#pragma unroll
+            for (int rs = 0; rs < 2; ++rs) {
+                c1[g][rs] = wsm[2 * H * H + g] - (KEYST ? 0.f : rc[g * RB + quarter * 16 + rs * 8 + gid]) + P_SHIFT;
+                dl_[g][rs] = KEYST ? 0.f : rc[H * RB + g * RB + quarter * 16 + rs * 8 + gid];
+                dsum[g][rs] = 0.f;
+            }
+        for (int jl = 0; jl < nb; ++jl) {
+            mbar_wait(sfull, (uint32_t)jl & 1u);
+            fence_after();
+            float x[H][4], da[H][4];
+            ld_tiles<H, CBB>(tT0 + tl + (uint32_t)(cg * 8), x);
+            ld_tiles<H, CBB>(tT1 + tl + (uint32_t)(cg * 8), da);
+            ld_wait();
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sempty);
+            // per-column constants (key-stationary): lse2 and delta of the thread's two query columns
+            float cl[H][2], cd[H][2];
+            if (KEYST) {
+                const int col = (blk0 + jl) * CBB + cg * 8 + 2 * tig;
+#pragma unroll
+                for (int g = 0; g < H; ++g)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const bool ok = col + j < p.N;
+                        const long long idx = ((long long)b * H + g) * p.N + col + j;
+                        cl[g][j] = c1[g][0] - (ok ? p.lse2[idx] : 0.f);
+                        cd[g][j] = ok ? p.delta[idx] : 0.f;
+                    }
+            }
+            mbar_wait(tempty, ((uint32_t)jl & 1u) ^ 1u);                 // the previous block's tiles have been consumed
+            const uint32_t t0 = sbase + SM::T0, t1 = t0 + SM::T_B, t2 = t1 + SM::T_B;
+            if (MODE == BW_DQ) st_tiles<H, CBB>(t2, quarter, cg, lane, x);                   // S (bf16) for dWl
+            if (MODE == BW_DELTA) st_tiles<H, CBB>(t1, quarter, cg, lane, da);               // dA (bf16) for dWw
+            float y[H][4];
+            if (KEYST) head_mix<H, false>(x, wl, [&](int g, int i) { return cl[g][i & 1]; }, y);
+            else head_mix<H, false>(x, wl, [&](int g, int i) { return c1[g][i >> 1]; }, y);
+#pragma unroll
+            for (int g = 0; g < H; ++g)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[g][i] = ex2(y[g][i]);                      // p' = 2^8 p
+            if (MODE == BW_DKV) {
+                uint32_t ww[(H / 4) * (H / 2)][2];
+                load_wfrag<H, false, false>(wsm + H * H, 1.f, lane, ww);
+                head_mix<H, false>(y, ww, [&](int g, int) { return wsm[2 * H * H + H + g]; }, x);      // A' = Ww p' + 2^8 bw
+                st_tiles<H, CBB>(t1, quarter, cg, lane, x);
+            }
+            head_mix<H, true>(da, wwT, [](int, int) { return 0.f; }, x);                // dP
+            if (MODE == BW_DELTA) {
+                st_tiles<H, CBB>(t0, quarter, cg, lane, y);                               // p' (bf16) for dWw
+#pragma unroll
+                for (int g = 0; g < H; ++g)
+#pragma unroll
+                    for (int rs = 0; rs < 2; ++rs) dsum[g][rs] += y[g][rs * 2] * x[g][rs * 2] + y[g][rs * 2 + 1] * x[g][rs * 2 + 1];
+            } else {
+#pragma unroll
+                for (int g = 0; g < H; ++g)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) y[g][i] *= x[g][i] - (KEYST ? cd[g][i & 1] : dl_[g][i >> 1]);      // dL' = p' (dP - delta)
+                if (MODE == BW_DQ) st_tiles<H, CBB>(t1, quarter, cg, lane, y);           // dL' (bf16) for dWl
+                uint32_t wlT[(H / 4) * (H / 2)][2];
+                load_wfrag<H, true, true>(wsm, 1.f / LOG2E, lane, wlT);                  // scale Wl^T: dS = Wl^T dL      (bf16)
+                head_mix<H, true>(y, wlT, [](int, int) { return 0.f; }, x);
+                st_tiles<H, CBB>(t0, quarter, cg, lane, x);                               // scale dS' (bf16)
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tfull);
+        }
+        // ---------------- epilogue ----------------
+        const float inv = 1.f / 256.f;
+        if (MODE == BW_DELTA) {
+#pragma unroll
+            for (int g = 0; g < H; ++g)
+#pragma unroll
+                for (int rs = 0; rs < 2; ++rs) {
+                    float v = dsum[g][rs];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    const int row = r0 + quarter * 16 + rs * 8 + gid;
+                    if (tig == 0 && row < p.N) atomicAdd(p.delta + ((long long)b * H + g) * p.N + row, v * inv);
+                }
+        }
+        mbar_wait(accfull, 0);
+        fence_after();
+        if (MODE == BW_DELTA && cg == 0) trick_epilogue<H>(tA0 + tl, quarter, lane, 0, p.dwacc, inv);
+        if (MODE == BW_DQ && cg == 0) trick_epilogue<H>(tA0 + tl, quarter, lane, 1, p.dwacc, inv * p.scale);
+        if (MODE != BW_DELTA) {
+            // lanes [0, 16): accumulator 0 (dQ | dK), lanes [16, 32): accumulator 1 (dV) of the same 16 rows; each warp half of the columns
+            const int row = r0 + quarter * 16 + (lane & 15);
+            float* dst0 = (lane < 16 ? p.out0 : p.out1);
+            const bool on = row < p.N && (lane < 16 || MODE == BW_DKV);
+#pragma unroll 1
+            for (int c = cg * (D / 2); c < (cg + 1) * (D / 2); c += 16) {
+                uint32_t o[16];
+                UMMA_LD_32x32_X16(tA0 + tl + (uint32_t)c, o);
+                ld_wait();
+                if (on) {
+                    float* dst = dst0 + ((long long)b * p.N + row) * D + c;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q4 * 4), "f"(__uint_as_float(o[q4 * 4]) * inv),
+                                     "f"(__uint_as_float(o[q4 * 4 + 1]) * inv), "f"(__uint_as_float(o[q4 * 4 + 2]) * inv),
+                                     "f"(__uint_as_float(o[q4 * 4 + 3]) * inv) : "memory");
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// dq | dk | dv (f32 [3][B*N][D]) -> packed bf16 dqkv [B, N, 3 D]
+__global__ void tf_pack_dqkv_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long rows, int D, long long dst_ld) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= 3 * rows * D) return;
+    const long long which = i / (rows * D), rem = i - which * rows * D;
+    const long long r = rem / D;
+    const int c = (int)(rem - r * D);
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<uint2*>(dst + r * dst_ld + which * D + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+}
+
+template <int H, int MODE>
+int launch_bwd_one(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& y1, const CUtensorMap& y2, TfBwdParams p, int nrb, int B, cudaStream_t st,
+                   const char* tag, double work) {
+    using SM = BwdSmem<H, MODE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SPE_CUDA(cudaFuncSetAttribute(tf_bwd_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL));
+        attr_done = true;
+    }
+    SpeProfScope ps(SPE_FAM_TALKING_BWD, work, st, tag);
+    tf_bwd_kernel<H, MODE><<<dim3(nrb, p.nchunk, B), TF_THREADS, SM::TOTAL, st>>>(x1, x2, y1, y2, p);
+    SPE_LAUNCHED();
+    return 0;
+}
+
+template <int H>
+int launch_bwd(const spe_talking_fused_bwd_args* a, cudaStream_t st) {
+    const int D = H * DHD, N = a->N, B = a->B;
+    const int nrb = (N + RB - 1) / RB, nblk = (N + CBB - 1) / CBB;
+    int nc = pick_nchunk(nrb * B, nblk, 6.0);
+    const int bpc = (nblk + nc - 1) / nc;
+    nc = (nblk + bpc - 1) / bpc;
+    const size_t delta_b = (((size_t)B * H * N * 4) + 255) / 256 * 256, dw_b = 256 * 4, acc_b = (size_t)3 * B * N * D * 4;
+    SPE_CHECK(a->workspace && (size_t)a->workspace_bytes >= delta_b + dw_b + acc_b, "spe_talking_fused_bwd: workspace too small");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+    float* delta = reinterpret_cast<float*>(ws);
+    float* dw = reinterpret_cast<float*>(ws + delta_b);                 // [2][H*H]: dWw, dWl
+    float* acc = reinterpret_cast<float*>(ws + delta_b + dw_b);        // [3][B*N][D]: dq, dk, dv
+    SPE_CUDA(cudaMemsetAsync(ws, 0, delta_b + dw_b + acc_b, st));
+    CUtensorMap q64, k64, v64, do64, q16, k16, v16, do16;
+    if (make_map(&q64, a->q, D, N, B, a->q_ld, a->q_sb, RB) || make_map(&k64, a->k, D, N, B, a->k_ld, a->k_sb, RB) ||
+        make_map(&v64, a->v, D, N, B, a->v_ld, a->v_sb, RB) || make_map(&do64, a->dO, D, N, B, a->do_ld, a->do_sb, RB) ||
+        make_map(&q16, a->q, D, N, B, a->q_ld, a->q_sb, CBB) || make_map(&k16, a->k, D, N, B, a->k_ld, a->k_sb, CBB) ||
+        make_map(&v16, a->v, D, N, B, a->v_ld, a->v_sb, CBB) || make_map(&do16, a->dO, D, N, B, a->do_ld, a->do_sb, CBB))
+        return -1;
+    TfBwdParams p;
+    p.N = N; p.nblk = nblk; p.nchunk = nc; p.bpc = bpc; p.Npad = nrb * RB;
+    p.Wl = a->Wl; p.bl = a->bl; p.Ww = a->Ww; p.bw = a->bw; p.scale = a->scale;
+    p.lse2 = a->lse2; p.delta = delta;
+    const double pos = (double)B * N * N * H;
+    p.dwacc = dw; p.out0 = nullptr; p.out1 = nullptr;
+    if (launch_bwd_one<H, BW_DELTA>(q64, do64, k16, v16, p, nrb, B, st, "tf_delta", pos * 4.0)) return -1;
+    p.dwacc = dw + H * H; p.out0 = acc;
+    if (launch_bwd_one<H, BW_DQ>(q64, do64, k16, v16, p, nrb, B, st, "tf_dq", pos * 4.0)) return -1;
+    p.dwacc = nullptr; p.out0 = acc + (size_t)B * N * D; p.out1 = acc + (size_t)2 * B * N * D;
+    if (launch_bwd_one<H, BW_DKV>(k64, v64, q16, do16, p, nrb, B, st, "tf_dkv", pos * 4.0)) return -1;
+    {
+        const long long tot = (long long)3 * B * N * D / 4;
+        tf_pack_dqkv_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(acc, reinterpret_cast<uint16_t*>(a->dqkv), (long long)B * N, D, a->dqkv_ld);
+        SPE_LAUNCHED();
+        tf_addw_kernel<<<1, 2 * H * H, 0, st>>>(dw, a->dWw, a->dWl, H * H);
+        SPE_LAUNCHED();
+    }
+    return 0;
+}
+
 }  // namespace
 
 // timing experiments: copies the clock64 trace of the last main-kernel launch (SPE_TF_DBG & 512) to host memory [4][32][8]
@@ -751,6 +1173,19 @@ extern "C" __attribute__((visibility("default"))) int64_t spe_talking_fused_fwd_
     const int nrb = (N + RB - 1) / RB;
     const int64_t part = (((int64_t)B * 8 * H * nrb * RB * 8 + 255) / 256) * 256;       // up to 8 chunks
     return part + (int64_t)B * N * H * dh * 4;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t spe_talking_fused_bwd_workspace(int B, int H, int N, int dh) {
+    return (((int64_t)B * H * N * 4 + 255) / 256) * 256 + 1024 + (int64_t)3 * B * N * H * dh * 4;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_talking_fused_bwd(const spe_talking_fused_bwd_args* a, void* stream) {
+    SPE_CHECK(a && a->q && a->k && a->v && a->dO && a->lse2 && a->dqkv && a->dWl && a->dWw && a->Wl && a->bl && a->Ww && a->bw, "spe_talking_fused_bwd: null argument");
+    SPE_CHECK(spe_talking_fused_supported(a->H, a->dh), "spe_talking_fused_bwd: unsupported head geometry H=%d dh=%d", a->H, a->dh);
+    SPE_CHECK(a->B > 0 && a->N > 0 && a->B <= 65535, "spe_talking_fused_bwd: bad shape");
+    SPE_CHECK(a->dqkv_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a->dqkv) & 7) == 0, "spe_talking_fused_bwd: dqkv not 8-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return a->H == 8 ? launch_bwd<8>(a, st) : launch_bwd<4>(a, st);
 }
 
 extern "C" __attribute__((visibility("default"))) int spe_talking_fused_fwd(const spe_talking_fused_args* a, void* stream) {
