@@ -770,12 +770,14 @@ struct TfBwdParams {
     float* dwacc;                        // [H*H]       DELTA: dWw +=    DQ: dWl +=
     float* out0;                         // f32 [B][N][D]  DQ: dq +=    DKV: dk +=
     float* out1;                         //                              DKV: dv +=
+    long long* trace;
 };
 
 template <int H, int MODE>
 struct BwdSmem {
-    static constexpr int D = H * DHD, NT = D / 64, NSTG = 2;
+    static constexpr int D = H * DHD, NT = D / 64;
     static constexpr int NTILE = MODE == BW_DQ ? 3 : 2;
+    static constexpr int NSTG = MODE == BW_DQ ? 2 : 3;                 // streamed-block ring (TMA latency ~1700 clocks against a ~2500 clock block)
     static constexpr uint32_t YT = CBB * 128;
     static constexpr uint32_t X1 = 0, X2 = X1 + NT * XT_B;
     static constexpr uint32_t Y1 = X2 + NT * XT_B, Y2 = Y1 + NSTG * NT * YT;
@@ -786,7 +788,8 @@ struct BwdSmem {
     static constexpr uint32_t TSLOT = BAR + NBAR * 8;
     static constexpr uint32_t WSM = TSLOT + 16;                        // Wl' [H*H], Ww [H*H], bl' [H], bw' [H]
     static constexpr uint32_t RC = WSM + (2 * H * H + 2 * H) * 4;      // row constants: lse2 [H][64], delta [H][64]
-    static constexpr uint32_t TOTAL = RC + 2 * H * RB * 4 + 1024;
+    static constexpr uint32_t FR = RC + 2 * H * RB * 4;                // packed B fragments of Ww (f16) and scale Wl^T (bf16): [2][H*H/4][32 lanes] words
+    static constexpr uint32_t TOTAL = FR + 2 * (H * H / 4) * 32 * 4 + 1024;
     static constexpr uint32_t S_COLS = H * CBB;
 };
 
@@ -945,14 +948,19 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_bwd_kernel(const __grid_cons
         __syncwarp();
         for (int jl = 0; jl < nb; ++jl) {
             const int s = jl % NSTG;
+            TF_TRACE(1, jl, 0);
             if (jl + 1 < nb) {
                 mbar_wait(yfull0 + 8 * ((jl + 1) % NSTG), (uint32_t)((jl + 1) / NSTG) & 1u);
+                TF_TRACE(1, jl, 1);
                 mbar_wait(sempty, (uint32_t)jl & 1u);                    // both tiles of block jl are in registers
+                TF_TRACE(1, jl, 2);
                 fence_after();
                 if (elect()) { issue_tiles(jl + 1); commit(sfull); }
                 __syncwarp();
+                TF_TRACE(1, jl, 3);
             }
             mbar_wait(tfull, (uint32_t)jl & 1u);
+            TF_TRACE(1, jl, 4);
             fence_after();
             if (elect()) {
                 const uint32_t t0 = sbase + SM::T0, t1 = t0 + SM::T_B, t2 = t1 + SM::T_B;
@@ -964,6 +972,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_bwd_kernel(const __grid_cons
                 commit(yempty0 + 8 * s);
             }
             __syncwarp();
+            TF_TRACE(1, jl, 5);
         }
         if (elect()) commit(accfull);
         __syncwarp();
@@ -975,6 +984,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_bwd_kernel(const __grid_cons
         uint32_t wl[(H / 4) * (H / 2)][2], wwT[(H / 4) * (H / 2)][2];
         load_wfrag<H, false, false>(wsm, 1.f, lane, wl);                               // log2e scale Wl          (f16)
         load_wfrag<H, true, true>(wsm + H * H, 1.f, lane, wwT);                        // Ww^T: dP = Ww^T dA      (bf16)
+        // the two remaining fragment sets are kept packed in shared memory (register budget) and re-read per block: 16 LDS each
+        uint32_t* frs = reinterpret_cast<uint32_t*>(smem + SM::FR);
+        constexpr int NFR = H * H / 4;                                                  // words per set and lane
+        if (warp == 2) {
+            uint32_t f0[(H / 4) * (H / 2)][2], f1[(H / 4) * (H / 2)][2];
+            load_wfrag<H, false, false>(wsm + H * H, 1.f, lane, f0);                   // Ww                      (f16)
+            load_wfrag<H, true, true>(wsm, 1.f / LOG2E, lane, f1);                     // scale Wl^T: dS = Wl^T dL (bf16)
+#pragma unroll
+            for (int i = 0; i < NFR; ++i) { frs[i * 32 + lane] = f0[i >> 1][i & 1]; frs[(NFR + i) * 32 + lane] = f1[i >> 1][i & 1]; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        auto load_frs = [&](int set, uint32_t (&f)[(H / 4) * (H / 2)][2]) {
+#pragma unroll
+            for (int i = 0; i < NFR; ++i) f[i >> 1][i & 1] = frs[(set * NFR + i) * 32 + lane];
+        };
         float c1[H][2], dl_[H][2];                                                     // query-stationary: per row
         float dsum[H][2];
 #pragma unroll
@@ -986,7 +1010,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_bwd_kernel(const __grid_cons
                 dsum[g][rs] = 0.f;
             }
         for (int jl = 0; jl < nb; ++jl) {
+            if (warp == 2) TF_TRACE(2, jl, 0);
             mbar_wait(sfull, (uint32_t)jl & 1u);
+            if (warp == 2) TF_TRACE(2, jl, 1);
             fence_after();
             float x[H][4], da[H][4];
             ld_tiles<H, CBB>(tT0 + tl + (uint32_t)(cg * 8), x);
@@ -995,6 +1021,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_bwd_kernel(const __grid_cons
             fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(sempty);
+            if (warp == 2) TF_TRACE(2, jl, 2);
             // per-column constants (key-stationary): lse2 and delta of the thread's two query columns
             float cl[H][2], cd[H][2];
             if (KEYST) {
@@ -1010,6 +1037,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_bwd_kernel(const __grid_cons
                     }
             }
             mbar_wait(tempty, ((uint32_t)jl & 1u) ^ 1u);                 // the previous block's tiles have been consumed
+            if (warp == 2) TF_TRACE(2, jl, 3);
             const uint32_t t0 = sbase + SM::T0, t1 = t0 + SM::T_B, t2 = t1 + SM::T_B;
             if (MODE == BW_DQ) st_tiles<H, CBB>(t2, quarter, cg, lane, x);                   // S (bf16) for dWl
             if (MODE == BW_DELTA) st_tiles<H, CBB>(t1, quarter, cg, lane, da);               // dA (bf16) for dWw
@@ -1022,7 +1050,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_bwd_kernel(const __grid_cons
                 for (int i = 0; i < 4; ++i) y[g][i] = ex2(y[g][i]);                      // p' = 2^8 p
             if (MODE == BW_DKV) {
                 uint32_t ww[(H / 4) * (H / 2)][2];
-                load_wfrag<H, false, false>(wsm + H * H, 1.f, lane, ww);
+                load_frs(0, ww);
                 head_mix<H, false>(y, ww, [&](int g, int) { return wsm[2 * H * H + H + g]; }, x);      // A' = Ww p' + 2^8 bw
                 st_tiles<H, CBB>(t1, quarter, cg, lane, x);
             }
@@ -1040,13 +1068,16 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_bwd_kernel(const __grid_cons
                     for (int i = 0; i < 4; ++i) y[g][i] *= x[g][i] - (KEYST ? cd[g][i & 1] : dl_[g][i >> 1]);      // dL' = p' (dP - delta)
                 if (MODE == BW_DQ) st_tiles<H, CBB>(t1, quarter, cg, lane, y);           // dL' (bf16) for dWl
                 uint32_t wlT[(H / 4) * (H / 2)][2];
-                load_wfrag<H, true, true>(wsm, 1.f / LOG2E, lane, wlT);                  // scale Wl^T: dS = Wl^T dL      (bf16)
+                if (MODE == BW_DQ) load_wfrag<H, true, true>(wsm, 1.f / LOG2E, lane, wlT);
+                else load_frs(1, wlT);                                                   // scale Wl^T: dS = Wl^T dL      (bf16)
                 head_mix<H, true>(y, wlT, [](int, int) { return 0.f; }, x);
                 st_tiles<H, CBB>(t0, quarter, cg, lane, x);                               // scale dS' (bf16)
             }
+            if (warp == 2) TF_TRACE(2, jl, 4);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(tfull);
+            if (warp == 2) TF_TRACE(2, jl, 5);
         }
         // ---------------- epilogue ----------------
         const float inv = 1.f / 256.f;
@@ -1103,6 +1134,8 @@ __global__ void tf_pack_dqkv_kernel(const float* __restrict__ src, uint16_t* __r
     *reinterpret_cast<uint2*>(dst + r * dst_ld + which * D + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
 }
 
+int g_bwd_trace_mode = -1;
+
 template <int H, int MODE>
 int launch_bwd_one(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& y1, const CUtensorMap& y2, TfBwdParams p, int nrb, int B, cudaStream_t st,
                    const char* tag, double work) {
@@ -1112,6 +1145,7 @@ int launch_bwd_one(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorM
         SPE_CUDA(cudaFuncSetAttribute(tf_bwd_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::TOTAL));
         attr_done = true;
     }
+    p.trace = (g_bwd_trace_mode == MODE) ? g_tf_trace : nullptr;
     SpeProfScope ps(SPE_FAM_TALKING_BWD, work, st, tag);
     tf_bwd_kernel<H, MODE><<<dim3(nrb, p.nchunk, B), TF_THREADS, SM::TOTAL, st>>>(x1, x2, y1, y2, p);
     SPE_LAUNCHED();
@@ -1142,6 +1176,13 @@ int launch_bwd(const spe_talking_fused_bwd_args* a, cudaStream_t st) {
     p.N = N; p.nblk = nblk; p.nchunk = nc; p.bpc = bpc; p.Npad = nrb * RB;
     p.Wl = a->Wl; p.bl = a->bl; p.Ww = a->Ww; p.bw = a->bw; p.scale = a->scale;
     p.lse2 = a->lse2; p.delta = delta;
+    {
+        static const char* dbg_env = getenv("SPE_TF_DBG");
+        const int dbg = dbg_env ? atoi(dbg_env) : 0;
+        if ((dbg & 1024) && !g_tf_trace) { cudaMalloc(&g_tf_trace, 4 * 32 * 8 * 8); cudaMemset(g_tf_trace, 0, 4 * 32 * 8 * 8); }
+        p.trace = nullptr;
+        g_bwd_trace_mode = (dbg & 1024) ? (dbg >> 12) : -1;
+    }
     const double pos = (double)B * N * N * H;
     p.dwacc = dw; p.out0 = nullptr; p.out1 = nullptr;
     if (launch_bwd_one<H, BW_DELTA>(q64, do64, k16, v16, p, nrb, B, st, "tf_delta", pos * 4.0)) return -1;

@@ -73,4 +73,16 @@ if __name__ == "__main__":
                 f = line.strip().split(",")
                 acc[f[1]].append(float(f[3]))
             print("TIMES", {k: round(1000 * sum(v) / len(v), 1) for k, v in acc.items()}, "us")
+    if int(os.environ.get("SPE_TF_DBG", "0")) & 1024:
+        import numpy as np
+        buf = (C.c_longlong * (4 * 32 * 8))()
+        lib().spe_talking_fused_trace.argtypes = [C.c_void_p]
+        lib().spe_talking_fused_trace(buf)
+        t = np.array(buf[:]).reshape(4, 32, 8)
+        t0 = t[t > 0].min()
+        names = {1: "MMA  [top, yfull, sempty, tiles issued, tfull, acc issued]", 2: "POS  [top, sfull, loaded, tempty, math done, arrived]"}
+        for role in (1, 2):
+            print(names[role])
+            for blk in range(4, 12):
+                print("   blk %2d " % blk, " ".join("%7d" % (v - t0 if v else -1) for v in t[role, blk, :6]))
     print("FAIL" if bad else "OK")
