@@ -79,6 +79,10 @@ class StaticTargets(PackedTargets):
         self._inv_num_boxes = torch.ones(1, dtype=torch.float32, device=device)
         self.img_label = torch.zeros(self.B, img_classes, dtype=torch.float32, device=device) if img_classes else None
         self.sizes, self.total = [0] * self.B, 0
+        # the pinned staging buffers are reused every step: the previous step's non_blocking copies must have been consumed
+        # before the host overwrites them (the host runs ahead of the graph replays)
+        self._staged = torch.cuda.Event() if pin else None
+        self._staged_pending = False
 
     def update(self, targets):
         assert len(targets) == self.B, "StaticTargets: batch size changed"
@@ -86,6 +90,9 @@ class StaticTargets(PackedTargets):
         if max(sizes, default=0) > self.cap:
             raise ValueError("StaticTargets: %d targets in one image exceed the static capacity %d" % (max(sizes), self.cap))
         self.sizes, self.total = sizes, sum(sizes)
+        if self._staged_pending:
+            self._staged.synchronize()
+            self._staged_pending = False
         tot, o = self.total, 0
         for b, n in enumerate(sizes):
             self._h_off[b] = o
@@ -120,6 +127,9 @@ class StaticTargets(PackedTargets):
         else:
             self._h_inv[0] = 1.0 / max(float(self.total), 1.0)
             self._inv_num_boxes.copy_(self._h_inv, non_blocking=True)
+        if self._staged is not None:
+            self._staged.record()
+            self._staged_pending = True
         return self
 
 
@@ -241,6 +251,10 @@ def set_losses(logits, boxes, T, match_weights, alpha, gamma, refine=False, loss
     """One decoder level: match + labels/boxes/cardinality losses; returns dict of 0-dim tensors (+ '_r2g')."""
     if r2g is None:
         r2g = match(logits, boxes, T, match_weights)
+    if refine and T.scores is None and T.total > 0:
+        # the reference indexes t['scores'] unconditionally (conditional_detr.py:523): a refine criterion without pseudo-label
+        # scores is a caller error, not "weight 1"
+        raise KeyError("scores: SetCriterionRefine needs a 'scores' entry in every target")
     res = {"_r2g": r2g}
     if "labels" in losses or "cardinality" in losses:
         f = FocalLossFn.apply(logits.float(), r2g, T, alpha, gamma, refine)

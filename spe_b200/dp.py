@@ -27,9 +27,21 @@ class FlatGradBuffer:
                 p.grad = v
                 p._spe_accum = fused_accumulate     # ops.grad_sink: backward kernels accumulate straight into the slice
 
+    def _repoint(self, fold):
+        """'views' mode: p.grad must BE the flat-buffer slice.  optimizer.zero_grad() (set_to_none=True is torch's default and what
+        the reference loop calls, engine.py:77/161) drops it; with `fold`, gradients that autograd then created free-standing are
+        added back into the slice (otherwise the all-reduce would ship zeros and the ranks would silently stop syncing)."""
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None or g.data_ptr() != v.data_ptr():
+                if fold and g is not None:
+                    v.add_(g.to(v.dtype).view_as(v))
+                p.grad = v
+
     def zero_(self):
         if self.mode == "views":
             self.flat.zero_()
+            self._repoint(fold=False)
         else:
             for p in self.params:
                 p.grad = None
@@ -52,6 +64,8 @@ class FlatGradBuffer:
 
     def all_reduce_mean(self):
         """grad <- mean over ranks (what DDP does, main.py:171-173).  No-op when not distributed."""
+        if self.mode == "views":
+            self._repoint(fold=True)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self.gather()
             if self.flat.is_cuda:

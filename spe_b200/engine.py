@@ -65,8 +65,11 @@ class TrainStep:
         if targets_refine is None:
             targets_refine = targets
         if not self.graph or not torch.is_tensor(samples):
-            tg = self.criterion.prepare_targets(targets)
-            tr = self.criterion_refine.prepare_targets(targets_refine) if self.criterion_refine is not None else None
+            # jitter / repeat ONCE (conditional_detr.py:410-431), then pack: criterion.forward prepares plain lists itself and
+            # would expand them a second time (every GT 25x instead of 5x with match_ratio 5)
+            dev = next(self.model.parameters()).device
+            tg = CO.pack_targets(self.criterion.prepare_targets(targets), dev)
+            tr = CO.pack_targets(self.criterion_refine.prepare_targets(targets_refine), dev) if self.criterion_refine is not None else None
             res = self._body(samples, tg, tr)
         else:
             res = self._replay(samples, targets, targets_refine)

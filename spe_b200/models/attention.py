@@ -11,8 +11,7 @@ from .. import ops
 class MultiheadAttention(nn.Module):
     def __init__(self, embed_dim, num_heads, dropout=0.0, bias=True, add_bias_kv=False, add_zero_attn=False, kdim=None, vdim=None):
         super().__init__()
-        if dropout:
-            raise NotImplementedError("spe_b200: attention dropout is not implemented (SURVEY.md H6)")
+        self.dropout = float(dropout)             # on the attention probabilities, training only (attention.py:371)
         assert not add_bias_kv and not add_zero_attn
         self.embed_dim = embed_dim
         self.vdim = vdim if vdim is not None else embed_dim
@@ -24,7 +23,8 @@ class MultiheadAttention(nn.Module):
 
     def core(self, q16, k16, v16, mask_u8=None, q2=None, k2=None):
         """batch-first bf16 [B,L,E] operands -> bf16 [B,L,vdim] (before out_proj)."""
-        return ops.attention(q16, k16, v16, self.num_heads, float(self.head_dim) ** -0.5, mask_u8=mask_u8, q2=q2, k2=k2)
+        return ops.attention(q16, k16, v16, self.num_heads, float(self.head_dim) ** -0.5, mask_u8=mask_u8, q2=q2, k2=k2,
+                             drop_p=self.dropout if self.training else 0.0)
 
     def forward(self, query, key, value, key_padding_mask=None, need_weights=False, attn_mask=None):
         assert attn_mask is None, "attn_mask is never used on this path"

@@ -5,7 +5,8 @@ Same class names, constructor arguments and state_dict keys as the reference (SU
   LayerScale_Block_CA_MultiClass (:311-328), PatchEmbedMine (:518-528), TSCAM_cait (:531-670),
   TSCAM_cait_two_branch (:674-831, the backbone the reference's launch scripts train).
 Internally activations are token-major: fp32 residual stream [B,N,D], bf16 GEMM operands.
-Dropout / DropPath / attention dropout are p=0 only (BASELINE configs): a non-zero rate raises.
+Dropout / DropPath / attention dropout (scripts/run_coco17.py:30-32) are honoured in train() mode through un-fused routes
+(ops.dropout / ops.drop_path / attention-probability dropout); p = 0 and eval() keep the fused epilogues (BASELINE configs).
 """
 from functools import partial
 
@@ -31,7 +32,7 @@ class Mlp(nn.Module):
 
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
         super().__init__()
-        _no_drop(mlp_drop=drop)
+        self.drop = float(drop)
         hidden_features = hidden_features or in_features
         out_features = out_features or in_features
         self.fc1 = nn.Linear(in_features, hidden_features)
@@ -53,7 +54,7 @@ class PatchEmbedMine(nn.Module):
 class Attention_talking_head(nn.Module):
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0.0, proj_drop=0.0):
         super().__init__()
-        _no_drop(attn_drop=attn_drop, proj_drop=proj_drop)
+        self.attn_drop, self.proj_drop = float(attn_drop), float(proj_drop)
         assert qk_scale is None
         self.num_heads = num_heads
         self.scale = (dim // num_heads) ** -0.5
@@ -69,14 +70,15 @@ class Attention_talking_head(nn.Module):
     def core(self, y16):
         """LN output bf16 [B,N,D] -> attention output bf16 [B,N,D] (before proj)."""
         qkv = ops.linear(y16, self.qkv.weight, self.qkv.bias)
-        return ops.talking_heads_attention(qkv, self.proj_l.weight, self.proj_l.bias, self.proj_w.weight, self.proj_w.bias, self.num_heads)
+        return ops.talking_heads_attention(qkv, self.proj_l.weight, self.proj_l.bias, self.proj_w.weight, self.proj_w.bias, self.num_heads,
+                                           drop_p=self.attn_drop if self.training else 0.0)
 
 
 class LayerScale_Block(nn.Module):
     def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, qk_scale=None, drop=0.0, attn_drop=0.0, drop_path=0.0,
                  act_layer=nn.GELU, norm_layer=nn.LayerNorm, Attention_block=Attention_talking_head, Mlp_block=Mlp, init_values=1e-4):
         super().__init__()
-        _no_drop(drop=drop, drop_path=drop_path)
+        self.drop, self.drop_path = float(drop), float(drop_path)
         self.norm1 = norm_layer(dim)
         self.attn = Attention_block(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
         self.norm2 = norm_layer(dim)
@@ -89,6 +91,14 @@ class LayerScale_Block(nn.Module):
         # layernorm_res hands x through so its residual-path gradient is added inside the LayerNorm backward kernel
         y, xr = ops.layernorm_res(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         o = self.attn.core(y)
+        if self.training and (self.drop > 0.0 or self.drop_path > 0.0):
+            # x + drop_path(gamma_1 * proj_drop(proj(o))) ; x + drop_path(gamma_2 * drop(fc2(drop(gelu(fc1(LN x))))))   (cait.py:391,414-415)
+            z = ops.dropout(ops.linear(o, self.attn.proj.weight, self.attn.proj.bias, out_f32=True), self.drop)
+            x = xr + ops.drop_path(self.gamma_1 * z, self.drop_path)
+            y, xr = ops.layernorm_res(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+            h = ops.dropout(torch.nn.functional.gelu(ops.linear(y, self.mlp.fc1.weight, self.mlp.fc1.bias)), self.drop)
+            z = ops.dropout(ops.linear(h, self.mlp.fc2.weight, self.mlp.fc2.bias, out_f32=True), self.drop)
+            return xr + ops.drop_path(self.gamma_2 * z, self.drop_path)
         x = ops.linear(o, self.attn.proj.weight, self.attn.proj.bias, residual=xr, gamma=self.gamma_1)
         y, xr = ops.layernorm_res(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         return ops.ffn(y, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, residual=xr, gamma=self.gamma_2, act="gelu")
@@ -161,7 +171,7 @@ class TSCAM_cait(nn.Module):
                  Attention_block_token_only=Multi_Class_Attention, Mlp_block_token_only=Mlp, depth_token_only=2, mlp_ratio_clstk=4.0,
                  layer_to_det=23):
         super().__init__()
-        _no_drop(drop_rate=drop_rate, drop_path_rate=drop_path_rate, attn_drop_rate=attn_drop_rate)
+        self.drop_rate = float(drop_rate)                      # pos_drop (cait.py:449,625)
         self.num_classes = num_classes
         self.num_features = self.embed_dim = embed_dim
         self.patch_embed = Patch_layer(img_size=img_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim)
@@ -224,6 +234,7 @@ class TSCAM_cait(nn.Module):
         ph, pw = self.img_size[0] // p, self.img_size[1] // p
         pos = ops.BicubicTokensFn.apply(self.pos_embed, ph, pw, h, w)                                   # cait.py:588-600,623
         x = ops.PatchEmbedFn.apply(x_img.float(), self.patch_embed.proj.weight, self.patch_embed.proj.bias, pos, p)   # :618,624
+        x = ops.dropout(x, self.drop_rate, self.training)                                                # pos_drop (:625)
         x_feat = None
         for i, blk in enumerate(self.blocks):                                                            # :627-630
             x = blk(x)
@@ -287,6 +298,7 @@ class TSCAM_cait_two_branch(TSCAM_cait):
         ph, pw = self.img_size[0] // p, self.img_size[1] // p
         pos = ops.BicubicTokensFn.apply(self.pos_embed, ph, pw, h, w)                                   # cait.py:731-745, :767
         x = ops.PatchEmbedFn.apply(x_img.float(), self.patch_embed.proj.weight, self.patch_embed.proj.bias, pos, p)
+        x = ops.dropout(x, self.drop_rate, self.training)                                                # pos_drop (:771)
         x_feat = None
         for i, blk in enumerate(self.blocks):                                                            # :773-777
             x = blk(x)

@@ -6,7 +6,7 @@ TransformerDecoderLayer (:313-466), build_transformer (:473-484).
 
 Internal layout is batch-first token-major ([B,N,D]; the reference is sequence-first [N,B,D]): fp32 residual
 streams + bf16 GEMM operands.  Only what the reference actually runs is implemented: post-norm layers, ReLU
-FFN, dropout 0, return_intermediate decoder.  Work the reference repeats is done once:
+FFN, return_intermediate decoder; dropout (main.py:73) in train() mode through un-fused routes (ops.dropout), fused epilogues otherwise.  Work the reference repeats is done once:
   * query_pos-only projections are batch invariant -> computed on [Q,D] and broadcast in the GEMM epilogue;
   * the decoder passes of forward_refine (transformer.py:147-155: same weights, same memory, different query embeddings) run as
     ONE pass over the concatenated queries [B, P*Q, D]: every token-wise GEMM / LayerNorm and the cross-attention see P*Q
@@ -58,8 +58,7 @@ class _PackedSelfAttention(nn.Module):
 
     def __init__(self, embed_dim, num_heads, dropout=0.0):
         super().__init__()
-        if dropout:
-            raise NotImplementedError("spe_b200: attention dropout is not implemented (SURVEY.md H6)")
+        self.dropout = float(dropout)             # nn.MultiheadAttention(dropout=...): on the attention probabilities, training only
         self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
         self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
         self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
@@ -68,17 +67,27 @@ class _PackedSelfAttention(nn.Module):
         nn.init.constant_(self.out_proj.bias, 0.0)
 
 
-def _no_dropout(p):
-    if p:
-        raise NotImplementedError("spe_b200: dropout is not implemented; construct with dropout=0 (SURVEY.md H6)")
+def _res_ffn(layer, s32, s16, p, training):
+    """x + dropout(linear2(dropout(relu(linear1(x)))))   (transformer.py:285-286, :424-425)"""
+    if training and p > 0.0:
+        h = ops.dropout(ops.linear(s16, layer.linear1.weight, layer.linear1.bias, act="relu"), p)
+        return s32 + ops.dropout(ops.linear(h, layer.linear2.weight, layer.linear2.bias, out_f32=True), p)
+    return ops.ffn(s16, layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias, residual=s32, act="relu")
+
+
+def _res_proj(a16, proj, res32, p, training):
+    """res + dropout(out_proj(a))   (transformer.py:283, :384, :421)"""
+    if training and p > 0.0:
+        return res32 + ops.dropout(ops.linear(a16, proj.weight, proj.bias, out_f32=True), p)
+    return ops.linear(a16, proj.weight, proj.bias, residual=res32, out_f32=True)
 
 
 class TransformerEncoderLayer(nn.Module):
     def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False):
         super().__init__()
-        _no_dropout(dropout)
+        self.dropout = float(dropout)
         assert activation == "relu" and not normalize_before, "the reference runs post-norm ReLU layers only"
-        self.self_attn = _PackedSelfAttention(d_model, nhead)
+        self.self_attn = _PackedSelfAttention(d_model, nhead, dropout=dropout)
         self.linear1 = nn.Linear(d_model, dim_feedforward)
         self.linear2 = nn.Linear(dim_feedforward, d_model)
         self.norm1 = nn.LayerNorm(d_model)
@@ -92,10 +101,11 @@ class TransformerEncoderLayer(nn.Module):
         qk_in = ops.add_cast(src32, pos32)                                         # with_pos_embed
         qk = ops.linear(qk_in, sa.in_proj_weight[:2 * D], sa.in_proj_bias[:2 * D])   # q | k in one GEMM
         v = ops.linear(src16, sa.in_proj_weight[2 * D:], sa.in_proj_bias[2 * D:])
-        a = ops.attention(qk[:, :, :D], qk[:, :, D:], v, sa.num_heads, float(sa.head_dim) ** -0.5, mask_u8=mask_u8)
-        x = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias, residual=src32, out_f32=True)
+        a = ops.attention(qk[:, :, :D], qk[:, :, D:], v, sa.num_heads, float(sa.head_dim) ** -0.5, mask_u8=mask_u8,
+                          drop_p=sa.dropout if self.training else 0.0)
+        x = _res_proj(a, sa.out_proj, src32, self.dropout, self.training)
         s32, s16 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, want_f32=True)
-        x = ops.ffn(s16, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias, residual=s32, act="relu")
+        x = _res_ffn(self, s32, s16, self.dropout, self.training)
         return ops.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, want_f32=True)
 
 
@@ -116,7 +126,7 @@ class TransformerEncoder(nn.Module):
 class TransformerDecoderLayer(nn.Module):
     def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False):
         super().__init__()
-        _no_dropout(dropout)
+        self.dropout = float(dropout)
         assert activation == "relu" and not normalize_before
         for n in ("sa_qcontent_proj", "sa_qpos_proj", "sa_kcontent_proj", "sa_kpos_proj", "sa_v_proj"):
             setattr(self, n, nn.Linear(d_model, d_model))
@@ -161,7 +171,7 @@ class TransformerDecoderLayer(nn.Module):
             a = self.self_attn.core(q.view(B * passes, Q, D), k.view(B * passes, Q, D), v.view(B * passes, Q, D)).view(B, PQ, D)
         else:
             a = self.self_attn.core(q, k, v)
-        x = lin(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, residual=tgt32, out_f32=True)
+        x = _res_proj(a, self.self_attn.out_proj, tgt32, self.dropout, self.training)
         t32, t16 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, want_f32=True)
         # ---- conditional cross-attention (:389-423)
         kc, vv, kpos16 = mem_side
@@ -172,9 +182,9 @@ class TransformerDecoderLayer(nn.Module):
             qc = lin(t16, self.ca_qcontent_proj.weight, self.ca_qcontent_proj.bias)
         qs = lin(qsine16, self.ca_qpos_sine_proj.weight, self.ca_qpos_sine_proj.bias)
         a = self.cross_attn.core(qc, kc, vv, mask_u8=mask_u8, q2=qs, k2=kpos16)       # scale = (2*dh)^-1/2 via embed_dim = 2*d_model
-        x = lin(a, self.cross_attn.out_proj.weight, self.cross_attn.out_proj.bias, residual=t32, out_f32=True)
+        x = _res_proj(a, self.cross_attn.out_proj, t32, self.dropout, self.training)
         t32, t16 = ops.layernorm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, want_f32=True)
-        x = ops.ffn(t16, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias, residual=t32, act="relu")
+        x = _res_ffn(self, t32, t16, self.dropout, self.training)
         return ops.layernorm(x, self.norm3.weight, self.norm3.bias, self.norm3.eps, want_f32=True)
 
 

@@ -584,6 +584,38 @@ def cast_f32(a):
     return CastF32Fn.apply(a)
 
 
+# ---- dropout (cait.py:36-38,294,449; transformer.py:268-270,333-337; attention.py:371) -----------------------------------------
+# The BASELINE configurations run p = 0; the reference's training scripts do not (scripts/run_coco17.py:30-32: backbone_drop_rate
+# 0.07, drop_path_rate 0.2, drop_attn_rate 0.05; main.py:73: decoder dropout 0.1).  With a non-zero rate in train() mode the modules
+# take un-fused routes (GEMM -> dropout -> residual) built from the same kernels; the masks come from torch's Philox generator
+# (elementwise glue, reproducible with torch.manual_seed, capturable in CUDA graphs).  Eval mode and p = 0 keep the fused epilogues.
+def dropout(x, p, training=True):
+    if not training or p <= 0.0:
+        return x
+    return torch.nn.functional.dropout(x, p, True)
+
+
+def drop_path(x, p, training=True):
+    """timm DropPath (stochastic depth per sample): x [B, ...] * bernoulli(1 - p) / (1 - p)."""
+    if not training or p <= 0.0:
+        return x
+    keep = 1.0 - p
+    m = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+    return x * (m / keep)
+
+
+def _drop_mask(shape, p, device):
+    """boolean keep-mask of an attention-probability tensor (True = kept), drawn from torch's CUDA generator"""
+    return torch.rand(shape, dtype=torch.float32, device=device) >= p
+
+
+def _apply_drop_(t16, keep, p):
+    """in place on a bf16 [B,H,Lq,ld] tensor: t * keep / (1 - p)   (the scalar multiply runs in fp32 op-math)"""
+    t16.mul_(1.0 / (1.0 - p))
+    t16.masked_fill_(~keep, 0.0)
+    return t16
+
+
 # ---- attention ---------------------------------------------------------------------------------
 def _qk_logits(q, k, H, alpha, S, ldS, q2=None, k2=None):
     """S[b,h] = alpha * (q_h k_h^T [+ q2_h k2_h^T])   q [B,Lq,H*d] (row stride free), S f32 [B,H,Lq,ldS]."""
@@ -695,12 +727,13 @@ class AttentionFn(torch.autograd.Function):
     Optionally returns the head-mean attention map (cait.py:658-667)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, q2, k2, mask_u8, H, scale, want_mean):
+    def forward(ctx, q, k, v, q2, k2, mask_u8, H, scale, want_mean, drop_p=0.0):
         _need_cuda(q, k, v)
         B, Lq, _ = q.shape
         Lk = k.shape[1]
         ld = rup(Lk, 8)
-        if not want_mean and _fused_attention_ok(q, k, v, q2, k2, H):
+        ctx.drop_p = float(drop_p)
+        if not want_mean and drop_p <= 0.0 and _fused_attention_ok(q, k, v, q2, k2, H):
             # fused forward (attn_fused.cu): logits stay in TMEM.  With the recomputing backward only the row statistics are kept
             # (nothing N^2 reaches HBM in either direction); SPE_ATTN_BWD=gemm keeps P (bf16) for the GEMM-based backward.
             out = torch.empty((B, Lq, v.shape[2]), dtype=torch.bfloat16, device=q.device)
@@ -726,8 +759,15 @@ class AttentionFn(torch.autograd.Function):
         check(lib().spe_softmax_fwd(ptr(S), ptr(P), ptr(mask_u8), B, H, Lq, Lk, ld, ld, ptr(pmean), stream()))
         del S
         out = torch.empty((B, Lq, v.shape[2]), dtype=torch.bfloat16, device=q.device)
-        _pv(P, v, H, out, Lq, Lk, ld)
-        ctx.save_for_backward(q, k, v, q2, k2, P, out)
+        if drop_p > 0.0:
+            # attention dropout (attention.py:371 / nn.MultiheadAttention): P V runs on the dropped probabilities; the softmax
+            # backward needs the clean ones, so both P and the keep-mask are saved
+            keep = _drop_mask(P.shape, drop_p, q.device)
+            _pv(_apply_drop_(P.clone(), keep, drop_p), v, H, out, Lq, Lk, ld)
+            ctx.save_for_backward(q, k, v, q2, k2, P, out, keep)
+        else:
+            _pv(P, v, H, out, Lq, Lk, ld)
+            ctx.save_for_backward(q, k, v, q2, k2, P, out)
         ctx.H, ctx.scale, ctx.ld = H, scale, ld
         if want_probs:
             Pv = P.detach()
@@ -741,7 +781,21 @@ class AttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dO, *unused):
         if ctx.recompute:
-            return AttentionFn._backward_recompute(ctx, dO)
+            return AttentionFn._backward_recompute(ctx, dO) + (None,)
+        if ctx.drop_p > 0.0:
+            q, k, v, q2, k2, P, out, keep = ctx.saved_tensors
+            H, scale, ld = ctx.H, ctx.scale, ctx.ld
+            B, Lq, _ = q.shape
+            Lk = k.shape[1]
+            dO = dO.contiguous()
+            dP, dV = _attn_bwd_common(dO, _apply_drop_(P.clone(), keep, ctx.drop_p), v, H, Lq, Lk, ld)
+            _apply_drop_(dP, keep, ctx.drop_p)                  # d(dropout): the same mask and scale
+            check(lib().spe_softmax_bwd(ptr(P), ptr(dP), ptr(dP), B, H, Lq, Lk, ld, stream()))
+            dq, dk = _dq_dk(dP, q, k, H, scale, Lq, Lk, ld)
+            dq2 = dk2 = None
+            if q2 is not None:
+                dq2, dk2 = _dq_dk(dP, q2, k2, H, scale, Lq, Lk, ld)
+            return dq, dk, dV, dq2, dk2, None, None, None, None, None
         q, k, v, q2, k2, P, out = ctx.saved_tensors
         H, scale, ld = ctx.H, ctx.scale, ctx.ld
         B, Lq, _ = q.shape
@@ -762,14 +816,14 @@ class AttentionFn(torch.autograd.Function):
             if q2 is not None:
                 dq2, dk2 = torch.empty_like(q2, memory_format=torch.contiguous_format), torch.empty_like(k2, memory_format=torch.contiguous_format)
                 fused_attention_bwd_gemms(dP, P, q2, k2, None, H, scale, dq2, dk2, None, delta=delta)
-            return dq, dk, dV, dq2, dk2, None, None, None, None
+            return dq, dk, dV, dq2, dk2, None, None, None, None, None
         dP, dV = _attn_bwd_common(dO, P, v, H, Lq, Lk, ld)
         check(lib().spe_softmax_bwd(ptr(P), ptr(dP), ptr(dP), B, H, Lq, Lk, ld, stream()))
         dq, dk = _dq_dk(dP, q, k, H, scale, Lq, Lk, ld)
         dq2 = dk2 = None
         if q2 is not None:
             dq2, dk2 = _dq_dk(dP, q2, k2, H, scale, Lq, Lk, ld)
-        return dq, dk, dV, dq2, dk2, None, None, None, None
+        return dq, dk, dV, dq2, dk2, None, None, None, None, None
 
 
 def _attention_backward_recompute(ctx, dO):
@@ -808,9 +862,10 @@ def _recompute_bwd():
     return _RECOMPUTE
 
 
-def attention(q, k, v, H, scale, mask_u8=None, q2=None, k2=None, want_mean=False):
-    """want_mean: False | True (also return the head-mean map f32 [B,Lq,Lk]) | "probs" (also return P bf16 [B,H,Lq,ld])."""
-    return AttentionFn.apply(q, k, v, q2, k2, mask_u8, H, scale, want_mean)
+def attention(q, k, v, H, scale, mask_u8=None, q2=None, k2=None, want_mean=False, drop_p=0.0):
+    """want_mean: False | True (also return the head-mean map f32 [B,Lq,Lk]) | "probs" (also return P bf16 [B,H,Lq,ld]).
+    drop_p > 0: dropout on the attention probabilities (training), un-fused route."""
+    return AttentionFn.apply(q, k, v, q2, k2, mask_u8, H, scale, want_mean, float(drop_p))
 
 
 def cam_std_reweight(P, q0, C, k0, N):
@@ -822,9 +877,42 @@ def cam_std_reweight(P, q0, C, k0, N):
     return out
 
 
-class TalkingHeadsAttentionFn(torch.autograd.Function):
-    """Attention_talking_head core (cait.py:377-389) on a packed qkv [B,N,3D] bf16:
-    S = scale q k^T -> proj_l over heads -> softmax -> proj_w over heads -> @ v."""
+_TH_FUSED = None
+
+
+def _talking_fused_mode():
+    """SPE_TH_FUSED selects the talking-heads implementation where the head geometry is supported by csrc/talking_fused.cu:
+      1    fused kernels in both directions: no [B,H,N,N] tensor in HBM (saved activations of a block: qkv + lse2 instead of
+           S f32 + A bf16: ~0.98 GB -> ~30 MB per block at cfg2), DRAM traffic ~4.4 GB -> ~0.2 GB per layer;
+      0    the unfused GEMM -> talking-softmax -> GEMM pipeline;
+      auto (default) fused forward when no gradient is required (inference: 6.7 vs 11.4 ms per cfg2 step), unfused for
+           training -- measured on B200 the three recomputing backward kernels are tensor-pipe bound (64-row x 16-column
+           tcgen05.mma re-read their A operand from shared memory per instruction) and a fused training step takes 58.7 ms
+           against 51.4 ms."""
+    global _TH_FUSED
+    if _TH_FUSED is None:
+        import os
+        _TH_FUSED = os.environ.get("SPE_TH_FUSED", "auto")
+    return _TH_FUSED
+
+
+def _talking_fused_ok(qkv, H, needs_grad):
+    mode = _talking_fused_mode()
+    if mode == "0" or (mode != "1" and needs_grad):
+        return False
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    return (D % H == 0 and lib().spe_talking_fused_supported(H, D // H) == 1 and qkv.stride(2) == 1
+            and qkv.stride(1) % 8 == 0 and qkv.stride(0) % 8 == 0 and qkv.data_ptr() % 16 == 0 and D % 8 == 0)
+
+
+def _fp32c(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+class TalkingHeadsFusedFn(torch.autograd.Function):
+    """Attention_talking_head core (cait.py:377-389), fused: logits in TMEM, head mixes on mma.sync, nothing of size N^2 in HBM.
+    Saves qkv, the output-independent log2 normalisers lse2 [B,H,N] and the four small parameters; the backward recomputes."""
 
     @staticmethod
     def forward(ctx, qkv, Wl, bl, Ww, bw, H):
@@ -833,22 +921,93 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         D = D3 // 3
         dh = D // H
         q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+        Wl32, bl32, Ww32, bw32 = _fp32c(Wl), _fp32c(bl), _fp32c(Ww), _fp32c(bw)
+        out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
+        lse2 = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+        ws = torch.empty(int(lib().spe_talking_fused_fwd_workspace(B, H, N, dh)), dtype=torch.uint8, device=qkv.device)
+        a = _lib.TalkingFusedArgs(B, H, N, dh, q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                                  v.data_ptr(), v.stride(1), v.stride(0), Wl32.data_ptr(), bl32.data_ptr(), Ww32.data_ptr(), bw32.data_ptr(),
+                                  dh ** -0.5, out.data_ptr(), out.stride(1), out.stride(0), lse2.data_ptr(), ws.data_ptr(), ws.numel())
+        check(lib().spe_talking_fused_fwd(C.byref(a), stream()))
+        ctx.save_for_backward(qkv, lse2, Wl, bl, Ww, bw)
+        ctx.H = H
+        return out
+
+    @staticmethod
+    def backward(ctx, dO):
+        qkv, lse2, Wl, bl, Ww, bw = ctx.saved_tensors
+        H = ctx.H
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        dh = D // H
+        q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+        dO = dO.contiguous()
+        if dO.dtype != torch.bfloat16:
+            dO = dO.to(torch.bfloat16)
+        dev = qkv.device
+
+        # exact bias gradient: dbw[g] = sum_b colsum_i(dO[b,:,g]) . colsum_j(V[b,:,g]);  dbl = 0 (softmax is shift invariant)
+        def _dbw():
+            cs = torch.zeros((2, B, D), dtype=torch.float32, device=dev)
+            check(lib().spe_colsum_bf16_batched(ptr(dO), B, N, D, dO.stride(1), dO.stride(0), ptr(cs[0]), stream()))
+            check(lib().spe_colsum_bf16_batched(ptr(v), B, N, D, v.stride(1), v.stride(0), ptr(cs[1]), stream()))
+            return (cs[0] * cs[1]).view(B, H, dh).sum((0, 2))
+
+        ss = None
+        if _overlap_wgrad():
+            with _SideStream() as ss:
+                dbw = _dbw()
+        Wl32, bl32, Ww32, bw32 = _fp32c(Wl), _fp32c(bl), _fp32c(Ww), _fp32c(bw)
+        dqkv = torch.empty((B, N, D3), dtype=torch.bfloat16, device=dev)
+        dWl_b, dWl = _grad_out(Wl, Wl.shape, dev)
+        dWw_b, dWw = _grad_out(Ww, Ww.shape, dev)
+        ws = torch.empty(int(lib().spe_talking_fused_bwd_workspace(B, H, N, dh)), dtype=torch.uint8, device=dev)
+        a = _lib.TalkingFusedBwdArgs(B, H, N, dh, q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                                     v.data_ptr(), v.stride(1), v.stride(0), dO.data_ptr(), dO.stride(1), dO.stride(0),
+                                     Wl32.data_ptr(), bl32.data_ptr(), Ww32.data_ptr(), bw32.data_ptr(), dh ** -0.5, lse2.data_ptr(),
+                                     dqkv.data_ptr(), dqkv.stride(1), dWl_b.data_ptr(), dWw_b.data_ptr(), ws.data_ptr(), ws.numel())
+        check(lib().spe_talking_fused_bwd(C.byref(a), stream()))
+        if ss is not None:
+            ss.join(dbw)
+        else:
+            dbw = _dbw()
+        dbl = None if grad_sink(bl) is not None else torch.zeros_like(bl)
+        return dqkv, dWl, dbl, dWw, dbw, None
+
+
+class TalkingHeadsAttentionFn(torch.autograd.Function):
+    """Attention_talking_head core (cait.py:377-389) on a packed qkv [B,N,3D] bf16:
+    S = scale q k^T -> proj_l over heads -> softmax -> proj_w over heads -> @ v.
+    Unfused pipeline (batched GEMMs around the row-staged talking-softmax kernels): head geometries the fused kernels do not take."""
+
+    @staticmethod
+    def forward(ctx, qkv, Wl, bl, Ww, bw, H, drop_p=0.0):
+        _need_cuda(qkv, Wl)
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        dh = D // H
+        q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
         ld = rup(N, 8)
         scale = dh ** -0.5
+        ctx.drop_p = float(drop_p)
         S = torch.empty((B, H, N, ld), dtype=torch.float32, device=qkv.device)
         _qk_logits(q, k, H, scale, S, ld)
         A = torch.empty((B, H, N, ld), dtype=torch.bfloat16, device=qkv.device)
         stats = torch.empty((B * N, H), dtype=torch.float32, device=qkv.device)
         check(lib().spe_talking_softmax_fwd(ptr(S), ptr(A), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, stream()))
         out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
+        keep = None
+        if drop_p > 0.0:                   # attn_drop on the post-mix probabilities (cait.py:387): A is saved dropped, + the mask
+            keep = _drop_mask(A.shape, drop_p, qkv.device)
+            _apply_drop_(A, keep, drop_p)
         _pv(A, v, H, out, N, N, ld)
-        ctx.save_for_backward(qkv, S, A, Wl, bl, Ww, bw, stats)
+        ctx.save_for_backward(qkv, S, A, Wl, bl, Ww, bw, stats, keep)
         ctx.H, ctx.ld = H, ld
         return out
 
     @staticmethod
     def backward(ctx, dO):
-        qkv, S, A, Wl, bl, Ww, bw, stats = ctx.saved_tensors
+        qkv, S, A, Wl, bl, Ww, bw, stats, keep = ctx.saved_tensors
         H, ld = ctx.H, ctx.ld
         B, N, D3 = qkv.shape
         D = D3 // 3
@@ -879,6 +1038,10 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         if not fused:
             gemm(A, dO, dv, N, dh, N, a_major=MAJOR_MN, lda=ld, a_sb=(H * N * ld, N * ld), b_major=MAJOR_MN, ldb=dO.stride(1), b_sb=(dO.stride(0), dh),
                  ldc=dv.stride(1), c_sb=(dv.stride(0), dh), batch=(B, H))
+        dbw_drop = None
+        if keep is not None:               # d(dropout): dA * keep / (1 - p); dV above used the dropped A, as the forward did
+            _apply_drop_(dA, keep, ctx.drop_p)
+            dbw_drop = dA.sum((0, 2, 3), dtype=torch.float32)      # the bias reaches only the kept positions
         dWl_b, dWl = _grad_out(Wl, Wl.shape, qkv.device)
         dWw_b, dWw = _grad_out(Ww, Ww.shape, qkv.device)
         junk = torch.zeros((2, H), dtype=torch.float32, device=qkv.device)      # the kernel's own bias sums (not used, see below)
@@ -894,12 +1057,18 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
             ss.join(dbw)
         else:
             dbw = _dbw()
+        if dbw_drop is not None:
+            dbw = dbw_drop
         dbl = None if grad_sink(bl) is not None else torch.zeros_like(bl)
-        return dqkv, dWl, dbl, dWw, dbw, None
+        return dqkv, dWl, dbl, dWw, dbw, None, None
 
 
-def talking_heads_attention(qkv, Wl, bl, Ww, bw, H):
-    return TalkingHeadsAttentionFn.apply(qkv, Wl, bl, Ww, bw, H)
+def talking_heads_attention(qkv, Wl, bl, Ww, bw, H, drop_p=0.0):
+    """drop_p > 0 (training): attn_drop on the post-mix probabilities (cait.py:387) -- un-fused route."""
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (qkv, Wl, bl, Ww, bw))
+    if drop_p <= 0.0 and _talking_fused_ok(qkv, H, needs_grad):
+        return TalkingHeadsFusedFn.apply(qkv, Wl, bl, Ww, bw, H)
+    return TalkingHeadsAttentionFn.apply(qkv, Wl, bl, Ww, bw, H, float(drop_p))
 
 
 # ---- patch embedding / position encodings ---------------------------------------------------------

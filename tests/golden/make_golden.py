@@ -87,6 +87,9 @@ def lsap_vectors():
 
 if __name__ == "__main__":
     assert ref_shim.available(), "needs /root/reference"
+    if "--only-cfg2" in sys.argv:
+        run_case("cfg2_s24_640", O.CFG2, 1, 640, 640, 0, ("labels", "boxes", "cardinality"), 2.0, repeat=5, max_gt=6)
+        sys.exit(0)
     tiny = O.tiny_config()
     run_case("tiny_det", tiny, 2, 48, 64, 0, ("labels", "boxes", "cardinality"), 2.0, repeat=2)
     run_case("tiny_refine", tiny, 2, 48, 64, 1, ("labels", "boxes", "cardinality"), 0.5, repeat=1, refine_idx=1)
@@ -97,4 +100,8 @@ if __name__ == "__main__":
     run_case("tiny_h16", O.tiny_config(embed_dim=768, num_heads=16, pos_grid=(4, 5)), 2, 48, 64, 4,
              ("labels", "boxes", "cardinality"), 2.0, repeat=1)
     run_case("cfg1_xxs24_224", O.CFG1, 1, 224, 224, 0, ("labels", "boxes", "cardinality"), 2.0, repeat=1, max_gt=2)
+    # BASELINE configs[1], the benchmarked configuration (TSCAM-S24, 300 queries, 81 logits, 3x640x640), batch 1: the backbone
+    # attention runs at its real shape (H = 8, N = 1600) -- ~1 min of CPU for the reference's forward + backward
+    if "--no-cfg2" not in sys.argv:
+        run_case("cfg2_s24_640", O.CFG2, 1, 640, 640, 0, ("labels", "boxes", "cardinality"), 2.0, repeat=5, max_gt=6)
     lsap_vectors()

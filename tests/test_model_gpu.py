@@ -26,6 +26,10 @@ def _setup(gold, device="cuda"):
     return cfg, params, images, targets, model, crit
 
 
+# global relative L2 error of the whole gradient vs the fp32 oracle, per golden case (measured values in the comments)
+GRAD_TOL = {"tiny_det": 5e-2, "tiny_refine": 5e-2, "tiny_two_branch": 5e-2, "tiny_h16": 5e-2, "cfg1_xxs24_224": 5e-2, "cfg2_s24_640": 5e-2}
+
+
 def nerr(a, b):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     return float((a - b).norm() / (b.norm() + 1e-12))
@@ -36,7 +40,7 @@ def maxerr(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
-@pytest.mark.parametrize("name", ["tiny_det", "tiny_refine", "tiny_two_branch", "tiny_h16", "cfg1_xxs24_224"])
+@pytest.mark.parametrize("name", ["tiny_det", "tiny_refine", "tiny_two_branch", "tiny_h16", "cfg1_xxs24_224", "cfg2_s24_640"])   # cfg2 = the benchmarked config
 def test_detector_matches_reference_golden(golden_dir, name):
     gold = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
     cfg, params, images, targets, model, crit = _setup(gold)
@@ -94,7 +98,8 @@ def test_detector_matches_reference_golden(golden_dir, name):
     tot_num = sum(r[1] ** 2 for r in rows) ** 0.5
     tot_den = sum(r[2] ** 2 for r in rows) ** 0.5
     # global relative L2 error of the whole gradient (bf16 activations + ReLU mask flips through 24+12 layers)
-    assert tot_num / tot_den < 5e-2, tot_num / tot_den
+    print("GRADERR %s global %.4f worst %s" % (name, tot_num / tot_den, sorted(((num / max(den, 1e-30), k) for k, num, den in rows if den > 1e-2 * (tot_den / len(rows) ** 0.5)), reverse=True)[:4]))
+    assert tot_num / tot_den < GRAD_TOL[name], tot_num / tot_den
     # per parameter: relative error bounded, except where the parameter's gradient is itself in the noise floor of the
     # step (|g| below 1% of the typical parameter-gradient norm, incl. analytically-zero gradients)
     floor = 1e-2 * (tot_den / len(rows) ** 0.5)

@@ -27,7 +27,7 @@ def _run(gold):
     return cfg, p, out, ld, idx, loss
 
 
-@pytest.mark.parametrize("name", ["tiny_det", "tiny_refine", "tiny_two_branch", "tiny_h16", "cfg1_xxs24_224"])
+@pytest.mark.parametrize("name", ["tiny_det", "tiny_refine", "tiny_two_branch", "tiny_h16", "cfg1_xxs24_224", "cfg2_s24_640"])
 def test_oracle_matches_reference_golden(golden_dir, name):
     gold = _load(golden_dir, name)
     cfg, p, out, ld, idx, loss = _run(gold)
