@@ -88,6 +88,45 @@ def matcher_cpu_us_per_img(n_img=24):
     return (time.perf_counter() - t0) * 1e6 / n_img
 
 
+def fused_talking_heads_microbench(dev, cfg, B, reps=3):
+    """The fused talking-heads kernels (csrc/talking_fused.cu; SPE_TH_FUSED=1) at the benchmarked backbone shape, one layer forward +
+    backward: per-kernel device time (library profiler, CUDA events on the launch stream) and the saved-activation footprint next to
+    the unfused pipeline the timed step uses for training (ops._talking_fused_mode: auto)."""
+    from spe_b200 import _lib, ops
+    H, D = cfg.num_heads, cfg.embed_dim
+    N = (640 // cfg.patch) ** 2
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B, N, 3 * D, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
+    Wl = (torch.eye(H) + 0.1 * torch.randn(H, H, generator=g)).to(dev).requires_grad_(True)
+    Ww = (torch.eye(H) + 0.1 * torch.randn(H, H, generator=g)).to(dev).requires_grad_(True)
+    bl = torch.zeros(H, device=dev, requires_grad=True)
+    bw = torch.zeros(H, device=dev, requires_grad=True)
+    go = torch.randn(B, N, D, generator=g).to(torch.bfloat16).to(dev)
+    res = {}
+    for name, fn in (("fused", ops.TalkingHeadsFusedFn), ("unfused", ops.TalkingHeadsAttentionFn)):
+        for it in range(reps + 1):
+            if it == 1:
+                torch.cuda.synchronize()
+                _lib.prof_enable(True)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            torch.cuda.reset_peak_memory_stats()
+            m0 = torch.cuda.memory_allocated()
+            out = fn.apply(qkv, Wl, bl, Ww, bw, H)
+            saved = torch.cuda.memory_allocated() - m0
+            out.backward(go)
+            qkv.grad = None
+        e1.record()
+        torch.cuda.synchronize()
+        _lib.prof_enable(False)
+        fam = _lib.prof_collect()
+        res[name] = {"fwd_bwd_ms_per_layer": e0.elapsed_time(e1) / reps, "saved_activation_bytes_per_layer": int(saved),
+                     "kernel_ms_per_layer": {k: v[0] / reps for k, v in fam.items() if v[2]}}
+    res["shape"] = "B=%d H=%d N=%d dh=%d (cfg2 backbone block), one layer forward + backward" % (B, H, N, D // H)
+    res["default"] = "training step uses the unfused pipeline (auto mode); fused forward is used when no gradient is required"
+    return res
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -327,6 +366,19 @@ def run_ours(args):
         roof["algorithmic_per_launch"] = breakdown[dominant]["work_per_step"] / max(1.0, breakdown[dominant]["launches_per_step"])
     except Exception:
         pass
+    # the fraction north_star asks for: attention-GEMM roofline.  Algorithmic FLOPs = SURVEY section 8(d): QK^T + PV only
+    # (L 4N^2D + E 4N^2Dd + P Ld (4Q^2Dd + 6QNDd) per image forward, x3 for forward + backward; recompute inside the fused kernels and
+    # the head mixes are NOT counted), over the device time of every kernel that implements attention (profiled pass, serialised).
+    N_tok, Dm, Q = (640 // cfg.patch) ** 2, cfg.embed_dim, cfg.num_queries
+    att_fwd = cfg.depth * 4 * N_tok * N_tok * Dm + cfg.enc_layers * 4 * N_tok * N_tok * Dm + \
+        (cfg.num_refines + 1) * cfg.dec_layers * (4 * Q * Q * Dm + 6 * Q * N_tok * Dm)
+    att_fams = ("gemm_attention", "talking_softmax_fwd", "talking_softmax_bwd", "attention_fused", "softmax")
+    att_ms = sum(fam[k][0] for k in att_fams) / nprof
+    att_tflops = 3.0 * att_fwd * B / (att_ms * 1e-3) / 1e12 if att_ms > 0 else 0.0
+    roof["attention_gemm"] = {"achieved": att_tflops, "unit": "TFLOP/s", "peak": peaks["tflops"], "frac": att_tflops / peaks["tflops"],
+                              "algorithmic_flops_per_step": 3.0 * att_fwd * B, "ms_per_step": att_ms,
+                              "families": {k: fam[k][0] / nprof for k in att_fams},
+                              "note": "QK^T + PV flops only (SURVEY 8d) over all attention kernels incl. softmax / head-mix time"}
     roof["peak_source"] = peaks["src"] + " -- of measured"
     roof["how"] = "CUDA events on the launch stream around every launch of the family during %d profiled steps; achieved = sum(algorithmic work)/sum(time)" % nprof
     roof["gemm_tflops"] = g_tflops
@@ -334,6 +386,11 @@ def run_ours(args):
     roof["hbm_families_gbs"] = hbm
 
     matcher = matcher_microbench(dev)
+    fused_th = None
+    try:
+        fused_th = fused_talking_heads_microbench(dev, cfg, B)
+    except Exception as e:                                        # informational block: never fails the bench line
+        fused_th = {"error": str(e)[:200]}
     cpu = None
     if args.cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -353,7 +410,7 @@ def run_ours(args):
                        "step": ("engine.TrainStep, whole step captured in a CUDA graph and replayed" if not args.eager else "engine.TrainStep, eager launches")},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernel_breakdown": breakdown, "matcher": matcher,
-            "cpu_baseline": cpu}
+            "talking_heads_fused": fused_th, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
