@@ -42,7 +42,7 @@ int spe_prof_family_count(void);
  * and their backward (dgrad: B operand MN-major = the same weight; wgrad: both MN-major).
  * ------------------------------------------------------------------------------------------- */
 enum { SPE_MAJOR_K = 0, SPE_MAJOR_MN = 1 };
-enum { SPE_DT_BF16 = 0, SPE_DT_F32 = 1 };
+enum { SPE_DT_BF16 = 0, SPE_DT_F32 = 1, SPE_DT_F16 = 2 };   /* F16: plain / alpha-scaled output only (the talking-heads logits) */
 enum { SPE_ACT_NONE = 0, SPE_ACT_RELU = 1, SPE_ACT_GELU = 2,
        SPE_ACT_RELU_GRAD = 3,   /* out = v * (aux_in > 0)           */
        SPE_ACT_GELU_GRAD = 4 }; /* out = v * gelu'(aux_in)          */
@@ -177,6 +177,16 @@ int spe_talking_softmax_bwd(const float* S, const void* dA, void* dS, const floa
                             float* dWl, float* dbl, float* dWw, float* dbw, float* workspace, int64_t workspace_floats,
                             void* stream);
 int64_t spe_talking_softmax_bwd_workspace(int B, int H, int Nq, int Nk);
+/* The same two kernels with the logits S kept in FP16 in HBM (spe_gemm with c_dtype = SPE_DT_F16): the head mix rounds S to fp16
+ * anyway (single-pass fp16 mma.sync), so the forward is bit-identical, and the N^2 logit traffic (S write + 2 reads per layer) and
+ * the saved-activation footprint of S halve.  Row-staged kernels only: query with spe_talking_s16_supported first. */
+int spe_talking_s16_supported(int H, int Nk, int64_t ldS, int64_t ldA);
+int spe_talking_softmax_fwd_s16(const void* S_f16, void* A, const float* Wl, const float* bl, const float* Ww,
+                                const float* bw, float* stats, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream);
+int spe_talking_softmax_bwd_s16(const void* S_f16, const void* dA, void* dS, const float* Wl, const float* bl,
+                                const float* Ww, const float* bw, const float* stats, int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA,
+                                float* dWl, float* dbl, float* dWw, float* dbw, float* workspace, int64_t workspace_floats,
+                                void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FUSED talking-heads attention (csrc/talking_fused.cu): the whole of Attention_talking_head.forward between the qkv and

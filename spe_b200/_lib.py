@@ -89,6 +89,10 @@ _SIGS = {
     "spe_talking_softmax_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p, c_p, c_p,
                                       c_p, c_l, c_p]),
     "spe_talking_softmax_bwd_workspace": (c_l, [c_i, c_i, c_i, c_i]),
+    "spe_talking_s16_supported": (c_i, [c_i, c_i, c_l, c_l]),
+    "spe_talking_softmax_fwd_s16": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p]),
+    "spe_talking_softmax_bwd_s16": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_l, c_p, c_p, c_p, c_p,
+                                          c_p, c_l, c_p]),
     "spe_talking_fused_supported": (c_i, [c_i, c_i]),
     "spe_talking_fused_fwd_workspace": (c_l, [c_i, c_i, c_i, c_i]),
     "spe_talking_fused_fwd": (c_i, [C.POINTER(TalkingFusedArgs), c_p]),

@@ -73,6 +73,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t pack_f16x2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint16_t f_to_f16(float f) {
+    uint16_t r;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(r) : "f"(f));
+    return r;
+}
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
     return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }

@@ -210,7 +210,7 @@ __device__ __noinline__ void epilogue_direct(const EpiParams& ep, const uint32_t
         const int dn = ep.split > 0 ? (n / ep.split) * ep.split_stride + (n % ep.split) : n;
         if (ep.splits > 1 || ep.accum) atomicAdd(Cf + dn, x);
         else if (ep.c_dtype == SPE_DT_F32) Cf[dn] = x;
-        else Cb[dn] = f_to_bf16(x);
+        else Cb[dn] = ep.c_dtype == SPE_DT_F16 ? f_to_f16(x) : f_to_bf16(x);
     }
 }
 
@@ -222,7 +222,7 @@ __device__ __noinline__ void epilogue_direct(const EpiParams& ep, const uint32_t
 //  warps per scheduler that made EVERY GEMM epilogue-latency bound: the MMA warp spent its time waiting on `tempty`.)
 //   ACT: 0 none, 1 relu, 2 gelu, 3 relu_grad (needs Xi), 4 gelu_grad (needs Xi)
 // ------------------------------------------------------------------------------------------------
-template <bool C32, bool BIAS, int ACT, bool GAMMA, bool RES, bool XO>
+template <bool C32, bool BIAS, int ACT, bool GAMMA, bool RES, bool XO, bool F16 = false>
 __device__ __forceinline__ void epi_fast(const EpiParams& ep, const uint32_t (&r)[64], int nb, int lane, uint32_t sRC, uint32_t sX) {
     const uint32_t rowoff = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
@@ -273,6 +273,9 @@ __device__ __forceinline__ void epi_fast(const EpiParams& ep, const uint32_t (&r
             const uint32_t sl = sRC + (g >> 2) * SLAB + rowoff;
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + (((uint32_t)((g & 3) * 2) ^ sw) << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + (((uint32_t)((g & 3) * 2 + 1) ^ sw) << 4)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+        } else if constexpr (F16) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sRC + rowoff + (((uint32_t)g ^ sw) << 4)), "r"(pack_f16x2_rn(v[0], v[1])),
+                         "r"(pack_f16x2_rn(v[2], v[3])), "r"(pack_f16x2_rn(v[4], v[5])), "r"(pack_f16x2_rn(v[6], v[7])) : "memory");
         } else {
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sRC + rowoff + (((uint32_t)g ^ sw) << 4)), "r"(pack_bf16x2(v[0], v[1])),
                          "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
@@ -282,7 +285,7 @@ __device__ __forceinline__ void epi_fast(const EpiParams& ep, const uint32_t (&r
 
 // the specialisations that exist (host picks one; anything else takes the generic run-time path)
 enum { EM_GENERIC = 0, EM_F32, EM_BF16, EM_BF16_BIAS, EM_F32_BIAS, EM_F32_BIAS_GAMMA_RES_XO, EM_F32_BIAS_RES, EM_F32_RES, EM_BF16_BIAS_RES,
-       EM_BF16_BIAS_GELU_XO, EM_BF16_BIAS_RELU, EM_BF16_RELUGRAD, EM_BF16_GELUGRAD };
+       EM_BF16_BIAS_GELU_XO, EM_BF16_BIAS_RELU, EM_BF16_RELUGRAD, EM_BF16_GELUGRAD, EM_F16 };
 
 // CG2 = CTA-pair mode: a cluster of 2 CTAs computes a 256 x BN tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows
 // of A and HALF of the B tile (BN/2 rows), the tensor core reads both halves, so the SM<->L2 operand traffic per flop drops by
@@ -562,6 +565,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                     switch (emode) {
                         case EM_F32: epi_fast<true, false, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
                         case EM_BF16: epi_fast<false, false, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
+                        case EM_F16: epi_fast<false, false, 0, false, false, false, true>(ep, r, nb, lane, sRC, sX); break;
                         case EM_BF16_BIAS: epi_fast<false, true, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
                         case EM_F32_BIAS: epi_fast<true, true, 0, false, false, false>(ep, r, nb, lane, sRC, sX); break;
                         case EM_F32_BIAS_GAMMA_RES_XO: epi_fast<true, true, 0, true, true, true>(ep, r, nb, lane, sRC, sX); break;
@@ -671,6 +675,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl + slab_off(lane, (g & 3) * 2 + 1)), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
                     } else {
                         // bf16 C chunk g overlays residual columns 4g..4g+3, which this thread consumed at group g/2 <= g
+                        if (ep.c_dtype == SPE_DT_F16)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sRC + slab_off(lane, g)), "r"(pack_f16x2_rn(v[0], v[1])),
+                                         "r"(pack_f16x2_rn(v[2], v[3])), "r"(pack_f16x2_rn(v[4], v[5])), "r"(pack_f16x2_rn(v[6], v[7])) : "memory");
+                        else
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sRC + slab_off(lane, g)), "r"(pack_bf16x2(v[0], v[1])),
                                      "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
                     }
@@ -876,6 +884,8 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
     const bool pair = pair_ok && (env.cg2 >= 2 || (env.cg2 == 1 && a->M >= 1024 && (a->M % 256 == 0 || a->M >= 4096)));
     const int BN = a->N <= 64 ? 64 : (pair ? (a->N >= 1024 ? 256 : 128) : (wideN ? 256 : 128));
     SPE_CHECK(batch == 1 || !(a->aux_in || a->aux_out), "spe_gemm: aux_in / aux_out are not batched");
+    SPE_CHECK(a->c_dtype != SPE_DT_F16 || (!a->bias && !a->gamma && !a->residual && !a->aux_in && !a->aux_out && a->act == SPE_ACT_NONE && a->split == 0),
+              "spe_gemm: fp16 output supports the plain alpha-scaled product only");
     CUtensorMap tA, tB;
     if (make_tmap(&tA, a->A, a->a_major, a->M, a->K, a->lda, a->a_sb1, a->a_sb2, a->batch1, a->batch2, BM)) return -1;
     if (make_tmap(&tB, a->B, a->b_major, a->N, a->K, a->ldb, a->b_sb1, a->b_sb2, a->batch1, a->batch2, pair ? BN / 2 : BN)) return -1;
@@ -918,6 +928,7 @@ extern "C" __attribute__((visibility("default"))) int spe_gemm(const spe_gemm_ar
         if (tma_io && !env.generic_epilogue) {
             if (a->act == SPE_ACT_NONE && !xi) {
                 if (cf32 && !bi && !ga && !re && !xo) m = EM_F32;
+                else if (a->c_dtype == SPE_DT_F16 && !bi && !ga && !re && !xo) m = EM_F16;
                 else if (!cf32 && !bi && !ga && !re && !xo) m = EM_BF16;
                 else if (!cf32 && bi && !ga && !re && !xo) m = EM_BF16_BIAS;
                 else if (cf32 && bi && !ga && !re && !xo) m = EM_F32_BIAS;

@@ -692,6 +692,34 @@ __device__ __forceinline__ void rw_bulk_g2s(uint32_t dst, const void* src, uint3
 // (N = 1600 unpadded put every head on the same banks: 56% of the shared wavefronts were conflicts).  bf16 rows: pitch = 32 (mod 64).
 __host__ __device__ __forceinline__ int talking_pitch_f32(int ld) { return ld + ((20 - ld % 16) % 16); }
 __host__ __device__ __forceinline__ int talking_pitch_bf16(int ld) { return ld + ((96 - ld % 64) % 64); }
+// fp16 logit rows (S kept in fp16 in HBM: half the N^2 traffic of the fp32 logits; the head mix rounds S to fp16 anyway, so the
+// forward is bit-identical): pitch = 16 (mod 32) halves, i.e. consecutive head PAIRS (the B-operand layout reads heads 2 r4, 2 r4 + 1)
+// start 64 bytes apart modulo 128 -- the 8-byte lane reads of r4 = 0 / 1 and of r4 = 2 / 3 share a wavefront without conflicts
+__host__ __device__ __forceinline__ int talking_pitch_f16(int ld) { return ld + ((48 - ld % 32) % 32); }
+
+// raw fp16 S of one 32-key step in the B-operand layout: 4 keys [base + 4 q4, +4) of heads 2 r4 (h0) and 2 r4 + 1 (h1)
+struct SRaw16 { uint2 h0, h1; };
+template <int H>
+__device__ __forceinline__ SRaw16 load_sraw16(const uint16_t* __restrict__ Sb, int pH, int base, int ldS, int q4, int r4) {
+    SRaw16 r;
+    r.h0 = make_uint2(0u, 0u); r.h1 = r.h0;
+    const int cb = base + 4 * q4;
+    if (cb + 4 <= ldS) {
+        if (2 * r4 < H) r.h0 = *reinterpret_cast<const uint2*>(Sb + (2 * r4) * pH + cb);
+        if (2 * r4 + 1 < H) r.h1 = *reinterpret_cast<const uint2*>(Sb + (2 * r4 + 1) * pH + cb);
+    }
+    return r;
+}
+// (head 2 r4, head 2 r4 + 1) of key t as one f16x2 register -- the mix operand, straight from the stored halves
+__device__ __forceinline__ uint32_t sraw16_pair(const SRaw16& r, int t) {
+    const uint32_t a = t < 2 ? r.h0.x : r.h0.y, b = t < 2 ? r.h1.x : r.h1.y;
+    return __byte_perm(a, b, (t & 1) ? 0x7632 : 0x5410);
+}
+__device__ __forceinline__ float f16_bits_to_f(uint32_t h) {
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"((uint16_t)h));
+    return f;
+}
 
 // ---- per-step bodies (TAIL = false: all 32 keys of the step are valid, no masking code at all) ----
 // forward sweep A: mixed logits of one step -> online (max, sum); the logits are written back over S in shared memory
@@ -743,14 +771,54 @@ __device__ __forceinline__ void tfwd_step_b(const float* Sb, int pS, int ldS, in
     }
 }
 
+// fp16-S flavour of sweep A: the raw logits come from the fp16 row buffer, the mixed logits go to a separate fp32 cache
+template <int H, bool TAIL>
+__device__ __forceinline__ void tfwd_step_a16(const uint16_t* S16b, int pH, float* Lb, int pS, int ldS, int base, int Nk, uint32_t fWl, float bl2, int q4, int r4,
+                                              float& m, float& z) {
+    float L2[8];
+    const SRaw16 raw = load_sraw16<H>(S16b, pH, base, ldS, q4, r4);
+    const int cb = base + 4 * q4;
+    const bool tail = TAIL && base + 32 > Nk;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const bool ok = !tail || cb + t < Nk;       // padding columns of S are never written: sanitise
+        mix_tile16(fWl, ok ? sraw16_pair(raw, t) : 0u, bl2, L2[t], L2[4 + t]);
+    }
+    const int c8 = base + 8 * r4;
+    if (tail) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) L2[i] = -INFINITY;
+    }
+    if (q4 < H && c8 + 8 <= ldS) {
+        float4* d = reinterpret_cast<float4*>(Lb + q4 * pS + c8);
+        d[0] = make_float4(L2[0], L2[1], L2[2], L2[3]);
+        d[1] = make_float4(L2[4], L2[5], L2[6], L2[7]);
+    }
+    float mx = fmaxf(fmaxf(fmaxf(L2[0], L2[1]), fmaxf(L2[2], L2[3])), fmaxf(fmaxf(L2[4], L2[5]), fmaxf(L2[6], L2[7])));
+    const float mn = fmaxf(m, mx);
+    if (!TAIL || mn > -INFINITY) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += fast_ex2(L2[i] - mn);
+        z = z * fast_ex2(m - mn) + acc;
+        m = mn;
+    }
+}
+
 // NW warps share one row; the steps of a row are dealt out evenly (NW = 10 fits the 50 steps of N = 1600 exactly).
-template <int H, int NW>
-__global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const float* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
+// S16: S is fp16 in HBM (row staged by the same bulk copies at half the bytes); the fp32 cache of the mixed logits is then a
+// separate single buffer (the in-place overwrite of the fp32 flavour needs equal element sizes).
+template <int H, int NW, bool S16>
+__global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const void* __restrict__ Sv, uint16_t* __restrict__ A, const float* __restrict__ Wl,
                                                                       const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
                                                                       float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
     extern __shared__ __align__(128) uint8_t rsm[];
-    float* Sbuf = reinterpret_cast<float*>(rsm);                       // [2][H][pS]
     const int pS = talking_pitch_f32(ldS);                             // padded row pitch: conflict-free in both fragment layouts
+    const int pH = talking_pitch_f16(ldS);
+    float* Sbuf = reinterpret_cast<float*>(rsm);                       // fp32 S: [2][H][pS] (logits cached in place);  fp16 S: [H][pS] logit cache
+    uint16_t* S16buf = reinterpret_cast<uint16_t*>(rsm + (size_t)H * pS * 4);     // fp16 S: [2][H][pH]
+    const float* S = reinterpret_cast<const float*>(Sv);
+    const uint16_t* Sh = reinterpret_cast<const uint16_t*>(Sv);
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ float red[NW][8][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q4 = lane >> 2, r4 = lane & 3;
@@ -769,9 +837,15 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const floa
         const uint32_t bar = bar0 + 8 * buf;
         // the generic-proxy writes (cached logits) of the row that used this buffer before are ordered before the async-proxy refill
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        rw_mbar_expect_tx(bar, (uint32_t)(H * ldS * 4));
-        for (int h = 0; h < H; ++h)
-            rw_bulk_g2s(rw_smem_u32(Sbuf + ((size_t)buf * H + h) * pS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar);
+        if (S16) {
+            rw_mbar_expect_tx(bar, (uint32_t)(H * ldS * 2));
+            for (int h = 0; h < H; ++h)
+                rw_bulk_g2s(rw_smem_u32(S16buf + ((size_t)buf * H + h) * pH), Sh + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 2), bar);
+        } else {
+            rw_mbar_expect_tx(bar, (uint32_t)(H * ldS * 4));
+            for (int h = 0; h < H; ++h)
+                rw_bulk_g2s(rw_smem_u32(Sbuf + ((size_t)buf * H + h) * pS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar);
+        }
     };
     const int nst = (ldA + 31) / 32;                                   // steps of 32 keys; both sweeps use the same deal
     const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;
@@ -782,15 +856,21 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_fwd_rows_kernel(const floa
         // buffer buf^1 was last touched in the previous iteration, which ended with __syncthreads
         if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x, buf ^ 1);
         rw_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
-        float* Sb = Sbuf + (size_t)buf * H * pS;
+        float* Sb = S16 ? Sbuf : Sbuf + (size_t)buf * H * pS;
+        const uint16_t* S16b = S16buf + (size_t)buf * H * pH;
         const int b = row / Nq, q = row % Nq;
         uint16_t* Ab = A + ((long long)b * H * Nq + q) * ldA;
         // ---- sweep A (this warp's steps): mixed logits -> smem, online (max, sum)
         float m = -INFINITY, z = 0.f;
         for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            if (base + 32 <= Nk) tfwd_step_a<H, false>(Sb, pS, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
-            else tfwd_step_a<H, true>(Sb, pS, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
+            if (S16) {
+                if (base + 32 <= Nk) tfwd_step_a16<H, false>(S16b, pH, Sb, pS, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
+                else tfwd_step_a16<H, true>(S16b, pH, Sb, pS, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
+            } else {
+                if (base + 32 <= Nk) tfwd_step_a<H, false>(Sb, pS, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
+                else tfwd_step_a<H, true>(Sb, pS, ldS, base, Nk, fWl, bl2, q4, r4, m, z);
+            }
         }
         {
             float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
@@ -905,17 +985,127 @@ __device__ __forceinline__ void tbwd_step_c(const float* Sb, const uint16_t* Db,
     }
 }
 
-template <int H, int NW>
-__global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const float* __restrict__ S, const uint16_t* dA, uint16_t* dS, const float* __restrict__ Wl,
+// fp16-S flavours: the raw logits stay in their own fp16 row buffer (never overwritten), so sweep C re-reads them for the dWl outer
+// product and the lane-private S_hi side buffer is not needed; dP goes to the fp32 buffer as before.
+template <int H, bool TAIL>
+__device__ __forceinline__ void tbwd_step_b16(const uint16_t* S16b, int pH, float* Sb, uint16_t* Db, int pS, int pA, int ldS, int ldA, int base, int Nk, uint32_t fWl,
+                                              const MixFrag& fWwT, float bl2, float c2, int q4, int r4, float& rho, float (&accWw)[4]) {
+    float L2[8], d[8], dP[8], p[8];
+    uint32_t dpk[4], ppk[4];
+    {
+        const SRaw16 raw = load_sraw16<H>(S16b, pH, base, ldS, q4, r4);
+        const int cb = base + 4 * q4;
+        const bool tail = TAIL && base + 32 > Nk;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const bool ok = !tail || cb + t < Nk;
+            mix_tile16(fWl, ok ? sraw16_pair(raw, t) : 0u, bl2, L2[t], L2[4 + t]);
+        }
+        if (tail) {
+            const int c8t = base + 8 * r4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (c8t + i >= Nk) L2[i] = -INFINITY;
+        }
+    }
+    const int c8 = base + 8 * r4;
+    const bool slot = q4 < H && c8 + 8 <= ldA;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (slot) v = *reinterpret_cast<const uint4*>(Db + q4 * pA + c8);
+    {
+        float2 t;
+        t = unpack_bf16x2(v.x); d[0] = t.x; d[1] = t.y;
+        t = unpack_bf16x2(v.y); d[2] = t.x; d[3] = t.y;
+        t = unpack_bf16x2(v.z); d[4] = t.x; d[5] = t.y;
+        t = unpack_bf16x2(v.w); d[6] = t.x; d[7] = t.y;
+    }
+    if (TAIL) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) d[i] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        p[t] = fast_ex2(L2[t] - c2); p[4 + t] = fast_ex2(L2[4 + t] - c2);
+        dpk[t] = pack_bf16x2(d[t], d[4 + t]);
+        ppk[t] = pack_bf16x2(p[t], p[4 + t]);
+        mix_tile(fWwT, movm_trans(dpk[t]), 0u, 0.f, dP[t], dP[4 + t]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rho += p[i] * dP[i];
+    mma16816(accWw, dpk[0], 0u, dpk[1], 0u, ppk[0], ppk[1]);
+    mma16816(accWw, dpk[2], 0u, dpk[3], 0u, ppk[2], ppk[3]);
+    if (slot) {
+        *reinterpret_cast<uint4*>(Db + q4 * pA + c8) = make_uint4(ppk[0], ppk[1], ppk[2], ppk[3]);
+        if (c8 + 8 <= ldS) {
+            float4* dst = reinterpret_cast<float4*>(Sb + q4 * pS + c8);
+            dst[0] = make_float4(dP[0], dP[1], dP[2], dP[3]);
+            dst[1] = make_float4(dP[4], dP[5], dP[6], dP[7]);
+        }
+    }
+}
+template <int H, bool TAIL>
+__device__ __forceinline__ void tbwd_step_c16(const uint16_t* S16b, int pH, const float* Sb, const uint16_t* Db, int pS, int pA, int ldS, int ldA, int base, int Nk,
+                                              const MixFrag& fWlT, float rho, uint16_t* dSb, long long hA, int q4, int r4, float (&accWl)[4]) {
+    const int c8 = base + 8 * r4;
+    const bool slot = q4 < H && c8 + 8 <= ldA && c8 + 8 <= ldS;
+    float l[8], o[8];
+    uint32_t lpk[4], shi[4];
+    if (slot) {
+        const uint4 pp = *reinterpret_cast<const uint4*>(Db + q4 * pA + c8);
+        const float4 u = *reinterpret_cast<const float4*>(Sb + q4 * pS + c8), w = *reinterpret_cast<const float4*>(Sb + q4 * pS + c8 + 4);
+        const float2 p0 = unpack_bf16x2(pp.x), p1 = unpack_bf16x2(pp.y), p2 = unpack_bf16x2(pp.z), p3 = unpack_bf16x2(pp.w);   // (p[t], p[4+t])
+        l[0] = p0.x * (u.x - rho); l[4] = p0.y * (w.x - rho);
+        l[1] = p1.x * (u.y - rho); l[5] = p1.y * (w.y - rho);
+        l[2] = p2.x * (u.z - rho); l[6] = p2.y * (w.z - rho);
+        l[3] = p3.x * (u.w - rho); l[7] = p3.y * (w.w - rho);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) l[i] = 0.f;
+    }
+    {
+        // S of the step in the B-operand layout, bf16 (heads 2 r4, 2 r4 + 1 of keys base + 4 q4 + t)
+        const SRaw16 raw = load_sraw16<H>(S16b, pH, base, ldS, q4, r4);
+        const int cb = base + 4 * q4;
+        const bool tail = TAIL && base + 32 > Nk;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const bool ok = !tail || cb + t < Nk;
+            const uint32_t pr = ok ? sraw16_pair(raw, t) : 0u;
+            shi[t] = pack_bf16x2(f16_bits_to_f(pr & 0xffffu), f16_bits_to_f(pr >> 16));
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        lpk[t] = pack_bf16x2(l[t], l[4 + t]);
+        mix_tile(fWlT, movm_trans(lpk[t]), 0u, 0.f, o[t], o[4 + t]);
+    }
+    if (!TAIL || base < Nk) {
+        mma16816(accWl, lpk[0], 0u, lpk[1], 0u, movm_trans(shi[0]), movm_trans(shi[1]));
+        mma16816(accWl, lpk[2], 0u, lpk[3], 0u, movm_trans(shi[2]), movm_trans(shi[3]));
+    }
+    if (q4 < H && c8 + 8 <= ldA) {
+        if (TAIL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (c8 + i >= Nk) o[i] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(dSb + q4 * hA + c8) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+}
+
+template <int H, int NW, bool S16>
+__global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const void* __restrict__ Sv, const uint16_t* dA, uint16_t* dS, const float* __restrict__ Wl,
                                                                       const float* __restrict__ bl, const float* __restrict__ Ww,
                                                                       const float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA,
                                                                       float* __restrict__ part) {
     extern __shared__ __align__(128) uint8_t rsm[];
     // single row buffer per CTA; TWO CTAs share an SM, so one CTA's row load overlaps the other's math
-    const int pS = talking_pitch_f32(ldS), pA = talking_pitch_bf16(ldA);                     // padded pitches: no bank conflicts
-    float* Sbuf = reinterpret_cast<float*>(rsm);                                            // [H][pS]   S, then dP
+    const int pS = talking_pitch_f32(ldS), pA = talking_pitch_bf16(ldA), pH = talking_pitch_f16(ldS);   // padded pitches: no bank conflicts
+    float* Sbuf = reinterpret_cast<float*>(rsm);                                            // [H][pS]   S, then dP   (fp16 S: dP only)
     uint16_t* Dbuf = reinterpret_cast<uint16_t*>(rsm + (size_t)H * pS * 4);                 // [H][pA]   dA, then P
-    uint4* Xbuf = reinterpret_cast<uint4*>(rsm + (size_t)H * pS * 4 + (size_t)H * pA * 2);  // [steps][32]  S_hi fragments
+    uint4* Xbuf = reinterpret_cast<uint4*>(rsm + (size_t)H * pS * 4 + (size_t)H * pA * 2);  // [steps][32]  S_hi fragments (fp32 S)
+    uint16_t* S16buf = reinterpret_cast<uint16_t*>(Xbuf);                                   // [H][pH]   fp16 S (instead of Xbuf)
+    const float* S = reinterpret_cast<const float*>(Sv);
+    const uint16_t* Sh = reinterpret_cast<const uint16_t*>(Sv);
     constexpr int NP = 2 * H * H + 2 * H;
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ float red[NW][8];
@@ -936,9 +1126,10 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const floa
     auto issue = [&](int row) {
         const int b = row / Nq, q = row % Nq;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of the previous row before the async refill
-        rw_mbar_expect_tx(bar0, (uint32_t)(H * ldS * 4 + H * ldA * 2));
+        rw_mbar_expect_tx(bar0, (uint32_t)(H * ldS * (S16 ? 2 : 4) + H * ldA * 2));
         for (int h = 0; h < H; ++h) {
-            rw_bulk_g2s(rw_smem_u32(Sbuf + (size_t)h * pS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar0);
+            if (S16) rw_bulk_g2s(rw_smem_u32(S16buf + (size_t)h * pH), Sh + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 2), bar0);
+            else rw_bulk_g2s(rw_smem_u32(Sbuf + (size_t)h * pS), S + ((long long)b * H * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 4), bar0);
             rw_bulk_g2s(rw_smem_u32(Dbuf + (size_t)h * pA), dA + ((long long)b * H * Nq + q) * ldA + h * hA, (uint32_t)(ldA * 2), bar0);
         }
     };
@@ -959,7 +1150,10 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const floa
         float rho = 0.f;
         for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            if (base + 32 <= Nk) tbwd_step_b<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, lane, rho, accWw);
+            if (S16) {
+                if (base + 32 <= Nk) tbwd_step_b16<H, false>(S16buf, pH, Sbuf, Dbuf, pS, pA, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, rho, accWw);
+                else tbwd_step_b16<H, true>(S16buf, pH, Sbuf, Dbuf, pS, pA, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, rho, accWw);
+            } else if (base + 32 <= Nk) tbwd_step_b<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, lane, rho, accWw);
             else tbwd_step_b<H, true>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWl, fWwT, bl2, c2, q4, r4, lane, rho, accWw);
         }
         rho += __shfl_xor_sync(0xffffffffu, rho, 1);
@@ -972,7 +1166,10 @@ __global__ void __launch_bounds__(NW * 32, 2) talking_bwd_rows_kernel(const floa
         // ---- sweep C: dL = P (dP - rho);  dS = Wl^T dL;  dWl += dL (x) S     (dbl = sum dL is identically 0: not accumulated)
         for (int st = s0; st < s1; ++st) {
             const int base = st * 32;
-            if (base + 32 <= Nk) tbwd_step_c<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, lane, accWl);
+            if (S16) {
+                if (base + 32 <= Nk) tbwd_step_c16<H, false>(S16buf, pH, Sbuf, Dbuf, pS, pA, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, accWl);
+                else tbwd_step_c16<H, true>(S16buf, pH, Sbuf, Dbuf, pS, pA, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, accWl);
+            } else if (base + 32 <= Nk) tbwd_step_c<H, false>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, lane, accWl);
             else tbwd_step_c<H, true>(Sbuf, Dbuf, Xbuf + (size_t)st * 32, pS, pA, ldS, ldA, base, Nk, fWlT, rho, dSb, hA, q4, r4, lane, accWl);
         }
         __syncthreads();                                               // every warp is done with the row buffer
@@ -1336,24 +1533,36 @@ static int talking_grid(int B, int Nq, int per_sm) {
     return (int)(blocks < cap ? blocks : cap);
 }
 
+// shared memory of the row-staged kernels with fp16 logits
+static size_t talking_fwd_smem16(int H, int ldS) { return (size_t)H * talking_pitch_f32(ldS) * 4 + (size_t)2 * H * talking_pitch_f16(ldS) * 2; }
+static size_t talking_bwd_smem16(int H, int ldS, int ldA) {
+    return (size_t)H * (talking_pitch_f32(ldS) * 4 + talking_pitch_bf16(ldA) * 2 + talking_pitch_f16(ldS) * 2);
+}
+
 template <int H>
-static int talking_fwd_launch(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats, int B, int Nq,
-                              int Nk, int64_t ldS, int64_t ldA, cudaStream_t st) {
-    SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 6.0, st);   // algorithmic bytes: S f32 read + A bf16 write
-    const size_t smem = (size_t)2 * H * talking_pitch_f32((int)ldS) * 4;
-    if (stats && smem <= 100 * 1024 + 4096 && getenv("SPE_TALKING_WARP_ROWS") == nullptr) {
+static int talking_fwd_launch(const void* Sv, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats, int B, int Nq,
+                              int Nk, int64_t ldS, int64_t ldA, cudaStream_t st, bool s16 = false) {
+    const float* S = reinterpret_cast<const float*>(Sv);
+    SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * (s16 ? 4.0 : 6.0), st);   // algorithmic bytes: S read + A bf16 write
+    const size_t smem = s16 ? talking_fwd_smem16(H, (int)ldS) : (size_t)2 * H * talking_pitch_f32((int)ldS) * 4;
+    if (s16) SPE_CHECK(stats && smem <= 100 * 1024 + 4096, "spe_talking_softmax_fwd_s16: row does not fit the staged kernel (check spe_talking_s16_supported)");
+    if (stats && smem <= 100 * 1024 + 4096 && (s16 || getenv("SPE_TALKING_WARP_ROWS") == nullptr)) {
         static bool done = false;
         if (!done) {
-            SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-            SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            SPE_CUDA(cudaFuncSetAttribute(talking_fwd_rows_kernel<H, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
             done = true;
         }
         const long long rows = (long long)B * Nq;
         const int grid = (int)(rows < 2LL * spe_num_sms() ? rows : 2LL * spe_num_sms());
-        if (talking_warps((int)ldA) == 10)
-            talking_fwd_rows_kernel<H, 10><<<grid, 320, smem, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
-        else
-            talking_fwd_rows_kernel<H, 8><<<grid, 256, smem, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
+        uint16_t* A16 = reinterpret_cast<uint16_t*>(A);
+        const bool w10 = talking_warps((int)ldA) == 10;
+        if (s16 && w10) talking_fwd_rows_kernel<H, 10, true><<<grid, 320, smem, st>>>(Sv, A16, Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
+        else if (s16) talking_fwd_rows_kernel<H, 8, true><<<grid, 256, smem, st>>>(Sv, A16, Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
+        else if (w10) talking_fwd_rows_kernel<H, 10, false><<<grid, 320, smem, st>>>(Sv, A16, Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
+        else talking_fwd_rows_kernel<H, 8, false><<<grid, 256, smem, st>>>(Sv, A16, Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);
     } else {
         talking_fwd_kernel<H><<<talking_grid(B, Nq, 4), 256, 0, st>>>(S, reinterpret_cast<uint16_t*>(A), Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, ldS, ldA);
     }
@@ -1377,6 +1586,24 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(co
     }
 }
 
+// fp16 logits (S from spe_gemm with c_dtype = SPE_DT_F16): row-staged kernels only, H in {2, 4, 8}
+extern "C" __attribute__((visibility("default"))) int spe_talking_s16_supported(int H, int Nk, int64_t ldS, int64_t ldA) {
+    if (H != 2 && H != 4 && H != 8) return 0;
+    if (ldS % 8 != 0 || ldA % 8 != 0 || ldS < Nk || ldA < Nk) return 0;
+    return talking_fwd_smem16(H, (int)ldS) <= 100 * 1024 + 4096 && talking_bwd_smem16(H, (int)ldS, (int)ldA) <= 104 * 1024 ? 1 : 0;
+}
+extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd_s16(const void* S16, void* A, const float* Wl, const float* bl, const float* Ww,
+                                                                                  const float* bw, float* stats, int B, int H, int Nq, int Nk, int64_t ldS,
+                                                                                  int64_t ldA, void* stream) {
+    SPE_CHECK(S16 && A && Wl && bl && Ww && bw && stats && B > 0 && Nq > 0 && Nk > 0, "spe_talking_softmax_fwd_s16: bad argument");
+    SPE_CHECK(spe_talking_s16_supported(H, Nk, ldS, ldA), "spe_talking_softmax_fwd_s16: unsupported shape H=%d Nk=%d", H, Nk);
+    switch (H) {
+        case 2: return talking_fwd_launch<2>(S16, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream), true);
+        case 4: return talking_fwd_launch<4>(S16, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream), true);
+        default: return talking_fwd_launch<8>(S16, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream), true);
+    }
+}
+
 static int talking_bwd_grid(int B, int Nq) { return talking_grid(B, Nq, 4); }
 
 static int talking_bwd_rows_grid(int B, int Nq);
@@ -1392,26 +1619,33 @@ static int talking_bwd_rows_grid(int B, int Nq) {
 }
 
 template <int H>
-static int talking_bwd_launch(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B,
-                              int Nq, int Nk, int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* ws, cudaStream_t st) {
-    const size_t smem = (size_t)H * (talking_pitch_f32((int)ldS) * 4 + talking_pitch_bf16((int)ldA) * 2) + (size_t)((ldA + 31) / 32) * 512;
-    const bool rows_ok = stats && smem <= 104 * 1024 && getenv("SPE_TALKING_WARP_ROWS") == nullptr;
+static int talking_bwd_launch(const void* Sv, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B,
+                              int Nq, int Nk, int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* ws, cudaStream_t st,
+                              bool s16 = false) {
+    const float* S = reinterpret_cast<const float*>(Sv);
+    const size_t smem = s16 ? talking_bwd_smem16(H, (int)ldS, (int)ldA)
+                            : (size_t)H * (talking_pitch_f32((int)ldS) * 4 + talking_pitch_bf16((int)ldA) * 2) + (size_t)((ldA + 31) / 32) * 512;
+    const bool rows_ok = stats && smem <= 104 * 1024 && (s16 || getenv("SPE_TALKING_WARP_ROWS") == nullptr);
+    if (s16) SPE_CHECK(rows_ok, "spe_talking_softmax_bwd_s16: row does not fit the staged kernel (check spe_talking_s16_supported)");
     const int grid = rows_ok ? talking_bwd_rows_grid(B, Nq) : talking_bwd_grid(B, Nq);
     {
-        SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * 8.0, st);   // S f32 read + dA bf16 read + dS bf16 write
+        SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * (s16 ? 6.0 : 8.0), st);   // S read + dA bf16 read + dS bf16 write
         if (rows_ok) {
             static bool done = false;
             if (!done) {
-                SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
-                SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
+                SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
+                SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
+                SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
+                SPE_CUDA(cudaFuncSetAttribute(talking_bwd_rows_kernel<H, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024));
                 done = true;
             }
-            if (talking_warps((int)ldA) == 10)
-                talking_bwd_rows_kernel<H, 10><<<grid, 320, smem, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww,
-                                                                          stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
-            else
-                talking_bwd_rows_kernel<H, 8><<<grid, 256, smem, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww,
-                                                                         stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
+            const uint16_t* dA16 = reinterpret_cast<const uint16_t*>(dA);
+            uint16_t* dS16 = reinterpret_cast<uint16_t*>(dS);
+            const bool w10 = talking_warps((int)ldA) == 10;
+            if (s16 && w10) talking_bwd_rows_kernel<H, 10, true><<<grid, 320, smem, st>>>(Sv, dA16, dS16, Wl, bl, Ww, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
+            else if (s16) talking_bwd_rows_kernel<H, 8, true><<<grid, 256, smem, st>>>(Sv, dA16, dS16, Wl, bl, Ww, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
+            else if (w10) talking_bwd_rows_kernel<H, 10, false><<<grid, 320, smem, st>>>(Sv, dA16, dS16, Wl, bl, Ww, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
+            else talking_bwd_rows_kernel<H, 8, false><<<grid, 256, smem, st>>>(Sv, dA16, dS16, Wl, bl, Ww, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, ws);
         } else {
             talking_bwd_kernel<H><<<grid, 256, 0, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, B * Nq, Nq, Nk,
                                                         ldS, ldA, ws);
@@ -1422,6 +1656,21 @@ static int talking_bwd_launch(const float* S, const void* dA, void* dS, const fl
     talking_bwd_finalize_kernel<<<(NP + 7) / 8, 256, 0, st>>>(ws, grid, H, dWl, dbl, dWw, dbw);
     SPE_LAUNCHED();
     return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd_s16(const void* S16, const void* dA, void* dS, const float* Wl, const float* bl,
+                                                                                  const float* Ww, const float* bw, const float* stats, int B, int H, int Nq, int Nk,
+                                                                                  int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw,
+                                                                                  float* workspace, int64_t workspace_floats, void* stream) {
+    (void)bw;
+    SPE_CHECK(S16 && dA && dS && Wl && bl && Ww && stats && dWl && dbl && dWw && dbw && workspace, "spe_talking_softmax_bwd_s16: null argument");
+    SPE_CHECK(spe_talking_s16_supported(H, Nk, ldS, ldA), "spe_talking_softmax_bwd_s16: unsupported shape H=%d Nk=%d", H, Nk);
+    SPE_CHECK(workspace_floats >= spe_talking_softmax_bwd_workspace(B, H, Nq, Nk), "spe_talking_softmax_bwd_s16: workspace too small");
+    switch (H) {
+        case 2: return talking_bwd_launch<2>(S16, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream), true);
+        case 4: return talking_bwd_launch<4>(S16, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream), true);
+        default: return talking_bwd_launch<8>(S16, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream), true);
+    }
 }
 
 extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd(const float* S, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* bw,

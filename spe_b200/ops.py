@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import GemmArgs, check, lib, ptr, stream
 
 MAJOR_K, MAJOR_MN = 0, 1
-DT_BF16, DT_F32 = 0, 1
+DT_BF16, DT_F32, DT_F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_RELU_GRAD, ACT_GELU_GRAD = 0, 1, 2, 3, 4
 _ACT = {None: ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU}
 _ACT_GRAD = {"relu": ACT_RELU_GRAD, "gelu": ACT_GELU_GRAD}
@@ -136,7 +136,7 @@ def gemm(a, b, c, M, N, K, *, a_major=MAJOR_K, lda=None, b_major=MAJOR_K, ldb=No
     g = GemmArgs(M, N, K, batch[0], batch[1],
                  a.data_ptr(), a_major, lda, a_sb[0], a_sb[1],
                  b.data_ptr(), b_major, ldb, b_sb[0], b_sb[1],
-                 c.data_ptr(), (DT_F32 if c.dtype == torch.float32 else DT_BF16), ldc, c_sb[0], c_sb[1],
+                 c.data_ptr(), (DT_F32 if c.dtype == torch.float32 else (DT_F16 if c.dtype == torch.float16 else DT_BF16)), ldc, c_sb[0], c_sb[1],
                  alpha, ptr(bias), act, ptr(aux_in), ptr(aux_out), ld_aux,
                  ptr(gamma), ptr(residual), ldr, r_sb[0], r_sb[1],
                  split, split_stride)
@@ -878,6 +878,16 @@ def cam_std_reweight(P, q0, C, k0, N):
 
 
 _TH_FUSED = None
+_TH_S16 = None
+
+
+def _talking_s16():
+    """SPE_TH_S16 (default 1): keep the talking-heads logits S in fp16 in HBM (unfused pipeline)."""
+    global _TH_S16
+    if _TH_S16 is None:
+        import os
+        _TH_S16 = os.environ.get("SPE_TH_S16", "1") != "0"
+    return _TH_S16
 
 
 def _talking_fused_mode():
@@ -990,11 +1000,14 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         ld = rup(N, 8)
         scale = dh ** -0.5
         ctx.drop_p = float(drop_p)
-        S = torch.empty((B, H, N, ld), dtype=torch.float32, device=qkv.device)
+        # logits in fp16 where the row-staged kernels apply: the head mix rounds S to fp16 anyway, half the N^2 logit traffic / memory
+        s16 = _talking_s16() and lib().spe_talking_s16_supported(H, N, ld, ld) == 1
+        S = torch.empty((B, H, N, ld), dtype=torch.float16 if s16 else torch.float32, device=qkv.device)
         _qk_logits(q, k, H, scale, S, ld)
         A = torch.empty((B, H, N, ld), dtype=torch.bfloat16, device=qkv.device)
         stats = torch.empty((B * N, H), dtype=torch.float32, device=qkv.device)
-        check(lib().spe_talking_softmax_fwd(ptr(S), ptr(A), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, stream()))
+        fwd = lib().spe_talking_softmax_fwd_s16 if s16 else lib().spe_talking_softmax_fwd
+        check(fwd(ptr(S), ptr(A), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, stream()))
         out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
         keep = None
         if drop_p > 0.0:                   # attn_drop on the post-mix probabilities (cait.py:387): A is saved dropped, + the mask
@@ -1047,8 +1060,9 @@ class TalkingHeadsAttentionFn(torch.autograd.Function):
         junk = torch.zeros((2, H), dtype=torch.float32, device=qkv.device)      # the kernel's own bias sums (not used, see below)
         nws = lib().spe_talking_softmax_bwd_workspace(B, H, N, N)
         ws = torch.empty(nws, dtype=torch.float32, device=qkv.device)
-        check(lib().spe_talking_softmax_bwd(ptr(S), ptr(dA), ptr(dA), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, ptr(dWl_b), ptr(junk[0]),
-                                            ptr(dWw_b), ptr(junk[1]), ptr(ws), nws, stream()))
+        bwd = lib().spe_talking_softmax_bwd_s16 if S.dtype == torch.float16 else lib().spe_talking_softmax_bwd
+        check(bwd(ptr(S), ptr(dA), ptr(dA), ptr(Wl), ptr(bl), ptr(Ww), ptr(bw), ptr(stats), B, H, N, N, ld, ld, ptr(dWl_b), ptr(junk[0]),
+                  ptr(dWw_b), ptr(junk[1]), ptr(ws), nws, stream()))
         if fused:       # dQ, dK, dV from one pass over dS (= dA, in place) and A
             fused_attention_bwd_gemms(dA, A, q, k, dO, H, scale, dqkv[:, :, :D], dqkv[:, :, D:2 * D], dv)
         else:
