@@ -25,6 +25,9 @@ const char* spe_last_error(void);
 int spe_version(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t spe_launch_count(void);
+/* device-wide L1 / shared-memory split preference: 1 = prefer shared memory (no carve-out reconfiguration between the ~200 KB tcgen05
+ * kernels and the small row-wise kernels), 0 = driver default */
+int spe_set_cache_config(int mode);
 /* Optional device-side timing of kernel families with CUDA events on the launching stream (bench.py roofline).
  * Families: 0 gemm (work = algorithmic flops), 1 talking-softmax fwd, 2 talking-softmax bwd, 3 softmax,
  * 4 layernorm (work = algorithmic bytes), 5 matcher LSAP (work = images), 6 other, 7 batched attention GEMMs (QK^T / PV and

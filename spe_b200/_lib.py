@@ -74,6 +74,7 @@ class TalkingFusedBwdArgs(C.Structure):
 _SIGS = {
     "spe_version": (c_i, []),
     "spe_launch_count": (c_l, []),
+    "spe_set_cache_config": (c_i, [c_i]),
     "spe_prof_enable": (c_i, [c_i]),
     "spe_prof_collect": (c_i, [c_p, c_p, c_p]),
     "spe_prof_family_count": (c_i, []),
@@ -142,6 +143,9 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = L
+        mode = os.environ.get("SPE_CACHE_CONFIG", "")
+        if mode != "" and torch.cuda.is_available():
+            L.spe_set_cache_config(int(mode))
     return _lib
 
 

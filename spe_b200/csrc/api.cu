@@ -6,6 +6,12 @@ std::atomic<int64_t> g_spe_launches{0};
 extern "C" __attribute__((visibility("default"))) const char* spe_last_error(void) { return g_spe_err; }
 extern "C" __attribute__((visibility("default"))) int spe_version(void) { return 100; }
 extern "C" __attribute__((visibility("default"))) int64_t spe_launch_count(void) { return g_spe_launches.load(); }
+// Device-wide L1 / shared-memory split preference.  The tcgen05 kernels run with ~200 KB of shared memory per CTA, the small row-wise
+// kernels with none: every switch between the two carve-outs makes the SMs drain and reconfigure.  mode 1 = prefer shared memory for
+// every kernel that states no preference of its own (cudaFuncCachePreferShared), 0 = driver default.
+extern "C" __attribute__((visibility("default"))) int spe_set_cache_config(int mode) {
+    return cudaDeviceSetCacheConfig(mode ? cudaFuncCachePreferShared : cudaFuncCachePreferNone) == cudaSuccess ? 0 : -1;
+}
 
 // ------------------------------------------------------------------------------------------------
 // per-family event profiler (off by default; bench.py turns it on for the timed region)

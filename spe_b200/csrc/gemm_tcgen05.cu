@@ -314,6 +314,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // let the next kernel of the stream (if it was launched with programmatic stream serialization) start its prologue now; it
+    // blocks at its own griddepcontrol.wait until this grid has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;
     const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;            // first tile / tile stride of this CTA (pair)
     const int tstride = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -350,6 +353,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     if constexpr (CG2) cluster_sync_all();             // both CTAs' barriers are initialised before any cross-CTA signal
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch -- and the launch latency
+    // itself) overlaps the tail of the preceding GEMM in the stream; nothing before this point touches global memory.  The wait
+    // returns when the preceding grid has completed and flushed (no-op for an ordinary launch).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tile -> coordinates (n fastest: consecutive CTAs share the A rows in L2)
     // (every role decodes every tile: the divisions are multiply-shift with host-made magics -- real divisions cost each epilogue
@@ -794,6 +801,13 @@ int make_tmap_io(CUtensorMap* tm, const void* ptr, bool f32, int M, int N, int64
 
 struct IoMaps { CUtensorMap C, R, Xi, Xo; };
 
+// SPE_GEMM_PDL (default 1): launch GEMMs with programmatic stream serialization -- a GEMM that follows another GEMM in the stream
+// starts its prologue (and absorbs its launch latency) under the predecessor's tail.  ~11 us of a 13-25 us launch were fixed costs.
+bool gemm_pdl() {
+    static const bool on = [] { const char* e = getenv("SPE_GEMM_PDL"); return e == nullptr || atoi(e) != 0; }();
+    return on;
+}
+
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool CG2>
 int launch(const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const EpiParams& ep, cudaStream_t st) {
     constexpr size_t SMEM = (size_t)STAGES * (BM * BK * 2 + (CG2 ? BN / 2 : BN) * BK * 2) + EPI_SMEM + (2 * STAGES + 4 + NUM_EPI_WARPS) * 8 + 16 + 1024;
@@ -814,15 +828,32 @@ int launch(const CUtensorMap& tA, const CUtensorMap& tB, const IoMaps& io, const
         cfg.blockDim = dim3(NUM_THREADS);
         cfg.dynamicSmemBytes = SMEM;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = gemm_pdl() ? 2 : 1;
         SPE_CUDA(cudaLaunchKernelEx(&cfg, kfn, tA, tB, io.C, io.R, io.Xi, io.Xo, ep));
     } else {
         const int grid = ep.num_tiles < spe_num_sms() ? ep.num_tiles : spe_num_sms();
-        kfn<<<grid, NUM_THREADS, SMEM, st>>>(tA, tB, io.C, io.R, io.Xi, io.Xo, ep);
+        if (gemm_pdl()) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(NUM_THREADS);
+            cfg.dynamicSmemBytes = SMEM;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            SPE_CUDA(cudaLaunchKernelEx(&cfg, kfn, tA, tB, io.C, io.R, io.Xi, io.Xo, ep));
+        } else {
+            kfn<<<grid, NUM_THREADS, SMEM, st>>>(tA, tB, io.C, io.R, io.Xi, io.Xo, ep);
+        }
     }
     SPE_LAUNCHED();
     return 0;

@@ -26,8 +26,12 @@ def _setup(gold, device="cuda"):
     return cfg, params, images, targets, model, crit
 
 
-# global relative L2 error of the whole gradient vs the fp32 oracle, per golden case (measured values in the comments)
-GRAD_TOL = {"tiny_det": 5e-2, "tiny_refine": 5e-2, "tiny_two_branch": 5e-2, "tiny_h16": 5e-2, "cfg1_xxs24_224": 5e-2, "cfg2_s24_640": 5e-2}
+# Global relative L2 error of the whole gradient vs the fp32 oracle, per golden case.  The path computes in bf16 (activations and GEMM
+# operands; fp32 accumulation, fp32 residual streams and statistics): measured on B200 over several runs (split-K / atomics make the
+# low bits run-dependent): tiny_det 0.045, tiny_refine 0.023, tiny_two_branch 0.023, tiny_h16 0.028, cfg1 0.025-0.027, cfg2 0.048-0.051.
+# The bound is the measured value + ~30 %.  The largest per-parameter errors are the ReLU FFNs of the decoder (linear1: 0.12-0.14 at cfg2,
+# mask flips of bf16 pre-activations near zero over 2 x 6 layers) and the proj_w biases (sums of N^2 bf16 terms with heavy cancellation).
+GRAD_TOL = {"tiny_det": 6e-2, "tiny_refine": 3.5e-2, "tiny_two_branch": 3.5e-2, "tiny_h16": 4e-2, "cfg1_xxs24_224": 3.5e-2, "cfg2_s24_640": 6.5e-2}
 
 
 def nerr(a, b):
