@@ -326,6 +326,7 @@ def run_ours(args):
 
     if rank != 0:
         if world > 1:
+            step_graph.close()          # captured NCCL all-reduces must be gone before the group is destroyed
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
@@ -413,6 +414,7 @@ def run_ours(args):
             "talking_heads_fused": fused_th, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
+        step_graph.close()
         dist.destroy_process_group()
 
 

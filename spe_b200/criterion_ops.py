@@ -84,7 +84,8 @@ class StaticTargets(PackedTargets):
         self._staged = torch.cuda.Event() if pin else None
         self._staged_pending = False
 
-    def update(self, targets):
+    def update(self, targets, sync_num_boxes=True):
+        """sync_num_boxes=False: the caller all-reduces num_boxes for several StaticTargets at once (sync_num_boxes below)."""
         assert len(targets) == self.B, "StaticTargets: batch size changed"
         sizes = [int(t["labels"].shape[0]) for t in targets]
         if max(sizes, default=0) > self.cap:
@@ -120,7 +121,10 @@ class StaticTargets(PackedTargets):
         if self.img_label is not None and targets and "img_label" in targets[0]:
             self.img_label.copy_(torch.stack([t["img_label"] for t in targets]).float(), non_blocking=True)
         # 1 / clamp(all_reduce(num_boxes) / world, 1)   (conditional_detr.py:436-440), refreshed in place
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        if dist_on and not sync_num_boxes:
+            pass
+        elif dist_on:
             nb = torch.tensor([float(self.total)], dtype=torch.float32, device=self.device)
             torch.distributed.all_reduce(nb)
             self._inv_num_boxes.copy_(1.0 / torch.clamp(nb / torch.distributed.get_world_size(), min=1.0))
@@ -131,6 +135,18 @@ class StaticTargets(PackedTargets):
             self._staged.record()
             self._staged_pending = True
         return self
+
+
+def sync_num_boxes(static_targets):
+    """ONE all-reduce for the num_boxes normalisers (conditional_detr.py:436-440) of all the step's criteria."""
+    ts = [t for t in static_targets if t is not None]
+    if not ts or not (torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1):
+        return
+    nb = torch.tensor([float(t.total) for t in ts], dtype=torch.float32, device=ts[0].device)
+    torch.distributed.all_reduce(nb)
+    inv = 1.0 / torch.clamp(nb / torch.distributed.get_world_size(), min=1.0)
+    for i, t in enumerate(ts):
+        t._inv_num_boxes.copy_(inv[i:i + 1])
 
 
 def pack_targets(targets, device):

@@ -38,6 +38,13 @@ class FlatGradBuffer:
                     v.add_(g.to(v.dtype).view_as(v))
                 p.grad = v
 
+    def offset_of(self, param):
+        """element offset of `param`'s slice in the flat buffer (None if it is not in the buffer)"""
+        for p, v in zip(self.params, self.views):
+            if p is param:
+                return (v.data_ptr() - self.flat.data_ptr()) // self.flat.element_size()
+        return None
+
     def zero_(self):
         if self.mode == "views":
             self.flat.zero_()

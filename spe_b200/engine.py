@@ -7,7 +7,12 @@ cudaGraphLaunch, which is what keeps the step device-bound (eager, the Python/la
 ~70 ms of device work).  Inputs are copied into static buffers before each replay; the matcher, the losses and the gradient
 accumulation all run on the device with no host synchronisation, so the captured step is the complete step.
 
-The gradient all-reduce (one NCCL call on the flat buffer) stays outside the graph."""
+Gradient all-reduce (N > 1): the flat buffer is reduced in TWO buckets issued from inside the step (and captured with it): the
+detector-side slice (transformer, heads, query embeddings: 138 MB of 331 MB at cfg2) as soon as the backward pass reaches the backbone
+tap -- it then runs on NCCL's stream under the backbone's backward --, the backbone slice after the last kernel.  SPE_AR_OVERLAP=0
+falls back to one all-reduce after the step."""
+import os
+
 import torch
 
 from . import criterion_ops as CO
@@ -27,12 +32,33 @@ class TrainStep:
         self.shadows = ops.ShadowSet(model.parameters()) if refresh_shadows else None
         self._g = {}            # (B, H, W, cap) -> captured state
         self._side = None       # second stream for the refine criterion's matching
+        # bucketed all-reduce: the flat buffer must hold every non-backbone parameter before the first backbone parameter
+        self._split = None
+        if os.environ.get("SPE_AR_OVERLAP", "1") != "0" and self.gbuf.mode == "views":
+            names = [n for n, p in model.named_parameters() if p.requires_grad]
+            first_bb = next((i for i, n in enumerate(names) if n.startswith("backbone")), None)
+            if first_bb not in (None, 0) and all(n.startswith("backbone") for n in names[first_bb:]):
+                pbb = dict(model.named_parameters())[names[first_bb]]
+                self._split = self.gbuf.offset_of(pbb)
+        self._works = []
 
     # ---- the step body (identical in both modes) ----
+    def _dist(self):
+        return torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+
+    def _reduce_bucket(self, lo, hi):
+        flat = self.gbuf.flat
+        op = torch.distributed.ReduceOp.AVG if flat.is_cuda else torch.distributed.ReduceOp.SUM
+        self._works.append(torch.distributed.all_reduce(flat[lo:hi], op=op, async_op=True))
+
     def _body(self, images, T, T_refine):
         self.gbuf.zero_()
         if self.shadows is not None:
             self.shadows.refresh()
+        bucketed = self._split is not None and self._dist() and self.gbuf.flat.is_cuda
+        self._works = []
+        hooked = bucketed and os.environ.get("SPE_AR_OVERLAP", "1") != "2"       # "2": both buckets after the backward pass (no hook)
+        ops.set_grad_milestone("detector_grads_done", (lambda: self._reduce_bucket(0, self._split)) if hooked else None)
         out = self.model(images)
         m1 = m2 = None
         packed = isinstance(T, CO.PackedTargets) and (T_refine is None or isinstance(T_refine, CO.PackedTargets))
@@ -56,6 +82,17 @@ class TrainStep:
             ld2 = self.criterion_refine(out[1], T_refine, _matches=m2)
             loss = loss + sum(ld2[k] * wd[k] for k in ld2 if k in wd)
         loss.backward()
+        ops.set_grad_milestone("detector_grads_done", None)
+        if bucketed:
+            if not self._works:                       # the milestone did not fire (model without the tap): reduce everything now
+                self._reduce_bucket(0, self._split)
+            self._reduce_bucket(self._split, self.gbuf.flat.numel())
+            for w in self._works:
+                w.wait()                              # the step's stream waits for NCCL's stream (captured with the step in graph mode)
+            self._works = []
+            self._reduced = True
+        else:
+            self._reduced = False
         return loss.detach(), {k: v.detach() for k, v in ld.items()}, (None if ld2 is None else {k: v.detach() for k, v in ld2.items()})
 
     def __call__(self, samples, targets, targets_refine=None):
@@ -73,8 +110,16 @@ class TrainStep:
             res = self._body(samples, tg, tr)
         else:
             res = self._replay(samples, targets, targets_refine)
-        self.gbuf.all_reduce_mean()
+        if not getattr(self, "_reduced", False):
+            self.gbuf.all_reduce_mean()
         return res
+
+    def close(self):
+        """Drop the captured graphs.  With N > 1 they hold the gradient all-reduce: NCCL keeps a communicator alive (and
+        destroy_process_group() waiting) for as long as a captured collective exists, so call this before tearing the group down."""
+        self._g.clear()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     # ---- graph mode ----
     def _replay(self, images, targets, targets_refine):
@@ -90,9 +135,10 @@ class TrainStep:
             st = self._capture(images, tg, tr, cap)
             self._g[key] = st
         st["images"].copy_(images, non_blocking=True)
-        st["T"].update(tg)
+        st["T"].update(tg, sync_num_boxes=False)
         if st["Tr"] is not None:
-            st["Tr"].update(tr)
+            st["Tr"].update(tr, sync_num_boxes=False)
+        CO.sync_num_boxes([st["T"], st["Tr"]])          # one 8-byte all-reduce for both criteria (N > 1)
         st["graph"].replay()
         return st["out"]
 

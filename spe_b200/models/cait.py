@@ -239,6 +239,7 @@ class TSCAM_cait(nn.Module):
         for i, blk in enumerate(self.blocks):                                                            # :627-630
             x = blk(x)
             if i == self.layer_to_det:
+                ops.grad_milestone(x, "detector_grads_done")       # backward: the transformer / head gradients are final from here on
                 x_feat, x_feat16 = ops.layernorm(x, self.norm_to_det.weight, self.norm_to_det.bias, self.norm_to_det.eps, want_f32=True)
         cls = torch.cat((self.cls_token.expand(B, -1, -1), self.extra_cls_token.expand(B, -1, -1)), dim=1)     # :620-622
         for i, blk in enumerate(self.blocks_token_only):                                                 # :635-637
@@ -306,6 +307,7 @@ class TSCAM_cait_two_branch(TSCAM_cait):
                 x_feat = x
         for blk in self.blocks_det:                                                                      # :779-780
             x_feat = blk(x_feat)
+        ops.grad_milestone(x_feat, "detector_grads_done")
         x_feat, x_feat16 = ops.layernorm(x_feat, self.norm_det.weight, self.norm_det.bias, self.norm_det.eps, want_f32=True)   # :782
         cls = torch.cat((self.cls_token.expand(B, -1, -1), self.extra_cls_token.expand(B, -1, -1)), dim=1)
         for i, blk in enumerate(self.blocks_token_only):                                                 # :787-789

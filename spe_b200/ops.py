@@ -584,6 +584,29 @@ def cast_f32(a):
     return CastF32Fn.apply(a)
 
 
+# ---- backward milestones -------------------------------------------------------------------------
+# A model marks a tensor whose gradient becomes ready at a known point of the backward pass (e.g. the backbone tap: once its gradient
+# exists, every detector-side parameter gradient is final); engine.TrainStep hangs the first bucket of the gradient all-reduce there.
+_MILESTONES = {}
+
+
+def set_grad_milestone(name, fn):
+    if fn is None:
+        _MILESTONES.pop(name, None)
+    else:
+        _MILESTONES[name] = fn
+
+
+def grad_milestone(x, name):
+    fn = _MILESTONES.get(name)
+    if fn is not None and x.requires_grad:
+        def _hook(g, _fn=fn):
+            _fn()
+            return g
+        x.register_hook(_hook)
+    return x
+
+
 # ---- dropout (cait.py:36-38,294,449; transformer.py:268-270,333-337; attention.py:371) -----------------------------------------
 # The BASELINE configurations run p = 0; the reference's training scripts do not (scripts/run_coco17.py:30-32: backbone_drop_rate
 # 0.07, drop_path_rate 0.2, drop_attn_rate 0.05; main.py:73: decoder dropout 0.1).  With a non-zero rate in train() mode the modules

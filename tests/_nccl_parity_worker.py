@@ -11,6 +11,8 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("SPE_TEST_DUMP_AFTER", "240")), exit=True)     # a hang prints where, then ends
     from oracle import spe_oracle as O
     from spe_b200 import factory
     from spe_b200.dp import FlatGradBuffer
@@ -59,6 +61,12 @@ def main():
     ok = err_loss < 2e-3 and num / den < 5e-3 and same == 0.0
     print("rank %d loss %.6f (avg %.6f vs %.6f, rel %.2e) grad rel err %.2e identical-across-ranks %s -> %s"
           % (rank, float(loss), float(l), ref_loss, err_loss, num / den, same == 0.0, "OK" if ok else "FAIL"), flush=True)
+    # second step (graph mode: a pure replay, the bucketed all-reduce captured inside it) must land on the same gradients
+    step(images[sl].to(dev), tg[sl], tr[sl])
+    err2 = float((step.gbuf.flat - ref_flat).norm()) / den
+    if err2 > 5e-3:
+        ok = False
+    print("rank %d second step grad rel err %.2e  bucketed all-reduce split at %s" % (rank, err2, step._split), flush=True)
     for k in ("loss_ce", "loss_bbox", "loss_giou"):
         v = ld[k].detach().clone().reshape(1)
         dist.all_reduce(v, op=dist.ReduceOp.AVG)
@@ -66,6 +74,7 @@ def main():
             ok = False
             print("rank %d %s avg %.6f vs %.6f FAIL" % (rank, k, float(v), ref_ld[k]), flush=True)
     dist.barrier()
+    step.close()            # captured collectives keep the communicator (and destroy_process_group) waiting
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
