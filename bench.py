@@ -2,13 +2,15 @@
 """bench.py -- images/sec of the SPE hot path (fwd + criterion incl. Hungarian matcher + bwd [+ grad all-reduce])
 on synthetic 3x640x640 images, TSCAM-S24 + 6enc/6dec conditional DETR, 300 queries, 81 logits (BASELINE configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 8]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg4] [--batch B]
     (N > 1: launched by torch.distributed.run, one rank per GPU)
 
 A step = model(images) -> criterion(out[0], targets) + criterion_refine(out[1], targets+scores) -> backward of the
-weighted loss sum -> (N > 1) ONE NCCL all-reduce of the flat gradient buffer.  No optimizer step, no dataloader
-(the metric BASELINE.json names).  `--impl reference` times the reference's own algorithm on the host CPU cores
-(the fp32 PyTorch restatement in oracle/, pinned to the unmodified reference by tests/golden) on the same config.
+weighted loss sum -> (N > 1) the flat gradient buffer all-reduced over NCCL in two buckets, the first one under the backbone's
+backward (engine.TrainStep).  No optimizer step, no dataloader (the metric BASELINE.json names).  `--impl reference` times the
+UNMODIFIED reference (staged verbatim under baseline/_ref by baseline/stage_reference.py, imported through oracle/ref_shim.py) on the
+host CPU cores on the same config -- the oracle port when it is not staged -- and adds an informational eager-on-GPU timing of it.
+`--config cfg4` = BASELINE configs[3] (TSCAM-M36, 800x1333, batch 1 per GPU); the default cfg2 is the metric's configuration.
 """
 import argparse
 import json
@@ -31,6 +33,20 @@ def cfg2():
     return SimpleNamespace(embed_dim=384, depth=24, num_heads=8, img_classes=80, patch=16, layer_to_det=23, depth_token_only=2,
                            mlp_ratio=4.0, pos_grid=(50, 84), det_heads=8, ffn=2048, enc_layers=6, dec_layers=6, num_queries=300,
                            det_classes=81, num_refines=1, ln_eps_backbone=1e-6, ln_eps_detr=1e-5)
+
+
+def cfg4():
+    """BASELINE configs[3]: TSCAM-M36 (D 768, depth 36, 16 heads, tap after block 35), 800x1333 -> 50 x 83 = 4150 tokens."""
+    c = cfg2()
+    c.embed_dim, c.depth, c.num_heads, c.layer_to_det = 768, 36, 16, 35
+    return c
+
+
+CONFIGS = {
+    "cfg2": dict(cfg=cfg2, hw=(640, 640), batch=8, workload=WORKLOAD),
+    "cfg4": dict(cfg=cfg4, hw=(800, 1333), batch=1,
+                 workload="cfg4: TSCAM-M36(D768,depth36,H16)+6enc/6dec cond-DETR, 300 queries, 81 logits, 3x800x1333 synthetic"),
+}
 
 
 def synth_targets(batch, seed, repeat=5, det_classes=81):
@@ -199,12 +215,84 @@ def cpu_reference_step_fn():
     return step
 
 
+def reference_step_fn(device, batch):
+    """The UNMODIFIED reference (models/, util/ staged verbatim under baseline/_ref by baseline/stage_reference.py, imported through
+    oracle/ref_shim.py) on the same config, parameters (oracle.make_params(CFG2, 0)), losses and targets as our arm."""
+    from oracle import ref_shim, spe_oracle as O
+    cfg = O.CFG2
+    ref, model = ref_shim.build_reference_model(cfg, O.make_params(cfg, 0))
+    model.train().to(device)
+    wd = O.default_weight_dict(cfg)
+    losses = ("labels", "boxes", "cardinality")
+    crit = ref_shim.build_reference_criterion(ref, cfg, wd, losses, gamma=2.0).to(device)
+    crit_r = ref_shim.build_reference_criterion(ref, cfg, wd, losses, gamma=2.0, refine=True).to(device)
+    g = torch.Generator().manual_seed(0)
+    images = torch.randn(batch, 3, 640, 640, generator=g).to(device)
+    targets = [{k: v.to(device) for k, v in t.items()} for t in synth_targets(batch, 0)]
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        out = model(images)
+        ld = crit(out[0], targets)
+        ld2 = crit_r(out[1], targets)
+        loss = sum(ld[k] * wd[k] for k in ld if k in wd) + sum(ld2[k] * wd[k] for k in ld2 if k in wd)
+        loss.backward()
+        return float(loss)
+
+    return step
+
+
+def reference_gpu_eager(batch, steps=3, warmup=2):
+    """Informational same-box comparator: the reference's own eager PyTorch code on the B200, fp32 storage
+    with TF32 matmuls allowed (the most favourable stock setting).  Not the reference arm's value: that is the CPU line."""
+    if not torch.cuda.is_available():
+        return None
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        b = batch
+        while b >= 1:
+            try:
+                step = reference_step_fn(torch.device("cuda", 0), b)
+                for _ in range(warmup):
+                    step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                return {"value": 1e3 * b / ms, "unit": "images/s", "ms_per_step": ms, "batch": b, "steps": steps,
+                        "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                        "precision": "fp32 parameters/activations, TF32 tensor-core matmuls allowed, eager PyTorch, scipy LSAP on the host",
+                        "note": "informational: the stock reference code on this B200; the arm's value/e2e are the CPU run"}
+            except torch.OutOfMemoryError:
+                step = None
+                torch.cuda.empty_cache()
+                b //= 2
+        return {"unavailable": "out of memory at batch 1"}
+    except Exception as e:                                        # informational leg: never fail the arm
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import ref_shim
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_reference_step_fn()
+    real = ref_shim.available()
+    if real:
+        step = reference_step_fn(torch.device("cpu"), 1)
+        kind, sample = "reference", "the unmodified reference (baseline/_ref via oracle/ref_shim.py): model fwd + SetCriterion + SetCriterionRefine (scipy LSAP) + bwd"
+    else:
+        step = cpu_reference_step_fn()
+        kind, sample = "port", "oracle/spe_oracle.py fwd+criterion(scipy LSAP)+bwd (reference not staged: run baseline/stage_reference.py in the build container)"
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -218,9 +306,12 @@ def run_reference(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_step": "1 image (bounded sample of the bs=8 step)", "losses": "det(out[0]) + refine(out[1])",
                        "device": "host CPU"},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "oracle/spe_oracle.py fwd+criterion(scipy LSAP)+bwd, bs=1 per step, fp32, torch threads=%d" % cores},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind,
+                             "sample": sample + ", bs=1 per step, fp32, torch threads=%d" % cores},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if real and args.ref_gpu:
+        step = None
+        line["reference_gpu_eager"] = reference_gpu_eager(args.batch or 8)
     print(json.dumps(line), flush=True)
 
 
@@ -238,7 +329,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = cfg2()
+    conf = CONFIGS[args.config]
+    cfg = conf["cfg"]()
+    IH, IW = conf["hw"]
+    workload = conf["workload"]
+    if args.batch is None:
+        args.batch = conf["batch"]
     torch.manual_seed(42 + rank)                                   # main.py:161 rank-dependent seed
     model = factory.build_detector(cfg, dev)
     # the reference zero-inits the last bbox layer and LayerScale=1e-5; keep the architecture's own random init
@@ -260,7 +356,7 @@ def run_ours(args):
 
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
-    host_images = torch.randn(B, 3, 640, 640, generator=g).pin_memory()
+    host_images = torch.randn(B, 3, IH, IW, generator=g).pin_memory()
     targets_host = synth_targets(B, 7 + rank)
     dev_images = host_images.to(dev)
     dev_targets = [{k: v.to(dev) for k, v in t.items()} for t in targets_host]
@@ -370,7 +466,7 @@ def run_ours(args):
     # the fraction north_star asks for: attention-GEMM roofline.  Algorithmic FLOPs = SURVEY section 8(d): QK^T + PV only
     # (L 4N^2D + E 4N^2Dd + P Ld (4Q^2Dd + 6QNDd) per image forward, x3 for forward + backward; recompute inside the fused kernels and
     # the head mixes are NOT counted), over the device time of every kernel that implements attention (profiled pass, serialised).
-    N_tok, Dm, Q = (640 // cfg.patch) ** 2, cfg.embed_dim, cfg.num_queries
+    N_tok, Dm, Q = (IH // cfg.patch) * (IW // cfg.patch), cfg.embed_dim, cfg.num_queries
     att_fwd = cfg.depth * 4 * N_tok * N_tok * Dm + cfg.enc_layers * 4 * N_tok * N_tok * Dm + \
         (cfg.num_refines + 1) * cfg.dec_layers * (4 * Q * Q * Dm + 6 * Q * N_tok * Dm)
     att_fams = ("gemm_attention", "talking_softmax_fwd", "talking_softmax_bwd", "attention_fused", "softmax")
@@ -389,24 +485,28 @@ def run_ours(args):
     matcher = matcher_microbench(dev)
     fused_th = None
     try:
-        fused_th = fused_talking_heads_microbench(dev, cfg, B)
+        fused_th = fused_talking_heads_microbench(dev, cfg, B) if args.config == "cfg2" else {"unsupported": "csrc/talking_fused.cu covers H in {4, 8}"}
     except Exception as e:                                        # informational block: never fails the bench line
         fused_th = {"error": str(e)[:200]}
     cpu = None
-    if args.cpu_baseline and world == 1:
+    if args.cpu_baseline and world == 1 and args.config == "cfg2":     # the CPU legs are cfg2's (a cfg4 CPU step takes minutes)
         torch.set_num_threads(os.cpu_count() or 1)
-        cstep = cpu_reference_step_fn()
+        from oracle import ref_shim
+        real = ref_shim.available()                                # baseline/_ref staged: time the unmodified reference, else the oracle port
+        cstep = reference_step_fn(torch.device("cpu"), 1) if real else cpu_reference_step_fn()
+        cstep()                                                     # one warm-up step (allocator, thread pool), then two timed
         t0 = time.perf_counter()
-        cstep()
-        dt = time.perf_counter() - t0
-        cpu = {"value": 1.0 / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "oracle (fp32 PyTorch restatement, scipy LSAP): ONE cold bs=1 fwd+criteria+bwd step of the same config (%.1f s)" % dt,
+        cstep(); cstep()
+        dt = (time.perf_counter() - t0) / 2
+        cpu = {"value": 1.0 / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "reference" if real else "port",
+               "sample": ("the unmodified reference (baseline/_ref)" if real else "oracle (fp32 PyTorch restatement, scipy LSAP)")
+                         + ": bs=1 fwd+criteria+bwd steps of the same config, 1 warm-up + 2 timed (%.1f s each)" % dt,
                "matcher_us_per_img": matcher_cpu_us_per_img(), "matcher_sample": "cfg5 shapes, 24 images, torch cost matrix + scipy LSAP per image"}
     line = {"metric": "images/sec fwd+bwd", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": imgs, "parallelism": "dp%d" % world,
+            "config": {"workload": workload, "batch_per_gpu": B, "global_batch": imgs, "parallelism": "dp%d" % world,
                        "losses": "det(out[0]) + refine(out[1]), 12 Hungarian matchings/step, hung_match_ratio 5",
-                       "l2": "working set per step >> 126 MB L2 (activations ~20 GB), no explicit flush",
+                       "l2": "working set per step >> 126 MB L2 (activations of one step: tens of GB), no explicit flush",
                        "weights": "random init (architecture default)",
                        "step": ("engine.TrainStep, whole step captured in a CUDA graph and replayed" if not args.eager else "engine.TrainStep, eager launches")},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -424,8 +524,10 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: 8 for cfg2, 1 for cfg4)")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="cfg2 = the configuration BASELINE.json's metric is quoted on")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-ref-gpu", dest="ref_gpu", action="store_false", help="reference arm: skip the informational eager-on-GPU timing")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

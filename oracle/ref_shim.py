@@ -1,7 +1,7 @@
 """Import the UNMODIFIED reference (/root/reference) on a modern torch without timm.
 
-TEST INFRASTRUCTURE ONLY, and only usable in the build container (the GPU box has no
-/root/reference).  Used by tests/golden/make_golden.py to produce the committed golden vectors that
+TEST / BASELINE INFRASTRUCTURE ONLY.  The GPU box has no /root/reference: there the shim only finds the staged
+copy under baseline/_ref/ (bench.py --impl reference); no test marked gpu may depend on it.  Used by tests/golden/make_golden.py to produce the committed golden vectors that
 pin oracle/spe_oracle.py, and by tests that are skipped when the reference is absent.
 Recipe = SURVEY.md Appendix D: a fake `timm` (Mlp / PatchEmbed / DropPath / trunc_normal_ /
 register_model / create_model) and the `_LinearWithBias` alias removed from torch.
@@ -13,7 +13,22 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("SPE_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _find_root():
+    """$SPE_REFERENCE_ROOT, else /root/reference (build container), else the verbatim copy baseline/stage_reference.py makes
+    (git-ignored; the only form in which the reference reaches the GPU box, for bench.py --impl reference)."""
+    env = os.environ.get("SPE_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isdir(os.path.join(cand, "models")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

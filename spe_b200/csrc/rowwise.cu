@@ -1570,6 +1570,12 @@ static int talking_fwd_launch(const void* Sv, void* A, const float* Wl, const fl
     return 0;
 }
 
+// SPE_TH16_GENERIC=1: keep H = 16 on the CUDA-core kernels (A/B switch)
+static bool talking_h16_on(int H) {
+    static const bool off = getenv("SPE_TH16_GENERIC") != nullptr && getenv("SPE_TH16_GENERIC")[0] == '1';
+    return H == 16 && !off;
+}
+
 extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(const float* S, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats,
                                        int B, int H, int Nq, int Nk, int64_t ldS, int64_t ldA, void* stream) {
     SPE_CHECK(S && A && Wl && bl && Ww && bw && B > 0 && Nq > 0 && Nk > 0, "spe_talking_softmax_fwd: bad argument");
@@ -1579,8 +1585,9 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(co
         case 4: return talking_fwd_launch<4>(S, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
         case 8: return talking_fwd_launch<8>(S, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
         default: {
-            // other head counts (H = 16 of CaiT-M36, 6 / 12 of the XS variants): CUDA-core formulation in talking_generic.cu
+            // H = 16 (CaiT-M36): mma.sync formulation in talking_h16.cu; 6 / 12 of the XS variants: CUDA cores, talking_generic.cu
             SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 6.0, ST(stream));
+            if (talking_h16_on(H)) return spe_talking_h16_fwd(S, 0, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
             return spe_talking_generic_fwd(S, A, Wl, bl, Ww, bw, stats, B, H, Nq, Nk, ldS, ldA, ST(stream));
         }
     }
@@ -1588,8 +1595,9 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(co
 
 // fp16 logits (S from spe_gemm with c_dtype = SPE_DT_F16): row-staged kernels only, H in {2, 4, 8}
 extern "C" __attribute__((visibility("default"))) int spe_talking_s16_supported(int H, int Nk, int64_t ldS, int64_t ldA) {
-    if (H != 2 && H != 4 && H != 8) return 0;
     if (ldS % 8 != 0 || ldA % 8 != 0 || ldS < Nk || ldA < Nk) return 0;
+    if (talking_h16_on(H)) return 1;                     // streamed from global memory: no row-size limit
+    if (H != 2 && H != 4 && H != 8) return 0;
     return talking_fwd_smem16(H, (int)ldS) <= 100 * 1024 + 4096 && talking_bwd_smem16(H, (int)ldS, (int)ldA) <= 104 * 1024 ? 1 : 0;
 }
 extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd_s16(const void* S16, void* A, const float* Wl, const float* bl, const float* Ww,
@@ -1597,6 +1605,10 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd_s1
                                                                                   int64_t ldA, void* stream) {
     SPE_CHECK(S16 && A && Wl && bl && Ww && bw && stats && B > 0 && Nq > 0 && Nk > 0, "spe_talking_softmax_fwd_s16: bad argument");
     SPE_CHECK(spe_talking_s16_supported(H, Nk, ldS, ldA), "spe_talking_softmax_fwd_s16: unsupported shape H=%d Nk=%d", H, Nk);
+    if (H == 16) {
+        SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 4.0, ST(stream));
+        return spe_talking_h16_fwd(S16, 1, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
+    }
     switch (H) {
         case 2: return talking_fwd_launch<2>(S16, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream), true);
         case 4: return talking_fwd_launch<4>(S16, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream), true);
@@ -1666,6 +1678,17 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd_s1
     SPE_CHECK(S16 && dA && dS && Wl && bl && Ww && stats && dWl && dbl && dWw && dbw && workspace, "spe_talking_softmax_bwd_s16: null argument");
     SPE_CHECK(spe_talking_s16_supported(H, Nk, ldS, ldA), "spe_talking_softmax_bwd_s16: unsupported shape H=%d Nk=%d", H, Nk);
     SPE_CHECK(workspace_floats >= spe_talking_softmax_bwd_workspace(B, H, Nq, Nk), "spe_talking_softmax_bwd_s16: workspace too small");
+    if (H == 16) {
+        const int grid = spe_talking_h16_grid(B, Nq);
+        {
+            SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * 6.0, ST(stream));
+            if (spe_talking_h16_bwd(S16, 1, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, workspace, ST(stream))) return -1;
+        }
+        const int NP = 2 * H * H + 2 * H;
+        talking_bwd_finalize_kernel<<<(NP + 7) / 8, 256, 0, ST(stream)>>>(workspace, grid, H, dWl, dbl, dWw, dbw);
+        SPE_LAUNCHED();
+        return 0;
+    }
     switch (H) {
         case 2: return talking_bwd_launch<2>(S16, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream), true);
         case 4: return talking_bwd_launch<4>(S16, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream), true);
@@ -1685,10 +1708,12 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd(co
         case 4: return talking_bwd_launch<4>(S, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
         case 8: return talking_bwd_launch<8>(S, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
         default: {
-            const int grid = spe_talking_generic_grid(B, Nq);
+            const int grid = talking_h16_on(H) ? spe_talking_h16_grid(B, Nq) : spe_talking_generic_grid(B, Nq);
             {
                 SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * 8.0, ST(stream));
-                if (spe_talking_generic_bwd(S, dA, dS, Wl, bl, Ww, stats, B, H, Nq, Nk, ldS, ldA, workspace, ST(stream))) return -1;
+                if (talking_h16_on(H)) {
+                    if (spe_talking_h16_bwd(S, 0, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, workspace, ST(stream))) return -1;
+                } else if (spe_talking_generic_bwd(S, dA, dS, Wl, bl, Ww, stats, B, H, Nq, Nk, ldS, ldA, workspace, ST(stream))) return -1;
             }
             const int NP = 2 * H * H + 2 * H;
             talking_bwd_finalize_kernel<<<(NP + 7) / 8, 256, 0, ST(stream)>>>(workspace, grid, H, dWl, dbl, dWw, dbw);

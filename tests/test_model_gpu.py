@@ -80,13 +80,23 @@ def test_detector_matches_reference_golden(golden_dir, name):
     for lvl, gidx in zip(levels, gold["indices"]):
         mine = crit.matcher(lvl, tg_dev)
         ref = O.hungarian_match(lvl["pred_logits"].detach().float().cpu(), lvl["pred_boxes"].detach().float().cpu(), targets)
-        for (i, j), (ri, rj), (gi, gj) in zip(mine, ref, gidx):
+        for b, ((i, j), (ri, rj), (gi, gj)) in enumerate(zip(mine, ref, gidx)):
             assert i.dtype == torch.int64 and not i.is_cuda
             assert torch.equal(i, ri) and torch.equal(j, rj)
             # vs the reference's golden indices (computed from ITS fp32 outputs): identical up to the choice among
             # exact-duplicate GT boxes (hung_match_ratio repeats are exactly tied; our bf16 outputs perturb the path)
             rep = gold["meta"]["repeat"]
-            assert torch.equal(i, gi) and torch.equal(j // rep, gj // rep)
+            if torch.equal(i, gi) and torch.equal(j // rep, gj // rep):
+                continue
+            # a different assignment is legitimate only where the costs are tied within the bf16 noise of our outputs (300 random-init
+            # queries at cfg2 do produce such near-ties): the reference's assignment must then be optimal on OUR cost matrix to 1e-3 of
+            # the total cost, and differ in a small minority of the pairs
+            c = O.match_cost(lvl["pred_logits"][b].detach().float().cpu(), lvl["pred_boxes"][b].detach().float().cpu(),
+                             targets[b]["labels"], targets[b]["boxes"])
+            ours, theirs = float(c[i, j].sum()), float(c[gi, gj].sum())
+            ndiff = len(set(i.tolist()) ^ set(gi.tolist()))
+            print("MATCH near-tie %s image %d: cost ours %.6f reference's %.6f, %d of %d queries differ" % (name, b, ours, theirs, ndiff // 2, len(i)))
+            assert theirs - ours <= 1e-3 * max(1.0, abs(ours)) and ndiff <= max(2, len(i) // 10), (ours, theirs, ndiff)
     # ---- backward: gradients vs the oracle's (fp32 CPU autograd) on the same parameters
     wd = crit.weight_dict
     loss = sum(ld[k] * wd[k] for k in ld if k in wd)
