@@ -330,6 +330,50 @@ int spe_bce_logits(const float* x, const float* y, int64_t n, float* out, float*
 /* Pairwise IoU / GIoU (util/box_ops.py:33-74): a f32 [N,4], b f32 [M,4] xyxy -> iou/giou/union f32 [N,M] */
 int spe_box_iou_pairwise(const float* a, int N, const float* b, int M, float* iou, float* uni, float* giou, void* stream);
 
+/* GT jitter + repeat of SetCriterion.forward in training mode (models/conditional_detr.py:410-431), device side.
+ *   in : boxes f32 [sumG,4] cxcywh, labels i32 [sumG], scores f32 [sumG] or NULL, offsets i32 [B+1] (CSR over images; sumG = offsets[B]
+ *        is read on the device, cap_total >= sumG sizes the launch)
+ *   out: ratio rows per GT box: the first min(ratio-1, #kept) of n_try candidates box * U(1-jitter, 1+jitter)^4 with IoU(candidate, box) >
+ *        iou_thr, in candidate order, then the original box; labels / scores repeated; offsets_out = ratio * offsets; counts_out (may be
+ *        NULL) = ratio * per-image counts.
+ *   rng_state: device u64[2] {seed, launch counter} -- the kernel advances the counter, so graph replays draw fresh candidates;
+ *   ticket: device u32 scratch, zero-initialised once. */
+int spe_gt_jitter_repeat(const float* boxes, const int32_t* labels, const float* scores, const int32_t* offsets, int B, int cap_total,
+                         int ratio, float jitter, int n_try, float iou_thr, uint64_t* rng_state, float* boxes_out, int32_t* labels_out,
+                         float* scores_out, int32_t* offsets_out, int32_t* counts_out, uint32_t* ticket, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step on the flat fp32 buffers: clip_grad_norm_ (engine.py:163-164) + torch.optim.AdamW with the three
+ * learning-rate groups of main.py:177-190.  No host synchronisation: step count, bias corrections, clip coefficient and the
+ * learning rates are device scalars.
+ * ------------------------------------------------------------------------------------------- */
+/* out[0] = sum_i x[i]^2 (deterministic two-stage reduction); workspace: spe_sumsq_workspace_floats() floats */
+int64_t spe_sumsq_workspace_floats(void);
+int spe_sumsq_f32(const float* x, int64_t n, float* out, float* workspace, void* stream);
+/* state f32[4] = {beta1^t, beta2^t, clip coefficient, t}: initialise to {1, 1, 1, 0}; tick advances t by one step and sets the clip
+ * coefficient min(1, max_norm / (sqrt(grad_sumsq[0]) + 1e-6)) (1 when grad_sumsq is NULL or max_norm <= 0) */
+int spe_adamw_tick(float* state, float beta1, float beta2, const float* grad_sumsq, float max_norm, void* stream);
+#define SPE_ADAMW_MAX_SEGMENTS 16
+typedef struct {
+    float* p;                 /* parameters  f32[n]  (updated in place) */
+    const float* g;           /* gradients   f32[n]  (multiplied by the clip coefficient on the fly) */
+    float* m;                 /* exp_avg     f32[n] */
+    float* v;                 /* exp_avg_sq  f32[n] */
+    int64_t n;                /* multiple of 4 */
+    int nseg;                 /* the buffer is nseg contiguous segments, each belonging to one parameter group */
+    int64_t seg_end[SPE_ADAMW_MAX_SEGMENTS];   /* exclusive end offsets, increasing, multiples of 4, last == n */
+    int32_t seg_group[SPE_ADAMW_MAX_SEGMENTS];
+    const float* lr;          /* device f32[groups] */
+    const float* wd;          /* device f32[groups] (decoupled weight decay) */
+    float beta1, beta2, eps;
+    const float* state;       /* device f32[4], see spe_adamw_tick */
+    float* g_out;             /* optional: the clipped gradients (may alias g), what clip_grad_norm_ leaves in .grad */
+    void* shadow_bf16;        /* optional: bf16 copy of the updated parameters, bf16[n] */
+} spe_adamw_args;
+int spe_adamw_flat(const spe_adamw_args* args, void* stream);
+/* x *= clip coefficient (state[2]): clip_grad_norm_ without an optimizer step */
+int spe_scale_by_clip_coef(float* x, int64_t n, const float* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

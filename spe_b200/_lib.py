@@ -71,7 +71,19 @@ class TalkingFusedBwdArgs(C.Structure):
                 ("dqkv", c_p), ("dqkv_ld", c_l), ("dWl", c_p), ("dWw", c_p), ("workspace", c_p), ("workspace_bytes", c_l)]
 
 
+class AdamwArgs(C.Structure):
+    _fields_ = [("p", c_p), ("g", c_p), ("m", c_p), ("v", c_p), ("n", c_l), ("nseg", c_i),
+                ("seg_end", c_l * 16), ("seg_group", C.c_int32 * 16), ("lr", c_p), ("wd", c_p),
+                ("beta1", c_f), ("beta2", c_f), ("eps", c_f), ("state", c_p), ("g_out", c_p), ("shadow_bf16", c_p)]
+
+
 _SIGS = {
+    "spe_gt_jitter_repeat": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "spe_sumsq_workspace_floats": (c_l, []),
+    "spe_sumsq_f32": (c_i, [c_p, c_l, c_p, c_p, c_p]),
+    "spe_adamw_tick": (c_i, [c_p, c_f, c_f, c_p, c_f, c_p]),
+    "spe_adamw_flat": (c_i, [C.POINTER(AdamwArgs), c_p]),
+    "spe_scale_by_clip_coef": (c_i, [c_p, c_l, c_p, c_p]),
     "spe_version": (c_i, []),
     "spe_launch_count": (c_l, []),
     "spe_set_cache_config": (c_i, [c_i]),

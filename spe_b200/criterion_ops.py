@@ -64,6 +64,7 @@ class StaticTargets(PackedTargets):
         self.max_g = self.cap
         self.device = device
         ct = max(self.B * self.cap, 1)
+        self.cap_total = ct
         pin = torch.cuda.is_available()
         self._h_labels = torch.zeros(ct, dtype=torch.int32, pin_memory=pin)
         self._h_boxes = torch.zeros(ct, 4, dtype=torch.float32, pin_memory=pin)
@@ -120,7 +121,16 @@ class StaticTargets(PackedTargets):
         self.counts.copy_(self._h_cnt, non_blocking=True)
         if self.img_label is not None and targets and "img_label" in targets[0]:
             self.img_label.copy_(torch.stack([t["img_label"] for t in targets]).float(), non_blocking=True)
-        # 1 / clamp(all_reduce(num_boxes) / world, 1)   (conditional_detr.py:436-440), refreshed in place
+        self.set_num_boxes(sync_num_boxes, staged=True)
+        if self._staged is not None:
+            self._staged.record()
+            self._staged_pending = True
+        return self
+
+    def set_num_boxes(self, sync_num_boxes=True, staged=False):
+        """1 / clamp(all_reduce(num_boxes) / world, 1)   (conditional_detr.py:436-440) from the host-side count self.total, refreshed in
+        place.  staged: called from update(), which guards the pinned staging word with its event; other callers copy from a fresh
+        pageable scalar."""
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
         if dist_on and not sync_num_boxes:
             pass
@@ -129,12 +139,51 @@ class StaticTargets(PackedTargets):
             torch.distributed.all_reduce(nb)
             self._inv_num_boxes.copy_(1.0 / torch.clamp(nb / torch.distributed.get_world_size(), min=1.0))
         else:
-            self._h_inv[0] = 1.0 / max(float(self.total), 1.0)
-            self._inv_num_boxes.copy_(self._h_inv, non_blocking=True)
-        if self._staged is not None:
-            self._staged.record()
-            self._staged_pending = True
-        return self
+            inv = 1.0 / max(float(self.total), 1.0)
+            if staged:
+                self._h_inv[0] = inv
+                self._inv_num_boxes.copy_(self._h_inv, non_blocking=True)
+            else:
+                self._inv_num_boxes.copy_(torch.tensor([inv], dtype=torch.float32))
+
+
+class JitterRng:
+    """Device-side generator state of spe_gt_jitter_repeat: u64 {seed, launch counter} + the kernel's ticket word."""
+
+    def __init__(self, device, seed=None):
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # follows torch.manual_seed like the reference's uniform_ draws
+        self.state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def jitter_repeat(T, ratio, jitter, rng, n_try=1000, iou_thr=0.7, out=None):
+    """conditional_detr.py:410-431 on packed device targets: every GT box -> `ratio` rows (up to ratio-1 accepted jittered copies, then
+    the box itself), labels / scores repeated.  Returns a PackedTargets over new device arrays (`out`: write into an existing object's
+    arrays -- StaticTargets).  No host synchronisation."""
+    if not T.boxes.is_cuda:
+        raise RuntimeError("spe_b200 GT jitter needs CUDA tensors (no CPU fallback exists)")
+    dev = T.boxes.device
+    cap = getattr(T, "cap_total", None) or max(T.total, 1)
+    if out is None:
+        out = PackedTargets.__new__(PackedTargets)
+        out.B, out.device = T.B, dev
+        out.labels = torch.zeros(cap * ratio, dtype=torch.int32, device=dev)
+        out.boxes = torch.zeros(cap * ratio, 4, dtype=torch.float32, device=dev)
+        out.scores = torch.ones(cap * ratio, dtype=torch.float32, device=dev) if T.scores is not None else None
+        out.offsets = torch.zeros(T.B + 1, dtype=torch.int32, device=dev)
+        out.counts = torch.zeros(T.B, dtype=torch.int32, device=dev)
+        out.img_label = T.img_label
+        out._inv_num_boxes = None
+    out.sizes = [n * ratio for n in T.sizes]
+    out.total = T.total * ratio
+    out.max_g = (T.cap * ratio) if isinstance(T, StaticTargets) else (max(out.sizes) if out.sizes else 0)
+    out.offsets_host = None
+    out.counts_host = None
+    check(lib().spe_gt_jitter_repeat(ptr(T.boxes), ptr(T.labels), ptr(T.scores) if T.scores is not None else None, ptr(T.offsets), T.B, cap, int(ratio),
+                                     float(jitter), int(n_try), float(iou_thr), ptr(rng.state), ptr(out.boxes), ptr(out.labels),
+                                     ptr(out.scores) if out.scores is not None else None, ptr(out.offsets), ptr(out.counts), ptr(rng.ticket), stream()))
+    return out
 
 
 def sync_num_boxes(static_targets):

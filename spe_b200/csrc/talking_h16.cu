@@ -19,6 +19,7 @@
 // Statistics convention of rowwise.cu / talking_generic.cu:  stats[row][g] = c2 = max_j L2 + log2 sum_j 2^(L2 - max),  L2 = log2e (Wl S + bl).
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -335,12 +336,12 @@ __device__ __forceinline__ void da_frag(const uint32_t (&raw)[4][4], int t, uint
     a[2] = prmt(raw[2][t], raw[3][t], 0x5410u); a[3] = prmt(raw[2][t], raw[3][t], 0x7632u);
 }
 
-template <bool S16>
-__global__ void __launch_bounds__(T16_THREADS, 1) th16_bwd_kernel(const void* __restrict__ S, const uint16_t* dA, uint16_t* dS, const float* __restrict__ Wl,
+template <bool S16, int NT>
+__global__ void __launch_bounds__(NT, 1) th16_bwd_kernel(const void* __restrict__ S, const uint16_t* dA, uint16_t* dS, const float* __restrict__ Wl,
                                                                   const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ stats,
                                                                   int rows_total, int Nq, int Nk, int ldS, int ldA, float* __restrict__ part) {
     constexpr int NP = 2 * 16 * 16 + 2 * 16;
-    __shared__ float redr[T16_WARPS][16], srho[16], sc2[16];
+    __shared__ float redr[(NT / 32)][16], srho[16], sc2[16];
     __shared__ float spart[NP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     Mix1W w1;
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) th16_bwd_kernel(const void* __
     for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
         for (int i = 0; i < 4; ++i) { accWw[nb][i] = 0.f; accWl[nb][i] = 0.f; }
-    for (int i = tid; i < NP; i += T16_THREADS) spart[i] = 0.f;
+    for (int i = tid; i < NP; i += NT) spart[i] = 0.f;
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
     const int nch = (ldA + 63) / 64;
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) th16_bwd_kernel(const void* __
 #pragma unroll
         for (int gs = 0; gs < 4; ++gs) { c2v[gs] = sc2[2 * tig + (gs & 1) + 8 * (gs >> 1)]; rho[gs] = 0.f; }
         // ---- sweep B: rho[g] = sum_j P dP,  dWw += dA^T P
-        for (int c = warp; c < nch; c += T16_WARPS) {
+        for (int c = warp; c < nch; c += (NT / 32)) {
             const int jb = c * 64 + gid * 8;
             float v[4][8];
             uint32_t raw[4][4];
@@ -401,14 +402,14 @@ __global__ void __launch_bounds__(T16_THREADS, 1) th16_bwd_kernel(const void* __
         __syncthreads();
         if (tid < 16) {
             float r = 0.f;
-            for (int w = 0; w < T16_WARPS; ++w) r += redr[w][tid];
+            for (int w = 0; w < (NT / 32); ++w) r += redr[w][tid];
             srho[tid] = r;
         }
         __syncthreads();
 #pragma unroll
         for (int gs = 0; gs < 4; ++gs) rho[gs] = srho[2 * tig + (gs & 1) + 8 * (gs >> 1)];
         // ---- sweep C: dL = P (dP - rho),  dS = dL Wl (in place over dA),  dWl += dL^T S
-        for (int c = warp; c < nch; c += T16_WARPS) {
+        for (int c = warp; c < nch; c += (NT / 32)) {
             const int jb = c * 64 + gid * 8;
             float v[4][8];
             uint32_t raw[4][4];
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) th16_bwd_kernel(const void* __
         }
     __syncthreads();
     float* pr = part + (long long)blockIdx.x * NP;
-    for (int i = tid; i < NP; i += T16_THREADS) pr[i] = spart[i];
+    for (int i = tid; i < NP; i += NT) pr[i] = spart[i];
 }
 
 int t16_grid(int B, int Nq) {
@@ -487,10 +488,17 @@ int spe_talking_h16_bwd(const void* S, int s16, const void* dA, void* dS, const 
     SPE_CHECK(stats, "talking-heads backward (H = 16) needs the forward statistics");
     SPE_CHECK(ldS % 8 == 0 && ldA % 8 == 0 && ldS >= Nk && ldA >= Nk && ldS < (1LL << 31) && ldA < (1LL << 31), "talking-heads H=16: bad leading dimensions");
     const int grid = t16_grid(B, Nq);
-    if (s16)
-        th16_bwd_kernel<true><<<grid, T16_THREADS, 0, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, part);
-    else
-        th16_bwd_kernel<false><<<grid, T16_THREADS, 0, st>>>(S, reinterpret_cast<const uint16_t*>(dA), reinterpret_cast<uint16_t*>(dS), Wl, bl, Ww, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, part);
+    // warps per CTA (one CTA per SM): 16 warps at <= 128 registers hide more of the load latency than 8 at 209 (measured at cfg4, fp16 logits: 0.92 / 0.79 / 0.73 ms for 256 / 384 / 512 threads) (SPE_TH16_BWD_THREADS: A/B)
+    static const int nt = getenv("SPE_TH16_BWD_THREADS") ? atoi(getenv("SPE_TH16_BWD_THREADS")) : 512;
+    const uint16_t* dA16 = reinterpret_cast<const uint16_t*>(dA);
+    uint16_t* dS16 = reinterpret_cast<uint16_t*>(dS);
+#define T16_BWD(S16_, NT_) th16_bwd_kernel<S16_, NT_><<<grid, NT_, 0, st>>>(S, dA16, dS16, Wl, bl, Ww, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, part)
+    if (s16) {
+        if (nt == 256) T16_BWD(true, 256); else if (nt == 512) T16_BWD(true, 512); else T16_BWD(true, 384);
+    } else {
+        if (nt == 256) T16_BWD(false, 256); else if (nt == 512) T16_BWD(false, 512); else T16_BWD(false, 384);
+    }
+#undef T16_BWD
     SPE_LAUNCHED();
     return 0;
 }

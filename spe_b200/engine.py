@@ -23,7 +23,11 @@ from .util.misc import NestedTensor
 
 class TrainStep:
     def __init__(self, model, criterion, criterion_refine=None, weight_dict=None, grad_buffer=None, graph=False, max_gt=None,
-                 refresh_shadows=True):
+                 refresh_shadows=True, optimizer=None):
+        """optimizer: an optim.FlatAdamW built on `grad_buffer` BEFORE this object (it re-points p.data into its flat parameter
+        buffer): clip_grad_norm_ + AdamW then run inside the step -- and inside its CUDA graph -- after the gradient all-reduce
+        (engine.py:161-165 of the reference: zero_grad, backward, clip, step)."""
+        self.optimizer = optimizer
         self.model, self.criterion, self.criterion_refine = model, criterion, criterion_refine
         self.weight_dict = dict(weight_dict if weight_dict is not None else criterion.weight_dict)
         self.gbuf = grad_buffer if grad_buffer is not None else FlatGradBuffer(model.parameters())
@@ -59,6 +63,9 @@ class TrainStep:
         self._works = []
         hooked = bucketed and os.environ.get("SPE_AR_OVERLAP", "1") != "2"       # "2": both buckets after the backward pass (no hook)
         ops.set_grad_milestone("detector_grads_done", (lambda: self._reduce_bucket(0, self._split)) if hooked else None)
+        for X in (T, T_refine):                       # device-side GT jitter / repeat of the raw static targets (graph mode, training criteria)
+            if X is not None and getattr(X, "_expand", None) is not None:
+                X._expand()
         out = self.model(images)
         m1 = m2 = None
         packed = isinstance(T, CO.PackedTargets) and (T_refine is None or isinstance(T_refine, CO.PackedTargets))
@@ -93,6 +100,10 @@ class TrainStep:
             self._reduced = True
         else:
             self._reduced = False
+        self._stepped = False
+        if self.optimizer is not None and (self._reduced or not self._dist()):
+            self.optimizer.step()                     # gradients are final here: part of the (captured) step
+            self._stepped = True
         return loss.detach(), {k: v.detach() for k, v in ld.items()}, (None if ld2 is None else {k: v.detach() for k, v in ld2.items()})
 
     def __call__(self, samples, targets, targets_refine=None):
@@ -105,13 +116,15 @@ class TrainStep:
             # jitter / repeat ONCE (conditional_detr.py:410-431), then pack: criterion.forward prepares plain lists itself and
             # would expand them a second time (every GT 25x instead of 5x with match_ratio 5)
             dev = next(self.model.parameters()).device
-            tg = CO.pack_targets(self.criterion.prepare_targets(targets), dev)
-            tr = CO.pack_targets(self.criterion_refine.prepare_targets(targets_refine), dev) if self.criterion_refine is not None else None
+            tg = self.criterion.prepare_packed(targets, dev)
+            tr = self.criterion_refine.prepare_packed(targets_refine, dev) if self.criterion_refine is not None else None
             res = self._body(samples, tg, tr)
         else:
             res = self._replay(samples, targets, targets_refine)
         if not getattr(self, "_reduced", False):
             self.gbuf.all_reduce_mean()
+        if self.optimizer is not None and not self._stepped:
+            self.optimizer.step()                     # single all-reduce after the step (SPE_AR_OVERLAP=0): the update follows it
         return res
 
     def close(self):
@@ -122,39 +135,72 @@ class TrainStep:
             torch.cuda.synchronize()
 
     # ---- graph mode ----
+    def _device_jitter(self):
+        """training-mode criteria with device_jitter: the GT jitter / repeat (conditional_detr.py:410-431) runs inside the step (and its
+        graph) on raw targets; otherwise the targets are prepared on the host before they are packed."""
+        cs = [c for c in (self.criterion, self.criterion_refine) if c is not None]
+        return all(c.training and getattr(c, "device_jitter", False) for c in cs)
+
     def _replay(self, images, targets, targets_refine):
-        tg = self.criterion.prepare_targets(targets)
-        tr = self.criterion_refine.prepare_targets(targets_refine) if self.criterion_refine is not None else None
-        need = max([len(t["labels"]) for t in tg] + ([len(t["labels"]) for t in tr] if tr is not None else []) + [1])
+        dj = self._device_jitter()
+        crits = [self.criterion] + ([self.criterion_refine] if self.criterion_refine is not None else [])
+        if dj:
+            tg, tr = targets, (targets_refine if self.criterion_refine is not None else None)
+            rs = [c.hung_match_ratio for c in crits]
+            need = max([len(t["labels"]) * rs[0] for t in tg] + ([len(t["labels"]) * rs[-1] for t in tr] if tr is not None else []) + [1])
+        else:
+            tg = self.criterion.prepare_targets(targets)
+            tr = self.criterion_refine.prepare_targets(targets_refine) if self.criterion_refine is not None else None
+            rs = [1, 1]
+            need = max([len(t["labels"]) for t in tg] + ([len(t["labels"]) for t in tr] if tr is not None else []) + [1])
         cap = self.max_gt if self.max_gt is not None else need
         if need > cap:
             raise ValueError("TrainStep(graph=True): %d targets in one image exceed max_gt=%d" % (need, cap))
-        key = (tuple(images.shape), cap)
+        key = (tuple(images.shape), cap, dj, tuple(rs))
         st = self._g.get(key)
         if st is None:
-            st = self._capture(images, tg, tr, cap)
+            st = self._capture(images, tg, tr, cap, rs if dj else None)
             self._g[key] = st
         st["images"].copy_(images, non_blocking=True)
-        st["T"].update(tg, sync_num_boxes=False)
-        if st["Tr"] is not None:
-            st["Tr"].update(tr, sync_num_boxes=False)
+        for name, raw, t, r in (("T", "Traw", tg, rs[0]), ("Tr", "Trraw", tr, rs[-1])):
+            if st[name] is None:
+                continue
+            if dj:                                           # raw targets in; the captured jitter kernel fills st[name] every replay
+                st[raw].update(t, sync_num_boxes=False)
+                st[name].sizes, st[name].total = [n * r for n in st[raw].sizes], st[raw].total * r
+                st[name].set_num_boxes(sync_num_boxes=False)
+            else:
+                st[name].update(t, sync_num_boxes=False)
         CO.sync_num_boxes([st["T"], st["Tr"]])          # one 8-byte all-reduce for both criteria (N > 1)
         st["graph"].replay()
         return st["out"]
 
-    def _capture(self, images, tg, tr, cap):
+    def _capture(self, images, tg, tr, cap, ratios=None):
         dev = next(self.model.parameters()).device
         B = images.shape[0]
         ncls = tg[0]["img_label"].numel() if tg and "img_label" in tg[0] else 0
         st = {"images": torch.empty(images.shape, dtype=torch.float32, device=dev),
               "T": CO.StaticTargets(B, cap, dev, with_scores=all("scores" in t for t in tg), img_classes=ncls),
-              "Tr": None}
+              "Tr": None, "Traw": None, "Trraw": None}
         if tr is not None:
             st["Tr"] = CO.StaticTargets(B, cap, dev, with_scores=all("scores" in t for t in tr), img_classes=ncls)
         st["images"].copy_(images)
-        st["T"].update(tg)
-        if st["Tr"] is not None:
-            st["Tr"].update(tr)
+        if ratios is None:
+            st["T"].update(tg)
+            if st["Tr"] is not None:
+                st["Tr"].update(tr)
+        else:
+            for name, raw, t, r, crit in (("T", "Traw", tg, ratios[0], self.criterion), ("Tr", "Trraw", tr, ratios[-1], self.criterion_refine)):
+                if st[name] is None:
+                    continue
+                R = CO.StaticTargets(B, max(cap // r, 1), dev, with_scores=st[name].scores is not None, img_classes=ncls)
+                R.update(t)
+                st[raw] = R
+                T = st[name]
+                T.img_label = R.img_label
+                T._expand = (lambda R=R, T=T, r=r, crit=crit: CO.jitter_repeat(R, r, crit.box_jitter, crit.jitter_rng(dev), out=T))
+                T.sizes, T.total = [n * r for n in R.sizes], R.total * r
+                T.set_num_boxes()
         # warm-up on a side stream (lazy one-time initialisation: shadows, kernel attributes, autograd buffers), then capture
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

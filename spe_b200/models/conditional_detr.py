@@ -81,8 +81,8 @@ class ConditionalDETR_Refine(nn.Module):
 
 
 class SetCriterion(nn.Module):
-    """conditional_detr.py:190-494.  Matching + every loss run on the device with no host synchronisation;
-    the GT jitter/repeat of training mode (:410-431) is host-side RNG prep and follows the reference."""
+    """conditional_detr.py:190-494.  Matching + every loss run on the device with no host synchronisation; so does the GT
+    jitter/repeat of training mode (:410-431; csrc/targets.cu) unless `device_jitter` is switched off."""
     refine = False
 
     def __init__(self, num_classes, matcher, weight_dict, focal_alpha, losses, gamma, box_jitter):
@@ -134,8 +134,30 @@ class SetCriterion(nn.Module):
         return out
 
     def prepare_targets(self, targets):
-        """the target list the losses see: jittered + repeated GT in training mode (:410-431), unchanged in eval mode."""
+        """the target list the losses see: jittered + repeated GT in training mode (:410-431), unchanged in eval mode.  Host loop with
+        torch's RNG, exactly the reference's sequence of draws (used when device_jitter is off, and by callers that want the list)."""
         return self._jitter_repeat(targets) if self.training else targets
+
+    # SURVEY N2: in training mode the jitter / repeat runs on the device (csrc/targets.cu), one launch instead of a Python loop over
+    # images x boxes; `criterion.device_jitter = False` restores the reference's host loop and its torch RNG stream.
+    device_jitter = True
+
+    def jitter_rng(self, device):
+        rngs = self.__dict__.setdefault("_jitter_rngs", {})
+        key = str(device)
+        if key not in rngs:
+            rngs[key] = CO.JitterRng(device)
+        return rngs[key]
+
+    def prepare_packed(self, targets, device):
+        """targets (list of dicts, or already packed) -> CO.PackedTargets on `device` as the losses see them."""
+        if isinstance(targets, CO.PackedTargets):
+            return targets
+        if not self.training:
+            return CO.pack_targets(targets, device)
+        if not self.device_jitter or not torch.device(device).type == "cuda" or not any(len(t["labels"]) for t in targets):
+            return CO.pack_targets(self._jitter_repeat(targets), device)
+        return CO.jitter_repeat(CO.pack_targets(targets, device), self.hung_match_ratio, self.box_jitter, self.jitter_rng(device))
 
     def loss_img_label(self, outputs, targets):
         if isinstance(targets, CO.PackedTargets):
@@ -164,8 +186,7 @@ class SetCriterion(nn.Module):
         if isinstance(targets, CO.PackedTargets):
             tg = T = targets            # pre-packed (engine.TrainStep: static buffers; jitter/repeat already applied by prepare_targets)
         else:
-            tg = self.prepare_targets(targets)
-            T = CO.pack_targets(tg, dev)
+            tg = T = self.prepare_packed(targets, dev)
         mw = self.matcher.weights
         det = tuple(l for l in self.losses if l in ("labels", "boxes", "cardinality"))
         losses = {}

@@ -333,7 +333,7 @@ def test_fused_attention_fwd(K, masked, two, Lq, Lk, d, dv, packed):
         assert rel_err(a, b_) < 3e-2, rel_err(a, b_)
 
 
-@pytest.mark.parametrize("H,N,dh", [(2, 35, 64), (4, 196, 48), (8, 130, 48), (8, 1600, 48), (4, 1024, 48), (16, 300, 48), (6, 77, 48), (12, 261, 32)])   # (8, 1600) = cfg2 = the benchmarked shape (fused kernels); 16 = CaiT-M36 (cfg4), 6/12: generic-H kernels
+@pytest.mark.parametrize("H,N,dh", [(2, 35, 64), (4, 196, 48), (8, 130, 48), (8, 1600, 48), (4, 1024, 48), (16, 300, 48), (6, 77, 48), (12, 261, 32)])   # (8, 1600) = cfg2 = the benchmarked shape (fused kernels); 16 = CaiT-M36 (cfg4, talking_h16.cu), 6/12: generic-H kernels
 def test_talking_heads_attention_fn(K, H, N, dh):
     g = torch.Generator().manual_seed(15)
     B, D = 2, H * dh

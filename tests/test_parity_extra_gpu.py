@@ -118,10 +118,11 @@ def test_train_step_train_mode_expands_targets_once():
     tg = [{k: v.to(dev) for k, v in t.items()} for t in targets]
     n_gt = sum(len(t["labels"]) for t in targets)
     seen = {}
-    for graph in (False, True):
+    for graph, device_jitter in ((False, False), (True, False), (False, True), (True, True)):
         model = factory.build_detector(cfg, dev).train()
         model.load_state_dict(params)
         crit = factory.build_criterion(cfg, match_ratio=5, device=dev).train()
+        crit.device_jitter = device_jitter          # False: the reference's host loop (torch RNG); True: csrc/targets.cu inside the step
         counts = []
         orig = crit.prepare_targets
         crit.prepare_targets = lambda t, _o=orig, _c=counts: (_c.append(1), _o(t))[1]
@@ -132,18 +133,22 @@ def test_train_step_train_mode_expands_targets_once():
         # the matched queries of the final level = min(Q, ratio * G_b) per image: read back from the cardinality bookkeeping
         idx = crit.matcher(model(images.to(dev))[0], crit._jitter_repeat(tg))
         assert sum(len(i) for i, _ in idx) == sum(min(cfg.num_queries, 5 * len(t["labels"])) for t in targets)
-        seen[graph] = (len(counts), {k: float(v) for k, v in ld.items()})
-    # one expansion per criterion call in both modes (the capture warm-up of graph mode calls the body, not prepare_targets)
-    assert seen[False][0] == 1 and seen[True][0] == 1, seen
+        seen[(graph, device_jitter)] = (len(counts), {k: float(v) for k, v in ld.items()})
+    # host jitter: one expansion per criterion call in both modes (the capture warm-up of graph mode calls the body, not
+    # prepare_targets); device jitter: none on the host
+    assert seen[(False, False)][0] == 1 and seen[(True, False)][0] == 1 and seen[(False, True)][0] == 0 and seen[(True, True)][0] == 0, seen
     # loss_ce is normalised by num_boxes = ratio * G (not ratio^2 * G): with 25x boxes the no-object part would shrink 5x
-    e, gph = seen[False][1], seen[True][1]
-    assert n_gt > 0 and abs(e["cardinality_error"] - gph["cardinality_error"]) < 1e-3, (e, gph)
+    e = seen[(False, False)][1]
+    for key, (_, other) in seen.items():
+        assert n_gt > 0 and abs(e["cardinality_error"] - other["cardinality_error"]) < 1e-3, (key, e, other)
 
 
-@pytest.mark.parametrize("H,N", [(16, 4150)])
-def test_talking_heads_h16_cfg4_tokens(H, N):
-    """CaiT-M36 head geometry at the cfg4 token count (50 x 83 = 4150): forward + gradients vs fp32 (generic-H kernels)."""
+@pytest.mark.parametrize("H,N,s16", [(16, 4150, True), (16, 4150, False), (16, 301, False)])
+def test_talking_heads_h16_cfg4_tokens(H, N, s16, monkeypatch):
+    """CaiT-M36 head geometry at the cfg4 token count (50 x 83 = 4150) and a ragged one: forward + gradients vs fp32
+    (csrc/talking_h16.cu: mma.sync mixes, logits stored as fp16 or fp32)."""
     from spe_b200 import ops as K
+    monkeypatch.setattr(K, "_TH_S16", s16)
     g = torch.Generator().manual_seed(31)
     dh, B = 48, 1
     D = H * dh

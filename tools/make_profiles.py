@@ -82,14 +82,20 @@ def main():
             ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma %"),
             ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
             ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"), ("lts__t_sector_hit_rate.pct", "l2 hit %")]
-    if os.path.exists(raw):
+    def table(raw, md, last_only=False):
         rows = list(csv.reader(open(raw)))
         hdr, units = rows[0], rows[1]
         ix = {n: i for i, n in enumerate(hdr)}
         use = [(c, t) for c, t in cols if c in ix]
-        hot_md.append("| kernel | " + " | ".join(t for _, t in use) + " |")
-        hot_md.append("|---|" + "---|" * len(use))
-        for r in rows[2:]:
+        md.append("| kernel | " + " | ".join(t for _, t in use) + " |")
+        md.append("|---|" + "---|" * len(use))
+        body = rows[2:]
+        if last_only:
+            seen = collections.OrderedDict()
+            for r in body:
+                seen[r[ix["Kernel Name"]]] = r
+            body = list(seen.values())
+        for r in body:
             vals = []
             for c, _ in use:
                 v = r[ix[c]]
@@ -103,12 +109,23 @@ def main():
                 except ValueError:
                     pass
                 vals.append(v)
-            hot_md.append("| `%s` | " % short(r[ix["Kernel Name"]])[:60] + " | ".join(vals) + " |")
+            md.append("| `%s` | " % short(r[ix["Kernel Name"]])[:60] + " | ".join(vals) + " |")
+
+    if os.path.exists(raw):
+        table(raw, hot_md)
+    fused_md = []
+    raw2 = os.path.join(OUT, "prof_fused_raw.csv")
+    if os.path.exists(raw2) and os.path.getsize(raw2) > 100:
+        table(raw2, fused_md, last_only=True)
     with open(os.path.join(PROF, TAG + "_ncu_hot_kernels.md"), "w") as f:
         f.write("# %s -- ncu `--set full --clock-control none` on the hot kernels (tools/prof_attn.py: encoder self-attention + conditional\n"
                 "# cross-attention fwd (fused) + bwd, one talking-heads attention fwd+bwd, one LayerScale FFN fwd+bwd, cfg2 shapes B=8, N=1600, D=384, H=8).\n"
                 "# Per launch; cold-cache, serialised (compare shares, not absolutes).\n\n" % TAG)
         f.write("\n".join(hot_md) + "\n")
+        if fused_md:
+            f.write("\n## kernels added in round 2 (tools/prof_fused.py): fused talking-heads forward / recomputing backward (csrc/talking_fused.cu, cfg2 shape\n"
+                    "## B=8, H=8, N=1600, dh=48) and the H=16 mix/softmax/mix kernels (csrc/talking_h16.cu, cfg4 shape B=1, N=4150, fp16 logits); last launch of each\n\n")
+            f.write("\n".join(fused_md) + "\n")
         rep = os.path.join(OUT, "prof_attn_fused.ncu-rep")
         if os.path.exists(rep):
             try:
@@ -117,10 +134,16 @@ def main():
             except Exception as e:                   # ncu missing: keep the table
                 f.write("\n(ncu_stalls failed: %s)\n" % e)
 
-    for src, dst in (("bench_default.json", TAG + "_bench_n1.json"), ("bench_reference.json", TAG + "_bench_reference_cpu.json")):
+    for src, dst in (("bench_default.json", TAG + "_bench_n1.json"), ("bench_reference.json", TAG + "_bench_reference_cpu.json"),
+                     ("bench_cfg4.json", TAG + "_bench_cfg4_n1.json"), ("bench_n2_ov1.json", TAG + "_bench_n2.json"),
+                     ("bench_n2_ov0.json", TAG + "_bench_n2_single_allreduce.json")):
         p = os.path.join(OUT, src)
         if os.path.exists(p) and os.path.getsize(p) > 10:
             shutil.copy(p, os.path.join(PROF, dst))
+    try:
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_summary.py"), os.path.join(PROF, TAG + "_sass_opcodes.md")], capture_output=True, timeout=600)
+    except Exception as e:
+        print("sass summary failed", e)
     write_readme(traffic, tot, len(L))
     print("launches", len(L), "total us %.0f" % tot)
     for k, a in list(traffic["kernels"].items())[:12]:
@@ -139,11 +162,14 @@ def write_readme(traffic, tot, n):
         f.write("# profiles -- round %s\n\nAll captured on a B200 through `gpurun` (`./tools_gpu_profiles.sh`, then `python tools/make_profiles.py %s` here).\n\n" % (TAG[1:], TAG))
         f.write("| file | what | command |\n|---|---|---|\n")
         f.write("| `%s_bench_n1.json` | default `python bench.py` line (N=1, cfg2, bs 8, CUDA-graph step) | `python bench.py` |\n" % TAG)
-        f.write("| `%s_bench_reference_cpu.json` | reference arm: the reference's algorithm (oracle port) on the host cores | `python bench.py --impl reference --steps 2 --warmup 1` |\n" % TAG)
+        f.write("| `%s_bench_reference_cpu.json` | reference arm: the UNMODIFIED reference (baseline/_ref) on the host cores + informational eager-on-B200 timing of it | `python bench.py --impl reference --steps 2 --warmup 1` |\n" % TAG)
         f.write("| `%s_launches_one_step.csv` | every kernel launch of ONE training step: device time, DRAM read / write bytes | `ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv python tools/step_once.py` |\n" % TAG)
         f.write("| `%s_kernel_traffic.json` | the launch list aggregated per kernel symbol (share of the step, mean DRAM bytes per launch); `bench.py` takes `roofline.traffic` from here | `python tools/make_profiles.py` |\n" % TAG)
         f.write("| `%s_ncu_hot_kernels.md` | `ncu --set full` of the hot kernels (fused attention fwd, attention / dense GEMMs, talking-heads kernels, softmax bwd, LayerNorm) + stall reasons of the fused attention kernel | `ncu --set full --clock-control none -k regex:... python tools/prof_attn.py 2` |\n" % TAG)
-        f.write("| `r01_bench_n2.json` | N=2 data-parallel line (298 images/s, NCCL all-reduce of the flat gradient buffer) | `torchrun --nproc-per-node 2 bench.py --gpus 2` |\n\n")
+        f.write("| `%s_bench_cfg4_n1.json` | BASELINE configs[3] (TSCAM-M36, 800x1333, bs 1) | `python bench.py --config cfg4 --steps 5 --warmup 3` |\n" % TAG)
+        f.write("| `%s_bench_n2.json`, `%s_bench_n2_single_allreduce.json` | N=2 data parallel: bucketed all-reduce overlapped with the backbone backward (default) vs one all-reduce after the step (`SPE_AR_OVERLAP=0`) | `torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 10` |\n" % (TAG, TAG))
+        f.write("| `%s_sass_opcodes.md` | static SASS census per kernel: UTCHMMA / LDTM / UTMALDG / HMMA / MOVM counts, spills | `python tools/sass_summary.py` |\n" % TAG)
+        f.write("| `r01_*` | round-1 evidence (kept for comparison) | |\n\n")
         if b:
             f.write("## bench line (CUDA events, not under a profiler)\n\n")
             f.write("* value **%.1f images/s** (%.2f ms/step of %d images), e2e (pinned-host H2D + loss D2H inside the timed region) %.1f images/s\n" % (
