@@ -330,6 +330,17 @@ int spe_bce_logits(const float* x, const float* y, int64_t n, float* out, float*
 /* Pairwise IoU / GIoU (util/box_ops.py:33-74): a f32 [N,4], b f32 [M,4] xyxy -> iou/giou/union f32 [N,M] */
 int spe_box_iou_pairwise(const float* a, int N, const float* b, int M, float* iou, float* uni, float* giou, void* stream);
 
+/* CAM -> pseudo ground-truth box: engine.get_pseudo_label (engine.py:310-352) = cams_deit.resize_cam (cams_deit.py:9-14)
+ * + cams_deit.get_bboxes (:34-58), for npairs (image, class) pairs at once, bit-exact with the OpenCV path the reference calls.
+ *   cams f32 [B,C,h,w]; pairs i32 [npairs,2] = (image, class) on the device; the map is resized to rows x cols (the reference passes
+ *   dsize = (H_img, W_img), i.e. rows = W_img, cols = H_img), min-max normalised, quantised to u8, thresholded at u8 > thr_u8
+ *   (= int(cam_thr * 255)), and the bounding box of the contour with the largest cv2.contourArea is returned as
+ *   boxes_out f32 [npairs,4] = cxcywh / (norm_x, norm_y, norm_x, norm_y)  and (optional) xyxy_out i32 [npairs,4] = [x, y, x+w, y+h].
+ *   workspace: spe_cam_boxes_workspace_bytes(npairs, rows, cols) bytes. */
+int64_t spe_cam_boxes_workspace_bytes(int npairs, int rows, int cols);
+int spe_cam_boxes(const float* cams, int B, int C, int h, int w, const int32_t* pairs, int npairs, int rows, int cols, int thr_u8,
+                  float norm_x, float norm_y, float* boxes_out, int32_t* xyxy_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* GT jitter + repeat of SetCriterion.forward in training mode (models/conditional_detr.py:410-431), device side.
  *   in : boxes f32 [sumG,4] cxcywh, labels i32 [sumG], scores f32 [sumG] or NULL, offsets i32 [B+1] (CSR over images; sumG = offsets[B]
  *        is read on the device, cap_total >= sumG sizes the launch)

@@ -156,7 +156,7 @@ class SetCriterion(nn.Module):
         if not self.training:
             return CO.pack_targets(targets, device)
         if not self.device_jitter or not torch.device(device).type == "cuda" or not any(len(t["labels"]) for t in targets):
-            return CO.pack_targets(self._jitter_repeat(targets), device)
+            return CO.pack_targets(self.prepare_targets(targets), device)
         return CO.jitter_repeat(CO.pack_targets(targets, device), self.hung_match_ratio, self.box_jitter, self.jitter_rng(device))
 
     def loss_img_label(self, outputs, targets):
