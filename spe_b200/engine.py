@@ -102,7 +102,11 @@ class TrainStep:
             self._reduced = False
         self._stepped = False
         if self.optimizer is not None and (self._reduced or not self._dist()):
-            self.optimizer.step()                     # gradients are final here: part of the (captured) step
+            if getattr(self, "_warming", False):      # capture warm-up passes must not move the parameters / Adam state:
+                if self.optimizer.shadows is not None:    # only settle the one-time host work of the step (shadow descriptor table)
+                    self.optimizer.shadows.refresh()
+            else:
+                self.optimizer.step()                 # gradients are final here: part of the (captured) step
             self._stepped = True
         return loss.detach(), {k: v.detach() for k, v in ld.items()}, (None if ld2 is None else {k: v.detach() for k, v in ld2.items()})
 
@@ -205,8 +209,12 @@ class TrainStep:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(2):
-                self._body(st["images"], st["T"], st["Tr"])
+            self._warming = True
+            try:
+                for _ in range(2):
+                    self._body(st["images"], st["T"], st["Tr"])
+            finally:
+                self._warming = False
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()

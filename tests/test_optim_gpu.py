@@ -89,3 +89,43 @@ def test_clip_grad_norm_flat():
     assert abs(float(tn) - float(tn_ref)) <= 1e-5 * float(tn_ref)
     for p, q in zip(ps, qs):
         assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_train_step_with_fused_optimizer_matches_reference_loop(graph):
+    """engine.py:161-165 (zero_grad, backward, clip_grad_norm_, optimizer.step) as ONE TrainStep call (captured in the CUDA graph when
+    graph=True).  After every call the gradients the step produced (still in the flat buffer) are handed to torch's
+    clip_grad_norm_ + AdamW on a shadow copy of the parameters: the two parameter sets must stay equal step after step.  (Comparing
+    two independently computed loss trajectories instead is meaningless: Adam's first updates are lr * sign(g), so the atomics-order
+    noise of the backward flips noise-level gradient signs and the runs drift apart within three steps.)"""
+    from oracle import spe_oracle as O
+    from spe_b200 import factory
+    from spe_b200.dp import FlatGradBuffer
+    from spe_b200.engine import TrainStep
+    from spe_b200.optim import FlatAdamW
+    dev = torch.device("cuda")
+    cfg = O.tiny_config()
+    params = O.make_params(cfg, 11)
+    images, targets = O.make_inputs(cfg, 2, 48, 64, seed=11, max_gt=3)
+    tg = [{k: v.to(dev) for k, v in t.items()} for t in targets]
+    lr, lrb, lrc, wd, clip = 2e-3, 1e-3, 1.5e-3, 1e-2, 0.1
+    model = factory.build_detector(cfg, dev).train()
+    model.load_state_dict(params)
+    crit = factory.build_criterion(cfg, device=dev).eval()
+    gbuf = FlatGradBuffer(model.parameters())
+    opt = FlatAdamW(model, gbuf, lr=lr, lr_backbone=lrb, lr_cls_head=lrc, weight_decay=wd, clip_max_norm=clip)
+    step = TrainStep(model, crit, None, grad_buffer=gbuf, graph=graph, max_gt=8, optimizer=opt)
+    ref = copy.deepcopy(model)                      # parameter holder for torch's optimizer (never run forward)
+    opt_ref = torch.optim.AdamW(_groups(ref, lr, lrb, lrc), lr=lr, weight_decay=wd)
+    losses = []
+    for it in range(4):
+        losses.append(float(step(images.to(dev), tg)[0]))
+        for p, q in zip(model.parameters(), ref.parameters()):
+            q.grad = p.grad.detach().clone()        # the step's own gradients (the flat buffer keeps them unclipped)
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), clip)
+        opt_ref.step()
+        for (n, p), q in zip(model.named_parameters(), ref.parameters()):
+            d = float((p.detach() - q.detach()).abs().max())
+            assert d <= 1e-4 * lr * (it + 1) + 5e-7 * float(q.detach().abs().max()) + 1e-9, (graph, it, n, d)
+    assert int(opt.state[3]) == 4                   # the capture warm-up passes did not step the optimizer
+    assert losses[-1] < losses[0], losses           # and the model is learning
