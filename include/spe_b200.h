@@ -341,6 +341,14 @@ int64_t spe_cam_boxes_workspace_bytes(int npairs, int rows, int cols);
 int spe_cam_boxes(const float* cams, int B, int C, int h, int w, const int32_t* pairs, int npairs, int rows, int cols, int thr_u8,
                   float norm_x, float norm_y, float* boxes_out, int32_t* xyxy_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Multi-box variant (engine.get_pseudo_label_multi_boxes, engine.py:356-398 = cams_deit.get_multi_bboxes :61-97): every contour of the
+ * thresholded map (outer borders at any nesting level and hole borders, cv2.RETR_TREE) whose cv2.contourArea is >= area_ratio * the
+ * largest one, by decreasing area; at most max_boxes (<= 64) per pair.  boxes_out f32 [npairs,max_boxes,4], xyxy_out i32 (optional),
+ * counts_out i32 [npairs] (>= 1: a map without contours yields [0,0,1,1]). */
+int spe_cam_boxes_multi(const float* cams, int B, int C, int h, int w, const int32_t* pairs, int npairs, int rows, int cols, int thr_u8,
+                        float norm_x, float norm_y, double area_ratio, int max_boxes, float* boxes_out, int32_t* xyxy_out,
+                        int32_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* GT jitter + repeat of SetCriterion.forward in training mode (models/conditional_detr.py:410-431), device side.
  *   in : boxes f32 [sumG,4] cxcywh, labels i32 [sumG], scores f32 [sumG] or NULL, offsets i32 [B+1] (CSR over images; sumG = offsets[B]
  *        is read on the device, cap_total >= sumG sizes the launch)

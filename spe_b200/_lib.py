@@ -80,6 +80,7 @@ class AdamwArgs(C.Structure):
 _SIGS = {
     "spe_cam_boxes_workspace_bytes": (c_l, [c_i, c_i, c_i]),
     "spe_cam_boxes": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_l, c_p]),
+    "spe_cam_boxes_multi": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_f, c_f, C.c_double, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
     "spe_gt_jitter_repeat": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "spe_sumsq_workspace_floats": (c_l, []),
     "spe_sumsq_f32": (c_i, [c_p, c_l, c_p, c_p, c_p]),

@@ -15,7 +15,9 @@
 //     tree from the left neighbour of every component's first pixel in raster order (exactly how the border follower assigns
 //     parents), map every pixel to its top-level enclosing component, count cells, take the arg-max (ties: the component found last in
 //     raster order, cv2's contour order is reverse raster), and emit its bounding box.
-// The `_multi_boxes` variant (all contours above an area ratio, holes included) is not covered.
+// The `_multi_boxes` variant (engine.py:356-398, cams_deit.get_multi_bboxes :61-97: every contour -- outer borders at any nesting level
+// and hole borders -- above an area ratio) uses the same labelling: nested outer borders through ancestor chains, hole borders through a
+// local shoelace sum over the crack edges of the filled hole.
 #include "common.cuh"
 #include <limits.h>
 
@@ -187,39 +189,90 @@ __global__ void __launch_bounds__(CB_THREADS) cam_parent_kernel(CamGeom g, CamWs
     }
 }
 
-// top-level foreground component enclosing every root (-1: outside); overwrites aux
-__global__ void __launch_bounds__(CB_THREADS) cam_top_kernel(CamGeom g, CamWs ws) {
+// contour area of EVERY foreground component (any nesting level): a pixel is inside component X's outer border iff X is on the
+// ancestor chain of the pixel's region in the nesting tree.  A 2x2 cell adds 1 (all four corners inside) or 1/2 (three) to X.
+constexpr int CB_MAXCHAIN = 12;     // fg nodes tracked per cell (nesting deeper than 12 levels is ignored)
+__global__ void __launch_bounds__(CB_THREADS) cam_cells_kernel(CamGeom g, CamWs ws) {
     const int m = blockIdx.y;
     const long long base = (long long)m * g.npix;
     const unsigned char* M = ws.mask + base;
     const int* L = ws.label + base;
-    for (int i = blockIdx.x * CB_THREADS + threadIdx.x; i < g.npix; i += gridDim.x * CB_THREADS) {
-        if (L[i] != i) continue;
-        int top = -1;
-        if (M[i] || ws.parent[base + i] >= 0) {     // background roots without a parent are the outside
-            int r = i;
-            while (ws.parent[base + r] >= 0) r = ws.parent[base + r];
-            top = r;                                 // the chain ends at a top-level foreground root
-        }
-        ws.aux[base + i] = top;                      // the border flags were consumed by cam_parent_kernel (finished): reuse the array
-    }
-}
-
-__global__ void __launch_bounds__(CB_THREADS) cam_cells_kernel(CamGeom g, CamWs ws) {
-    const int m = blockIdx.y;
-    const long long base = (long long)m * g.npix;
-    const int* L = ws.label + base;
-    const int* T = ws.aux + base;
+    const int* P = ws.parent + base;
     const int ncell = (g.rows - 1) * (g.cols - 1);
     for (int c = blockIdx.x * CB_THREADS + threadIdx.x; c < ncell; c += gridDim.x * CB_THREADS) {
         const int y = c / (g.cols - 1), x = c % (g.cols - 1);
         const int i = y * g.cols + x;
-        const int t00 = T[L[i]], t01 = T[L[i + 1]], t10 = T[L[i + g.cols]], t11 = T[L[i + g.cols + 1]];
-        const int t = max(max(t00, t01), max(t10, t11));            // all enclosed corners share one top-level component
-        if (t < 0) continue;
-        const int k = (t00 == t) + (t01 == t) + (t10 == t) + (t11 == t);
-        if (k == 4) atomicAdd(&ws.area2[base + t], 2);
-        else if (k == 3) atomicAdd(&ws.area2[base + t], 1);
+        const int r[4] = {L[i], L[i + 1], L[i + g.cols], L[i + g.cols + 1]};
+        if (r[0] == r[1] && r[0] == r[2] && r[0] == r[3]) {                // uniform cell (the common case): whole chain gets a full cell
+            for (int q = r[0]; q >= 0; q = P[q])
+                if (M[q]) atomicAdd(&ws.area2[base + q], 2);
+            continue;
+        }
+        int node[CB_MAXCHAIN], cnt[CB_MAXCHAIN], n = 0;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            for (int q = r[k]; q >= 0; q = P[q]) {
+                if (!M[q]) continue;
+                int t = 0;
+                while (t < n && node[t] != q) ++t;
+                if (t == n) {
+                    if (n == CB_MAXCHAIN) continue;
+                    node[n] = q; cnt[n] = 0; ++n;
+                }
+                ++cnt[t];
+            }
+        }
+        for (int t = 0; t < n; ++t) {
+            if (cnt[t] == 4) atomicAdd(&ws.area2[base + node[t]], 2);
+            else if (cnt[t] == 3) atomicAdd(&ws.area2[base + node[t]], 1);
+        }
+    }
+}
+
+// hole borders (cv2 traces them on the foreground pixels around the hole): 2 x signed polygon area by the shoelace formula summed
+// over the crack edges of the FILLED hole region R (hole + everything inside it), walked clockwise.  Vertex of an edge = the outside
+// pixel across it; the next edge follows from the two pixels ahead (convex corner: same R pixel, next side; concave: the diagonal
+// pixel's side, same outside pixel; straight).  Every term is local, so no traversal order is needed.  Checked against cv2 on 19 000
+// hole contours incl. salt-and-pepper masks (tests/golden/make_cam_fixture.py).  bbox of a hole contour = bbox of the vertices.
+__device__ __forceinline__ bool in_chain(const int* P, int root, int X) {
+    for (int q = root; q >= 0; q = P[q])
+        if (q == X) return true;
+    return false;
+}
+__global__ void __launch_bounds__(CB_THREADS) cam_hole_edges_kernel(CamGeom g, CamWs ws) {
+    const int m = blockIdx.y;
+    const long long base = (long long)m * g.npix;
+    const unsigned char* M = ws.mask + base;
+    const int* L = ws.label + base;
+    const int* P = ws.parent + base;
+    const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0};                // N, E, S, W
+    for (int i = blockIdx.x * CB_THREADS + threadIdx.x; i < g.npix; i += gridDim.x * CB_THREADS) {
+        if (M[i]) continue;
+        const int Hh = L[i];
+        if (P[Hh] < 0) continue;                                            // background connected to the image border: not a hole
+        const int y = i / g.cols, x = i % g.cols;                           // holes never touch the border: all 8 neighbours exist
+        unsigned int sum = 0;                                               // modular arithmetic: the partial sums exceed 32 bits, the total does not
+        int x0 = INT_MAX, y0 = INT_MAX, x1 = -1, y1 = -1;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int ox = x + DX[d], oy = y + DY[d];
+            if (in_chain(P, L[oy * g.cols + ox], Hh)) continue;             // neighbour inside R (hole pixel or an island in it)
+            const int tx = DX[(d + 1) & 3], ty = DY[(d + 1) & 3];           // travel direction along this edge
+            const int bx = x + tx, by = y + ty, ax = bx + DX[d], ay = by + DY[d];
+            int nx, ny;
+            if (!in_chain(P, L[by * g.cols + bx], Hh)) { nx = bx; ny = by; }            // convex corner
+            else if (in_chain(P, L[ay * g.cols + ax], Hh)) { nx = ox; ny = oy; }        // concave corner
+            else { nx = ax; ny = ay; }                                                  // straight
+            sum += (unsigned int)(ox * ny - nx * oy);
+            x0 = min(x0, ox); y0 = min(y0, oy); x1 = max(x1, ox); y1 = max(y1, oy);
+        }
+        if (x1 >= 0) {
+            if (sum) atomicAdd(reinterpret_cast<unsigned int*>(&ws.area2[base + Hh]), sum);
+            atomicMin(&ws.bbox[base * 4 + 0LL * g.npix + Hh], x0);
+            atomicMin(&ws.bbox[base * 4 + 1LL * g.npix + Hh], y0);
+            atomicMax(&ws.bbox[base * 4 + 2LL * g.npix + Hh], x1);
+            atomicMax(&ws.bbox[base * 4 + 3LL * g.npix + Hh], y1);
+        }
     }
 }
 
@@ -261,6 +314,74 @@ __global__ void __launch_bounds__(CB_THREADS) cam_select_kernel(CamGeom g, CamWs
     }
 }
 
+// get_multi_bboxes (cams_deit.py:61-97): every contour (outer borders at any nesting level AND hole borders) whose area is
+// >= area_ratio * the largest area, by decreasing area (equal areas: later raster position first -- cv2's tree order may differ for
+// exact ties), each as boundingRect -> [x, y, x + w, y + h].  One block per map.
+constexpr int CB_MAXBOX = 64;
+__global__ void __launch_bounds__(CB_THREADS) cam_select_multi_kernel(CamGeom g, CamWs ws, float norm_x, float norm_y, double ratio, int max_boxes,
+                                                                       float* __restrict__ boxes, int* __restrict__ xyxy, int* __restrict__ counts) {
+    __shared__ int red[CB_THREADS];
+    __shared__ int s_n, s_area[CB_MAXBOX], s_idx[CB_MAXBOX];
+    const int m = blockIdx.x;
+    const long long base = (long long)m * g.npix;
+    const unsigned char* M = ws.mask + base;
+    const int* L = ws.label + base;
+    const int* P = ws.parent + base;
+    int best = -1;
+    for (int i = threadIdx.x; i < g.npix; i += CB_THREADS) {
+        if (L[i] != i || (!M[i] && P[i] < 0)) continue;                    // not a root, or the outside background
+        const int a = ws.area2[base + i];
+        best = max(best, a < 0 ? -a : a);
+    }
+    red[threadIdx.x] = best;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int s = CB_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] = max(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    const int amax = red[0];
+    const double thr = (double)amax * 0.5 * ratio;                          // areas[idx] >= areas[area_idx[0]] * area_ratio, in double as in Python
+    for (int i = threadIdx.x; i < g.npix; i += CB_THREADS) {
+        if (L[i] != i || (!M[i] && P[i] < 0)) continue;
+        int a = ws.area2[base + i];
+        a = a < 0 ? -a : a;
+        if ((double)a * 0.5 >= thr) {
+            const int slot = atomicAdd(&s_n, 1);
+            if (slot < CB_MAXBOX) { s_area[slot] = a; s_idx[slot] = i; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = min(s_n, CB_MAXBOX);
+        for (int a = 1; a < n; ++a) {                                       // insertion sort: area descending, then root index descending
+            const int ka = s_area[a], ki = s_idx[a];
+            int b = a - 1;
+            while (b >= 0 && (s_area[b] < ka || (s_area[b] == ka && s_idx[b] < ki))) { s_area[b + 1] = s_area[b]; s_idx[b + 1] = s_idx[b]; --b; }
+            s_area[b + 1] = ka; s_idx[b + 1] = ki;
+        }
+        n = min(n, max_boxes);
+        if (amax < 0) n = 0;
+        const long long o = (long long)m * max_boxes;
+        for (int k = 0; k < max(n, 1); ++k) {
+            int x0 = 0, y0 = 0, x1 = 1, y1 = 1;                             // no contour: [[0, 0, 1, 1]] (cams_deit.py:95)
+            if (n > 0) {
+                const int r = s_idx[k];
+                x0 = ws.bbox[base * 4 + 0LL * g.npix + r];
+                y0 = ws.bbox[base * 4 + 1LL * g.npix + r];
+                x1 = ws.bbox[base * 4 + 2LL * g.npix + r] + 1;
+                y1 = ws.bbox[base * 4 + 3LL * g.npix + r] + 1;
+            }
+            if (xyxy) { xyxy[4 * (o + k)] = x0; xyxy[4 * (o + k) + 1] = y0; xyxy[4 * (o + k) + 2] = x1; xyxy[4 * (o + k) + 3] = y1; }
+            boxes[4 * (o + k) + 0] = __fdiv_rn((float)(x0 + x1) * 0.5f, norm_x);
+            boxes[4 * (o + k) + 1] = __fdiv_rn((float)(y0 + y1) * 0.5f, norm_y);
+            boxes[4 * (o + k) + 2] = __fdiv_rn((float)(x1 - x0), norm_x);
+            boxes[4 * (o + k) + 3] = __fdiv_rn((float)(y1 - y0), norm_y);
+        }
+        counts[m] = max(n, 1);
+    }
+}
+
 __global__ void cam_minmax_init_kernel(int* minmax, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -278,9 +399,9 @@ extern "C" __attribute__((visibility("default"))) int64_t spe_cam_boxes_workspac
     return (int64_t)(align256(n * 2 * 4) + align256(n * npix) + 4 * align256(n * npix * 4) + align256(n * npix * 16));
 }
 
-extern "C" __attribute__((visibility("default"))) int spe_cam_boxes(const float* cams, int B, int C, int h, int w, const int32_t* pairs, int npairs, int rows, int cols,
-                                                                    int thr_u8, float norm_x, float norm_y, float* boxes_out, int32_t* xyxy_out, void* workspace,
-                                                                    int64_t workspace_bytes, void* stream) {
+namespace {
+int cam_boxes_run(const float* cams, int B, int C, int h, int w, const int32_t* pairs, int npairs, int rows, int cols, int thr_u8, float norm_x, float norm_y,
+                  double area_ratio, int max_boxes, float* boxes_out, int32_t* xyxy_out, int32_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream) {
     SPE_CHECK(cams && pairs && boxes_out && workspace && B > 0 && C > 0 && h > 0 && w > 0 && npairs > 0 && rows > 1 && cols > 1, "spe_cam_boxes: bad argument");
     SPE_CHECK((long long)rows * cols < (1LL << 30) && thr_u8 >= 0 && thr_u8 <= 255 && norm_x > 0.f && norm_y > 0.f, "spe_cam_boxes: bad argument");
     SPE_CHECK(workspace_bytes >= spe_cam_boxes_workspace_bytes(npairs, rows, cols), "spe_cam_boxes: workspace too small");
@@ -312,11 +433,33 @@ extern "C" __attribute__((visibility("default"))) int spe_cam_boxes(const float*
     SPE_LAUNCHED();
     cam_parent_kernel<<<grid, CB_THREADS, 0, st>>>(g, ws);
     SPE_LAUNCHED();
-    cam_top_kernel<<<grid, CB_THREADS, 0, st>>>(g, ws);
-    SPE_LAUNCHED();
     cam_cells_kernel<<<grid, CB_THREADS, 0, st>>>(g, ws);
     SPE_LAUNCHED();
-    cam_select_kernel<<<npairs, CB_THREADS, 0, st>>>(g, ws, norm_x, norm_y, boxes_out, xyxy_out);
-    SPE_LAUNCHED();
+    if (max_boxes <= 0) {
+        cam_select_kernel<<<npairs, CB_THREADS, 0, st>>>(g, ws, norm_x, norm_y, boxes_out, xyxy_out);
+        SPE_LAUNCHED();
+    } else {
+        cam_hole_edges_kernel<<<grid, CB_THREADS, 0, st>>>(g, ws);
+        SPE_LAUNCHED();
+        cam_select_multi_kernel<<<npairs, CB_THREADS, 0, st>>>(g, ws, norm_x, norm_y, area_ratio, max_boxes, boxes_out, xyxy_out, counts_out);
+        SPE_LAUNCHED();
+    }
     return 0;
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int spe_cam_boxes(const float* cams, int B, int C, int h, int w, const int32_t* pairs, int npairs, int rows, int cols,
+                                                                    int thr_u8, float norm_x, float norm_y, float* boxes_out, int32_t* xyxy_out, void* workspace,
+                                                                    int64_t workspace_bytes, void* stream) {
+    return cam_boxes_run(cams, B, C, h, w, pairs, npairs, rows, cols, thr_u8, norm_x, norm_y, 0.0, 0, boxes_out, xyxy_out, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int spe_cam_boxes_multi(const float* cams, int B, int C, int h, int w, const int32_t* pairs, int npairs, int rows,
+                                                                          int cols, int thr_u8, float norm_x, float norm_y, double area_ratio, int max_boxes,
+                                                                          float* boxes_out, int32_t* xyxy_out, int32_t* counts_out, void* workspace,
+                                                                          int64_t workspace_bytes, void* stream) {
+    SPE_CHECK(max_boxes >= 1 && max_boxes <= CB_MAXBOX && counts_out && area_ratio >= 0.0, "spe_cam_boxes_multi: 1 <= max_boxes <= %d", CB_MAXBOX);
+    return cam_boxes_run(cams, B, C, h, w, pairs, npairs, rows, cols, thr_u8, norm_x, norm_y, area_ratio, max_boxes, boxes_out, xyxy_out, counts_out, workspace,
+                         workspace_bytes, stream);
 }

@@ -131,6 +131,28 @@ class TrainStep:
             self.optimizer.step()                     # single all-reduce after the step (SPE_AR_OVERLAP=0): the update follows it
         return res
 
+    def prefetch(self, images):
+        """Start the host-to-device copy of the NEXT step's image batch (a pinned host tensor) on a copy stream, so that it overlaps
+        the step that is running; the next __call__ with the same tensor object picks the staged copy up (graph mode).  Input
+        pipelining, what a data loader with pin_memory + non_blocking does for the reference loop."""
+        if not (torch.is_tensor(images) and not images.is_cuda and images.is_pinned()):
+            return
+        dev = next(self.model.parameters()).device
+        if self.__dict__.get("_copy_stream") is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [None, None]
+            self._stage_i = 0
+        i = self._stage_i = self._stage_i ^ 1
+        if self._stage[i] is None or self._stage[i].shape != images.shape:
+            self._stage[i] = torch.empty(images.shape, dtype=torch.float32, device=dev)
+        ev = torch.cuda.Event()
+        if self.__dict__.get("_stage_read") is not None:
+            self._copy_stream.wait_event(self._stage_read)
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[i].copy_(images, non_blocking=True)
+            ev.record()
+        self._prefetched = (images, self._stage[i], ev)
+
     def close(self):
         """Drop the captured graphs.  With N > 1 they hold the gradient all-reduce: NCCL keeps a communicator alive (and
         destroy_process_group() waiting) for as long as a captured collective exists, so call this before tearing the group down."""
@@ -165,7 +187,16 @@ class TrainStep:
         if st is None:
             st = self._capture(images, tg, tr, cap, rs if dj else None)
             self._g[key] = st
-        st["images"].copy_(images, non_blocking=True)
+        pre = self.__dict__.pop("_prefetched", None)
+        if pre is not None and pre[0] is images and pre[1].shape == st["images"].shape:
+            # the batch was staged by prefetch() on the copy stream while the previous step ran: a device-to-device copy is left
+            self._prefetch_hits = self.__dict__.get("_prefetch_hits", 0) + 1
+            torch.cuda.current_stream().wait_event(pre[2])
+            st["images"].copy_(pre[1], non_blocking=True)
+            self._stage_read = torch.cuda.Event()
+            self._stage_read.record()                 # a later prefetch may overwrite the staging buffers only after this copy
+        else:
+            st["images"].copy_(images, non_blocking=True)
         for name, raw, t, r in (("T", "Traw", tg, rs[0]), ("Tr", "Trraw", tr, rs[-1])):
             if st[name] is None:
                 continue

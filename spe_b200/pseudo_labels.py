@@ -1,4 +1,4 @@
-"""engine.get_pseudo_label of the reference (engine.py:310-352) on the device: the class-activation maps never leave the
+"""engine.get_pseudo_label (engine.py:310-352) and engine.get_pseudo_label_multi_boxes (:356-398) of the reference on the device: the class-activation maps never leave the
 GPU.  One batched sequence of launches (csrc/cam_boxes.cu) handles every (image, present class) pair: bilinear resize to the image
 size, min-max normalisation, uint8 quantisation, threshold, connected components + contour areas, bounding box of the largest
 contour -- bit-exact with the cv2 calls the reference makes (tests/test_cam_boxes_gpu.py)."""
@@ -28,6 +28,55 @@ def cam_boxes(cams_cls, pairs, image_size, cam_thr=0.2, return_xyxy=False):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     check(lib().spe_cam_boxes(ptr(cams), B, C, h, w, ptr(pairs), n, rows, cols, thr, float(W), float(H), ptr(boxes), ptr(xyxy), ptr(ws), nbytes, stream()))
     return (boxes, xyxy) if return_xyxy else boxes
+
+
+def cam_boxes_multi(cams_cls, pairs, image_size, cam_thr=0.2, area_ratio=0.5, max_boxes=16, return_xyxy=False):
+    """cams_deit.get_multi_bboxes for every (image, class) pair: boxes f32 [npairs, max_boxes, 4] (cxcywh / [W,H,W,H], by decreasing
+    contour area), counts i32 [npairs] (+ integer boxes) -- all on the device."""
+    if not cams_cls.is_cuda:
+        raise RuntimeError("spe_b200 CAM boxes need CUDA tensors (no CPU fallback exists)")
+    dev = cams_cls.device
+    cams = cams_cls.detach().float().contiguous()
+    B, C, h, w = cams.shape
+    pairs = torch.as_tensor(pairs, dtype=torch.int32).reshape(-1, 2).to(dev).contiguous()
+    n = int(pairs.shape[0])
+    H, W = int(image_size[0]), int(image_size[1])
+    boxes = torch.zeros((n, max_boxes, 4), dtype=torch.float32, device=dev)
+    xyxy = torch.zeros((n, max_boxes, 4), dtype=torch.int32, device=dev)
+    counts = torch.zeros((n,), dtype=torch.int32, device=dev)
+    if n:
+        rows, cols = W, H
+        nbytes = int(lib().spe_cam_boxes_workspace_bytes(n, rows, cols))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib().spe_cam_boxes_multi(ptr(cams), B, C, h, w, ptr(pairs), n, rows, cols, int(cam_thr * 255), float(W), float(H), float(area_ratio),
+                                        int(max_boxes), ptr(boxes), ptr(xyxy), ptr(counts), ptr(ws), nbytes, stream()))
+    return (boxes, counts, xyxy) if return_xyxy else (boxes, counts)
+
+
+@torch.no_grad()
+def get_pseudo_label_multi_boxes(outputs, samples, targets, args=None, cam_thr=None, area_ratio=None, max_boxes=16):
+    """Same call as the reference's engine.get_pseudo_label_multi_boxes (engine.py:356-398), the variant its refine training loops use:
+    per image {'boxes': cxcywh normalised [k,4], 'labels': class + 1 [k]} with every contour above args.multi_box_ratio of the largest.
+    One D2H read of the per-pair box counts (the result is ragged); maps and boxes stay on the device."""
+    cams = outputs["cams_cls"]
+    tens = samples.tensors if hasattr(samples, "tensors") else samples
+    H, W = int(tens.shape[-2]), int(tens.shape[-1])
+    thr = cam_thr if cam_thr is not None else float(getattr(args, "cam_thr", 0.2))
+    ratio = area_ratio if area_ratio is not None else float(getattr(args, "multi_box_ratio", 0.5))
+    ncls = int(getattr(args, "num_classes", cams.shape[1])) if args is not None else cams.shape[1]
+    labels = torch.stack([t["img_label"].reshape(-1)[:ncls] for t in targets]).cpu()
+    pairs = torch.nonzero(labels > 0)
+    boxes, counts = cam_boxes_multi(cams, pairs, (H, W), thr, ratio, max_boxes)
+    cnt = counts.cpu()
+    keep = torch.arange(max_boxes)[None, :] < cnt[:, None]                       # [npairs, max_boxes]
+    flat = boxes[keep.to(boxes.device)]                                           # pairs in order, boxes by decreasing area
+    cls = (pairs[:, 1] + 1).repeat_interleave(cnt.long()).to(cams.device)
+    per_img = torch.zeros(len(targets), dtype=torch.int64).index_add_(0, pairs[:, 0], cnt.long()).tolist()
+    out, o = [], 0
+    for n in per_img:
+        out.append({"boxes": flat[o:o + n], "labels": cls[o:o + n]})
+        o += n
+    return out
 
 
 @torch.no_grad()
