@@ -14,7 +14,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 # per-file extra flags: the matcher cost must not contract a*b+c into FMAs (SURVEY.md H2 iii)
 EXTRA = {"matcher.cu": ["-fmad=false"]}
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "matcher.cu", "criterion.cu", "rowwise.cu", "talking_generic.cu", "attn_fused.cu", "talking_fused.cu", "talking_h16.cu", "optim.cu", "targets.cu", "cam_boxes.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "matcher.cu", "criterion.cu", "rowwise.cu", "talking_generic.cu", "attn_fused.cu", "talking_fused.cu", "talking_h16.cu", "talking_h8.cu", "optim.cu", "targets.cu", "cam_boxes.cu"]
 
 
 def _stale(target, deps):

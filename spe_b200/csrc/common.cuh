@@ -58,6 +58,13 @@ static inline int spe_num_sms() {
 }
 
 // talking-heads kernels for head counts outside {2, 4, 8} (talking_generic.cu)
+// talking_h8.cu: H = 8 streamed from global memory on m16n8k8 fragments (s16: S holds f16 logits)
+int spe_talking_h8_grid(int B, int Nq);
+bool spe_talking_h8_fits(long long ldS, long long ldA);
+int spe_talking_h8_fwd(const void* S, int s16, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats, int B, int Nq, int Nk,
+                       long long ldS, long long ldA, cudaStream_t st);
+int spe_talking_h8_bwd(const void* S, int s16, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B, int Nq,
+                       int Nk, long long ldS, long long ldA, float* part, cudaStream_t st);
 // talking_h16.cu: H = 16 on mma.sync (s16: S holds f16 logits)
 int spe_talking_h16_grid(int B, int Nq);
 int spe_talking_h16_fwd(const void* S, int s16, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats, int B, int Nq, int Nk,

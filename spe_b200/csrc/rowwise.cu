@@ -1570,6 +1570,14 @@ static int talking_fwd_launch(const void* Sv, void* A, const float* Wl, const fl
     return 0;
 }
 
+// SPE_TH8_STREAM=0: keep H = 8 (fp16 logits) on the kernels of this file (A/B switch); default: the register-chained kernels of talking_h8.cu
+static bool talking_h8_on(int H) {
+    static const bool off = getenv("SPE_TH8_STREAM") != nullptr && getenv("SPE_TH8_STREAM")[0] == '0';
+    return H == 8 && !off;
+}
+static int talking_h8_bwd_run(const void* S, int s16, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B, int Nq,
+                              int Nk, long long ldS, long long ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* workspace, cudaStream_t st);
+
 // SPE_TH16_GENERIC=1: keep H = 16 on the CUDA-core kernels (A/B switch)
 static bool talking_h16_on(int H) {
     static const bool off = getenv("SPE_TH16_GENERIC") != nullptr && getenv("SPE_TH16_GENERIC")[0] == '1';
@@ -1597,6 +1605,7 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd(co
 extern "C" __attribute__((visibility("default"))) int spe_talking_s16_supported(int H, int Nk, int64_t ldS, int64_t ldA) {
     if (ldS % 8 != 0 || ldA % 8 != 0 || ldS < Nk || ldA < Nk) return 0;
     if (talking_h16_on(H)) return 1;                     // streamed from global memory: no row-size limit
+    if (talking_h8_on(H) && spe_talking_h8_fits(ldS, ldA)) return 1;
     if (H != 2 && H != 4 && H != 8) return 0;
     return talking_fwd_smem16(H, (int)ldS) <= 100 * 1024 + 4096 && talking_bwd_smem16(H, (int)ldS, (int)ldA) <= 104 * 1024 ? 1 : 0;
 }
@@ -1608,6 +1617,10 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_fwd_s1
     if (H == 16) {
         SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 4.0, ST(stream));
         return spe_talking_h16_fwd(S16, 1, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
+    }
+    if (talking_h8_on(H) && spe_talking_h8_fits(ldS, ldA)) {
+        SpeProfScope prof(SPE_FAM_TALKING_FWD, (double)B * H * Nq * Nk * 4.0, ST(stream));
+        return spe_talking_h8_fwd(S16, 1, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream));
     }
     switch (H) {
         case 2: return talking_fwd_launch<2>(S16, A, Wl, bl, Ww, bw, stats, B, Nq, Nk, ldS, ldA, ST(stream), true);
@@ -1670,6 +1683,19 @@ static int talking_bwd_launch(const void* Sv, const void* dA, void* dS, const fl
     return 0;
 }
 
+static int talking_h8_bwd_run(const void* S, int s16, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B, int Nq,
+                              int Nk, long long ldS, long long ldA, float* dWl, float* dbl, float* dWw, float* dbw, float* workspace, cudaStream_t st) {
+    const int H = 8, grid = spe_talking_h8_grid(B, Nq);
+    {
+        SpeProfScope prof(SPE_FAM_TALKING_BWD, (double)B * H * Nq * Nk * (s16 ? 6.0 : 8.0), st);
+        if (spe_talking_h8_bwd(S, s16, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, workspace, st)) return -1;
+    }
+    const int NP = 2 * H * H + 2 * H;
+    talking_bwd_finalize_kernel<<<(NP + 7) / 8, 256, 0, st>>>(workspace, grid, H, dWl, dbl, dWw, dbw);
+    SPE_LAUNCHED();
+    return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd_s16(const void* S16, const void* dA, void* dS, const float* Wl, const float* bl,
                                                                                   const float* Ww, const float* bw, const float* stats, int B, int H, int Nq, int Nk,
                                                                                   int64_t ldS, int64_t ldA, float* dWl, float* dbl, float* dWw, float* dbw,
@@ -1678,6 +1704,7 @@ extern "C" __attribute__((visibility("default"))) int spe_talking_softmax_bwd_s1
     SPE_CHECK(S16 && dA && dS && Wl && bl && Ww && stats && dWl && dbl && dWw && dbw && workspace, "spe_talking_softmax_bwd_s16: null argument");
     SPE_CHECK(spe_talking_s16_supported(H, Nk, ldS, ldA), "spe_talking_softmax_bwd_s16: unsupported shape H=%d Nk=%d", H, Nk);
     SPE_CHECK(workspace_floats >= spe_talking_softmax_bwd_workspace(B, H, Nq, Nk), "spe_talking_softmax_bwd_s16: workspace too small");
+    if (talking_h8_on(H) && spe_talking_h8_fits(ldS, ldA)) return talking_h8_bwd_run(S16, 1, dA, dS, Wl, bl, Ww, stats, B, Nq, Nk, ldS, ldA, dWl, dbl, dWw, dbw, workspace, ST(stream));
     if (H == 16) {
         const int grid = spe_talking_h16_grid(B, Nq);
         {

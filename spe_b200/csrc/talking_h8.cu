@@ -1,0 +1,474 @@
+// Talking-heads mix -> softmax -> mix (cait.py:381-386) and its backward for H = 8 (CaiT-S24 / the benchmarked cfg2), fp16 logits:
+// the row staging of rowwise.cu (bulk async copies of the (b, q) row into shared memory, double buffered) with the transposed, register-
+// chained mixes of talking_h16.cu on m16n8k8 fragments (8 heads = the k / n extent of one MMA).
+//
+// Why: the rowwise.cu kernels spend ~31 (forward) / ~41 (backward) instructions per logit (ncu: issue bound at 2.8-3.0 TB/s); a first
+// version of this file that streamed from global memory needed ~10 but was latency bound at N = 1600 (3 steps per warp and sweep).
+// Here every thread owns 4 consecutive keys of 2 heads (one 8-byte shared-memory read per head), builds MMA fragments with byte
+// permutes, and chains the mixes in registers (keys are the MMA rows, so an accumulator fragment IS the next A fragment):
+//   forward  sweep A: L = S Wl'^T (+ bias)        -> online (max, sum); the exponentials of the statistics run as ex2.f16x2
+//            sweep B: accumulator initialised with bias - c2 + 4, so P' = 2^4 P = ex2.f16x2(pack(L')) is ALREADY the A fragment of the
+//                     output mix (Ww 2^-4): 2 packs + 2 MUFU per 16 x 8 tile, no per-element subtract / convert
+//   backward sweep B: P (f32), dP = dA Ww, rho = sum P dP, dWw += dA^T P       sweep C: dL = P (dP - rho), dS = dL Wl, dWl += dL^T S
+//            parameter-gradient outer products: movmatrix transposes of the same fragments, one m16n8k16 MMA per tile (rows 8..15 idle).
+// Precision: as rowwise.cu -- logits through one f16 pass; probabilities in f16 (2^4 P: relative 2^-11, tails down to 4e-9); the
+// exponent argument of sweep B is rounded to f16 (|L'| <= 4 for the dominant probabilities: <= 7e-4 relative); gradient mixes bf16 with
+// hi + lo weights.  Statistics convention of rowwise.cu: stats[row][g] = c2 = max_j L2 + log2 sum_j 2^(L2 - max), L2 = log2e (Wl S + bl).
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr float T8_LOG2E = 1.4426950408889634f;
+constexpr float T8_NEG = -1e30f;
+constexpr float T8_SHIFT = 4.f;          // P' = 2^4 P in f16
+constexpr float T8_UNSHIFT = 0.0625f;
+
+__device__ __forceinline__ uint32_t pk_f16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pk_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t add_h2(uint32_t a, uint32_t b) {
+    uint32_t y;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+    return y;
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t x) { return __half22float2(*reinterpret_cast<const __half2*>(&x)); }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ uint32_t movm(uint32_t x) {
+    uint32_t y;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+// D (16 x 8, f32) += A (16 x 8) B (8 x 8)
+__device__ __forceinline__ void mma8_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void mma8_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void mma16_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ---- row staging (as rowwise.cu): the (b, q) row of all 8 heads comes into shared memory by bulk async copies, double buffered ----
+__device__ __forceinline__ uint32_t t8_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t8_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void t8_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void t8_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 8000000000LL) __trap();          // a protocol bug traps instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void t8_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// shared-memory pitch of a 16-bit head row: = 8 (mod 32) elements, so the 8-byte reads of a half warp (4 key groups x 4 head pairs,
+// head pairs 2 pitches apart) fall into 16 distinct 8-byte bank pairs
+__host__ __device__ __forceinline__ int t8_pitch(int ld) { return ld + ((40 - ld % 32) % 32); }
+
+constexpr int T8_CH = 32;       // keys per warp step: 2 MMA tiles; a thread owns 4 consecutive keys of heads 2 tig, 2 tig + 1
+
+// the 4 keys [jb, jb + 4) of heads 2 tig and 2 tig + 1 from a staged row, as 16-bit pairs along the keys: r[hs][t] = {key 2 t, key 2 t + 1}.
+// Keys >= Nk come back as 0 (the pitch padding may hold anything).
+__device__ __forceinline__ void lds_row(const uint16_t* __restrict__ rowbuf, int pitch, int tig, int jb, int Nk, uint32_t (&r)[2][2]) {
+#pragma unroll
+    for (int hs = 0; hs < 2; ++hs) {
+        const uint2 v = *reinterpret_cast<const uint2*>(rowbuf + (2 * tig + hs) * pitch + jb);
+        r[hs][0] = v.x;
+        r[hs][1] = v.y;
+    }
+    if (jb + 4 > Nk) {
+#pragma unroll
+        for (int hs = 0; hs < 2; ++hs)
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if (jb + 2 * t >= Nk) r[hs][t] = 0u;
+                else if (jb + 2 * t + 1 >= Nk) r[hs][t] &= 0xffffu;
+            }
+    }
+}
+// tile t of a step as an A fragment [rows = keys (slot 2 t | slot 2 t + 1), k = heads 2 tig, 2 tig + 1]
+__device__ __forceinline__ void frag(const uint32_t (&r)[2][2], int t, uint32_t& a0, uint32_t& a1) {
+    a0 = prmt(r[0][t], r[1][t], 0x5410u);
+    a1 = prmt(r[0][t], r[1][t], 0x7632u);
+}
+// key validity of a partial group: d0, d1 belong to key jb + 2 t, d2, d3 to key jb + 2 t + 1
+__device__ __forceinline__ void mask_tile(float (&d)[4], int jb, int t, int Nk, float v) {
+    if (jb + 2 * t >= Nk) { d[0] = v; d[1] = v; }
+    if (jb + 2 * t + 1 >= Nk) { d[2] = v; d[3] = v; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// forward.  dynamic shared memory: [2][8][pS] f16 row buffers
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 2) th8_fwd_kernel(const uint16_t* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
+                                                            const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
+                                                            float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
+    extern __shared__ __align__(128) uint8_t t8sm[];
+    uint16_t* Sbuf = reinterpret_cast<uint16_t*>(t8sm);
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ float redm[NW][8], redz[NW][8], sc2[8];
+    const int pS = t8_pitch(ldS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    // B operands: logit mix [k = h, n = g] = Wl[g][h] log2e;  output mix [k = g, n = o] = Ww[o][g] 2^-4
+    const uint32_t w1 = pk_f16(Wl[gid * 8 + 2 * tig] * T8_LOG2E, Wl[gid * 8 + 2 * tig + 1] * T8_LOG2E);
+    const uint32_t w2 = pk_f16(Ww[gid * 8 + 2 * tig] * T8_UNSHIFT, Ww[gid * 8 + 2 * tig + 1] * T8_UNSHIFT);
+    const float b1[2] = {bl[2 * tig] * T8_LOG2E, bl[2 * tig + 1] * T8_LOG2E};
+    const float b2[2] = {bw[2 * tig], bw[2 * tig + 1]};
+    const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
+    const uint32_t bar0 = t8_smem(bars);
+    if (tid == 0) {
+        t8_mbar_init(bar0, 1); t8_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int row, int buf) {                                 // thread 0 only
+        const int b = row / Nq, q = row % Nq;
+        const uint32_t bar = bar0 + 8 * buf;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        t8_mbar_expect_tx(bar, (uint32_t)(8 * ldS * 2));
+        for (int h = 0; h < 8; ++h)
+            t8_bulk_g2s(t8_smem(Sbuf + ((size_t)buf * 8 + h) * pS), S + ((long long)b * 8 * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 2), bar);
+    };
+    const int nst = (ldA + T8_CH - 1) / T8_CH;
+    const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;         // contiguous steps per warp (N = 1600: 50 steps, 5 per warp at NW = 10)
+    if (tid == 0 && blockIdx.x < rows_total) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x, buf ^ 1);      // buf^1 was released by the previous iteration's last barrier
+        t8_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        const uint16_t* Sb = Sbuf + (size_t)buf * 8 * pS;
+        const int b = row / Nq, q = row % Nq;
+        uint16_t* Ab = A + ((long long)b * 8 * Nq + q) * ldA;
+        // ---- sweep A
+        float m[2] = {T8_NEG, T8_NEG}, z[2] = {0.f, 0.f};
+        for (int st = s0; st < s1; ++st) {
+            const int jb = st * T8_CH + gid * 4;
+            uint32_t r[2][2];
+            lds_row(Sb, pS, tig, jb, Nk, r);
+            float L[2][4];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                uint32_t a0, a1;
+                frag(r, t, a0, a1);
+                L[t][0] = b1[0]; L[t][1] = b1[1]; L[t][2] = b1[0]; L[t][3] = b1[1];
+                mma8_f16(L[t], a0, a1, w1);
+            }
+            if (jb + 4 > Nk) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) mask_tile(L[t], jb, t, Nk, T8_NEG);
+            }
+#pragma unroll
+            for (int gs = 0; gs < 2; ++gs) {
+                const float mx = fmaxf(fmaxf(m[gs], fmaxf(L[0][gs], L[0][2 + gs])), fmaxf(L[1][gs], L[1][2 + gs]));
+                const uint32_t acc = add_h2(ex2_h2(pk_f16(L[0][gs] - mx, L[0][2 + gs] - mx)), ex2_h2(pk_f16(L[1][gs] - mx, L[1][2 + gs] - mx)));
+                const float2 s2 = h2_to_f2(acc);
+                z[gs] = z[gs] * ex2f(m[gs] - mx) + (s2.x + s2.y);
+                m[gs] = mx;
+            }
+        }
+#pragma unroll
+        for (int gs = 0; gs < 2; ++gs) {
+            if (m[gs] == T8_NEG) z[gs] = 0.f;             // no valid key seen: (NEG, junk) must vanish in the merge
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+                const float mo = __shfl_xor_sync(0xffffffffu, m[gs], off), zo = __shfl_xor_sync(0xffffffffu, z[gs], off);
+                const float mx = fmaxf(m[gs], mo);
+                z[gs] = z[gs] * ex2f(m[gs] - mx) + zo * ex2f(mo - mx);
+                m[gs] = mx;
+            }
+            if (gid == 0) { redm[warp][2 * tig + gs] = m[gs]; redz[warp][2 * tig + gs] = z[gs]; }
+        }
+        __syncthreads();
+        if (tid < 8) {
+            float M = T8_NEG, Z = 0.f;
+            for (int w = 0; w < NW; ++w) M = fmaxf(M, redm[w][tid]);
+            for (int w = 0; w < NW; ++w) Z += redz[w][tid] * ex2f(redm[w][tid] - M);
+            const float c2 = M + log2f(Z);
+            sc2[tid] = c2;
+            if (stats) stats[(long long)row * 8 + tid] = c2;
+        }
+        __syncthreads();
+        // ---- sweep B
+        const float ci[2] = {b1[0] - sc2[2 * tig] + T8_SHIFT, b1[1] - sc2[2 * tig + 1] + T8_SHIFT};
+        for (int st = s0; st < s1; ++st) {
+            const int jb = st * T8_CH + gid * 4;
+            uint32_t r[2][2], pkt[2][2];
+            lds_row(Sb, pS, tig, jb, Nk, r);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                uint32_t a0, a1;
+                frag(r, t, a0, a1);
+                float d[4] = {ci[0], ci[1], ci[0], ci[1]};
+                mma8_f16(d, a0, a1, w1);
+                if (jb + 4 > Nk) mask_tile(d, jb, t, Nk, T8_NEG);
+                const uint32_t p0 = ex2_h2(pk_f16(d[0], d[1])), p1 = ex2_h2(pk_f16(d[2], d[3]));     // = the A fragment of the output mix
+                float e[4] = {b2[0], b2[1], b2[0], b2[1]};
+                mma8_f16(e, p0, p1, w2);
+                if (jb + 4 > Nk) mask_tile(e, jb, t, Nk, 0.f);                                      // padding keys stay clean (the PV GEMM reads the pitch)
+                pkt[0][t] = pk_bf16(e[0], e[2]);
+                pkt[1][t] = pk_bf16(e[1], e[3]);
+            }
+            if (jb < ldA) {
+#pragma unroll
+                for (int os = 0; os < 2; ++os) *reinterpret_cast<uint2*>(Ab + (long long)(2 * tig + os) * hA + jb) = make_uint2(pkt[os][0], pkt[os][1]);
+            }
+        }
+        __syncthreads();                                 // the row buffer, sc2 and red* are free again
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+struct GradW8 { uint32_t hi, lo; };
+// B[k][n] = W[k * 8 + n]: rows k = 2 tig, 2 tig + 1 of column n = gid, bf16 hi + lo
+__device__ __forceinline__ GradW8 load_gradw8(const float* __restrict__ W, int gid, int tig) {
+    const float x0 = W[(2 * tig) * 8 + gid], x1 = W[(2 * tig + 1) * 8 + gid];
+    GradW8 w;
+    w.hi = pk_bf16(x0, x1);
+    w.lo = pk_bf16(x0 - __uint_as_float(w.hi << 16), x1 - __uint_as_float(w.hi & 0xffff0000u));
+    return w;
+}
+// f16x2 -> bf16x2 (same two values)
+__device__ __forceinline__ uint32_t h2_to_bf2(uint32_t x) {
+    const float2 f = h2_to_f2(x);
+    return pk_bf16(f.x, f.y);
+}
+// acc (rows 0..7 = heads of X, columns = heads of Y) += sum over the tile's 16 keys X[key][.] Y[key][.];  (x0, x1), (y0, y1): m16k8 A-style
+__device__ __forceinline__ void outer8(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, float (&acc)[4]) {
+    mma16_bf16(acc, movm(x0), 0u, movm(x1), 0u, movm(y0), movm(y1));
+}
+
+// backward.  dynamic shared memory: [2][8][pS] f16 logit rows, then [2][8][pA] bf16 dA rows
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __restrict__ S, const uint16_t* dA, uint16_t* dS, const float* __restrict__ Wl,
+                                                            const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ stats,
+                                                            int rows_total, int Nq, int Nk, int ldS, int ldA, float* __restrict__ part) {
+    constexpr int NT = NW * 32;
+    constexpr int NP = 2 * 8 * 8 + 2 * 8;
+    extern __shared__ __align__(128) uint8_t t8sm[];
+    const int pS = t8_pitch(ldS), pA = t8_pitch(ldA);
+    uint16_t* Sbuf = reinterpret_cast<uint16_t*>(t8sm);
+    uint16_t* Dbuf = Sbuf + (size_t)2 * 8 * pS;
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ float redr[NW][8], srho[8], sc2[8], spart[NP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const uint32_t w1 = pk_f16(Wl[gid * 8 + 2 * tig] * T8_LOG2E, Wl[gid * 8 + 2 * tig + 1] * T8_LOG2E);
+    const float b1[2] = {bl[2 * tig] * T8_LOG2E, bl[2 * tig + 1] * T8_LOG2E};
+    const GradW8 gww = load_gradw8(Ww, gid, tig);       // dP[j, g] = sum_o dA[j, o] Ww[o, g]
+    const GradW8 gwl = load_gradw8(Wl, gid, tig);       // dS[j, h] = sum_g dL[j, g] Wl[g, h]
+    float accWw[4] = {0.f, 0.f, 0.f, 0.f}, accWl[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < NP; i += NT) spart[i] = 0.f;
+    const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
+    const uint32_t bar0 = t8_smem(bars);
+    if (tid == 0) {
+        t8_mbar_init(bar0, 1); t8_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int row, int buf) {                                 // thread 0 only
+        const int b = row / Nq, q = row % Nq;
+        const uint32_t bar = bar0 + 8 * buf;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        t8_mbar_expect_tx(bar, (uint32_t)(8 * ldS * 2 + 8 * ldA * 2));
+        for (int h = 0; h < 8; ++h) {
+            t8_bulk_g2s(t8_smem(Sbuf + ((size_t)buf * 8 + h) * pS), S + ((long long)b * 8 * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 2), bar);
+            t8_bulk_g2s(t8_smem(Dbuf + ((size_t)buf * 8 + h) * pA), dA + ((long long)b * 8 * Nq + q) * ldA + h * hA, (uint32_t)(ldA * 2), bar);
+        }
+    };
+    const int nst = (ldA + T8_CH - 1) / T8_CH;
+    const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;
+    if (tid == 0 && blockIdx.x < rows_total) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x, buf ^ 1);
+        if (tid < 8) sc2[tid] = stats[(long long)row * 8 + tid];
+        t8_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        __syncthreads();
+        const uint16_t* Sb = Sbuf + (size_t)buf * 8 * pS;
+        const uint16_t* Db = Dbuf + (size_t)buf * 8 * pA;
+        const int b = row / Nq, q = row % Nq;
+        uint16_t* dSb = dS + ((long long)b * 8 * Nq + q) * ldA;      // may alias this row of dA: it is staged in shared memory by now
+        const float ci[2] = {b1[0] - sc2[2 * tig], b1[1] - sc2[2 * tig + 1]};
+        float rho[2] = {0.f, 0.f};
+        // ---- sweep B
+        for (int st = s0; st < s1; ++st) {
+            const int jb = st * T8_CH + gid * 4;
+            uint32_t r[2][2], rd[2][2];
+            lds_row(Sb, pS, tig, jb, Nk, r);
+            lds_row(Db, pA, tig, jb, Nk, rd);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                uint32_t a0, a1, d0, d1;
+                frag(r, t, a0, a1);
+                frag(rd, t, d0, d1);
+                float P[4] = {ci[0], ci[1], ci[0], ci[1]};
+                mma8_f16(P, a0, a1, w1);
+                if (jb + 4 > Nk) mask_tile(P, jb, t, Nk, T8_NEG);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) P[i] = ex2f(P[i]);
+                float dP[4] = {0.f, 0.f, 0.f, 0.f};
+                mma8_bf16(dP, d0, d1, gww.hi);
+                mma8_bf16(dP, d0, d1, gww.lo);
+                rho[0] += P[0] * dP[0] + P[2] * dP[2];
+                rho[1] += P[1] * dP[1] + P[3] * dP[3];
+                outer8(d0, d1, pk_bf16(P[0], P[1]), pk_bf16(P[2], P[3]), accWw);            // [o, g]
+            }
+        }
+#pragma unroll
+        for (int gs = 0; gs < 2; ++gs) {
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) rho[gs] += __shfl_xor_sync(0xffffffffu, rho[gs], off);
+            if (gid == 0) redr[warp][2 * tig + gs] = rho[gs];
+        }
+        __syncthreads();
+        if (tid < 8) {
+            float x = 0.f;
+            for (int w = 0; w < NW; ++w) x += redr[w][tid];
+            srho[tid] = x;
+        }
+        __syncthreads();
+        rho[0] = srho[2 * tig];
+        rho[1] = srho[2 * tig + 1];
+        // ---- sweep C
+        for (int st = s0; st < s1; ++st) {
+            const int jb = st * T8_CH + gid * 4;
+            uint32_t r[2][2], rd[2][2], pkt[2][2];
+            lds_row(Sb, pS, tig, jb, Nk, r);
+            lds_row(Db, pA, tig, jb, Nk, rd);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                uint32_t a0, a1, d0, d1;
+                frag(r, t, a0, a1);
+                frag(rd, t, d0, d1);
+                float P[4] = {ci[0], ci[1], ci[0], ci[1]};
+                mma8_f16(P, a0, a1, w1);
+                if (jb + 4 > Nk) mask_tile(P, jb, t, Nk, T8_NEG);
+                float dP[4] = {0.f, 0.f, 0.f, 0.f};
+                mma8_bf16(dP, d0, d1, gww.hi);
+                mma8_bf16(dP, d0, d1, gww.lo);
+                float dL[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dL[i] = ex2f(P[i]) * (dP[i] - rho[i & 1]);
+                const uint32_t l0 = pk_bf16(dL[0], dL[1]), l1 = pk_bf16(dL[2], dL[3]);
+                float dSv[4] = {0.f, 0.f, 0.f, 0.f};
+                mma8_bf16(dSv, l0, l1, gwl.hi);
+                mma8_bf16(dSv, l0, l1, gwl.lo);
+                pkt[0][t] = pk_bf16(dSv[0], dSv[2]);
+                pkt[1][t] = pk_bf16(dSv[1], dSv[3]);
+                outer8(l0, l1, h2_to_bf2(a0), h2_to_bf2(a1), accWl);                         // [g, h]
+            }
+            if (jb < ldA) {
+#pragma unroll
+                for (int os = 0; os < 2; ++os) *reinterpret_cast<uint2*>(dSb + (long long)(2 * tig + os) * hA + jb) = make_uint2(pkt[os][0], pkt[os][1]);
+            }
+        }
+        __syncthreads();                                 // the row buffers, sc2, srho, redr are free again
+    }
+    // per-CTA partials: [dWl (g, h) | dbl = 0 | dWw (o, g) | dbw = 0]  (talking_bwd_finalize_kernel's layout)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        atomicAdd(&spart[gid * 8 + 2 * tig + i], accWl[i]);
+        atomicAdd(&spart[64 + 8 + gid * 8 + 2 * tig + i], accWw[i]);
+    }
+    __syncthreads();
+    float* pr = part + (long long)blockIdx.x * NP;
+    for (int i = tid; i < NP; i += NT) pr[i] = spart[i];
+}
+
+int t8_grid(int B, int Nq) {
+    const long long rows = (long long)B * Nq;
+    return (int)(rows < 2LL * spe_num_sms() ? rows : 2LL * spe_num_sms());
+}
+int t8_threads(const char* env, int dflt) {
+    const char* e = getenv(env);
+    const int v = e ? atoi(e) : dflt;
+    return (v == 8 || v == 10 || v == 16) ? v : dflt;
+}
+
+}  // namespace
+
+int spe_talking_h8_grid(int B, int Nq) { return t8_grid(B, Nq); }
+
+// the staged kernels take fp16 logits only (the default storage); fp32 logits stay on rowwise.cu
+bool spe_talking_h8_fits(long long ldS, long long ldA) {
+    return (size_t)2 * 8 * (t8_pitch((int)ldS) + t8_pitch((int)ldA)) * 2 + 128 <= 110 * 1024;      // two CTAs per SM
+}
+
+int spe_talking_h8_fwd(const void* S, int s16, void* A, const float* Wl, const float* bl, const float* Ww, const float* bw, float* stats, int B, int Nq, int Nk,
+                       long long ldS, long long ldA, cudaStream_t st) {
+    SPE_CHECK(s16, "talking-heads H=8 (staged): fp16 logits only");
+    SPE_CHECK(ldS % 8 == 0 && ldA % 8 == 0 && ldS >= Nk && ldA >= Nk && spe_talking_h8_fits(ldS, ldA), "talking-heads H=8: bad leading dimensions");
+    const int grid = t8_grid(B, Nq);
+    const size_t smem = (size_t)2 * 8 * t8_pitch((int)ldS) * 2 + 128;      // + slack: the last step reads up to 24 keys past the pitch (masked)
+    static const int nw = t8_threads("SPE_TH8_FWD_WARPS", 10);
+    const uint16_t* S16p = reinterpret_cast<const uint16_t*>(S);
+    uint16_t* A16 = reinterpret_cast<uint16_t*>(A);
+#define T8_FWD(NW_)                                                                                                              \
+    {                                                                                                                            \
+        static bool attr = false;                                                                                                \
+        if (!attr) { SPE_CUDA(cudaFuncSetAttribute(th8_fwd_kernel<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
+        th8_fwd_kernel<NW_><<<grid, NW_ * 32, smem, st>>>(S16p, A16, Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);   \
+    }
+    if (nw == 8) T8_FWD(8) else if (nw == 16) T8_FWD(16) else T8_FWD(10)
+#undef T8_FWD
+    SPE_LAUNCHED();
+    return 0;
+}
+
+int spe_talking_h8_bwd(const void* S, int s16, const void* dA, void* dS, const float* Wl, const float* bl, const float* Ww, const float* stats, int B, int Nq,
+                       int Nk, long long ldS, long long ldA, float* part, cudaStream_t st) {
+    SPE_CHECK(s16, "talking-heads H=8 (staged): fp16 logits only");
+    SPE_CHECK(stats, "talking-heads backward (H = 8) needs the forward statistics");
+    SPE_CHECK(ldS % 8 == 0 && ldA % 8 == 0 && ldS >= Nk && ldA >= Nk && ldS < (1LL << 31) && ldA < (1LL << 31), "talking-heads H=8: bad leading dimensions");
+    const int grid = t8_grid(B, Nq);
+    const size_t smem = (size_t)2 * 8 * (t8_pitch((int)ldS) + t8_pitch((int)ldA)) * 2 + 128;
+    static const int nw = t8_threads("SPE_TH8_BWD_WARPS", 10);
+    const uint16_t* S16p = reinterpret_cast<const uint16_t*>(S);
+    const uint16_t* dA16 = reinterpret_cast<const uint16_t*>(dA);
+    uint16_t* dS16 = reinterpret_cast<uint16_t*>(dS);
+#define T8_BWD(NW_)                                                                                                              \
+    {                                                                                                                            \
+        static bool attr = false;                                                                                                \
+        if (!attr) { SPE_CUDA(cudaFuncSetAttribute(th8_bwd_kernel<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
+        th8_bwd_kernel<NW_><<<grid, NW_ * 32, smem, st>>>(S16p, dA16, dS16, Wl, bl, Ww, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, part); \
+    }
+    if (nw == 8) T8_BWD(8) else if (nw == 16) T8_BWD(16) else T8_BWD(10)
+#undef T8_BWD
+    SPE_LAUNCHED();
+    return 0;
+}
