@@ -131,13 +131,13 @@ __device__ __forceinline__ void mask_tile(float (&d)[4], int jb, int t, int Nk, 
 
 // ------------------------------------------------------------------------------------------------------------------------
 // forward.  dynamic shared memory: [2][8][pS] f16 row buffers
-template <int NW>
+template <int NW, int NBUF>
 __global__ void __launch_bounds__(NW * 32, 2) th8_fwd_kernel(const uint16_t* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
                                                             const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
                                                             float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
     extern __shared__ __align__(128) uint8_t t8sm[];
     uint16_t* Sbuf = reinterpret_cast<uint16_t*>(t8sm);
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[NBUF];
     __shared__ float redm[NW][8], redz[NW][8], sc2[8];
     const int pS = t8_pitch(ldS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_fwd_kernel(const uint16_t* __r
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
     const uint32_t bar0 = t8_smem(bars);
     if (tid == 0) {
-        t8_mbar_init(bar0, 1); t8_mbar_init(bar0 + 8, 1);
+        for (int k = 0; k < NBUF; ++k) t8_mbar_init(bar0 + 8 * k, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -164,12 +164,16 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_fwd_kernel(const uint16_t* __r
     };
     const int nst = (ldA + T8_CH - 1) / T8_CH;
     const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;         // contiguous steps per warp (N = 1600: 50 steps, 5 per warp at NW = 10)
-    if (tid == 0 && blockIdx.x < rows_total) issue(blockIdx.x, 0);
+    // ring of NBUF row buffers: NBUF - 1 rows are in flight while one is processed (the kernel is bound by bytes in flight per SM)
+    if (tid == 0)
+        for (int k = 0; k < NBUF - 1; ++k)
+            if (blockIdx.x + (long long)k * gridDim.x < rows_total) issue(blockIdx.x + k * gridDim.x, k);
     int it = 0;
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x, buf ^ 1);      // buf^1 was released by the previous iteration's last barrier
-        t8_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
+        const int buf = it % NBUF;
+        if (tid == 0 && row + (long long)(NBUF - 1) * gridDim.x < rows_total)
+            issue(row + (NBUF - 1) * gridDim.x, (it + NBUF - 1) % NBUF);       // that buffer was released by the previous iteration's last barrier
+        t8_mbar_wait(bar0 + 8 * buf, (uint32_t)(it / NBUF) & 1u);
         const uint16_t* Sb = Sbuf + (size_t)buf * 8 * pS;
         const int b = row / Nq, q = row % Nq;
         uint16_t* Ab = A + ((long long)b * 8 * Nq + q) * ldA;
@@ -433,18 +437,25 @@ int spe_talking_h8_fwd(const void* S, int s16, void* A, const float* Wl, const f
                        long long ldS, long long ldA, cudaStream_t st) {
     SPE_CHECK(s16, "talking-heads H=8 (staged): fp16 logits only");
     SPE_CHECK(ldS % 8 == 0 && ldA % 8 == 0 && ldS >= Nk && ldA >= Nk && spe_talking_h8_fits(ldS, ldA), "talking-heads H=8: bad leading dimensions");
-    const int grid = t8_grid(B, Nq);
-    const size_t smem = (size_t)2 * 8 * t8_pitch((int)ldS) * 2 + 128;      // + slack: the last step reads up to 24 keys past the pitch (masked)
-    static const int nw = t8_threads("SPE_TH8_FWD_WARPS", 10);
+    static const int ctas = getenv("SPE_TH8_FWD_CTAS") ? atoi(getenv("SPE_TH8_FWD_CTAS")) : 3;      // resident CTAs per SM the grid is sized for (measured at cfg2: 2 x 10 warps 0.209 ms, 3 x 10 0.203, 3 x 8 0.189)
+    const long long rows = (long long)B * Nq;
+    const int grid = (int)(rows < (long long)ctas * spe_num_sms() ? rows : (long long)ctas * spe_num_sms());
+    static const int nw = t8_threads("SPE_TH8_FWD_WARPS", 8);
+    static const int nbuf_env = getenv("SPE_TH8_FWD_NBUF") ? atoi(getenv("SPE_TH8_FWD_NBUF")) : 2;     // deeper rings (3, 4 rows in flight) change nothing: not bound by bytes in flight
+    const size_t row_bytes = (size_t)8 * t8_pitch((int)ldS) * 2;
+    const int nbuf = (nbuf_env >= 4 && 4 * row_bytes + 128 <= 110 * 1024) ? 4 : (nbuf_env >= 3 && 3 * row_bytes + 128 <= 110 * 1024) ? 3 : 2;
+    const size_t smem = nbuf * row_bytes + 128;      // + slack: the last step reads up to 24 keys past the pitch (masked)
     const uint16_t* S16p = reinterpret_cast<const uint16_t*>(S);
     uint16_t* A16 = reinterpret_cast<uint16_t*>(A);
-#define T8_FWD(NW_)                                                                                                              \
+#define T8_FWD(NW_, NB_)                                                                                                         \
     {                                                                                                                            \
         static bool attr = false;                                                                                                \
-        if (!attr) { SPE_CUDA(cudaFuncSetAttribute(th8_fwd_kernel<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
-        th8_fwd_kernel<NW_><<<grid, NW_ * 32, smem, st>>>(S16p, A16, Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);   \
+        if (!attr) { SPE_CUDA(cudaFuncSetAttribute(th8_fwd_kernel<NW_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
+        th8_fwd_kernel<NW_, NB_><<<grid, NW_ * 32, smem, st>>>(S16p, A16, Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);   \
     }
-    if (nw == 8) T8_FWD(8) else if (nw == 16) T8_FWD(16) else T8_FWD(10)
+#define T8_FWD_NB(NW_) { if (nbuf == 4) T8_FWD(NW_, 4) else if (nbuf == 3) T8_FWD(NW_, 3) else T8_FWD(NW_, 2) }
+    if (nw == 8) T8_FWD_NB(8) else if (nw == 16) T8_FWD_NB(16) else T8_FWD_NB(10)
+#undef T8_FWD_NB
 #undef T8_FWD
     SPE_LAUNCHED();
     return 0;
