@@ -45,11 +45,6 @@ __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
     asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
-__device__ __forceinline__ uint32_t add_h2(uint32_t a, uint32_t b) {
-    uint32_t y;
-    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
-    return y;
-}
 __device__ __forceinline__ float2 h2_to_f2(uint32_t x) { return __half22float2(*reinterpret_cast<const __half2*>(&x)); }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r;
@@ -99,16 +94,13 @@ __host__ __device__ __forceinline__ int t8_pitch(int ld) { return ld + ((40 - ld
 
 constexpr int T8_CH = 32;       // keys per warp step: 2 MMA tiles; a thread owns 4 consecutive keys of heads 2 tig, 2 tig + 1
 
-// the 4 keys [jb, jb + 4) of heads 2 tig and 2 tig + 1 from a staged row, as 16-bit pairs along the keys: r[hs][t] = {key 2 t, key 2 t + 1}.
-// Keys >= Nk come back as 0 (the pitch padding may hold anything).
-__device__ __forceinline__ void lds_row(const uint16_t* __restrict__ rowbuf, int pitch, int tig, int jb, int Nk, uint32_t (&r)[2][2]) {
-#pragma unroll
-    for (int hs = 0; hs < 2; ++hs) {
-        const uint2 v = *reinterpret_cast<const uint2*>(rowbuf + (2 * tig + hs) * pitch + jb);
-        r[hs][0] = v.x;
-        r[hs][1] = v.y;
-    }
-    if (jb + 4 > Nk) {
+// the 4 keys [jb, jb + 4) of heads 2 tig and 2 tig + 1 from a staged row (sp = this thread's position in the row of head 2 tig), as
+// 16-bit pairs along the keys: r[hs][t] = {key 2 t, key 2 t + 1}.  MASK: keys >= Nk come back as 0 (the pitch padding may hold anything).
+template <bool MASK>
+__device__ __forceinline__ void lds_row(const uint16_t* __restrict__ sp, int pitch, int jb, int Nk, uint32_t (&r)[2][2]) {
+    const uint2 v0 = *reinterpret_cast<const uint2*>(sp), v1 = *reinterpret_cast<const uint2*>(sp + pitch);
+    r[0][0] = v0.x; r[0][1] = v0.y; r[1][0] = v1.x; r[1][1] = v1.y;
+    if (MASK) {
 #pragma unroll
         for (int hs = 0; hs < 2; ++hs)
 #pragma unroll
@@ -129,10 +121,57 @@ __device__ __forceinline__ void mask_tile(float (&d)[4], int jb, int t, int Nk, 
     if (jb + 2 * t + 1 >= Nk) { d[2] = v; d[3] = v; }
 }
 
+// ---- forward steps (32 keys per warp: 2 tiles) ----
+template <bool MASK>
+__device__ __forceinline__ void fwd_step_a(const uint16_t* __restrict__ sp, int pS, int jb, int Nk, uint32_t w1, const float (&b1)[2], float (&m)[2], float (&z)[2]) {
+    uint32_t r[2][2];
+    lds_row<MASK>(sp, pS, jb, Nk, r);
+    float L[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        uint32_t a0, a1;
+        frag(r, t, a0, a1);
+        L[t][0] = b1[0]; L[t][1] = b1[1]; L[t][2] = b1[0]; L[t][3] = b1[1];
+        mma8_f16(L[t], a0, a1, w1);
+        if (MASK) mask_tile(L[t], jb, t, Nk, T8_NEG);
+    }
+#pragma unroll
+    for (int gs = 0; gs < 2; ++gs) {
+        const float mx = fmaxf(fmaxf(m[gs], fmaxf(L[0][gs], L[0][2 + gs])), fmaxf(L[1][gs], L[1][2 + gs]));
+        const float acc = (ex2f(L[0][gs] - mx) + ex2f(L[0][2 + gs] - mx)) + (ex2f(L[1][gs] - mx) + ex2f(L[1][2 + gs] - mx));
+        z[gs] = z[gs] * ex2f(m[gs] - mx) + acc;
+        m[gs] = mx;
+    }
+}
+template <bool MASK>
+__device__ __forceinline__ void fwd_step_b(const uint16_t* __restrict__ sp, int pS, uint16_t* __restrict__ ap, long long hA, int jb, int Nk, int ldA, uint32_t w1,
+                                           uint32_t w2, const float (&ci)[2], const float (&b2)[2]) {
+    uint32_t r[2][2], pkt[2][2];
+    lds_row<MASK>(sp, pS, jb, Nk, r);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        uint32_t a0, a1;
+        frag(r, t, a0, a1);
+        float d[4] = {ci[0], ci[1], ci[0], ci[1]};
+        mma8_f16(d, a0, a1, w1);
+        if (MASK) mask_tile(d, jb, t, Nk, T8_NEG);
+        const uint32_t p0 = ex2_h2(pk_f16(d[0], d[1])), p1 = ex2_h2(pk_f16(d[2], d[3]));     // = the A fragment of the output mix
+        float e[4] = {b2[0], b2[1], b2[0], b2[1]};
+        mma8_f16(e, p0, p1, w2);
+        if (MASK) mask_tile(e, jb, t, Nk, 0.f);                                              // padding keys stay clean (the PV GEMM reads the pitch)
+        pkt[0][t] = pk_bf16(e[0], e[2]);
+        pkt[1][t] = pk_bf16(e[1], e[3]);
+    }
+    if (!MASK || jb < ldA) {
+        *reinterpret_cast<uint2*>(ap) = make_uint2(pkt[0][0], pkt[0][1]);
+        *reinterpret_cast<uint2*>(ap + hA) = make_uint2(pkt[1][0], pkt[1][1]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
-// forward.  dynamic shared memory: [2][8][pS] f16 row buffers
+// forward.  dynamic shared memory: [NBUF][8][pS] f16 row buffers
 template <int NW, int NBUF>
-__global__ void __launch_bounds__(NW * 32, 2) th8_fwd_kernel(const uint16_t* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
+__global__ void __launch_bounds__(NW * 32, NW <= 5 ? 4 : NW <= 8 ? 3 : 2) th8_fwd_kernel(const uint16_t* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
                                                             const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
                                                             float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
     extern __shared__ __align__(128) uint8_t t8sm[];
@@ -163,46 +202,29 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_fwd_kernel(const uint16_t* __r
             t8_bulk_g2s(t8_smem(Sbuf + ((size_t)buf * 8 + h) * pS), S + ((long long)b * 8 * Nq + q) * ldS + h * hS, (uint32_t)(ldS * 2), bar);
     };
     const int nst = (ldA + T8_CH - 1) / T8_CH;
-    const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;         // contiguous steps per warp (N = 1600: 50 steps, 5 per warp at NW = 10)
-    // ring of NBUF row buffers: NBUF - 1 rows are in flight while one is processed (the kernel is bound by bytes in flight per SM)
+    const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;         // contiguous steps per warp
+    const int sf = min(s1, max(s0, Nk / T8_CH));                        // steps [s0, sf) hold valid keys only: no masks
+    const int toff = (2 * tig) * pS + s0 * T8_CH + gid * 4;             // this thread's position inside a staged row
+    // ring of NBUF row buffers: NBUF - 1 rows are in flight while one is processed
     if (tid == 0)
         for (int k = 0; k < NBUF - 1; ++k)
             if (blockIdx.x + (long long)k * gridDim.x < rows_total) issue(blockIdx.x + k * gridDim.x, k);
     int it = 0;
+    int rb = blockIdx.x / Nq, rq = blockIdx.x % Nq;                     // (image, query) of the row, advanced without divisions
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
         const int buf = it % NBUF;
         if (tid == 0 && row + (long long)(NBUF - 1) * gridDim.x < rows_total)
             issue(row + (NBUF - 1) * gridDim.x, (it + NBUF - 1) % NBUF);       // that buffer was released by the previous iteration's last barrier
         t8_mbar_wait(bar0 + 8 * buf, (uint32_t)(it / NBUF) & 1u);
-        const uint16_t* Sb = Sbuf + (size_t)buf * 8 * pS;
-        const int b = row / Nq, q = row % Nq;
-        uint16_t* Ab = A + ((long long)b * 8 * Nq + q) * ldA;
+        const uint16_t* sp0 = Sbuf + (size_t)buf * 8 * pS + toff;
+        uint16_t* ap0 = A + ((long long)rb * 8 * Nq + rq) * ldA + (long long)(2 * tig) * hA + s0 * T8_CH + gid * 4;
         // ---- sweep A
         float m[2] = {T8_NEG, T8_NEG}, z[2] = {0.f, 0.f};
-        for (int st = s0; st < s1; ++st) {
-            const int jb = st * T8_CH + gid * 4;
-            uint32_t r[2][2];
-            lds_row(Sb, pS, tig, jb, Nk, r);
-            float L[2][4];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                uint32_t a0, a1;
-                frag(r, t, a0, a1);
-                L[t][0] = b1[0]; L[t][1] = b1[1]; L[t][2] = b1[0]; L[t][3] = b1[1];
-                mma8_f16(L[t], a0, a1, w1);
-            }
-            if (jb + 4 > Nk) {
-#pragma unroll
-                for (int t = 0; t < 2; ++t) mask_tile(L[t], jb, t, Nk, T8_NEG);
-            }
-#pragma unroll
-            for (int gs = 0; gs < 2; ++gs) {
-                const float mx = fmaxf(fmaxf(m[gs], fmaxf(L[0][gs], L[0][2 + gs])), fmaxf(L[1][gs], L[1][2 + gs]));
-                const uint32_t acc = add_h2(ex2_h2(pk_f16(L[0][gs] - mx, L[0][2 + gs] - mx)), ex2_h2(pk_f16(L[1][gs] - mx, L[1][2 + gs] - mx)));
-                const float2 s2 = h2_to_f2(acc);
-                z[gs] = z[gs] * ex2f(m[gs] - mx) + (s2.x + s2.y);
-                m[gs] = mx;
-            }
+        {
+            const uint16_t* sp = sp0;
+            int st = s0;
+            for (; st < sf; ++st, sp += T8_CH) fwd_step_a<false>(sp, pS, 0, Nk, w1, b1, m, z);
+            for (; st < s1; ++st, sp += T8_CH) fwd_step_a<true>(sp, pS, st * T8_CH + gid * 4, Nk, w1, b1, m, z);
         }
 #pragma unroll
         for (int gs = 0; gs < 2; ++gs) {
@@ -219,39 +241,27 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_fwd_kernel(const uint16_t* __r
         __syncthreads();
         if (tid < 8) {
             float M = T8_NEG, Z = 0.f;
+#pragma unroll
             for (int w = 0; w < NW; ++w) M = fmaxf(M, redm[w][tid]);
+#pragma unroll
             for (int w = 0; w < NW; ++w) Z += redz[w][tid] * ex2f(redm[w][tid] - M);
-            const float c2 = M + log2f(Z);
+            const float c2 = M + __log2f(Z);
             sc2[tid] = c2;
             if (stats) stats[(long long)row * 8 + tid] = c2;
         }
         __syncthreads();
         // ---- sweep B
         const float ci[2] = {b1[0] - sc2[2 * tig] + T8_SHIFT, b1[1] - sc2[2 * tig + 1] + T8_SHIFT};
-        for (int st = s0; st < s1; ++st) {
-            const int jb = st * T8_CH + gid * 4;
-            uint32_t r[2][2], pkt[2][2];
-            lds_row(Sb, pS, tig, jb, Nk, r);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                uint32_t a0, a1;
-                frag(r, t, a0, a1);
-                float d[4] = {ci[0], ci[1], ci[0], ci[1]};
-                mma8_f16(d, a0, a1, w1);
-                if (jb + 4 > Nk) mask_tile(d, jb, t, Nk, T8_NEG);
-                const uint32_t p0 = ex2_h2(pk_f16(d[0], d[1])), p1 = ex2_h2(pk_f16(d[2], d[3]));     // = the A fragment of the output mix
-                float e[4] = {b2[0], b2[1], b2[0], b2[1]};
-                mma8_f16(e, p0, p1, w2);
-                if (jb + 4 > Nk) mask_tile(e, jb, t, Nk, 0.f);                                      // padding keys stay clean (the PV GEMM reads the pitch)
-                pkt[0][t] = pk_bf16(e[0], e[2]);
-                pkt[1][t] = pk_bf16(e[1], e[3]);
-            }
-            if (jb < ldA) {
-#pragma unroll
-                for (int os = 0; os < 2; ++os) *reinterpret_cast<uint2*>(Ab + (long long)(2 * tig + os) * hA + jb) = make_uint2(pkt[os][0], pkt[os][1]);
-            }
+        {
+            const uint16_t* sp = sp0;
+            uint16_t* ap = ap0;
+            int st = s0;
+            for (; st < sf; ++st, sp += T8_CH, ap += T8_CH) fwd_step_b<false>(sp, pS, ap, hA, 0, Nk, ldA, w1, w2, ci, b2);
+            for (; st < s1; ++st, sp += T8_CH, ap += T8_CH) fwd_step_b<true>(sp, pS, ap, hA, st * T8_CH + gid * 4, Nk, ldA, w1, w2, ci, b2);
         }
         __syncthreads();                                 // the row buffer, sc2 and red* are free again
+        rq += gridDim.x;
+        while (rq >= Nq) { rq -= Nq; ++rb; }
     }
 }
 
@@ -273,6 +283,66 @@ __device__ __forceinline__ uint32_t h2_to_bf2(uint32_t x) {
 // acc (rows 0..7 = heads of X, columns = heads of Y) += sum over the tile's 16 keys X[key][.] Y[key][.];  (x0, x1), (y0, y1): m16k8 A-style
 __device__ __forceinline__ void outer8(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, float (&acc)[4]) {
     mma16_bf16(acc, movm(x0), 0u, movm(x1), 0u, movm(y0), movm(y1));
+}
+
+// ---- backward steps ----
+template <bool MASK>
+__device__ __forceinline__ void bwd_step_b(const uint16_t* __restrict__ sp, int pS, const uint16_t* __restrict__ dp, int pA, int jb, int Nk, uint32_t w1,
+                                           const float (&ci)[2], const GradW8& gww, float (&rho)[2], float (&accWw)[4]) {
+    uint32_t r[2][2], rd[2][2];
+    lds_row<MASK>(sp, pS, jb, Nk, r);
+    lds_row<MASK>(dp, pA, jb, Nk, rd);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        uint32_t a0, a1, d0, d1;
+        frag(r, t, a0, a1);
+        frag(rd, t, d0, d1);
+        float P[4] = {ci[0], ci[1], ci[0], ci[1]};
+        mma8_f16(P, a0, a1, w1);
+        if (MASK) mask_tile(P, jb, t, Nk, T8_NEG);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) P[i] = ex2f(P[i]);
+        float dP[4] = {0.f, 0.f, 0.f, 0.f};
+        mma8_bf16(dP, d0, d1, gww.hi);
+        mma8_bf16(dP, d0, d1, gww.lo);
+        rho[0] += P[0] * dP[0] + P[2] * dP[2];
+        rho[1] += P[1] * dP[1] + P[3] * dP[3];
+        outer8(d0, d1, pk_bf16(P[0], P[1]), pk_bf16(P[2], P[3]), accWw);            // [o, g]
+    }
+}
+template <bool MASK>
+__device__ __forceinline__ void bwd_step_c(const uint16_t* __restrict__ sp, int pS, const uint16_t* __restrict__ dp, int pA, uint16_t* gp, long long hA, int jb,
+                                           int Nk, int ldA, uint32_t w1, const float (&ci)[2], const GradW8& gww, const GradW8& gwl, const float (&rho)[2],
+                                           float (&accWl)[4]) {
+    uint32_t r[2][2], rd[2][2], pkt[2][2];
+    lds_row<MASK>(sp, pS, jb, Nk, r);
+    lds_row<MASK>(dp, pA, jb, Nk, rd);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        uint32_t a0, a1, d0, d1;
+        frag(r, t, a0, a1);
+        frag(rd, t, d0, d1);
+        float P[4] = {ci[0], ci[1], ci[0], ci[1]};
+        mma8_f16(P, a0, a1, w1);
+        if (MASK) mask_tile(P, jb, t, Nk, T8_NEG);
+        float dP[4] = {0.f, 0.f, 0.f, 0.f};
+        mma8_bf16(dP, d0, d1, gww.hi);
+        mma8_bf16(dP, d0, d1, gww.lo);
+        float dL[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dL[i] = ex2f(P[i]) * (dP[i] - rho[i & 1]);
+        const uint32_t l0 = pk_bf16(dL[0], dL[1]), l1 = pk_bf16(dL[2], dL[3]);
+        float dSv[4] = {0.f, 0.f, 0.f, 0.f};
+        mma8_bf16(dSv, l0, l1, gwl.hi);
+        mma8_bf16(dSv, l0, l1, gwl.lo);
+        pkt[0][t] = pk_bf16(dSv[0], dSv[2]);
+        pkt[1][t] = pk_bf16(dSv[1], dSv[3]);
+        outer8(l0, l1, h2_to_bf2(a0), h2_to_bf2(a1), accWl);                         // [g, h]
+    }
+    if (!MASK || jb < ldA) {
+        *reinterpret_cast<uint2*>(gp) = make_uint2(pkt[0][0], pkt[0][1]);
+        *reinterpret_cast<uint2*>(gp + hA) = make_uint2(pkt[1][0], pkt[1][1]);
+    }
 }
 
 // backward.  dynamic shared memory: [2][8][pS] f16 logit rows, then [2][8][pA] bf16 dA rows
@@ -315,43 +385,29 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __r
     };
     const int nst = (ldA + T8_CH - 1) / T8_CH;
     const int s0 = warp * nst / NW, s1 = (warp + 1) * nst / NW;
+    const int sf = min(s1, max(s0, Nk / T8_CH));
+    const int toffS = (2 * tig) * pS + s0 * T8_CH + gid * 4, toffA = (2 * tig) * pA + s0 * T8_CH + gid * 4;
     if (tid == 0 && blockIdx.x < rows_total) issue(blockIdx.x, 0);
     int it = 0;
+    int rb = blockIdx.x / Nq, rq = blockIdx.x % Nq;
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
         const int buf = it & 1;
         if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x, buf ^ 1);
         if (tid < 8) sc2[tid] = stats[(long long)row * 8 + tid];
         t8_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
         __syncthreads();
-        const uint16_t* Sb = Sbuf + (size_t)buf * 8 * pS;
-        const uint16_t* Db = Dbuf + (size_t)buf * 8 * pA;
-        const int b = row / Nq, q = row % Nq;
-        uint16_t* dSb = dS + ((long long)b * 8 * Nq + q) * ldA;      // may alias this row of dA: it is staged in shared memory by now
+        const uint16_t* sp0 = Sbuf + (size_t)buf * 8 * pS + toffS;
+        const uint16_t* dp0 = Dbuf + (size_t)buf * 8 * pA + toffA;
+        // dS may alias this row of dA: it is staged in shared memory by now
+        uint16_t* gp0 = dS + ((long long)rb * 8 * Nq + rq) * ldA + (long long)(2 * tig) * hA + s0 * T8_CH + gid * 4;
         const float ci[2] = {b1[0] - sc2[2 * tig], b1[1] - sc2[2 * tig + 1]};
         float rho[2] = {0.f, 0.f};
         // ---- sweep B
-        for (int st = s0; st < s1; ++st) {
-            const int jb = st * T8_CH + gid * 4;
-            uint32_t r[2][2], rd[2][2];
-            lds_row(Sb, pS, tig, jb, Nk, r);
-            lds_row(Db, pA, tig, jb, Nk, rd);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                uint32_t a0, a1, d0, d1;
-                frag(r, t, a0, a1);
-                frag(rd, t, d0, d1);
-                float P[4] = {ci[0], ci[1], ci[0], ci[1]};
-                mma8_f16(P, a0, a1, w1);
-                if (jb + 4 > Nk) mask_tile(P, jb, t, Nk, T8_NEG);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) P[i] = ex2f(P[i]);
-                float dP[4] = {0.f, 0.f, 0.f, 0.f};
-                mma8_bf16(dP, d0, d1, gww.hi);
-                mma8_bf16(dP, d0, d1, gww.lo);
-                rho[0] += P[0] * dP[0] + P[2] * dP[2];
-                rho[1] += P[1] * dP[1] + P[3] * dP[3];
-                outer8(d0, d1, pk_bf16(P[0], P[1]), pk_bf16(P[2], P[3]), accWw);            // [o, g]
-            }
+        {
+            const uint16_t *sp = sp0, *dp = dp0;
+            int st = s0;
+            for (; st < sf; ++st, sp += T8_CH, dp += T8_CH) bwd_step_b<false>(sp, pS, dp, pA, 0, Nk, w1, ci, gww, rho, accWw);
+            for (; st < s1; ++st, sp += T8_CH, dp += T8_CH) bwd_step_b<true>(sp, pS, dp, pA, st * T8_CH + gid * 4, Nk, w1, ci, gww, rho, accWw);
         }
 #pragma unroll
         for (int gs = 0; gs < 2; ++gs) {
@@ -362,6 +418,7 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __r
         __syncthreads();
         if (tid < 8) {
             float x = 0.f;
+#pragma unroll
             for (int w = 0; w < NW; ++w) x += redr[w][tid];
             srho[tid] = x;
         }
@@ -369,39 +426,17 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __r
         rho[0] = srho[2 * tig];
         rho[1] = srho[2 * tig + 1];
         // ---- sweep C
-        for (int st = s0; st < s1; ++st) {
-            const int jb = st * T8_CH + gid * 4;
-            uint32_t r[2][2], rd[2][2], pkt[2][2];
-            lds_row(Sb, pS, tig, jb, Nk, r);
-            lds_row(Db, pA, tig, jb, Nk, rd);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                uint32_t a0, a1, d0, d1;
-                frag(r, t, a0, a1);
-                frag(rd, t, d0, d1);
-                float P[4] = {ci[0], ci[1], ci[0], ci[1]};
-                mma8_f16(P, a0, a1, w1);
-                if (jb + 4 > Nk) mask_tile(P, jb, t, Nk, T8_NEG);
-                float dP[4] = {0.f, 0.f, 0.f, 0.f};
-                mma8_bf16(dP, d0, d1, gww.hi);
-                mma8_bf16(dP, d0, d1, gww.lo);
-                float dL[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dL[i] = ex2f(P[i]) * (dP[i] - rho[i & 1]);
-                const uint32_t l0 = pk_bf16(dL[0], dL[1]), l1 = pk_bf16(dL[2], dL[3]);
-                float dSv[4] = {0.f, 0.f, 0.f, 0.f};
-                mma8_bf16(dSv, l0, l1, gwl.hi);
-                mma8_bf16(dSv, l0, l1, gwl.lo);
-                pkt[0][t] = pk_bf16(dSv[0], dSv[2]);
-                pkt[1][t] = pk_bf16(dSv[1], dSv[3]);
-                outer8(l0, l1, h2_to_bf2(a0), h2_to_bf2(a1), accWl);                         // [g, h]
-            }
-            if (jb < ldA) {
-#pragma unroll
-                for (int os = 0; os < 2; ++os) *reinterpret_cast<uint2*>(dSb + (long long)(2 * tig + os) * hA + jb) = make_uint2(pkt[os][0], pkt[os][1]);
-            }
+        {
+            const uint16_t *sp = sp0, *dp = dp0;
+            uint16_t* gp = gp0;
+            int st = s0;
+            for (; st < sf; ++st, sp += T8_CH, dp += T8_CH, gp += T8_CH) bwd_step_c<false>(sp, pS, dp, pA, gp, hA, 0, Nk, ldA, w1, ci, gww, gwl, rho, accWl);
+            for (; st < s1; ++st, sp += T8_CH, dp += T8_CH, gp += T8_CH)
+                bwd_step_c<true>(sp, pS, dp, pA, gp, hA, st * T8_CH + gid * 4, Nk, ldA, w1, ci, gww, gwl, rho, accWl);
         }
         __syncthreads();                                 // the row buffers, sc2, srho, redr are free again
+        rq += gridDim.x;
+        while (rq >= Nq) { rq -= Nq; ++rb; }
     }
     // per-CTA partials: [dWl (g, h) | dbl = 0 | dWw (o, g) | dbw = 0]  (talking_bwd_finalize_kernel's layout)
 #pragma unroll
@@ -421,7 +456,7 @@ int t8_grid(int B, int Nq) {
 int t8_threads(const char* env, int dflt) {
     const char* e = getenv(env);
     const int v = e ? atoi(e) : dflt;
-    return (v == 8 || v == 10 || v == 16) ? v : dflt;
+    return (v == 5 || v == 8 || v == 10 || v == 16) ? v : dflt;
 }
 
 }  // namespace
@@ -451,10 +486,10 @@ int spe_talking_h8_fwd(const void* S, int s16, void* A, const float* Wl, const f
     {                                                                                                                            \
         static bool attr = false;                                                                                                \
         if (!attr) { SPE_CUDA(cudaFuncSetAttribute(th8_fwd_kernel<NW_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
-        th8_fwd_kernel<NW_, NB_><<<grid, NW_ * 32, smem, st>>>(S16p, A16, Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);   \
+        th8_fwd_kernel<NW_, NB_><<<grid, NW_ * 32, smem, st>>>(S16p, A16, Wl, bl, Ww, bw, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA);      \
     }
 #define T8_FWD_NB(NW_) { if (nbuf == 4) T8_FWD(NW_, 4) else if (nbuf == 3) T8_FWD(NW_, 3) else T8_FWD(NW_, 2) }
-    if (nw == 8) T8_FWD_NB(8) else if (nw == 16) T8_FWD_NB(16) else T8_FWD_NB(10)
+    if (nw == 5) T8_FWD_NB(5) else if (nw == 8) T8_FWD_NB(8) else if (nw == 16) T8_FWD_NB(16) else T8_FWD_NB(10)
 #undef T8_FWD_NB
 #undef T8_FWD
     SPE_LAUNCHED();
@@ -468,7 +503,7 @@ int spe_talking_h8_bwd(const void* S, int s16, const void* dA, void* dS, const f
     SPE_CHECK(ldS % 8 == 0 && ldA % 8 == 0 && ldS >= Nk && ldA >= Nk && ldS < (1LL << 31) && ldA < (1LL << 31), "talking-heads H=8: bad leading dimensions");
     const int grid = t8_grid(B, Nq);
     const size_t smem = (size_t)2 * 8 * (t8_pitch((int)ldS) + t8_pitch((int)ldA)) * 2 + 128;
-    static const int nw = t8_threads("SPE_TH8_BWD_WARPS", 10);
+    static const int nw = t8_threads("SPE_TH8_BWD_WARPS", 8);
     const uint16_t* S16p = reinterpret_cast<const uint16_t*>(S);
     const uint16_t* dA16 = reinterpret_cast<const uint16_t*>(dA);
     uint16_t* dS16 = reinterpret_cast<uint16_t*>(dS);
@@ -478,7 +513,7 @@ int spe_talking_h8_bwd(const void* S, int s16, const void* dA, void* dS, const f
         if (!attr) { SPE_CUDA(cudaFuncSetAttribute(th8_bwd_kernel<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
         th8_bwd_kernel<NW_><<<grid, NW_ * 32, smem, st>>>(S16p, dA16, dS16, Wl, bl, Ww, stats, B * Nq, Nq, Nk, (int)ldS, (int)ldA, part); \
     }
-    if (nw == 8) T8_BWD(8) else if (nw == 16) T8_BWD(16) else T8_BWD(10)
+    if (nw == 5) T8_BWD(5) else if (nw == 8) T8_BWD(8) else if (nw == 16) T8_BWD(16) else T8_BWD(10)
 #undef T8_BWD
     SPE_LAUNCHED();
     return 0;
