@@ -14,8 +14,9 @@
 //   * the parameter gradients  dWw[o, g] = sum_j dA[j, o] P[j, g],  dWl[g, h] = sum_j dL[j, g] S[j, h]  contract over the MMA ROW index:
 //     the same fragments are transposed in registers with movmatrix (8 x 8 b16 blocks) and fed to two more MMAs per tile; the key
 //     permutation above is irrelevant for a sum over keys.
-// Precision (as rowwise.cu for H <= 8): logits through one f16 pass (S rounded to f16, Wl log2e in f16, f32 accumulate); the second
-// forward mix carries 2^8 P in f16 against 2^-8 Ww; gradient mixes in bf16 with the weights split hi + lo (two MMAs).
+// Precision (as rowwise.cu for H <= 8): logits through one f16 pass (S rounded to f16, Wl log2e in f16, f32 accumulate); the forward
+// starts the accumulator at bias - c2 + 4, so ex2.f16x2(pack(L')) = 2^4 P IS the A fragment of the output mix (2^-4 Ww); gradient mixes in
+// bf16 with the weights split hi + lo (two MMAs).  Full 64-key chunks take a mask-free path; addresses advance by pointer increments.
 // Statistics convention of rowwise.cu / talking_generic.cu:  stats[row][g] = c2 = max_j L2 + log2 sum_j 2^(L2 - max),  L2 = log2e (Wl S + bl).
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -63,76 +64,166 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return r;
 }
 
-// 8 consecutive logits of one head as floats; S16: stored as f16
-template <bool S16>
-__device__ __forceinline__ void load8(const void* __restrict__ S, long long off, float (&v)[8]) {
-    if (S16) {
-        const uint4 r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(S) + off));
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-            v[2 * i] = f.x;
-            v[2 * i + 1] = f.y;
-        }
-    } else {
-        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(S) + off);
-        const float4 x = __ldg(p), y = __ldg(p + 1);
-        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-        v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
-    }
+constexpr float T16_SHIFT = 4.f;        // the forward carries P' = 2^4 P in f16 (output mix weights 2^-4 Ww)
+constexpr float T16_UNSHIFT = 0.0625f;
+
+__device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t x) { return __half22float2(*reinterpret_cast<const __half2*>(&x)); }
+__device__ __forceinline__ uint32_t h2_to_bf2(uint32_t x) {
+    const float2 f = h2_to_f2(x);
+    return pk_bf16(f.x, f.y);
 }
 
-struct Mix1W {            // Wl log2e as the B operand [k = h, n = g] of the transposed logit mix, f16;  bias per head slot
+// 8 consecutive logits of the 4 head slots {2 tig, 2 tig + 1, 2 tig + 8, 2 tig + 9} as f16 pairs along the keys: r[hs][t] = {key 2 t, key 2 t + 1}
+// (fp32 logits are rounded here: the mix rounds them to f16 anyway).  MASK: keys >= Nk come back as 0 (the pitch padding may hold anything).
+template <bool S16, bool MASK>
+__device__ __forceinline__ void load_s(const void* __restrict__ S, long long off0, long long hS, int jb, int Nk, uint32_t (&r)[4][4]) {
+    if (!MASK || jb < Nk) {
+#pragma unroll
+        for (int hs = 0; hs < 4; ++hs) {
+            const long long off = off0 + (long long)((hs & 1) + 8 * (hs >> 1)) * hS;
+            if (S16) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(S) + off));
+                r[hs][0] = v.x; r[hs][1] = v.y; r[hs][2] = v.z; r[hs][3] = v.w;
+            } else {
+                const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(S) + off);
+                const float4 x = __ldg(p), y = __ldg(p + 1);
+                r[hs][0] = pk_f16(x.x, x.y); r[hs][1] = pk_f16(x.z, x.w); r[hs][2] = pk_f16(y.x, y.y); r[hs][3] = pk_f16(y.z, y.w);
+            }
+        }
+        if (MASK) {
+#pragma unroll
+            for (int hs = 0; hs < 4; ++hs)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (jb + 2 * t >= Nk) r[hs][t] = 0u;
+                    else if (jb + 2 * t + 1 >= Nk) r[hs][t] &= 0xffffu;
+                }
+        }
+    } else {
+#pragma unroll
+        for (int hs = 0; hs < 4; ++hs)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) r[hs][t] = 0u;
+    }
+}
+template <bool MASK>
+__device__ __forceinline__ void load_da(const uint16_t* dp, long long hA, int jb, int Nk, uint32_t (&r)[4][4]) {
+    if (!MASK || jb < Nk) {
+#pragma unroll
+        for (int hs = 0; hs < 4; ++hs) {
+            const uint4 v = *reinterpret_cast<const uint4*>(dp + (long long)((hs & 1) + 8 * (hs >> 1)) * hA);
+            r[hs][0] = v.x; r[hs][1] = v.y; r[hs][2] = v.z; r[hs][3] = v.w;
+        }
+        if (MASK) {
+#pragma unroll
+            for (int hs = 0; hs < 4; ++hs)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (jb + 2 * t >= Nk) r[hs][t] = 0u;
+                    else if (jb + 2 * t + 1 >= Nk) r[hs][t] &= 0xffffu;
+                }
+        }
+    } else {
+#pragma unroll
+        for (int hs = 0; hs < 4; ++hs)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) r[hs][t] = 0u;
+    }
+}
+// tile t of a chunk as an m16k16 A fragment [rows = keys (slot 2 t | slot 2 t + 1), k = the 16 heads]
+__device__ __forceinline__ void frag(const uint32_t (&r)[4][4], int t, uint32_t (&a)[4]) {
+    a[0] = prmt(r[0][t], r[1][t], 0x5410u); a[1] = prmt(r[0][t], r[1][t], 0x7632u);
+    a[2] = prmt(r[2][t], r[3][t], 0x5410u); a[3] = prmt(r[2][t], r[3][t], 0x7632u);
+}
+
+struct Mix1W {            // Wl log2e as the B operand [k = h, n = g] of the transposed logit mix, f16
     uint32_t b[2][2];
-    float bias[4];
 };
-__device__ __forceinline__ void load_mix1(const float* __restrict__ Wl, const float* __restrict__ bl, int gid, int tig, Mix1W& w) {
+__device__ __forceinline__ void load_mix1(const float* __restrict__ Wl, int gid, int tig, Mix1W& w) {
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) {
         const float* r = Wl + (8 * nb + gid) * 16;
         w.b[nb][0] = pk_f16(r[2 * tig] * T16_LOG2E, r[2 * tig + 1] * T16_LOG2E);
         w.b[nb][1] = pk_f16(r[2 * tig + 8] * T16_LOG2E, r[2 * tig + 9] * T16_LOG2E);
     }
-    w.bias[0] = bl[2 * tig] * T16_LOG2E;
-    w.bias[1] = bl[2 * tig + 1] * T16_LOG2E;
-    w.bias[2] = bl[2 * tig + 8] * T16_LOG2E;
-    w.bias[3] = bl[2 * tig + 9] * T16_LOG2E;
 }
-// logits (log2 domain) of tile t: L[r][gs], r = 0 -> key slot 2 t, r = 1 -> key slot 2 t + 1; gs = head slot {2 tig, 2 tig + 1, 2 tig + 8, 2 tig + 9}
-__device__ __forceinline__ void mix1_tile(const float (&v)[4][8], int t, const Mix1W& w, float (&L)[2][4]) {
-    const uint32_t a0 = pk_f16(v[0][2 * t], v[1][2 * t]), a1 = pk_f16(v[0][2 * t + 1], v[1][2 * t + 1]);
-    const uint32_t a2 = pk_f16(v[2][2 * t], v[3][2 * t]), a3 = pk_f16(v[2][2 * t + 1], v[3][2 * t + 1]);
+// L[r][gs] = init[gs] + sum_h S[key r][h] Wl'[g(gs)][h];  r = 0 -> key slot 2 t, r = 1 -> slot 2 t + 1;  gs = head slot
+template <bool MASK>
+__device__ __forceinline__ void mix1(const uint32_t (&a)[4], const Mix1W& w, const float (&init)[4], int jb, int t, int Nk, float (&L)[2][4]) {
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) {
-        float d[4] = {w.bias[2 * nb], w.bias[2 * nb + 1], w.bias[2 * nb], w.bias[2 * nb + 1]};
-        mma_f16(d, a0, a1, a2, a3, w.b[nb][0], w.b[nb][1]);
+        float d[4] = {init[2 * nb], init[2 * nb + 1], init[2 * nb], init[2 * nb + 1]};
+        mma_f16(d, a[0], a[1], a[2], a[3], w.b[nb][0], w.b[nb][1]);
         L[0][2 * nb] = d[0]; L[0][2 * nb + 1] = d[1];
         L[1][2 * nb] = d[2]; L[1][2 * nb + 1] = d[3];
     }
+    if (MASK) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (jb + 2 * t + r >= Nk) {
+#pragma unroll
+                for (int gs = 0; gs < 4; ++gs) L[r][gs] = T16_NEG;
+            }
+    }
 }
 
-// the 4 head rows of this thread, 8 keys from jb; keys >= Nk come back as 0 (the pitch padding may hold anything)
-template <bool S16>
-__device__ __forceinline__ void load_s_group(const void* __restrict__ S, long long row_off, long long hS, int tig, int jb, int Nk, float (&v)[4][8]) {
-    if (jb < Nk) {
+// ---- forward chunk steps (64 keys per warp: 4 tiles) ----
+template <bool S16, bool MASK>
+__device__ __forceinline__ void fwd_chunk_a(const void* __restrict__ S, long long off, long long hS, int jb, int Nk, const Mix1W& w1, const float (&b1)[4],
+                                            float (&m)[4], float (&z)[4]) {
+    uint32_t r[4][4];
+    load_s<S16, MASK>(S, off, hS, jb, Nk, r);
+    float L[4][2][4];
 #pragma unroll
-        for (int hs = 0; hs < 4; ++hs) {
-            const int h = 2 * tig + (hs & 1) + 8 * (hs >> 1);
-            load8<S16>(S, row_off + h * hS + jb, v[hs]);
+    for (int t = 0; t < 4; ++t) {
+        uint32_t a[4];
+        frag(r, t, a);
+        mix1<MASK>(a, w1, b1, jb, t, Nk, L[t]);
+    }
+#pragma unroll
+    for (int gs = 0; gs < 4; ++gs) {
+        float mx = m[gs];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) mx = fmaxf(mx, fmaxf(L[t][0][gs], L[t][1][gs]));
+        float acc = z[gs] * ex2f(m[gs] - mx);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc += ex2f(L[t][0][gs] - mx) + ex2f(L[t][1][gs] - mx);
+        z[gs] = acc;
+        m[gs] = mx;
+    }
+}
+template <bool S16, bool MASK>
+__device__ __forceinline__ void fwd_chunk_b(const void* __restrict__ S, long long off, long long hS, uint16_t* __restrict__ ap, long long hA, int jb, int Nk,
+                                            int ldA, const Mix1W& w1, const uint32_t (&w2)[2][2], const float (&ci)[4], const float (&b2)[4]) {
+    uint32_t r[4][4], pkt[4][4];
+    load_s<S16, MASK>(S, off, hS, jb, Nk, r);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        uint32_t a[4];
+        frag(r, t, a);
+        float L[2][4];
+        mix1<MASK>(a, w1, ci, jb, t, Nk, L);
+        // P' = 2^4 P = 2^L packed = the A fragment of the output mix (rows = keys, k = mixed heads)
+        const uint32_t p0 = ex2_h2(pk_f16(L[0][0], L[0][1])), p1 = ex2_h2(pk_f16(L[1][0], L[1][1]));
+        const uint32_t p2 = ex2_h2(pk_f16(L[0][2], L[0][3])), p3 = ex2_h2(pk_f16(L[1][2], L[1][3]));
+        const bool v0 = !MASK || jb + 2 * t < Nk, v1 = !MASK || jb + 2 * t + 1 < Nk;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+            float e[4] = {b2[2 * nb], b2[2 * nb + 1], b2[2 * nb], b2[2 * nb + 1]};
+            mma_f16(e, p0, p1, p2, p3, w2[nb][0], w2[nb][1]);
+            pkt[2 * nb][t] = pk_bf16(v0 ? e[0] : 0.f, v1 ? e[2] : 0.f);                    // padding keys stay clean (the PV GEMM reads the pitch)
+            pkt[2 * nb + 1][t] = pk_bf16(v0 ? e[1] : 0.f, v1 ? e[3] : 0.f);
         }
-        if (jb + 8 > Nk) {
+    }
+    if (!MASK || jb < ldA) {
 #pragma unroll
-            for (int hs = 0; hs < 4; ++hs)
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    if (jb + s >= Nk) v[hs][s] = 0.f;
-        }
-    } else {
-#pragma unroll
-        for (int hs = 0; hs < 4; ++hs)
-#pragma unroll
-            for (int s = 0; s < 8; ++s) v[hs][s] = 0.f;
+        for (int os = 0; os < 4; ++os)
+            *reinterpret_cast<uint4*>(ap + (long long)((os & 1) + 8 * (os >> 1)) * hA) = make_uint4(pkt[os][0], pkt[os][1], pkt[os][2], pkt[os][3]);
     }
 }
 
@@ -146,57 +237,34 @@ __global__ void __launch_bounds__(T16_THREADS, 2) th16_fwd_kernel(const void* __
     __shared__ float redm[T16_WARPS][16], redz[T16_WARPS][16], sc2[16];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     Mix1W w1;
-    load_mix1(Wl, bl, gid, tig, w1);
-    uint32_t w2[2][2];                      // 2^-8 Ww as the B operand [k = g, n = o] of the output mix, f16
-    float b2[4];
+    load_mix1(Wl, gid, tig, w1);
+    uint32_t w2[2][2];                      // 2^-4 Ww as the B operand [k = g, n = o] of the output mix, f16
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) {
         const float* r = Ww + (8 * nb + gid) * 16;
-        w2[nb][0] = pk_f16(r[2 * tig] * 0.00390625f, r[2 * tig + 1] * 0.00390625f);
-        w2[nb][1] = pk_f16(r[2 * tig + 8] * 0.00390625f, r[2 * tig + 9] * 0.00390625f);
+        w2[nb][0] = pk_f16(r[2 * tig] * T16_UNSHIFT, r[2 * tig + 1] * T16_UNSHIFT);
+        w2[nb][1] = pk_f16(r[2 * tig + 8] * T16_UNSHIFT, r[2 * tig + 9] * T16_UNSHIFT);
     }
-    b2[0] = bw[2 * tig]; b2[1] = bw[2 * tig + 1]; b2[2] = bw[2 * tig + 8]; b2[3] = bw[2 * tig + 9];
+    const float b1[4] = {bl[2 * tig] * T16_LOG2E, bl[2 * tig + 1] * T16_LOG2E, bl[2 * tig + 8] * T16_LOG2E, bl[2 * tig + 9] * T16_LOG2E};
+    const float b2[4] = {bw[2 * tig], bw[2 * tig + 1], bw[2 * tig + 8], bw[2 * tig + 9]};
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
-    const int nch = (ldA + 63) / 64;
+    const int nch = (ldA + 63) / 64, nfull = Nk / 64;                       // chunks [0, nfull) hold valid keys only: no masks
+    int rb = blockIdx.x / Nq, rq = blockIdx.x % Nq;
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
-        const int b = row / Nq, q = row % Nq;
-        const long long s_off = ((long long)b * 16 * Nq + q) * ldS;
-        uint16_t* Ab = A + ((long long)b * 16 * Nq + q) * ldA;
+        const long long s_off = ((long long)rb * 16 * Nq + rq) * ldS + (long long)(2 * tig) * hS + gid * 8;
+        uint16_t* Ab = A + ((long long)rb * 16 * Nq + rq) * ldA + (long long)(2 * tig) * hA + gid * 8;
         // ---- sweep A: online (max, sum) of the mixed logits, 4 head slots per thread
         float m[4], z[4];
 #pragma unroll
         for (int gs = 0; gs < 4; ++gs) { m[gs] = T16_NEG; z[gs] = 0.f; }
-        for (int c = warp; c < nch; c += T16_WARPS) {
-            const int jb = c * 64 + gid * 8;
-            float v[4][8];
-            load_s_group<S16>(S, s_off, hS, tig, jb, Nk, v);
-            float L[4][2][4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                mix1_tile(v, t, w1, L[t]);
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-                    if (jb + 2 * t + r >= Nk) {
-#pragma unroll
-                        for (int gs = 0; gs < 4; ++gs) L[t][r][gs] = T16_NEG;
-                    }
-            }
-#pragma unroll
-            for (int gs = 0; gs < 4; ++gs) {
-                float mx = m[gs];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) mx = fmaxf(mx, fmaxf(L[t][0][gs], L[t][1][gs]));
-                float acc = z[gs] * ex2f(m[gs] - mx);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) acc += ex2f(L[t][0][gs] - mx) + ex2f(L[t][1][gs] - mx);
-                z[gs] = acc;
-                m[gs] = mx;
-            }
+        {
+            int c = warp;
+            for (; c < nfull; c += T16_WARPS) fwd_chunk_a<S16, false>(S, s_off + c * 64, hS, 0, Nk, w1, b1, m, z);
+            for (; c < nch; c += T16_WARPS) fwd_chunk_a<S16, true>(S, s_off + c * 64, hS, c * 64 + gid * 8, Nk, w1, b1, m, z);
         }
-        // threads that saw no valid key hold (m = NEG, z = junk): they vanish in the merge through 2^(NEG - max) = 0
 #pragma unroll
         for (int gs = 0; gs < 4; ++gs) {
-            if (m[gs] == T16_NEG) z[gs] = 0.f;
+            if (m[gs] == T16_NEG) z[gs] = 0.f;           // no valid key seen: (NEG, junk) must vanish in the merge
 #pragma unroll
             for (int off = 4; off < 32; off <<= 1) {
                 const float mo = __shfl_xor_sync(0xffffffffu, m[gs], off), zo = __shfl_xor_sync(0xffffffffu, z[gs], off);
@@ -213,53 +281,27 @@ __global__ void __launch_bounds__(T16_THREADS, 2) th16_fwd_kernel(const void* __
         __syncthreads();
         if (tid < 16) {
             float M = T16_NEG, Z = 0.f;
+#pragma unroll
             for (int w = 0; w < T16_WARPS; ++w) M = fmaxf(M, redm[w][tid]);
+#pragma unroll
             for (int w = 0; w < T16_WARPS; ++w) Z += redz[w][tid] * ex2f(redm[w][tid] - M);
-            const float c2 = M + log2f(Z);
+            const float c2 = M + __log2f(Z);
             sc2[tid] = c2;
             if (stats) stats[(long long)row * 16 + tid] = c2;
         }
         __syncthreads();
-        // ---- sweep B: P = 2^(L - c2) -> output mix -> bf16 A
-        float c2v[4];
+        // ---- sweep B: the accumulator starts at bias - c2 + 4, so 2^L is 2^4 P
+        float ci[4];
 #pragma unroll
-        for (int gs = 0; gs < 4; ++gs) c2v[gs] = sc2[2 * tig + (gs & 1) + 8 * (gs >> 1)] - 8.f;       // carries 2^8 P
-        for (int c = warp; c < nch; c += T16_WARPS) {
-            const int jb = c * 64 + gid * 8;
-            float v[4][8];
-            load_s_group<S16>(S, s_off, hS, tig, jb, Nk, v);
-            uint32_t pkt[4][4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                float L[2][4];
-                mix1_tile(v, t, w1, L);
-                float P[2][4];
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const bool valid = jb + 2 * t + r < Nk;
-#pragma unroll
-                    for (int gs = 0; gs < 4; ++gs) P[r][gs] = valid ? ex2f(L[r][gs] - c2v[gs]) : 0.f;
-                }
-                const uint32_t a0 = pk_f16(P[0][0], P[0][1]), a1 = pk_f16(P[1][0], P[1][1]);
-                const uint32_t a2 = pk_f16(P[0][2], P[0][3]), a3 = pk_f16(P[1][2], P[1][3]);
-                const bool v0 = jb + 2 * t < Nk, v1 = jb + 2 * t + 1 < Nk;
-#pragma unroll
-                for (int nb = 0; nb < 2; ++nb) {
-                    float e[4] = {b2[2 * nb], b2[2 * nb + 1], b2[2 * nb], b2[2 * nb + 1]};
-                    mma_f16(e, a0, a1, a2, a3, w2[nb][0], w2[nb][1]);
-                    pkt[2 * nb][t] = pk_bf16(v0 ? e[0] : 0.f, v1 ? e[2] : 0.f);            // padding keys stay clean (the PV GEMM reads the pitch)
-                    pkt[2 * nb + 1][t] = pk_bf16(v0 ? e[1] : 0.f, v1 ? e[3] : 0.f);
-                }
-            }
-            if (jb < ldA) {
-#pragma unroll
-                for (int os = 0; os < 4; ++os) {
-                    const int o = 2 * tig + (os & 1) + 8 * (os >> 1);
-                    *reinterpret_cast<uint4*>(Ab + o * hA + jb) = make_uint4(pkt[os][0], pkt[os][1], pkt[os][2], pkt[os][3]);
-                }
-            }
+        for (int gs = 0; gs < 4; ++gs) ci[gs] = b1[gs] - sc2[2 * tig + (gs & 1) + 8 * (gs >> 1)] + T16_SHIFT;
+        {
+            int c = warp;
+            for (; c < nfull; c += T16_WARPS) fwd_chunk_b<S16, false>(S, s_off + c * 64, hS, Ab + c * 64, hA, 0, Nk, ldA, w1, w2, ci, b2);
+            for (; c < nch; c += T16_WARPS) fwd_chunk_b<S16, true>(S, s_off + c * 64, hS, Ab + c * 64, hA, c * 64 + gid * 8, Nk, ldA, w1, w2, ci, b2);
         }
         __syncthreads();                        // sc2 / red* are reused by the next row
+        rq += gridDim.x;
+        while (rq >= Nq) { rq -= Nq; ++rb; }
     }
 }
 
@@ -306,46 +348,76 @@ __device__ __forceinline__ void outer_acc(const uint32_t (&x)[4], const uint32_t
     mma_bf16(acc[1], xa0, xa1, xa2, xa3, y2, y3);
 }
 
-__device__ __forceinline__ void load_da_group(const uint16_t* __restrict__ dAb, long long hA, int tig, int jb, int Nk, uint32_t (&raw)[4][4]) {
-    if (jb < Nk) {
+template <bool S16, bool MASK>
+__device__ __forceinline__ void bwd_chunk_b(const void* __restrict__ S, long long off, long long hS, const uint16_t* dp, long long hA, int jb, int Nk,
+                                            const Mix1W& w1, const float (&ci)[4], const GradW& gww, float (&rho)[4], float (&accWw)[2][4]) {
+    uint32_t r[4][4], rd[4][4];
+    load_s<S16, MASK>(S, off, hS, jb, Nk, r);
+    load_da<MASK>(dp, hA, jb, Nk, rd);
 #pragma unroll
-        for (int os = 0; os < 4; ++os) {
-            const int o = 2 * tig + (os & 1) + 8 * (os >> 1);
-            const uint4 r = *reinterpret_cast<const uint4*>(dAb + o * hA + jb);
-            raw[os][0] = r.x; raw[os][1] = r.y; raw[os][2] = r.z; raw[os][3] = r.w;
-        }
-        if (jb + 8 > Nk) {
+    for (int t = 0; t < 4; ++t) {
+        uint32_t a[4], da[4], pa[4];
+        frag(r, t, a);
+        frag(rd, t, da);
+        float P[2][4], dP[2][4];
+        mix1<MASK>(a, w1, ci, jb, t, Nk, P);
 #pragma unroll
-            for (int os = 0; os < 4; ++os)
+        for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (jb + 2 * t >= Nk) raw[os][t] = 0u;
-                    else if (jb + 2 * t + 1 >= Nk) raw[os][t] &= 0xffffu;
-                }
-        }
-    } else {
+            for (int gs = 0; gs < 4; ++gs) P[rr][gs] = ex2f(P[rr][gs]);
+        grad_mix(da, gww, dP);
 #pragma unroll
-        for (int os = 0; os < 4; ++os)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) raw[os][t] = 0u;
+        for (int gs = 0; gs < 4; ++gs) rho[gs] += P[0][gs] * dP[0][gs] + P[1][gs] * dP[1][gs];
+        pack_a_bf16(P, pa);
+        outer_acc(da, pa, accWw);                                    // [o, g]
     }
 }
-// dA of tile t as the A fragment [rows = keys, k = o]
-__device__ __forceinline__ void da_frag(const uint32_t (&raw)[4][4], int t, uint32_t (&a)[4]) {
-    a[0] = prmt(raw[0][t], raw[1][t], 0x5410u); a[1] = prmt(raw[0][t], raw[1][t], 0x7632u);
-    a[2] = prmt(raw[2][t], raw[3][t], 0x5410u); a[3] = prmt(raw[2][t], raw[3][t], 0x7632u);
+template <bool S16, bool MASK>
+__device__ __forceinline__ void bwd_chunk_c(const void* __restrict__ S, long long off, long long hS, const uint16_t* dp, uint16_t* gp, long long hA, int jb,
+                                            int Nk, int ldA, const Mix1W& w1, const float (&ci)[4], const GradW& gww, const GradW& gwl, const float (&rho)[4],
+                                            float (&accWl)[2][4]) {
+    uint32_t r[4][4], rd[4][4], pkt[4][4];
+    load_s<S16, MASK>(S, off, hS, jb, Nk, r);
+    load_da<MASK>(dp, hA, jb, Nk, rd);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        uint32_t a[4], da[4], la[4], sa[4];
+        frag(r, t, a);
+        frag(rd, t, da);
+        float L[2][4], dP[2][4], dL[2][4], dSv[2][4];
+        mix1<MASK>(a, w1, ci, jb, t, Nk, L);
+        grad_mix(da, gww, dP);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int gs = 0; gs < 4; ++gs) dL[rr][gs] = ex2f(L[rr][gs]) * (dP[rr][gs] - rho[gs]);
+        pack_a_bf16(dL, la);
+        grad_mix(la, gwl, dSv);
+#pragma unroll
+        for (int os = 0; os < 4; ++os) pkt[os][t] = pk_bf16(dSv[0][os], dSv[1][os]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sa[i] = h2_to_bf2(a[i]);
+        outer_acc(la, sa, accWl);                                    // [g, h]
+    }
+    if (!MASK || jb < ldA) {
+#pragma unroll
+        for (int os = 0; os < 4; ++os)
+            *reinterpret_cast<uint4*>(gp + (long long)((os & 1) + 8 * (os >> 1)) * hA) = make_uint4(pkt[os][0], pkt[os][1], pkt[os][2], pkt[os][3]);
+    }
 }
 
 template <bool S16, int NT>
 __global__ void __launch_bounds__(NT, 1) th16_bwd_kernel(const void* __restrict__ S, const uint16_t* dA, uint16_t* dS, const float* __restrict__ Wl,
-                                                                  const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ stats,
-                                                                  int rows_total, int Nq, int Nk, int ldS, int ldA, float* __restrict__ part) {
+                                                         const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ stats,
+                                                         int rows_total, int Nq, int Nk, int ldS, int ldA, float* __restrict__ part) {
+    constexpr int NW = NT / 32;
     constexpr int NP = 2 * 16 * 16 + 2 * 16;
-    __shared__ float redr[(NT / 32)][16], srho[16], sc2[16];
+    __shared__ float redr[NW][16], srho[16], sc2[16];
     __shared__ float spart[NP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     Mix1W w1;
-    load_mix1(Wl, bl, gid, tig, w1);
+    load_mix1(Wl, gid, tig, w1);
+    const float b1[4] = {bl[2 * tig] * T16_LOG2E, bl[2 * tig + 1] * T16_LOG2E, bl[2 * tig + 8] * T16_LOG2E, bl[2 * tig + 9] * T16_LOG2E};
     GradW gww, gwl;
     load_gradw(Ww, gid, tig, gww);          // dP[j, g] = sum_o dA[j, o] Ww[o, g]
     load_gradw(Wl, gid, tig, gwl);          // dS[j, h] = sum_g dL[j, g] Wl[g, h]
@@ -356,42 +428,23 @@ __global__ void __launch_bounds__(NT, 1) th16_bwd_kernel(const void* __restrict_
         for (int i = 0; i < 4; ++i) { accWw[nb][i] = 0.f; accWl[nb][i] = 0.f; }
     for (int i = tid; i < NP; i += NT) spart[i] = 0.f;
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
-    const int nch = (ldA + 63) / 64;
+    const int nch = (ldA + 63) / 64, nfull = Nk / 64;
+    int rb = blockIdx.x / Nq, rq = blockIdx.x % Nq;
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
-        const int b = row / Nq, q = row % Nq;
-        const long long s_off = ((long long)b * 16 * Nq + q) * ldS;
-        const uint16_t* dAb = dA + ((long long)b * 16 * Nq + q) * ldA;
-        uint16_t* dSb = dS + ((long long)b * 16 * Nq + q) * ldA;     // may alias dAb: every thread reads its own (head, key group) cells first
+        const long long s_off = ((long long)rb * 16 * Nq + rq) * ldS + (long long)(2 * tig) * hS + gid * 8;
+        const long long a_off = ((long long)rb * 16 * Nq + rq) * ldA + (long long)(2 * tig) * hA + gid * 8;
+        const uint16_t* dAb = dA + a_off;
+        uint16_t* dSb = dS + a_off;                  // may alias dAb: every thread reads its own (head, key group) cells first
         if (tid < 16) sc2[tid] = stats[(long long)row * 16 + tid];
         __syncthreads();
-        float c2v[4], rho[4];
+        float ci[4], rho[4];
 #pragma unroll
-        for (int gs = 0; gs < 4; ++gs) { c2v[gs] = sc2[2 * tig + (gs & 1) + 8 * (gs >> 1)]; rho[gs] = 0.f; }
+        for (int gs = 0; gs < 4; ++gs) { ci[gs] = b1[gs] - sc2[2 * tig + (gs & 1) + 8 * (gs >> 1)]; rho[gs] = 0.f; }
         // ---- sweep B: rho[g] = sum_j P dP,  dWw += dA^T P
-        for (int c = warp; c < nch; c += (NT / 32)) {
-            const int jb = c * 64 + gid * 8;
-            float v[4][8];
-            uint32_t raw[4][4];
-            load_s_group<S16>(S, s_off, hS, tig, jb, Nk, v);
-            load_da_group(dAb, hA, tig, jb, Nk, raw);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                float L[2][4], P[2][4], dP[2][4];
-                mix1_tile(v, t, w1, L);
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const bool valid = jb + 2 * t + r < Nk;
-#pragma unroll
-                    for (int gs = 0; gs < 4; ++gs) P[r][gs] = valid ? ex2f(L[r][gs] - c2v[gs]) : 0.f;
-                }
-                uint32_t da[4], pa[4];
-                da_frag(raw, t, da);
-                grad_mix(da, gww, dP);
-#pragma unroll
-                for (int gs = 0; gs < 4; ++gs) rho[gs] += P[0][gs] * dP[0][gs] + P[1][gs] * dP[1][gs];
-                pack_a_bf16(P, pa);
-                outer_acc(da, pa, accWw);                                    // [o, g]
-            }
+        {
+            int c = warp;
+            for (; c < nfull; c += NW) bwd_chunk_b<S16, false>(S, s_off + c * 64, hS, dAb + c * 64, hA, 0, Nk, w1, ci, gww, rho, accWw);
+            for (; c < nch; c += NW) bwd_chunk_b<S16, true>(S, s_off + c * 64, hS, dAb + c * 64, hA, c * 64 + gid * 8, Nk, w1, ci, gww, rho, accWw);
         }
 #pragma unroll
         for (int gs = 0; gs < 4; ++gs) {
@@ -402,50 +455,23 @@ __global__ void __launch_bounds__(NT, 1) th16_bwd_kernel(const void* __restrict_
         __syncthreads();
         if (tid < 16) {
             float r = 0.f;
-            for (int w = 0; w < (NT / 32); ++w) r += redr[w][tid];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) r += redr[w][tid];
             srho[tid] = r;
         }
         __syncthreads();
 #pragma unroll
         for (int gs = 0; gs < 4; ++gs) rho[gs] = srho[2 * tig + (gs & 1) + 8 * (gs >> 1)];
         // ---- sweep C: dL = P (dP - rho),  dS = dL Wl (in place over dA),  dWl += dL^T S
-        for (int c = warp; c < nch; c += (NT / 32)) {
-            const int jb = c * 64 + gid * 8;
-            float v[4][8];
-            uint32_t raw[4][4];
-            load_s_group<S16>(S, s_off, hS, tig, jb, Nk, v);
-            load_da_group(dAb, hA, tig, jb, Nk, raw);
-            uint32_t pkt[4][4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                float L[2][4], dP[2][4], dL[2][4], dSv[2][4];
-                mix1_tile(v, t, w1, L);
-                uint32_t da[4], la[4], sa[4];
-                da_frag(raw, t, da);
-                grad_mix(da, gww, dP);
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const bool valid = jb + 2 * t + r < Nk;
-#pragma unroll
-                    for (int gs = 0; gs < 4; ++gs) dL[r][gs] = valid ? ex2f(L[r][gs] - c2v[gs]) * (dP[r][gs] - rho[gs]) : 0.f;
-                }
-                pack_a_bf16(dL, la);
-                grad_mix(la, gwl, dSv);
-#pragma unroll
-                for (int os = 0; os < 4; ++os) pkt[os][t] = pk_bf16(dSv[0][os], dSv[1][os]);
-                sa[0] = pk_bf16(v[0][2 * t], v[1][2 * t]); sa[1] = pk_bf16(v[0][2 * t + 1], v[1][2 * t + 1]);
-                sa[2] = pk_bf16(v[2][2 * t], v[3][2 * t]); sa[3] = pk_bf16(v[2][2 * t + 1], v[3][2 * t + 1]);
-                outer_acc(la, sa, accWl);                                    // [g, h]
-            }
-            if (jb < ldA) {
-#pragma unroll
-                for (int os = 0; os < 4; ++os) {
-                    const int h = 2 * tig + (os & 1) + 8 * (os >> 1);
-                    *reinterpret_cast<uint4*>(dSb + h * hA + jb) = make_uint4(pkt[os][0], pkt[os][1], pkt[os][2], pkt[os][3]);
-                }
-            }
+        {
+            int c = warp;
+            for (; c < nfull; c += NW) bwd_chunk_c<S16, false>(S, s_off + c * 64, hS, dAb + c * 64, dSb + c * 64, hA, 0, Nk, ldA, w1, ci, gww, gwl, rho, accWl);
+            for (; c < nch; c += NW)
+                bwd_chunk_c<S16, true>(S, s_off + c * 64, hS, dAb + c * 64, dSb + c * 64, hA, c * 64 + gid * 8, Nk, ldA, w1, ci, gww, gwl, rho, accWl);
         }
         __syncthreads();                        // sc2 / srho / redr are reused by the next row
+        rq += gridDim.x;
+        while (rq >= Nq) { rq -= Nq; ++rb; }
     }
     // per-CTA partials in the layout talking_bwd_finalize_kernel reduces: [dWl (g, h) | dbl = 0 | dWw (o, g) | dbw = 0]
 #pragma unroll

@@ -92,6 +92,10 @@ __device__ __forceinline__ void t8_bulk_g2s(uint32_t dst, const void* src, uint3
 // head pairs 2 pitches apart) fall into 16 distinct 8-byte bank pairs
 __host__ __device__ __forceinline__ int t8_pitch(int ld) { return ld + ((40 - ld % 32) % 32); }
 
+#ifndef T8_UNROLL
+#define T8_UNROLL 2
+#endif
+constexpr int T8_UNROLL_N = T8_UNROLL;      // full-step loops: independent chains of consecutive steps interleave
 constexpr int T8_CH = 32;       // keys per warp step: 2 MMA tiles; a thread owns 4 consecutive keys of heads 2 tig, 2 tig + 1
 
 // the 4 keys [jb, jb + 4) of heads 2 tig and 2 tig + 1 from a staged row (sp = this thread's position in the row of head 2 tig), as
@@ -223,6 +227,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 5 ? 4 : NW <= 8 ? 3 : 2) th8_fw
         {
             const uint16_t* sp = sp0;
             int st = s0;
+#pragma unroll T8_UNROLL_N
             for (; st < sf; ++st, sp += T8_CH) fwd_step_a<false>(sp, pS, 0, Nk, w1, b1, m, z);
             for (; st < s1; ++st, sp += T8_CH) fwd_step_a<true>(sp, pS, st * T8_CH + gid * 4, Nk, w1, b1, m, z);
         }
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 5 ? 4 : NW <= 8 ? 3 : 2) th8_fw
             const uint16_t* sp = sp0;
             uint16_t* ap = ap0;
             int st = s0;
+#pragma unroll T8_UNROLL_N
             for (; st < sf; ++st, sp += T8_CH, ap += T8_CH) fwd_step_b<false>(sp, pS, ap, hA, 0, Nk, ldA, w1, w2, ci, b2);
             for (; st < s1; ++st, sp += T8_CH, ap += T8_CH) fwd_step_b<true>(sp, pS, ap, hA, st * T8_CH + gid * 4, Nk, ldA, w1, w2, ci, b2);
         }
@@ -406,6 +412,7 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __r
         {
             const uint16_t *sp = sp0, *dp = dp0;
             int st = s0;
+#pragma unroll T8_UNROLL_N
             for (; st < sf; ++st, sp += T8_CH, dp += T8_CH) bwd_step_b<false>(sp, pS, dp, pA, 0, Nk, w1, ci, gww, rho, accWw);
             for (; st < s1; ++st, sp += T8_CH, dp += T8_CH) bwd_step_b<true>(sp, pS, dp, pA, st * T8_CH + gid * 4, Nk, w1, ci, gww, rho, accWw);
         }
@@ -430,6 +437,7 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __r
             const uint16_t *sp = sp0, *dp = dp0;
             uint16_t* gp = gp0;
             int st = s0;
+#pragma unroll T8_UNROLL_N
             for (; st < sf; ++st, sp += T8_CH, dp += T8_CH, gp += T8_CH) bwd_step_c<false>(sp, pS, dp, pA, gp, hA, 0, Nk, ldA, w1, ci, gww, gwl, rho, accWl);
             for (; st < s1; ++st, sp += T8_CH, dp += T8_CH, gp += T8_CH)
                 bwd_step_c<true>(sp, pS, dp, pA, gp, hA, st * T8_CH + gid * 4, Nk, ldA, w1, ci, gww, gwl, rho, accWl);
