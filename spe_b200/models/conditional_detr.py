@@ -219,14 +219,15 @@ class PostProcess(nn.Module):
     """conditional_detr.py:592-623 (eval-time top-k box decoding; host-side torch, not on the training path)."""
 
     @torch.no_grad()
-    def forward(self, outputs, target_sizes):
+    def forward(self, outputs, target_sizes, keep_queries=100):
         out_logits, out_bbox = outputs["pred_logits"], outputs["pred_boxes"]
+        assert len(out_logits) == len(target_sizes) and target_sizes.shape[1] == 2
         prob = out_logits.sigmoid()
-        k = min(100, prob.shape[1] * prob.shape[2])
+        k = min(keep_queries, prob.shape[1] * prob.shape[2])
         topk_values, topk_indexes = torch.topk(prob.view(out_logits.shape[0], -1), k, dim=1)
         topk_boxes = topk_indexes // out_logits.shape[2]
         labels = topk_indexes % out_logits.shape[2]
-        boxes = box_ops.box_cxcywh_to_xyxy(out_bbox)
+        boxes = box_ops.box_cxcywh_to_xyxy(out_bbox).clamp(min=0)            # :611 clamps the corners at 0
         boxes = torch.gather(boxes, 1, topk_boxes.unsqueeze(-1).repeat(1, 1, 4))
         img_h, img_w = target_sizes.unbind(1)
         boxes = boxes * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :]

@@ -54,7 +54,7 @@ def cam_boxes_multi(cams_cls, pairs, image_size, cam_thr=0.2, area_ratio=0.5, ma
 
 
 @torch.no_grad()
-def get_pseudo_label_multi_boxes(outputs, samples, targets, args=None, cam_thr=None, area_ratio=None, max_boxes=16):
+def get_pseudo_label_multi_boxes(outputs, samples, targets, args=None, cam_thr=None, area_ratio=None, max_boxes=16, label_key="img_label"):
     """Same call as the reference's engine.get_pseudo_label_multi_boxes (engine.py:356-398), the variant its refine training loops use:
     per image {'boxes': cxcywh normalised [k,4], 'labels': class + 1 [k]} with every contour above args.multi_box_ratio of the largest.
     One D2H read of the per-pair box counts (the result is ragged); maps and boxes stay on the device."""
@@ -64,7 +64,7 @@ def get_pseudo_label_multi_boxes(outputs, samples, targets, args=None, cam_thr=N
     thr = cam_thr if cam_thr is not None else float(getattr(args, "cam_thr", 0.2))
     ratio = area_ratio if area_ratio is not None else float(getattr(args, "multi_box_ratio", 0.5))
     ncls = int(getattr(args, "num_classes", cams.shape[1])) if args is not None else cams.shape[1]
-    labels = torch.stack([t["img_label"].reshape(-1)[:ncls] for t in targets]).cpu()
+    labels = torch.stack([torch.as_tensor(t[label_key]).reshape(-1)[:ncls] for t in targets]).cpu()
     pairs = torch.nonzero(labels > 0)
     boxes, counts = cam_boxes_multi(cams, pairs, (H, W), thr, ratio, max_boxes)
     cnt = counts.cpu()
@@ -77,6 +77,13 @@ def get_pseudo_label_multi_boxes(outputs, samples, targets, args=None, cam_thr=N
         out.append({"boxes": flat[o:o + n], "labels": cls[o:o + n]})
         o += n
     return out
+
+
+@torch.no_grad()
+def get_pseudo_label_multi_boxes_voc(outputs, samples, targets, args=None, cam_thr=None, max_boxes=16):
+    """engine.get_pseudo_label_multi_boxes_voc (engine.py:402-442): present classes from targets[b]['label'], get_multi_bboxes with its
+    default area ratio 0.5."""
+    return get_pseudo_label_multi_boxes(outputs, samples, targets, args, cam_thr=cam_thr, area_ratio=0.5, max_boxes=max_boxes, label_key="label")
 
 
 @torch.no_grad()

@@ -45,3 +45,23 @@ def test_postprocess_refine_matches_reference_loops():
         exp = ref(logits, boxes, targets)
         for a, b in zip(got, exp):
             assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["scores"], b["scores"]) and torch.equal(a["boxes"], b["boxes"])
+
+
+def test_postprocess_classes_match_the_reference_classes():
+    """PostProcess against the reference's own class (models/conditional_detr.py:592-623),
+    imported through oracle/ref_shim.py -- skipped where neither /root/reference nor the staged copy baseline/_ref exists."""
+    import pytest
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    from spe_b200.models.conditional_detr import PostProcess
+    ref = ref_shim.load_reference().conditional_detr
+    g = torch.Generator().manual_seed(4)
+    B, Q, C = 3, 120, 21
+    logits, boxes = torch.randn(B, Q, C, generator=g), torch.rand(B, Q, 4, generator=g) * 0.5 + 0.1
+    out = {"pred_logits": logits, "pred_boxes": boxes}
+    sizes = torch.tensor([[480., 640.], [333., 500.], [800., 1333.]])
+    targets = [{"labels": torch.tensor([3, 7, 7, 20])}, {"labels": torch.tensor([1])}, {"labels": torch.tensor([5, 2, 19, 0])}]
+    for a, b in zip(PostProcess()(out, sizes), ref.PostProcess()(out, sizes)):
+        assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["scores"], b["scores"]) and torch.equal(a["boxes"], b["boxes"])
+    # PostProcessRefine / PostProcessRefineMulti of the reference call .get_device(): CUDA only -> tests/test_postprocess_gpu.py
