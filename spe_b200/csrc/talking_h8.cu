@@ -175,7 +175,7 @@ __device__ __forceinline__ void fwd_step_b(const uint16_t* __restrict__ sp, int 
 // ------------------------------------------------------------------------------------------------------------------------
 // forward.  dynamic shared memory: [NBUF][8][pS] f16 row buffers
 template <int NW, int NBUF>
-__global__ void __launch_bounds__(NW * 32, NW <= 5 ? 4 : NW <= 8 ? 3 : 2) th8_fwd_kernel(const uint16_t* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
+__global__ void __launch_bounds__(NW * 32, NW <= 5 ? 4 : NW <= 10 ? 3 : 2) th8_fwd_kernel(const uint16_t* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
                                                             const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
                                                             float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
     extern __shared__ __align__(128) uint8_t t8sm[];
