@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
 timeout 1500 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/step_once.py > gpurun_out/launchlist.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:"attn_fwd_kernel|attn_bwd|gemm_tcgen05|talking_fwd|talking_bwd_rows|layernorm" -s 17 -c 19 -o gpurun_out/prof_hot -f python tools/prof_attn.py 2 > gpurun_out/ncu_hot.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:"attn_fwd_kernel|attn_bwd|gemm_tcgen05|talking_fwd|talking_bwd_rows|th8_fwd|th8_bwd|layernorm" -s 17 -c 19 -o gpurun_out/prof_hot -f python tools/prof_attn.py 2 > gpurun_out/ncu_hot.log 2>&1
 ncu -i gpurun_out/prof_hot.ncu-rep --page raw --csv > gpurun_out/prof_hot_raw.csv 2>/dev/null
 rm -f gpurun_out/prof_hot.ncu-rep
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_fwd_kernel" -s 2 -c 1 -o gpurun_out/prof_attn_fused -f python tools/prof_attn.py 2 > gpurun_out/ncu_attn_fused.log 2>&1
