@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 5 ? 4 : NW <= 10 ? 3 : 2) th8_f
     extern __shared__ __align__(128) uint8_t t8sm[];
     uint16_t* Sbuf = reinterpret_cast<uint16_t*>(t8sm);
     __shared__ __align__(8) uint64_t bars[NBUF];
-    __shared__ float redm[NW][8], redz[NW][8], sc2[8];
+    __shared__ float redm[2][NW][8], redz[2][NW][8], sc2[2][8];      // double buffered over rows
     const int pS = t8_pitch(ldS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     // B operands: logit mix [k = h, n = g] = Wl[g][h] log2e;  output mix [k = g, n = o] = Ww[o][g] 2^-4
@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 5 ? 4 : NW <= 10 ? 3 : 2) th8_f
         if (tid == 0 && row + (long long)(NBUF - 1) * gridDim.x < rows_total)
             issue(row + (NBUF - 1) * gridDim.x, (it + NBUF - 1) % NBUF);       // that buffer was released by the previous iteration's last barrier
         t8_mbar_wait(bar0 + 8 * buf, (uint32_t)(it / NBUF) & 1u);
+        const int par = it & 1;
         const uint16_t* sp0 = Sbuf + (size_t)buf * 8 * pS + toff;
         uint16_t* ap0 = A + ((long long)rb * 8 * Nq + rq) * ldA + (long long)(2 * tig) * hA + s0 * T8_CH + gid * 4;
         // ---- sweep A
@@ -241,22 +242,22 @@ __global__ void __launch_bounds__(NW * 32, NW <= 5 ? 4 : NW <= 10 ? 3 : 2) th8_f
                 z[gs] = z[gs] * ex2f(m[gs] - mx) + zo * ex2f(mo - mx);
                 m[gs] = mx;
             }
-            if (gid == 0) { redm[warp][2 * tig + gs] = m[gs]; redz[warp][2 * tig + gs] = z[gs]; }
+            if (gid == 0) { redm[par][warp][2 * tig + gs] = m[gs]; redz[par][warp][2 * tig + gs] = z[gs]; }
         }
         __syncthreads();
-        if (tid < 8) {
-            float M = T8_NEG, Z = 0.f;
+        if (tid < 8) {                                   // (merging in every thread instead saves this barrier pair in the backward, but costs
+            float M = T8_NEG, Z = 0.f;                   //  16 more MUFU per thread here and the forward is MUFU bound: 0.152 -> 0.162 ms)
 #pragma unroll
-            for (int w = 0; w < NW; ++w) M = fmaxf(M, redm[w][tid]);
+            for (int w = 0; w < NW; ++w) M = fmaxf(M, redm[par][w][tid]);
 #pragma unroll
-            for (int w = 0; w < NW; ++w) Z += redz[w][tid] * ex2f(redm[w][tid] - M);
+            for (int w = 0; w < NW; ++w) Z += redz[par][w][tid] * ex2f(redm[par][w][tid] - M);
             const float c2 = M + __log2f(Z);
-            sc2[tid] = c2;
+            sc2[par][tid] = c2;
             if (stats) stats[(long long)row * 8 + tid] = c2;
         }
         __syncthreads();
+        const float ci[2] = {b1[0] - sc2[par][2 * tig] + T8_SHIFT, b1[1] - sc2[par][2 * tig + 1] + T8_SHIFT};
         // ---- sweep B
-        const float ci[2] = {b1[0] - sc2[2 * tig] + T8_SHIFT, b1[1] - sc2[2 * tig + 1] + T8_SHIFT};
         {
             const uint16_t* sp = sp0;
             uint16_t* ap = ap0;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 5 ? 4 : NW <= 10 ? 3 : 2) th8_f
             for (; st < sf; ++st, sp += T8_CH, ap += T8_CH) fwd_step_b<false>(sp, pS, ap, hA, 0, Nk, ldA, w1, w2, ci, b2);
             for (; st < s1; ++st, sp += T8_CH, ap += T8_CH) fwd_step_b<true>(sp, pS, ap, hA, st * T8_CH + gid * 4, Nk, ldA, w1, w2, ci, b2);
         }
-        __syncthreads();                                 // the row buffer, sc2 and red* are free again
+        __syncthreads();                                 // the row buffer is free again (red* are double buffered)
         rq += gridDim.x;
         while (rq >= Nq) { rq -= Nq; ++rb; }
     }
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __r
     uint16_t* Sbuf = reinterpret_cast<uint16_t*>(t8sm);
     uint16_t* Dbuf = Sbuf + (size_t)2 * 8 * pS;
     __shared__ __align__(8) uint64_t bars[2];
-    __shared__ float redr[NW][8], srho[8], sc2[8], spart[NP];
+    __shared__ float redr[2][NW][8], spart[NP];           // redr double buffered over rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     const uint32_t w1 = pk_f16(Wl[gid * 8 + 2 * tig] * T8_LOG2E, Wl[gid * 8 + 2 * tig + 1] * T8_LOG2E);
     const float b1[2] = {bl[2 * tig] * T8_LOG2E, bl[2 * tig + 1] * T8_LOG2E};
@@ -399,14 +400,14 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __r
     for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++it) {
         const int buf = it & 1;
         if (tid == 0 && row + (int)gridDim.x < rows_total) issue(row + gridDim.x, buf ^ 1);
-        if (tid < 8) sc2[tid] = stats[(long long)row * 8 + tid];
+        const float c2a = __ldg(stats + (long long)row * 8 + 2 * tig), c2b = __ldg(stats + (long long)row * 8 + 2 * tig + 1);
         t8_mbar_wait(bar0 + 8 * buf, (uint32_t)(it >> 1) & 1u);
-        __syncthreads();
+        const int par = it & 1;
         const uint16_t* sp0 = Sbuf + (size_t)buf * 8 * pS + toffS;
         const uint16_t* dp0 = Dbuf + (size_t)buf * 8 * pA + toffA;
         // dS may alias this row of dA: it is staged in shared memory by now
         uint16_t* gp0 = dS + ((long long)rb * 8 * Nq + rq) * ldA + (long long)(2 * tig) * hA + s0 * T8_CH + gid * 4;
-        const float ci[2] = {b1[0] - sc2[2 * tig], b1[1] - sc2[2 * tig + 1]};
+        const float ci[2] = {b1[0] - c2a, b1[1] - c2b};
         float rho[2] = {0.f, 0.f};
         // ---- sweep B
         {
@@ -420,18 +421,16 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __r
         for (int gs = 0; gs < 2; ++gs) {
 #pragma unroll
             for (int off = 4; off < 32; off <<= 1) rho[gs] += __shfl_xor_sync(0xffffffffu, rho[gs], off);
-            if (gid == 0) redr[warp][2 * tig + gs] = rho[gs];
+            if (gid == 0) redr[par][warp][2 * tig + gs] = rho[gs];
         }
         __syncthreads();
-        if (tid < 8) {
+#pragma unroll
+        for (int gs = 0; gs < 2; ++gs) {                 // every thread sums the per-warp partials of its own two heads
             float x = 0.f;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) x += redr[w][tid];
-            srho[tid] = x;
+            for (int w = 0; w < NW; ++w) x += redr[par][w][2 * tig + gs];
+            rho[gs] = x;
         }
-        __syncthreads();
-        rho[0] = srho[2 * tig];
-        rho[1] = srho[2 * tig + 1];
         // ---- sweep C
         {
             const uint16_t *sp = sp0, *dp = dp0;
@@ -442,7 +441,7 @@ __global__ void __launch_bounds__(NW * 32, 2) th8_bwd_kernel(const uint16_t* __r
             for (; st < s1; ++st, sp += T8_CH, dp += T8_CH, gp += T8_CH)
                 bwd_step_c<true>(sp, pS, dp, pA, gp, hA, st * T8_CH + gid * 4, Nk, ldA, w1, ci, gww, gwl, rho, accWl);
         }
-        __syncthreads();                                 // the row buffers, sc2, srho, redr are free again
+        __syncthreads();                                 // the row buffers are free again
         rq += gridDim.x;
         while (rq >= Nq) { rq -= Nq; ++rb; }
     }

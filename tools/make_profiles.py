@@ -117,6 +117,10 @@ def main():
     raw2 = os.path.join(OUT, "prof_fused_raw.csv")
     if os.path.exists(raw2) and os.path.getsize(raw2) > 100:
         table(raw2, fused_md, last_only=True)
+    th8_md = []
+    raw3 = os.path.join(OUT, "prof_th8_raw.csv")
+    if os.path.exists(raw3) and os.path.getsize(raw3) > 100:
+        table(raw3, th8_md, last_only=True)
     with open(os.path.join(PROF, TAG + "_ncu_hot_kernels.md"), "w") as f:
         f.write("# %s -- ncu `--set full --clock-control none` on the hot kernels (tools/prof_attn.py: encoder self-attention + conditional\n"
                 "# cross-attention fwd (fused) + bwd, one talking-heads attention fwd+bwd, one LayerScale FFN fwd+bwd, cfg2 shapes B=8, N=1600, D=384, H=8).\n"
@@ -126,6 +130,9 @@ def main():
             f.write("\n## kernels added in round 2 (tools/prof_fused.py): fused talking-heads forward / recomputing backward (csrc/talking_fused.cu, cfg2 shape\n"
                     "## B=8, H=8, N=1600, dh=48) and the H=16 mix/softmax/mix kernels (csrc/talking_h16.cu, cfg4 shape B=1, N=4150, fp16 logits); last launch of each\n\n")
             f.write("\n".join(fused_md) + "\n")
+        if th8_md:
+            f.write("\n## the H = 8 mix / softmax / mix kernels of the training step (csrc/talking_h8.cu; captured after the table at the top, which still\n"
+                    "## shows the rowwise.cu kernels they replaced)\n\n" + "\n".join(th8_md) + "\n")
         rep = os.path.join(OUT, "prof_attn_fused.ncu-rep")
         if os.path.exists(rep):
             try:
