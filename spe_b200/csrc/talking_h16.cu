@@ -234,7 +234,7 @@ template <bool S16>
 __global__ void __launch_bounds__(T16_THREADS, 2) th16_fwd_kernel(const void* __restrict__ S, uint16_t* __restrict__ A, const float* __restrict__ Wl,
                                                                   const float* __restrict__ bl, const float* __restrict__ Ww, const float* __restrict__ bw,
                                                                   float* __restrict__ stats, int rows_total, int Nq, int Nk, int ldS, int ldA) {
-    __shared__ float redm[T16_WARPS][16], redz[T16_WARPS][16], sc2[16];
+    __shared__ float redm[2][T16_WARPS][16], redz[2][T16_WARPS][16], sc2[2][16];      // double buffered over rows: no end-of-row barrier
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     Mix1W w1;
     load_mix1(Wl, gid, tig, w1);
@@ -250,7 +250,9 @@ __global__ void __launch_bounds__(T16_THREADS, 2) th16_fwd_kernel(const void* __
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
     const int nch = (ldA + 63) / 64, nfull = Nk / 64;                       // chunks [0, nfull) hold valid keys only: no masks
     int rb = blockIdx.x / Nq, rq = blockIdx.x % Nq;
-    for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
+    int rowit = 0;
+    for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++rowit) {
+        const int par = rowit & 1;
         const long long s_off = ((long long)rb * 16 * Nq + rq) * ldS + (long long)(2 * tig) * hS + gid * 8;
         uint16_t* Ab = A + ((long long)rb * 16 * Nq + rq) * ldA + (long long)(2 * tig) * hA + gid * 8;
         // ---- sweep A: online (max, sum) of the mixed logits, 4 head slots per thread
@@ -274,32 +276,31 @@ __global__ void __launch_bounds__(T16_THREADS, 2) th16_fwd_kernel(const void* __
             }
             if (gid == 0) {
                 const int g = 2 * tig + (gs & 1) + 8 * (gs >> 1);
-                redm[warp][g] = m[gs];
-                redz[warp][g] = z[gs];
+                redm[par][warp][g] = m[gs];
+                redz[par][warp][g] = z[gs];
             }
         }
         __syncthreads();
         if (tid < 16) {
             float M = T16_NEG, Z = 0.f;
 #pragma unroll
-            for (int w = 0; w < T16_WARPS; ++w) M = fmaxf(M, redm[w][tid]);
+            for (int w = 0; w < T16_WARPS; ++w) M = fmaxf(M, redm[par][w][tid]);
 #pragma unroll
-            for (int w = 0; w < T16_WARPS; ++w) Z += redz[w][tid] * ex2f(redm[w][tid] - M);
+            for (int w = 0; w < T16_WARPS; ++w) Z += redz[par][w][tid] * ex2f(redm[par][w][tid] - M);
             const float c2 = M + __log2f(Z);
-            sc2[tid] = c2;
+            sc2[par][tid] = c2;
             if (stats) stats[(long long)row * 16 + tid] = c2;
         }
         __syncthreads();
         // ---- sweep B: the accumulator starts at bias - c2 + 4, so 2^L is 2^4 P
         float ci[4];
 #pragma unroll
-        for (int gs = 0; gs < 4; ++gs) ci[gs] = b1[gs] - sc2[2 * tig + (gs & 1) + 8 * (gs >> 1)] + T16_SHIFT;
+        for (int gs = 0; gs < 4; ++gs) ci[gs] = b1[gs] - sc2[par][2 * tig + (gs & 1) + 8 * (gs >> 1)] + T16_SHIFT;
         {
             int c = warp;
             for (; c < nfull; c += T16_WARPS) fwd_chunk_b<S16, false>(S, s_off + c * 64, hS, Ab + c * 64, hA, 0, Nk, ldA, w1, w2, ci, b2);
             for (; c < nch; c += T16_WARPS) fwd_chunk_b<S16, true>(S, s_off + c * 64, hS, Ab + c * 64, hA, c * 64 + gid * 8, Nk, ldA, w1, w2, ci, b2);
         }
-        __syncthreads();                        // sc2 / red* are reused by the next row
         rq += gridDim.x;
         while (rq >= Nq) { rq -= Nq; ++rb; }
     }
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(NT, 1) th16_bwd_kernel(const void* __restrict_
                                                          int rows_total, int Nq, int Nk, int ldS, int ldA, float* __restrict__ part) {
     constexpr int NW = NT / 32;
     constexpr int NP = 2 * 16 * 16 + 2 * 16;
-    __shared__ float redr[NW][16], srho[16], sc2[16];
+    __shared__ float redr[2][NW][16];               // double buffered over rows
     __shared__ float spart[NP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     Mix1W w1;
@@ -430,16 +431,16 @@ __global__ void __launch_bounds__(NT, 1) th16_bwd_kernel(const void* __restrict_
     const long long hS = (long long)Nq * ldS, hA = (long long)Nq * ldA;
     const int nch = (ldA + 63) / 64, nfull = Nk / 64;
     int rb = blockIdx.x / Nq, rq = blockIdx.x % Nq;
-    for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
+    int rowit = 0;
+    for (int row = blockIdx.x; row < rows_total; row += gridDim.x, ++rowit) {
         const long long s_off = ((long long)rb * 16 * Nq + rq) * ldS + (long long)(2 * tig) * hS + gid * 8;
         const long long a_off = ((long long)rb * 16 * Nq + rq) * ldA + (long long)(2 * tig) * hA + gid * 8;
         const uint16_t* dAb = dA + a_off;
         uint16_t* dSb = dS + a_off;                  // may alias dAb: every thread reads its own (head, key group) cells first
-        if (tid < 16) sc2[tid] = stats[(long long)row * 16 + tid];
-        __syncthreads();
         float ci[4], rho[4];
 #pragma unroll
-        for (int gs = 0; gs < 4; ++gs) { ci[gs] = b1[gs] - sc2[2 * tig + (gs & 1) + 8 * (gs >> 1)]; rho[gs] = 0.f; }
+        for (int gs = 0; gs < 4; ++gs) { ci[gs] = b1[gs] - __ldg(stats + (long long)row * 16 + 2 * tig + (gs & 1) + 8 * (gs >> 1)); rho[gs] = 0.f; }
+        const int par = rowit & 1;
         // ---- sweep B: rho[g] = sum_j P dP,  dWw += dA^T P
         {
             int c = warp;
@@ -450,18 +451,16 @@ __global__ void __launch_bounds__(NT, 1) th16_bwd_kernel(const void* __restrict_
         for (int gs = 0; gs < 4; ++gs) {
 #pragma unroll
             for (int off = 4; off < 32; off <<= 1) rho[gs] += __shfl_xor_sync(0xffffffffu, rho[gs], off);
-            if (gid == 0) redr[warp][2 * tig + (gs & 1) + 8 * (gs >> 1)] = rho[gs];
+            if (gid == 0) redr[par][warp][2 * tig + (gs & 1) + 8 * (gs >> 1)] = rho[gs];
         }
         __syncthreads();
-        if (tid < 16) {
+#pragma unroll
+        for (int gs = 0; gs < 4; ++gs) {             // every thread sums the per-warp partials of its own four heads (two barriers per row, not four)
             float r = 0.f;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) r += redr[w][tid];
-            srho[tid] = r;
+            for (int w = 0; w < NW; ++w) r += redr[par][w][2 * tig + (gs & 1) + 8 * (gs >> 1)];
+            rho[gs] = r;
         }
-        __syncthreads();
-#pragma unroll
-        for (int gs = 0; gs < 4; ++gs) rho[gs] = srho[2 * tig + (gs & 1) + 8 * (gs >> 1)];
         // ---- sweep C: dL = P (dP - rho),  dS = dL Wl (in place over dA),  dWl += dL^T S
         {
             int c = warp;
@@ -469,7 +468,7 @@ __global__ void __launch_bounds__(NT, 1) th16_bwd_kernel(const void* __restrict_
             for (; c < nch; c += NW)
                 bwd_chunk_c<S16, true>(S, s_off + c * 64, hS, dAb + c * 64, dSb + c * 64, hA, c * 64 + gid * 8, Nk, ldA, w1, ci, gww, gwl, rho, accWl);
         }
-        __syncthreads();                        // sc2 / srho / redr are reused by the next row
+        // no end-of-row barrier: redr is double buffered and the mid-row barrier keeps the warps within one row of each other
         rq += gridDim.x;
         while (rq >= Nq) { rq -= Nq; ++rb; }
     }
