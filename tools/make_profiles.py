@@ -144,7 +144,7 @@ def main():
     for src, dst in (("bench_default.json", TAG + "_bench_n1.json"), ("bench_reference.json", TAG + "_bench_reference_cpu.json"),
                      ("bench_cfg4.json", TAG + "_bench_cfg4_n1.json"), ("bench_n2_ov1.json", TAG + "_bench_n2.json"),
                      ("bench_n2_ov0.json", TAG + "_bench_n2_single_allreduce.json"), ("bench_n4_ov1.json", TAG + "_bench_n4.json"),
-                     ("bench_n4_ov0.json", TAG + "_bench_n4_single_allreduce.json")):
+                     ("bench_n4_ov0.json", TAG + "_bench_n4_single_allreduce.json"), ("bench_n8.json", TAG + "_bench_n8.json")):
         p = os.path.join(OUT, src)
         if os.path.exists(p) and os.path.getsize(p) > 10:
             shutil.copy(p, os.path.join(PROF, dst))
@@ -177,6 +177,7 @@ def write_readme(traffic, tot, n):
         f.write("| `%s_bench_cfg4_n1.json` | BASELINE configs[3] (TSCAM-M36, 800x1333, bs 1) | `python bench.py --config cfg4 --steps 5 --warmup 3` |\n" % TAG)
         f.write("| `%s_bench_n2.json`, `%s_bench_n2_single_allreduce.json` | N=2 data parallel: bucketed all-reduce overlapped with the backbone backward (default) vs one all-reduce after the step (`SPE_AR_OVERLAP=0`) | `torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 10` |\n" % (TAG, TAG))
         f.write("| `%s_bench_n4.json`, `%s_bench_n4_single_allreduce.json` | the same at N=4 | `torchrun --nproc-per-node 4 bench.py --gpus 4 --steps 20 --warmup 5` |\n" % (TAG, TAG))
+        f.write("| `%s_bench_n8.json` | N=8 (default bucketed all-reduce) | `torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 10 --warmup 3` |\n" % TAG)
         f.write("| `%s_sass_opcodes.md` | static SASS census per kernel: UTCHMMA / LDTM / UTMALDG / HMMA / MOVM counts, spills | `python tools/sass_summary.py` |\n" % TAG)
         f.write("| `r01_*` | round-1 evidence (kept for comparison) | |\n\n")
         if b:
