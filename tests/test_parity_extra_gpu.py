@@ -257,3 +257,29 @@ def test_flat_grad_buffer_survives_zero_grad_set_to_none():
     backward()
     out = buf.all_reduce_mean()
     torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-6)
+
+
+def test_train_step_prefetch_matches_plain_call():
+    """TrainStep.prefetch stages the next pinned host batch on a copy stream; the step that consumes it sees the same images."""
+    from spe_b200 import factory
+    from spe_b200.engine import TrainStep
+    cfg = O.tiny_config()
+    dev = torch.device("cuda")
+    model = factory.build_detector(cfg, dev).train()
+    model.load_state_dict(O.make_params(cfg, 29))
+    crit = factory.build_criterion(cfg, device=dev).eval()
+    images, targets = O.make_inputs(cfg, 2, 48, 64, seed=29, max_gt=3)
+    other, _ = O.make_inputs(cfg, 2, 48, 64, seed=30, max_gt=3)
+    host_a, host_b = images.pin_memory(), other.pin_memory()
+    step = TrainStep(model, crit, None, graph=True, max_gt=8)
+    la = float(step(host_a, targets)[0])
+    lb = float(step(host_b, targets)[0])
+    assert abs(la - lb) > 1e-4                       # different images, different loss
+    step.prefetch(host_a)
+    la2 = float(step(host_a, targets)[0])            # staged copy
+    step.prefetch(host_b)
+    lb2 = float(step(host_b, targets)[0])
+    step.prefetch(host_a)
+    lb3 = float(step(host_b, targets)[0])            # a prefetch for another tensor is ignored
+    assert step._prefetch_hits == 2
+    assert abs(la2 - la) <= 1e-3 * abs(la) and abs(lb2 - lb) <= 1e-3 * abs(lb) and abs(lb3 - lb) <= 1e-3 * abs(lb), (la, la2, lb, lb2, lb3)
