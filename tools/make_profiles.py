@@ -179,6 +179,7 @@ def write_readme(traffic, tot, n):
         f.write("| `%s_bench_n4.json`, `%s_bench_n4_single_allreduce.json` | the same at N=4 | `torchrun --nproc-per-node 4 bench.py --gpus 4 --steps 20 --warmup 5` |\n" % (TAG, TAG))
         f.write("| `%s_bench_n8.json` | N=8 (default bucketed all-reduce) | `torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 10 --warmup 3` |\n" % TAG)
         f.write("| `%s_sass_opcodes.md` | static SASS census per kernel: UTCHMMA / LDTM / UTMALDG / HMMA / MOVM counts, spills | `python tools/sass_summary.py` |\n" % TAG)
+        f.write("| `%s_ncu_qk_gemm.md` | `ncu --set full` of one K = 48 batched QK^T GEMM launch: metrics + stall reasons (DESIGN section 8 item 1) | `ncu --set full --import-source on -k regex:gemm_tcgen05 -s 2 -c 1 python tools/dev/qk_once.py` |\n" % TAG)
         f.write("| `r01_*` | round-1 evidence (kept for comparison) | |\n\n")
         if b:
             f.write("## bench line (CUDA events, not under a profiler)\n\n")
